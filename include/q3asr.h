@@ -1,0 +1,179 @@
+/*
+ * q3asr.h — C ABI of libq3asr.so, the B200-native (sm_100a) implementation of the Qwen3-ASR batch
+ * transcription hot path: log-mel -> audio encoder -> Qwen3 decoder prefill -> greedy decode.
+ *
+ * This is the drop-in boundary for the reference's Swift API (paths relative to /root/reference):
+ *   Qwen3ASRModel.fromPretrained            Sources/Qwen3ASR/Qwen3ASR.swift:608-668   -> q3asr_create + q3asr_load_safetensors
+ *   Qwen3ASRModel.transcribe(audio:...)     Sources/Qwen3ASR/Qwen3ASR.swift:107-164   -> q3asr_transcribe_ids (ids; the tokenizer stays in Swift)
+ *   WhisperFeatureExtractor.extractFeaturesRaw  Sources/Qwen3ASR/AudioPreprocessing.swift:347-470 -> q3asr_mel / q3asr_mel_batch
+ *   Qwen3AudioEncoder.callAsFunction        Sources/Qwen3ASR/AudioEncoder.swift:362-511 -> q3asr_encode
+ *   ModelMemoryManageable                   Sources/Qwen3ASR/Qwen3ASR+Memory.swift:3-17 -> q3asr_is_loaded / q3asr_unload / q3asr_memory_footprint
+ *   sc_stt_vtable_t (the reference's own C bridge)  Sources/SpeechCore/VoicePipeline.swift:374-411 -> q3asr_transcribe_ids has the same shape
+ *
+ * Conventions: every function returns 0 (Q3ASR_OK) or a positive error code; q3asr_last_error() gives
+ * the message.  Nothing aborts.  Input pointers are borrowed for the duration of the call; outputs are
+ * written into caller-provided buffers.  A handle is single-caller (the reference's model classes are
+ * documented as not thread-safe, Qwen3ASR.swift:67); use one handle per GPU, or a q3asr_pool.
+ * There is no CPU fallback: without a Blackwell GPU q3asr_create fails.
+ */
+#ifndef Q3ASR_H
+#define Q3ASR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3ASR_OK 0
+#define Q3ASR_ERR_INVALID 1 /* bad argument */
+#define Q3ASR_ERR_STATE 2   /* e.g. weights not loaded (the reference returns a placeholder string, Qwen3ASR.swift:116-119) */
+#define Q3ASR_ERR_CUDA 3
+#define Q3ASR_ERR_NOMEM 4
+#define Q3ASR_ERR_IO 5
+
+#define Q3ASR_EOS_TOKEN 151645 /* <|im_end|>, Qwen3ASR.swift:59 */
+
+typedef struct q3asr_handle q3asr_handle;
+typedef struct q3asr_pool q3asr_pool;
+
+/* Model dimensions.  Presets mirror Qwen3AudioEncoderConfig (AudioEncoder.swift:28-68) and
+ * TextDecoderConfig (Configuration.swift:47-100). */
+typedef struct q3asr_config {
+    /* audio encoder */
+    int enc_d_model;     /* 896 / 1024 */
+    int enc_heads;       /* 14 / 16 (head dim must be 64) */
+    int enc_ffn;         /* 3584 / 4096 */
+    int enc_layers;      /* 18 / 24 */
+    int enc_out_dim;     /* 1024 / 2048 */
+    int enc_conv_ch;     /* 480 (downsampleHiddenSize) */
+    int enc_n_window;    /* 50  -> conv chunks of 100 frames */
+    int enc_n_window_infer; /* 800 -> attention windows of 13*8 tokens */
+    float enc_ln_eps;    /* 1e-5 */
+    /* text decoder */
+    int dec_vocab;       /* 151936 */
+    int dec_hidden;      /* 1024 / 2048 */
+    int dec_layers;      /* 28 */
+    int dec_heads;       /* 16 */
+    int dec_kv_heads;    /* 8 */
+    int dec_head_dim;    /* 128 */
+    int dec_inter;       /* 3072 / 6144 */
+    float dec_rope_theta; /* 1e6 */
+    float dec_rms_eps;   /* 1e-6 */
+    /* prompt token ids (Qwen3ASR.swift:181-195); only the tests' tiny vocabulary changes them */
+    int32_t tok_im_start, tok_im_end, tok_audio_start, tok_audio_end, tok_audio_pad, tok_asr_text, tok_newline, tok_system,
+        tok_user, tok_assistant, tok_eos;
+} q3asr_config;
+
+/* name: "0.6B", "1.7B", or "tiny" (a small configuration used by the parity tests) */
+int q3asr_config_preset(const char* name, q3asr_config* cfg);
+
+const char* q3asr_version(void);
+/* message of the last failed call on this handle (handle may be NULL: last failed create) */
+const char* q3asr_last_error(const q3asr_handle* h);
+
+int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out);
+void q3asr_destroy(q3asr_handle* h);
+
+/* ---- weights (names are the reference's safetensors keys, WeightLoading.swift:17-126, 235-323) ---- */
+/* deterministic random initialisation: bf16(0.02 * approx-normal) keyed by (seed, tensor name); norm weights 1 */
+int q3asr_init_random(q3asr_handle* h, uint64_t seed);
+int q3asr_tensor_count(const q3asr_handle* h);
+int q3asr_tensor_info(const q3asr_handle* h, int index, char* name, int name_cap, int64_t* shape4, int* ndim);
+/* dtype: 0 = fp32, 1 = bf16, 2 = fp16; converted to bf16 on upload */
+int q3asr_set_tensor(q3asr_handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+int q3asr_get_tensor(const q3asr_handle* h, const char* name, float* out, size_t out_elems);
+/* builds the fused / permuted device layouts from the named tensors; required after q3asr_set_tensor */
+int q3asr_commit_weights(q3asr_handle* h);
+/* reads every *.safetensors in dir (audio_tower.* and model.* keys; fp32/fp16/bf16; conv weights in
+ * MLX [O,kH,kW,I] or PyTorch [O,I,kH,kW] layout) and commits */
+int q3asr_load_safetensors(q3asr_handle* h, const char* dir);
+int q3asr_is_loaded(const q3asr_handle* h);
+int q3asr_unload(q3asr_handle* h);
+size_t q3asr_memory_footprint(const q3asr_handle* h);
+
+/* ---- stages (parity surface) ---- */
+/* frames kept for n samples at 16 kHz: min(n / 160, 120000) (AudioPreprocessing.swift:195, 296, 304) */
+int q3asr_mel_frames(size_t n_samples);
+/* out: [128, frames] fp32 row-major (mel-major), the layout of MelFeatures.data */
+int q3asr_mel(q3asr_handle* h, const float* pcm, size_t n_samples, float* out, int* frames);
+int q3asr_mel_batch(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch, float* const* out,
+                    int* frames);
+/* audio tokens produced for `frames` mel frames (AudioEncoder.swift:287-303) */
+int q3asr_encoder_tokens(int frames);
+/* mel: [128, frames] fp32 (host).  out: [tokens, enc_out_dim] fp32 (converted from the bf16 result) */
+int q3asr_encode(q3asr_handle* h, const float* mel, int frames, float* out, int* tokens);
+
+/* per-utterance prompt extras (token ids from the Swift tokenizer; either may be NULL/0):
+ * context goes into the system turn, language ("language xx") before <asr_text>  (Qwen3ASR.swift:203-232) */
+typedef struct q3asr_prompt {
+    const int32_t* context_ids;
+    int n_context;
+    const int32_t* language_ids;
+    int n_language;
+} q3asr_prompt;
+
+/* Batched greedy transcription.  ids_out: [batch, max_tokens] int32; lens_out: [batch].
+ * stop_on_eos != 0 reproduces the reference loop (EOS appended, then stop, Qwen3ASR.swift:378-379);
+ * stop_on_eos == 0 decodes exactly max_tokens ids (fixed-length parity runs).  prompts may be NULL. */
+int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch,
+                         const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out);
+
+/* Teacher-forced scoring (parity on a prescribed token stream): the decoder consumes forced[0..n) as its
+ * own outputs; argmax_out[i] / top_out[i] are the argmax id and its bf16 logit at step i (i = 0 is the
+ * prefill position), n_forced + 1 entries. */
+int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt,
+                        const int32_t* forced, int n_forced, int32_t* argmax_out, float* top_out);
+/* full logits of the prefill's last position, [vocab] fp32 (debug / parity) */
+int q3asr_prefill_logits(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt, float* logits);
+
+/* ---- resident-batch interface (what q3asr_transcribe_ids is made of; lets a caller time the stages
+ * with inputs already in HBM) ---- */
+int q3asr_batch_upload(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch,
+                       const q3asr_prompt* prompts);
+/* stages: bit 0 mel, bit 1 encoder, bit 2 prefill (+ first token), bit 3 greedy decode */
+#define Q3ASR_STAGE_MEL 1
+#define Q3ASR_STAGE_ENCODER 2
+#define Q3ASR_STAGE_PREFILL 4
+#define Q3ASR_STAGE_DECODE 8
+#define Q3ASR_STAGE_ALL 15
+int q3asr_batch_run(q3asr_handle* h, int stages, int max_tokens, int stop_on_eos);
+int q3asr_batch_download(q3asr_handle* h, int32_t* ids_out, int max_tokens, int* lens_out);
+int q3asr_sync(q3asr_handle* h);
+/* device-side timing on the handle's stream: record slot (0..15), elapsed between two recorded slots */
+int q3asr_timer_record(q3asr_handle* h, int slot);
+int q3asr_timer_elapsed_ms(q3asr_handle* h, int slot_a, int slot_b, float* ms);
+/* per-stage device time of the last q3asr_batch_run: [mel, encoder, prefill, decode] in ms */
+int q3asr_stage_ms(q3asr_handle* h, float* ms4);
+/* kernels launched by this handle so far */
+uint64_t q3asr_launch_count(const q3asr_handle* h);
+/* L2 flush helper for benchmarks: overwrites a >L2-sized scratch buffer on the handle's stream */
+int q3asr_flush_l2(q3asr_handle* h);
+
+/* ---- utterance-batching scheduler over several GPUs of one box (one worker thread + handle per GPU,
+ * weights replicated, utterances dealt longest-first; no collective on the data path) ---- */
+int q3asr_pool_create(const q3asr_config* cfg, const int* devices, int n_devices, uint64_t random_seed, const char* weights_dir,
+                      q3asr_pool** out);
+void q3asr_pool_destroy(q3asr_pool* p);
+const char* q3asr_pool_last_error(const q3asr_pool* p);
+int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, int batch,
+                              const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int max_batch_per_gpu,
+                              int32_t* ids_out, int* lens_out);
+/* the scheduler's assignment alone (host logic; no GPU needed): gpu_out[i] = GPU of utterance i */
+int q3asr_schedule(const size_t* n_samples, int batch, int n_gpus, int* gpu_out);
+
+/* ---- debug / test hooks (exercise single kernels through the C ABI) ---- */
+/* C[M,N] = A[M,K] W[N,K]^T with bf16 (uint16) host operands; epi: 0 store(+bias,+gelu), 1 swiglu, 2 fp32, 3 argmax.
+ * use_simt != 0 runs the CUDA-core checker kernel instead of tcgen05.  out: bf16 as uint16 (epi 0,1: [M,N] / [M,N/2]),
+ * fp32 (epi 2) or int32 argmax ids [M] (epi 3). bn = 0 picks the tile width. */
+int q3asr_debug_gemm(q3asr_handle* h, const uint16_t* A, const uint16_t* W, const uint16_t* bias, const uint16_t* resid, int M,
+                     int N, int K, int epi, int gelu, int bn, int use_simt, void* out);
+/* 3x3 stride-2 pad-1 NHWC convolution as implicit GEMM: in [B,H,W,C] bf16, w [O,3,3,C] bf16, out [B,OH,OW,O] bf16 (+bias, GELU) */
+int q3asr_debug_conv(q3asr_handle* h, const uint16_t* in, const uint16_t* w, const uint16_t* bias, int B, int H, int W, int C, int O,
+                     int box_w, int box_h, int box_b, int use_simt, uint16_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q3ASR_H */

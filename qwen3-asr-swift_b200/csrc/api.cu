@@ -1,0 +1,390 @@
+// api.cu — the extern "C" surface declared in include/q3asr.h.  Every entry point catches, records the
+// message on the handle and returns a status code; nothing aborts (SURVEY.md §8b error contract).
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "gemm.cuh"
+#include "model.h"
+
+using namespace q3;
+
+struct q3asr_handle {
+    Handle h;
+};
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_create_mu;
+
+template <typename F>
+int guarded(q3asr_handle* hh, F&& fn) {
+    if (hh == nullptr) return Q3ASR_ERR_INVALID;
+    try {
+        DeviceGuard g(hh->h.device);
+        fn(hh->h);
+        return Q3ASR_OK;
+    } catch (const Error& e) {
+        hh->h.last_error = e.what();
+        return e.code > 0 ? e.code : Q3ASR_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        hh->h.last_error = "out of host memory";
+        return Q3ASR_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        hh->h.last_error = e.what();
+        return Q3ASR_ERR_INVALID;
+    }
+}
+
+void set_common_tokens(q3asr_config* c) {
+    c->tok_im_start = 151644;
+    c->tok_im_end = 151645;
+    c->tok_audio_start = 151669;
+    c->tok_audio_end = 151670;
+    c->tok_audio_pad = 151676;
+    c->tok_asr_text = 151704;
+    c->tok_newline = 198;
+    c->tok_system = 8948;
+    c->tok_user = 872;
+    c->tok_assistant = 77091;
+    c->tok_eos = Q3ASR_EOS_TOKEN;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* q3asr_version(void) { return "q3asr-b200 0.1.0 (sm_100a)"; }
+
+int q3asr_config_preset(const char* name, q3asr_config* c) {
+    if (name == nullptr || c == nullptr) return Q3ASR_ERR_INVALID;
+    memset(c, 0, sizeof(*c));
+    c->enc_conv_ch = 480;
+    c->enc_n_window = 50;
+    c->enc_n_window_infer = 800;
+    c->enc_ln_eps = 1e-5f;
+    c->dec_vocab = 151936;
+    c->dec_layers = 28;
+    c->dec_heads = 16;
+    c->dec_kv_heads = 8;
+    c->dec_head_dim = 128;
+    c->dec_rope_theta = 1000000.0f;
+    c->dec_rms_eps = 1e-6f;
+    set_common_tokens(c);
+    const std::string n(name);
+    if (n == "0.6B" || n == "small") {
+        c->enc_d_model = 896; c->enc_heads = 14; c->enc_ffn = 3584; c->enc_layers = 18; c->enc_out_dim = 1024;
+        c->dec_hidden = 1024; c->dec_inter = 3072;
+    } else if (n == "1.7B" || n == "large") {
+        c->enc_d_model = 1024; c->enc_heads = 16; c->enc_ffn = 4096; c->enc_layers = 24; c->enc_out_dim = 2048;
+        c->dec_hidden = 2048; c->dec_inter = 6144;
+    } else if (n == "tiny") {
+        // small enough for the CPU oracle to finish in seconds; same graph, same kernels
+        c->enc_d_model = 128; c->enc_heads = 2; c->enc_ffn = 256; c->enc_layers = 2; c->enc_out_dim = 128;
+        c->enc_conv_ch = 32;
+        c->dec_vocab = 2048; c->dec_hidden = 128; c->dec_layers = 2; c->dec_heads = 4; c->dec_kv_heads = 2;
+        c->dec_inter = 256;
+        c->tok_im_start = 2001; c->tok_im_end = 2002; c->tok_audio_start = 2003; c->tok_audio_end = 2004;
+        c->tok_audio_pad = 2005; c->tok_asr_text = 2006; c->tok_newline = 198; c->tok_system = 1948; c->tok_user = 872;
+        c->tok_assistant = 1091; c->tok_eos = 2002;
+    } else {
+        return Q3ASR_ERR_INVALID;
+    }
+    return Q3ASR_OK;
+}
+
+const char* q3asr_last_error(const q3asr_handle* h) {
+    if (h == nullptr) return g_create_error.c_str();
+    return h->h.last_error.c_str();
+}
+
+int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out) {
+    if (cfg == nullptr || out == nullptr) return Q3ASR_ERR_INVALID;
+    *out = nullptr;
+    q3asr_handle* hh = nullptr;
+    try {
+        config_validate(*cfg);
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(Q3ASR_ERR_CUDA, std::string("no CUDA device: libq3asr has no CPU fallback (") + cudaGetErrorString(e) + ")");
+        Q3_CHECK(device >= 0 && device < ndev, Q3ASR_ERR_INVALID, "device index out of range");
+        DeviceGuard g(device);
+        hh = new q3asr_handle();
+        Handle& h = hh->h;
+        h.cfg = *cfg;
+        h.device = device;
+        gemm_init(device);
+        cudaDeviceProp prop;
+        Q3_CUDA(cudaGetDeviceProperties(&prop, device));
+        h.num_sms = prop.multiProcessorCount;
+        Q3_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+        mel_tables_create(&h.mel_tables);
+        h.mel_ready = true;
+        for (int i = 0; i < 16; i++) Q3_CUDA(cudaEventCreate(&h.timer[i]));
+        h.gemm_base = gemm_launch_count();
+        *out = hh;
+        return Q3ASR_OK;
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(g_create_mu);
+        g_create_error = e.what();
+        const Error* qe = dynamic_cast<const Error*>(&e);
+        if (hh) q3asr_destroy(hh);
+        return qe ? qe->code : Q3ASR_ERR_INVALID;
+    }
+}
+
+void q3asr_destroy(q3asr_handle* hh) {
+    if (hh == nullptr) return;
+    Handle& h = hh->h;
+    try {
+        DeviceGuard g(h.device);
+        if (h.stream) cudaStreamSynchronize(h.stream);
+        model_unload(&h);
+        if (h.mel_ready) mel_tables_destroy(&h.mel_tables);
+        for (DevBuf* b : {&h.mel_pcm, &h.mel_out, &h.mel_clips, &h.mel_gmax, &h.mel_tmin, &h.flush_buf}) b->release();
+        h.mel_stage.release();
+        for (int i = 0; i < 16; i++)
+            if (h.timer[i]) cudaEventDestroy(h.timer[i]);
+        if (h.stream) cudaStreamDestroy(h.stream);
+    } catch (...) {
+    }
+    delete hh;
+}
+
+// ---- weights ----
+int q3asr_init_random(q3asr_handle* h, uint64_t seed) {
+    return guarded(h, [&](Handle& x) { model_init_random(&x, seed); });
+}
+int q3asr_tensor_count(const q3asr_handle* h) { return h ? (int)h->h.tensors.size() : 0; }
+int q3asr_tensor_info(const q3asr_handle* h, int index, char* name, int name_cap, int64_t* shape4, int* ndim) {
+    if (h == nullptr || index < 0 || index >= (int)h->h.tensors.size()) return Q3ASR_ERR_INVALID;
+    const Tensor& t = h->h.tensors[index];
+    if (name && name_cap > 0) {
+        strncpy(name, t.name.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (shape4)
+        for (int i = 0; i < 4; i++) shape4[i] = i < (int)t.shape.size() ? t.shape[i] : 1;
+    if (ndim) *ndim = (int)t.shape.size();
+    return Q3ASR_OK;
+}
+int q3asr_set_tensor(q3asr_handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+    return guarded(h, [&](Handle& x) { model_set_tensor(&x, name, data, dtype, shape, ndim); });
+}
+int q3asr_get_tensor(const q3asr_handle* h, const char* name, float* out, size_t n) {
+    return guarded(const_cast<q3asr_handle*>(h), [&](Handle& x) { model_get_tensor(&x, name, out, n); });
+}
+int q3asr_commit_weights(q3asr_handle* h) {
+    return guarded(h, [&](Handle& x) { model_commit(&x); });
+}
+int q3asr_load_safetensors(q3asr_handle* h, const char* dir) {
+    return guarded(h, [&](Handle& x) { model_load_safetensors(&x, dir); });
+}
+int q3asr_is_loaded(const q3asr_handle* h) { return h != nullptr && h->h.loaded ? 1 : 0; }
+int q3asr_unload(q3asr_handle* h) {
+    return guarded(h, [&](Handle& x) { model_unload(&x); });
+}
+size_t q3asr_memory_footprint(const q3asr_handle* h) { return h ? h->h.dev_bytes : 0; }
+
+// ---- mel ----
+int q3asr_mel_frames(size_t n) { return mel_frames_for(n); }
+
+int q3asr_mel_batch(q3asr_handle* hh, const float* const* pcm, const size_t* n, int batch, float* const* out, int* frames) {
+    return guarded(hh, [&](Handle& h) {
+        Q3_CHECK(pcm != nullptr && n != nullptr && out != nullptr && batch > 0, Q3ASR_ERR_INVALID, "mel: null argument / empty batch");
+        for (int b = 0; b < batch; b++)
+            Q3_CHECK(pcm[b] != nullptr && n[b] > 0 && n[b] < (size_t)1 << 30, Q3ASR_ERR_INVALID, "mel: empty or oversized clip");
+        MelPlan plan = mel_plan(n, batch);
+        h.mel_pcm.reserve(sizeof(float) * (plan.pcm_floats + 64));
+        h.mel_out.reserve(sizeof(float) * std::max<long long>(plan.out_floats, 1));
+        h.mel_clips.reserve(sizeof(MelClip) * batch);
+        h.mel_gmax.reserve(sizeof(int) * batch);
+        h.mel_tmin.reserve(sizeof(float) * plan.total_tiles);
+        h.mel_stage.reserve(sizeof(float) * std::max<long long>(plan.pcm_floats, plan.out_floats));
+        float* stage = h.mel_stage.as<float>();
+        for (int b = 0; b < batch; b++) memcpy(stage + plan.clips[b].in_off, pcm[b], sizeof(float) * n[b]);
+        Q3_CUDA(cudaMemcpyAsync(h.mel_pcm.p, stage, sizeof(float) * plan.pcm_floats, cudaMemcpyHostToDevice, h.stream));
+        Q3_CUDA(cudaMemcpyAsync(h.mel_clips.p, plan.clips.data(), sizeof(MelClip) * batch, cudaMemcpyHostToDevice, h.stream));
+        mel_launch(h.mel_tables, h.mel_pcm.as<float>(), h.mel_out.as<float>(), h.mel_clips.as<MelClip>(), batch, plan.total_tiles,
+                   h.mel_gmax.as<int>(), h.mel_tmin.as<float>(), h.num_sms, h.stream);
+        h.launches += 3;
+        Q3_CUDA(cudaStreamSynchronize(h.stream));  // staging buffer is reused for the way back
+        if (plan.out_floats > 0)
+            Q3_CUDA(cudaMemcpyAsync(stage, h.mel_out.p, sizeof(float) * plan.out_floats, cudaMemcpyDeviceToHost, h.stream));
+        Q3_CUDA(cudaStreamSynchronize(h.stream));
+        for (int b = 0; b < batch; b++) {
+            const MelClip& c = plan.clips[b];
+            if (c.frames > 0) memcpy(out[b], stage + c.out_off, sizeof(float) * (size_t)MEL_BINS * c.frames);
+            if (frames) frames[b] = c.frames;
+        }
+    });
+}
+
+int q3asr_mel(q3asr_handle* h, const float* pcm, size_t n, float* out, int* frames) {
+    const float* pp[1] = {pcm};
+    float* oo[1] = {out};
+    return q3asr_mel_batch(h, pp, &n, 1, oo, frames);
+}
+
+int q3asr_encoder_tokens(int frames) { return encoder_tokens_for(frames); }
+
+int q3asr_encode(q3asr_handle* h, const float* mel, int frames, float* out, int* tokens) {
+    return guarded(h, [&](Handle& x) { encode_one(&x, mel, frames, out, tokens); });
+}
+
+// ---- transcription ----
+int q3asr_batch_upload(q3asr_handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts) {
+    return guarded(h, [&](Handle& x) { batch_upload(&x, pcm, n, batch, prompts); });
+}
+int q3asr_batch_run(q3asr_handle* h, int stages, int max_tokens, int stop_on_eos) {
+    return guarded(h, [&](Handle& x) { batch_run(&x, stages, max_tokens, stop_on_eos); });
+}
+int q3asr_batch_download(q3asr_handle* h, int32_t* ids, int max_tokens, int* lens) {
+    return guarded(h, [&](Handle& x) { batch_download(&x, ids, max_tokens, lens); });
+}
+int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts,
+                         int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
+        batch_upload(&x, pcm, n, batch, prompts);
+        batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
+        batch_download(&x, ids_out, max_tokens, lens_out);
+    });
+}
+int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
+                        int32_t* argmax_out, float* top_out) {
+    return guarded(h, [&](Handle& x) { decode_forced(&x, pcm, n, prompt, forced, n_forced, argmax_out, top_out); });
+}
+int q3asr_prefill_logits(q3asr_handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits) {
+    return guarded(h, [&](Handle& x) { prefill_logits(&x, pcm, n, prompt, logits); });
+}
+
+int q3asr_sync(q3asr_handle* h) {
+    return guarded(h, [&](Handle& x) { Q3_CUDA(cudaStreamSynchronize(x.stream)); });
+}
+int q3asr_timer_record(q3asr_handle* h, int slot) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(slot >= 0 && slot < 16, Q3ASR_ERR_INVALID, "timer slot");
+        Q3_CUDA(cudaEventRecord(x.timer[slot], x.stream));
+    });
+}
+int q3asr_timer_elapsed_ms(q3asr_handle* h, int a, int b, float* ms) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(a >= 0 && a < 16 && b >= 0 && b < 16 && ms != nullptr, Q3ASR_ERR_INVALID, "timer slot");
+        Q3_CUDA(cudaEventSynchronize(x.timer[b]));
+        Q3_CUDA(cudaEventElapsedTime(ms, x.timer[a], x.timer[b]));
+    });
+}
+int q3asr_stage_ms(q3asr_handle* h, float* ms4) {
+    if (h == nullptr || ms4 == nullptr) return Q3ASR_ERR_INVALID;
+    for (int i = 0; i < 4; i++) ms4[i] = h->h.stage_ms[i];
+    return Q3ASR_OK;
+}
+uint64_t q3asr_launch_count(const q3asr_handle* h) {
+    if (h == nullptr) return 0;
+    return h->h.launches + (gemm_launch_count() - h->h.gemm_base);
+}
+int q3asr_flush_l2(q3asr_handle* h) {
+    return guarded(h, [&](Handle& x) {
+        const size_t bytes = (size_t)256 << 20;
+        x.flush_buf.reserve(bytes);
+        Q3_CUDA(cudaMemsetAsync(x.flush_buf.p, 0, bytes, x.stream));
+    });
+}
+
+// ---- debug hooks ----
+int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, const uint16_t* bias, const uint16_t* resid, int M, int N,
+                     int K, int epi, int gelu, int bn, int use_simt, void* out) {
+    return guarded(hh, [&](Handle& h) {
+        Q3_CHECK(A && W && out && M > 0 && N > 0 && K > 0, Q3ASR_ERR_INVALID, "debug_gemm: bad argument");
+        bf16 *dA, *dW, *dB = nullptr, *dR = nullptr;
+        void* dO;
+        float* dv = nullptr;
+        int* di = nullptr;
+        int32_t* dtok = nullptr;
+        const int bnn = bn ? bn : gemm_pick_bn(N, epi, cdiv(M, GEMM_BM));
+        const int tiles_n = N / bnn;
+        const size_t out_bytes = epi == EPI_F32 ? sizeof(float) * (size_t)M * N
+                                 : epi == EPI_SWIGLU ? 2 * (size_t)M * (N / 2)
+                                 : epi == EPI_ARGMAX ? sizeof(int32_t) * (size_t)M
+                                                     : 2 * (size_t)M * N;
+        Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
+        Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
+        Q3_CUDA(cudaMalloc(&dO, std::max<size_t>(out_bytes, 2 * (size_t)M * N)));
+        Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+        if (bias) {
+            Q3_CUDA(cudaMalloc(&dB, 2 * (size_t)N));
+            Q3_CUDA(cudaMemcpy(dB, bias, 2 * (size_t)N, cudaMemcpyHostToDevice));
+        }
+        if (resid) {
+            Q3_CUDA(cudaMalloc(&dR, 2 * (size_t)M * N));
+            Q3_CUDA(cudaMemcpy(dR, resid, 2 * (size_t)M * N, cudaMemcpyHostToDevice));
+        }
+        GemmEpiArgs e;
+        e.epi = epi;
+        e.out = dO;
+        e.ldo = epi == EPI_SWIGLU ? N / 2 : N;
+        e.bias = dB;
+        e.resid = dR;
+        e.ldr = N;
+        e.gelu = gelu;
+        if (epi == EPI_ARGMAX) {
+            Q3_CUDA(cudaMalloc(&dv, sizeof(float) * (size_t)M * tiles_n));
+            Q3_CUDA(cudaMalloc(&di, sizeof(int) * (size_t)M * tiles_n));
+            Q3_CUDA(cudaMalloc(&dtok, sizeof(int32_t) * (size_t)M));
+            e.amax_val = dv;
+            e.amax_idx = di;
+        }
+        gemm(dA, K, M, K, dW, N, e, h.stream, use_simt != 0, bnn);
+        if (epi == EPI_ARGMAX) {
+            argmax_reduce(dv, di, M, tiles_n, dtok, nullptr, h.stream);
+            Q3_CUDA(cudaMemcpyAsync(out, dtok, out_bytes, cudaMemcpyDeviceToHost, h.stream));
+        } else {
+            Q3_CUDA(cudaMemcpyAsync(out, dO, out_bytes, cudaMemcpyDeviceToHost, h.stream));
+        }
+        cudaError_t se = cudaStreamSynchronize(h.stream);
+        cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dB); cudaFree(dR); cudaFree(dv); cudaFree(di); cudaFree(dtok);
+        Q3_CUDA(se);
+    });
+}
+
+int q3asr_debug_conv(q3asr_handle* hh, const uint16_t* in, const uint16_t* w, const uint16_t* bias, int B, int H, int W, int C, int O,
+                     int box_w, int box_h, int box_b, int use_simt, uint16_t* out) {
+    return guarded(hh, [&](Handle& h) {
+        Q3_CHECK(in && w && out && B > 0 && H > 0 && W > 0 && C > 0 && O > 0, Q3ASR_ERR_INVALID, "debug_conv: bad argument");
+        const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+        bf16 *dI, *dW, *dB = nullptr, *dO;
+        const size_t in_n = (size_t)B * H * W * C, w_n = (size_t)O * 9 * C, out_n = (size_t)B * OH * OW * O;
+        Q3_CUDA(cudaMalloc(&dI, 2 * in_n));
+        Q3_CUDA(cudaMalloc(&dW, 2 * w_n));
+        Q3_CUDA(cudaMalloc(&dO, 2 * out_n));
+        Q3_CUDA(cudaMemcpy(dI, in, 2 * in_n, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dW, w, 2 * w_n, cudaMemcpyHostToDevice));
+        if (bias) {
+            Q3_CUDA(cudaMalloc(&dB, 2 * (size_t)O));
+            Q3_CUDA(cudaMemcpy(dB, bias, 2 * (size_t)O, cudaMemcpyHostToDevice));
+        }
+        GemmA a;
+        a.ptr = dI; a.C = C; a.W = W; a.H = H; a.B = B;
+        a.sW = C; a.sH = (long)W * C; a.sB = (long)H * W * C;
+        GemmShape s;
+        s.Wb = box_w; s.Hb = box_h; s.Bb = box_b;
+        s.OW = OW; s.OH = OH; s.OB = B;
+        s.sw = 2; s.sh = 2;
+        s.taps = 9;
+        for (int t = 0; t < 9; t++) { s.tap_dw[t] = (signed char)(t % 3 - 1); s.tap_dh[t] = (signed char)(t / 3 - 1); }
+        GemmEpiArgs e;
+        e.out = dO; e.ldo = O; e.bias = dB; e.gelu = 1;
+        gemm_conv(a, s, dW, O, e, h.stream, use_simt != 0, 0);
+        Q3_CUDA(cudaMemcpyAsync(out, dO, 2 * out_n, cudaMemcpyDeviceToHost, h.stream));
+        cudaError_t se = cudaStreamSynchronize(h.stream);
+        cudaFree(dI); cudaFree(dW); cudaFree(dO); cudaFree(dB);
+        Q3_CUDA(se);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,690 @@
+// forward.cu — the batched transcription pipeline behind q3asr_batch_* / q3asr_transcribe_ids:
+// host-side planning (chunks, audio tokens, attention windows, prompts, KV pages) and the kernel
+// sequence  mel -> conv stack -> encoder layers -> prompt splice -> prefill -> greedy decode.
+//
+// Follows (paths relative to /root/reference/Sources/Qwen3ASR):
+//   AudioEncoder.swift:362-511   chunking, conv stack, conv_out + positions, valid-token gather, windows, layers, projector
+//   Qwen3ASR.swift:181-256       prompt layout, audio splice, prefill, tied LM head on the last position
+//   Qwen3ASR.swift:317-390       greedy loop (token appended, then EOS check)
+//   FloatTextDecoder.swift:35-226 decoder block
+// B200 design notes: all utterances of a batch are packed row-wise (no padding to the longest one);
+// every dense product is one launch of the persistent tcgen05 GEMM; the conv stack is walked in
+// L2-sized groups of chunks; a decode step is a CUDA graph replayed max_tokens-1 times with the
+// per-sequence state (positions, cache lengths, EOS flags) living on the device.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "model.h"
+
+namespace q3 {
+
+namespace {
+
+int env_int(const char* name, int def) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : def;
+}
+
+template <typename T>
+size_t push_ints(std::vector<int>& buf, const std::vector<T>& v) {
+    static_assert(sizeof(T) % sizeof(int) == 0, "int-multiple types only");
+    // 16-byte aligned sub-arrays
+    while (buf.size() % 4) buf.push_back(0);
+    const size_t off = buf.size();
+    const size_t n = v.size() * sizeof(T) / sizeof(int);
+    buf.resize(off + n);
+    if (n) memcpy(buf.data() + off, v.data(), n * sizeof(int));
+    return off;
+}
+
+void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at) {
+    // Qwen3ASR.swift:196-233
+    ids->insert(ids->end(), {c.tok_im_start, c.tok_system, c.tok_newline});
+    if (pr && pr->context_ids && pr->n_context > 0) ids->insert(ids->end(), pr->context_ids, pr->context_ids + pr->n_context);
+    ids->insert(ids->end(), {c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_user, c.tok_newline, c.tok_audio_start});
+    *audio_at = (int)ids->size();
+    ids->insert(ids->end(), (size_t)ntok, c.tok_audio_pad);
+    ids->insert(ids->end(), {c.tok_audio_end, c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_assistant, c.tok_newline});
+    if (pr && pr->language_ids && pr->n_language > 0) ids->insert(ids->end(), pr->language_ids, pr->language_ids + pr->n_language);
+    ids->push_back(c.tok_asr_text);
+}
+
+BatchState* fresh_batch(Handle* h) {
+    if (!h->batch) {
+        h->batch.reset(new BatchState());
+        h->batch->bind(&h->dev_bytes);
+        for (auto& e : h->batch->ev) Q3_CUDA(cudaEventCreate(&e));
+    }
+    return h->batch.get();
+}
+
+// Plans the encoder side for clips with the given frame counts (mel already known or to be computed).
+void plan_encoder(Handle* h, BatchState* bs, const std::vector<int>& frames, const std::vector<long long>& mel_off,
+                  std::vector<int>* ints) {
+    const Geom g(h->cfg);
+    const int B = (int)frames.size();
+    bs->clips.assign(B, ClipInfo());
+    std::vector<Conv1Chunk> chunks;
+    std::vector<int> vw1, vw2, vw3, rowmap, win_row0, win_len;
+    int tok = 0, max_win = 0;
+    for (int b = 0; b < B; b++) {
+        ClipInfo& ci = bs->clips[b];
+        const int T = frames[b];
+        ci.frames = T;
+        ci.chunk0 = (int)chunks.size();
+        ci.nchunks = (T + g.chunk - 1) / g.chunk;
+        ci.tok0 = tok;
+        int maxv = 0;
+        const int w0 = ci.nchunks > 1 ? g.chunk : T;  // max chunk length of this clip (AudioEncoder.swift:380)
+        for (int k = 0; k < ci.nchunks; k++) {
+            Conv1Chunk cc;
+            cc.mel_off = mel_off[b];
+            cc.T = T;
+            cc.f0 = k * g.chunk;
+            cc.len = std::min(g.chunk, T - cc.f0);
+            cc.w0 = w0;
+            chunks.push_back(cc);
+            const int a1 = conv_len(w0), a2 = conv_len(a1), a3 = conv_len(a2);
+            vw1.push_back(a1);
+            vw2.push_back(a2);
+            vw3.push_back(a3);
+            const int v = conv_len3(cc.len);  // valid tokens of this chunk (:441-448)
+            maxv = std::max(maxv, v);
+            for (int t = 0; t < g.tpc; t++) rowmap.push_back(t < v ? tok + t : -1);
+            tok += v;
+        }
+        ci.ntok = tok - ci.tok0;
+        ci.win_size = maxv * g.win_mult;  // :463-465
+        for (int s = 0; s < ci.ntok; s += ci.win_size) {
+            win_row0.push_back(ci.tok0 + s);
+            win_len.push_back(std::min(ci.win_size, ci.ntok - s));
+            max_win = std::max(max_win, win_len.back());
+        }
+    }
+    bs->n_chunks = (int)chunks.size();
+    bs->n_tok = tok;
+    bs->n_win = (int)win_row0.size();
+    bs->max_win = max_win;
+    bs->o_conv_chunks = push_ints(*ints, chunks);
+    bs->o_vw1 = push_ints(*ints, vw1);
+    bs->o_vw2 = push_ints(*ints, vw2);
+    bs->o_vw3 = push_ints(*ints, vw3);
+    bs->o_rowmap = push_ints(*ints, rowmap);
+    bs->o_win_row0 = push_ints(*ints, win_row0);
+    bs->o_win_len = push_ints(*ints, win_len);
+}
+
+void plan_decoder(Handle* h, BatchState* bs, const q3asr_prompt* prompts, int max_tokens, std::vector<int>* ints) {
+    const q3asr_config& c = h->cfg;
+    const int B = bs->B;
+    std::vector<int> ids, audio_src, pos, row_seq, seq_row0, seq_len, last_row, ident, pos0;
+    int row = 0, max_prompt = 0;
+    for (int b = 0; b < B; b++) {
+        ClipInfo& ci = bs->clips[b];
+        std::vector<int32_t> p;
+        build_prompt(c, prompts ? &prompts[b] : nullptr, ci.ntok, &p, &ci.audio_at);
+        ci.row0 = row;
+        ci.prompt_len = (int)p.size();
+        for (int i = 0; i < ci.prompt_len; i++) {
+            Q3_CHECK(p[i] >= 0 && p[i] < c.dec_vocab, Q3ASR_ERR_INVALID, "prompt token id out of range");
+            ids.push_back(p[i]);
+            const int a = i - ci.audio_at;
+            audio_src.push_back(a >= 0 && a < ci.ntok ? ci.tok0 + a : -1);
+            pos.push_back(i);
+            row_seq.push_back(b);
+        }
+        seq_row0.push_back(row);
+        seq_len.push_back(ci.prompt_len);
+        pos0.push_back(ci.prompt_len - 1);
+        row += ci.prompt_len;
+        last_row.push_back(row - 1);
+        ident.push_back(b);
+        max_prompt = std::max(max_prompt, ci.prompt_len);
+    }
+    bs->R = row;
+    bs->max_prompt = max_prompt;
+    bs->max_tokens = max_tokens;
+    bs->pages_per_seq = (max_prompt + max_tokens + KV_PAGE - 1) / KV_PAGE;
+    std::vector<int> table((size_t)B * bs->pages_per_seq);
+    for (size_t i = 0; i < table.size(); i++) table[i] = (int)i;  // pages handed out in order; freed with the batch
+    bs->o_ids = push_ints(*ints, ids);
+    bs->o_audio_src = push_ints(*ints, audio_src);
+    bs->o_pos = push_ints(*ints, pos);
+    bs->o_row_seq = push_ints(*ints, row_seq);
+    bs->o_seq_row0 = push_ints(*ints, seq_row0);
+    bs->o_seq_len = push_ints(*ints, seq_len);
+    bs->o_last_row = push_ints(*ints, last_row);
+    bs->o_ident = push_ints(*ints, ident);
+    bs->o_pos0 = push_ints(*ints, pos0);
+    bs->o_page_table = push_ints(*ints, table);
+}
+
+void upload_ints(Handle* h, BatchState* bs, const std::vector<int>& ints) {
+    bs->ints.reserve(ints.size() * sizeof(int) + 16);
+    bs->h_stage.reserve(ints.size() * sizeof(int) + 16);
+    memcpy(bs->h_stage.p, ints.data(), ints.size() * sizeof(int));
+    Q3_CUDA(cudaMemcpyAsync(bs->ints.p, bs->h_stage.p, ints.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));  // h_stage is reused by the next upload
+}
+
+void reserve_encoder(Handle* h, BatchState* bs) {
+    const q3asr_config& c = h->cfg;
+    const Geom g(c);
+    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 32)));
+    const size_t d = c.enc_d_model;
+    bs->a1.reserve((size_t)grp * 64 * g.w1 * g.C * 2);
+    bs->a2.reserve((size_t)grp * 32 * g.w2 * g.C * 2);
+    bs->a3.reserve((size_t)bs->n_chunks * 16 * g.w3 * g.C * 2);
+    const size_t T = std::max(bs->n_tok, 1);
+    bs->ex.reserve(T * d * 2);
+    bs->exn.reserve(T * d * 2);
+    bs->eqkv.reserve(T * 3 * d * 2);
+    bs->eatt.reserve(T * d * 2);
+    bs->effn.reserve(T * c.enc_ffn * 2);
+    bs->audio.reserve(T * c.enc_out_dim * 2);
+}
+
+void reserve_decoder(Handle* h, BatchState* bs) {
+    const q3asr_config& c = h->cfg;
+    const size_t R = std::max(bs->R, bs->B), hd = c.dec_head_dim;
+    const size_t nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, H = c.dec_hidden;
+    bs->dx.reserve(R * H * 2);
+    bs->dxn.reserve(R * H * 2);
+    bs->dqkv.reserve(R * (nq + 2 * nkv) * 2);
+    bs->dq.reserve(R * nq * 2);
+    bs->dkc.reserve(R * nkv * 2);
+    bs->dvc.reserve(R * nkv * 2);
+    bs->datt.reserve(R * nq * 2);
+    bs->dact.reserve(R * c.dec_inter * 2);
+    bs->dlast.reserve((size_t)bs->B * H * 2);
+    const size_t page_elems = (size_t)c.dec_layers * 2 * c.dec_kv_heads * KV_PAGE * hd;
+    bs->kv_pool.reserve((size_t)bs->B * bs->pages_per_seq * page_elems * 2);
+    const size_t tiles = c.dec_vocab / 32;  // upper bound on LM-head n-tiles
+    bs->amax_val.reserve((size_t)bs->B * tiles * 4);
+    bs->amax_idx.reserve((size_t)bs->B * tiles * 4);
+    const size_t B = bs->B, mt = std::max(bs->max_tokens, 1);
+    bs->st_next_tok.reserve(B * 4);
+    bs->st_next_val.reserve(B * 4);
+    bs->st_cur_tok.reserve(B * 4);
+    bs->st_pos.reserve(B * 4);
+    bs->st_kv_len.reserve(B * 4);
+    bs->st_out_ids.reserve(B * mt * 4);
+    bs->st_out_val.reserve(B * mt * 4);
+    bs->st_out_len.reserve(B * 4);
+    bs->st_finished.reserve(B * 4);
+    bs->st_scalars.reserve(64);
+    bs->h_out.reserve(B * mt * 8 + B * 8 + 64);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------
+void run_mel(Handle* h, BatchState* bs) {
+    mel_launch(h->mel_tables, bs->pcm.as<float>(), bs->mel_out.as<float>(), bs->mel_clips.as<MelClip>(), bs->B, bs->mel.total_tiles,
+               bs->mel_gmax.as<int>(), bs->mel_tmin.as<float>(), h->num_sms, h->stream);
+    h->launches += 3;
+    bs->mel_done = true;
+}
+
+GemmEpiArgs epi_store(void* out, int ldo, const bf16* bias, int gelu = 0, const bf16* resid = nullptr, int ldr = 0) {
+    GemmEpiArgs e;
+    e.out = out; e.ldo = ldo; e.bias = bias; e.gelu = gelu; e.resid = resid; e.ldr = ldr;
+    return e;
+}
+
+void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
+    const q3asr_config& c = h->cfg;
+    const Geom g(c);
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int* ints = bs->ints.as<int>();
+    const int d = c.enc_d_model;
+    if (bs->n_tok == 0) { bs->enc_done = true; return; }
+
+    // ---- conv stack, walked in groups of chunks so conv1/conv2 activations stay L2-resident ----
+    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 32)));
+    const Conv1Chunk* chunks = reinterpret_cast<const Conv1Chunk*>(ints + bs->o_conv_chunks);
+    GemmShape s2, s3;
+    s2.Wb = g.w2; s2.Hb = 1; s2.Bb = std::max(1, GEMM_BM / g.w2);
+    s2.OW = g.w2; s2.OH = 32; s2.sw = 2; s2.sh = 2; s2.taps = 9;
+    s3.Wb = g.w3; s3.Hb = 1; s3.Bb = std::max(1, GEMM_BM / g.w3);
+    s3.OW = g.w3; s3.OH = 16; s3.sw = 2; s3.sh = 2; s3.taps = 9;
+    for (int t = 0; t < 9; t++) {
+        s2.tap_dw[t] = s3.tap_dw[t] = (signed char)(t % 3 - 1);
+        s2.tap_dh[t] = s3.tap_dh[t] = (signed char)(t / 3 - 1);
+    }
+    for (int c0 = 0; c0 < bs->n_chunks; c0 += grp) {
+        const int n = std::min(grp, bs->n_chunks - c0);
+        conv1_launch(d_mel, chunks + c0, n, m.conv1_w, m.conv1_b, g.C, g.chunk, bs->a1.as<bf16>(), st);
+        h->launches++;
+        GemmA a;
+        a.ptr = bs->a1.as<bf16>(); a.C = g.C; a.W = g.w1; a.H = 64; a.B = n;
+        a.sW = g.C; a.sH = (long)g.w1 * g.C; a.sB = 64L * g.w1 * g.C;
+        s2.OB = n;
+        GemmEpiArgs e2 = epi_store(bs->a2.p, g.C, m.conv2_b, 1);
+        e2.valid_w = ints + bs->o_vw2 + c0;
+        gemm_conv(a, s2, m.conv2_w, g.C, e2, st);
+        a.ptr = bs->a2.as<bf16>(); a.W = g.w2; a.H = 32;
+        a.sH = (long)g.w2 * g.C; a.sB = 32L * g.w2 * g.C;
+        s3.OB = n;
+        GemmEpiArgs e3 = epi_store(bs->a3.as<bf16>() + (size_t)c0 * 16 * g.w3 * g.C, g.C, m.conv3_b, 1);
+        e3.valid_w = ints + bs->o_vw3 + c0;
+        gemm_conv(a, s3, m.conv3_w, g.C, e3, st);
+    }
+    // ---- conv_out over the [chunk, t, (f, c)] view of the conv3 output, + positions, gather valid tokens ----
+    {
+        GemmA a;
+        a.ptr = bs->a3.as<bf16>(); a.C = g.C; a.W = g.w3; a.H = 16; a.B = bs->n_chunks;
+        a.sW = g.C; a.sH = (long)g.w3 * g.C; a.sB = 16L * g.w3 * g.C;
+        GemmShape s;
+        s.Wb = g.w3; s.Hb = 1; s.Bb = std::max(1, GEMM_BM / g.w3);
+        s.OW = g.w3; s.OH = 1; s.OB = bs->n_chunks;
+        s.sw = 1; s.sh = 1; s.taps = 16;
+        for (int f = 0; f < 16; f++) { s.tap_dw[f] = 0; s.tap_dh[f] = (signed char)f; }
+        GemmEpiArgs e = epi_store(bs->ex.p, d, nullptr);
+        e.row_add = m.pe;
+        e.row_map = ints + bs->o_rowmap;
+        gemm_conv(a, s, m.conv_out_w, d, e, st);
+    }
+    // ---- transformer layers over the packed tokens ----
+    const int T = bs->n_tok;
+    AttnSegs segs{ints + bs->o_win_row0, ints + bs->o_win_len, bs->n_win, bs->max_win};
+    bf16 *x = bs->ex.as<bf16>(), *xn = bs->exn.as<bf16>(), *qkv = bs->eqkv.as<bf16>(), *att = bs->eatt.as<bf16>(),
+         *ffn = bs->effn.as<bf16>();
+    for (int l = 0; l < c.enc_layers; l++) {
+        const EncLayerW& w = m.enc[l];
+        layernorm_launch(x, w.ln1_w, w.ln1_b, xn, T, d, c.enc_ln_eps, st);
+        gemm(xn, d, T, d, w.qkv_w, 3 * d, epi_store(qkv, 3 * d, w.qkv_b), st);
+        flash_attn_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, c.enc_heads, 1, 64, false, 0.125f, st);
+        gemm(att, d, T, d, w.o_w, d, epi_store(x, d, w.o_b, 0, x, d), st);
+        layernorm_launch(x, w.ln2_w, w.ln2_b, xn, T, d, c.enc_ln_eps, st);
+        gemm(xn, d, T, d, w.fc1_w, c.enc_ffn, epi_store(ffn, c.enc_ffn, w.fc1_b, 1), st);
+        gemm(ffn, c.enc_ffn, T, c.enc_ffn, w.fc2_w, d, epi_store(x, d, w.fc2_b, 0, x, d), st);
+        h->launches += 3;
+    }
+    layernorm_launch(x, m.ln_post_w, m.ln_post_b, xn, T, d, c.enc_ln_eps, st);
+    gemm(xn, d, T, d, m.proj1_w, d, epi_store(att, d, m.proj1_b, 1), st);
+    gemm(att, d, T, d, m.proj2_w, c.enc_out_dim, epi_store(bs->audio.p, c.enc_out_dim, m.proj2_b), st);
+    h->launches++;
+    bs->enc_done = true;
+}
+
+KvCache kv_cache(Handle* h, BatchState* bs) {
+    KvCache kc;
+    kc.pool = bs->kv_pool.as<bf16>();
+    kc.page_table = bs->ints.as<int>() + bs->o_page_table;
+    kc.max_pages = bs->pages_per_seq;
+    kc.layers = h->cfg.dec_layers;
+    kc.kv_heads = h->cfg.dec_kv_heads;
+    kc.head_dim = h->cfg.dec_head_dim;
+    return kc;
+}
+
+// rows: packed token rows in bs->dx.  prefill: segs describe the prompts; decode: one row per sequence.
+void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int* ints = bs->ints.as<int>();
+    const int H = c.dec_hidden, hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
+    const float scale = 1.0f / sqrtf((float)hd);
+    bf16 *x = bs->dx.as<bf16>(), *xn = bs->dxn.as<bf16>(), *qkv = bs->dqkv.as<bf16>(), *q = bs->dq.as<bf16>(),
+         *att = bs->datt.as<bf16>(), *act = bs->dact.as<bf16>();
+    const KvCache kc = kv_cache(h, bs);
+    const int* pos = prefill ? ints + bs->o_pos : bs->st_pos.as<int>();
+    const int* row_seq = prefill ? ints + bs->o_row_seq : ints + bs->o_ident;
+    AttnSegs segs{ints + bs->o_seq_row0, ints + bs->o_seq_len, bs->B, bs->max_prompt};
+    for (int l = 0; l < c.dec_layers; l++) {
+        const DecLayerW& w = m.dec[l];
+        rmsnorm_launch(x, w.in_ln, xn, rows, H, c.dec_rms_eps, nullptr, st);
+        gemm(xn, H, rows, H, w.qkv_w, nqkv, epi_store(qkv, nqkv, nullptr), st);
+        qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
+                              c.dec_rope_theta, m.inv_freq, q, prefill ? bs->dkc.as<bf16>() : nullptr,
+                              prefill ? bs->dvc.as<bf16>() : nullptr, kc, l, st);
+        if (prefill)
+            flash_attn_launch(q, nq, bs->dkc.as<bf16>(), nkv, bs->dvc.as<bf16>(), nkv, att, nq, segs, c.dec_heads,
+                              c.dec_heads / c.dec_kv_heads, hd, true, scale, st);
+        else
+            decode_attn_launch(q, kc, l, bs->st_kv_len.as<int>(), rows, c.dec_heads, scale, att, st);
+        gemm(att, nq, rows, nq, w.o_w, H, epi_store(x, H, nullptr, 0, x, H), st);
+        rmsnorm_launch(x, w.post_ln, xn, rows, H, c.dec_rms_eps, nullptr, st);
+        GemmEpiArgs eg;
+        eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
+        gemm(xn, H, rows, H, w.gu_w, 2 * c.dec_inter, eg, st, false, m.gu_bn);
+        gemm(act, c.dec_inter, rows, c.dec_inter, w.down_w, H, epi_store(x, H, nullptr, 0, x, H), st);
+        h->launches += 4;
+    }
+}
+
+// final norm of the given rows + tied LM head + argmax -> st_next_tok / st_next_val
+void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int H = c.dec_hidden, B = bs->B;
+    rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
+    const int bn = gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
+    GemmEpiArgs e;
+    e.epi = EPI_ARGMAX;
+    e.amax_val = bs->amax_val.as<float>();
+    e.amax_idx = bs->amax_idx.as<int>();
+    gemm(bs->dlast.as<bf16>(), H, B, H, m.embed, c.dec_vocab, e, st, false, bn);
+    argmax_reduce(e.amax_val, e.amax_idx, B, c.dec_vocab / bn, bs->st_next_tok.as<int32_t>(), bs->st_next_val.as<float>(), st);
+    h->launches += 2;
+}
+
+DecodeState decode_state(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
+    DecodeState s;
+    s.next_tok = bs->st_next_tok.as<int32_t>();
+    s.next_val = bs->st_next_val.as<float>();
+    s.cur_tok = bs->st_cur_tok.as<int32_t>();
+    s.pos = bs->st_pos.as<int>();
+    s.kv_len = bs->st_kv_len.as<int>();
+    s.out_ids = bs->st_out_ids.as<int32_t>();
+    s.out_val = bs->st_out_val.as<float>();
+    s.out_len = bs->st_out_len.as<int>();
+    s.finished = bs->st_finished.as<int>();
+    s.n_active = bs->st_scalars.as<int>();
+    s.step = bs->st_scalars.as<int>() + 1;
+    s.forced = forced ? bs->st_forced.as<int32_t>() : nullptr;
+    s.max_tokens = bs->max_tokens;
+    s.eos = h->cfg.tok_eos;
+    s.stop_on_eos = stop_on_eos;
+    return s;
+}
+
+void run_prefill(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int* ints = bs->ints.as<int>();
+    const int B = bs->B;
+    embed_splice_launch(ints + bs->o_ids, ints + bs->o_audio_src, m.embed, bs->audio.as<bf16>(), bs->dx.as<bf16>(), bs->R, c.dec_hidden,
+                        st);
+    h->launches++;
+    decoder_layers(h, bs, bs->R, true);
+    // decode state: positions / cache lengths start at the prompt length
+    Q3_CUDA(cudaMemcpyAsync(bs->st_pos.p, ints + bs->o_pos0, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    Q3_CUDA(cudaMemcpyAsync(bs->st_kv_len.p, ints + bs->o_seq_len, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    Q3_CUDA(cudaMemsetAsync(bs->st_out_len.p, 0, sizeof(int) * B, st));
+    Q3_CUDA(cudaMemsetAsync(bs->st_finished.p, 0, sizeof(int) * B, st));
+    Q3_CUDA(cudaMemsetAsync(bs->st_out_ids.p, 0, sizeof(int32_t) * B * std::max(bs->max_tokens, 1), st));
+    const int scal[2] = {B, 0};
+    memcpy(bs->h_out.p, scal, sizeof(scal));
+    Q3_CUDA(cudaMemcpyAsync(bs->st_scalars.p, bs->h_out.p, sizeof(scal), cudaMemcpyHostToDevice, st));
+    lm_head_argmax(h, bs, ints + bs->o_last_row);
+    // step 0 records the first token.  decode_advance increments pos and kv_len, so they start at
+    // prompt_len - 1 / prompt_len and come out as prompt_len (position of the first generated token) and
+    // prompt_len + 1 (keys visible to the first decode step).
+    DecodeState s = decode_state(h, bs, stop_on_eos, forced);
+    decode_advance_launch(s, B, st);
+    h->launches++;
+    bs->prefill_done = true;
+    bs->steps_done = 1;
+}
+
+void decode_step_kernels(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    embed_splice_launch(bs->st_cur_tok.as<int32_t>(), nullptr, m.embed, nullptr, bs->dx.as<bf16>(), bs->B, c.dec_hidden, st);
+    h->launches++;
+    decoder_layers(h, bs, bs->B, false);
+    lm_head_argmax(h, bs, nullptr);
+    decode_advance_launch(decode_state(h, bs, stop_on_eos, forced), bs->B, st);
+    h->launches++;
+}
+
+void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool forced) {
+    cudaStream_t st = h->stream;
+    const bool use_graph = env_int("Q3ASR_NO_GRAPH", 0) == 0;
+    int* h_active = reinterpret_cast<int*>(bs->h_out.p);
+    int step = bs->steps_done;
+    if (step < max_tokens) {  // one eager step: sets function attributes, warms the instruction cache
+        decode_step_kernels(h, bs, stop_on_eos, forced);
+        step++;
+    }
+    if (step < max_tokens && use_graph) {
+        if (bs->step_graph && bs->graph_B != bs->B) {
+            cudaGraphExecDestroy(bs->step_graph);
+            bs->step_graph = nullptr;
+        }
+        // the graph bakes in buffer addresses and flags; rebuild it for every batch (cheap: ~1 ms)
+        if (bs->step_graph) {
+            cudaGraphExecDestroy(bs->step_graph);
+            bs->step_graph = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        const unsigned long long l0 = h->launches;
+        Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            decode_step_kernels(h, bs, stop_on_eos, forced);
+        } catch (...) {
+            cudaStreamEndCapture(st, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        Q3_CUDA(cudaStreamEndCapture(st, &graph));
+        const unsigned long long per_step = h->launches - l0;
+        h->launches = l0;
+        Q3_CUDA(cudaGraphInstantiate(&bs->step_graph, graph, 0));
+        Q3_CUDA(cudaGraphDestroy(graph));
+        bs->graph_B = bs->B;
+        for (; step < max_tokens; step++) {
+            Q3_CUDA(cudaGraphLaunch(bs->step_graph, st));
+            h->launches += per_step;
+            if (stop_on_eos && (step & 15) == 15) {
+                Q3_CUDA(cudaMemcpyAsync(h_active, bs->st_scalars.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                Q3_CUDA(cudaStreamSynchronize(st));
+                if (*h_active <= 0) { step++; break; }
+            }
+        }
+    } else {
+        for (; step < max_tokens; step++) {
+            decode_step_kernels(h, bs, stop_on_eos, forced);
+            if (stop_on_eos && (step & 15) == 15) {
+                Q3_CUDA(cudaMemcpyAsync(h_active, bs->st_scalars.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                Q3_CUDA(cudaStreamSynchronize(st));
+                if (*h_active <= 0) { step++; break; }
+            }
+        }
+    }
+    bs->steps_done = step;
+}
+
+}  // namespace
+
+int encoder_tokens_for(int frames) {
+    // AudioEncoder.swift:287-303 with chunk = 100
+    if (frames <= 0) return 0;
+    const int full = frames / 100, rem = frames % 100;
+    return full * 13 + (rem > 0 ? std::max(conv_len3(rem), 1) : 0);
+}
+
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts) {
+    Q3_CHECK(pcm != nullptr && n != nullptr && batch > 0, Q3ASR_ERR_INVALID, "batch_upload: null argument / empty batch");
+    Q3_CHECK(batch <= 1024, Q3ASR_ERR_INVALID, "batch_upload: at most 1024 utterances per call");
+    for (int b = 0; b < batch; b++)
+        Q3_CHECK(pcm[b] != nullptr && n[b] >= (size_t)MEL_HOP && n[b] < (size_t)1 << 30, Q3ASR_ERR_INVALID,
+                 "batch_upload: every clip needs at least 160 samples (one mel frame)");
+    BatchState* bs = fresh_batch(h);
+    bs->B = batch;
+    bs->mel = mel_plan(n, batch);
+    bs->mel_done = bs->enc_done = bs->prefill_done = false;
+    bs->steps_done = 0;
+    bs->has_audio = true;
+    // samples: pinned staging -> device
+    bs->pcm.reserve(sizeof(float) * (bs->mel.pcm_floats + 64));
+    bs->mel_out.reserve(sizeof(float) * std::max<long long>(bs->mel.out_floats, 1));
+    bs->mel_clips.reserve(sizeof(MelClip) * batch);
+    bs->mel_gmax.reserve(sizeof(int) * batch);
+    bs->mel_tmin.reserve(sizeof(float) * bs->mel.total_tiles);
+    bs->h_stage.reserve(sizeof(float) * bs->mel.pcm_floats);
+    float* stage = bs->h_stage.as<float>();
+    for (int b = 0; b < batch; b++) memcpy(stage + bs->mel.clips[b].in_off, pcm[b], sizeof(float) * n[b]);
+    Q3_CUDA(cudaMemcpyAsync(bs->pcm.p, stage, sizeof(float) * bs->mel.pcm_floats, cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaMemcpyAsync(bs->mel_clips.p, bs->mel.clips.data(), sizeof(MelClip) * batch, cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    // plan
+    std::vector<int> frames(batch);
+    std::vector<long long> mel_off(batch);
+    for (int b = 0; b < batch; b++) {
+        frames[b] = bs->mel.clips[b].frames;
+        mel_off[b] = bs->mel.clips[b].out_off;
+    }
+    std::vector<int> ints;
+    plan_encoder(h, bs, frames, mel_off, &ints);
+    for (int b = 0; b < batch; b++) bs->clips[b].n = (int)n[b];
+    // the decoder plan needs max_tokens for the page reservation; use the largest the API allows by default
+    // and let batch_run re-plan if a larger value is requested
+    const int reserve_tokens = std::max(1, env_int("Q3ASR_RESERVE_TOKENS", 448));
+    plan_decoder(h, bs, prompts, reserve_tokens, &ints);
+    upload_ints(h, bs, ints);
+    bs->prompt_ids.clear();
+}
+
+void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos) {
+    BatchState* bs = h->batch.get();
+    Q3_CHECK(bs != nullptr && bs->B > 0 && bs->has_audio, Q3ASR_ERR_STATE, "batch_run: no batch uploaded");
+    Q3_CHECK(max_tokens >= 0 && max_tokens <= bs->max_tokens, Q3ASR_ERR_INVALID,
+             "batch_run: max_tokens exceeds the reserved decode capacity (Q3ASR_RESERVE_TOKENS, default 448)");
+    if (stages & (Q3ASR_STAGE_ENCODER | Q3ASR_STAGE_PREFILL | Q3ASR_STAGE_DECODE))
+        Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded (q3asr_init_random / q3asr_load_safetensors)");
+    cudaStream_t st = h->stream;
+    Q3_CUDA(cudaEventRecord(bs->ev[0], st));
+    if (stages & Q3ASR_STAGE_MEL) run_mel(h, bs);
+    Q3_CUDA(cudaEventRecord(bs->ev[1], st));
+    if (stages & Q3ASR_STAGE_ENCODER) {
+        Q3_CHECK(bs->mel_done, Q3ASR_ERR_STATE, "batch_run: encoder stage needs the mel stage first");
+        reserve_encoder(h, bs);
+        run_encoder(h, bs, bs->mel_out.as<float>());
+    }
+    Q3_CUDA(cudaEventRecord(bs->ev[2], st));
+    if (stages & Q3ASR_STAGE_PREFILL) {
+        Q3_CHECK(bs->enc_done, Q3ASR_ERR_STATE, "batch_run: prefill stage needs the encoder stage first");
+        reserve_decoder(h, bs);
+        if (max_tokens > 0) run_prefill(h, bs, stop_on_eos, false);
+    }
+    Q3_CUDA(cudaEventRecord(bs->ev[3], st));
+    if ((stages & Q3ASR_STAGE_DECODE) && max_tokens > 1) {
+        Q3_CHECK(bs->prefill_done, Q3ASR_ERR_STATE, "batch_run: decode stage needs the prefill stage first");
+        run_decode(h, bs, max_tokens, stop_on_eos, false);
+    }
+    Q3_CUDA(cudaEventRecord(bs->ev[4], st));
+}
+
+void batch_download(Handle* h, int32_t* ids, int max_tokens, int* lens) {
+    BatchState* bs = h->batch.get();
+    Q3_CHECK(bs != nullptr && bs->B > 0, Q3ASR_ERR_STATE, "batch_download: no batch");
+    Q3_CHECK(ids != nullptr && lens != nullptr && max_tokens >= 0, Q3ASR_ERR_INVALID, "batch_download: bad argument");
+    const int B = bs->B, mt = bs->max_tokens;
+    cudaStream_t st = h->stream;
+    if (!bs->prefill_done) {
+        Q3_CUDA(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; b++) lens[b] = 0;
+    } else {
+        int32_t* h_ids = reinterpret_cast<int32_t*>(bs->h_out.p) + 16;
+        int* h_len = reinterpret_cast<int*>(h_ids + (size_t)B * mt);
+        Q3_CUDA(cudaMemcpyAsync(h_ids, bs->st_out_ids.p, sizeof(int32_t) * B * mt, cudaMemcpyDeviceToHost, st));
+        Q3_CUDA(cudaMemcpyAsync(h_len, bs->st_out_len.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        Q3_CUDA(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; b++) {
+            const int L = std::min(std::min(h_len[b], max_tokens), mt);
+            lens[b] = L;
+            memcpy(ids + (size_t)b * max_tokens, h_ids + (size_t)b * mt, sizeof(int32_t) * L);
+        }
+    }
+    for (int i = 0; i < 4; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, bs->ev[i], bs->ev[i + 1]) == cudaSuccess) h->stage_ms[i] = ms;
+    }
+}
+
+void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens) {
+    Q3_CHECK(mel != nullptr && out != nullptr && frames > 0 && frames <= MEL_MAX_FRAMES, Q3ASR_ERR_INVALID, "encode: bad argument");
+    Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded");
+    BatchState* bs = fresh_batch(h);
+    bs->B = 1;
+    bs->has_audio = false;
+    bs->mel_done = bs->enc_done = bs->prefill_done = false;
+    const size_t nmel = (size_t)MEL_BINS * frames;
+    bs->mel_out.reserve(nmel * 4);
+    bs->h_stage.reserve(nmel * 4);
+    memcpy(bs->h_stage.p, mel, nmel * 4);
+    Q3_CUDA(cudaMemcpyAsync(bs->mel_out.p, bs->h_stage.p, nmel * 4, cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> ints;
+    plan_encoder(h, bs, {frames}, {0}, &ints);
+    upload_ints(h, bs, ints);
+    reserve_encoder(h, bs);
+    run_encoder(h, bs, bs->mel_out.as<float>());
+    const size_t n = (size_t)bs->n_tok * h->cfg.enc_out_dim;
+    bs->logits.reserve(std::max<size_t>(n, 1) * 4);
+    bf16_to_f32_launch(bs->audio.as<bf16>(), bs->logits.as<float>(), n, h->stream);
+    h->launches++;
+    bs->h_stage.reserve(std::max<size_t>(n, 1) * 4);
+    Q3_CUDA(cudaMemcpyAsync(bs->h_stage.p, bs->logits.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(out, bs->h_stage.p, n * 4);
+    if (tokens) *tokens = bs->n_tok;
+}
+
+void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
+                   int32_t* argmax_out, float* top_out) {
+    Q3_CHECK(forced != nullptr && n_forced >= 0 && argmax_out != nullptr, Q3ASR_ERR_INVALID, "decode_forced: bad argument");
+    Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded");
+    const float* pp[1] = {pcm};
+    batch_upload(h, pp, &n, 1, prompt);
+    BatchState* bs = h->batch.get();
+    const int steps = n_forced + 1;
+    Q3_CHECK(steps <= bs->max_tokens, Q3ASR_ERR_INVALID, "decode_forced: too many forced tokens");
+    for (int i = 0; i < n_forced; i++) Q3_CHECK(forced[i] >= 0 && forced[i] < h->cfg.dec_vocab, Q3ASR_ERR_INVALID, "forced id out of range");
+    cudaStream_t st = h->stream;
+    run_mel(h, bs);
+    reserve_encoder(h, bs);
+    run_encoder(h, bs, bs->mel_out.as<float>());
+    reserve_decoder(h, bs);
+    std::vector<int32_t> f(forced, forced + n_forced);
+    f.push_back(0);
+    bs->st_forced.reserve(f.size() * 4);
+    Q3_CUDA(cudaMemcpy(bs->st_forced.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    run_prefill(h, bs, 0, true);
+    run_decode(h, bs, steps, 0, true);
+    std::vector<int32_t> ids((size_t)bs->max_tokens);
+    std::vector<float> vals((size_t)bs->max_tokens);
+    Q3_CUDA(cudaStreamSynchronize(st));
+    Q3_CUDA(cudaMemcpy(ids.data(), bs->st_out_ids.p, ids.size() * 4, cudaMemcpyDeviceToHost));
+    Q3_CUDA(cudaMemcpy(vals.data(), bs->st_out_val.p, vals.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < steps; i++) {
+        argmax_out[i] = ids[i];
+        if (top_out) top_out[i] = vals[i];
+    }
+}
+
+void prefill_logits(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits) {
+    Q3_CHECK(logits != nullptr, Q3ASR_ERR_INVALID, "prefill_logits: null output");
+    Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded");
+    const float* pp[1] = {pcm};
+    batch_upload(h, pp, &n, 1, prompt);
+    BatchState* bs = h->batch.get();
+    const q3asr_config& c = h->cfg;
+    cudaStream_t st = h->stream;
+    run_mel(h, bs);
+    reserve_encoder(h, bs);
+    run_encoder(h, bs, bs->mel_out.as<float>());
+    reserve_decoder(h, bs);
+    run_prefill(h, bs, 0, false);
+    // dlast holds the normed last hidden state; full-vocabulary fp32 logits through the same GEMM
+    bs->logits.reserve((size_t)c.dec_vocab * 4);
+    GemmEpiArgs e;
+    e.epi = EPI_F32;
+    e.out = bs->logits.p;
+    e.ldo = c.dec_vocab;
+    gemm(bs->dlast.as<bf16>(), c.dec_hidden, 1, c.dec_hidden, h->model->embed, c.dec_vocab, e, st);
+    Q3_CUDA(cudaStreamSynchronize(st));
+    Q3_CUDA(cudaMemcpy(logits, bs->logits.p, (size_t)c.dec_vocab * 4, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace q3

@@ -1,0 +1,379 @@
+// gemm.cuh — bf16 tensor-core GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[rows, N] = A[rows, K] · W[N, K]^T      (both operands K-major, fp32 accumulation in TMEM)
+//
+// Replaces the reference's MLX `Linear`, `Conv2d` and tied-embedding `asLinear` calls on the hot path:
+//   Sources/Qwen3ASR/AudioEncoder.swift:117-124,157-159,409-427,506-508
+//   Sources/Qwen3ASR/FloatTextDecoder.swift:77-79,107,128-132
+//   Sources/MLXCommon/PreQuantizedEmbedding.swift:45-49 (LM head, fused argmax)
+//
+// Structure (persistent, one CTA per SM, 256 threads):
+//   warp 0    TMA producer     cp.async.bulk.tensor (4-D A boxes, 2-D W boxes), 128B swizzle, mbarrier ring
+//   warp 1    MMA issuer       one lane issues tcgen05.mma (M=128, N=BN, K=16), commits to mbarriers
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue         tcgen05.ld 32x32b -> registers -> bias/PE/GELU/residual/SwiGLU/argmax -> global
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// The A operand is always described by a 4-D tensor map {c, w, h, b}.  A plain GEMM is the degenerate
+// case {K, M, 1, 1}.  A convolution (NHWC activations, [O][kh][kw][I] weights) is run as an implicit GEMM:
+// the M tile is a box of output positions (Wb x Hb x Bb <= 128), each k-block is (tap, 64-channel chunk),
+// and the producer shifts the box origin by the tap offset; out-of-image taps are zero-filled by TMA,
+// the input stride (2) is the tensor map's element stride.  Channel counts that are not multiples of
+// 64 (480) are handled by issuing fewer K=16 MMA steps for the last chunk of a tap.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace q3 {
+
+enum GemmEpi : int {
+    EPI_NORMAL = 0,  // out(bf16) = [resid +] bf16( act(acc + bias + row_add) ), optional zero mask / row map
+    EPI_SWIGLU = 1,  // tile cols [0,BN/2) gate, [BN/2,BN) up: out = bf16( bf16(silu(bf16 g)) * bf16 u )
+    EPI_F32 = 2,     // out(fp32) = acc + bias
+    EPI_ARGMAX = 3,  // per (row, n-tile): max / lowest index of bf16(acc)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_MAX_TAPS = 16;
+
+struct GemmDev {  // by-value kernel parameter
+    int N, num_kb, kb_per_tap, C;
+    int tiles_n, tiles_w, tiles_h, tiles_b;
+    int Wb, Hb, Bb;
+    int OW, OH, OB;
+    int sw, sh;
+    signed char tap_dw[GEMM_MAX_TAPS], tap_dh[GEMM_MAX_TAPS];
+    void* out;
+    int ldo;
+    const bf16* bias;      // [N] or null
+    const bf16* resid;     // [rows, ldr] or null (indexed by the destination row)
+    int ldr;
+    const float* row_add;  // [OW, N] fp32 or null (sinusoidal positions, indexed by w)
+    const int* row_map;    // [rows] destination row or -1, or null (identity)
+    const int* valid_w;    // [OB] columns w >= valid_w[b] are stored as zero, or null
+    int gelu;
+    float* amax_val;       // [rows, tiles_n]
+    int* amax_idx;
+};
+
+__host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
+__host__ __device__ constexpr int gemm_stage_bytes(int BN) { return GEMM_BM * 128 + BN * 128; }
+__host__ __device__ constexpr int gemm_stages(int BN) {
+    return (196 * 1024) / gemm_stage_bytes(BN) > 8 ? 8 : (196 * 1024) / gemm_stage_bytes(BN);
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int BN) { return gemm_stages(BN) * gemm_stage_bytes(BN) + 1024 + 256; }
+
+__device__ __forceinline__ float epi_swiglu(float g_acc, float u_acc) {
+    const float g = bf16_round(g_acc);
+    const float s = bf16_round(silu(g));
+    const float u = bf16_round(u_acc);
+    return s * u;  // caller rounds to bf16 on store
+}
+
+struct TileCoord {
+    int tn, w0, h0, b0;
+};
+__device__ __forceinline__ TileCoord gemm_tile_coord(const GemmDev& p, int tile) {
+    TileCoord t;
+    t.tn = tile % p.tiles_n;
+    int r = tile / p.tiles_n;
+    t.w0 = (r % p.tiles_w) * p.Wb;
+    r /= p.tiles_w;
+    t.h0 = (r % p.tiles_h) * p.Hb;
+    t.b0 = (r / p.tiles_h) * p.Bb;
+    return t;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+    constexpr int STAGES = gemm_stages(BN);
+    constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
+    constexpr int ACC_STRIDE = gemm_acc_stride(BN);
+    constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(GEMM_BM, BN);
+    static_assert(BN % 32 == 0 && BN <= 256, "BN");
+    static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512, "tmem");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_b;
+    const int tile_rows = p.Wb * p.Hb * p.Bb;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(tile_rows * 128 + BN * 128);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const TileCoord tc = gemm_tile_coord(p, tile);
+                const int n0 = tc.tn * BN;
+                int tap = 0, cc = 0;
+                for (int kb = 0; kb < p.num_kb; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + GEMM_BM * 128;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    ptx::tma_load_4d(sa, &tmA, cc * GEMM_BK, tc.w0 * p.sw + p.tap_dw[tap], tc.h0 * p.sh + p.tap_dh[tap],
+                                     tc.b0, &full_bar[stage]);
+                    ptx::tma_load_2d(sb, &tmB, tap * p.C + cc * GEMM_BK, n0, &full_bar[stage]);
+                    if (++cc == p.kb_per_tap) { cc = 0; tap++; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            const int last_steps = (p.C - (p.kb_per_tap - 1) * GEMM_BK + 15) >> 4;  // K=16 steps in a tap's last chunk
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+                int cc = 0;
+                for (int kb = 0; kb < p.num_kb; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + GEMM_BM * 128;
+                    const int steps = (cc == p.kb_per_tap - 1) ? last_steps : GEMM_BK / 16;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; k++) {
+                        if (k < steps) {
+                            const uint64_t da = ptx::umma_desc_sw128(sa + k * 32);
+                            const uint64_t db = ptx::umma_desc_sw128(sb + k * 32);
+                            ptx::mma_bf16_ss(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++cc == p.kb_per_tap) cc = 0;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const TileCoord tc = gemm_tile_coord(p, tile);
+            const int n0 = tc.tn * BN;
+            const int r = q * 32 + lane;
+            const int w = tc.w0 + r % p.Wb;
+            const int h = tc.h0 + (r / p.Wb) % p.Hb;
+            const int b = tc.b0 + r / (p.Wb * p.Hb);
+            bool row_ok = r < tile_rows && w < p.OW && h < p.OH && b < p.OB;
+            long row = row_ok ? ((long)b * p.OH + h) * p.OW + w : 0;
+            bool zero = false;
+            if (row_ok && p.valid_w != nullptr) zero = w >= __ldg(p.valid_w + b);
+            if (row_ok && p.row_map != nullptr) {
+                row = __ldg(p.row_map + row);
+                row_ok = row >= 0;
+            }
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
+
+            if constexpr (EPI == EPI_SWIGLU) {
+                constexpr int HALF = BN / 2;
+                bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * HALF;
+#pragma unroll 1
+                for (int c = 0; c < HALF / 16; c++) {
+                    uint32_t g[16], u[16];
+                    ptx::tmem_ld_32x16(t_row + c * 16, g);
+                    ptx::tmem_ld_32x16(t_row + HALF + c * 16, u);
+                    ptx::tmem_ld_wait();
+                    if (row_ok) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float a = epi_swiglu(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
+                            const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
+                            pk[j] = pack_bf16x2(a, bb);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
+                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            } else if constexpr (EPI == EPI_ARGMAX) {
+                float best = -INFINITY;
+                int best_i = 0;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_row + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float x = bf16_round(__uint_as_float(v[j]));
+                        if (x > best) { best = x; best_i = n0 + c * 32 + j; }
+                    }
+                }
+                if (row_ok) {
+                    p.amax_val[(size_t)row * p.tiles_n + tc.tn] = best;
+                    p.amax_idx[(size_t)row * p.tiles_n + tc.tn] = best_i;
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_row + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    if (row_ok) {
+                        const int col = n0 + c * 32;
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+                        if (p.bias != nullptr) {
+                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint4 bv = __ldg(bp + j);
+                                float2 t;
+                                t = unpack_bf16x2(bv.x); f[8 * j + 0] += t.x; f[8 * j + 1] += t.y;
+                                t = unpack_bf16x2(bv.y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
+                                t = unpack_bf16x2(bv.z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
+                                t = unpack_bf16x2(bv.w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
+                            }
+                        }
+                        if constexpr (EPI == EPI_F32) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+                            if (p.row_add != nullptr) {
+                                const float4* ap = reinterpret_cast<const float4*>(p.row_add + (size_t)w * p.N + col);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const float4 a = __ldg(ap + j);
+                                    f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
+                                }
+                            }
+                            if (p.gelu) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) f[j] = gelu_erf(f[j]);
+                            }
+                            if (zero) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) f[j] = 0.f;
+                            }
+                            if (p.resid != nullptr) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const uint4 rv = __ldg(rp + j);
+                                    float2 t;
+                                    t = unpack_bf16x2(rv.x); f[8 * j + 0] = t.x + bf16_round(f[8 * j + 0]); f[8 * j + 1] = t.y + bf16_round(f[8 * j + 1]);
+                                    t = unpack_bf16x2(rv.y); f[8 * j + 2] = t.x + bf16_round(f[8 * j + 2]); f[8 * j + 3] = t.y + bf16_round(f[8 * j + 3]);
+                                    t = unpack_bf16x2(rv.z); f[8 * j + 4] = t.x + bf16_round(f[8 * j + 4]); f[8 * j + 5] = t.y + bf16_round(f[8 * j + 5]);
+                                    t = unpack_bf16x2(rv.w); f[8 * j + 6] = t.x + bf16_round(f[8 * j + 6]); f[8 * j + 7] = t.y + bf16_round(f[8 * j + 7]);
+                                }
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col);
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host API (gemm.cu)
+// ---------------------------------------------------------------------------------------------
+struct GemmA {               // activation operand as a 4-D {c, w, h, b} view, element strides (bf16 units)
+    const bf16* ptr = nullptr;
+    int C = 0, W = 1, H = 1, B = 1;
+    long sW = 0, sH = 0, sB = 0;   // strides of w, h, b in elements (c is contiguous)
+};
+struct GemmShape {           // how output rows map onto the view, and the k-block program
+    int Wb = 128, Hb = 1, Bb = 1;  // M-tile box in output positions
+    int OW = 0, OH = 1, OB = 1;    // output extents
+    int sw = 1, sh = 1;            // input step per output step
+    int taps = 1;
+    signed char tap_dw[GEMM_MAX_TAPS] = {0}, tap_dh[GEMM_MAX_TAPS] = {0};
+};
+struct GemmEpiArgs {
+    int epi = EPI_NORMAL;
+    void* out = nullptr;
+    int ldo = 0;
+    const bf16* bias = nullptr;
+    const bf16* resid = nullptr;
+    int ldr = 0;
+    const float* row_add = nullptr;
+    const int* row_map = nullptr;
+    const int* valid_w = nullptr;
+    int gelu = 0;
+    float* amax_val = nullptr;
+    int* amax_idx = nullptr;
+};
+
+void gemm_init(int device);  // resolves cuTensorMapEncodeTiled, sets smem attributes, reads the SM count
+int gemm_pick_bn(int N, int epi);
+int gemm_pick_bn(int N, int epi, long m_tiles);
+// General form.  W is [N, taps*C] row-major bf16.  `simt` runs the CUDA-core checker kernel instead
+// (tests only: bisects tensor-core bugs; never used by the model code).
+void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const GemmEpiArgs& e, cudaStream_t st,
+               bool simt = false, int bn = 0);
+// Plain C[M,N] = A[M,K](lda) W[N,K]^T
+void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const GemmEpiArgs& e, cudaStream_t st,
+          bool simt = false, int bn = 0);
+unsigned long long gemm_launch_count();
+// final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
+void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st);
+
+}  // namespace q3

@@ -1,0 +1,151 @@
+// handle.h — the object behind q3asr_handle: device, stream, constant tables, weights, work buffers.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/q3asr.h"
+#include "common.cuh"
+#include "mel.cuh"
+
+namespace q3 {
+
+// growable device buffer (capacity only ever grows; contents are scratch)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    size_t* total = nullptr;  // accounting (bytes held by the handle)
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) {
+            Q3_CUDA(cudaFree(p));
+            if (total) *total -= cap;
+            p = nullptr;
+            cap = 0;
+        }
+        bytes = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(Q3ASR_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        }
+        cap = bytes;
+        if (total) *total += cap;
+    }
+    void release() {
+        if (p) {
+            cudaFree(p);
+            if (total) *total -= cap;
+        }
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// pinned host staging buffer
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(Q3ASR_ERR_NOMEM, std::string("cudaMallocHost(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        }
+        cap = bytes;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Tensor {
+    std::string name;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+    bf16* d = nullptr;  // canonical copy, bf16, device
+};
+
+struct Model;      // weights in kernel-ready layouts (model.cu)
+struct BatchState; // resident batch: plan + activations (model.cu)
+
+struct Handle {
+    q3asr_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    size_t dev_bytes = 0;          // bytes held in DevBufs + tensors
+    unsigned long long launches = 0;  // kernels launched by this handle (non-GEMM; GEMMs are counted in gemm.cu)
+    unsigned long long gemm_base = 0;
+
+    MelTables mel_tables{};
+    bool mel_ready = false;
+    // mel scratch
+    DevBuf mel_pcm, mel_out, mel_clips, mel_gmax, mel_tmin;
+    HostBuf mel_stage;
+
+    std::vector<Tensor> tensors;            // canonical named weights
+    std::map<std::string, int> tensor_index;
+    bool loaded = false;
+    std::unique_ptr<Model> model;
+    std::unique_ptr<BatchState> batch;
+
+    cudaEvent_t timer[16] = {nullptr};
+    float stage_ms[4] = {0, 0, 0, 0};
+    DevBuf flush_buf;
+
+    Handle() {
+        for (DevBuf* b : {&mel_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &flush_buf}) b->total = &dev_bytes;
+    }
+};
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) Q3_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+// ---- mel front (frontend.cu) ----
+struct MelPlan {
+    std::vector<MelClip> clips;
+    long long pcm_floats = 0, out_floats = 0;
+    int total_tiles = 0;
+};
+MelPlan mel_plan(const size_t* n_samples, int batch);
+int mel_frames_for(size_t n);
+
+// ---- model (model.cu) ----
+void model_tensor_specs(const q3asr_config& c, std::vector<std::pair<std::string, std::vector<int64_t>>>* out);
+void model_init_random(Handle* h, uint64_t seed);
+void model_set_tensor(Handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+void model_get_tensor(const Handle* h, const char* name, float* out, size_t n);
+void model_commit(Handle* h);
+void model_unload(Handle* h);
+void model_load_safetensors(Handle* h, const char* dir);
+int encoder_tokens_for(int frames);
+
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts);
+void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos);
+void batch_download(Handle* h, int32_t* ids, int max_tokens, int* lens);
+void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens);
+void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
+                   int32_t* argmax_out, float* top_out);
+void prefill_logits(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits);
+void config_validate(const q3asr_config& c);
+
+}  // namespace q3

@@ -1,0 +1,110 @@
+// model.h — kernel-ready weights and the resident-batch state of one handle.
+#pragma once
+#include "gemm.cuh"
+#include "handle.h"
+#include "ops.cuh"
+
+namespace q3 {
+
+struct EncLayerW {
+    bf16 *ln1_w, *ln1_b, *qkv_w, *qkv_b, *o_w, *o_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+struct DecLayerW {
+    bf16 *in_ln, *qkv_w, *q_norm, *k_norm, *o_w, *post_ln, *gu_w, *down_w;
+};
+
+struct Model {
+    // encoder
+    bf16 *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b, *conv_out_w;
+    std::vector<EncLayerW> enc;
+    bf16 *ln_post_w, *ln_post_b, *proj1_w, *proj1_b, *proj2_w, *proj2_b;
+    float* pe = nullptr;  // [tokens per chunk][d_model] sinusoidal positions, fp32
+    // decoder
+    bf16* embed;
+    std::vector<DecLayerW> dec;
+    bf16* final_norm;
+    float* inv_freq = nullptr;  // [head_dim/2]
+    int gu_bn = 128;            // tile width the gate/up rows are interleaved for
+    std::vector<void*> owned;   // derived device buffers
+    size_t owned_bytes = 0;
+};
+
+// geometry derived from the config
+struct Geom {
+    int chunk;       // frames per conv chunk (2 * n_window = 100)
+    int w1, w2, w3;  // conv output widths of a full chunk (50, 25, 13)
+    int tpc;         // tokens per full chunk (= w3)
+    int win_mult;    // n_window_infer / chunk (8)
+    int C;           // conv channels
+    explicit Geom(const q3asr_config& c) {
+        chunk = 2 * c.enc_n_window;
+        w1 = (chunk - 1) / 2 + 1;
+        w2 = (w1 - 1) / 2 + 1;
+        w3 = (w2 - 1) / 2 + 1;
+        tpc = w3;
+        win_mult = c.enc_n_window_infer / chunk;
+        C = c.enc_conv_ch;
+    }
+};
+inline int conv_len(int x) { return (x - 1) / 2 + 1; }
+inline int conv_len3(int x) { return conv_len(conv_len(conv_len(x))); }
+
+struct ClipInfo {
+    int n = 0, frames = 0;
+    int chunk0 = 0, nchunks = 0;
+    int tok0 = 0, ntok = 0;
+    int win_size = 0;
+    int row0 = 0, prompt_len = 0, audio_at = 0;
+};
+
+struct BatchState {
+    int B = 0;
+    MelPlan mel;
+    std::vector<ClipInfo> clips;
+    std::vector<int32_t> prompt_ids;  // packed
+    int n_chunks = 0, n_tok = 0, n_win = 0, max_win = 0;
+    int R = 0, max_prompt = 0;
+    int max_tokens = 0;      // decode capacity the KV pages were reserved for
+    int pages_per_seq = 0;
+    bool has_audio = false, mel_done = false, enc_done = false, prefill_done = false;
+    int steps_done = 0;
+
+    // device buffers
+    DevBuf pcm, mel_out, mel_clips, mel_gmax, mel_tmin;
+    DevBuf ints;  // all small int arrays, one upload
+    // offsets into `ints` (in ints)
+    size_t o_conv_chunks = 0;  // Conv1Chunk[] (as bytes, see model.cu)
+    size_t o_vw1 = 0, o_vw2 = 0, o_vw3 = 0, o_rowmap = 0, o_win_row0 = 0, o_win_len = 0;
+    size_t o_ids = 0, o_audio_src = 0, o_pos = 0, o_row_seq = 0, o_seq_row0 = 0, o_seq_len = 0, o_last_row = 0, o_page_table = 0,
+           o_ident = 0, o_pos0 = 0;
+    DevBuf a1, a2, a3, ex, exn, eqkv, eatt, effn, audio;        // encoder activations
+    DevBuf dx, dxn, dqkv, dq, dkc, dvc, datt, dact, dlast;      // decoder activations
+    DevBuf kv_pool;
+    DevBuf amax_val, amax_idx, logits;
+    // decode state (device)
+    DevBuf st_next_tok, st_next_val, st_cur_tok, st_pos, st_kv_len, st_out_ids, st_out_val, st_out_len, st_finished, st_scalars, st_forced;
+    HostBuf h_stage, h_out;
+    cudaGraphExec_t step_graph = nullptr;
+    int graph_B = 0;
+    cudaEvent_t ev[5] = {nullptr};
+
+    void bind(size_t* total) {
+        for (DevBuf* b : all()) b->total = total;
+    }
+    std::vector<DevBuf*> all() {
+        return {&pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
+                &dx, &dxn, &dqkv, &dq, &dkc, &dvc, &datt, &dact, &dlast, &kv_pool, &amax_val, &amax_idx, &logits,
+                &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
+                &st_scalars, &st_forced};
+    }
+    ~BatchState() {
+        for (DevBuf* b : all()) b->release();
+        h_stage.release();
+        h_out.release();
+        if (step_graph) cudaGraphExecDestroy(step_graph);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
+}  // namespace q3

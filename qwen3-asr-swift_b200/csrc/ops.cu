@@ -1,0 +1,459 @@
+// ops.cu — CUDA-core kernels around the GEMMs: conv2d1, LayerNorm, RMSNorm, embedding gather/splice,
+// q/k-norm + RoPE + KV-cache write, paged decode attention, greedy bookkeeping, dtype/init helpers.
+// Reductions are warp-shuffle based (one warp per row / per head).
+#include "ops.cuh"
+
+namespace q3 {
+
+namespace {
+
+__device__ __forceinline__ uint2 ld8(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void st8(bf16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+
+// ------------------------------------------------------------------------------------------
+// conv2d1 + GELU.  grid (64 output rows, chunks); thread = one output-channel pair, loops over columns.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ mel, const Conv1Chunk* __restrict__ chunks,
+                                                    const bf16* __restrict__ w, const bf16* __restrict__ bias, int C, int chunk_w,
+                                                    bf16* __restrict__ out) {
+    extern __shared__ float s_in[];  // [3][chunk_w + 2]
+    const int oh = blockIdx.x, g = blockIdx.y;
+    const Conv1Chunk c = chunks[g];
+    const int pitch = chunk_w + 2;
+    for (int i = threadIdx.x; i < 3 * pitch; i += blockDim.x) {
+        const int r = i / pitch, j = i % pitch - 1;  // input column j in [-1, chunk_w]
+        const int ih = 2 * oh + r - 1;
+        float v = 0.f;
+        if (ih >= 0 && ih < 128 && j >= 0 && j < c.len) v = __ldg(mel + c.mel_off + (long long)ih * c.T + c.f0 + j);
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int OW = chunk_w / 2;
+    const int w1 = (c.w0 - 1) / 2 + 1;  // valid output columns of this chunk
+    bf16* orow = out + ((size_t)g * 64 + oh) * OW * C;
+    for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
+        float wa[9], wb[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            wa[t] = __bfloat162float(w[(2 * cp) * 9 + t]);
+            wb[t] = __bfloat162float(w[(2 * cp + 1) * 9 + t]);
+        }
+        const float ba = __bfloat162float(bias[2 * cp]), bb = __bfloat162float(bias[2 * cp + 1]);
+        for (int ow = 0; ow < OW; ow++) {
+            float a = 0.f, b = 0.f;
+            if (ow < w1) {
+                a = ba;
+                b = bb;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const float x = s_in[r * pitch + 2 * ow + q];  // column 2*ow + q - 1, stored at +1
+                        a = fmaf(x, wa[r * 3 + q], a);
+                        b = fmaf(x, wb[r * 3 + q], b);
+                    }
+                a = gelu_erf(a);
+                b = gelu_erf(b);
+            }
+            *reinterpret_cast<uint32_t*>(orow + (size_t)ow * C + 2 * cp) = pack_bf16x2(a, b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm: one warp per row, 4 elements per lane per step (8-byte loads).
+// ------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                        const bf16* __restrict__ b, bf16* __restrict__ y, int rows, int d, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = d >> 7;
+    const bf16* xr = x + (size_t)row * d;
+    float v[MAXV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+        if (i < nv) {
+            const uint2 u = ld8(xr + i * 128 + lane * 4);
+            const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+            v[i][0] = a.x; v[i][1] = a.y; v[i][2] = c.x; v[i][3] = c.y;
+            s += (a.x + a.y) + (c.x + c.y);
+        }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+        if (i < nv) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float t = v[i][j] - mean;
+                q = fmaf(t, t, q);
+            }
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+    bf16* yr = y + (size_t)row * d;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+        if (i < nv) {
+            const int c0 = i * 128 + lane * 4;
+            const uint2 wu = ld8(w + c0), bu = ld8(b + c0);
+            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y), b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y);
+            st8(yr + c0, fmaf((v[i][0] - mean) * rstd, w0.x, b0.x), fmaf((v[i][1] - mean) * rstd, w0.y, b0.y),
+                fmaf((v[i][2] - mean) * rstd, w1.x, b1.x), fmaf((v[i][3] - mean) * rstd, w1.y, b1.y));
+        }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                      int rows, int d, float eps, const int* __restrict__ row_index) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = d >> 7;
+    const int src = row_index ? row_index[row] : row;
+    const bf16* xr = x + (size_t)src * d;
+    float v[MAXV][4];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+        if (i < nv) {
+            const uint2 u = ld8(xr + i * 128 + lane * 4);
+            const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+            v[i][0] = a.x; v[i][1] = a.y; v[i][2] = c.x; v[i][3] = c.y;
+            q = fmaf(a.x, a.x, q); q = fmaf(a.y, a.y, q); q = fmaf(c.x, c.x, q); q = fmaf(c.y, c.y, q);
+        }
+    const float r = rsqrtf(warp_sum(q) / (float)d + eps);
+    bf16* yr = y + (size_t)row * d;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+        if (i < nv) {
+            const int c0 = i * 128 + lane * 4;
+            const uint2 wu = ld8(w + c0);
+            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+            st8(yr + c0, v[i][0] * r * w0.x, v[i][1] * r * w0.y, v[i][2] * r * w1.x, v[i][3] * r * w1.y);
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const int* __restrict__ audio_src, const bf16* __restrict__ embed,
+                                    const bf16* __restrict__ audio, bf16* __restrict__ x, int rows, int h) {
+    const int vec = h >> 3;  // 16-byte vectors per row
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)rows * vec) return;
+    const int r = (int)(idx / vec), c = (int)(idx % vec);
+    const int a = audio_src ? audio_src[r] : -1;
+    const bf16* src = a >= 0 ? audio + (size_t)a * h : embed + (size_t)ids[r] * h;
+    reinterpret_cast<uint4*>(x + (size_t)r * h)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+}
+
+// ------------------------------------------------------------------------------------------
+// q/k RMSNorm + RoPE + KV write.  One warp per (row, head slot); head_dim == 128 (4 dims per lane).
+// slots [0, heads) = q, [heads, heads+kvh) = k, [heads+kvh, heads+2kvh) = v.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw,
+                                                            const bf16* __restrict__ kw, const int* __restrict__ pos,
+                                                            const int* __restrict__ row_seq, int rows, int heads, int kv_heads, float eps,
+                                                            const float* __restrict__ inv_freq, bf16* __restrict__ qout,
+                                                            bf16* __restrict__ kc, bf16* __restrict__ vc, KvCache cache, int layer) {
+    const int slots = heads + 2 * kv_heads;
+    const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long)rows * slots) return;
+    const int row = (int)(wid / slots), slot = (int)(wid % slots);
+    const int lane = threadIdx.x & 31;
+    const int d0 = lane * 4;
+    const uint2 u = ld8(qkv + (size_t)row * ld + slot * 128 + d0);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    float x[4] = {a.x, a.y, b.x, b.y};
+    const int p = pos[row];
+    const bool is_v = slot >= heads + kv_heads;
+    if (!is_v) {
+        float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
+        const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
+        const bf16* wv = slot < heads ? qw : kw;
+        const uint2 wu = ld8(wv + d0);
+        const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+        x[0] = bf16_round(x[0] * r * w0.x);
+        x[1] = bf16_round(x[1] * r * w0.y);
+        x[2] = bf16_round(x[2] * r * w1.x);
+        x[3] = bf16_round(x[3] * r * w1.y);
+        // split-half rotation: dims (i, i+64); the partner values live in lane ^ 16
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
+        const int i0 = d0 & 63;
+        const float sgn = lane < 16 ? -1.f : 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float sn, cs;
+            sincosf((float)p * __ldg(inv_freq + i0 + j), &sn, &cs);
+            x[j] = fmaf(x[j], cs, sgn * y[j] * sn);
+        }
+    }
+    if (slot < heads) {
+        st8(qout + (size_t)row * heads * 128 + slot * 128 + d0, x[0], x[1], x[2], x[3]);
+        return;
+    }
+    const int kvh = is_v ? slot - heads - kv_heads : slot - heads;
+    bf16* cont = is_v ? vc : kc;
+    if (cont) st8(cont + (size_t)row * kv_heads * 128 + kvh * 128 + d0, x[0], x[1], x[2], x[3]);
+    const int seq = row_seq[row];
+    const int page = cache.page_table[(size_t)seq * cache.max_pages + p / KV_PAGE];
+    bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (is_v ? 1 : 0)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
+                (p % KV_PAGE) * 128 + d0;
+    st8(dst, x[0], x[1], x[2], x[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Paged decode attention: one CTA per (sequence, kv head), 4 warps; a warp scores 4 keys at a time
+// (8 lanes x 16 dims each), online softmax per lane group, groups merged through shared memory.
+// ------------------------------------------------------------------------------------------
+template <int GROUP>
+__global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict__ q, KvCache cache, int layer,
+                                                         const int* __restrict__ kv_len, int heads, float scale_log2,
+                                                         bf16* __restrict__ out) {
+    const int seq = blockIdx.x, kvh = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, sub = lane & 7;  // key slot within the warp, 16-dim slice
+    const int len = kv_len[seq];
+    float qf[GROUP][16];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        const bf16* qp = q + ((size_t)seq * heads + kvh * GROUP + g) * 128 + sub * 16;
+        const uint4 u0 = *reinterpret_cast<const uint4*>(qp), u1 = *reinterpret_cast<const uint4*>(qp + 8);
+        const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float2 f = unpack_bf16x2(w[j]);
+            qf[g][2 * j] = f.x;
+            qf[g][2 * j + 1] = f.y;
+        }
+    }
+    float m[GROUP], l[GROUP], acc[GROUP][16];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        m[g] = -INFINITY;
+        l[g] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[g][j] = 0.f;
+    }
+    const int* pt = cache.page_table + (size_t)seq * cache.max_pages;
+    for (int j0 = warp * 4; j0 < len; j0 += 16) {
+        const int j = j0 + grp;
+        const bool ok = j < len;
+        float kf[16], vf[16];
+        if (ok) {
+            const int page = pt[j / KV_PAGE];
+            const bf16* kp = cache.pool + ((((size_t)page * cache.layers + layer) * 2) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
+                             (j % KV_PAGE) * 128 + sub * 16;
+            const bf16* vp = kp + (size_t)cache.kv_heads * (KV_PAGE * 128);
+            const uint4 k0 = *reinterpret_cast<const uint4*>(kp), k1 = *reinterpret_cast<const uint4*>(kp + 8);
+            const uint4 v0 = *reinterpret_cast<const uint4*>(vp), v1 = *reinterpret_cast<const uint4*>(vp + 8);
+            const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const float2 a = unpack_bf16x2(kw[t]), b = unpack_bf16x2(vw[t]);
+                kf[2 * t] = a.x; kf[2 * t + 1] = a.y;
+                vf[2 * t] = b.x; vf[2 * t + 1] = b.y;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 16; t++) { kf[t] = 0.f; vf[t] = 0.f; }
+        }
+#pragma unroll
+        for (int g = 0; g < GROUP; g++) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t++) s = fmaf(qf[g][t], kf[t], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s = ok ? s * scale_log2 : -INFINITY;
+            const float mn = fmaxf(m[g], s);
+            const float alpha = mn == -INFINITY ? 1.f : exp2f(m[g] - mn);
+            const float pj = mn == -INFINITY ? 0.f : exp2f(s - mn);
+            l[g] = l[g] * alpha + pj;
+            const float pb = bf16_round(pj);
+#pragma unroll
+            for (int t = 0; t < 16; t++) acc[g][t] = fmaf(pb, vf[t], acc[g][t] * alpha);
+            m[g] = mn;
+        }
+    }
+    // merge the 16 (warp, group) partials per head
+    __shared__ float s_m[GROUP][16], s_l[GROUP][16];
+    __shared__ float s_acc[GROUP][16][128];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        if (sub == 0) { s_m[g][warp * 4 + grp] = m[g]; s_l[g][warp * 4 + grp] = l[g]; }
+#pragma unroll
+        for (int t = 0; t < 16; t++) s_acc[g][warp * 4 + grp][sub * 16 + t] = acc[g][t];
+    }
+    __syncthreads();
+    for (int g = 0; g < GROUP; g++) {
+        const int d = threadIdx.x;  // 128 threads = 128 dims
+        float mm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; i++) mm = fmaxf(mm, s_m[g][i]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float f = s_m[g][i] == -INFINITY ? 0.f : exp2f(s_m[g][i] - mm);
+            num = fmaf(f, s_acc[g][i][d], num);
+            den = fmaf(f, s_l[g][i], den);
+        }
+        out[((size_t)seq * heads + kvh * GROUP + g) * 128 + d] = __float2bfloat16_rn(num / den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = *s.step;
+    if (i < n_seqs) {
+        const int32_t tok = s.next_tok[i];
+        if (!s.finished[i] && step < s.max_tokens) {
+            s.out_ids[(size_t)i * s.max_tokens + step] = tok;
+            if (s.out_val && s.next_val) s.out_val[(size_t)i * s.max_tokens + step] = s.next_val[i];
+            s.out_len[i] = step + 1;
+            if (s.stop_on_eos && tok == s.eos) {
+                s.finished[i] = 1;
+                atomicSub(s.n_active, 1);
+            }
+        }
+        s.cur_tok[i] = s.forced ? s.forced[step] : tok;
+        s.pos[i] += 1;
+        s.kv_len[i] += 1;
+    }
+    __syncthreads();
+    if (i == 0) *s.step = step + 1;
+}
+
+__global__ void fill_i32_kernel(int* p, int v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+__global__ void f32_to_bf16_kernel(const float* in, bf16* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void f16_to_bf16_kernel(const uint16_t* in, bf16* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(__half2float(__ushort_as_half(in[i])));
+}
+__global__ void fill_bf16_kernel(bf16* out, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__global__ void random_init_kernel(bf16* out, size_t n, unsigned long long seed, float mult) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long z = splitmix(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL);
+    const int s = (int)(z & 0xFFFF) + (int)((z >> 16) & 0xFFFF) + (int)((z >> 32) & 0xFFFF) + (int)(z >> 48) - 131070;
+    out[i] = __float2bfloat16_rn(__fmul_rn(__int2float_rn(s), mult));
+}
+
+inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+void conv1_launch(const float* mel, const Conv1Chunk* chunks, int n_chunks, const bf16* w, const bf16* bias, int C, int chunk_w,
+                  bf16* out, cudaStream_t st) {
+    if (n_chunks <= 0) return;
+    dim3 grid(64, n_chunks);
+    conv1_kernel<<<grid, 256, sizeof(float) * 3 * (chunk_w + 2), st>>>(mel, chunks, w, bias, C, chunk_w, out);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void layernorm_launch(const bf16* x, const bf16* w, const bf16* b, bf16* y, int rows, int d, float eps, cudaStream_t st) {
+    if (rows <= 0) return;
+    Q3_CHECK(d % 128 == 0 && d <= 2048, 1, "layernorm: d must be a multiple of 128, <= 2048");
+    const unsigned grid = blocks_for(rows, 8);
+    if (d <= 1024) layernorm_kernel<8><<<grid, 256, 0, st>>>(x, w, b, y, rows, d, eps);
+    else layernorm_kernel<16><<<grid, 256, 0, st>>>(x, w, b, y, rows, d, eps);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void rmsnorm_launch(const bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, const int* row_index, cudaStream_t st) {
+    if (rows <= 0) return;
+    Q3_CHECK(d % 128 == 0 && d <= 2048, 1, "rmsnorm: d must be a multiple of 128, <= 2048");
+    const unsigned grid = blocks_for(rows, 8);
+    if (d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, st>>>(x, w, y, rows, d, eps, row_index);
+    else rmsnorm_kernel<16><<<grid, 256, 0, st>>>(x, w, y, rows, d, eps, row_index);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void embed_splice_launch(const int32_t* ids, const int* audio_src, const bf16* embed, const bf16* audio, bf16* x, int rows, int h,
+                         cudaStream_t st) {
+    if (rows <= 0) return;
+    embed_splice_kernel<<<blocks_for((size_t)rows * (h / 8), 256), 256, 0, st>>>(ids, audio_src, embed, audio, x, rows, h);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* kw, const int* pos, const int* row_seq, int rows,
+                           int heads, int kv_heads, float eps, float theta, const float* inv_freq, bf16* qout, bf16* kc, bf16* vc,
+                           const KvCache& cache, int layer, cudaStream_t st) {
+    (void)theta;
+    if (rows <= 0) return;
+    Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
+    const size_t warps = (size_t)rows * (heads + 2 * kv_heads);
+    qknorm_rope_kv_kernel<<<blocks_for(warps, 8), 256, 0, st>>>(qkv, ld, qw, kw, pos, row_seq, rows, heads, kv_heads, eps, inv_freq, qout,
+                                                                kc, vc, cache, layer);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void decode_attn_launch(const bf16* q, const KvCache& cache, int layer, const int* kv_len, int n_seqs, int heads, float scale, bf16* out,
+                        cudaStream_t st) {
+    if (n_seqs <= 0) return;
+    const int group = heads / cache.kv_heads;
+    const float sl2 = scale * 1.4426950408889634f;
+    dim3 grid(n_seqs, cache.kv_heads);
+    switch (group) {
+        case 1: decode_attn_kernel<1><<<grid, 128, 0, st>>>(q, cache, layer, kv_len, heads, sl2, out); break;
+        case 2: decode_attn_kernel<2><<<grid, 128, 0, st>>>(q, cache, layer, kv_len, heads, sl2, out); break;
+        default: throw Error(1, "decode attention: only 1 or 2 query heads per kv head are built");
+    }
+    Q3_CUDA(cudaGetLastError());
+}
+
+void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st) {
+    Q3_CHECK(n_seqs <= 1024, 1, "decode_advance: at most 1024 sequences per handle");
+    decode_advance_kernel<<<1, 1024, 0, st>>>(s, n_seqs);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st) {
+    if (n) fill_i32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, v, n);
+}
+void bf16_to_f32_launch(const bf16* in, float* out, size_t n, cudaStream_t st) {
+    if (n) bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+}
+void f32_to_bf16_launch(const float* in, bf16* out, size_t n, cudaStream_t st) {
+    if (n) f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+}
+void f16_to_bf16_launch(const uint16_t* in, bf16* out, size_t n, cudaStream_t st) {
+    if (n) f16_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+}
+void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st) {
+    // std of the 4x16-bit Irwin-Hall sum is sqrt((65536^2 - 1) / 3)
+    const float mult = (float)((double)scale / 37837.22668596909);
+    if (n) random_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, (unsigned long long)seed, mult);
+}
+void fill_bf16_launch(bf16* out, size_t n, float v, cudaStream_t st) {
+    if (n) fill_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, v);
+}
+
+}  // namespace q3

@@ -1,0 +1,90 @@
+// ops.cuh — the non-GEMM kernels of the encoder and decoder (ops.cu, attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace q3 {
+
+constexpr int KV_PAGE = 32;  // tokens per KV-cache page
+
+// ---- encoder ----
+// conv2d1 (1 -> C channels, 3x3, stride 2, pad 1) + exact GELU, fp32 math on the fp32 mel, bf16 NHWC output.
+// AudioEncoder.swift:380-410 (chunk extraction, zero padding of the last chunk, conv2d1, gelu).
+struct Conv1Chunk {
+    long long mel_off;  // start of the clip's [128, T] block
+    int T;              // frames of the clip (row pitch)
+    int f0;             // first frame of the chunk
+    int len;            // valid frames in the chunk
+    int w0;             // padded chunk width (frames >= w0 are convolution padding)
+};
+void conv1_launch(const float* mel, const Conv1Chunk* chunks, int n_chunks, const bf16* w /*[C,3,3,1]*/, const bf16* bias, int C,
+                  int chunk_w /*100*/, bf16* out /*[n_chunks,64,chunk_w/2,C]*/, cudaStream_t st);
+
+// LayerNorm over the last dim (biased variance, fp32 statistics), bf16 in/out.  d % 128 == 0, d <= 2048.
+void layernorm_launch(const bf16* x, const bf16* w, const bf16* b, bf16* y, int rows, int d, float eps, cudaStream_t st);
+// RMSNorm; row_index (optional) gathers input rows: y[r] = norm(x[row_index[r]]).
+void rmsnorm_launch(const bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, const int* row_index, cudaStream_t st);
+
+// ---- attention (attention.cu) ----
+// Multi-head attention over independent segments of a packed row list (encoder windows, decoder prompts).
+// q/k/v/o are row-major with the given leading dimensions; head h of q lives at columns [h*HD, (h+1)*HD),
+// kv head h/group likewise in k and v.  causal: key j visible to query i iff j <= i (same segment).
+struct AttnSegs {
+    const int* row0;  // [n_segs] first row of each segment
+    const int* len;   // [n_segs]
+    int n_segs;
+    int max_len;
+};
+void flash_attn_launch(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, const AttnSegs& segs,
+                       int heads, int group, int head_dim, bool causal, float scale, cudaStream_t st);
+
+// ---- decoder ----
+// x[r] = audio_src[r] >= 0 ? audio[audio_src[r]] : embed[ids[r]]   (Qwen3ASR.swift:236-244)
+void embed_splice_launch(const int32_t* ids, const int* audio_src, const bf16* embed, const bf16* audio, bf16* x, int rows, int h,
+                         cudaStream_t st);
+
+struct KvCache {
+    bf16* pool;             // [pages][layers][2][kv_heads][KV_PAGE][head_dim]
+    const int* page_table;  // [n_seqs][max_pages]
+    int max_pages;
+    int layers, kv_heads, head_dim;
+};
+// Per (row, head): q/k RMSNorm over head_dim, split-half RoPE at pos[row], v passthrough; writes q to qout
+// [rows, heads*hd], k/v to the paged cache (slot pos[row] of sequence row_seq[row]) and, if kc/vc != null, to
+// contiguous [rows, kv_heads*hd] buffers for the prefill attention.  FloatTextDecoder.swift:85-102.
+void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* kw, const int* pos, const int* row_seq, int rows,
+                           int heads, int kv_heads, float eps, float theta, const float* inv_freq, bf16* qout, bf16* kc, bf16* vc,
+                           const KvCache& cache, int layer, cudaStream_t st);
+// One query token per sequence against its paged cache (kv_len[seq] keys, the new token included), GQA.
+void decode_attn_launch(const bf16* q /*[n_seqs, heads*hd]*/, const KvCache& cache, int layer, const int* kv_len, int n_seqs, int heads,
+                        float scale, bf16* out, cudaStream_t st);
+
+// Greedy bookkeeping after each LM-head argmax (Qwen3ASR.swift:344-389): appends the token, handles EOS,
+// advances positions, selects the next input token (the argmax, or forced[step] when teacher forcing).
+struct DecodeState {
+    int32_t* next_tok;    // [n_seqs] argmax of this step (input)
+    float* next_val;      // [n_seqs] its logit (input, may be null)
+    int32_t* cur_tok;     // [n_seqs] token fed to the next step (output)
+    int* pos;             // [n_seqs] position of the next token
+    int* kv_len;          // [n_seqs]
+    int32_t* out_ids;     // [n_seqs, max_tokens]
+    float* out_val;       // [n_seqs, max_tokens] or null
+    int* out_len;         // [n_seqs]
+    int* finished;        // [n_seqs]
+    int* n_active;        // [1]
+    const int32_t* forced;  // [n_seqs? no: steps] or null
+    int* step;            // [1] device-side step counter
+    int max_tokens;
+    int eos;
+    int stop_on_eos;
+};
+void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st);
+
+void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st);
+void bf16_to_f32_launch(const bf16* in, float* out, size_t n, cudaStream_t st);
+void f32_to_bf16_launch(const float* in, bf16* out, size_t n, cudaStream_t st);
+void f16_to_bf16_launch(const uint16_t* in, bf16* out, size_t n, cudaStream_t st);
+// deterministic random init (see model.cu / oracle/weights.py): out[i] = bf16(scale * irwin_hall4(seed, i))
+void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st);
+void fill_bf16_launch(bf16* out, size_t n, float v, cudaStream_t st);
+
+}  // namespace q3

@@ -1,0 +1,121 @@
+// pool.cu — the utterance-batching scheduler across the GPUs of one box.
+//
+// The reference has no batching layer: `speech transcribe-batch` is a serial loop over files
+// (/root/reference/Sources/AudioCLILib/TranscribeBatchCommand.swift:82-125).  Here every utterance is an
+// independent unit (transcribe builds a fresh cache per call, Qwen3ASR.swift:246-251), so the pool
+// replicates the weights on each GPU, deals utterances longest-processing-time-first to the least loaded
+// GPU, lets one worker thread per GPU run its share in length-sorted sub-batches, and gathers the ids on
+// the host.  No collective touches the data path.
+#include <algorithm>
+#include <numeric>
+#include <thread>
+
+#include "model.h"
+
+using namespace q3;
+
+struct q3asr_pool {
+    std::vector<q3asr_handle*> handles;
+    std::string last_error;
+};
+
+extern "C" {
+
+int q3asr_schedule(const size_t* n_samples, int batch, int n_gpus, int* gpu_out) {
+    if (n_samples == nullptr || gpu_out == nullptr || batch < 0 || n_gpus <= 0) return Q3ASR_ERR_INVALID;
+    std::vector<int> order(batch);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_samples[a] > n_samples[b]; });
+    std::vector<unsigned long long> load(n_gpus, 0);
+    for (int i : order) {
+        int best = 0;
+        for (int g = 1; g < n_gpus; g++)
+            if (load[g] < load[best]) best = g;
+        gpu_out[i] = best;
+        // cost model: encoder/prefill/decode work all grow with the audio length; the constant stands for
+        // the fixed prompt and decode cost of an utterance
+        load[best] += (unsigned long long)n_samples[i] + 16000ull;
+    }
+    return Q3ASR_OK;
+}
+
+int q3asr_pool_create(const q3asr_config* cfg, const int* devices, int n_devices, uint64_t random_seed, const char* weights_dir,
+                      q3asr_pool** out) {
+    if (cfg == nullptr || devices == nullptr || n_devices <= 0 || out == nullptr) return Q3ASR_ERR_INVALID;
+    *out = nullptr;
+    q3asr_pool* p = new q3asr_pool();
+    for (int i = 0; i < n_devices; i++) {
+        q3asr_handle* h = nullptr;
+        int rc = q3asr_create(cfg, devices[i], &h);
+        if (rc == Q3ASR_OK) rc = weights_dir ? q3asr_load_safetensors(h, weights_dir) : q3asr_init_random(h, random_seed);
+        if (rc != Q3ASR_OK) {
+            p->last_error = q3asr_last_error(h);
+            if (h) q3asr_destroy(h);
+            q3asr_pool_destroy(p);
+            return rc;
+        }
+        p->handles.push_back(h);
+    }
+    *out = p;
+    return Q3ASR_OK;
+}
+
+void q3asr_pool_destroy(q3asr_pool* p) {
+    if (p == nullptr) return;
+    for (q3asr_handle* h : p->handles) q3asr_destroy(h);
+    delete p;
+}
+
+const char* q3asr_pool_last_error(const q3asr_pool* p) { return p ? p->last_error.c_str() : ""; }
+
+int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, int batch, const q3asr_prompt* prompts,
+                              int max_tokens, int stop_on_eos, int max_batch_per_gpu, int32_t* ids_out, int* lens_out) {
+    if (p == nullptr || pcm == nullptr || n_samples == nullptr || ids_out == nullptr || lens_out == nullptr || batch <= 0)
+        return Q3ASR_ERR_INVALID;
+    const int G = (int)p->handles.size();
+    if (max_batch_per_gpu <= 0) max_batch_per_gpu = 64;
+    std::vector<int> gpu(batch);
+    q3asr_schedule(n_samples, batch, G, gpu.data());
+    std::vector<int> rc(G, Q3ASR_OK);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++) {
+        workers.emplace_back([&, g]() {
+            std::vector<int> mine;
+            for (int i = 0; i < batch; i++)
+                if (gpu[i] == g) mine.push_back(i);
+            // similar lengths together: prefill rows and decode steps stay homogeneous
+            std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) { return n_samples[a] > n_samples[b]; });
+            for (size_t s = 0; s < mine.size() && rc[g] == Q3ASR_OK; s += max_batch_per_gpu) {
+                const int nb = (int)std::min<size_t>(max_batch_per_gpu, mine.size() - s);
+                std::vector<const float*> pp(nb);
+                std::vector<size_t> nn(nb);
+                std::vector<q3asr_prompt> pr(nb);
+                for (int j = 0; j < nb; j++) {
+                    pp[j] = pcm[mine[s + j]];
+                    nn[j] = n_samples[mine[s + j]];
+                    if (prompts) pr[j] = prompts[mine[s + j]];
+                }
+                std::vector<int32_t> ids((size_t)nb * max_tokens);
+                std::vector<int> lens(nb);
+                rc[g] = q3asr_transcribe_ids(p->handles[g], pp.data(), nn.data(), nb, prompts ? pr.data() : nullptr, max_tokens,
+                                             stop_on_eos, ids.data(), lens.data());
+                if (rc[g] != Q3ASR_OK) break;
+                for (int j = 0; j < nb; j++) {  // host-side result gather, original order
+                    const int i = mine[s + j];
+                    lens_out[i] = lens[j];
+                    std::copy(ids.begin() + (size_t)j * max_tokens, ids.begin() + (size_t)j * max_tokens + lens[j],
+                              ids_out + (size_t)i * max_tokens);
+                }
+            }
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g] != Q3ASR_OK) {
+            p->last_error = std::string("gpu worker ") + std::to_string(g) + ": " + q3asr_last_error(p->handles[g]);
+            return rc[g];
+        }
+    return Q3ASR_OK;
+}
+
+}  // extern "C"

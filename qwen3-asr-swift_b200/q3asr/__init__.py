@@ -1,0 +1,437 @@
+"""ctypes binding of libq3asr.so — the Python host side above the C ABI (include/q3asr.h).
+
+The reference's host language is Swift (no toolchain in this image); this module mirrors the reference's
+operator interface for the path so the parity tests read like the reference's own:
+
+    Qwen3ASRModel.fromPretrained / transcribe      /root/reference/Sources/Qwen3ASR/Qwen3ASR.swift:107-164, 608-668
+    WhisperFeatureExtractor.extractFeaturesRaw     /root/reference/Sources/Qwen3ASR/AudioPreprocessing.swift:347-470
+    Qwen3AudioEncoder.callAsFunction               /root/reference/Sources/Qwen3ASR/AudioEncoder.swift:362-511
+
+There is no CPU fallback and nothing here imports oracle/: if the shared library is missing, or no
+Blackwell GPU is present, construction fails loudly.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libq3asr.so")
+
+OK = 0
+STAGE_MEL, STAGE_ENCODER, STAGE_PREFILL, STAGE_DECODE, STAGE_ALL = 1, 2, 4, 8, 15
+EPI_NORMAL, EPI_SWIGLU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 3
+
+
+class Q3Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"q3asr error {code}: {msg}")
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "enc_d_model", "enc_heads", "enc_ffn", "enc_layers", "enc_out_dim", "enc_conv_ch", "enc_n_window",
+        "enc_n_window_infer")] + [("enc_ln_eps", ctypes.c_float)] + [(n, ctypes.c_int) for n in (
+            "dec_vocab", "dec_hidden", "dec_layers", "dec_heads", "dec_kv_heads", "dec_head_dim", "dec_inter")] + [
+                ("dec_rope_theta", ctypes.c_float), ("dec_rms_eps", ctypes.c_float)] + [(n, ctypes.c_int32) for n in (
+                    "tok_im_start", "tok_im_end", "tok_audio_start", "tok_audio_end", "tok_audio_pad", "tok_asr_text",
+                    "tok_newline", "tok_system", "tok_user", "tok_assistant", "tok_eos")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Prompt(ctypes.Structure):
+    _fields_ = [("context_ids", ctypes.POINTER(ctypes.c_int32)), ("n_context", ctypes.c_int),
+                ("language_ids", ctypes.POINTER(ctypes.c_int32)), ("n_language", ctypes.c_int)]
+
+
+# every symbol include/q3asr.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
+    "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
+    "q3asr_load_safetensors", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
+    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
+    "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
+    "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
+    "q3asr_pool_create", "q3asr_pool_destroy", "q3asr_pool_last_error", "q3asr_pool_transcribe_ids", "q3asr_schedule",
+    "q3asr_debug_gemm", "q3asr_debug_conv",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Q3Error(-1, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        L.q3asr_version.restype = ctypes.c_char_p
+        L.q3asr_last_error.restype = ctypes.c_char_p
+        L.q3asr_last_error.argtypes = [vp]
+        L.q3asr_pool_last_error.restype = ctypes.c_char_p
+        L.q3asr_pool_last_error.argtypes = [vp]
+        L.q3asr_config_preset.argtypes = [ctypes.c_char_p, ctypes.POINTER(Config)]
+        L.q3asr_create.argtypes = [ctypes.POINTER(Config), ci, ctypes.POINTER(vp)]
+        L.q3asr_destroy.argtypes = [vp]
+        L.q3asr_destroy.restype = None
+        L.q3asr_init_random.argtypes = [vp, ctypes.c_uint64]
+        L.q3asr_tensor_count.argtypes = [vp]
+        L.q3asr_tensor_info.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ci)]
+        L.q3asr_set_tensor.argtypes = [vp, ctypes.c_char_p, vp, ci, ctypes.POINTER(ctypes.c_int64), ci]
+        L.q3asr_get_tensor.argtypes = [vp, ctypes.c_char_p, vp, cs]
+        L.q3asr_commit_weights.argtypes = [vp]
+        L.q3asr_load_safetensors.argtypes = [vp, ctypes.c_char_p]
+        L.q3asr_is_loaded.argtypes = [vp]
+        L.q3asr_unload.argtypes = [vp]
+        L.q3asr_memory_footprint.argtypes = [vp]
+        L.q3asr_memory_footprint.restype = cs
+        L.q3asr_mel_frames.argtypes = [cs]
+        L.q3asr_mel.argtypes = [vp, vp, cs, vp, ctypes.POINTER(ci)]
+        L.q3asr_mel_batch.argtypes = [vp, vp, vp, ci, vp, vp]
+        L.q3asr_encoder_tokens.argtypes = [ci]
+        L.q3asr_encode.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
+        L.q3asr_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp]
+        L.q3asr_decode_forced.argtypes = [vp, vp, cs, vp, vp, ci, vp, vp]
+        L.q3asr_prefill_logits.argtypes = [vp, vp, cs, vp, vp]
+        L.q3asr_batch_upload.argtypes = [vp, vp, vp, ci, vp]
+        L.q3asr_batch_run.argtypes = [vp, ci, ci, ci]
+        L.q3asr_batch_download.argtypes = [vp, vp, ci, vp]
+        L.q3asr_sync.argtypes = [vp]
+        L.q3asr_timer_record.argtypes = [vp, ci]
+        L.q3asr_timer_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
+        L.q3asr_stage_ms.argtypes = [vp, vp]
+        L.q3asr_launch_count.argtypes = [vp]
+        L.q3asr_launch_count.restype = ctypes.c_uint64
+        L.q3asr_flush_l2.argtypes = [vp]
+        L.q3asr_pool_create.argtypes = [ctypes.POINTER(Config), vp, ci, ctypes.c_uint64, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.q3asr_pool_destroy.argtypes = [vp]
+        L.q3asr_pool_destroy.restype = None
+        L.q3asr_pool_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, vp, vp]
+        L.q3asr_schedule.argtypes = [vp, ci, ci, vp]
+        L.q3asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.q3asr_debug_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        _lib = L
+    return _lib
+
+
+def version():
+    return lib().q3asr_version().decode()
+
+
+def preset(name):
+    c = Config()
+    rc = lib().q3asr_config_preset(name.encode(), ctypes.byref(c))
+    if rc != OK:
+        raise Q3Error(rc, f"unknown preset {name!r}")
+    return c
+
+
+def mel_frames(n):
+    return lib().q3asr_mel_frames(int(n))
+
+
+def encoder_tokens(frames):
+    return lib().q3asr_encoder_tokens(int(frames))
+
+
+def schedule(n_samples, n_gpus):
+    """The scheduler's utterance -> GPU assignment (host logic, no GPU needed)."""
+    n = np.ascontiguousarray(n_samples, dtype=np.uint64)
+    out = np.zeros(n.size, dtype=np.int32)
+    rc = lib().q3asr_schedule(n.ctypes.data, n.size, int(n_gpus), out.ctypes.data)
+    if rc != OK:
+        raise Q3Error(rc, "schedule: bad argument")
+    return out
+
+
+def f32_to_bf16_bits(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return r
+
+
+def bf16_bits_to_f32(b):
+    return (np.ascontiguousarray(b, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+def _ptr_array(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+class _PromptPack:
+    """Keeps the numpy arrays behind an array of q3asr_prompt alive."""
+
+    def __init__(self, prompts, batch):
+        self.keep = []
+        self.arr = None
+        if prompts is None:
+            return
+        assert len(prompts) == batch
+        self.arr = (Prompt * batch)()
+        for i, p in enumerate(prompts):
+            ctx, lang = (p or {}).get("context"), (p or {}).get("language")
+            for key, ids in (("context", ctx), ("language", lang)):
+                if ids is not None and len(ids):
+                    a = np.ascontiguousarray(ids, dtype=np.int32)
+                    self.keep.append(a)
+                    setattr(self.arr[i], f"{key}_ids", a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+                    setattr(self.arr[i], f"n_{key}", a.size)
+
+    @property
+    def ptr(self):
+        return ctypes.cast(self.arr, ctypes.c_void_p) if self.arr is not None else None
+
+
+class Qwen3ASRModel:
+    """Mirror of the reference's Qwen3ASRModel for the transcription path (ids instead of text: the
+    tokenizer stays on the Swift side, and with no tokenizer the reference itself returns the ids joined by
+    spaces, Qwen3ASR.swift:290-293)."""
+
+    def __init__(self, size="0.6B", device=0, config=None):
+        self.cfg = config if config is not None else preset(size)
+        self._h = ctypes.c_void_p()
+        rc = lib().q3asr_create(ctypes.byref(self.cfg), int(device), ctypes.byref(self._h))
+        if rc != OK:
+            raise Q3Error(rc, lib().q3asr_last_error(None).decode())
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, model_dir, size="0.6B", device=0):
+        m = cls(size=size, device=device)
+        m._ck(lib().q3asr_load_safetensors(m._h, os.fspath(model_dir).encode()))
+        return m
+
+    @classmethod
+    def random_init(cls, size="0.6B", seed=20260418, device=0, config=None):
+        m = cls(size=size, device=device, config=config)
+        m._ck(lib().q3asr_init_random(m._h, int(seed)))
+        return m
+
+    def close(self):
+        if self._h:
+            lib().q3asr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise Q3Error(rc, lib().q3asr_last_error(self._h).decode())
+
+    @property
+    def is_loaded(self):
+        return bool(lib().q3asr_is_loaded(self._h))
+
+    def unload(self):
+        self._ck(lib().q3asr_unload(self._h))
+
+    @property
+    def memory_footprint(self):
+        return int(lib().q3asr_memory_footprint(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib().q3asr_launch_count(self._h))
+
+    # -- weights -----------------------------------------------------------------------------
+    def tensor_names(self):
+        out = []
+        name = ctypes.create_string_buffer(256)
+        shape = (ctypes.c_int64 * 4)()
+        nd = ctypes.c_int()
+        for i in range(lib().q3asr_tensor_count(self._h)):
+            self._ck(lib().q3asr_tensor_info(self._h, i, name, 256, shape, ctypes.byref(nd)))
+            out.append((name.value.decode(), tuple(shape[j] for j in range(nd.value))))
+        return out
+
+    def get_tensor(self, name, shape):
+        out = np.empty(int(np.prod(shape)), dtype=np.float32)
+        self._ck(lib().q3asr_get_tensor(self._h, name.encode(), out.ctypes.data, out.size))
+        return out.reshape(shape)
+
+    def set_tensor(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+        self._ck(lib().q3asr_set_tensor(self._h, name.encode(), a.ctypes.data, 0, shape, a.ndim))
+
+    def commit_weights(self):
+        self._ck(lib().q3asr_commit_weights(self._h))
+
+    def state_dict(self):
+        return {n: self.get_tensor(n, s) for n, s in self.tensor_names()}
+
+    # -- stages ------------------------------------------------------------------------------
+    def extract_features(self, audio):
+        """WhisperFeatureExtractor.extractFeaturesRaw: float32 [n] at 16 kHz -> [128, n // 160]."""
+        return self.extract_features_batch([audio])[0]
+
+    def extract_features_batch(self, clips):
+        clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        n = np.array([c.size for c in clips], dtype=np.uint64)
+        outs = [np.empty((128, mel_frames(c.size)), dtype=np.float32) for c in clips]
+        frames = np.zeros(len(clips), dtype=np.int32)
+        self._ck(lib().q3asr_mel_batch(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips),
+                                       ctypes.cast(_ptr_array(outs), ctypes.c_void_p), frames.ctypes.data))
+        return outs
+
+    def encode(self, mel):
+        """Qwen3AudioEncoder: mel float32 [128, T] -> [tokens, out_dim] float32."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        T = mel.shape[1]
+        out = np.empty((encoder_tokens(T) + 16, self.cfg.enc_out_dim), dtype=np.float32)
+        ntok = ctypes.c_int()
+        self._ck(lib().q3asr_encode(self._h, mel.ctypes.data, T, out.ctypes.data, ctypes.byref(ntok)))
+        return out[:ntok.value].copy()
+
+    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, prompts=None):
+        """Batched greedy transcription -> list of int32 id arrays (EOS included when it stops the loop)."""
+        clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        n = np.array([c.size for c in clips], dtype=np.uint64)
+        ids = np.zeros((len(clips), max_tokens), dtype=np.int32)
+        lens = np.zeros(len(clips), dtype=np.int32)
+        pp = _PromptPack(prompts, len(clips))
+        self._ck(lib().q3asr_transcribe_ids(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), pp.ptr,
+                                            int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
+        return [ids[i, :lens[i]].copy() for i in range(len(clips))]
+
+    def transcribe(self, audio, sample_rate=16000, language_ids=None, max_tokens=448, context_ids=None):
+        """Signature of Qwen3ASRModel.transcribe(audio:sampleRate:language:maxTokens:context:); returns the ids
+        joined by spaces, the reference's own no-tokenizer fallback."""
+        if sample_rate != 16000:
+            raise Q3Error(1, "resampling is outside the B200 path: feed 16 kHz audio (AudioPreprocessing.swift:323-337)")
+        pr = [{"context": context_ids, "language": language_ids}]
+        ids = self.transcribe_ids([audio], max_tokens=max_tokens, stop_on_eos=True, prompts=pr)[0]
+        return " ".join(str(int(t)) for t in ids)
+
+    def decode_forced(self, audio, forced, prompt=None):
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        forced = np.ascontiguousarray(forced, dtype=np.int32)
+        am = np.zeros(forced.size + 1, dtype=np.int32)
+        top = np.zeros(forced.size + 1, dtype=np.float32)
+        pp = _PromptPack([prompt] if prompt else None, 1)
+        self._ck(lib().q3asr_decode_forced(self._h, audio.ctypes.data, audio.size, pp.ptr, forced.ctypes.data, forced.size,
+                                           am.ctypes.data, top.ctypes.data))
+        return am, top
+
+    def prefill_logits(self, audio, prompt=None):
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        out = np.empty(self.cfg.dec_vocab, dtype=np.float32)
+        pp = _PromptPack([prompt] if prompt else None, 1)
+        self._ck(lib().q3asr_prefill_logits(self._h, audio.ctypes.data, audio.size, pp.ptr, out.ctypes.data))
+        return out
+
+    # -- resident batch (benchmarks) -----------------------------------------------------------
+    def batch_upload(self, clips, prompts=None):
+        self._clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        n = np.array([c.size for c in self._clips], dtype=np.uint64)
+        pp = _PromptPack(prompts, len(self._clips))
+        self._ck(lib().q3asr_batch_upload(self._h, ctypes.cast(_ptr_array(self._clips), ctypes.c_void_p), n.ctypes.data,
+                                          len(self._clips), pp.ptr))
+
+    def batch_run(self, stages=STAGE_ALL, max_tokens=128, stop_on_eos=False):
+        self._ck(lib().q3asr_batch_run(self._h, int(stages), int(max_tokens), int(bool(stop_on_eos))))
+
+    def batch_download(self, batch, max_tokens):
+        ids = np.zeros((batch, max(max_tokens, 1)), dtype=np.int32)
+        lens = np.zeros(batch, dtype=np.int32)
+        self._ck(lib().q3asr_batch_download(self._h, ids.ctypes.data, int(max_tokens), lens.ctypes.data))
+        return [ids[i, :lens[i]].copy() for i in range(batch)]
+
+    def sync(self):
+        self._ck(lib().q3asr_sync(self._h))
+
+    def timer_record(self, slot):
+        self._ck(lib().q3asr_timer_record(self._h, slot))
+
+    def timer_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._ck(lib().q3asr_timer_elapsed_ms(self._h, a, b, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def stage_ms(self):
+        out = np.zeros(4, dtype=np.float32)
+        self._ck(lib().q3asr_stage_ms(self._h, out.ctypes.data))
+        return out
+
+    def flush_l2(self):
+        self._ck(lib().q3asr_flush_l2(self._h))
+
+    # -- debug hooks -----------------------------------------------------------------------------
+    def debug_gemm(self, A, W, bias=None, resid=None, epi=EPI_NORMAL, gelu=False, bn=0, simt=False):
+        """A [M,K], W [N,K] float32 holding bf16-representable values."""
+        M, K = A.shape
+        N = W.shape[0]
+        a, w = f32_to_bf16_bits(A), f32_to_bf16_bits(W)
+        b = f32_to_bf16_bits(bias) if bias is not None else None
+        r = f32_to_bf16_bits(resid) if resid is not None else None
+        if epi == EPI_F32:
+            out = np.empty((M, N), dtype=np.float32)
+        elif epi == EPI_ARGMAX:
+            out = np.empty(M, dtype=np.int32)
+        elif epi == EPI_SWIGLU:
+            out = np.empty((M, N // 2), dtype=np.uint16)
+        else:
+            out = np.empty((M, N), dtype=np.uint16)
+        self._ck(lib().q3asr_debug_gemm(self._h, a.ctypes.data, w.ctypes.data, b.ctypes.data if b is not None else None,
+                                        r.ctypes.data if r is not None else None, M, N, K, int(epi), int(bool(gelu)), int(bn),
+                                        int(bool(simt)), out.ctypes.data))
+        return bf16_bits_to_f32(out) if out.dtype == np.uint16 else out
+
+    def debug_conv(self, x, w, bias, box=(0, 0, 0), simt=False):
+        """x [B,H,W,C], w [O,3,3,C] float32 (bf16-representable) -> gelu(conv3x3 s2 p1 + bias) [B,OH,OW,O]."""
+        B, H, Wd, C = x.shape
+        O = w.shape[0]
+        OH, OW = (H - 1) // 2 + 1, (Wd - 1) // 2 + 1
+        bw, bh, bb = box
+        if bw == 0:
+            bw, bh, bb = OW, 1, max(1, 128 // OW)
+        out = np.empty((B, OH, OW, O), dtype=np.uint16)
+        xb, wb, bbias = f32_to_bf16_bits(x), f32_to_bf16_bits(w), f32_to_bf16_bits(bias)
+        self._ck(lib().q3asr_debug_conv(self._h, xb.ctypes.data, wb.ctypes.data, bbias.ctypes.data, B, H, Wd, C, O, bw, bh, bb,
+                                        int(bool(simt)), out.ctypes.data))
+        return bf16_bits_to_f32(out)
+
+
+class Pool:
+    """Utterance-batching scheduler over several GPUs of one process (q3asr_pool_*)."""
+
+    def __init__(self, size="0.6B", devices=(0,), seed=20260418, weights_dir=None, config=None):
+        self.cfg = config if config is not None else preset(size)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self._p = ctypes.c_void_p()
+        rc = lib().q3asr_pool_create(ctypes.byref(self.cfg), dev.ctypes.data, dev.size, int(seed),
+                                     os.fspath(weights_dir).encode() if weights_dir else None, ctypes.byref(self._p))
+        if rc != OK:
+            raise Q3Error(rc, "pool_create failed: " + lib().q3asr_last_error(None).decode())
+
+    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, max_batch_per_gpu=64):
+        clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        n = np.array([c.size for c in clips], dtype=np.uint64)
+        ids = np.zeros((len(clips), max_tokens), dtype=np.int32)
+        lens = np.zeros(len(clips), dtype=np.int32)
+        rc = lib().q3asr_pool_transcribe_ids(self._p, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), None,
+                                             int(max_tokens), int(bool(stop_on_eos)), int(max_batch_per_gpu), ids.ctypes.data,
+                                             lens.ctypes.data)
+        if rc != OK:
+            raise Q3Error(rc, lib().q3asr_pool_last_error(self._p).decode())
+        return [ids[i, :lens[i]].copy() for i in range(len(clips))]
+
+    def close(self):
+        if self._p:
+            lib().q3asr_pool_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,134 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM convolution against NumPy and the CUDA-core checker,
+through the C-ABI debug hooks.  Inputs are bf16-representable, accumulation is fp32, so the only
+difference from the fp32 NumPy product is summation order; outputs are rounded to bf16 (1 ulp = 2^-8 rel)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.weights import bf16_round
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, shape, scale=1.0):
+    return bf16_round((scale * rng.standard_normal(shape)).astype(np.float32))
+
+
+def _gelu(x):
+    return np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x.ravel()], dtype=np.float64).reshape(x.shape)
+
+
+def _close_bf16(got, ref, what, ulps=1.5):
+    # outputs are bf16: allow `ulps` bf16 ulps of the reference magnitude plus a small absolute floor
+    tol = ulps * np.maximum(np.abs(ref), 1e-2) * 2.0 ** -8
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} off; worst {np.abs(got - ref).max():.4g} at {np.argwhere(bad)[:4].tolist()}"
+
+
+SHAPES = [(128, 128, 64), (256, 256, 256), (300, 256, 192), (1000, 896, 896), (77, 480, 4320), (64, 2048, 128), (513, 160, 96),
+          (1, 128, 128), (130, 32, 40)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("simt", [False, True])
+def test_gemm_store_bias(tiny_model, M, N, K, simt):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A, W, b = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05), _rand(rng, (N,))
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + b
+    got = tiny_model.debug_gemm(A, W, bias=b, simt=simt)
+    _close_bf16(got, ref, f"{'simt' if simt else 'tc'} store {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+def test_gemm_every_tile_width(tiny_model, bn):
+    rng = np.random.default_rng(bn)
+    M, N, K = 200, 512, 320
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    _close_bf16(tiny_model.debug_gemm(A, W, bn=bn), ref, f"bn={bn}")
+
+
+def test_gemm_tile_width_160(tiny_model):
+    rng = np.random.default_rng(160)
+    M, N, K = 333, 480, 480
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    _close_bf16(tiny_model.debug_gemm(A, W, bn=160), ref, "bn=160")
+
+
+def test_gemm_gelu_and_residual(tiny_model):
+    rng = np.random.default_rng(3)
+    M, N, K = 260, 256, 128
+    A, W, b, R = _rand(rng, (M, K)), _rand(rng, (N, K), 0.08), _rand(rng, (N,)), _rand(rng, (M, N))
+    acc = A.astype(np.float64) @ W.astype(np.float64).T + b
+    _close_bf16(tiny_model.debug_gemm(A, W, bias=b, gelu=True), _gelu(acc), "gelu")
+    ref = R + bf16_round(acc.astype(np.float32))
+    _close_bf16(tiny_model.debug_gemm(A, W, bias=b, resid=R), ref, "resid")
+
+
+def test_gemm_fp32_out(tiny_model):
+    rng = np.random.default_rng(4)
+    M, N, K = 150, 128, 512
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    got = tiny_model.debug_gemm(A, W, epi=2)
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_swiglu(tiny_model, bn):
+    rng = np.random.default_rng(5 + bn)
+    M, I, K = 140, 512, 128
+    A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
+    half = bn // 2
+    # the library interleaves gate/up rows per output tile (csrc/weights.cu)
+    Wi = np.concatenate([np.concatenate([G[t * half:(t + 1) * half], U[t * half:(t + 1) * half]]) for t in range(I // half)])
+    g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    s = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
+    got = tiny_model.debug_gemm(A, Wi, epi=1, bn=bn)
+    _close_bf16(got, s * u, f"swiglu bn={bn}", ulps=3)
+
+
+def test_gemm_argmax(tiny_model):
+    rng = np.random.default_rng(6)
+    M, N, K = 64, 4096, 128
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    logits = bf16_round((A.astype(np.float64) @ W.astype(np.float64).T).astype(np.float32))
+    got = tiny_model.debug_gemm(A, W, epi=3)
+    ref = logits.argmax(axis=1)  # first maximal index, like MLX argMax
+    # accumulation order can flip a bf16 rounding: accept a different index only if its logit ties the maximum
+    for r in range(M):
+        assert got[r] == ref[r] or logits[r, got[r]] >= logits[r, ref[r]] - abs(logits[r, ref[r]]) * 2.0 ** -7, (r, got[r], ref[r])
+    # exact ties resolve to the lowest index
+    W2 = W.copy()
+    W2[1000] = W2[17]
+    W2[3000] = W2[17]
+    A2 = np.tile(bf16_round(W2[17:18] * 4), (M, 1))
+    got2 = tiny_model.debug_gemm(A2, W2, epi=3)
+    assert (got2 == 17).all(), got2[:8]
+
+
+def _conv_ref(x, w, b):
+    B, H, Wd, C = x.shape
+    O = w.shape[0]
+    OH, OW = (H - 1) // 2 + 1, (Wd - 1) // 2 + 1
+    xp = np.zeros((B, H + 2, Wd + 2, C), np.float64)
+    xp[:, 1:-1, 1:-1] = x
+    out = np.zeros((B, OH, OW, O), np.float64)
+    for kh in range(3):
+        for kw in range(3):
+            patch = xp[:, kh:kh + 2 * OH:2, kw:kw + 2 * OW:2, :]
+            out += np.einsum("bhwc,oc->bhwo", patch, w[:, kh, kw, :].astype(np.float64))
+    return _gelu(out + b)
+
+
+@pytest.mark.parametrize("B,H,W,C,O,box", [(7, 16, 10, 96, 64, (0, 0, 0)), (5, 64, 50, 32, 32, (25, 1, 5)), (11, 32, 25, 480, 160, (13, 1, 9)),
+                                          (3, 8, 7, 64, 128, (4, 4, 3)), (2, 5, 5, 40, 32, (3, 3, 2))])
+@pytest.mark.parametrize("simt", [False, True])
+def test_conv_implicit_gemm(tiny_model, B, H, W, C, O, box, simt):
+    rng = np.random.default_rng(B * 100 + C)
+    x, w, b = _rand(rng, (B, H, W, C)), _rand(rng, (O, 3, 3, C), 0.05), _rand(rng, (O,))
+    got = tiny_model.debug_conv(x, w, b, box=box, simt=simt)
+    _close_bf16(got, _conv_ref(x, w, b), f"conv {'simt' if simt else 'tc'} {B}x{H}x{W}x{C}->{O} box {box}", ulps=2)

@@ -1,0 +1,75 @@
+"""GPU parity of the log-mel kernel (K1) against the CPU oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star: "mel features within 1e-4 relative error in fp32"):
+|gpu - oracle| <= 1e-4 * max(1, |oracle|) on every element.
+"""
+import numpy as np
+import pytest
+
+from oracle import mel as omel
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _check(gpu, ref, what, tol=TOL):
+    assert gpu.shape == ref.shape, (what, gpu.shape, ref.shape)
+    err = np.abs(gpu - ref) / np.maximum(1.0, np.abs(ref))
+    i = np.unravel_index(np.argmax(err), err.shape) if err.size else None
+    assert err.size == 0 or err.max() <= tol, f"{what}: max rel err {err.max():.3e} at {i} gpu={gpu[i]} ref={ref[i]}"
+
+
+@pytest.mark.parametrize("n", [160, 161, 400, 1599, 1600, 5119, 5120, 5121, 16000, 47999, 240000, 480000])
+def test_mel_matches_oracle(tiny_model, n):
+    x = synth.clip(n % 7, n)
+    got = tiny_model.extract_features(x)
+    _check(got, omel.mel(x), f"n={n}")
+
+
+def test_mel_edge_signals(tiny_model):
+    zeros = np.zeros(16000, np.float32)
+    _check(tiny_model.extract_features(zeros), omel.mel(zeros), "zeros")
+    imp = np.zeros(8000, np.float32)
+    imp[4000] = 1.0
+    # an impulse has frames that are exactly silent next to frames that are not: exercises the max-8 clamp pass
+    _check(tiny_model.extract_features(imp), omel.mel(imp), "impulse")
+    rng = np.random.default_rng(5)
+    quiet_loud = np.concatenate([1e-6 * rng.standard_normal(8000), 0.5 * rng.standard_normal(8000)]).astype(np.float32)
+    _check(tiny_model.extract_features(quiet_loud), omel.mel(quiet_loud), "quiet+loud (clamp active)")
+
+
+def test_mel_pure_tone_near_floor(tiny_model):
+    # a noiseless tone puts most bins 60-80 dB below the peak, where fp32 round-off of ANY FFT ordering is
+    # ~1e-3 relative; the double-precision oracle is the fair reference there and the tolerance is 2e-3
+    t = np.arange(32000) / 16000.0
+    x = (0.4 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    _check(tiny_model.extract_features(x), omel.mel(x, precise=True), "tone", tol=2e-3)
+
+
+def test_mel_ragged_batch_equals_single(tiny_model):
+    lens = [480000, 1600, 47999, 16000, 240000, 161]
+    clips = [synth.clip(i, n) for i, n in enumerate(lens)]
+    outs = tiny_model.extract_features_batch(clips)
+    for c, o in zip(clips, outs):
+        single = tiny_model.extract_features(c)
+        assert np.array_equal(o, single)  # batching must not change a single bit
+        _check(o, omel.mel(c), f"batch n={c.size}")
+
+
+def test_mel_properties_full_size(tiny_model):
+    # BASELINE config sizes (64 x 30 s): size-independent properties instead of a slow oracle pass
+    clips = [synth.clip(i, 480000) for i in range(64)]
+    outs = tiny_model.extract_features_batch(clips)
+    for o in outs:
+        assert o.shape == (128, 3000) and np.isfinite(o).all()
+        # dynamic range: nothing is below (max - 8)/4 + 1 once the dropped frame is accounted for
+        assert o.min() >= o.max() - 2.0 - 1e-3
+    # identical clip -> identical features regardless of its slot in the batch
+    again = tiny_model.extract_features_batch([clips[5], clips[0]])
+    assert np.array_equal(again[0], outs[5]) and np.array_equal(again[1], outs[0])
+    # amplitude scaling by 2 shifts every unclamped log-mel by log10(4)/4
+    a = tiny_model.extract_features(clips[3][:48000])
+    b = tiny_model.extract_features((2.0 * clips[3][:48000]).astype(np.float32))
+    assert np.allclose(b - a, np.log10(4.0) / 4.0, atol=2e-4)
