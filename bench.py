@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — RTFx (audio-seconds transcribed per second) of the Qwen3-ASR-0.6B batch transcription path.
+
+Workload (BASELINE.json `metric` / configs[2], extended by the decode the metric's "transcribed" implies):
+64 x 30 s synthetic 16 kHz clips PER GPU (utterance-sharded, no collective on the data path, weak scaling),
+random-init bf16 weights, full pipeline per step: log-mel -> audio encoder -> prompt splice + prefill -> 128 greedy
+tokens over the paged KV cache.  One "step" = one pass over one such batch.
+
+  value     whole-job RTFx with the batch already resident in HBM when the timed region starts (device time, CUDA
+            events on the library's stream, max over ranks)
+  e2e       the same metric through q3asr_transcribe_ids with HOST buffers: pinned staging + H2D of the samples and
+            D2H of the ids inside the timed region (wall clock around the blocking call, max over ranks)
+  roofline  the dominant kernel family (by device time) of the step, timed live with CUDA events around its launches
+            in extra profiled steps of the same workload, against MEASURED_PEAKS.json; roofline_mel is the log-mel
+            kernel against the HBM peak (the north star's "mel GB/s")
+  cpu_baseline  the CPU oracle (a restatement of the reference's algorithm; the Swift/MLX reference cannot build on
+            Linux) timed on this box's host cores on a bounded sample
+
+`--impl reference` times only that CPU restatement (rank 0), for the driver's reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
+
+MODEL = "0.6B"
+CLIPS_PER_GPU = 64
+CLIP_SECONDS = 30
+MAX_TOKENS = 128
+SEED = 20260418
+METRIC = "RTFx (audio-sec/sec) Qwen3-ASR-0.6B batched"
+UNIT = "audio-seconds/second"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_clips(rank):
+    from oracle import synth  # input data generator shared with the tests (not oracle arithmetic)
+    n = CLIP_SECONDS * 16000
+    return [synth.clip(rank * CLIPS_PER_GPU + i, n) for i in range(CLIPS_PER_GPU)]
+
+
+def cpu_sample(seconds, tokens, state_dict=None, threads=None):
+    """Times the CPU oracle (fp32, torch-CPU matmuls, all host threads) on one clip; returns (rtfx, cores, sample)."""
+    import torch
+    from oracle import mel as omel
+    from oracle import model as omodel
+    from oracle import synth, weights
+    cfg = weights.preset(MODEL)
+    if state_dict is None:
+        state_dict = weights.random_state_dict(cfg, SEED)
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = omodel.Oracle(cfg, state_dict, emulate_bf16=False)
+    x = synth.clip(0, seconds * 16000)
+
+    def once():
+        t0 = time.perf_counter()
+        feats = omel.mel(x)
+        emb = orc.encode(feats)
+        orc.greedy(emb, tokens, stop_on_eos=False)
+        return time.perf_counter() - t0
+    return once, cores, f"1 clip x {seconds} s, mel + encoder + prefill + {tokens} greedy tokens, fp32 torch-CPU, {cores} threads"
+
+
+def run_reference(args, rank):
+    """The reference arm: the CPU restatement of the reference's algorithm (oracle/), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    seconds, tokens = 10, 16
+    once, cores, sample = cpu_sample(seconds, tokens)
+    for _ in range(args.warmup):
+        once()
+    t = [once() for _ in range(args.steps)]
+    total = float(sum(t))
+    val = seconds * args.steps / total
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"Qwen3-ASR-{MODEL} full transcribe on the host CPU, bounded sample: {sample}", "parallelism": "cpu"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the Swift/MLX reference does not build on Linux; this is the CPU restatement in oracle/ (kind=port)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import q3asr
+    model = q3asr.Qwen3ASRModel.random_init(MODEL, seed=SEED, device=local_rank)
+    clips = make_clips(rank)
+    audio_s = CLIPS_PER_GPU * CLIP_SECONDS
+
+    # ---- device-timed steps: batch resident in HBM ----
+    model.batch_upload(clips)
+    for _ in range(args.warmup):
+        model.batch_run(q3asr.STAGE_ALL, MAX_TOKENS, False)
+        model.sync()
+    ids_ref = model.batch_download(CLIPS_PER_GPU, MAX_TOKENS)
+    assert all(len(t) == MAX_TOKENS for t in ids_ref)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = model.launch_count
+    dev_ms, stage = 0.0, np.zeros(4)
+    for _ in range(args.steps):
+        model.flush_l2()  # between timed iterations; outside the event pair
+        model.timer_record(0)
+        model.batch_run(q3asr.STAGE_ALL, MAX_TOKENS, False)
+        model.timer_record(1)
+        dev_ms += model.timer_ms(0, 1)
+        model.batch_download(CLIPS_PER_GPU, MAX_TOKENS)
+        stage += model.stage_ms()
+    barrier()
+    clocks = sampler.stop()
+    launches = model.launch_count - l0
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * audio_s * args.steps / (dev_ms / 1000.0)
+
+    # ---- end to end: host buffers in, ids out ----
+    model.transcribe_ids(clips, MAX_TOKENS, stop_on_eos=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = model.transcribe_ids(clips, MAX_TOKENS, stop_on_eos=False)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert [t.tolist() for t in out] == [t.tolist() for t in ids_ref], "greedy ids changed between runs"
+    e2e = world * audio_s * args.steps / e2e_s
+    h2d = int(sum(c.nbytes for c in clips))
+    d2h = int(CLIPS_PER_GPU * MAX_TOKENS * 4 + CLIPS_PER_GPU * 4)
+
+    # ---- per-kernel-family timing (extra steps, CUDA events around the launches) ----
+    pk = peaks()
+    roof, roof_mel, families = None, None, None
+    if not args.no_profile:
+        model.batch_upload(clips)
+        model.profile(True)
+        nprof = 2
+        for _ in range(nprof):
+            model.flush_l2()
+            model.batch_run(q3asr.STAGE_ALL, MAX_TOKENS, False)
+            model.sync()
+        rep = model.profile_report()
+        model.profile(False)
+        families = {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] // nprof,
+                        "tflops": (v["flops"] / max(v["ms"], 1e-9)) / 1e9 if v["flops"] else None,
+                        "gbs": (v["bytes"] / max(v["ms"], 1e-9)) / 1e6 if v["bytes"] else None} for k, v in rep.items()}
+        tensor_fams = {k: v for k, v in rep.items() if v["flops"] > 0 and k != "decode_graph_steps"}
+        dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms"])
+        d = tensor_fams[dom]
+        ach = d["flops"] / d["ms"] / 1e9  # TFLOP/s
+        roof = {"bound": "tensor", "kernel": f"gemm_tc_kernel ({dom})", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"bf16_tflops_sustained, {pk['src']}",
+                "launches_per_step": d["launches"] // nprof, "ms_per_launch": d["ms"] / d["launches"]}
+        m = rep.get("mel")
+        if m:
+            gbs = m["bytes"] / m["ms"] / 1e6
+            roof_mel = {"bound": "hbm", "kernel": "mel_kernel + mel_clamp_kernel", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": gbs / pk["hbm"], "traffic": None, "peak_source": f"hbm_gbs, {pk['src']}", "ms_per_launch": m["ms"] / m["launches"]}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = model.state_dict()  # the same bf16 weights, read back through the C ABI
+        once, cores, sample = cpu_sample(CLIP_SECONDS, 16, state_dict=sd)
+        sec = once()
+        cpu = {"value": CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s)"}
+    model.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"Qwen3-ASR-{MODEL}: {CLIPS_PER_GPU} x {CLIP_SECONDS} s clips per GPU, mel -> encoder -> prefill -> "
+                                   f"{MAX_TOKENS} greedy tokens (fixed length), random-init weights seed {SEED}",
+                       "clips_per_gpu": CLIPS_PER_GPU, "clip_seconds": CLIP_SECONDS, "max_tokens": MAX_TOKENS,
+                       "parallelism": f"dp{world} (utterance-sharded, no collective on the data path)",
+                       "l2": "256 MiB flush between timed iterations; activations (>5 GB per step) exceed L2"},
+            "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(("mel", "encoder", "prefill", "decode"), stage)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_mel": roof_mel, "kernel_families": families,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,10 @@ int q3asr_timer_elapsed_ms(q3asr_handle* h, int slot_a, int slot_b, float* ms);
 int q3asr_stage_ms(q3asr_handle* h, float* ms4);
 /* kernels launched by this handle so far */
 uint64_t q3asr_launch_count(const q3asr_handle* h);
+/* per-kernel-family device timing (CUDA events around tagged launches of the encoder / prefill / decode stages).
+ * report: one line per tag "tag,launches,total_ms,algorithmic_flops,algorithmic_bytes"; reading it resets the log. */
+int q3asr_profile(q3asr_handle* h, int enable);
+int q3asr_profile_report(q3asr_handle* h, char* buf, size_t cap);
 /* L2 flush helper for benchmarks: overwrites a >L2-sized scratch buffer on the handle's stream */
 int q3asr_flush_l2(q3asr_handle* h);
 

@@ -62,8 +62,10 @@ def filterbank(fft_size=512):
 # ---------------------------------------------------------------------------------------
 # Independent NumPy twin (same algorithm card; different code path: rfft)
 # ---------------------------------------------------------------------------------------
-def filterbank_numpy(fft_size=512):
-    f32 = np.float32
+def filterbank_numpy(fft_size=512, dtype=np.float32):
+    """dtype=np.float32 is the reference's Float arithmetic; np.float64 is used only by the HF cross-check to
+    separate "same algorithm" from "same rounding" (the fp32 weights differ by up to 0.5 % near triangle edges)."""
+    f32 = dtype
     nb = fft_size // 2 + 1
     min_log_hz, min_log_mel = f32(1000.0), f32(15.0)
     h2m = f32(27.0) / np.log(f32(6.4))
@@ -80,7 +82,7 @@ def filterbank_numpy(fft_size=512):
     return (fb * (f32(2.0) / (hz[2:] - hz[:-2]))[:, None]).astype(f32)
 
 
-def mel_numpy(x, fft_size=512, vdsp_scale2=True, max_before_trim=True):
+def mel_numpy(x, fft_size=512, vdsp_scale2=True, max_before_trim=True, fb_dtype=np.float32):
     x = np.asarray(x, dtype=np.float32)
     n = x.size
     left = x[np.clip(200 - np.arange(200), 0, n - 1)]
@@ -94,7 +96,9 @@ def mel_numpy(x, fft_size=512, vdsp_scale2=True, max_before_trim=True):
     if vdsp_scale2:
         spec = spec * 2.0
     power = (spec.real ** 2 + spec.imag ** 2).astype(np.float32)
-    m = power.astype(np.float64) @ filterbank_numpy(fft_size).astype(np.float64).T
+    if fb_dtype == np.float64:
+        power = spec.real ** 2 + spec.imag ** 2
+    m = power.astype(np.float64) @ filterbank_numpy(fft_size, fb_dtype).astype(np.float64).T
     lm = np.log10(np.maximum(m, 1e-10)).astype(np.float32)
     g = lm.max() if max_before_trim else lm[:-1].max()
     lm = np.maximum(lm, g - np.float32(8.0)) * np.float32(0.25) + np.float32(1.0)

@@ -1,5 +1,6 @@
 // api.cu — the extern "C" surface declared in include/q3asr.h.  Every entry point catches, records the
 // message on the handle and returns a status code; nothing aborts (SURVEY.md §8b error contract).
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -148,6 +149,10 @@ void q3asr_destroy(q3asr_handle* hh) {
         h.mel_stage.release();
         for (int i = 0; i < 16; i++)
             if (h.timer[i]) cudaEventDestroy(h.timer[i]);
+        for (auto& r : h.prof) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
         if (h.stream) cudaStreamDestroy(h.stream);
     } catch (...) {
     }
@@ -286,6 +291,43 @@ int q3asr_stage_ms(q3asr_handle* h, float* ms4) {
 uint64_t q3asr_launch_count(const q3asr_handle* h) {
     if (h == nullptr) return 0;
     return h->h.launches + (gemm_launch_count() - h->h.gemm_base);
+}
+int q3asr_profile(q3asr_handle* h, int enable) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CUDA(cudaStreamSynchronize(x.stream));
+        x.prof_on = enable != 0;
+        x.prof_used = 0;
+    });
+}
+int q3asr_profile_report(q3asr_handle* h, char* buf, size_t cap) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(buf != nullptr && cap > 0, Q3ASR_ERR_INVALID, "profile_report: null buffer");
+        Q3_CUDA(cudaStreamSynchronize(x.stream));
+        struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+        std::vector<std::pair<std::string, Agg>> agg;
+        for (size_t i = 0; i < x.prof_used; i++) {
+            float ms = 0.f;
+            Q3_CUDA(cudaEventElapsedTime(&ms, x.prof[i].a, x.prof[i].b));
+            size_t k = 0;
+            for (; k < agg.size(); k++)
+                if (agg[k].first == x.prof[i].tag) break;
+            if (k == agg.size()) agg.emplace_back(x.prof[i].tag, Agg());
+            agg[k].second.ms += ms;
+            agg[k].second.flops += x.prof[i].flops;
+            agg[k].second.bytes += x.prof[i].bytes;
+            agg[k].second.n++;
+        }
+        std::string out;
+        char line[256];
+        for (auto& kv : agg) {
+            snprintf(line, sizeof(line), "%s,%ld,%.6f,%.6e,%.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops,
+                     kv.second.bytes);
+            out += line;
+        }
+        Q3_CHECK(out.size() + 1 <= cap, Q3ASR_ERR_INVALID, "profile_report: buffer too small");
+        memcpy(buf, out.c_str(), out.size() + 1);
+        x.prof_used = 0;
+    });
 }
 int q3asr_flush_l2(q3asr_handle* h) {
     return guarded(h, [&](Handle& x) {

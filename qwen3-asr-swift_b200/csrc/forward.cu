@@ -222,6 +222,9 @@ void reserve_decoder(Handle* h, BatchState* bs) {
 // stages
 // ---------------------------------------------------------------------------------------------
 void run_mel(Handle* h, BatchState* bs) {
+    double mel_bytes = 0;
+    for (const MelClip& mc : bs->mel.clips) mel_bytes += 4.0 * mc.n + 4.0 * MEL_BINS * mc.frames;
+    ProfScope ps(h, "mel", 0, mel_bytes);
     mel_launch(h->mel_tables, bs->pcm.as<float>(), bs->mel_out.as<float>(), bs->mel_clips.as<MelClip>(), bs->B, bs->mel.total_tiles,
                bs->mel_gmax.as<int>(), bs->mel_tmin.as<float>(), h->num_sms, h->stream);
     h->launches += 3;
@@ -257,7 +260,10 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
     }
     for (int c0 = 0; c0 < bs->n_chunks; c0 += grp) {
         const int n = std::min(grp, bs->n_chunks - c0);
-        conv1_launch(d_mel, chunks + c0, n, m.conv1_w, m.conv1_b, g.C, g.chunk, bs->a1.as<bf16>(), st);
+        {
+            ProfScope ps(h, "conv1", 2.0 * 9 * n * 64.0 * g.w1 * g.C, n * (128.0 * g.chunk * 4 + 64.0 * g.w1 * g.C * 2));
+            conv1_launch(d_mel, chunks + c0, n, m.conv1_w, m.conv1_b, g.C, g.chunk, bs->a1.as<bf16>(), st);
+        }
         h->launches++;
         GemmA a;
         a.ptr = bs->a1.as<bf16>(); a.C = g.C; a.W = g.w1; a.H = 64; a.B = n;
@@ -265,13 +271,19 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
         s2.OB = n;
         GemmEpiArgs e2 = epi_store(bs->a2.p, g.C, m.conv2_b, 1);
         e2.valid_w = ints + bs->o_vw2 + c0;
-        gemm_conv(a, s2, m.conv2_w, g.C, e2, st);
+        {
+            ProfScope ps(h, "conv2", 2.0 * n * 32.0 * g.w2 * g.C * 9.0 * g.C, 0);
+            gemm_conv(a, s2, m.conv2_w, g.C, e2, st);
+        }
         a.ptr = bs->a2.as<bf16>(); a.W = g.w2; a.H = 32;
         a.sH = (long)g.w2 * g.C; a.sB = 32L * g.w2 * g.C;
         s3.OB = n;
         GemmEpiArgs e3 = epi_store(bs->a3.as<bf16>() + (size_t)c0 * 16 * g.w3 * g.C, g.C, m.conv3_b, 1);
         e3.valid_w = ints + bs->o_vw3 + c0;
-        gemm_conv(a, s3, m.conv3_w, g.C, e3, st);
+        {
+            ProfScope ps(h, "conv3", 2.0 * n * 16.0 * g.w3 * g.C * 9.0 * g.C, 0);
+            gemm_conv(a, s3, m.conv3_w, g.C, e3, st);
+        }
     }
     // ---- conv_out over the [chunk, t, (f, c)] view of the conv3 output, + positions, gather valid tokens ----
     {
@@ -286,6 +298,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
         GemmEpiArgs e = epi_store(bs->ex.p, d, nullptr);
         e.row_add = m.pe;
         e.row_map = ints + bs->o_rowmap;
+        ProfScope ps(h, "conv_out", 2.0 * bs->n_tok * (double)d * 16.0 * g.C, 0);
         gemm_conv(a, s, m.conv_out_w, d, e, st);
     }
     // ---- transformer layers over the packed tokens ----
@@ -293,20 +306,33 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
     AttnSegs segs{ints + bs->o_win_row0, ints + bs->o_win_len, bs->n_win, bs->max_win};
     bf16 *x = bs->ex.as<bf16>(), *xn = bs->exn.as<bf16>(), *qkv = bs->eqkv.as<bf16>(), *att = bs->eatt.as<bf16>(),
          *ffn = bs->effn.as<bf16>();
+    double win_pairs = 0;  // sum over windows of len^2 (attention work)
+    for (const ClipInfo& ci : bs->clips)
+        for (int s0 = 0; s0 < ci.ntok; s0 += ci.win_size) {
+            const double L = std::min(ci.win_size, ci.ntok - s0);
+            win_pairs += L * L;
+        }
     for (int l = 0; l < c.enc_layers; l++) {
         const EncLayerW& w = m.enc[l];
-        layernorm_launch(x, w.ln1_w, w.ln1_b, xn, T, d, c.enc_ln_eps, st);
-        gemm(xn, d, T, d, w.qkv_w, 3 * d, epi_store(qkv, 3 * d, w.qkv_b), st);
-        flash_attn_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, c.enc_heads, 1, 64, false, 0.125f, st);
-        gemm(att, d, T, d, w.o_w, d, epi_store(x, d, w.o_b, 0, x, d), st);
-        layernorm_launch(x, w.ln2_w, w.ln2_b, xn, T, d, c.enc_ln_eps, st);
-        gemm(xn, d, T, d, w.fc1_w, c.enc_ffn, epi_store(ffn, c.enc_ffn, w.fc1_b, 1), st);
-        gemm(ffn, c.enc_ffn, T, c.enc_ffn, w.fc2_w, d, epi_store(x, d, w.fc2_b, 0, x, d), st);
+        const double Td = T, dd = d, fd = c.enc_ffn;
+        { ProfScope ps(h, "enc_ln", 0, 4.0 * Td * dd); layernorm_launch(x, w.ln1_w, w.ln1_b, xn, T, d, c.enc_ln_eps, st); }
+        { ProfScope ps(h, "enc_qkv", 6.0 * Td * dd * dd, 0); gemm(xn, d, T, d, w.qkv_w, 3 * d, epi_store(qkv, 3 * d, w.qkv_b), st); }
+        {
+            ProfScope ps(h, "enc_attn", 4.0 * win_pairs * dd, 8.0 * Td * dd);
+            flash_attn_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, c.enc_heads, 1, 64, false, 0.125f, st);
+        }
+        { ProfScope ps(h, "enc_out", 2.0 * Td * dd * dd, 0); gemm(att, d, T, d, w.o_w, d, epi_store(x, d, w.o_b, 0, x, d), st); }
+        { ProfScope ps(h, "enc_ln", 0, 4.0 * Td * dd); layernorm_launch(x, w.ln2_w, w.ln2_b, xn, T, d, c.enc_ln_eps, st); }
+        { ProfScope ps(h, "enc_fc1", 2.0 * Td * dd * fd, 0); gemm(xn, d, T, d, w.fc1_w, c.enc_ffn, epi_store(ffn, c.enc_ffn, w.fc1_b, 1), st); }
+        { ProfScope ps(h, "enc_fc2", 2.0 * Td * dd * fd, 0); gemm(ffn, c.enc_ffn, T, c.enc_ffn, w.fc2_w, d, epi_store(x, d, w.fc2_b, 0, x, d), st); }
         h->launches += 3;
     }
-    layernorm_launch(x, m.ln_post_w, m.ln_post_b, xn, T, d, c.enc_ln_eps, st);
-    gemm(xn, d, T, d, m.proj1_w, d, epi_store(att, d, m.proj1_b, 1), st);
-    gemm(att, d, T, d, m.proj2_w, c.enc_out_dim, epi_store(bs->audio.p, c.enc_out_dim, m.proj2_b), st);
+    {
+        ProfScope ps(h, "enc_proj", 2.0 * T * (double)d * (d + c.enc_out_dim), 0);
+        layernorm_launch(x, m.ln_post_w, m.ln_post_b, xn, T, d, c.enc_ln_eps, st);
+        gemm(xn, d, T, d, m.proj1_w, d, epi_store(att, d, m.proj1_b, 1), st);
+        gemm(att, d, T, d, m.proj2_w, c.enc_out_dim, epi_store(bs->audio.p, c.enc_out_dim, m.proj2_b), st);
+    }
     h->launches++;
     bs->enc_done = true;
 }
@@ -336,24 +362,41 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
     const int* pos = prefill ? ints + bs->o_pos : bs->st_pos.as<int>();
     const int* row_seq = prefill ? ints + bs->o_row_seq : ints + bs->o_ident;
     AttnSegs segs{ints + bs->o_seq_row0, ints + bs->o_seq_len, bs->B, bs->max_prompt};
+    double causal_pairs = 0;  // sum over prompts of S(S+1)/2
+    for (const ClipInfo& ci : bs->clips) causal_pairs += 0.5 * ci.prompt_len * (ci.prompt_len + 1.0);
     for (int l = 0; l < c.dec_layers; l++) {
         const DecLayerW& w = m.dec[l];
+        const double Rd = rows;
+        ProfScope* ps = nullptr;
+        auto tag = [&](const char* pre, const char* dec, double fl, double by) {
+            delete ps;
+            ps = new ProfScope(h, prefill ? pre : dec, fl, by);
+        };
+        tag("pre_norm", "dec_norm", 0, 4.0 * Rd * H);
         rmsnorm_launch(x, w.in_ln, xn, rows, H, c.dec_rms_eps, nullptr, st);
+        tag("pre_qkv", "dec_qkv", 2.0 * Rd * H * nqkv, 2.0 * H * nqkv);
         gemm(xn, H, rows, H, w.qkv_w, nqkv, epi_store(qkv, nqkv, nullptr), st);
+        tag("pre_rope", "dec_rope", 0, 4.0 * Rd * nqkv);
         qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
                               c.dec_rope_theta, m.inv_freq, q, prefill ? bs->dkc.as<bf16>() : nullptr,
                               prefill ? bs->dvc.as<bf16>() : nullptr, kc, l, st);
+        tag("pre_attn", "dec_attn", prefill ? 4.0 * causal_pairs * nq : 0, 0);
         if (prefill)
             flash_attn_launch(q, nq, bs->dkc.as<bf16>(), nkv, bs->dvc.as<bf16>(), nkv, att, nq, segs, c.dec_heads,
                               c.dec_heads / c.dec_kv_heads, hd, true, scale, st);
         else
             decode_attn_launch(q, kc, l, bs->st_kv_len.as<int>(), rows, c.dec_heads, scale, att, st);
+        tag("pre_o", "dec_o", 2.0 * Rd * nq * H, 2.0 * nq * H);
         gemm(att, nq, rows, nq, w.o_w, H, epi_store(x, H, nullptr, 0, x, H), st);
+        tag("pre_norm", "dec_norm", 0, 4.0 * Rd * H);
         rmsnorm_launch(x, w.post_ln, xn, rows, H, c.dec_rms_eps, nullptr, st);
+        tag("pre_gateup", "dec_gateup", 4.0 * Rd * H * c.dec_inter, 4.0 * H * c.dec_inter);
         GemmEpiArgs eg;
         eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
         gemm(xn, H, rows, H, w.gu_w, 2 * c.dec_inter, eg, st, false, m.gu_bn);
+        tag("pre_down", "dec_down", 2.0 * Rd * H * c.dec_inter, 2.0 * H * c.dec_inter);
         gemm(act, c.dec_inter, rows, c.dec_inter, w.down_w, H, epi_store(x, H, nullptr, 0, x, H), st);
+        delete ps;
         h->launches += 4;
     }
 }
@@ -364,6 +407,7 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index) {
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
     const int H = c.dec_hidden, B = bs->B;
+    ProfScope ps(h, "lm_head", 2.0 * B * (double)H * c.dec_vocab, 2.0 * H * c.dec_vocab);
     rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
     const int bn = gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
     GemmEpiArgs e;
@@ -458,20 +502,25 @@ void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool
         }
         cudaGraph_t graph = nullptr;
         const unsigned long long l0 = h->launches;
+        const bool prof_was = h->prof_on;
+        h->prof_on = false;  // event records inside a captured graph cannot be read back per replay
         Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
             decode_step_kernels(h, bs, stop_on_eos, forced);
         } catch (...) {
+            h->prof_on = prof_was;
             cudaStreamEndCapture(st, &graph);
             if (graph) cudaGraphDestroy(graph);
             throw;
         }
         Q3_CUDA(cudaStreamEndCapture(st, &graph));
+        h->prof_on = prof_was;
         const unsigned long long per_step = h->launches - l0;
         h->launches = l0;
         Q3_CUDA(cudaGraphInstantiate(&bs->step_graph, graph, 0));
         Q3_CUDA(cudaGraphDestroy(graph));
         bs->graph_B = bs->B;
+        ProfScope ps(h, "decode_graph_steps", 0, 0);
         for (; step < max_tokens; step++) {
             Q3_CUDA(cudaGraphLaunch(bs->step_graph, st));
             h->launches += per_step;

@@ -102,12 +102,45 @@ struct Handle {
     std::unique_ptr<Model> model;
     std::unique_ptr<BatchState> batch;
 
+    // optional per-kernel-family profiling (q3asr_profile): CUDA events around tagged launches
+    struct ProfRec {
+        const char* tag;
+        cudaEvent_t a, b;
+        double flops, bytes;
+    };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    size_t prof_used = 0;
+
     cudaEvent_t timer[16] = {nullptr};
     float stage_ms[4] = {0, 0, 0, 0};
     DevBuf flush_buf;
 
     Handle() {
         for (DevBuf* b : {&mel_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &flush_buf}) b->total = &dev_bytes;
+    }
+};
+
+// RAII tag around one or more launches; no-op unless profiling is enabled on the handle
+struct ProfScope {
+    Handle* h;
+    size_t idx = (size_t)-1;
+    ProfScope(Handle* hh, const char* tag, double flops, double bytes) : h(hh) {
+        if (!h->prof_on) return;
+        if (h->prof_used == h->prof.size()) {
+            Handle::ProfRec r{tag, nullptr, nullptr, 0, 0};
+            Q3_CUDA(cudaEventCreate(&r.a));
+            Q3_CUDA(cudaEventCreate(&r.b));
+            h->prof.push_back(r);
+        }
+        idx = h->prof_used++;
+        h->prof[idx].tag = tag;
+        h->prof[idx].flops = flops;
+        h->prof[idx].bytes = bytes;
+        cudaEventRecord(h->prof[idx].a, h->stream);
+    }
+    ~ProfScope() {
+        if (idx != (size_t)-1) cudaEventRecord(h->prof[idx].b, h->stream);
     }
 };
 

@@ -55,6 +55,7 @@ EXPORTS = [
     "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
+    "q3asr_profile", "q3asr_profile_report",
     "q3asr_pool_create", "q3asr_pool_destroy", "q3asr_pool_last_error", "q3asr_pool_transcribe_ids", "q3asr_schedule",
     "q3asr_debug_gemm", "q3asr_debug_conv",
 ]
@@ -108,6 +109,8 @@ def lib():
         L.q3asr_launch_count.argtypes = [vp]
         L.q3asr_launch_count.restype = ctypes.c_uint64
         L.q3asr_flush_l2.argtypes = [vp]
+        L.q3asr_profile.argtypes = [vp, ci]
+        L.q3asr_profile_report.argtypes = [vp, ctypes.c_char_p, cs]
         L.q3asr_pool_create.argtypes = [ctypes.POINTER(Config), vp, ci, ctypes.c_uint64, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.q3asr_pool_destroy.argtypes = [vp]
         L.q3asr_pool_destroy.restype = None
@@ -360,6 +363,19 @@ class Qwen3ASRModel:
     def stage_ms(self):
         out = np.zeros(4, dtype=np.float32)
         self._ck(lib().q3asr_stage_ms(self._h, out.ctypes.data))
+        return out
+
+    def profile(self, enable=True):
+        self._ck(lib().q3asr_profile(self._h, int(bool(enable))))
+
+    def profile_report(self):
+        """{tag: dict(launches, ms, flops, bytes)} for the launches since profiling was enabled / last read."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._ck(lib().q3asr_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms, fl, by = line.split(",")
+            out[tag] = dict(launches=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
         return out
 
     def flush_l2(self):

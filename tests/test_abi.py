@@ -1,0 +1,81 @@
+"""The C-ABI library loads and exports every symbol include/q3asr.h declares; host-side logic that needs no GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import HAS_GPU, ROOT
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "q3asr.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(q3asr_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    L = built_lib.lib()
+    names = _declared()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(built_lib.EXPORTS) == names  # the binding covers the whole header
+    assert "sm_100a" in built_lib.version()
+
+
+def test_presets_match_reference_configs(built_lib):
+    # Tests/Qwen3ASRTests/Qwen3ASRTests.swift:11-118 pins these integers
+    s = built_lib.preset("0.6B")
+    assert (s.enc_d_model, s.enc_layers, s.enc_heads, s.enc_ffn, s.enc_out_dim) == (896, 18, 14, 3584, 1024)
+    assert (s.dec_hidden, s.dec_layers, s.dec_heads, s.dec_kv_heads, s.dec_inter, s.dec_head_dim) == (1024, 28, 16, 8, 3072, 128)
+    l = built_lib.preset("1.7B")
+    assert (l.enc_d_model, l.enc_layers, l.enc_heads, l.enc_ffn, l.enc_out_dim) == (1024, 24, 16, 4096, 2048)
+    assert (l.dec_hidden, l.dec_inter, l.dec_vocab) == (2048, 6144, 151936)
+    assert (s.enc_conv_ch, s.enc_n_window, s.enc_n_window_infer, s.enc_conv_ch * 16) == (480, 50, 800, 7680)
+    assert (s.tok_im_start, s.tok_im_end, s.tok_audio_start, s.tok_audio_end, s.tok_audio_pad, s.tok_asr_text) == (
+        151644, 151645, 151669, 151670, 151676, 151704)
+    assert (s.tok_system, s.tok_user, s.tok_assistant, s.tok_newline, s.tok_eos) == (8948, 872, 77091, 198, 151645)
+    with pytest.raises(built_lib.Q3Error):
+        built_lib.preset("7B")
+    # the NumPy twin of the presets used by the oracle agrees
+    from oracle import weights
+    for name in ("0.6B", "1.7B", "tiny"):
+        c, o = built_lib.preset(name).as_dict(), weights.preset(name)
+        for k, v in o.items():
+            assert abs(c[k] - v) <= 1e-6 * max(1.0, abs(v)), (name, k)
+
+
+def test_frame_and_token_counts(built_lib):
+    from oracle import model as omodel
+    from oracle import mel as omel
+    for n in (0, 159, 160, 1600, 47999, 480000, 16000 * 1300):
+        assert built_lib.mel_frames(n) == omel.mel_frames(n)
+    # AudioEncoder.swift:287-303
+    for t, want in ((3000, 390), (1500, 195), (100, 13), (101, 14), (60, 8), (1, 1), (1730, 221 + 0)):
+        assert built_lib.encoder_tokens(t) == omodel.output_length(t)
+    assert built_lib.encoder_tokens(3000) == 390 and built_lib.encoder_tokens(1500) == 195
+
+
+def test_scheduler_assignment(built_lib):
+    n = np.array([480000] * 64, dtype=np.uint64)
+    for g in (1, 2, 4, 8):
+        a = built_lib.schedule(n, g)
+        assert np.bincount(a, minlength=g).tolist() == [64 // g] * g
+    # longest-first: a mixed load is balanced within one short clip
+    rng = np.random.default_rng(0)
+    n = rng.integers(16000, 480000, size=200).astype(np.uint64)
+    a = built_lib.schedule(n, 8)
+    load = np.array([n[a == g].sum() for g in range(8)], dtype=np.float64)
+    assert load.max() - load.min() <= 480000
+    assert built_lib.schedule(np.zeros(0, np.uint64), 4).size == 0
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu(built_lib):
+    # no CPU fallback: the product path must refuse to run without a Blackwell GPU
+    with pytest.raises(built_lib.Q3Error) as e:
+        built_lib.Qwen3ASRModel("tiny")
+    assert e.value.code == 3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(built_lib.Q3Error):
+        built_lib.Pool("tiny", devices=(0,))

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""One short pass of the hot path for ncu: 0.6B, a few 30 s clips, a few decode steps (so the launch list stays
+in the hundreds).  Usage: python tools/profile_step.py [clips] [max_tokens] [repeats]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
+import q3asr  # noqa: E402
+from oracle import synth  # noqa: E402  (input generator only)
+
+clips = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+repeats = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+os.environ.setdefault("Q3ASR_NO_GRAPH", "1")  # ncu sees plain launches
+m = q3asr.Qwen3ASRModel.random_init("0.6B")
+x = [synth.clip(i, 480000) for i in range(clips)]
+m.batch_upload(x)
+for _ in range(repeats):
+    m.batch_run(q3asr.STAGE_ALL, tokens, False)
+    m.sync()
+ids = m.batch_download(clips, tokens)
+print("ok", [t.tolist() for t in ids[:2]], "launches", m.launch_count)
+m.close()
