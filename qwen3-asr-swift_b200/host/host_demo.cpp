@@ -1,0 +1,43 @@
+// host_demo.cpp — exercises the C++ host mirror (qwen3_asr.hpp) end to end; used by tests/test_host_cpp.py.
+//   host_demo symbols        -> checks option defaults / size detection (no GPU needed)
+//   host_demo run <seconds>  -> random-init 0.6B, mel + transcribe of a synthetic clip (needs a B200)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "qwen3_asr.hpp"
+
+using namespace qwen3asr;
+
+int main(int argc, char** argv) {
+    const char* mode = argc > 1 ? argv[1] : "symbols";
+    if (!strcmp(mode, "symbols")) {
+        Qwen3DecodingOptions o;
+        if (o.maxTokens != 448 || !o.isGreedyFastPath() || o.language || o.context) return 1;
+        if (detectModelSize("aufklarer/Qwen3-ASR-1.7B-MLX-8bit") != ASRModelSize::large) return 2;
+        if (detectModelSize("aufklarer/Qwen3-ASR-0.6B-MLX-4bit") != ASRModelSize::small) return 3;
+        try {
+            auto m = Qwen3ASRModel::randomInit(ASRModelSize::small);
+            printf("created on GPU, footprint %zu\n", m->memoryFootprint());
+        } catch (const AudioModelError& e) {
+            printf("load error (expected without a GPU): %s\n", e.what());
+        }
+        printf("%s\n", q3asr_version());
+        return 0;
+    }
+    const int seconds = argc > 2 ? atoi(argv[2]) : 3;
+    std::vector<float> x((size_t)seconds * 16000);
+    for (size_t i = 0; i < x.size(); i++) x[i] = 0.4f * sinf(2.f * 3.14159265f * 440.f * (float)i / 16000.f);
+    auto m = Qwen3ASRModel::randomInit(ASRModelSize::small);
+    MelFeatures f = m->featureExtractor.extractFeaturesRaw(x);
+    printf("mel %d x %d\n", f.melBins, f.timeFrames);
+    Qwen3DecodingOptions opt;
+    opt.maxTokens = 8;
+    std::string t = m->transcribe(x, 16000, opt);
+    printf("text(ids) %s\n", t.c_str());
+    auto both = m->transcribeBatch({&x, &x}, {}, 8);
+    if (both[0] != both[1] || both[0] != t) return 4;
+    m->unload();
+    if (m->isLoaded() || m->transcribe(x).find("not loaded") == std::string::npos) return 5;
+    return f.timeFrames == seconds * 100 ? 0 : 6;
+}

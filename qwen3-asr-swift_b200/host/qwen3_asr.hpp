@@ -1,0 +1,208 @@
+// qwen3_asr.hpp — C++ host-side mirror of the reference's Swift API for the batch-transcription path,
+// written above the C ABI (include/q3asr.h).  The reference's own language (Swift) has no toolchain in
+// this image, so this header plays the role the Swift shim (swift/Qwen3ASRB200.swift) plays on a Mac/Linux
+// box with Swift: same type and method names, same defaults, same error behaviour.
+//
+//   Qwen3DecodingOptions                     Sources/Qwen3ASR/Qwen3ASR.swift:13-51
+//   ASRModelSize / detect                    Sources/Qwen3ASR/Qwen3ASR.swift:541-586
+//   MelFeatures / WhisperFeatureExtractor    Sources/Qwen3ASR/AudioPreprocessing.swift:8-18, 347
+//   Qwen3ASRModel::fromPretrained            Sources/Qwen3ASR/Qwen3ASR.swift:608-668  (load: throws)
+//   Qwen3ASRModel::transcribe (2 overloads)  Sources/Qwen3ASR/Qwen3ASR.swift:107-164  (inference: never throws)
+//   isLoaded / unload / memoryFootprint      Sources/Qwen3ASR/Qwen3ASR+Memory.swift:3-17
+//   inputSampleRate                          Sources/Qwen3ASR/Qwen3ASR+Protocols.swift:5-11
+// Header-only; link with -lq3asr.  Not thread-safe per instance (Qwen3ASR.swift:67).
+#pragma once
+#include <algorithm>
+#include <cctype>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/q3asr.h"
+
+namespace qwen3asr {
+
+struct Qwen3DecodingOptions {
+    int maxTokens = 448;
+    std::optional<std::string> language;
+    std::optional<std::string> context;
+    float repetitionPenalty = 1.0f;
+    int noRepeatNgramSize = 0;
+    float temperature = 0.0f;
+    bool isGreedyFastPath() const {  // Qwen3ASR.swift:300-304
+        return temperature == 0.0f && repetitionPenalty == 1.0f && noRepeatNgramSize == 0;
+    }
+};
+
+enum class ASRModelSize { small, large };
+inline ASRModelSize detectModelSize(const std::string& modelId) {  // Qwen3ASR.swift:581-586: "1.7B"/"1.7b" in the id -> large
+    std::string s = modelId;
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    return s.find("1.7b") != std::string::npos ? ASRModelSize::large : ASRModelSize::small;
+}
+
+struct MelFeatures {  // row-major [melBins, timeFrames]
+    std::vector<float> data;
+    int melBins = 128;
+    int timeFrames = 0;
+};
+
+struct AudioModelError : std::runtime_error {  // AudioCommon/AudioModelError.swift:4-34 (modelLoadFailed / weightLoadingFailed)
+    int code;
+    AudioModelError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// token-id <-> text is the host's business (the reference keeps Qwen3Tokenizer in Swift); a caller plugs one in here
+struct Tokenizer {
+    std::function<std::vector<int32_t>(const std::string&)> encode;
+    std::function<std::string(const std::vector<int32_t>&)> decode;
+};
+
+class Qwen3ASRModel;
+
+class WhisperFeatureExtractor {
+  public:
+    static constexpr int sampleRate = 16000, nFFT = 400, hopLength = 160, nMels = 128;  // AudioPreprocessing.swift:24-30
+    MelFeatures extractFeaturesRaw(const std::vector<float>& audio) const {
+        MelFeatures m;
+        m.timeFrames = q3asr_mel_frames(audio.size());
+        m.data.assign((size_t)128 * std::max(m.timeFrames, 0), 0.f);
+        int frames = 0;
+        if (q3asr_mel(h_, audio.data(), audio.size(), m.data.data(), &frames) != Q3ASR_OK) {
+            m.timeFrames = 0;
+            m.data.clear();
+        } else {
+            m.timeFrames = frames;
+        }
+        return m;
+    }
+
+  private:
+    friend class Qwen3ASRModel;
+    q3asr_handle* h_ = nullptr;
+};
+
+class Qwen3ASRModel {
+  public:
+    WhisperFeatureExtractor featureExtractor;
+    static constexpr int inputSampleRate = 16000;
+
+    // modelDir: a directory holding the checkpoint's *.safetensors (the reference resolves it from the HF cache);
+    // modelId decides the size like ASRModelSize.detect.  Throws AudioModelError on load failure.
+    static std::unique_ptr<Qwen3ASRModel> fromPretrained(const std::string& modelId, const std::string& modelDir, int device = 0,
+                                                         std::function<void(double, const std::string&)> progressHandler = nullptr) {
+        if (progressHandler) progressHandler(0.0, "Loading model...");
+        std::unique_ptr<Qwen3ASRModel> m(new Qwen3ASRModel(detectModelSize(modelId), device));
+        int rc = q3asr_load_safetensors(m->h_, modelDir.c_str());
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("weightLoadingFailed: ") + q3asr_last_error(m->h_));
+        if (progressHandler) progressHandler(1.0, "Ready");
+        return m;
+    }
+    // random-init weights of the right architecture (weights are not available offline; parity / bench runs)
+    static std::unique_ptr<Qwen3ASRModel> randomInit(ASRModelSize size, uint64_t seed = 20260418, int device = 0) {
+        std::unique_ptr<Qwen3ASRModel> m(new Qwen3ASRModel(size, device));
+        int rc = q3asr_init_random(m->h_, seed);
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("modelLoadFailed: ") + q3asr_last_error(m->h_));
+        return m;
+    }
+    ~Qwen3ASRModel() { q3asr_destroy(h_); }
+    Qwen3ASRModel(const Qwen3ASRModel&) = delete;
+    Qwen3ASRModel& operator=(const Qwen3ASRModel&) = delete;
+
+    void setTokenizer(Tokenizer t) { tok_ = std::move(t); }
+
+    // Qwen3ASR.swift:131-137.  16 kHz input only (resampling is the caller's, §8a3).  Never throws.
+    std::string transcribe(const std::vector<float>& audio, int sampleRate = 16000, const std::optional<std::string>& language = {},
+                           int maxTokens = 448, const std::optional<std::string>& context = {}) {
+        if (sampleRate != 16000) return "[Qwen3-ASR B200 error: resample to 16 kHz before calling]";
+        return transcribeBatch({&audio}, language, maxTokens, context)[0];
+    }
+    // Qwen3ASR.swift:107-111
+    std::string transcribe(const std::vector<float>& audio, int sampleRate, const Qwen3DecodingOptions& options) {
+        if (!options.isGreedyFastPath()) return "[Qwen3-ASR B200 error: only greedy decoding is implemented on this path]";
+        return transcribe(audio, sampleRate, options.language, options.maxTokens, options.context);
+    }
+    // SpeechRecognitionModel.transcribe(audio:sampleRate:language:)
+    std::string transcribe(const std::vector<float>& audio, int sampleRate, const std::optional<std::string>& language) {
+        return transcribe(audio, sampleRate, language, 448);
+    }
+
+    // the batched entry the utterance scheduler enables; ids per utterance (EOS included when hit, like the reference loop)
+    std::vector<std::vector<int32_t>> transcribeIds(const std::vector<const std::vector<float>*>& audio, int maxTokens = 448,
+                                                    bool stopOnEos = true, const std::vector<int32_t>& contextIds = {},
+                                                    const std::vector<int32_t>& languageIds = {}, std::string* error = nullptr) {
+        const int n = (int)audio.size();
+        std::vector<const float*> pcm(n);
+        std::vector<size_t> len(n);
+        for (int i = 0; i < n; i++) {
+            pcm[i] = audio[i]->data();
+            len[i] = audio[i]->size();
+        }
+        q3asr_prompt pr{contextIds.data(), (int)contextIds.size(), languageIds.data(), (int)languageIds.size()};
+        std::vector<q3asr_prompt> prompts(n, pr);
+        std::vector<int32_t> ids((size_t)n * maxTokens);
+        std::vector<int> lens(n);
+        std::vector<std::vector<int32_t>> out(n);
+        int rc = q3asr_transcribe_ids(h_, pcm.data(), len.data(), n, prompts.data(), maxTokens, stopOnEos ? 1 : 0, ids.data(), lens.data());
+        if (rc != Q3ASR_OK) {
+            if (error) *error = q3asr_last_error(h_);
+            return out;
+        }
+        for (int i = 0; i < n; i++) out[i].assign(ids.begin() + (size_t)i * maxTokens, ids.begin() + (size_t)i * maxTokens + lens[i]);
+        return out;
+    }
+
+    std::vector<std::string> transcribeBatch(const std::vector<const std::vector<float>*>& audio, const std::optional<std::string>& language = {},
+                                             int maxTokens = 448, const std::optional<std::string>& context = {}) {
+        const size_t n = audio.size();
+        if (!isLoaded()) return std::vector<std::string>(n, "[Audio encoded] - Text decoder not loaded");  // Qwen3ASR.swift:116-119
+        std::vector<int32_t> ctx, lang;
+        if (tok_.encode) {
+            if (context) ctx = tok_.encode(*context);                  // Qwen3ASR.swift:203-206
+            if (language) lang = tok_.encode("language " + *language);  // Qwen3ASR.swift:228-232
+        }
+        std::string err;
+        auto ids = transcribeIds(audio, maxTokens, true, ctx, lang, &err);
+        std::vector<std::string> out(n);
+        for (size_t i = 0; i < n; i++) {
+            if (!err.empty()) {
+                out[i] = "[Qwen3-ASR B200 error: " + err + "]";
+                continue;
+            }
+            std::vector<int32_t> t = ids[i];
+            if (tok_.decode) {
+                std::string raw = tok_.decode(t);
+                const size_t at = raw.find("<asr_text>");  // Qwen3ASR.swift:283-287
+                if (at != std::string::npos) raw = raw.substr(at + 10);
+                const size_t a = raw.find_first_not_of(' '), b = raw.find_last_not_of(' ');
+                out[i] = a == std::string::npos ? std::string() : raw.substr(a, b - a + 1);
+            } else {  // id-string fallback, Qwen3ASR.swift:288-289
+                for (size_t j = 0; j < t.size(); j++) out[i] += (j ? " " : "") + std::to_string(t[j]);
+            }
+        }
+        return out;
+    }
+
+    // ModelMemoryManageable
+    bool isLoaded() const { return q3asr_is_loaded(h_) != 0; }
+    void unload() { q3asr_unload(h_); }
+    size_t memoryFootprint() const { return q3asr_memory_footprint(h_); }
+    q3asr_handle* handle() const { return h_; }
+
+  private:
+    Qwen3ASRModel(ASRModelSize size, int device) {
+        q3asr_config cfg;
+        q3asr_config_preset(size == ASRModelSize::large ? "1.7B" : "0.6B", &cfg);
+        int rc = q3asr_create(&cfg, device, &h_);
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("modelLoadFailed: ") + q3asr_last_error(nullptr));
+        featureExtractor.h_ = h_;
+    }
+    q3asr_handle* h_ = nullptr;
+    Tokenizer tok_;
+};
+
+}  // namespace qwen3asr
