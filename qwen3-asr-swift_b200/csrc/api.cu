@@ -342,6 +342,45 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
                      int K, int epi, int gelu, int bn, int use_simt, void* out) {
     return guarded(hh, [&](Handle& h) {
         Q3_CHECK(A && W && out && M > 0 && N > 0 && K > 0, Q3ASR_ERR_INVALID, "debug_gemm: bad argument");
+        if (epi >= 4) {  // decode-step weight-streaming kernel (skinny.cuh): 4 partial (summed here), 5 store, 6 swiglu
+            const int sk = epi - 4;
+            const int splits = gemm_skinny_splits(N, K, sk);
+            bf16 *dA, *dW;
+            void* dO;
+            const size_t out_elems = sk == SK_SWIGLU ? (size_t)M * (N / 2) : (size_t)M * N;
+            const size_t dev_bytes = sk == SK_PARTIAL ? sizeof(float) * out_elems * splits : 2 * out_elems;
+            Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
+            Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
+            Q3_CUDA(cudaMalloc(&dO, dev_bytes));
+            Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
+            Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+            std::vector<float> part;
+            cudaError_t se = cudaSuccess;
+            try {
+                gemm_skinny(dA, K, M, K, dW, N, sk, dO, sk == SK_SWIGLU ? N / 2 : N, bn ? bn / 2 : 64, h.stream);
+                se = cudaStreamSynchronize(h.stream);
+                if (se == cudaSuccess) {
+                    if (sk == SK_PARTIAL) {
+                        part.resize(out_elems * splits);
+                        se = cudaMemcpy(part.data(), dO, dev_bytes, cudaMemcpyDeviceToHost);
+                        float* o = reinterpret_cast<float*>(out);
+                        for (size_t i = 0; i < out_elems; i++) {
+                            float a = part[i];
+                            for (int sp = 1; sp < splits; sp++) a += part[(size_t)sp * out_elems + i];
+                            o[i] = a;
+                        }
+                    } else {
+                        se = cudaMemcpy(out, dO, dev_bytes, cudaMemcpyDeviceToHost);
+                    }
+                }
+            } catch (...) {
+                cudaFree(dA); cudaFree(dW); cudaFree(dO);
+                throw;
+            }
+            cudaFree(dA); cudaFree(dW); cudaFree(dO);
+            Q3_CUDA(se);
+            return;
+        }
         bf16 *dA, *dW, *dB = nullptr, *dR = nullptr;
         void* dO;
         float* dv = nullptr;

@@ -199,6 +199,13 @@ void reserve_decoder(Handle* h, BatchState* bs) {
     bs->datt.reserve(R * nq * 2);
     bs->dact.reserve(R * c.dec_inter * 2);
     bs->dlast.reserve((size_t)bs->B * H * 2);
+    if (bs->B <= SKINNY_MAX_ROWS) {  // split-K partials of the decode-step GEMMs
+        const size_t Bq = bs->B;
+        const size_t w1 = (size_t)gemm_skinny_splits((int)(nq + 2 * nkv), (int)H, SK_PARTIAL) * Bq * (nq + 2 * nkv);
+        const size_t w2 = (size_t)gemm_skinny_splits((int)H, (int)nq, SK_PARTIAL) * Bq * H;
+        const size_t w3 = (size_t)gemm_skinny_splits((int)H, c.dec_inter, SK_PARTIAL) * Bq * H;
+        bs->dws.reserve(std::max(w1, std::max(w2, w3)) * 4);
+    }
     const size_t page_elems = (size_t)c.dec_layers * 2 * c.dec_kv_heads * KV_PAGE * hd;
     bs->kv_pool.reserve((size_t)bs->B * bs->pages_per_seq * page_elems * 2);
     const size_t tiles = c.dec_vocab / 32;  // upper bound on LM-head n-tiles
@@ -401,14 +408,77 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
     }
 }
 
-// final norm of the given rows + tied LM head + argmax -> st_next_tok / st_next_val
-void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index) {
+// Decode step for B <= SKINNY_MAX_ROWS sequences: weight-streaming split-K GEMMs (skinny.cuh) whose fp32 partials are
+// consumed by fused kernels — 7 launches per layer.  On entry bs->dx holds the new token embeddings; on exit bs->dlast
+// holds the final-norm hidden states (the LM-head input).
+void decoder_layers_decode(Handle* h, BatchState* bs) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int B = bs->B;
+    const int H = c.dec_hidden, hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
+    const float scale = 1.0f / sqrtf((float)hd);
+    bf16 *x = bs->dx.as<bf16>(), *xn = bs->dxn.as<bf16>(), *att = bs->datt.as<bf16>(), *act = bs->dact.as<bf16>();
+    float* ws = bs->dws.as<float>();
+    const KvCache kc = kv_cache(h, bs);
+    const int s_qkv = gemm_skinny_splits(nqkv, H, SK_PARTIAL), s_o = gemm_skinny_splits(H, nq, SK_PARTIAL),
+              s_dn = gemm_skinny_splits(H, c.dec_inter, SK_PARTIAL);
+    double kv_bytes = 0;  // keys + values read by one layer's attention
+    for (const ClipInfo& ci : bs->clips) kv_bytes += 2.0 * 2.0 * nkv * (ci.prompt_len + bs->steps_done);
+    {
+        ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
+        rmsnorm_launch(x, m.dec[0].in_ln, xn, B, H, c.dec_rms_eps, nullptr, st);
+        h->launches++;
+    }
+    for (int l = 0; l < c.dec_layers; l++) {
+        const DecLayerW& w = m.dec[l];
+        const bool last = l + 1 == c.dec_layers;
+        {
+            ProfScope ps(h, "dec_qkv", 2.0 * B * H * nqkv, 2.0 * H * nqkv);
+            gemm_skinny(xn, H, B, H, w.qkv_w, nqkv, SK_PARTIAL, ws, 0, 0, st);
+        }
+        {
+            ProfScope ps(h, "dec_attn", 0, kv_bytes);
+            decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, m.inv_freq,
+                                     kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale, att, h->num_sms, st);
+        }
+        {
+            ProfScope ps(h, "dec_o", 2.0 * B * nq * H, 2.0 * nq * H);
+            gemm_skinny(att, nq, B, nq, w.o_w, H, SK_PARTIAL, ws, 0, 0, st);
+        }
+        {
+            ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
+            reduce_resid_rmsnorm_launch(ws, s_o, (long long)B * H, x, w.post_ln, xn, B, H, c.dec_rms_eps, st);
+        }
+        {
+            ProfScope ps(h, "dec_gateup", 4.0 * B * H * c.dec_inter, 4.0 * H * c.dec_inter);
+            gemm_skinny(xn, H, B, H, w.gu_w, 2 * c.dec_inter, SK_SWIGLU, act, c.dec_inter, m.gu_bn / 2, st);
+        }
+        {
+            ProfScope ps(h, "dec_down", 2.0 * B * H * c.dec_inter, 2.0 * H * c.dec_inter);
+            gemm_skinny(act, c.dec_inter, B, c.dec_inter, w.down_w, H, SK_PARTIAL, ws, 0, 0, st);
+        }
+        {
+            ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
+            reduce_resid_rmsnorm_launch(ws, s_dn, (long long)B * H, x, last ? m.final_norm : m.dec[l + 1].in_ln,
+                                        last ? bs->dlast.as<bf16>() : xn, B, H, c.dec_rms_eps, st);
+        }
+        h->launches += 3;
+    }
+}
+
+// final norm of the given rows + tied LM head + argmax -> st_next_tok / st_next_val.  normed: bs->dlast already holds
+// the final-norm hidden states (fused decode path).
+void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed = false) {
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
     const int H = c.dec_hidden, B = bs->B;
     ProfScope ps(h, "lm_head", 2.0 * B * (double)H * c.dec_vocab, 2.0 * H * c.dec_vocab);
-    rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
+    if (!normed) {
+        rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
+        h->launches++;
+    }
     const int bn = gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
     GemmEpiArgs e;
     e.epi = EPI_ARGMAX;
@@ -416,7 +486,7 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index) {
     e.amax_idx = bs->amax_idx.as<int>();
     gemm(bs->dlast.as<bf16>(), H, B, H, m.embed, c.dec_vocab, e, st, false, bn);
     argmax_reduce(e.amax_val, e.amax_idx, B, c.dec_vocab / bn, bs->st_next_tok.as<int32_t>(), bs->st_next_val.as<float>(), st);
-    h->launches += 2;
+    h->launches++;
 }
 
 DecodeState decode_state(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
@@ -475,8 +545,13 @@ void decode_step_kernels(Handle* h, BatchState* bs, int stop_on_eos, bool forced
     cudaStream_t st = h->stream;
     embed_splice_launch(bs->st_cur_tok.as<int32_t>(), nullptr, m.embed, nullptr, bs->dx.as<bf16>(), bs->B, c.dec_hidden, st);
     h->launches++;
-    decoder_layers(h, bs, bs->B, false);
-    lm_head_argmax(h, bs, nullptr);
+    if (bs->B <= SKINNY_MAX_ROWS && c.dec_heads == 2 * c.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0) {
+        decoder_layers_decode(h, bs);
+        lm_head_argmax(h, bs, nullptr, true);
+    } else {
+        decoder_layers(h, bs, bs->B, false);
+        lm_head_argmax(h, bs, nullptr);
+    }
     decode_advance_launch(decode_state(h, bs, stop_on_eos, forced), bs->B, st);
     h->launches++;
 }
@@ -501,7 +576,7 @@ void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool
             bs->step_graph = nullptr;
         }
         cudaGraph_t graph = nullptr;
-        const unsigned long long l0 = h->launches;
+        const unsigned long long l0 = h->launches, g0 = gemm_launch_count();
         const bool prof_was = h->prof_on;
         h->prof_on = false;  // event records inside a captured graph cannot be read back per replay
         Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -515,8 +590,10 @@ void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool
         }
         Q3_CUDA(cudaStreamEndCapture(st, &graph));
         h->prof_on = prof_was;
-        const unsigned long long per_step = h->launches - l0;
+        const unsigned long long gper = gemm_launch_count() - g0;  // captured, not executed
+        const unsigned long long per_step = (h->launches - l0) + gper;
         h->launches = l0;
+        h->gemm_base += gper;
         Q3_CUDA(cudaGraphInstantiate(&bs->step_graph, graph, 0));
         Q3_CUDA(cudaGraphDestroy(graph));
         bs->graph_B = bs->B;

@@ -5,7 +5,7 @@
 #include <atomic>
 #include <vector>
 
-#include "gemm.cuh"
+#include "skinny.cuh"
 
 namespace q3 {
 
@@ -292,6 +292,82 @@ void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const Gemm
 }
 
 unsigned long long gemm_launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// decode-step weight-streaming GEMM
+// ------------------------------------------------------------------------------------------
+namespace {
+template <int NB, int EPI>
+void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB, EPI)));
+        attr_set = true;
+    }
+    gemm_skinny_kernel<NB, EPI><<<grid, 256, sk_smem_bytes(NB, EPI), st>>>(tw, tx, p);
+}
+template <int NB>
+void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
+    switch (epi) {
+        case SK_PARTIAL: launch_skinny<NB, SK_PARTIAL>(tw, tx, p, grid, st); break;
+        case SK_STORE: launch_skinny<NB, SK_STORE>(tw, tx, p, grid, st); break;
+        case SK_SWIGLU: launch_skinny<NB, SK_SWIGLU>(tw, tx, p, grid, st); break;
+        default: throw Error(1, "gemm_skinny: bad epilogue");
+    }
+}
+}  // namespace
+
+int gemm_skinny_splits(int N, int K, int epi) {
+    if (epi != SK_PARTIAL) return 1;
+    const int tiles_n = cdiv(N, SK_BM), num_kb = cdiv(K, SK_BK);
+    int splits = std::min(num_kb, std::max(1, g_num_sms / tiles_n));
+    const int per = cdiv(num_kb, splits);
+    return cdiv(num_kb, per);  // no empty slices
+}
+
+void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
+                 cudaStream_t st) {
+    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "gemm_skinny: 1..128 token rows per launch");
+    Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0, 1, "gemm_skinny: K and ldx must be multiples of 8");
+    if (epi == SK_SWIGLU)
+        Q3_CHECK(N % SK_BM == 0 && (gu_half == 32 || gu_half == 64), 1, "gemm_skinny: SwiGLU needs N % 128 == 0 and 32- or 64-row gate/up blocks");
+    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
+    SkinnyDev p;
+    memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.Mtok = Mtok;
+    p.num_kb = cdiv(K, SK_BK);
+    const int splits = gemm_skinny_splits(N, K, epi);
+    p.kb_per_split = cdiv(p.num_kb, splits);
+    p.out = out;
+    p.ldo = ldo;
+    p.split_stride = (long long)Mtok * N;
+    p.gu_half = gu_half;
+    CUtensorMap tw, tx;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)SK_BK, (cuuint32_t)SK_BM};
+        cuuint32_t es[2] = {1, 1};
+        make_tmap(&tw, W, 2, dims, str, box, es);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Mtok};
+        cuuint64_t str[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {(cuuint32_t)SK_BK, (cuuint32_t)nb};
+        cuuint32_t es[2] = {1, 1};
+        make_tmap(&tx, X, 2, dims, str, box, es);
+    }
+    const dim3 grid(cdiv(N, SK_BM), splits);
+    switch (nb) {
+        case 16: launch_skinny_nb<16>(epi, tw, tx, p, grid, st); break;
+        case 32: launch_skinny_nb<32>(epi, tw, tx, p, grid, st); break;
+        case 64: launch_skinny_nb<64>(epi, tw, tx, p, grid, st); break;
+        default: launch_skinny_nb<128>(epi, tw, tx, p, grid, st); break;
+    }
+    Q3_CUDA(cudaGetLastError());
+    g_launches++;
+}
 
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st) {
     if (rows <= 0) return;

@@ -373,6 +373,21 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
 void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const GemmEpiArgs& e, cudaStream_t st,
           bool simt = false, int bn = 0);
 unsigned long long gemm_launch_count();
+
+// ---- decode-step weight-streaming GEMM (skinny.cuh): Y[Mtok, N] = X[Mtok, K](ldx) W[N, K]^T, Mtok <= 128 per launch ----
+constexpr int SKINNY_MAX_ROWS = 128;
+enum SkinnyEpi : int {
+    SK_PARTIAL = 0,  // out(fp32)[split][m][n] = acc
+    SK_STORE = 1,    // out(bf16)[m][n] = bf16(acc)                       (splits must be 1)
+    SK_SWIGLU = 2,   // W rows interleaved gate/up in blocks of `gu_half`: out(bf16)[m][j] = bf16(bf16(silu(bf16 g)) * bf16 u)
+};
+
+// number of K splits the launch will use for this shape (1 for SK_STORE / SK_SWIGLU)
+int gemm_skinny_splits(int N, int K, int epi);
+// SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo];
+// SK_SWIGLU: W = gate/up rows interleaved in blocks of gu_half rows, out = bf16 [Mtok, ldo] (N/2 columns)
+void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
+                 cudaStream_t st);
 // final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st);
 

@@ -310,6 +310,256 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused decode-step attention: one CTA per (sequence, kv head), NW warps.
+//   1. q (GROUP heads), k, v of the new token = fixed-order sum of the split-K fp32 partials of the QKV
+//      product, rounded to bf16 (the oracle's rounding point); per-head RMSNorm + split-half RoPE on q and k
+//      (same arithmetic as qknorm_rope_kv_kernel); k and v are appended to the paged cache.
+//   2. the query heads attend over kv_len keys (the new one included): a warp scores 8 keys per iteration
+//      (4 lane groups x 2 keys in flight, 8 lanes x 16 dims each), online softmax per lane group.
+//   3. lane groups are merged with shuffles, warps through shared memory.
+// FloatTextDecoder.swift:77-107 (q/k/v, q_norm/k_norm, rope, cache update, attention) for seqLen == 1.
+// ------------------------------------------------------------------------------------------
+constexpr int DA_CHUNK = 8;   // keys per warp step
+constexpr int DA_STAGES = 3;  // cp.async ring depth per warp
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+constexpr int decode_attn_smem(int nw) { return nw * DA_STAGES * 2 * DA_CHUNK * 128 * 2; }
+
+template <int GROUP, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_kernel(const float* __restrict__ qkv_part, int splits, long long split_stride,
+                                                                    int nqkv, const bf16* __restrict__ qw, const bf16* __restrict__ kw,
+                                                                    const int* __restrict__ pos, float eps,
+                                                                    const float* __restrict__ inv_freq, KvCache cache, int layer,
+                                                                    const int* __restrict__ kv_len, int heads, float scale_log2,
+                                                                    bf16* __restrict__ out) {
+    const int seq = blockIdx.x, kvh = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float s_q[GROUP][128];
+    __shared__ float s_m[GROUP][NW], s_l[GROUP][NW];
+    __shared__ float s_acc[GROUP][NW][128];
+    const int* pt = cache.page_table + (size_t)seq * cache.max_pages;
+
+    // ---- 1. new-token q / k / v ----
+    if (warp < GROUP + 2) {
+        const int slot = warp;  // 0..GROUP-1 = q heads, GROUP = k, GROUP+1 = v
+        const int d0 = lane * 4;
+        const int col = slot < GROUP ? (kvh * GROUP + slot) * 128
+                                     : slot == GROUP ? heads * 128 + kvh * 128 : (heads + cache.kv_heads) * 128 + kvh * 128;
+        const float* src = qkv_part + (size_t)seq * nqkv + col + d0;
+        float4 a = *reinterpret_cast<const float4*>(src);
+        for (int s = 1; s < splits; s++) {
+            const float4 b = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float x[4] = {bf16_round(a.x), bf16_round(a.y), bf16_round(a.z), bf16_round(a.w)};
+        const int p = pos[seq];
+        if (slot <= GROUP) {
+            float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
+            const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
+            const uint2 wu = ld8((slot < GROUP ? qw : kw) + d0);
+            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+            x[0] = bf16_round(x[0] * r * w0.x);
+            x[1] = bf16_round(x[1] * r * w0.y);
+            x[2] = bf16_round(x[2] * r * w1.x);
+            x[3] = bf16_round(x[3] * r * w1.y);
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
+            const int i0 = d0 & 63;
+            const float sgn = lane < 16 ? -1.f : 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float sn, cs;
+                sincosf((float)p * __ldg(inv_freq + i0 + j), &sn, &cs);
+                x[j] = bf16_round(fmaf(x[j], cs, sgn * y[j] * sn));
+            }
+        }
+        if (slot < GROUP) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) s_q[slot][d0 + j] = x[j];
+        } else {
+            const int page = pt[p / KV_PAGE];
+            bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (slot == GROUP ? 0 : 1)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
+                        (p % KV_PAGE) * 128 + d0;
+            st8(dst, x[0], x[1], x[2], x[3]);
+        }
+    }
+    __syncthreads();  // s_q ready; the new k/v rows are visible to this CTA
+
+    // ---- 2. attention: each warp streams chunks of 8 keys (K and V rows are contiguous inside a page) through
+    //         its own cp.async ring, so the bytes in flight do not depend on registers ----
+    const int grp = lane >> 3, sub = lane & 7;
+    const int len = kv_len[seq];
+    // lane `sub` owns dims [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8): a lane group reads 128 contiguous bytes
+    float qf[GROUP][16];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++)
+#pragma unroll
+        for (int t = 0; t < 16; t++) qf[g][t] = s_q[g][(t >> 3) * 64 + sub * 8 + (t & 7)];
+    float m[GROUP], l[GROUP], acc[GROUP][16];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        m[g] = -INFINITY;
+        l[g] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; t++) acc[g][t] = 0.f;
+    }
+    extern __shared__ uint4 da_smem[];
+    bf16* ring = reinterpret_cast<bf16*>(da_smem) + (size_t)warp * DA_STAGES * 2 * DA_CHUNK * 128;
+    const size_t head_off = (((size_t)layer * 2) * cache.kv_heads + kvh) * (KV_PAGE * 128);
+    const size_t page_elems = (size_t)cache.layers * 2 * cache.kv_heads * (KV_PAGE * 128);
+    const size_t v_off = (size_t)cache.kv_heads * (KV_PAGE * 128);
+    const int n_chunks = (len + DA_CHUNK - 1) / DA_CHUNK;
+    auto issue = [&](int chunk, int stage) {
+        if (chunk < n_chunks) {
+            const int j0 = chunk * DA_CHUNK;
+            const bf16* kb = cache.pool + (size_t)pt[j0 / KV_PAGE] * page_elems + head_off + (j0 % KV_PAGE) * 128;
+            bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
+#pragma unroll
+            for (int i = 0; i < DA_CHUNK * 16 / 32; i++) {
+                const int seg = i * 32 + lane;  // 16-byte segment of the chunk; key = seg / 16
+                const uint32_t n = j0 + (seg >> 4) < len ? 16u : 0u;  // rows past the end are zero-filled
+                cp_async16(sk + seg * 8, kb + seg * 8, n);
+                cp_async16(sk + DA_CHUNK * 128 + seg * 8, kb + v_off + seg * 8, n);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < DA_STAGES - 1; s++) issue(warp + s * NW, s);
+    int stage = 0;
+    for (int chunk = warp; chunk < n_chunks; chunk += NW) {
+        issue(chunk + (DA_STAGES - 1) * NW, (stage + DA_STAGES - 1) % DA_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(DA_STAGES - 1) : "memory");
+        __syncwarp();
+        const bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
+        const int j0 = chunk * DA_CHUNK;
+#pragma unroll
+        for (int u = 0; u < DA_CHUNK / 4; u++) {
+            const int key = u * 4 + grp;
+            const bool ok = j0 + key < len;
+            const uint4 k0 = *reinterpret_cast<const uint4*>(sk + key * 128 + sub * 8);
+            const uint4 k1 = *reinterpret_cast<const uint4*>(sk + key * 128 + 64 + sub * 8);
+            const uint4 v0 = *reinterpret_cast<const uint4*>(sk + DA_CHUNK * 128 + key * 128 + sub * 8);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(sk + DA_CHUNK * 128 + key * 128 + 64 + sub * 8);
+            const uint32_t kw32[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            const uint32_t vw32[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float kf[16], vf[16];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const float2 a = unpack_bf16x2(kw32[t]), b = unpack_bf16x2(vw32[t]);
+                kf[2 * t] = a.x; kf[2 * t + 1] = a.y;
+                vf[2 * t] = b.x; vf[2 * t + 1] = b.y;
+            }
+#pragma unroll
+            for (int g = 0; g < GROUP; g++) {
+                float s = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; t++) s = fmaf(qf[g][t], kf[t], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s = ok ? s * scale_log2 : -INFINITY;
+                const float mn = fmaxf(m[g], s);
+                const float alpha = mn == -INFINITY ? 1.f : exp2f(m[g] - mn);
+                const float pj = mn == -INFINITY ? 0.f : exp2f(s - mn);
+                l[g] = l[g] * alpha + pj;
+                const float pb = bf16_round(pj);
+#pragma unroll
+                for (int t = 0; t < 16; t++) acc[g][t] = fmaf(pb, vf[t], acc[g][t] * alpha);
+                m[g] = mn;
+            }
+        }
+        __syncwarp();  // the slot is refilled by the next iteration's issue
+        stage = (stage + 1) % DA_STAGES;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- 3. merge the four lane groups of the warp, then the warps ----
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            const float mo = __shfl_xor_sync(0xffffffffu, m[g], off);
+            const float lo = __shfl_xor_sync(0xffffffffu, l[g], off);
+            const float mn = fmaxf(m[g], mo);
+            const float a = mn == -INFINITY ? 1.f : exp2f(m[g] - mn);
+            const float b = mn == -INFINITY ? 0.f : exp2f(mo - mn);
+            l[g] = l[g] * a + lo * b;
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const float ao = __shfl_xor_sync(0xffffffffu, acc[g][t], off);
+                acc[g][t] = acc[g][t] * a + ao * b;
+            }
+            m[g] = mn;
+        }
+        if (grp == 0) {
+            if (sub == 0) { s_m[g][warp] = m[g]; s_l[g][warp] = l[g]; }
+#pragma unroll
+            for (int t = 0; t < 16; t++) s_acc[g][warp][(t >> 3) * 64 + sub * 8 + (t & 7)] = acc[g][t];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GROUP * 128; i += NW * 32) {
+        const int g = i >> 7, d = i & 127;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; w++) mm = fmaxf(mm, s_m[g][w]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const float f = s_m[g][w] == -INFINITY ? 0.f : exp2f(s_m[g][w] - mm);
+            num = fmaf(f, s_acc[g][w][d], num);
+            den = fmaf(f, s_l[g][w], den);
+        }
+        out[((size_t)seq * heads + kvh * GROUP + g) * 128 + d] = __float2bfloat16_rn(num / den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Split-K consumer of the decode step: x[r] = bf16(x[r] + bf16(sum_s part[s][r])) (residual stream, in place),
+// y[r] = RMSNorm(x[r]) * w  (the next block's input).  One CTA per row, 4 columns per thread.
+// FloatTextDecoder.swift:144-147 (residual adds) + :139, :146 (the norms that follow them).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) reduce_resid_rmsnorm_kernel(const float* __restrict__ part, int splits, long long split_stride,
+                                                                   bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                                   int d, float eps) {
+    const int row = blockIdx.x, c0 = threadIdx.x * 4;
+    const bool on = c0 < d;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float q = 0.f;
+    if (on) {
+        const float* src = part + (size_t)row * d + c0;
+        float4 a = *reinterpret_cast<const float4*>(src);
+        for (int s = 1; s < splits; s++) {
+            const float4 b = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        const uint2 u = ld8(x + (size_t)row * d + c0);
+        const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y);
+        v[0] = bf16_round(x0.x + bf16_round(a.x));
+        v[1] = bf16_round(x0.y + bf16_round(a.y));
+        v[2] = bf16_round(x1.x + bf16_round(a.z));
+        v[3] = bf16_round(x1.y + bf16_round(a.w));
+        st8(x + (size_t)row * d + c0, v[0], v[1], v[2], v[3]);
+        q = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+    }
+    __shared__ float s_red[16];
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += s_red[i];
+    const float r = rsqrtf(tot / (float)d + eps);
+    if (on) {
+        const uint2 wu = ld8(w + c0);
+        const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+        st8(y + (size_t)row * d + c0, v[0] * r * w0.x, v[1] * r * w0.y, v[2] * r * w1.x, v[3] * r * w1.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int step = *s.step;
@@ -426,6 +676,38 @@ void decode_attn_launch(const bf16* q, const KvCache& cache, int layer, const in
         case 2: decode_attn_kernel<2><<<grid, 128, 0, st>>>(q, cache, layer, kv_len, heads, sl2, out); break;
         default: throw Error(1, "decode attention: only 1 or 2 query heads per kv head are built");
     }
+    Q3_CUDA(cudaGetLastError());
+}
+
+void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
+                              const int* pos, float eps, const float* inv_freq, const KvCache& cache, int layer, const int* kv_len,
+                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st) {
+    if (n_seqs <= 0) return;
+    Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
+    Q3_CHECK(heads == 2 * cache.kv_heads, 1, "fused decode attention is built for 2 query heads per kv head");
+    const float sl2 = scale * 1.4426950408889634f;
+    dim3 grid(n_seqs, cache.kv_heads);
+    // few (sequence, head) pairs: more warps per CTA so that short batches still spread the key loop
+    static bool attr = false;
+    if (!attr) {
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(4)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(16)));
+        attr = true;
+    }
+    if ((long)n_seqs * cache.kv_heads >= 2L * num_sms)
+        decode_attn_fused_kernel<2, 4><<<grid, 128, decode_attn_smem(4), st>>>(qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps, inv_freq,
+                                                                               cache, layer, kv_len, heads, sl2, out);
+    else
+        decode_attn_fused_kernel<2, 16><<<grid, 512, decode_attn_smem(16), st>>>(qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                                                                                 inv_freq, cache, layer, kv_len, heads, sl2, out);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,
+                                 float eps, cudaStream_t st) {
+    if (rows <= 0) return;
+    Q3_CHECK(d % 128 == 0 && d <= 2048, 1, "reduce_resid_rmsnorm: d must be a multiple of 128, <= 2048");
+    reduce_resid_rmsnorm_kernel<<<rows, d / 4, 0, st>>>(part, splits, split_stride, x, w, y, d, eps);
     Q3_CUDA(cudaGetLastError());
 }
 

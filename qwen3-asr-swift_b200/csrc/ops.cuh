@@ -58,6 +58,15 @@ void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* 
 void decode_attn_launch(const bf16* q /*[n_seqs, heads*hd]*/, const KvCache& cache, int layer, const int* kv_len, int n_seqs, int heads,
                         float scale, bf16* out, cudaStream_t st);
 
+// Decode step, fused: sums the split-K partials of the QKV product (fp32 [splits][n_seqs][nqkv]), applies q/k-norm + RoPE,
+// appends k/v to the cache and attends (one launch instead of qknorm_rope_kv + decode_attn).
+void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
+                              const int* pos, float eps, const float* inv_freq, const KvCache& cache, int layer, const int* kv_len,
+                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st);
+// x += bf16(sum of split-K partials) (in place), y = RMSNorm(x) * w.  d % 128 == 0, d <= 2048.
+void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,
+                                 float eps, cudaStream_t st);
+
 // Greedy bookkeeping after each LM-head argmax (Qwen3ASR.swift:344-389): appends the token, handles EOS,
 // advances positions, selects the next input token (the argmax, or forced[step] when teacher forcing).
 struct DecodeState {

@@ -135,3 +135,34 @@ def test_conv_implicit_gemm(tiny_model, B, H, W, C, O, box, simt):
     x, w, b = _rand(rng, (B, H, W, C)), _rand(rng, (O, 3, 3, C), 0.05), _rand(rng, (O,))
     got = tiny_model.debug_conv(x, w, b, box=box, simt=simt)
     _close_bf16(got, _conv_ref(x, w, b), f"conv {'simt' if simt else 'tc'} {B}x{H}x{W}x{C}->{O} box {box}", ulps=2)
+
+
+# ---- decode-step weight-streaming kernel (csrc/skinny.cuh) ----
+@pytest.mark.parametrize("M,N,K", [(64, 4096, 1024), (64, 1024, 3072), (1, 1024, 2048), (8, 256, 192), (17, 384, 64), (33, 128, 1000),
+                                   (100, 640, 512), (128, 1024, 1024), (5, 200, 136)])
+def test_skinny_partial_and_store(tiny_model, M, N, K):
+    rng = np.random.default_rng(M * 11 + N + K)
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    got = tiny_model.debug_gemm(A, W, epi=4)
+    assert got.shape == (M, N)
+    assert np.allclose(got, ref, rtol=2e-5, atol=2e-4), np.abs(got - ref).max()
+    _close_bf16(tiny_model.debug_gemm(A, W, epi=5), ref, f"skinny store {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,I,bn", [(64, 3072, 128), (7, 256, 128), (40, 192, 64), (128, 512, 64), (16, 128, 128)])
+def test_skinny_swiglu(tiny_model, M, I, bn):
+    rng = np.random.default_rng(M + I + bn)
+    K = 256
+    A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
+    half = bn // 2
+    Wi = np.concatenate([np.concatenate([G[t * half:(t + 1) * half], U[t * half:(t + 1) * half]]) for t in range(I // half)])
+    g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    s = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
+    got = tiny_model.debug_gemm(A, Wi, epi=6, bn=bn)
+    _close_bf16(got, s * u, f"skinny swiglu {M}x{I} bn={bn}", ulps=3)
+    # the two SwiGLU kernels agree bit for bit when fed the same operands (same epilogue arithmetic)
+    if M <= 128:
+        same = tiny_model.debug_gemm(A, Wi, epi=1, bn=bn)
+        assert (np.abs(got - same) <= 2.0 ** -7 * np.maximum(np.abs(same), 1e-2)).all()

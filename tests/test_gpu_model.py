@@ -80,6 +80,23 @@ def test_teacher_forced_argmax_and_logits(tiny_model, tiny_oracle):
         assert abs(got_top[s] - ref_top[s]) <= 4 * ulp, (s, got_top[s], ref_top[s])
 
 
+def test_decode_paths_agree(tiny_model, monkeypatch):
+    """The weight-streaming decode path (split-K tcgen05 GEMMs + fused attention / residual-norm kernels) and the
+    general path (one kernel per op) are two schedules of the same arithmetic: same ids, same top logits up to the
+    fp32 summation order (a couple of bf16 ulps after 24 steps)."""
+    clips = [synth.clip(i, n) for i, n in enumerate([30000, 16000, 48000])]
+    forced = np.random.default_rng(5).integers(0, 2000, size=20).astype(np.int32)
+    fused_ids = tiny_model.transcribe_ids(clips, max_tokens=24, stop_on_eos=False)
+    f_ids, f_top = tiny_model.decode_forced(clips[0], forced)
+    monkeypatch.setenv("Q3ASR_NO_SKINNY", "1")
+    plain_ids = tiny_model.transcribe_ids(clips, max_tokens=24, stop_on_eos=False)
+    p_ids, p_top = tiny_model.decode_forced(clips[0], forced)
+    monkeypatch.delenv("Q3ASR_NO_SKINNY")
+    assert [t.tolist() for t in fused_ids] == [t.tolist() for t in plain_ids]
+    assert np.abs(f_top - p_top).max() <= 4 * np.abs(p_top).max() * 2.0 ** -8
+    assert (f_ids == p_ids).mean() >= 0.9
+
+
 def test_prefill_logits_close(tiny_model, tiny_oracle):
     x = synth.clip(2, 48000)
     emb = tiny_oracle.encode(omel.mel(x))
@@ -163,7 +180,24 @@ def test_golden_0p6b(built_lib):
         x = synth.clip(int(g["clip_index"]), int(g["n_samples"]))
         enc = m.encode(omel.mel(x))
         assert _rel_l2(enc[:, :64], g["encoder_first64"]) <= 1.5e-2
-        ids = m.transcribe_ids([x], max_tokens=len(g["ids"]), stop_on_eos=False)[0]
-        assert ids.tolist() == g["ids"].tolist(), (ids.tolist(), g["ids"].tolist(), g["margins"].tolist())
+        # Random-init weights make the decoder an echo machine whose top-2 logits often tie at bf16 resolution
+        # (margins of 0 or 1 ulp in the fixture), so free-running ids are only defined up to those ties.  The
+        # discriminating check is teacher-forced: feed the oracle's own ids, compare the top logit of every step
+        # (4 bf16 ulps) and the argmax wherever the oracle's margin exceeds 2 ulps.
+        ref_ids, ref_top, margins = g["ids"], g["tops"], g["margins"]
+        got_ids, got_top = m.decode_forced(x, ref_ids[:-1])
+        assert len(got_ids) == len(ref_ids)
+        for s_ in range(len(ref_ids)):
+            ulp = max(abs(float(ref_top[s_])), 2.0 ** -6) * 2.0 ** -7
+            assert abs(got_top[s_] - ref_top[s_]) <= 4 * ulp, (s_, got_top[s_], ref_top[s_])
+            if margins[s_] > 2 * ulp:
+                assert got_ids[s_] == ref_ids[s_], (s_, got_ids[s_], ref_ids[s_], margins[s_])
+        # free-running ids agree with the oracle up to the first step whose margin is inside bf16 resolution
+        ids = m.transcribe_ids([x], max_tokens=len(ref_ids), stop_on_eos=False)[0]
+        for s_ in range(len(ref_ids)):
+            ulp = max(abs(float(ref_top[s_])), 2.0 ** -6) * 2.0 ** -7
+            if margins[s_] <= 2 * ulp:
+                break
+            assert ids[s_] == ref_ids[s_], (s_, ids.tolist(), ref_ids.tolist())
     finally:
         m.close()
