@@ -357,8 +357,17 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
             std::vector<float> part;
             cudaError_t se = cudaSuccess;
             try {
-                gemm_skinny(dA, K, M, K, dW, N, sk, dO, sk == SK_SWIGLU ? N / 2 : N, bn ? bn / 2 : 64, h.stream);
+                float* fix = nullptr;
+                const size_t fix_elems = sk == SK_SWIGLU ? gemm_skinny_fix_elems(N, K) : 0;
+                if (fix_elems) {  // split-K SwiGLU with the last-arriver fix-up; run twice so the ticket reset is exercised
+                    Q3_CUDA(cudaMalloc(&fix, fix_elems * 4 + 4096));
+                    Q3_CUDA(cudaMemsetAsync(fix, 0, fix_elems * 4 + 4096, h.stream));
+                    gemm_skinny(dA, K, M, K, dW, N, sk, dO, N / 2, GU_UNIT, h.stream, fix);
+                    Q3_CUDA(cudaMemsetAsync(dO, 0xff, dev_bytes, h.stream));
+                }
+                gemm_skinny(dA, K, M, K, dW, N, sk, dO, sk == SK_SWIGLU ? N / 2 : N, GU_UNIT, h.stream, fix);
                 se = cudaStreamSynchronize(h.stream);
+                cudaFree(fix);
                 if (se == cudaSuccess) {
                     if (sk == SK_PARTIAL) {
                         part.resize(out_elems * splits);

@@ -6,6 +6,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace q3 {
 
@@ -30,6 +31,30 @@ struct Error : public std::runtime_error {
     } while (0)
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// Kernel launch with optional programmatic stream serialization (PDL): the kernel may start while its predecessor
+// in the stream is still draining; it must call ptx::grid_dep_wait() before touching the predecessor's outputs.
+// The flag is per host thread (one handle = one caller thread); forward.cu raises it around the decode step.
+inline bool& pdl_enabled() {
+    static thread_local bool on = false;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    Q3_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
 
 // ---- device helpers -----------------------------------------------------------------
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

@@ -400,7 +400,7 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
         tag("pre_gateup", "dec_gateup", 4.0 * Rd * H * c.dec_inter, 4.0 * H * c.dec_inter);
         GemmEpiArgs eg;
         eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
-        gemm(xn, H, rows, H, w.gu_w, 2 * c.dec_inter, eg, st, false, m.gu_bn);
+        gemm(xn, H, rows, H, w.gu_w, 2 * c.dec_inter, eg, st);
         tag("pre_down", "dec_down", 2.0 * Rd * H * c.dec_inter, 2.0 * H * c.dec_inter);
         gemm(act, c.dec_inter, rows, c.dec_inter, w.down_w, H, epi_store(x, H, nullptr, 0, x, H), st);
         delete ps;
@@ -423,6 +423,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
     const KvCache kc = kv_cache(h, bs);
     const int s_qkv = gemm_skinny_splits(nqkv, H, SK_PARTIAL), s_o = gemm_skinny_splits(H, nq, SK_PARTIAL),
               s_dn = gemm_skinny_splits(H, c.dec_inter, SK_PARTIAL);
+    const int skip = env_int("Q3ASR_DEC_SKIP", 0);  // timing ablation only (results are wrong when set): bit i drops kernel i of the layer
     double kv_bytes = 0;  // keys + values read by one layer's attention
     for (const ClipInfo& ci : bs->clips) kv_bytes += 2.0 * 2.0 * nkv * (ci.prompt_len + bs->steps_done);
     {
@@ -435,32 +436,35 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         const bool last = l + 1 == c.dec_layers;
         {
             ProfScope ps(h, "dec_qkv", 2.0 * B * H * nqkv, 2.0 * H * nqkv);
-            gemm_skinny(xn, H, B, H, w.qkv_w, nqkv, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 1)) gemm_skinny(xn, H, B, H, w.qkv_w, nqkv, SK_PARTIAL, ws, 0, 0, st);
         }
         {
             ProfScope ps(h, "dec_attn", 0, kv_bytes);
-            decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, m.inv_freq,
+            if (!(skip & 2)) decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, m.inv_freq,
                                      kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale, att, h->num_sms, st);
         }
         {
             ProfScope ps(h, "dec_o", 2.0 * B * nq * H, 2.0 * nq * H);
-            gemm_skinny(att, nq, B, nq, w.o_w, H, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 4)) gemm_skinny(att, nq, B, nq, w.o_w, H, SK_PARTIAL, ws, 0, 0, st);
         }
         {
             ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
-            reduce_resid_rmsnorm_launch(ws, s_o, (long long)B * H, x, w.post_ln, xn, B, H, c.dec_rms_eps, st);
+            if (!(skip & 8)) reduce_resid_rmsnorm_launch(ws, s_o, (long long)B * H, x, w.post_ln, xn, B, H, c.dec_rms_eps, st);
         }
         {
             ProfScope ps(h, "dec_gateup", 4.0 * B * H * c.dec_inter, 4.0 * H * c.dec_inter);
-            gemm_skinny(xn, H, B, H, w.gu_w, 2 * c.dec_inter, SK_SWIGLU, act, c.dec_inter, m.gu_bn / 2, st);
+            // M = B <= 128 fits one M tile of the general kernel; 64-column tiles give N/64 CTAs, each streaming its weight rows once
+            GemmEpiArgs eg;
+            eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
+            if (!(skip & 16)) gemm(xn, H, B, H, w.gu_w, 2 * c.dec_inter, eg, st, false, 64);
         }
         {
             ProfScope ps(h, "dec_down", 2.0 * B * H * c.dec_inter, 2.0 * H * c.dec_inter);
-            gemm_skinny(act, c.dec_inter, B, c.dec_inter, w.down_w, H, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 32)) gemm_skinny(act, c.dec_inter, B, c.dec_inter, w.down_w, H, SK_PARTIAL, ws, 0, 0, st);
         }
         {
             ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
-            reduce_resid_rmsnorm_launch(ws, s_dn, (long long)B * H, x, last ? m.final_norm : m.dec[l + 1].in_ln,
+            if (!(skip & 64)) reduce_resid_rmsnorm_launch(ws, s_dn, (long long)B * H, x, last ? m.final_norm : m.dec[l + 1].in_ln,
                                         last ? bs->dlast.as<bf16>() : xn, B, H, c.dec_rms_eps, st);
         }
         h->launches += 3;
@@ -539,12 +543,21 @@ void run_prefill(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     bs->steps_done = 1;
 }
 
+// RAII: kernels launched while this is alive may overlap their prologue with the previous kernel's tail (PDL)
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
+    ~PdlScope() { pdl_enabled() = prev; }
+};
+
 void decode_step_kernels(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
+    // the first kernel of a step is fully serialised against the previous step; the rest chain programmatically
     embed_splice_launch(bs->st_cur_tok.as<int32_t>(), nullptr, m.embed, nullptr, bs->dx.as<bf16>(), bs->B, c.dec_hidden, st);
     h->launches++;
+    PdlScope pdl(env_int("Q3ASR_NO_PDL", 0) == 0 && !h->prof_on);
     if (bs->B <= SKINNY_MAX_ROWS && c.dec_heads == 2 * c.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0) {
         decoder_layers_decode(h, bs);
         lm_head_argmax(h, bs, nullptr, true);

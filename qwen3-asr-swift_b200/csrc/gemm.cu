@@ -41,7 +41,7 @@ void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, i
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
         attr_set = true;
     }
-    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, gemm_smem_bytes(BN), st>>>(ta, tb, p);
+    launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, gemm_smem_bytes(BN), st, ta, tb, p);
 }
 
 template <int BN>
@@ -109,8 +109,8 @@ __global__ void simt_epi_kernel(const float* acc, long rows, GemmDev p, int epi,
         if (idx >= rows * half) return;
         const int oc = (int)(idx % half);
         const long row = idx / half;
-        const int tn = oc / (BN / 2), j = oc % (BN / 2);
-        const float g = acc[row * p.N + tn * BN + j], u = acc[row * p.N + tn * BN + BN / 2 + j];
+        const int blk = oc / GU_UNIT, j = oc % GU_UNIT;
+        const float g = acc[row * p.N + blk * 2 * GU_UNIT + j], u = acc[row * p.N + blk * 2 * GU_UNIT + GU_UNIT + j];
         reinterpret_cast<bf16*>(p.out)[row * p.ldo + oc] = __float2bfloat16_rn(epi_swiglu(g, u));
         return;
     }
@@ -137,6 +137,8 @@ __global__ void simt_epi_kernel(const float* acc, long rows, GemmDev p, int epi,
 }
 
 __global__ void argmax_reduce_kernel(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int row = blockIdx.x;
     if (row >= rows) return;
     float best = -INFINITY;
@@ -196,7 +198,7 @@ int gemm_pick_bn(int N, int epi, long m_tiles) {
     int smallest = 0;
     for (int bn : cand) {
         if (N % bn) continue;
-        if (epi == EPI_SWIGLU && (bn / 2) % 16) continue;
+        if (epi == EPI_SWIGLU && bn % (2 * GU_UNIT)) continue;
         smallest = bn;
         if (m_tiles * (N / bn) >= 2L * g_num_sms) return bn;
     }
@@ -231,6 +233,7 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     const long m_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_b;
     if (bn == 0) bn = gemm_pick_bn(N, e.epi, m_tiles);
     Q3_CHECK(N % bn == 0, 1, "gemm: N must be a multiple of the tile width");
+    Q3_CHECK(e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0, 1, "gemm: SwiGLU tiles must be multiples of 64 columns");
     p.tiles_n = N / bn;
     Q3_CHECK(e.epi == EPI_ARGMAX || e.out != nullptr, 1, "gemm: null output");
 
@@ -304,7 +307,7 @@ void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev
         Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB, EPI)));
         attr_set = true;
     }
-    gemm_skinny_kernel<NB, EPI><<<grid, 256, sk_smem_bytes(NB, EPI), st>>>(tw, tx, p);
+    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB, EPI), st, tw, tx, p);
 }
 template <int NB>
 void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
@@ -318,27 +321,36 @@ void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, con
 }  // namespace
 
 int gemm_skinny_splits(int N, int K, int epi) {
-    if (epi != SK_PARTIAL) return 1;
+    if (epi == SK_STORE) return 1;
     const int tiles_n = cdiv(N, SK_BM), num_kb = cdiv(K, SK_BK);
     int splits = std::min(num_kb, std::max(1, g_num_sms / tiles_n));
     const int per = cdiv(num_kb, splits);
     return cdiv(num_kb, per);  // no empty slices
 }
 
+size_t gemm_skinny_fix_elems(int N, int K) {
+    const int splits = gemm_skinny_splits(N, K, SK_SWIGLU);
+    return splits > 1 ? (size_t)cdiv(N, SK_BM) * splits * SKINNY_MAX_ROWS * SK_BM : 0;
+}
+
 void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
-                 cudaStream_t st) {
+                 cudaStream_t st, float* fix_ws) {
     Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "gemm_skinny: 1..128 token rows per launch");
     Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0, 1, "gemm_skinny: K and ldx must be multiples of 8");
     if (epi == SK_SWIGLU)
         Q3_CHECK(N % SK_BM == 0 && (gu_half == 32 || gu_half == 64), 1, "gemm_skinny: SwiGLU needs N % 128 == 0 and 32- or 64-row gate/up blocks");
+
     const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
     SkinnyDev p;
     memset(&p, 0, sizeof(p));
     p.N = N;
     p.Mtok = Mtok;
     p.num_kb = cdiv(K, SK_BK);
-    const int splits = gemm_skinny_splits(N, K, epi);
+    const int splits = (epi == SK_SWIGLU && fix_ws == nullptr) ? 1 : gemm_skinny_splits(N, K, epi);
     p.kb_per_split = cdiv(p.num_kb, splits);
+    p.splits = splits;
+    p.fix_ws = fix_ws;
+    p.tickets = fix_ws ? reinterpret_cast<int*>(fix_ws + gemm_skinny_fix_elems(N, K)) : nullptr;
     p.out = out;
     p.ldo = ldo;
     p.split_stride = (long long)Mtok * N;
@@ -371,8 +383,7 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
 
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st) {
     if (rows <= 0) return;
-    argmax_reduce_kernel<<<rows, 256, 0, st>>>(val, idx, rows, tiles, out, out_val);
-    Q3_CUDA(cudaGetLastError());
+    launch_kernel(argmax_reduce_kernel, rows, 256, 0, st, val, idx, rows, tiles, out, out_val);
 }
 
 }  // namespace q3

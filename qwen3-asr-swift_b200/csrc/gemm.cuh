@@ -28,7 +28,7 @@ namespace q3 {
 
 enum GemmEpi : int {
     EPI_NORMAL = 0,  // out(bf16) = [resid +] bf16( act(acc + bias + row_add) ), optional zero mask / row map
-    EPI_SWIGLU = 1,  // tile cols [0,BN/2) gate, [BN/2,BN) up: out = bf16( bf16(silu(bf16 g)) * bf16 u )
+    EPI_SWIGLU = 1,  // columns alternate 32 gate / 32 up (GU_UNIT): out = bf16( bf16(silu(bf16 g)) * bf16 u ), N/2 outputs
     EPI_F32 = 2,     // out(fp32) = acc + bias
     EPI_ARGMAX = 3,  // per (row, n-tile): max / lowest index of bf16(acc)
 };
@@ -37,6 +37,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_MAX_TAPS = 16;
+constexpr int GU_UNIT = 32;  // fused gate/up weights: 32 gate rows, then the matching 32 up rows, repeating
 
 struct GemmDev {  // by-value kernel parameter
     int N, num_kb, kb_per_tap, C;
@@ -134,21 +135,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            ptx::grid_dep_launch();
+            const uint32_t tx_bytes = (uint32_t)(tile_rows * 128 + BN * 128);
+            // The weight (B) tiles do not depend on the previous kernel: start the first tile's ring with them, then wait for
+            // the producer of A (programmatic dependent launch; a no-op for ordinary launches).
+            int pre = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                const int n0 = gemm_tile_coord(p, blockIdx.x).tn * BN;
+                pre = min(STAGES, p.num_kb);
+                int tap = 0, cc = 0;
+                for (int i = 0; i < pre; i++) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[i], tx_bytes);
+                    ptx::tma_load_2d(smem + i * STAGE_BYTES + GEMM_BM * 128, &tmB, tap * p.C + cc * GEMM_BK, n0, &full_bar[i]);
+                    if (++cc == p.kb_per_tap) { cc = 0; tap++; }
+                }
+            }
+            ptx::grid_dep_wait();  // A (and everything the epilogue reads) comes from the previous kernel
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(tile_rows * 128 + BN * 128);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const TileCoord tc = gemm_tile_coord(p, tile);
                 const int n0 = tc.tn * BN;
                 int tap = 0, cc = 0;
                 for (int kb = 0; kb < p.num_kb; kb++) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + GEMM_BM * 128;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    if (pre > 0) {
+                        pre--;  // slot already armed and its B tile in flight
+                    } else {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                        ptx::tma_load_2d(sb, &tmB, tap * p.C + cc * GEMM_BK, n0, &full_bar[stage]);
+                    }
                     ptx::tma_load_4d(sa, &tmA, cc * GEMM_BK, tc.w0 * p.sw + p.tap_dw[tap], tc.h0 * p.sh + p.tap_dh[tap],
                                      tc.b0, &full_bar[stage]);
-                    ptx::tma_load_2d(sb, &tmB, tap * p.C + cc * GEMM_BK, n0, &full_bar[stage]);
                     if (++cc == p.kb_per_tap) { cc = 0; tap++; }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -215,25 +235,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
 
             if constexpr (EPI == EPI_SWIGLU) {
-                constexpr int HALF = BN / 2;
-                bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * HALF;
+                // weight rows alternate GU_UNIT gate rows / GU_UNIT up rows, so every 64 accumulator columns hold 32 outputs
+                if constexpr (BN % (2 * GU_UNIT) == 0) {
+                    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * (BN / 2);
 #pragma unroll 1
-                for (int c = 0; c < HALF / 16; c++) {
-                    uint32_t g[16], u[16];
-                    ptx::tmem_ld_32x16(t_row + c * 16, g);
-                    ptx::tmem_ld_32x16(t_row + HALF + c * 16, u);
-                    ptx::tmem_ld_wait();
-                    if (row_ok) {
-                        uint32_t pk[8];
+                    for (int c = 0; c < BN / 32; c++) {  // 16 outputs per step
+                        const int col = (c >> 1) * (2 * GU_UNIT) + (c & 1) * 16;
+                        uint32_t g[16], u[16];
+                        ptx::tmem_ld_32x16(t_row + col, g);
+                        ptx::tmem_ld_32x16(t_row + col + GU_UNIT, u);
+                        ptx::tmem_ld_wait();
+                        if (row_ok) {
+                            uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const float a = epi_swiglu(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
-                            const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
-                            pk[j] = pack_bf16x2(a, bb);
+                            for (int j = 0; j < 8; j++) {
+                                const float a = epi_swiglu(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
+                                const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
+                                pk[j] = pack_bf16x2(a, bb);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
+                            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
-                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
             } else if constexpr (EPI == EPI_ARGMAX) {
@@ -382,12 +405,15 @@ enum SkinnyEpi : int {
     SK_SWIGLU = 2,   // W rows interleaved gate/up in blocks of `gu_half`: out(bf16)[m][j] = bf16(bf16(silu(bf16 g)) * bf16 u)
 };
 
-// number of K splits the launch will use for this shape (1 for SK_STORE / SK_SWIGLU)
+// number of K splits the launch will use for this shape (1 for SK_STORE; SK_SWIGLU splits only when given a fix-up workspace)
 int gemm_skinny_splits(int N, int K, int epi);
+// fp32 elements of the SK_SWIGLU split-K fix-up workspace for this shape (0: no split); it is followed by one int ticket
+// per 128-row tile, which must be zero before the first launch (the kernel leaves them zero)
+size_t gemm_skinny_fix_elems(int N, int K);
 // SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo];
-// SK_SWIGLU: W = gate/up rows interleaved in blocks of gu_half rows, out = bf16 [Mtok, ldo] (N/2 columns)
+// SK_SWIGLU: W = gate/up rows interleaved in blocks of gu_half (= GU_UNIT) rows, out = bf16 [Mtok, ldo] (N/2 columns)
 void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
-                 cudaStream_t st);
+                 cudaStream_t st, float* fix_ws = nullptr);
 // final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st);
 

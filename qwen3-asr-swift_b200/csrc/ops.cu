@@ -1,7 +1,10 @@
 // ops.cu — CUDA-core kernels around the GEMMs: conv2d1, LayerNorm, RMSNorm, embedding gather/splice,
 // q/k-norm + RoPE + KV-cache write, paged decode attention, greedy bookkeeping, dtype/init helpers.
 // Reductions are warp-shuffle based (one warp per row / per head).
+#include <algorithm>
+
 #include "ops.cuh"
+#include "ptx.cuh"
 
 namespace q3 {
 
@@ -110,6 +113,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 template <int MAXV>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                       int rows, int d, float eps, const int* __restrict__ row_index) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -141,6 +146,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
 // ------------------------------------------------------------------------------------------
 __global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const int* __restrict__ audio_src, const bf16* __restrict__ embed,
                                     const bf16* __restrict__ audio, bf16* __restrict__ x, int rows, int h) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int vec = h >> 3;  // 16-byte vectors per row
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)rows * vec) return;
@@ -334,12 +341,44 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
                                                                     const float* __restrict__ inv_freq, KvCache cache, int layer,
                                                                     const int* __restrict__ kv_len, int heads, float scale_log2,
                                                                     bf16* __restrict__ out) {
+    ptx::grid_dep_launch();
     const int seq = blockIdx.x, kvh = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_q[GROUP][128];
+    __shared__ __align__(16) bf16 s_new[2][128];  // the new token's k and v rows
     __shared__ float s_m[GROUP][NW], s_l[GROUP][NW];
     __shared__ float s_acc[GROUP][NW][128];
     const int* pt = cache.page_table + (size_t)seq * cache.max_pages;
+
+    // ---- 0. start streaming the cached keys/values: each warp owns a cp.async ring of 8-key chunks (K and V rows are
+    //         contiguous inside a page).  Nothing here depends on the previous kernel, so it runs ahead of the
+    //         programmatic-dependency wait; the row of the new token (position len - 1) is patched in from shared memory. ----
+    const int len = kv_len[seq];
+    extern __shared__ uint4 da_smem[];
+    bf16* ring = reinterpret_cast<bf16*>(da_smem) + (size_t)warp * DA_STAGES * 2 * DA_CHUNK * 128;
+    const size_t head_off = (((size_t)layer * 2) * cache.kv_heads + kvh) * (KV_PAGE * 128);
+    const size_t page_elems = (size_t)cache.layers * 2 * cache.kv_heads * (KV_PAGE * 128);
+    const size_t v_off = (size_t)cache.kv_heads * (KV_PAGE * 128);
+    const int n_chunks = (len + DA_CHUNK - 1) / DA_CHUNK;
+    auto issue = [&](int chunk, int stage) {
+        if (chunk < n_chunks) {
+            const int j0 = chunk * DA_CHUNK;
+            const bf16* kb = cache.pool + (size_t)pt[j0 / KV_PAGE] * page_elems + head_off + (j0 % KV_PAGE) * 128;
+            bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
+#pragma unroll
+            for (int i = 0; i < DA_CHUNK * 16 / 32; i++) {
+                const int seg = i * 32 + lane;  // 16-byte segment of the chunk; key = seg / 16
+                const uint32_t n = j0 + (seg >> 4) < len ? 16u : 0u;  // rows past the end are zero-filled
+                cp_async16(sk + seg * 8, kb + seg * 8, n);
+                cp_async16(sk + DA_CHUNK * 128 + seg * 8, kb + v_off + seg * 8, n);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < DA_STAGES - 1; s++) issue(warp + s * NW, s);
+
+    ptx::grid_dep_wait();
 
     // ---- 1. new-token q / k / v ----
     if (warp < GROUP + 2) {
@@ -348,10 +387,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
         const int col = slot < GROUP ? (kvh * GROUP + slot) * 128
                                      : slot == GROUP ? heads * 128 + kvh * 128 : (heads + cache.kv_heads) * 128 + kvh * 128;
         const float* src = qkv_part + (size_t)seq * nqkv + col + d0;
-        float4 a = *reinterpret_cast<const float4*>(src);
-        for (int s = 1; s < splits; s++) {
-            const float4 b = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < splits; s0 += 4) {  // fixed summation order, four loads in flight
+            float4 b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                b[i] = s0 + i < splits ? *reinterpret_cast<const float4*>(src + (size_t)(s0 + i) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
         }
         float x[4] = {bf16_round(a.x), bf16_round(a.y), bf16_round(a.z), bf16_round(a.w)};
         const int p = pos[seq];
@@ -384,14 +427,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
             bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (slot == GROUP ? 0 : 1)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
                         (p % KV_PAGE) * 128 + d0;
             st8(dst, x[0], x[1], x[2], x[3]);
+            st8(&s_new[slot - GROUP][d0], x[0], x[1], x[2], x[3]);
         }
     }
-    __syncthreads();  // s_q ready; the new k/v rows are visible to this CTA
+    __syncthreads();  // s_q and s_new ready
 
-    // ---- 2. attention: each warp streams chunks of 8 keys (K and V rows are contiguous inside a page) through
-    //         its own cp.async ring, so the bytes in flight do not depend on registers ----
+    // ---- 2. attention ----
     const int grp = lane >> 3, sub = lane & 7;
-    const int len = kv_len[seq];
     // lane `sub` owns dims [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8): a lane group reads 128 contiguous bytes
     float qf[GROUP][16];
 #pragma unroll
@@ -406,36 +448,21 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
 #pragma unroll
         for (int t = 0; t < 16; t++) acc[g][t] = 0.f;
     }
-    extern __shared__ uint4 da_smem[];
-    bf16* ring = reinterpret_cast<bf16*>(da_smem) + (size_t)warp * DA_STAGES * 2 * DA_CHUNK * 128;
-    const size_t head_off = (((size_t)layer * 2) * cache.kv_heads + kvh) * (KV_PAGE * 128);
-    const size_t page_elems = (size_t)cache.layers * 2 * cache.kv_heads * (KV_PAGE * 128);
-    const size_t v_off = (size_t)cache.kv_heads * (KV_PAGE * 128);
-    const int n_chunks = (len + DA_CHUNK - 1) / DA_CHUNK;
-    auto issue = [&](int chunk, int stage) {
-        if (chunk < n_chunks) {
-            const int j0 = chunk * DA_CHUNK;
-            const bf16* kb = cache.pool + (size_t)pt[j0 / KV_PAGE] * page_elems + head_off + (j0 % KV_PAGE) * 128;
-            bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
-#pragma unroll
-            for (int i = 0; i < DA_CHUNK * 16 / 32; i++) {
-                const int seg = i * 32 + lane;  // 16-byte segment of the chunk; key = seg / 16
-                const uint32_t n = j0 + (seg >> 4) < len ? 16u : 0u;  // rows past the end are zero-filled
-                cp_async16(sk + seg * 8, kb + seg * 8, n);
-                cp_async16(sk + DA_CHUNK * 128 + seg * 8, kb + v_off + seg * 8, n);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-#pragma unroll
-    for (int s = 0; s < DA_STAGES - 1; s++) issue(warp + s * NW, s);
     int stage = 0;
     for (int chunk = warp; chunk < n_chunks; chunk += NW) {
         issue(chunk + (DA_STAGES - 1) * NW, (stage + DA_STAGES - 1) % DA_STAGES);
         asm volatile("cp.async.wait_group %0;" ::"n"(DA_STAGES - 1) : "memory");
         __syncwarp();
-        const bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
+        bf16* sk = ring + (size_t)stage * 2 * DA_CHUNK * 128;
         const int j0 = chunk * DA_CHUNK;
+        if (chunk == n_chunks - 1) {  // the prefetch may have read the new token's row before it was written
+            const int row = (len - 1) - j0;
+            reinterpret_cast<uint4*>(sk + (lane >> 4) * DA_CHUNK * 128 + row * 128)[lane & 15] = reinterpret_cast<const uint4*>(s_new[lane >> 4])[lane & 15];
+            __syncwarp();
+        }
+        // scores of the chunk's two keys per lane group, then one running-max update for both
+        float sc[GROUP][2];
+        uint32_t vraw[2][8];
 #pragma unroll
         for (int u = 0; u < DA_CHUNK / 4; u++) {
             const int key = u * 4 + grp;
@@ -445,31 +472,46 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
             const uint4 v0 = *reinterpret_cast<const uint4*>(sk + DA_CHUNK * 128 + key * 128 + sub * 8);
             const uint4 v1 = *reinterpret_cast<const uint4*>(sk + DA_CHUNK * 128 + key * 128 + 64 + sub * 8);
             const uint32_t kw32[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-            const uint32_t vw32[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            float kf[16], vf[16];
+            vraw[u][0] = v0.x; vraw[u][1] = v0.y; vraw[u][2] = v0.z; vraw[u][3] = v0.w;
+            vraw[u][4] = v1.x; vraw[u][5] = v1.y; vraw[u][6] = v1.z; vraw[u][7] = v1.w;
+            float s[GROUP];
+#pragma unroll
+            for (int g = 0; g < GROUP; g++) s[g] = 0.f;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                const float2 a = unpack_bf16x2(kw32[t]), b = unpack_bf16x2(vw32[t]);
-                kf[2 * t] = a.x; kf[2 * t + 1] = a.y;
-                vf[2 * t] = b.x; vf[2 * t + 1] = b.y;
+                const float2 kk = unpack_bf16x2(kw32[t]);
+#pragma unroll
+                for (int g = 0; g < GROUP; g++) s[g] = fmaf(qf[g][2 * t + 1], kk.y, fmaf(qf[g][2 * t], kk.x, s[g]));
             }
 #pragma unroll
             for (int g = 0; g < GROUP; g++) {
-                float s = 0.f;
+                s[g] += __shfl_xor_sync(0xffffffffu, s[g], 1);
+                s[g] += __shfl_xor_sync(0xffffffffu, s[g], 2);
+                s[g] += __shfl_xor_sync(0xffffffffu, s[g], 4);
+                sc[g][u] = ok ? s[g] * scale_log2 : -INFINITY;
+            }
+        }
+        float b0[GROUP], b1[GROUP];
 #pragma unroll
-                for (int t = 0; t < 16; t++) s = fmaf(qf[g][t], kf[t], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s = ok ? s * scale_log2 : -INFINITY;
-                const float mn = fmaxf(m[g], s);
-                const float alpha = mn == -INFINITY ? 1.f : exp2f(m[g] - mn);
-                const float pj = mn == -INFINITY ? 0.f : exp2f(s - mn);
-                l[g] = l[g] * alpha + pj;
-                const float pb = bf16_round(pj);
+        for (int g = 0; g < GROUP; g++) {
+            const float mn = fmaxf(m[g], fmaxf(sc[g][0], sc[g][1]));
+            const float alpha = mn == -INFINITY ? 1.f : exp2f(m[g] - mn);
+            const float p0 = mn == -INFINITY ? 0.f : exp2f(sc[g][0] - mn);
+            const float p1 = mn == -INFINITY ? 0.f : exp2f(sc[g][1] - mn);
+            l[g] = l[g] * alpha + (p0 + p1);
+            b0[g] = bf16_round(p0);
+            b1[g] = bf16_round(p1);
+            m[g] = mn;
 #pragma unroll
-                for (int t = 0; t < 16; t++) acc[g][t] = fmaf(pb, vf[t], acc[g][t] * alpha);
-                m[g] = mn;
+            for (int t = 0; t < 16; t++) acc[g][t] *= alpha;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const float2 va = unpack_bf16x2(vraw[0][t]), vb = unpack_bf16x2(vraw[1][t]);
+#pragma unroll
+            for (int g = 0; g < GROUP; g++) {
+                acc[g][2 * t] = fmaf(b1[g], vb.x, fmaf(b0[g], va.x, acc[g][2 * t]));
+                acc[g][2 * t + 1] = fmaf(b1[g], vb.y, fmaf(b0[g], va.y, acc[g][2 * t + 1]));
             }
         }
         __syncwarp();  // the slot is refilled by the next iteration's issue
@@ -522,19 +564,39 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
 // y[r] = RMSNorm(x[r]) * w  (the next block's input).  One CTA per row, 4 columns per thread.
 // FloatTextDecoder.swift:144-147 (residual adds) + :139, :146 (the norms that follow them).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) reduce_resid_rmsnorm_kernel(const float* __restrict__ part, int splits, long long split_stride,
-                                                                   bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
-                                                                   int d, float eps) {
-    const int row = blockIdx.x, c0 = threadIdx.x * 4;
-    const bool on = c0 < d;
+__global__ void __launch_bounds__(1024) reduce_resid_rmsnorm_kernel(const float* __restrict__ part, int splits, long long split_stride,
+                                                                    bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                                    int d, float eps) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    // blockDim.x = (d / 4) * SG: thread (cg, sg) sums the splits sg, sg + SG, ... of four columns (all loads in flight at once);
+    // the SG partial sums are then added in a fixed order, so the result does not depend on scheduling.
+    __shared__ float4 s_part[1024];
+    __shared__ float s_red[32];
+    const int ncg = d >> 2, sg_count = blockDim.x / ncg;
+    const int row = blockIdx.x, cg = threadIdx.x % ncg, sg = threadIdx.x / ncg, c0 = cg * 4;
+    const float* src = part + (size_t)row * d + c0;
+    float4 b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int sp = sg + i * sg_count;
+        b[i] = sp < splits ? *reinterpret_cast<const float4*>(src + (size_t)sp * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 a = b[0];
+#pragma unroll
+    for (int i = 1; i < 4; i++) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
+    for (int sp = sg + 4 * sg_count; sp < splits; sp += sg_count) {  // more than 4 * SG splits: rare, serial tail
+        const float4 t = *reinterpret_cast<const float4*>(src + (size_t)sp * split_stride);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    s_part[threadIdx.x] = a;
+    __syncthreads();
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float q = 0.f;
-    if (on) {
-        const float* src = part + (size_t)row * d + c0;
-        float4 a = *reinterpret_cast<const float4*>(src);
-        for (int s = 1; s < splits; s++) {
-            const float4 b = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    if (sg == 0) {
+        for (int g = 1; g < sg_count; g++) {
+            const float4 t = s_part[g * ncg + cg];
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         const uint2 u = ld8(x + (size_t)row * d + c0);
         const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y);
@@ -545,14 +607,13 @@ __global__ void __launch_bounds__(512) reduce_resid_rmsnorm_kernel(const float* 
         st8(x + (size_t)row * d + c0, v[0], v[1], v[2], v[3]);
         q = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
     }
-    __shared__ float s_red[16];
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = q;
     __syncthreads();
-    float tot = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += s_red[i];
-    const float r = rsqrtf(tot / (float)d + eps);
-    if (on) {
+    if (sg == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < (ncg >> 5); i++) tot += s_red[i];  // the sg == 0 threads are the first ncg / 32 warps
+        const float r = rsqrtf(tot / (float)d + eps);
         const uint2 wu = ld8(w + c0);
         const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
         st8(y + (size_t)row * d + c0, v[0] * r * w0.x, v[1] * r * w0.y, v[2] * r * w1.x, v[3] * r * w1.y);
@@ -561,6 +622,8 @@ __global__ void __launch_bounds__(512) reduce_resid_rmsnorm_kernel(const float* 
 
 // ------------------------------------------------------------------------------------------
 __global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int step = *s.step;
     if (i < n_seqs) {
@@ -641,16 +704,14 @@ void rmsnorm_launch(const bf16* x, const bf16* w, bf16* y, int rows, int d, floa
     if (rows <= 0) return;
     Q3_CHECK(d % 128 == 0 && d <= 2048, 1, "rmsnorm: d must be a multiple of 128, <= 2048");
     const unsigned grid = blocks_for(rows, 8);
-    if (d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, st>>>(x, w, y, rows, d, eps, row_index);
-    else rmsnorm_kernel<16><<<grid, 256, 0, st>>>(x, w, y, rows, d, eps, row_index);
-    Q3_CUDA(cudaGetLastError());
+    if (d <= 1024) launch_kernel(rmsnorm_kernel<8>, grid, 256, 0, st, x, w, y, rows, d, eps, row_index);
+    else launch_kernel(rmsnorm_kernel<16>, grid, 256, 0, st, x, w, y, rows, d, eps, row_index);
 }
 
 void embed_splice_launch(const int32_t* ids, const int* audio_src, const bf16* embed, const bf16* audio, bf16* x, int rows, int h,
                          cudaStream_t st) {
     if (rows <= 0) return;
-    embed_splice_kernel<<<blocks_for((size_t)rows * (h / 8), 256), 256, 0, st>>>(ids, audio_src, embed, audio, x, rows, h);
-    Q3_CUDA(cudaGetLastError());
+    launch_kernel(embed_splice_kernel, blocks_for((size_t)rows * (h / 8), 256), 256, 0, st, ids, audio_src, embed, audio, x, rows, h);
 }
 
 void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* kw, const int* pos, const int* row_seq, int rows,
@@ -695,26 +756,26 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
         attr = true;
     }
     if ((long)n_seqs * cache.kv_heads >= 2L * num_sms)
-        decode_attn_fused_kernel<2, 4><<<grid, 128, decode_attn_smem(4), st>>>(qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps, inv_freq,
-                                                                               cache, layer, kv_len, heads, sl2, out);
+        launch_kernel(decode_attn_fused_kernel<2, 4>, grid, 128, decode_attn_smem(4), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                      inv_freq, cache, layer, kv_len, heads, sl2, out);
     else
-        decode_attn_fused_kernel<2, 16><<<grid, 512, decode_attn_smem(16), st>>>(qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
-                                                                                 inv_freq, cache, layer, kv_len, heads, sl2, out);
-    Q3_CUDA(cudaGetLastError());
+        launch_kernel(decode_attn_fused_kernel<2, 16>, grid, 512, decode_attn_smem(16), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos,
+                      eps, inv_freq, cache, layer, kv_len, heads, sl2, out);
 }
 
 void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,
                                  float eps, cudaStream_t st) {
     if (rows <= 0) return;
     Q3_CHECK(d % 128 == 0 && d <= 2048, 1, "reduce_resid_rmsnorm: d must be a multiple of 128, <= 2048");
-    reduce_resid_rmsnorm_kernel<<<rows, d / 4, 0, st>>>(part, splits, split_stride, x, w, y, d, eps);
-    Q3_CUDA(cudaGetLastError());
+    const int ncg = d / 4;
+    int sg = std::max(1, std::min(1024 / ncg, (splits + 3) / 4 > 0 ? 1024 / ncg : 1));
+    while (sg > 1 && sg > splits) sg >>= 1;  // no more split groups than splits
+    launch_kernel(reduce_resid_rmsnorm_kernel, rows, ncg * sg, 0, st, part, splits, split_stride, x, w, y, d, eps);
 }
 
 void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st) {
     Q3_CHECK(n_seqs <= 1024, 1, "decode_advance: at most 1024 sequences per handle");
-    decode_advance_kernel<<<1, 1024, 0, st>>>(s, n_seqs);
-    Q3_CUDA(cudaGetLastError());
+    launch_kernel(decode_advance_kernel, 1, 1024, 0, st, s, n_seqs);
 }
 
 void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st) {

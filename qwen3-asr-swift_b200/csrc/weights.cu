@@ -332,8 +332,7 @@ void model_commit(Handle* h) {
     const int nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd;
     m->embed = W("model.embed_tokens.weight");
     m->final_norm = W("model.norm.weight");
-    m->gu_bn = (2 * I) % 128 == 0 && I % 64 == 0 ? 128 : 64;
-    Q3_CHECK((2 * I) % m->gu_bn == 0, Q3ASR_ERR_INVALID, "dec_inter must be a multiple of 64");
+    Q3_CHECK(I % GU_UNIT == 0, Q3ASR_ERR_INVALID, "dec_inter must be a multiple of 32");
     m->dec.resize(c.dec_layers);
     for (int l = 0; l < c.dec_layers; l++) {
         const std::string p = "model.layers." + std::to_string(l) + ".";
@@ -350,14 +349,15 @@ void model_commit(Handle* h) {
                                 cudaMemcpyDeviceToDevice, st));
         Q3_CUDA(cudaMemcpyAsync(e.qkv_w + (size_t)(nq + nkv) * hdim, W(p + "self_attn.v_proj.weight"), (size_t)nkv * hdim * 2,
                                 cudaMemcpyDeviceToDevice, st));
-        // gate/up interleaved per output tile: tile t holds gate rows [t*half, (t+1)*half) then the same up rows
+        // gate/up interleaved in units of GU_UNIT rows: [g 0..31 | u 0..31 | g 32..63 | u 32..63 | ...], so any tile that is a
+        // multiple of 64 rows (columns of the accumulator) holds matching gate and up values for the SwiGLU epilogue
         e.gu_w = dev_alloc<bf16>(m, (size_t)2 * I * hdim, &h->dev_bytes);
-        const int half = m->gu_bn / 2;
+        const int half = GU_UNIT;
         const bf16* gw = W(p + "mlp.gate_proj.weight");
         const bf16* uw = W(p + "mlp.up_proj.weight");
         // rows of tile t: a 2-D copy with destination pitch 2*half rows
-        copy_rows(e.gu_w, (size_t)m->gu_bn * hdim, gw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
-        copy_rows(e.gu_w + (size_t)half * hdim, (size_t)m->gu_bn * hdim, uw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
+        copy_rows(e.gu_w, (size_t)2 * half * hdim, gw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
+        copy_rows(e.gu_w + (size_t)half * hdim, (size_t)2 * half * hdim, uw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
     }
     {
         std::vector<float> inv(hd / 2);

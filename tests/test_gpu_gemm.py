@@ -26,6 +26,11 @@ def _close_bf16(got, ref, what, ulps=1.5):
     assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} off; worst {np.abs(got - ref).max():.4g} at {np.argwhere(bad)[:4].tolist()}"
 
 
+def _interleave_gate_up(G, U, unit=32):
+    # the library stores the fused gate/up weight as 32 gate rows, the matching 32 up rows, repeating (csrc/weights.cu)
+    return np.concatenate([np.concatenate([G[t * unit:(t + 1) * unit], U[t * unit:(t + 1) * unit]]) for t in range(G.shape[0] // unit)])
+
+
 SHAPES = [(128, 128, 64), (256, 256, 256), (300, 256, 192), (1000, 896, 896), (77, 480, 4320), (64, 2048, 128), (513, 160, 96),
           (1, 128, 128), (130, 32, 40)]
 
@@ -84,9 +89,7 @@ def test_gemm_swiglu(tiny_model, bn):
     rng = np.random.default_rng(5 + bn)
     M, I, K = 140, 512, 128
     A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
-    half = bn // 2
-    # the library interleaves gate/up rows per output tile (csrc/weights.cu)
-    Wi = np.concatenate([np.concatenate([G[t * half:(t + 1) * half], U[t * half:(t + 1) * half]]) for t in range(I // half)])
+    Wi = _interleave_gate_up(G, U)
     g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
     u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
     s = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
@@ -153,16 +156,16 @@ def test_skinny_partial_and_store(tiny_model, M, N, K):
 @pytest.mark.parametrize("M,I,bn", [(64, 3072, 128), (7, 256, 128), (40, 192, 64), (128, 512, 64), (16, 128, 128)])
 def test_skinny_swiglu(tiny_model, M, I, bn):
     rng = np.random.default_rng(M + I + bn)
-    K = 256
+    K = 1024 if I >= 3072 else 256  # the 0.6B shape splits K three ways (last-arriver fix-up); small ones split up to four ways
     A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
-    half = bn // 2
-    Wi = np.concatenate([np.concatenate([G[t * half:(t + 1) * half], U[t * half:(t + 1) * half]]) for t in range(I // half)])
+    Wi = _interleave_gate_up(G, U)
     g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
     u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
     s = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
     got = tiny_model.debug_gemm(A, Wi, epi=6, bn=bn)
-    _close_bf16(got, s * u, f"skinny swiglu {M}x{I} bn={bn}", ulps=3)
+    # three bf16 roundings (g, silu(g), u) feed the product; with K = 1024 the fp32 summation order flips a few of them
+    _close_bf16(got, s * u, f"skinny swiglu {M}x{I} bn={bn}", ulps=3 if K == 256 else 6)
     # the two SwiGLU kernels agree bit for bit when fed the same operands (same epilogue arithmetic)
     if M <= 128:
         same = tiny_model.debug_gemm(A, Wi, epi=1, bn=bn)
-        assert (np.abs(got - same) <= 2.0 ** -7 * np.maximum(np.abs(same), 1e-2)).all()
+        assert (np.abs(got - same) <= (1 if K == 256 else 4) * 2.0 ** -7 * np.maximum(np.abs(same), 1e-2)).all()

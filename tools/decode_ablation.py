@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Timing ablation of the decode step (debug): drops one kernel of the layer at a time (Q3ASR_DEC_SKIP bit mask; results
+are wrong while a bit is set) and reports the decode-stage time per step.  Usage: python tools/decode_ablation.py [clips] [tokens]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
+import q3asr  # noqa: E402
+from oracle import synth  # noqa: E402
+
+clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+m = q3asr.Qwen3ASRModel.random_init("0.6B")
+x = [synth.clip(i, 480000) for i in range(clips)]
+m.batch_upload(x)
+names = ["none", "qkv", "attn", "o", "norm1", "gateup", "down", "norm2", "all-gemm", "all-but-attn", "everything"]
+masks = [0, 1, 2, 4, 8, 16, 32, 64, 1 | 4 | 16 | 32, 1 | 4 | 8 | 16 | 32 | 64, 127]
+base = None
+for name, mask in zip(names, masks):
+    os.environ["Q3ASR_DEC_SKIP"] = str(mask)
+    best = 1e9
+    for _ in range(3):
+        m.batch_run(q3asr.STAGE_ALL, tokens, False)
+        m.sync()
+        m.batch_download(clips, tokens)
+        best = min(best, m.stage_ms()[3])
+    per = best / (tokens - 1) * 1000.0
+    base = base or per
+    print(f"skip {name:14s} decode {best:8.2f} ms  {per:8.1f} us/step  {per / 28:6.2f} us/layer  delta {(base - per) / 28:6.2f} us/layer", flush=True)
+m.close()
