@@ -172,10 +172,10 @@ void upload_ints(Handle* h, BatchState* bs, const std::vector<int>& ints) {
 void reserve_encoder(Handle* h, BatchState* bs) {
     const q3asr_config& c = h->cfg;
     const Geom g(c);
-    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 32)));
+    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 30)));
     const size_t d = c.enc_d_model;
     bs->a1.reserve((size_t)grp * 64 * g.w1 * g.C * 2);
-    bs->a2.reserve((size_t)grp * 32 * g.w2 * g.C * 2);
+    bs->a2.reserve((size_t)bs->n_chunks * 32 * g.w2 * g.C * 2);  // conv3 runs once over all chunks
     bs->a3.reserve((size_t)bs->n_chunks * 16 * g.w3 * g.C * 2);
     const size_t T = std::max(bs->n_tok, 1);
     bs->ex.reserve(T * d * 2);
@@ -195,7 +195,15 @@ void reserve_decoder(Handle* h, BatchState* bs) {
     bs->dqkv.reserve(R * (nq + 2 * nkv) * 2);
     bs->dq.reserve(R * nq * 2);
     bs->dkc.reserve(R * nkv * 2);
-    bs->dvc.reserve(R * nkv * 2);
+    {  // RoPE table for every position the KV pages can hold
+        const int n_pos = bs->pages_per_seq * KV_PAGE;
+        if (bs->rope_n < n_pos) {
+            bs->rope_tab.reserve((size_t)n_pos * 64 * sizeof(float2));
+            rope_table_launch(h->model->inv_freq, n_pos, bs->rope_tab.as<float2>(), h->stream);
+            h->launches++;
+            bs->rope_n = n_pos;
+        }
+    }
     bs->datt.reserve(R * nq * 2);
     bs->dact.reserve(R * c.dec_inter * 2);
     bs->dlast.reserve((size_t)bs->B * H * 2);
@@ -254,7 +262,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
     if (bs->n_tok == 0) { bs->enc_done = true; return; }
 
     // ---- conv stack, walked in groups of chunks so conv1/conv2 activations stay L2-resident ----
-    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 32)));
+    const int grp = std::min(bs->n_chunks, std::max(1, env_int("Q3ASR_CONV_GROUP", 30)));
     const Conv1Chunk* chunks = reinterpret_cast<const Conv1Chunk*>(ints + bs->o_conv_chunks);
     GemmShape s2, s3;
     s2.Wb = g.w2; s2.Hb = 1; s2.Bb = std::max(1, GEMM_BM / g.w2);
@@ -276,21 +284,24 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
         a.ptr = bs->a1.as<bf16>(); a.C = g.C; a.W = g.w1; a.H = 64; a.B = n;
         a.sW = g.C; a.sH = (long)g.w1 * g.C; a.sB = 64L * g.w1 * g.C;
         s2.OB = n;
-        GemmEpiArgs e2 = epi_store(bs->a2.p, g.C, m.conv2_b, 1);
+        GemmEpiArgs e2 = epi_store(bs->a2.as<bf16>() + (size_t)c0 * 32 * g.w2 * g.C, g.C, m.conv2_b, 1);
         e2.valid_w = ints + bs->o_vw2 + c0;
         {
             ProfScope ps(h, "conv2", 2.0 * n * 32.0 * g.w2 * g.C * 9.0 * g.C, 0);
             gemm_conv(a, s2, m.conv2_w, g.C, e2, st);
         }
-        a.ptr = bs->a2.as<bf16>(); a.W = g.w2; a.H = 32;
-        a.sH = (long)g.w2 * g.C; a.sB = 32L * g.w2 * g.C;
-        s3.OB = n;
-        GemmEpiArgs e3 = epi_store(bs->a3.as<bf16>() + (size_t)c0 * 16 * g.w3 * g.C, g.C, m.conv3_b, 1);
-        e3.valid_w = ints + bs->o_vw3 + c0;
-        {
-            ProfScope ps(h, "conv3", 2.0 * n * 16.0 * g.w3 * g.C * 9.0 * g.C, 0);
-            gemm_conv(a, s3, m.conv3_w, g.C, e3, st);
-        }
+    }
+    // conv3 in one launch over every chunk: per group it would be 192 tiles on 148 SMs (two waves, the second 30 % full);
+    // the conv2 output (24 MB per 32 chunks) is read back from HBM instead of L2, which costs far less than the idle SMs did.
+    {
+        GemmA a;
+        a.ptr = bs->a2.as<bf16>(); a.C = g.C; a.W = g.w2; a.H = 32; a.B = bs->n_chunks;
+        a.sW = g.C; a.sH = (long)g.w2 * g.C; a.sB = 32L * g.w2 * g.C;
+        s3.OB = bs->n_chunks;
+        GemmEpiArgs e3 = epi_store(bs->a3.p, g.C, m.conv3_b, 1);
+        e3.valid_w = ints + bs->o_vw3;
+        ProfScope ps(h, "conv3", 2.0 * bs->n_chunks * 16.0 * g.w3 * g.C * 9.0 * g.C, 0);
+        gemm_conv(a, s3, m.conv3_w, g.C, e3, st);
     }
     // ---- conv_out over the [chunk, t, (f, c)] view of the conv3 output, + positions, gather valid tokens ----
     {
@@ -384,12 +395,12 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
         tag("pre_qkv", "dec_qkv", 2.0 * Rd * H * nqkv, 2.0 * H * nqkv);
         gemm(xn, H, rows, H, w.qkv_w, nqkv, epi_store(qkv, nqkv, nullptr), st);
         tag("pre_rope", "dec_rope", 0, 4.0 * Rd * nqkv);
+        // v is not transformed: the prefill attention reads it straight from the QKV product, only k needs a contiguous copy
         qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
-                              c.dec_rope_theta, m.inv_freq, q, prefill ? bs->dkc.as<bf16>() : nullptr,
-                              prefill ? bs->dvc.as<bf16>() : nullptr, kc, l, st);
+                              bs->rope_tab.as<float2>(), q, prefill ? bs->dkc.as<bf16>() : nullptr, nullptr, kc, l, st);
         tag("pre_attn", "dec_attn", prefill ? 4.0 * causal_pairs * nq : 0, 0);
         if (prefill)
-            flash_attn_launch(q, nq, bs->dkc.as<bf16>(), nkv, bs->dvc.as<bf16>(), nkv, att, nq, segs, c.dec_heads,
+            flash_attn_launch(q, nq, bs->dkc.as<bf16>(), nkv, qkv + nq + nkv, nqkv, att, nq, segs, c.dec_heads,
                               c.dec_heads / c.dec_kv_heads, hd, true, scale, st);
         else
             decode_attn_launch(q, kc, l, bs->st_kv_len.as<int>(), rows, c.dec_heads, scale, att, st);
@@ -440,7 +451,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         }
         {
             ProfScope ps(h, "dec_attn", 0, kv_bytes);
-            if (!(skip & 2)) decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, m.inv_freq,
+            if (!(skip & 2)) decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, bs->rope_tab.as<float2>(),
                                      kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale, att, h->num_sms, st);
         }
         {

@@ -194,7 +194,8 @@ void gemm_init(int device) {
 }
 
 int gemm_pick_bn(int N, int epi, long m_tiles) {
-    static const int cand[] = {256, 160, 128, 64, 32};
+    // wide tiles first: a 128-row M tile with N <= 128 is bound by shared-memory operand reads, not by the tensor pipe
+    static const int cand[] = {256, 224, 160, 128, 64, 32};
     int smallest = 0;
     for (int bn : cand) {
         if (N % bn) continue;
@@ -279,6 +280,7 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
         case 64: launch_bn<64>(e.epi, ta, tb, p, grid, st); break;
         case 128: launch_bn<128>(e.epi, ta, tb, p, grid, st); break;
         case 160: launch_bn<160>(e.epi, ta, tb, p, grid, st); break;
+        case 224: launch_bn<224>(e.epi, ta, tb, p, grid, st); break;
         case 256: launch_bn<256>(e.epi, ta, tb, p, grid, st); break;
         default: throw Error(1, "gemm: unsupported tile width " + std::to_string(bn));
     }

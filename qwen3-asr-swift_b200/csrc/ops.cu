@@ -164,7 +164,7 @@ __global__ void embed_splice_kernel(const int32_t* __restrict__ ids, const int* 
 __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw,
                                                             const bf16* __restrict__ kw, const int* __restrict__ pos,
                                                             const int* __restrict__ row_seq, int rows, int heads, int kv_heads, float eps,
-                                                            const float* __restrict__ inv_freq, bf16* __restrict__ qout,
+                                                            const float2* __restrict__ rope_tab, bf16* __restrict__ qout,
                                                             bf16* __restrict__ kc, bf16* __restrict__ vc, KvCache cache, int layer) {
     const int slots = heads + 2 * kv_heads;
     const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -193,12 +193,11 @@ __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const bf16* __restr
         for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
         const int i0 = d0 & 63;
         const float sgn = lane < 16 ? -1.f : 1.f;
+        const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + i0);  // (cos, sin) pairs of 4 dims
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float sn, cs;
-            sincosf((float)p * __ldg(inv_freq + i0 + j), &sn, &cs);
-            x[j] = fmaf(x[j], cs, sgn * y[j] * sn);
-        }
+        for (int j = 0; j < 4; j++) x[j] = fmaf(x[j], cs[j], sgn * y[j] * sn[j]);
     }
     if (slot < heads) {
         st8(qout + (size_t)row * heads * 128 + slot * 128 + d0, x[0], x[1], x[2], x[3]);
@@ -338,7 +337,7 @@ template <int GROUP, int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_kernel(const float* __restrict__ qkv_part, int splits, long long split_stride,
                                                                     int nqkv, const bf16* __restrict__ qw, const bf16* __restrict__ kw,
                                                                     const int* __restrict__ pos, float eps,
-                                                                    const float* __restrict__ inv_freq, KvCache cache, int layer,
+                                                                    const float2* __restrict__ rope_tab, KvCache cache, int layer,
                                                                     const int* __restrict__ kv_len, int heads, float scale_log2,
                                                                     bf16* __restrict__ out) {
     ptx::grid_dep_launch();
@@ -412,12 +411,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
             for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
             const int i0 = d0 & 63;
             const float sgn = lane < 16 ? -1.f : 1.f;
+            const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + i0);  // (cos, sin) pairs of 4 dims
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+            const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float sn, cs;
-                sincosf((float)p * __ldg(inv_freq + i0 + j), &sn, &cs);
-                x[j] = bf16_round(fmaf(x[j], cs, sgn * y[j] * sn));
-            }
+            for (int j = 0; j < 4; j++) x[j] = bf16_round(fmaf(x[j], cs[j], sgn * y[j] * sn[j]));
         }
         if (slot < GROUP) {
 #pragma unroll
@@ -679,6 +677,15 @@ __global__ void random_init_kernel(bf16* out, size_t n, unsigned long long seed,
     out[i] = __float2bfloat16_rn(__fmul_rn(__int2float_rn(s), mult));
 }
 
+// (cos, sin)(pos * inv_freq[i]) for pos < n_pos, i < 64: the fp32 product and sincosf of the per-element kernels, tabulated
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, int n_pos, float2* __restrict__ tab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pos * 64) return;
+    float sn, cs;
+    sincosf((float)(idx >> 6) * inv_freq[idx & 63], &sn, &cs);
+    tab[idx] = make_float2(cs, sn);
+}
+
 inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -715,14 +722,18 @@ void embed_splice_launch(const int32_t* ids, const int* audio_src, const bf16* e
 }
 
 void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* kw, const int* pos, const int* row_seq, int rows,
-                           int heads, int kv_heads, float eps, float theta, const float* inv_freq, bf16* qout, bf16* kc, bf16* vc,
+                           int heads, int kv_heads, float eps, const float2* rope_tab, bf16* qout, bf16* kc, bf16* vc,
                            const KvCache& cache, int layer, cudaStream_t st) {
-    (void)theta;
     if (rows <= 0) return;
     Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
     const size_t warps = (size_t)rows * (heads + 2 * kv_heads);
-    qknorm_rope_kv_kernel<<<blocks_for(warps, 8), 256, 0, st>>>(qkv, ld, qw, kw, pos, row_seq, rows, heads, kv_heads, eps, inv_freq, qout,
+    qknorm_rope_kv_kernel<<<blocks_for(warps, 8), 256, 0, st>>>(qkv, ld, qw, kw, pos, row_seq, rows, heads, kv_heads, eps, rope_tab, qout,
                                                                 kc, vc, cache, layer);
+    Q3_CUDA(cudaGetLastError());
+}
+
+void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, cudaStream_t st) {
+    if (n_pos > 0) rope_table_kernel<<<blocks_for((size_t)n_pos * 64, 256), 256, 0, st>>>(inv_freq, n_pos, tab);
     Q3_CUDA(cudaGetLastError());
 }
 
@@ -741,7 +752,7 @@ void decode_attn_launch(const bf16* q, const KvCache& cache, int layer, const in
 }
 
 void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
-                              const int* pos, float eps, const float* inv_freq, const KvCache& cache, int layer, const int* kv_len,
+                              const int* pos, float eps, const float2* rope_tab, const KvCache& cache, int layer, const int* kv_len,
                               int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st) {
     if (n_seqs <= 0) return;
     Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
@@ -757,10 +768,10 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
     }
     if ((long)n_seqs * cache.kv_heads >= 2L * num_sms)
         launch_kernel(decode_attn_fused_kernel<2, 4>, grid, 128, decode_attn_smem(4), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
-                      inv_freq, cache, layer, kv_len, heads, sl2, out);
+                      rope_tab, cache, layer, kv_len, heads, sl2, out);
     else
         launch_kernel(decode_attn_fused_kernel<2, 16>, grid, 512, decode_attn_smem(16), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos,
-                      eps, inv_freq, cache, layer, kv_len, heads, sl2, out);
+                      eps, rope_tab, cache, layer, kv_len, heads, sl2, out);
 }
 
 void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,

@@ -48,11 +48,13 @@ struct KvCache {
     int max_pages;
     int layers, kv_heads, head_dim;
 };
+// rope_tab[pos][i] = (cos, sin)(pos * theta^(-2i/128)), i < 64 (head_dim 128), for pos < n_pos
+void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, cudaStream_t st);
 // Per (row, head): q/k RMSNorm over head_dim, split-half RoPE at pos[row], v passthrough; writes q to qout
 // [rows, heads*hd], k/v to the paged cache (slot pos[row] of sequence row_seq[row]) and, if kc/vc != null, to
 // contiguous [rows, kv_heads*hd] buffers for the prefill attention.  FloatTextDecoder.swift:85-102.
 void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* kw, const int* pos, const int* row_seq, int rows,
-                           int heads, int kv_heads, float eps, float theta, const float* inv_freq, bf16* qout, bf16* kc, bf16* vc,
+                           int heads, int kv_heads, float eps, const float2* rope_tab, bf16* qout, bf16* kc, bf16* vc,
                            const KvCache& cache, int layer, cudaStream_t st);
 // One query token per sequence against its paged cache (kv_len[seq] keys, the new token included), GQA.
 void decode_attn_launch(const bf16* q /*[n_seqs, heads*hd]*/, const KvCache& cache, int layer, const int* kv_len, int n_seqs, int heads,
@@ -61,7 +63,7 @@ void decode_attn_launch(const bf16* q /*[n_seqs, heads*hd]*/, const KvCache& cac
 // Decode step, fused: sums the split-K partials of the QKV product (fp32 [splits][n_seqs][nqkv]), applies q/k-norm + RoPE,
 // appends k/v to the cache and attends (one launch instead of qknorm_rope_kv + decode_attn).
 void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
-                              const int* pos, float eps, const float* inv_freq, const KvCache& cache, int layer, const int* kv_len,
+                              const int* pos, float eps, const float2* rope_tab, const KvCache& cache, int layer, const int* kv_len,
                               int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st);
 // x += bf16(sum of split-K partials) (in place), y = RMSNorm(x) * w.  d % 128 == 0, d <= 2048.
 void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,

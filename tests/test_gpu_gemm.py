@@ -54,6 +54,14 @@ def test_gemm_every_tile_width(tiny_model, bn):
     _close_bf16(tiny_model.debug_gemm(A, W, bn=bn), ref, f"bn={bn}")
 
 
+def test_gemm_tile_width_224(tiny_model):
+    rng = np.random.default_rng(224)
+    M, N, K = 300, 896, 448
+    A, W, b = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05), _rand(rng, (N,))
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + b
+    _close_bf16(tiny_model.debug_gemm(A, W, bias=b, bn=224), ref, "bn=224")
+
+
 def test_gemm_tile_width_160(tiny_model):
     rng = np.random.default_rng(160)
     M, N, K = 333, 480, 480
@@ -85,7 +93,7 @@ def test_gemm_fp32_out(tiny_model):
 
 
 @pytest.mark.parametrize("bn", [64, 128, 256])
-def test_gemm_swiglu(tiny_model, bn):
+def test_gemm_swiglu(tiny_model, bn):  # one 32/32 row interleave serves every tile width
     rng = np.random.default_rng(5 + bn)
     M, I, K = 140, 512, 128
     A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
