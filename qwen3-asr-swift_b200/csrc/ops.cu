@@ -1,6 +1,8 @@
 // ops.cu — CUDA-core kernels around the GEMMs: conv2d1, LayerNorm, RMSNorm, embedding gather/splice,
 // q/k-norm + RoPE + KV-cache write, paged decode attention, greedy bookkeeping, dtype/init helpers.
 // Reductions are warp-shuffle based (one warp per row / per head).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ops.cuh"
@@ -558,6 +560,229 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused decode-step attention, tensor-core version (the default): same contract as decode_attn_fused_kernel, but the
+// two query heads of a kv head form rows 0 and 1 of an m16n8k16 tile, so a warp scores a 16-key chunk with 16 mma.sync
+// and accumulates P V with 16 more — about a fifth of the CUDA-core instruction count, which leaves the kernel bound by
+// the KV stream.  Each warp owns a 3-deep cp.async ring of 16-key chunks (K and V rows are contiguous in a page); rows are
+// stored with a 16-byte XOR swizzle so ldmatrix is conflict-free without padding.
+// ------------------------------------------------------------------------------------------
+constexpr int DM_CHUNK = 16;
+constexpr int DM_STAGES = 3;
+constexpr int decode_attn_mma_smem(int nw) { return nw * DM_STAGES * 2 * DM_CHUNK * 128 * 2; }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// element offset of 16-byte segment `seg` of row `key` in a swizzled [16 keys][128] tile
+__device__ __forceinline__ int dm_off(int key, int seg) { return key * 128 + ((seg ^ (key & 7)) << 3); }
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kernel(const float* __restrict__ qkv_part, int splits, long long split_stride,
+                                                                  int nqkv, const bf16* __restrict__ qw, const bf16* __restrict__ kw,
+                                                                  const int* __restrict__ pos, float eps,
+                                                                  const float2* __restrict__ rope_tab, KvCache cache, int layer,
+                                                                  const int* __restrict__ kv_len, int heads, float scale_log2,
+                                                                  bf16* __restrict__ out) {
+    constexpr int GROUP = 2;
+    ptx::grid_dep_launch();
+    const int seq = blockIdx.x, kvh = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(16) bf16 s_qb[GROUP][128];  // the two query heads (bf16, after norm + RoPE)
+    __shared__ __align__(16) bf16 s_new[2][128];     // the new token's k and v rows
+    __shared__ float s_m[GROUP][NW], s_l[GROUP][NW];
+    __shared__ float s_acc[GROUP][NW][128];
+    const int* pt = cache.page_table + (size_t)seq * cache.max_pages;
+
+    // ---- 0. start streaming cached keys/values (independent of the previous kernel) ----
+    const int len = kv_len[seq];
+    extern __shared__ uint4 da_smem[];
+    bf16* ring = reinterpret_cast<bf16*>(da_smem) + (size_t)warp * DM_STAGES * 2 * DM_CHUNK * 128;
+    const size_t head_off = (((size_t)layer * 2) * cache.kv_heads + kvh) * (KV_PAGE * 128);
+    const size_t page_elems = (size_t)cache.layers * 2 * cache.kv_heads * (KV_PAGE * 128);
+    const size_t v_off = (size_t)cache.kv_heads * (KV_PAGE * 128);
+    const int n_chunks = (len + DM_CHUNK - 1) / DM_CHUNK;
+    auto issue = [&](int chunk, int stage) {
+        if (chunk < n_chunks) {
+            const int j0 = chunk * DM_CHUNK;
+            const bf16* kb = cache.pool + (size_t)pt[j0 / KV_PAGE] * page_elems + head_off + (j0 % KV_PAGE) * 128;
+            bf16* sk = ring + (size_t)stage * 2 * DM_CHUNK * 128;
+#pragma unroll
+            for (int i = 0; i < DM_CHUNK * 16 / 32; i++) {
+                const int lin = i * 32 + lane, key = lin >> 4, seg = lin & 15;
+                const uint32_t n = j0 + key < len ? 16u : 0u;  // rows past the end are zero-filled
+                cp_async16(sk + dm_off(key, seg), kb + lin * 8, n);
+                cp_async16(sk + DM_CHUNK * 128 + dm_off(key, seg), kb + v_off + lin * 8, n);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < DM_STAGES - 1; s++) issue(warp + s * NW, s);
+
+    ptx::grid_dep_wait();
+
+    // ---- 1. new-token q / k / v (slots 0,1 = q heads, 2 = k, 3 = v) ----
+    for (int slot = warp; slot < GROUP + 2; slot += NW) {
+        const int d0 = lane * 4;
+        const int col = slot < GROUP ? (kvh * GROUP + slot) * 128
+                                     : slot == GROUP ? heads * 128 + kvh * 128 : (heads + cache.kv_heads) * 128 + kvh * 128;
+        const float* src = qkv_part + (size_t)seq * nqkv + col + d0;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < splits; s0 += 4) {  // fixed summation order, four loads in flight
+            float4 b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                b[i] = s0 + i < splits ? *reinterpret_cast<const float4*>(src + (size_t)(s0 + i) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
+        }
+        float x[4] = {bf16_round(a.x), bf16_round(a.y), bf16_round(a.z), bf16_round(a.w)};
+        const int p = pos[seq];
+        if (slot <= GROUP) {
+            float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
+            const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
+            const uint2 wu = ld8((slot < GROUP ? qw : kw) + d0);
+            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+            x[0] = bf16_round(x[0] * r * w0.x);
+            x[1] = bf16_round(x[1] * r * w0.y);
+            x[2] = bf16_round(x[2] * r * w1.x);
+            x[3] = bf16_round(x[3] * r * w1.y);
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
+            const int i0 = d0 & 63;
+            const float sgn = lane < 16 ? -1.f : 1.f;
+            const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + i0);
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+            const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[j] = fmaf(x[j], cs[j], sgn * y[j] * sn[j]);  // rounded to bf16 by the stores below
+        }
+        if (slot < GROUP) {
+            st8(&s_qb[slot][d0], x[0], x[1], x[2], x[3]);
+        } else {
+            const int page = pt[p / KV_PAGE];
+            bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (slot == GROUP ? 0 : 1)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
+                        (p % KV_PAGE) * 128 + d0;
+            st8(dst, x[0], x[1], x[2], x[3]);
+            st8(&s_new[slot - GROUP][d0], x[0], x[1], x[2], x[3]);
+        }
+    }
+    __syncthreads();  // s_qb and s_new ready
+
+    // ---- 2. attention on the tensor cores ----
+    const int g = lane >> 2, t = lane & 3;  // accumulator row (query head when < 2) and column pair
+    uint32_t qa[8][2];                      // A fragments of Q: rows 0,1 real, the rest zero
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        qa[ks][0] = lane < 8 ? *reinterpret_cast<const uint32_t*>(&s_qb[g & 1][ks * 16 + t * 2]) : 0u;
+        qa[ks][1] = lane < 8 ? *reinterpret_cast<const uint32_t*>(&s_qb[g & 1][ks * 16 + 8 + t * 2]) : 0u;
+    }
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const int mi = lane >> 3, r8 = lane & 7;
+    int stage = 0;
+    for (int chunk = warp; chunk < n_chunks; chunk += NW) {
+        issue(chunk + (DM_STAGES - 1) * NW, (stage + DM_STAGES - 1) % DM_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(DM_STAGES - 1) : "memory");
+        __syncwarp();
+        bf16* sk = ring + (size_t)stage * 2 * DM_CHUNK * 128;
+        bf16* sv = sk + DM_CHUNK * 128;
+        const int j0 = chunk * DM_CHUNK;
+        if (chunk == n_chunks - 1) {  // the prefetch may have read the new token's row before it was written
+            const int row = (len - 1) - j0;
+            *reinterpret_cast<uint4*>((lane < 16 ? sk : sv) + dm_off(row, lane & 15)) = reinterpret_cast<const uint4*>(s_new[lane >> 4])[lane & 15];
+            __syncwarp();
+        }
+        // S = Q K^T: 16 (2 real) x 16 keys
+        float s[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            uint32_t b[4];
+            const int key = (mi >> 1) * 8 + r8;
+            ldsm_x4(b, sk + dm_off(key, ks * 2 + (mi & 1)));
+            const uint32_t a[4] = {qa[ks][0], 0u, qa[ks][1], 0u};
+            mma16816(s[0], a, b[0], b[1]);
+            mma16816(s[1], a, b[2], b[3]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const bool ok = j0 + nt * 8 + t * 2 + e < len;
+                s[nt][e] = ok ? s[nt][e] * scale_log2 : -INFINITY;
+                mx = fmaxf(mx, s[nt][e]);
+            }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m_run, mx);  // finite: every chunk holds at least one valid key
+        const float alpha = exp2f(m_run - mn);
+        m_run = mn;
+        const float p00 = exp2f(s[0][0] - mn), p01 = exp2f(s[0][1] - mn), p10 = exp2f(s[1][0] - mn), p11 = exp2f(s[1][1] - mn);
+        l_run = l_run * alpha + ((p00 + p01) + (p10 + p11));
+        const uint32_t pa[4] = {pack_bf16x2(p00, p01), 0u, pack_bf16x2(p10, p11), 0u};
+#pragma unroll
+        for (int i = 0; i < 16; i++) { o[i][0] *= alpha; o[i][1] *= alpha; }
+        // O += P V
+#pragma unroll
+        for (int np = 0; np < 8; np++) {
+            uint32_t b[4];
+            const int key = r8 + (mi & 1) * 8;
+            ldsm_x4_t(b, sv + dm_off(key, np * 2 + (mi >> 1)));
+            mma16816(o[2 * np], pa, b[0], b[1]);
+            mma16816(o[2 * np + 1], pa, b[2], b[3]);
+        }
+        __syncwarp();  // the slot is refilled by the next iteration's issue
+        stage = (stage + 1) % DM_STAGES;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // ---- 3. merge the warps ----
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (lane < 8) {
+        if (t == 0) { s_m[g][warp] = m_run; s_l[g][warp] = l_run; }
+#pragma unroll
+        for (int nt = 0; nt < 16; nt++) {
+            s_acc[g][warp][nt * 8 + t * 2] = o[nt][0];
+            s_acc[g][warp][nt * 8 + t * 2 + 1] = o[nt][1];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GROUP * 128; i += NW * 32) {
+        const int gg = i >> 7, d = i & 127;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; w++) mm = fmaxf(mm, s_m[gg][w]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const float f = s_m[gg][w] == -INFINITY ? 0.f : exp2f(s_m[gg][w] - mm);
+            num = fmaf(f, s_acc[gg][w][d], num);
+            den = fmaf(f, s_l[gg][w], den);
+        }
+        out[((size_t)seq * heads + kvh * GROUP + gg) * 128 + d] = __float2bfloat16_rn(num / den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Split-K consumer of the decode step: x[r] = bf16(x[r] + bf16(sum_s part[s][r])) (residual stream, in place),
 // y[r] = RMSNorm(x[r]) * w  (the next block's input).  One CTA per row, 4 columns per thread.
 // FloatTextDecoder.swift:144-147 (residual adds) + :139, :146 (the norms that follow them).
@@ -764,14 +989,26 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
     if (!attr) {
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(4)));
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(16)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(2)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(8)));
         attr = true;
     }
-    if ((long)n_seqs * cache.kv_heads >= 2L * num_sms)
+    const bool many = (long)n_seqs * cache.kv_heads >= 2L * num_sms;  // few (sequence, head) pairs: more warps per CTA share the key loop
+    static const bool simt = getenv("Q3ASR_DECODE_ATTN_SIMT") != nullptr && atoi(getenv("Q3ASR_DECODE_ATTN_SIMT")) != 0;
+    if (!simt) {
+        if (many)
+            launch_kernel(decode_attn_mma_kernel<2>, grid, 64, decode_attn_mma_smem(2), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                          rope_tab, cache, layer, kv_len, heads, sl2, out);
+        else
+            launch_kernel(decode_attn_mma_kernel<8>, grid, 256, decode_attn_mma_smem(8), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                          rope_tab, cache, layer, kv_len, heads, sl2, out);
+    } else if (many) {
         launch_kernel(decode_attn_fused_kernel<2, 4>, grid, 128, decode_attn_smem(4), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
                       rope_tab, cache, layer, kv_len, heads, sl2, out);
-    else
+    } else {
         launch_kernel(decode_attn_fused_kernel<2, 16>, grid, 512, decode_attn_smem(16), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos,
                       eps, rope_tab, cache, layer, kv_len, heads, sl2, out);
+    }
 }
 
 void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,
