@@ -180,6 +180,12 @@ int q3asr_debug_gemm(q3asr_handle* h, const uint16_t* A, const uint16_t* W, cons
 int q3asr_debug_conv(q3asr_handle* h, const uint16_t* in, const uint16_t* w, const uint16_t* bias, int B, int H, int W, int C, int O,
                      int box_w, int box_h, int box_b, int use_simt, uint16_t* out);
 
+/* Segment-packed attention: q [rows, heads*hd], k/v [rows, (heads/group)*hd] bf16 (uint16), segments (row0, len) independent;
+ * kernel: 0 = tcgen05/TMEM (attention_tc.cu, the product path), 1 = mma.sync checker (attention.cu).  out: [rows, heads*hd] bf16. */
+int q3asr_debug_attention(q3asr_handle* h, const uint16_t* q, const uint16_t* k, const uint16_t* v, int rows, int heads, int group,
+                          int head_dim, const int* seg_row0, const int* seg_len, int n_segs, int causal, float scale, int kernel,
+                          uint16_t* out);
+
 #ifdef __cplusplus
 }
 #endif

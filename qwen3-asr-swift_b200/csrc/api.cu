@@ -477,4 +477,45 @@ int q3asr_debug_conv(q3asr_handle* hh, const uint16_t* in, const uint16_t* w, co
     });
 }
 
+int q3asr_debug_attention(q3asr_handle* hh, const uint16_t* q, const uint16_t* k, const uint16_t* v, int rows, int heads, int group,
+                          int head_dim, const int* seg_row0, const int* seg_len, int n_segs, int causal, float scale, int kernel,
+                          uint16_t* out) {
+    return guarded(hh, [&](Handle& h) {
+        Q3_CHECK(q && k && v && out && seg_row0 && seg_len && rows > 0 && heads > 0 && group > 0 && heads % group == 0 && n_segs > 0,
+                 Q3ASR_ERR_INVALID, "debug_attention: bad argument");
+        const size_t nq = (size_t)rows * heads * head_dim, nk = (size_t)rows * (heads / group) * head_dim;
+        bf16 *dq, *dk, *dv, *dout;
+        int* dseg;
+        Q3_CUDA(cudaMalloc(&dq, 2 * nq));
+        Q3_CUDA(cudaMalloc(&dk, 2 * nk));
+        Q3_CUDA(cudaMalloc(&dv, 2 * nk));
+        Q3_CUDA(cudaMalloc(&dout, 2 * nq));
+        Q3_CUDA(cudaMalloc(&dseg, sizeof(int) * 2 * n_segs));
+        Q3_CUDA(cudaMemcpy(dq, q, 2 * nq, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dk, k, 2 * nk, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dv, v, 2 * nk, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dseg, seg_row0, sizeof(int) * n_segs, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemcpy(dseg + n_segs, seg_len, sizeof(int) * n_segs, cudaMemcpyHostToDevice));
+        Q3_CUDA(cudaMemset(dout, 0, 2 * nq));
+        int max_len = 0;
+        for (int i = 0; i < n_segs; i++) max_len = std::max(max_len, seg_len[i]);
+        AttnSegs segs{dseg, dseg + n_segs, n_segs, max_len};
+        cudaError_t se = cudaSuccess;
+        try {
+            const int ldq = heads * head_dim, ldk = (heads / group) * head_dim;
+            if (kernel == 0)
+                flash_attn_tc_launch(dq, ldq, dk, ldk, dv, ldk, dout, ldq, segs, rows, heads, group, head_dim, causal != 0, scale, h.stream);
+            else
+                flash_attn_launch(dq, ldq, dk, ldk, dv, ldk, dout, ldq, segs, heads, group, head_dim, causal != 0, scale, h.stream);
+            se = cudaStreamSynchronize(h.stream);
+            if (se == cudaSuccess) se = cudaMemcpy(out, dout, 2 * nq, cudaMemcpyDeviceToHost);
+        } catch (...) {
+            cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout); cudaFree(dseg);
+            throw;
+        }
+        cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout); cudaFree(dseg);
+        Q3_CUDA(se);
+    });
+}
+
 }  // extern "C"

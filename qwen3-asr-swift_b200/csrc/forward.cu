@@ -324,6 +324,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
     AttnSegs segs{ints + bs->o_win_row0, ints + bs->o_win_len, bs->n_win, bs->max_win};
     bf16 *x = bs->ex.as<bf16>(), *xn = bs->exn.as<bf16>(), *qkv = bs->eqkv.as<bf16>(), *att = bs->eatt.as<bf16>(),
          *ffn = bs->effn.as<bf16>();
+    const bool attn_tc = env_int("Q3ASR_ATTN_MMASYNC", 0) == 0;  // tcgen05 attention unless the mma.sync checker kernel is asked for
     double win_pairs = 0;  // sum over windows of len^2 (attention work)
     for (const ClipInfo& ci : bs->clips)
         for (int s0 = 0; s0 < ci.ntok; s0 += ci.win_size) {
@@ -337,7 +338,10 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
         { ProfScope ps(h, "enc_qkv", 6.0 * Td * dd * dd, 0); gemm(xn, d, T, d, w.qkv_w, 3 * d, epi_store(qkv, 3 * d, w.qkv_b), st); }
         {
             ProfScope ps(h, "enc_attn", 4.0 * win_pairs * dd, 8.0 * Td * dd);
-            flash_attn_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, c.enc_heads, 1, 64, false, 0.125f, st);
+            if (attn_tc)
+                flash_attn_tc_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, T, c.enc_heads, 1, 64, false, 0.125f, st);
+            else
+                flash_attn_launch(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, att, d, segs, c.enc_heads, 1, 64, false, 0.125f, st);
         }
         { ProfScope ps(h, "enc_out", 2.0 * Td * dd * dd, 0); gemm(att, d, T, d, w.o_w, d, epi_store(x, d, w.o_b, 0, x, d), st); }
         { ProfScope ps(h, "enc_ln", 0, 4.0 * Td * dd); layernorm_launch(x, w.ln2_w, w.ln2_b, xn, T, d, c.enc_ln_eps, st); }
@@ -399,7 +403,10 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
         qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
                               bs->rope_tab.as<float2>(), q, prefill ? bs->dkc.as<bf16>() : nullptr, nullptr, kc, l, st);
         tag("pre_attn", "dec_attn", prefill ? 4.0 * causal_pairs * nq : 0, 0);
-        if (prefill)
+        if (prefill && env_int("Q3ASR_ATTN_MMASYNC", 0) == 0)
+            flash_attn_tc_launch(q, nq, bs->dkc.as<bf16>(), nkv, qkv + nq + nkv, nqkv, att, nq, segs, rows, c.dec_heads,
+                                 c.dec_heads / c.dec_kv_heads, hd, true, scale, st);
+        else if (prefill)
             flash_attn_launch(q, nq, bs->dkc.as<bf16>(), nkv, qkv + nq + nkv, nqkv, att, nq, segs, c.dec_heads,
                               c.dec_heads / c.dec_kv_heads, hd, true, scale, st);
         else

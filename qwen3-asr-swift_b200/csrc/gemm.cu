@@ -178,6 +178,15 @@ __global__ void argmax_reduce_kernel(const float* val, const int* idx, int rows,
 
 }  // namespace
 
+void make_tmap_2d_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_elems, uint32_t box_cols,
+                       uint32_t box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    make_tmap(m, ptr, 2, dims, str, box, es);
+}
+
 void gemm_init(int device) {
     if (g_encode == nullptr) {
         void* fn = nullptr;

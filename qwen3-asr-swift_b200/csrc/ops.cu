@@ -168,51 +168,52 @@ __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const bf16* __restr
                                                             const int* __restrict__ row_seq, int rows, int heads, int kv_heads, float eps,
                                                             const float2* __restrict__ rope_tab, bf16* __restrict__ qout,
                                                             bf16* __restrict__ kc, bf16* __restrict__ vc, KvCache cache, int layer) {
+    // one CTA per row, 8 warps; warp w takes head slots w, w + 8, ... so the row's position, page and table entries are
+    // fetched once per warp (the kernel is instruction-bound when every (row, slot) pair recomputes them)
+    const int row = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slots = heads + 2 * kv_heads;
-    const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (long)rows * slots) return;
-    const int row = (int)(wid / slots), slot = (int)(wid % slots);
-    const int lane = threadIdx.x & 31;
     const int d0 = lane * 4;
-    const uint2 u = ld8(qkv + (size_t)row * ld + slot * 128 + d0);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    float x[4] = {a.x, a.y, b.x, b.y};
     const int p = pos[row];
-    const bool is_v = slot >= heads + kv_heads;
-    if (!is_v) {
-        float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
-        const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
-        const bf16* wv = slot < heads ? qw : kw;
-        const uint2 wu = ld8(wv + d0);
-        const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
-        x[0] = bf16_round(x[0] * r * w0.x);
-        x[1] = bf16_round(x[1] * r * w0.y);
-        x[2] = bf16_round(x[2] * r * w1.x);
-        x[3] = bf16_round(x[3] * r * w1.y);
-        // split-half rotation: dims (i, i+64); the partner values live in lane ^ 16
-        float y[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
-        const int i0 = d0 & 63;
-        const float sgn = lane < 16 ? -1.f : 1.f;
-        const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + i0);  // (cos, sin) pairs of 4 dims
-        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-        const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) x[j] = fmaf(x[j], cs[j], sgn * y[j] * sn[j]);
-    }
-    if (slot < heads) {
-        st8(qout + (size_t)row * heads * 128 + slot * 128 + d0, x[0], x[1], x[2], x[3]);
-        return;
-    }
-    const int kvh = is_v ? slot - heads - kv_heads : slot - heads;
-    bf16* cont = is_v ? vc : kc;
-    if (cont) st8(cont + (size_t)row * kv_heads * 128 + kvh * 128 + d0, x[0], x[1], x[2], x[3]);
     const int seq = row_seq[row];
     const int page = cache.page_table[(size_t)seq * cache.max_pages + p / KV_PAGE];
-    bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (is_v ? 1 : 0)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
-                (p % KV_PAGE) * 128 + d0;
-    st8(dst, x[0], x[1], x[2], x[3]);
+    bf16* page_base = cache.pool + (((size_t)page * cache.layers + layer) * 2) * cache.kv_heads * (KV_PAGE * 128) + (p % KV_PAGE) * 128 + d0;
+    const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + (d0 & 63));  // (cos, sin) pairs of 4 dims
+    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+    const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+    const float sgn = lane < 16 ? -1.f : 1.f;
+    const uint2 qwu = ld8(qw + d0), kwu = ld8(kw + d0);
+    const bf16* src = qkv + (size_t)row * ld + d0;
+    for (int slot = warp; slot < slots; slot += 8) {
+        const uint2 u = ld8(src + slot * 128);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        float x[4] = {a.x, a.y, b.x, b.y};
+        const bool is_v = slot >= heads + kv_heads;
+        if (!is_v) {
+            float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
+            const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
+            const uint2 wu = slot < heads ? qwu : kwu;
+            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
+            x[0] = bf16_round(x[0] * r * w0.x);
+            x[1] = bf16_round(x[1] * r * w0.y);
+            x[2] = bf16_round(x[2] * r * w1.x);
+            x[3] = bf16_round(x[3] * r * w1.y);
+            // split-half rotation: dims (i, i+64); the partner values live in lane ^ 16
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[j] = fmaf(x[j], cs[j], sgn * y[j] * sn[j]);
+        }
+        if (slot < heads) {
+            st8(qout + (size_t)row * heads * 128 + slot * 128 + d0, x[0], x[1], x[2], x[3]);
+            continue;
+        }
+        const int kvh = is_v ? slot - heads - kv_heads : slot - heads;
+        bf16* cont = is_v ? vc : kc;
+        if (cont) st8(cont + (size_t)row * kv_heads * 128 + kvh * 128 + d0, x[0], x[1], x[2], x[3]);
+        st8(page_base + ((size_t)(is_v ? 1 : 0) * cache.kv_heads + kvh) * (KV_PAGE * 128), x[0], x[1], x[2], x[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -951,8 +952,7 @@ void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* 
                            const KvCache& cache, int layer, cudaStream_t st) {
     if (rows <= 0) return;
     Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
-    const size_t warps = (size_t)rows * (heads + 2 * kv_heads);
-    qknorm_rope_kv_kernel<<<blocks_for(warps, 8), 256, 0, st>>>(qkv, ld, qw, kw, pos, row_seq, rows, heads, kv_heads, eps, rope_tab, qout,
+    qknorm_rope_kv_kernel<<<rows, 256, 0, st>>>(qkv, ld, qw, kw, pos, row_seq, rows, heads, kv_heads, eps, rope_tab, qout,
                                                                 kc, vc, cache, layer);
     Q3_CUDA(cudaGetLastError());
 }

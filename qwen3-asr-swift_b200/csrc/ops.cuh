@@ -37,6 +37,10 @@ struct AttnSegs {
 void flash_attn_launch(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, const AttnSegs& segs,
                        int heads, int group, int head_dim, bool causal, float scale, cudaStream_t st);
 
+// The same contract on tcgen05 / TMEM / TMA (attention_tc.cu); total_rows = rows of the packed q/k/v buffers.
+void flash_attn_tc_launch(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, const AttnSegs& segs,
+                          int total_rows, int heads, int group, int head_dim, bool causal, float scale, cudaStream_t st);
+
 // ---- decoder ----
 // x[r] = audio_src[r] >= 0 ? audio[audio_src[r]] : embed[ids[r]]   (Qwen3ASR.swift:236-244)
 void embed_splice_launch(const int32_t* ids, const int* audio_src, const bf16* embed, const bf16* audio, bf16* x, int rows, int h,

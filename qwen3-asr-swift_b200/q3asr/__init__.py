@@ -58,7 +58,7 @@ EXPORTS = [
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
     "q3asr_pool_create", "q3asr_pool_destroy", "q3asr_pool_last_error", "q3asr_pool_transcribe_ids", "q3asr_schedule",
-    "q3asr_debug_gemm", "q3asr_debug_conv",
+    "q3asr_debug_gemm", "q3asr_debug_conv", "q3asr_debug_attention",
 ]
 
 _lib = None
@@ -119,6 +119,7 @@ def lib():
         L.q3asr_schedule.argtypes = [vp, ci, ci, vp]
         L.q3asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.q3asr_debug_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, ci, ci, ctypes.c_float, ci, vp]
         _lib = L
     return _lib
 
@@ -402,6 +403,19 @@ class Qwen3ASRModel:
                                         r.ctypes.data if r is not None else None, M, N, K, int(epi), int(bool(gelu)), int(bn),
                                         int(bool(simt)), out.ctypes.data))
         return bf16_bits_to_f32(out) if out.dtype == np.uint16 else out
+
+    def debug_attention(self, q, k, v, segs, heads, group, causal, scale, kernel=0):
+        """q [rows, heads*hd], k/v [rows, heads/group*hd] float32 holding bf16 values; segs: list of (row0, len)."""
+        rows = q.shape[0]
+        hd = q.shape[1] // heads
+        qb, kb, vb = f32_to_bf16_bits(q), f32_to_bf16_bits(k), f32_to_bf16_bits(v)
+        r0 = np.ascontiguousarray([s[0] for s in segs], dtype=np.int32)
+        ln = np.ascontiguousarray([s[1] for s in segs], dtype=np.int32)
+        out = np.empty((rows, heads * hd), dtype=np.uint16)
+        self._ck(lib().q3asr_debug_attention(self._h, qb.ctypes.data, kb.ctypes.data, vb.ctypes.data, rows, heads, group, hd,
+                                             r0.ctypes.data, ln.ctypes.data, len(segs), int(bool(causal)), ctypes.c_float(scale),
+                                             int(kernel), out.ctypes.data))
+        return bf16_bits_to_f32(out)
 
     def debug_conv(self, x, w, bias, box=(0, 0, 0), simt=False):
         """x [B,H,W,C], w [O,3,3,C] float32 (bf16-representable) -> gelu(conv3x3 s2 p1 + bias) [B,OH,OW,O]."""

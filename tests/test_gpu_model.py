@@ -167,6 +167,30 @@ def test_full_size_model_properties():
         m.close()
 
 
+def test_tcgen05_attention_matches_mma_sync_checker(built_lib, monkeypatch):
+    """The tcgen05/TMEM attention (attention_tc.cu) against the mma.sync kernel it replaced (attention.cu), full-size
+    dimensions: a 30 s clip gives four encoder windows (104,104,104,78 tokens, head_dim 64) and a 406-token causal prompt
+    (four 128-query tiles, up to four 128-key blocks each, head_dim 128, GQA)."""
+    m = built_lib.Qwen3ASRModel.random_init("0.6B", seed=7)
+    try:
+        x = synth.clip(3, 480000)
+        mel = omel.mel(x)
+        enc_tc = m.encode(mel)
+        log_tc = m.prefill_logits(x)
+        monkeypatch.setenv("Q3ASR_ATTN_MMASYNC", "1")
+        enc_ms = m.encode(mel)
+        log_ms = m.prefill_logits(x)
+        monkeypatch.delenv("Q3ASR_ATTN_MMASYNC")
+        assert enc_tc.shape == (390, 1024)
+        # two valid bf16 schedules (128- vs 64-key softmax blocks) drift apart by bf16 noise over 18 + 28 layers; the exact
+        # per-kernel check against NumPy is tests/test_gpu_attention.py
+        assert _rel_l2(enc_tc, enc_ms) <= 2e-2, _rel_l2(enc_tc, enc_ms)
+        assert _rel_l2(log_tc, log_ms) <= 2e-2, _rel_l2(log_tc, log_ms)
+        assert np.abs(log_tc - log_ms).max() <= 6 * np.abs(log_ms).max() * 2.0 ** -8
+    finally:
+        m.close()
+
+
 def test_golden_0p6b(built_lib):
     """Greedy ids and encoder statistics of the 0.6B configuration on one 5 s clip, against the fixture the
     CPU oracle produced (tests/golden/make_golden.py)."""
