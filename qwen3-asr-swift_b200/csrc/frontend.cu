@@ -1,5 +1,5 @@
 // frontend.cu — host-side planning for the mel stage: packs a ragged batch of clips into one buffer and
-// enumerates the 32-frame tiles the kernel walks.
+// enumerates the MEL_TILE-frame tiles the kernel walks.
 #include "model.h"
 
 namespace q3 {

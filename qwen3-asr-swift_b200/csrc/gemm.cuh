@@ -11,7 +11,9 @@
 //   warp 0    TMA producer     cp.async.bulk.tensor (4-D A boxes, 2-D W boxes), 128B swizzle, mbarrier ring
 //   warp 1    MMA issuer       one lane issues tcgen05.mma (M=128, N=BN, K=16), commits to mbarriers
 //   warp 2    TMEM allocator
-//   warps 4-7 epilogue         tcgen05.ld 32x32b -> registers -> bias/PE/GELU/residual/SwiGLU/argmax -> global
+//   warps 4-11 epilogue        tcgen05.ld 32x32b -> registers -> bias/PE/GELU/residual/SwiGLU/argmax -> global; two warps
+//                              share each TMEM lane quadrant and take alternate 32-column chunks (GELU / SwiGLU epilogues
+//                              of wide tiles are otherwise slower than the tile's MMAs)
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // The A operand is always described by a 4-D tensor map {c, w, h, b}.  A plain GEMM is the degenerate
@@ -35,7 +37,7 @@ enum GemmEpi : int {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int GEMM_MAX_TAPS = 16;
 constexpr int GU_UNIT = 32;  // fused gate/up weights: 32 gate rows, then the matching 32 up rows, repeating
 
@@ -122,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; s++) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 128);
+            ptx::mbar_init(&tempty_bar[s], 256);
         }
         ptx::fence_barrier_init();
     }
@@ -211,7 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int q = warp & 3;          // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 4) >> 2;  // which of the quadrant's two warps: takes chunks chalf, chalf + 2, ...
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int as = it & 1;
@@ -239,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if constexpr (BN % (2 * GU_UNIT) == 0) {
                     bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * (BN / 2);
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; c++) {  // 16 outputs per step
+                    for (int c = chalf; c < BN / 32; c += 2) {  // 16 outputs per step
                         const int col = (c >> 1) * (2 * GU_UNIT) + (c & 1) * 16;
                         uint32_t g[16], u[16];
                         ptx::tmem_ld_32x16(t_row + col, g);
@@ -263,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float best = -INFINITY;
                 int best_i = 0;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = 0; c < (chalf == 0 ? BN / 32 : 0); c++) {  // one warp per quadrant scans the whole row (weight-streaming bound)
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_row + c * 32, v);
                     ptx::tmem_ld_wait();
@@ -273,13 +276,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (x > best) { best = x; best_i = n0 + c * 32 + j; }
                     }
                 }
-                if (row_ok) {
+                if (row_ok && chalf == 0) {
                     p.amax_val[(size_t)row * p.tiles_n + tc.tn] = best;
                     p.amax_idx[(size_t)row * p.tiles_n + tc.tn] = best_i;
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = chalf; c < BN / 32; c += 2) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_row + c * 32, v);
                     ptx::tmem_ld_wait();

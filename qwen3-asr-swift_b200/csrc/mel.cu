@@ -6,8 +6,8 @@
 // slaney filterbank product (:263-268), clip/log10/clip-to-(max-8)/scale (:275-293), drop of the
 // last frame and the 120000-frame cap (:296-313), [128, T] mel-major output (:315-316).
 //
-// B200 design.  One persistent CTA (128 threads, 3 per SM) walks 32-frame tiles.  A tile's samples
-// (5360 floats, reflect padding resolved while loading) are staged in shared memory with 128-bit
+// B200 design.  One persistent CTA (128 threads, 4 per SM) walks 24-frame tiles.  A tile's samples
+// (4080 floats, reflect padding resolved while loading) are staged in shared memory with 128-bit
 // coalesced loads; sixteen lanes share one frame and two frames share a warp, so every
 // synchronisation inside the transform is a __syncwarp.  The 512-point real FFT is the 256-point
 // complex FFT of the even/odd packed frame, done as 16x16 (two in-register radix-16 passes with one
@@ -35,7 +35,7 @@ constexpr int FR_PER_IT = (MEL_THREADS / TPF);         // 8 frames in flight per
 constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 5360
 constexpr int SX_FLOATS = TILE_SAMPLES + 16;
 constexpr int XROW = 17;                               // padded row (float2) of the 16x16 transpose
-constexpr int SCR_FLOATS = 2 * TPF * XROW;             // 544 floats per frame
+constexpr int SCR_FLOATS = 2 * TPF * XROW + 16;        // 544 floats per frame + 16: the two frames of a warp sit 16 banks apart
 constexpr int OUT_STRIDE = MEL_TILE + 1;
 
 struct MelParams {
@@ -56,7 +56,7 @@ struct MelParams {
 };
 
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
-    return (SX_FLOATS + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + FR_PER_IT * SCR_FLOATS + MEL_BINS * OUT_STRIDE + 16) * 4;
+    return (SX_FLOATS + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + FR_PER_IT * SCR_FLOATS + MEL_BINS * OUT_STRIDE + 32) * 4;
 }
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -108,7 +108,7 @@ __device__ __forceinline__ int find_clip(const MelClip* clips, int batch, int ti
     return lo;
 }
 
-__global__ void __launch_bounds__(MEL_THREADS, 3) mel_kernel(const MelParams p) {
+__global__ void __launch_bounds__(MEL_THREADS, 4) mel_kernel(const MelParams p) {
     extern __shared__ float4 smem4[];
     float* s_x = reinterpret_cast<float*>(smem4);
     float2* s_tw256 = reinterpret_cast<float2*>(s_x + SX_FLOATS);
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(MEL_THREADS, 3) mel_kernel(const MelParams p) 
     float* s_scr = reinterpret_cast<float*>(s_fbstart + 128);
     float* s_out = s_scr + FR_PER_IT * SCR_FLOATS;
     float* s_red = s_out + MEL_BINS * OUT_STRIDE;
+    int* s_next = reinterpret_cast<int*>(s_red + 8);  // clip of the tile this CTA takes next (searched one tile ahead)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -139,8 +140,10 @@ __global__ void __launch_bounds__(MEL_THREADS, 3) mel_kernel(const MelParams p) 
     float2* scr2 = reinterpret_cast<float2*>(scr);
     __syncthreads();
 
+    if (tid == 0) *s_next = find_clip(p.clips, p.batch, min((int)blockIdx.x, p.total_tiles - 1));
+    __syncthreads();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ci = find_clip(p.clips, p.batch, tile);
+        const int ci = *s_next;
         const MelClip c = p.clips[ci];
         const int f0 = (tile - c.tile0) * MEL_TILE;
         const int nF = c.n / MEL_HOP + 1;  // frames incl. the one that is dropped (max runs over it, Q3)
@@ -173,6 +176,8 @@ __global__ void __launch_bounds__(MEL_THREADS, 3) mel_kernel(const MelParams p) 
             }
         }
         __syncthreads();
+        // the binary search for the next tile's clip (dependent L2 loads) overlaps this tile's transforms
+        if (tid == MEL_THREADS - 1 && tile + (int)gridDim.x < p.total_tiles) *s_next = find_clip(p.clips, p.batch, tile + gridDim.x);
 
         float lmax = -INFINITY, lmin = INFINITY;
 #pragma unroll 1
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(MEL_THREADS, 3) mel_kernel(const MelParams p) 
             p.tmin[tile] = tm;
         }
         const int T = c.frames;
-        if (f0 + lane < T) {
+        if (lane < MEL_TILE && f0 + lane < T) {
             float* o = p.out + c.out_off + f0 + lane;
 #pragma unroll 4
             for (int m = warp; m < MEL_BINS; m += MEL_THREADS / 32) o[(size_t)m * T] = s_out[m * OUT_STRIDE + lane];
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(128) mel_clamp_kernel(float* out, const MelCli
     const int f0 = (tile - c.tile0) * MEL_TILE;
     const float lo_s = fmaf(0.25f, lo, 1.0f);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (f0 + lane >= c.frames) return;
+    if (lane >= MEL_TILE || f0 + lane >= c.frames) return;
     float* o = out + c.out_off + f0 + lane;
     for (int m = warp; m < MEL_BINS; m += 4) o[(size_t)m * c.frames] = fmaxf(o[(size_t)m * c.frames], lo_s);
 }
@@ -404,7 +409,7 @@ void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelC
     p.gmax = d_gmax;
     p.tmin = d_tmin;
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
-    const int grid = std::min(total_tiles, num_sms * 3);
+    const int grid = std::min(total_tiles, num_sms * 4);
     mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
     mel_clamp_kernel<<<total_tiles, 128, 0, st>>>(d_out, d_clips, batch, total_tiles, d_gmax, d_tmin);
     Q3_CUDA(cudaGetLastError());
