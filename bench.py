@@ -224,7 +224,7 @@ def main():
 
     # ---- per-kernel-family timing (extra steps, CUDA events around the launches) ----
     pk = peaks()
-    roof, roof_mel, families = None, None, None
+    roof, roof_mel, roof_gemm, families = None, None, None, None
     if not args.no_profile:
         model.batch_upload(clips)
         model.profile(True)
@@ -238,18 +238,54 @@ def main():
         families = {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] // nprof,
                         "tflops": (v["flops"] / max(v["ms"], 1e-9)) / 1e9 if v["flops"] else None,
                         "gbs": (v["bytes"] / max(v["ms"], 1e-9)) / 1e6 if v["bytes"] else None} for k, v in rep.items()}
-        tensor_fams = {k: v for k, v in rep.items() if v["flops"] > 0 and k != "decode_graph_steps"}
-        dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms"])
-        d = tensor_fams[dom]
-        ach = d["flops"] / d["ms"] / 1e9  # TFLOP/s
-        roof = {"bound": "tensor", "kernel": f"gemm_tc_kernel ({dom})", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"bf16_tflops_sustained, {pk['src']}",
-                "launches_per_step": d["launches"] // nprof, "ms_per_launch": d["ms"] / d["launches"]}
-        m = rep.get("mel")
-        if m:
-            gbs = m["bytes"] / m["ms"] / 1e6
-            roof_mel = {"bound": "hbm", "kernel": "mel_kernel + mel_clamp_kernel", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": gbs / pk["hbm"], "traffic": None, "peak_source": f"hbm_gbs, {pk['src']}", "ms_per_launch": m["ms"] / m["launches"]}
+        # share of the step: the profiled run executes ONE decode step eagerly (the other MAX_TOKENS - 2 are graph replays that
+        # events cannot see inside), so a dec_* family stands for (MAX_TOKENS - 1) times its measured time
+        def est_ms(k, v):
+            if k == "lm_head":  # one call after the prefill + one in the eager decode step
+                return v["ms"] / nprof / 2 * MAX_TOKENS
+            return v["ms"] / nprof * ((MAX_TOKENS - 1) if k.startswith("dec_") else 1)
+        kernel_of = {"dec_attn": "decode_attn_mma_kernel", "mel": "mel_kernel"}
+        ranked = sorted(((est_ms(k, v), k) for k, v in rep.items() if k != "decode_graph_steps" and (v["flops"] or v["bytes"])), reverse=True)
+        for k in families:
+            families[k]["est_ms_in_step"] = est_ms(k, rep[k])
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+
+        def roof_of(fam):
+            v = rep[fam]
+            name = kernel_of.get(fam, f"gemm_tc_kernel ({fam})" if v["flops"] else fam)
+            hbm = fam in ("dec_attn", "mel") or not v["flops"]
+            if hbm:
+                ach, peak, unit, src = v["bytes"] / v["ms"] / 1e6, pk["hbm"], "GB/s", f"hbm_gbs, {pk['src']}"
+            else:
+                ach, peak, unit, src = v["flops"] / v["ms"] / 1e9, pk["tf_sustained"], "TFLOP/s", f"bf16_tflops_sustained, {pk['src']}"
+            return {"bound": "hbm" if hbm else "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": traffic.get(fam), "peak_source": src, "launches_per_step": v["launches"] // nprof,
+                    "ms_per_launch": v["ms"] / v["launches"], "est_share_of_step": est_ms(fam, v) / (dev_ms / args.steps),
+                    "algorithmic_per_launch": (v["bytes"] if hbm else v["flops"]) / v["launches"]}
+
+        roof = roof_of(ranked[0][1])  # the dominant kernel of the step (decode attention: KV-cache streaming, HBM-bound)
+        if roof["kernel"] == "decode_attn_mma_kernel":
+            # the same kernel inside the replayed CUDA graph (PDL overlap, warm instruction cache): marginal decode time with and
+            # without the attention launches, CUDA events around the decode stage
+            def decode_ms(skip):
+                os.environ["Q3ASR_DEC_SKIP"] = skip
+                model.batch_run(q3asr.STAGE_ALL, MAX_TOKENS, False)
+                model.sync()
+                model.batch_download(CLIPS_PER_GPU, MAX_TOKENS)
+                return float(model.stage_ms()[3])
+            full, without = decode_ms("0"), decode_ms("2")
+            os.environ["Q3ASR_DEC_SKIP"] = "0"
+            n_launch = (MAX_TOKENS - 1) * 28
+            kv_avg = 64 * (406 + (MAX_TOKENS + 1) / 2.0) * 4096.0  # mean K+V bytes one layer's attention reads per step
+            roof["in_graph"] = {"us_per_launch": (full - without) * 1000.0 / n_launch, "achieved": kv_avg / ((full - without) / n_launch) / 1e6,
+                                "frac": kv_avg / ((full - without) / n_launch) / 1e6 / pk["hbm"],
+                                "how": "decode stage time minus the same with attention launches dropped, / launches"}
+        tens = [k for _, k in ranked if rep[k]["flops"] > 0]
+        roof_gemm = roof_of(tens[0]) if tens else None
+        roof_mel = roof_of("mel") if "mel" in rep else None
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -272,7 +308,7 @@ def main():
                        "l2": "256 MiB flush between timed iterations; activations (>5 GB per step) exceed L2"},
             "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(("mel", "encoder", "prefill", "decode"), stage)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_mel": roof_mel, "kernel_families": families,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_mel": roof_mel, "kernel_families": families,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -342,12 +342,13 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
                      int K, int epi, int gelu, int bn, int use_simt, void* out) {
     return guarded(hh, [&](Handle& h) {
         Q3_CHECK(A && W && out && M > 0 && N > 0 && K > 0, Q3ASR_ERR_INVALID, "debug_gemm: bad argument");
-        if (epi >= 4) {  // decode-step weight-streaming kernel (skinny.cuh): 4 partial (summed here), 5 store, 6 swiglu
+        if (epi >= 4) {  // decode-step weight-streaming kernel (skinny.cuh): 4 split-K partials (summed here), 5 store
+            Q3_CHECK(epi <= 5, Q3ASR_ERR_INVALID, "debug_gemm: bad epilogue");
             const int sk = epi - 4;
             const int splits = gemm_skinny_splits(N, K, sk);
             bf16 *dA, *dW;
             void* dO;
-            const size_t out_elems = sk == SK_SWIGLU ? (size_t)M * (N / 2) : (size_t)M * N;
+            const size_t out_elems = (size_t)M * N;
             const size_t dev_bytes = sk == SK_PARTIAL ? sizeof(float) * out_elems * splits : 2 * out_elems;
             Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
             Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
@@ -357,17 +358,8 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
             std::vector<float> part;
             cudaError_t se = cudaSuccess;
             try {
-                float* fix = nullptr;
-                const size_t fix_elems = sk == SK_SWIGLU ? gemm_skinny_fix_elems(N, K) : 0;
-                if (fix_elems) {  // split-K SwiGLU with the last-arriver fix-up; run twice so the ticket reset is exercised
-                    Q3_CUDA(cudaMalloc(&fix, fix_elems * 4 + 4096));
-                    Q3_CUDA(cudaMemsetAsync(fix, 0, fix_elems * 4 + 4096, h.stream));
-                    gemm_skinny(dA, K, M, K, dW, N, sk, dO, N / 2, GU_UNIT, h.stream, fix);
-                    Q3_CUDA(cudaMemsetAsync(dO, 0xff, dev_bytes, h.stream));
-                }
-                gemm_skinny(dA, K, M, K, dW, N, sk, dO, sk == SK_SWIGLU ? N / 2 : N, GU_UNIT, h.stream, fix);
+                gemm_skinny(dA, K, M, K, dW, N, sk, dO, N, h.stream);
                 se = cudaStreamSynchronize(h.stream);
-                cudaFree(fix);
                 if (se == cudaSuccess) {
                     if (sk == SK_PARTIAL) {
                         part.resize(out_elems * splits);

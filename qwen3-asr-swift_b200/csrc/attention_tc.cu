@@ -17,6 +17,7 @@
 // The score buffer is double-buffered for head_dim 128, so the tensor core computes block j+1's scores while the softmax
 // warps work on block j.  Rounding points are those of attention.cu (P in bf16 for the PV product, row sums unrounded).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "ops.cuh"
 #include "ptx.cuh"
@@ -39,16 +40,21 @@ struct FaParams {
     float scale_log2;
 };
 
-template <int HD>
+// NQ = query tiles per CTA that share the K / V blocks: the two query heads of a kv head (GQA group 2) are processed
+// side by side, each by its own group of four softmax warps with its own score / output regions in TMEM, so the tensor
+// core works on one tile while the softmax warps work on the other (and K / V are fetched once for both).
+template <int HD, int NQ>
 struct FaCfg {
     static constexpr int SUBS = HD / 64;                   // 64-column (128-byte) sub-tiles along head_dim
-    static constexpr int KV_STAGES = HD == 128 ? 2 : 1;
-    static constexpr int S_BUFS = HD == 128 ? 2 : 1;
+    static constexpr int KV_STAGES = (HD == 128 && NQ == 1) ? 2 : 1;
+    static constexpr int S_BUFS = (HD == 128 && NQ == 1) ? 2 : 1;  // score buffers per tile
     static constexpr int Q_BYTES = FA_BQ * HD * 2;
     static constexpr int KV_BYTES = FA_BKV * HD * 2;       // one K (or V) block
     static constexpr int P_BYTES = FA_BQ * FA_BKV * 2;
-    static constexpr int TMEM_COLS = HD == 128 ? 512 : 256;  // S_BUFS * 128 score columns + HD output columns
-    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + 1024 + 256;
+    static constexpr int TMEM_NEED = NQ * (S_BUFS * FA_BKV + HD);
+    static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+    static constexpr int THREADS = 128 + 128 * NQ;
+    static constexpr int SMEM = NQ * Q_BYTES + 2 * KV_STAGES * KV_BYTES + NQ * P_BYTES + 1024 + 256;
 };
 
 // MN-major, 128-byte-swizzled operand descriptor: rows of 64 contiguous MN elements (128 B) per K index, 8 K indices per
@@ -57,37 +63,46 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(256, HD == 64 ? 2 : 1)
+// 2^x on the SFU (ex2.approx: 2 ulp; the result is rounded to bf16 or only scales fp32 partial sums)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int HD, bool CAUSAL, int NQ>
+__global__ void __launch_bounds__(FaCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1) ? 2 : 1)
 fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
              const FaParams p) {
-    using C = FaCfg<HD>;
-    const int seg = blockIdx.z, head = blockIdx.y;
+    using C = FaCfg<HD, NQ>;
+    // NQ == 1: blockIdx.y = query head.  NQ == 2: blockIdx.y = kv head, tiles = its two query heads.
+    const int seg = blockIdx.z;
+    const int head0 = NQ == 1 ? blockIdx.y : blockIdx.y * NQ;
     const int len = p.len[seg];
     const int q0 = blockIdx.x * FA_BQ;
     if (q0 >= len) return;
     const int row0 = p.row0[seg];
-    const int kvh = head / p.group;
+    const int kvh = head0 / p.group;
     const int kv_end = CAUSAL ? min(len, q0 + FA_BQ) : len;
     const int nb = (kv_end + FA_BKV - 1) / FA_BKV;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + C::Q_BYTES;
+    uint8_t* sQ = smem;                                   // [NQ] tiles
+    uint8_t* sK = sQ + NQ * C::Q_BYTES;
     uint8_t* sV = sK + C::KV_STAGES * C::KV_BYTES;
-    uint8_t* sP = sV + C::KV_STAGES * C::KV_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
+    uint8_t* sP = sV + C::KV_STAGES * C::KV_BYTES;        // [NQ] tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQ * C::P_BYTES);
     uint64_t* q_full = bars;
     uint64_t* k_full = q_full + 1;
     uint64_t* k_empty = k_full + C::KV_STAGES;
     uint64_t* v_full = k_empty + C::KV_STAGES;
     uint64_t* v_empty = v_full + C::KV_STAGES;
-    uint64_t* s_full = v_empty + C::KV_STAGES;
-    uint64_t* s_free = s_full + C::S_BUFS;
-    uint64_t* p_full = s_free + C::S_BUFS;
-    uint64_t* pv_full = p_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 1);
+    uint64_t* s_full = v_empty + C::KV_STAGES;            // [NQ][S_BUFS]
+    uint64_t* s_free = s_full + NQ * C::S_BUFS;           // [NQ][S_BUFS]
+    uint64_t* p_full = s_free + NQ * C::S_BUFS;           // [NQ]
+    uint64_t* pv_full = p_full + NQ;                      // [NQ]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + NQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -103,12 +118,14 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             ptx::mbar_init(&v_full[s], 1);
             ptx::mbar_init(&v_empty[s], 1);
         }
-        for (int s = 0; s < C::S_BUFS; s++) {
+        for (int s = 0; s < NQ * C::S_BUFS; s++) {
             ptx::mbar_init(&s_full[s], 1);
             ptx::mbar_init(&s_free[s], 128);
         }
-        ptx::mbar_init(p_full, 128);
-        ptx::mbar_init(pv_full, 1);
+        for (int t = 0; t < NQ; t++) {
+            ptx::mbar_init(&p_full[t], 128);
+            ptx::mbar_init(&pv_full[t], 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -116,13 +133,17 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_pv = tmem_base + C::S_BUFS * FA_BKV;
+    // TMEM columns: tile t has S_BUFS score buffers at t * (S_BUFS * 128) and its P V region after all score buffers
+    auto tmem_s = [&](int t, int sb) { return tmem_base + (uint32_t)((t * C::S_BUFS + sb) * FA_BKV); };
+    auto tmem_o = [&](int t) { return tmem_base + (uint32_t)(NQ * C::S_BUFS * FA_BKV + t * HD); };
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-            for (int s = 0; s < C::SUBS; s++) ptx::tma_load_2d(sQ + s * FA_BQ * 128, &tmQ, head * HD + s * 64, row0 + q0, q_full);
+            ptx::mbar_arrive_expect_tx(q_full, NQ * C::Q_BYTES);
+            for (int t = 0; t < NQ; t++)
+                for (int s = 0; s < C::SUBS; s++)
+                    ptx::tma_load_2d(sQ + t * C::Q_BYTES + s * FA_BQ * 128, &tmQ, (head0 + t) * HD + s * 64, row0 + q0, q_full);
             for (int j = 0; j < nb; j++) {
                 const int st = j % C::KV_STAGES;
                 const uint32_t ph = (j / C::KV_STAGES) & 1;
@@ -142,101 +163,142 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             constexpr uint32_t IDESC_S = ptx::umma_idesc_bf16(FA_BQ, FA_BKV);
             constexpr uint32_t IDESC_PV = ptx::umma_idesc_bf16(FA_BQ, HD) | (1u << 16);  // B (= V) is MN-major
             const uint32_t aQ = ptx::smem_u32(sQ), aP = ptx::smem_u32(sP);
-            auto issue_s = [&](int j) {
+            auto issue_s = [&](int t, int j) {  // scores of tile t against key block j (K_j already waited for)
                 const int st = j % C::KV_STAGES, sb = j % C::S_BUFS;
-                ptx::mbar_wait(&k_full[st], (j / C::KV_STAGES) & 1);
-                ptx::mbar_wait(&s_free[sb], ((j / C::S_BUFS) & 1) ^ 1);
+                ptx::mbar_wait(&s_free[t * C::S_BUFS + sb], ((j / C::S_BUFS) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t aK = ptx::smem_u32(sK + st * C::KV_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < HD / 16; ks++) {
                     const uint32_t off = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
-                    ptx::mma_bf16_ss(tmem_base + sb * FA_BKV, ptx::umma_desc_sw128(aQ + off), ptx::umma_desc_sw128(aK + off), IDESC_S, ks > 0 ? 1u : 0u);
+                    ptx::mma_bf16_ss(tmem_s(t, sb), ptx::umma_desc_sw128(aQ + t * C::Q_BYTES + off), ptx::umma_desc_sw128(aK + off), IDESC_S,
+                                     ks > 0 ? 1u : 0u);
                 }
-                ptx::mma_commit(&s_full[sb]);
-                ptx::mma_commit(&k_empty[st]);
+                ptx::mma_commit(&s_full[t * C::S_BUFS + sb]);
             };
-            ptx::mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < nb; j++) {
-                if (j + 1 < nb) issue_s(j + 1);
+            auto issue_pv = [&](int t, int j) {  // P_t V_j (V_j already waited for)
                 const int st = j % C::KV_STAGES;
-                ptx::mbar_wait(&v_full[st], (j / C::KV_STAGES) & 1);
-                ptx::mbar_wait(p_full, j & 1);
+                ptx::mbar_wait(&p_full[t], j & 1);
                 ptx::tc_fence_after();
                 const uint32_t aV = ptx::smem_u32(sV + st * C::KV_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < FA_BKV / 16; ks++) {
-                    const uint64_t da = ptx::umma_desc_sw128(aP + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
+                    const uint64_t da = ptx::umma_desc_sw128(aP + t * C::P_BYTES + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
                     const uint64_t db = umma_desc_mn_sw128(aV + ks * 16 * 128, FA_BKV * 128);
-                    ptx::mma_bf16_ss(tmem_pv, da, db, IDESC_PV, ks > 0 ? 1u : 0u);
+                    ptx::mma_bf16_ss(tmem_o(t), da, db, IDESC_PV, ks > 0 ? 1u : 0u);
                 }
-                ptx::mma_commit(pv_full);
+                ptx::mma_commit(&pv_full[t]);
+            };
+            ptx::mbar_wait(q_full, 0);
+            ptx::mbar_wait(&k_full[0], 0);
+            for (int t = 0; t < NQ; t++) issue_s(t, 0);
+            ptx::mma_commit(&k_empty[0]);
+            for (int j = 0; j < nb; j++) {
+                const int st = j % C::KV_STAGES;
+                const bool more = j + 1 < nb;
+                if (more) ptx::mbar_wait(&k_full[(j + 1) % C::KV_STAGES], ((j + 1) / C::KV_STAGES) & 1);
+                ptx::mbar_wait(&v_full[st], (j / C::KV_STAGES) & 1);
+                // per tile: this block's P V, then the next block's scores, so each softmax group always has work queued
+                for (int t = 0; t < NQ; t++) {
+                    if (NQ == 1 && more) issue_s(t, j + 1);  // double-buffered scores: run ahead of the softmax
+                    issue_pv(t, j);
+                    if (NQ > 1 && more) issue_s(t, j + 1);
+                }
                 ptx::mma_commit(&v_empty[st]);
+                if (more) ptx::mma_commit(&k_empty[(j + 1) % C::KV_STAGES]);
             }
         }
     } else if (warp >= 4) {
         // ===== softmax / output: one thread per query row =====
         const int q = warp & 3;
+        const int tq = (warp - 4) >> 2;  // which query tile this softmax group owns
+        const int head = head0 + tq;
         const int r = q * 32 + lane;
         const int q_abs = q0 + r;
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
+        const uint32_t tmem_pv = tmem_o(tq);
         float o_acc[HD];
 #pragma unroll
         for (int i = 0; i < HD; i++) o_acc[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
-        uint8_t* p_row = sP + r * 128;
+        uint8_t* p_row = sP + tq * C::P_BYTES + r * 128;
         for (int j = 0; j < nb; j++) {
             const int sb = j % C::S_BUFS;
             const int k0 = j * FA_BKV;
-            ptx::mbar_wait(&s_full[sb], (j / C::S_BUFS) & 1);
+            ptx::mbar_wait(&s_full[tq * C::S_BUFS + sb], (j / C::S_BUFS) & 1);
             ptx::tc_fence_after();
-            const uint32_t t_s = tmem_base + lane_addr + sb * FA_BKV;
+            const uint32_t t_s = tmem_s(tq, sb) + lane_addr;
             // columns this row may see in this block: keys < len, and <= its own position when causal
             int vis = len - k0;
             if (CAUSAL) vis = min(vis, q_abs - k0 + 1);
             vis = min(vis, FA_BKV);  // rows past the segment end (garbage rows) still see >= 1 key, so the max stays finite
-            // pass 1: row maximum
+            // TMEM loads are software-pipelined when this group is alone on the tensor core's results (NQ == 1): the load of
+            // chunk c + 1 is in flight while chunk c is processed.  With two groups the other group hides the latency.
+            constexpr bool PIPE = NQ == 1 && HD == 128;  // head_dim 64 runs two CTAs per SM at 128 registers: no room, no need
+            constexpr int NC = FA_BKV / 32;
+            uint32_t v[PIPE ? 2 : 1][32];
+            // pass 1: row maximum (only the chunk that straddles `vis` needs per-element masking)
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < FA_BKV / 32; c++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(t_s + c * 32, v);
-                ptx::tmem_ld_wait();
+            if (PIPE) ptx::tmem_ld_32x32(t_s, v[0]);
 #pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (c * 32 + i < vis) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int c = 0; c < NC; c++) {
+                uint32_t(&cur)[32] = v[PIPE ? (c & 1) : 0];
+                if (!PIPE) ptx::tmem_ld_32x32(t_s + c * 32, cur);
+                ptx::tmem_ld_wait();
+                if (PIPE && c + 1 < NC) ptx::tmem_ld_32x32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
+                if (c * 32 + 32 <= vis) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                } else if (c * 32 < vis) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (c * 32 + i < vis) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                }
             }
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);
+            const float alpha = fast_exp2(m_run - m_new);
             m_run = m_new;
             // fold in the previous block's P V (this also guarantees the tensor core is done reading the P buffer)
             if (j > 0) {
-                ptx::mbar_wait(pv_full, (j - 1) & 1);
+                ptx::mbar_wait(&pv_full[tq], (j - 1) & 1);
                 ptx::tc_fence_after();
+                if (PIPE) ptx::tmem_ld_32x32(tmem_pv + lane_addr, v[0]);
 #pragma unroll
                 for (int c = 0; c < HD / 32; c++) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(tmem_pv + lane_addr + c * 32, v);
+                    uint32_t(&cur)[32] = v[PIPE ? (c & 1) : 0];
+                    if (!PIPE) ptx::tmem_ld_32x32(tmem_pv + lane_addr + c * 32, cur);
                     ptx::tmem_ld_wait();
+                    if (PIPE && c + 1 < HD / 32) ptx::tmem_ld_32x32(tmem_pv + lane_addr + (c + 1) * 32, v[(c + 1) & 1]);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+                    for (int i = 0; i < 32; i++) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(cur[i])) * alpha;
                 }
             }
             // pass 2: P = exp2(s * scale - m), rounded to bf16 into the swizzled A-operand tile; row sum unrounded
             float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < FA_BKV / 32; c++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(t_s + c * 32, v);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
+            if (PIPE) ptx::tmem_ld_32x32(t_s, v[0]);
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float a = c * 32 + 2 * i < vis ? exp2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_new)) : 0.f;
-                    const float b = c * 32 + 2 * i + 1 < vis ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_new)) : 0.f;
-                    rs += a + b;
-                    pk[i] = pack_bf16x2(a, b);
+            for (int c = 0; c < NC; c++) {
+                uint32_t(&cur)[32] = v[PIPE ? (c & 1) : 0];
+                if (!PIPE) ptx::tmem_ld_32x32(t_s + c * 32, cur);
+                ptx::tmem_ld_wait();
+                if (PIPE && c + 1 < NC) ptx::tmem_ld_32x32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
+                uint32_t pk[16];
+                if (c * 32 + 32 <= vis) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float a = fast_exp2(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -m_new));
+                        const float b = fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -m_new));
+                        rs += a + b;
+                        pk[i] = pack_bf16x2(a, b);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float a = c * 32 + 2 * i < vis ? fast_exp2(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -m_new)) : 0.f;
+                        const float b = c * 32 + 2 * i + 1 < vis ? fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -m_new)) : 0.f;
+                        rs += a + b;
+                        pk[i] = pack_bf16x2(a, b);
+                    }
                 }
                 // 32 keys = four 16-byte chunks; chunk index within the 64-key sub-tile is XOR-swizzled with the row
                 uint8_t* sub = p_row + (c >> 1) * (128 * 128);
@@ -248,11 +310,11 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             }
             l_run = l_run * alpha + rs;
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&s_free[sb]);  // score buffer may be overwritten
-            ptx::fence_proxy_async();       // P stores visible to the tensor core
-            ptx::mbar_arrive(p_full);
+            ptx::mbar_arrive(&s_free[tq * C::S_BUFS + sb]);  // score buffer may be overwritten
+            ptx::fence_proxy_async();                        // P stores visible to the tensor core
+            ptx::mbar_arrive(&p_full[tq]);
         }
-        ptx::mbar_wait(pv_full, (nb - 1) & 1);
+        ptx::mbar_wait(&pv_full[tq], (nb - 1) & 1);
         ptx::tc_fence_after();
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         bf16* orow = p.o + (size_t)(row0 + q_abs) * p.ldo + head * HD;
@@ -284,16 +346,17 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, int NQ>
 void launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FaParams& p, const AttnSegs& segs, int heads,
             cudaStream_t st) {
+    using C = FaCfg<HD, NQ>;
     static bool attr = false;
     if (!attr) {
-        Q3_CUDA(cudaFuncSetAttribute(fa_tc_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaCfg<HD>::SMEM));
+        Q3_CUDA(cudaFuncSetAttribute(fa_tc_kernel<HD, CAUSAL, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr = true;
     }
-    dim3 grid((segs.max_len + FA_BQ - 1) / FA_BQ, heads, segs.n_segs);
-    fa_tc_kernel<HD, CAUSAL><<<grid, 256, FaCfg<HD>::SMEM, st>>>(tq, tk, tv, p);
+    dim3 grid((segs.max_len + FA_BQ - 1) / FA_BQ, heads / NQ, segs.n_segs);
+    fa_tc_kernel<HD, CAUSAL, NQ><<<grid, C::THREADS, C::SMEM, st>>>(tq, tk, tv, p);
     Q3_CUDA(cudaGetLastError());
 }
 
@@ -317,10 +380,14 @@ void flash_attn_tc_launch(const bf16* q, int ldq, const bf16* k, int ldk, const 
     p.ldo = ldo;
     p.group = group;
     p.scale_log2 = scale * 1.4426950408889634f;
-    if (head_dim == 64 && !causal) launch<64, false>(tq, tk, tv, p, segs, heads, st);
-    else if (head_dim == 64 && causal) launch<64, true>(tq, tk, tv, p, segs, heads, st);
-    else if (!causal) launch<128, false>(tq, tk, tv, p, segs, heads, st);
-    else launch<128, true>(tq, tk, tv, p, segs, heads, st);
+    static const bool no_pair = getenv("Q3ASR_ATTN_NO_PAIR") != nullptr && atoi(getenv("Q3ASR_ATTN_NO_PAIR")) != 0;
+    const bool pair = group == 2 && head_dim == 128 && !no_pair;  // GQA: both query heads of a kv head in one CTA
+    if (head_dim == 64 && !causal) launch<64, false, 1>(tq, tk, tv, p, segs, heads, st);
+    else if (head_dim == 64 && causal) launch<64, true, 1>(tq, tk, tv, p, segs, heads, st);
+    else if (!causal && pair) launch<128, false, 2>(tq, tk, tv, p, segs, heads, st);
+    else if (!causal) launch<128, false, 1>(tq, tk, tv, p, segs, heads, st);
+    else if (pair) launch<128, true, 2>(tq, tk, tv, p, segs, heads, st);
+    else launch<128, true, 1>(tq, tk, tv, p, segs, heads, st);
 }
 
 }  // namespace q3

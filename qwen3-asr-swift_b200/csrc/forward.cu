@@ -454,7 +454,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         const bool last = l + 1 == c.dec_layers;
         {
             ProfScope ps(h, "dec_qkv", 2.0 * B * H * nqkv, 2.0 * H * nqkv);
-            if (!(skip & 1)) gemm_skinny(xn, H, B, H, w.qkv_w, nqkv, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 1)) gemm_skinny(xn, H, B, H, w.qkv_w, nqkv, SK_PARTIAL, ws, 0, st);
         }
         {
             ProfScope ps(h, "dec_attn", 0, kv_bytes);
@@ -463,7 +463,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         }
         {
             ProfScope ps(h, "dec_o", 2.0 * B * nq * H, 2.0 * nq * H);
-            if (!(skip & 4)) gemm_skinny(att, nq, B, nq, w.o_w, H, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 4)) gemm_skinny(att, nq, B, nq, w.o_w, H, SK_PARTIAL, ws, 0, st);
         }
         {
             ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
@@ -478,7 +478,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         }
         {
             ProfScope ps(h, "dec_down", 2.0 * B * H * c.dec_inter, 2.0 * H * c.dec_inter);
-            if (!(skip & 32)) gemm_skinny(act, c.dec_inter, B, c.dec_inter, w.down_w, H, SK_PARTIAL, ws, 0, 0, st);
+            if (!(skip & 32)) gemm_skinny(act, c.dec_inter, B, c.dec_inter, w.down_w, H, SK_PARTIAL, ws, 0, st);
         }
         {
             ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);

@@ -1,6 +1,7 @@
 // gemm.cu — host side of the tcgen05 GEMM: tensor-map construction, tile selection, dispatch, plus the
 // CUDA-core checker kernels used by the GPU tests to bisect tensor-core bugs (never by the model code).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -315,17 +316,16 @@ template <int NB, int EPI>
 void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB, EPI)));
+        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB)));
         attr_set = true;
     }
-    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB, EPI), st, tw, tx, p);
+    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB), st, tw, tx, p);
 }
 template <int NB>
 void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
     switch (epi) {
         case SK_PARTIAL: launch_skinny<NB, SK_PARTIAL>(tw, tx, p, grid, st); break;
         case SK_STORE: launch_skinny<NB, SK_STORE>(tw, tx, p, grid, st); break;
-        case SK_SWIGLU: launch_skinny<NB, SK_SWIGLU>(tw, tx, p, grid, st); break;
         default: throw Error(1, "gemm_skinny: bad epilogue");
     }
 }
@@ -339,33 +339,20 @@ int gemm_skinny_splits(int N, int K, int epi) {
     return cdiv(num_kb, per);  // no empty slices
 }
 
-size_t gemm_skinny_fix_elems(int N, int K) {
-    const int splits = gemm_skinny_splits(N, K, SK_SWIGLU);
-    return splits > 1 ? (size_t)cdiv(N, SK_BM) * splits * SKINNY_MAX_ROWS * SK_BM : 0;
-}
-
-void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
-                 cudaStream_t st, float* fix_ws) {
+void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, cudaStream_t st) {
     Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "gemm_skinny: 1..128 token rows per launch");
     Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0, 1, "gemm_skinny: K and ldx must be multiples of 8");
-    if (epi == SK_SWIGLU)
-        Q3_CHECK(N % SK_BM == 0 && (gu_half == 32 || gu_half == 64), 1, "gemm_skinny: SwiGLU needs N % 128 == 0 and 32- or 64-row gate/up blocks");
-
     const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
     SkinnyDev p;
     memset(&p, 0, sizeof(p));
     p.N = N;
     p.Mtok = Mtok;
     p.num_kb = cdiv(K, SK_BK);
-    const int splits = (epi == SK_SWIGLU && fix_ws == nullptr) ? 1 : gemm_skinny_splits(N, K, epi);
+    const int splits = gemm_skinny_splits(N, K, epi);
     p.kb_per_split = cdiv(p.num_kb, splits);
-    p.splits = splits;
-    p.fix_ws = fix_ws;
-    p.tickets = fix_ws ? reinterpret_cast<int*>(fix_ws + gemm_skinny_fix_elems(N, K)) : nullptr;
     p.out = out;
     p.ldo = ldo;
     p.split_stride = (long long)Mtok * N;
-    p.gu_half = gu_half;
     CUtensorMap tw, tx;
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};

@@ -405,18 +405,12 @@ constexpr int SKINNY_MAX_ROWS = 128;
 enum SkinnyEpi : int {
     SK_PARTIAL = 0,  // out(fp32)[split][m][n] = acc
     SK_STORE = 1,    // out(bf16)[m][n] = bf16(acc)                       (splits must be 1)
-    SK_SWIGLU = 2,   // W rows interleaved gate/up in blocks of `gu_half`: out(bf16)[m][j] = bf16(bf16(silu(bf16 g)) * bf16 u)
 };
 
-// number of K splits the launch will use for this shape (1 for SK_STORE; SK_SWIGLU splits only when given a fix-up workspace)
+// number of K splits the launch will use for this shape (1 for SK_STORE)
 int gemm_skinny_splits(int N, int K, int epi);
-// fp32 elements of the SK_SWIGLU split-K fix-up workspace for this shape (0: no split); it is followed by one int ticket
-// per 128-row tile, which must be zero before the first launch (the kernel leaves them zero)
-size_t gemm_skinny_fix_elems(int N, int K);
-// SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo];
-// SK_SWIGLU: W = gate/up rows interleaved in blocks of gu_half (= GU_UNIT) rows, out = bf16 [Mtok, ldo] (N/2 columns)
-void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, int gu_half,
-                 cudaStream_t st, float* fix_ws = nullptr);
+// SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo]
+void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, cudaStream_t st);
 // final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st);
 

@@ -77,7 +77,7 @@ struct BatchState {
     size_t o_ids = 0, o_audio_src = 0, o_pos = 0, o_row_seq = 0, o_seq_row0 = 0, o_seq_len = 0, o_last_row = 0, o_page_table = 0,
            o_ident = 0, o_pos0 = 0;
     DevBuf a1, a2, a3, ex, exn, eqkv, eatt, effn, audio;        // encoder activations
-    DevBuf dx, dxn, dqkv, dq, dkc, dvc, datt, dact, dlast, dws, dfix; // decoder activations (dws: fp32 split-K partials, dfix: SwiGLU fix-up slabs)
+    DevBuf dx, dxn, dqkv, dq, dkc, datt, dact, dlast, dws; // decoder activations (dws: fp32 split-K partials of the decode step)
     DevBuf kv_pool, rope_tab;
     int rope_n = 0;          // positions tabulated in rope_tab
     DevBuf amax_val, amax_idx, logits;
@@ -93,7 +93,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &dvc, &datt, &dact, &dlast, &dws, &dfix, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }

@@ -22,10 +22,6 @@ struct SkinnyDev {
     void* out;
     int ldo;                // bf16 outputs: row pitch in elements
     long long split_stride; // SK_PARTIAL: elements between split slabs
-    int gu_half;            // SK_SWIGLU: rows per gate (and per up) block
-    float* fix_ws;          // SK_SWIGLU with split K: fp32 slabs [tile][split][NB][128]
-    int* tickets;           // SK_SWIGLU with split K: one arrival counter per tile (zero on entry, left zero)
-    int splits;
 };
 
 constexpr int SK_BM = 128;  // weight rows per CTA
@@ -35,15 +31,7 @@ __host__ __device__ constexpr int sk_stage_bytes(int NB) { return SK_BM * 128 + 
 // CTAs to become resident early (programmatic dependent launch)
 __host__ __device__ constexpr int sk_stages(int NB) { return (96 * 1024) / sk_stage_bytes(NB) > 6 ? 6 : (96 * 1024) / sk_stage_bytes(NB); }
 __host__ __device__ constexpr int sk_tmem_cols(int NB) { return NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256; }
-__host__ __device__ constexpr int sk_smem_bytes(int NB, int epi) {
-    return sk_stages(NB) * sk_stage_bytes(NB) + 1024 + 256 + (epi == SK_SWIGLU ? 64 * (NB + 1) * 4 : 0);
-}
-
-__device__ __forceinline__ float sk_swiglu(float g_acc, float u_acc) {
-    const float g = bf16_round(g_acc);
-    const float s = bf16_round(silu(g));
-    return s * bf16_round(u_acc);
-}
+__host__ __device__ constexpr int sk_smem_bytes(int NB) { return sk_stages(NB) * sk_stage_bytes(NB) + 1024 + 256; }
 
 template <int NB, int EPI>
 __global__ void __launch_bounds__(256, 1)
@@ -61,7 +49,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-    float* s_u = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // SK_SWIGLU: [64][NB + 1]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * SK_BM;
@@ -137,97 +124,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16);
         const bool have = kb1 > kb0;  // an empty K slice contributes zeros (its accumulator was never written)
 
-        if constexpr (EPI == SK_SWIGLU) {
-            const int blk = r / p.gu_half;
-            const bool is_up = blk & 1;
-            const int jl = (blk >> 1) * p.gu_half + r % p.gu_half;  // output column within the tile, 0..63
-            bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)blockIdx.x * 64 + jl;
-            if (p.splits == 1) {
-                // pass 1: up lanes publish their values
-#pragma unroll 1
-                for (int c = 0; c < NB / CH; c++) {
-                    uint32_t v[CH];
-                    if constexpr (CH == 32) ptx::tmem_ld_32x32(t_row + c * CH, v); else ptx::tmem_ld_32x16(t_row + c * CH, reinterpret_cast<uint32_t(&)[16]>(v));
-                    ptx::tmem_ld_wait();
-                    if (is_up) {
-#pragma unroll
-                        for (int j = 0; j < CH; j++) s_u[jl * (NB + 1) + c * CH + j] = __uint_as_float(v[j]);
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-#pragma unroll 1
-                for (int c = 0; c < NB / CH; c++) {
-                    uint32_t v[CH];
-                    if constexpr (CH == 32) ptx::tmem_ld_32x32(t_row + c * CH, v); else ptx::tmem_ld_32x16(t_row + c * CH, reinterpret_cast<uint32_t(&)[16]>(v));
-                    ptx::tmem_ld_wait();
-                    if (!is_up) {
-#pragma unroll
-                        for (int j = 0; j < CH; j++) {
-                            const int m = c * CH + j;
-                            if (m < p.Mtok)
-                                out[(size_t)m * p.ldo] = __float2bfloat16_rn(sk_swiglu(__uint_as_float(v[j]), s_u[jl * (NB + 1) + m]));
-                        }
-                    }
-                }
-            } else {
-                // split K: every CTA of the tile parks its fp32 accumulator in a slab; the last one to arrive sums the slabs
-                // in split order (deterministic) and applies SwiGLU.
-                float* slab0 = p.fix_ws + (size_t)blockIdx.x * p.splits * NB * SK_BM;
-                float* mine = slab0 + (size_t)split * NB * SK_BM + r;
-#pragma unroll 1
-                for (int c = 0; c < NB / CH; c++) {
-                    uint32_t v[CH];
-                    if constexpr (CH == 32) ptx::tmem_ld_32x32(t_row + c * CH, v); else ptx::tmem_ld_32x16(t_row + c * CH, reinterpret_cast<uint32_t(&)[16]>(v));
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < CH; j++)
-                        if (c * CH + j < p.Mtok) mine[(size_t)(c * CH + j) * SK_BM] = __uint_as_float(v[j]);
-                }
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-                if (r == 0) *s_flag = atomicAdd(p.tickets + blockIdx.x, 1);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (*s_flag == p.splits - 1) {
-                    __threadfence();
-                    if (r == 0) p.tickets[blockIdx.x] = 0;  // ready for the next launch
-                    // thread t owns outputs [4 (t & 15), +4) of the tile for token rows m = (t >> 4) + 8 i: float4 loads of the gate
-                    // rows and of their up partners, two token rows (12 loads for three splits) in flight at a time
-                    const int t = q * 32 + lane;
-                    const int j4 = (t & 15) * 4;
-                    const int rg = (j4 / p.gu_half) * 2 * p.gu_half + j4 % p.gu_half;  // gate row; the up row is rg + gu_half
-                    bf16* o4 = reinterpret_cast<bf16*>(p.out) + (size_t)blockIdx.x * 64 + j4;
-                    for (int m0 = t >> 4; m0 < p.Mtok; m0 += 16) {
-                        float4 g[2], u[2];
-#pragma unroll
-                        for (int i = 0; i < 2; i++) g[i] = u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int sp = 0; sp < p.splits; sp++) {
-                            float4 a[2], b[2];
-#pragma unroll
-                            for (int i = 0; i < 2; i++) {
-                                const int m = m0 + 8 * i;
-                                const float* rowp = slab0 + ((size_t)sp * NB + (m < p.Mtok ? m : m0)) * SK_BM;
-                                a[i] = __ldcg(reinterpret_cast<const float4*>(rowp + rg));
-                                b[i] = __ldcg(reinterpret_cast<const float4*>(rowp + rg + p.gu_half));
-                            }
-#pragma unroll
-                            for (int i = 0; i < 2; i++) {
-                                g[i].x += a[i].x; g[i].y += a[i].y; g[i].z += a[i].z; g[i].w += a[i].w;
-                                u[i].x += b[i].x; u[i].y += b[i].y; u[i].z += b[i].z; u[i].w += b[i].w;
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; i++) {
-                            const int m = m0 + 8 * i;
-                            if (m < p.Mtok)
-                                *reinterpret_cast<uint2*>(o4 + (size_t)m * p.ldo) =
-                                    make_uint2(pack_bf16x2(sk_swiglu(g[i].x, u[i].x), sk_swiglu(g[i].y, u[i].y)),
-                                               pack_bf16x2(sk_swiglu(g[i].z, u[i].z), sk_swiglu(g[i].w, u[i].w)));
-                        }
-                    }
-                }
-            }
-        } else {
+        {
 #pragma unroll 1
             for (int c = 0; c < NB / CH; c++) {
                 uint32_t v[CH];

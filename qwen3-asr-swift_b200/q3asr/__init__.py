@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libq3asr.so")
 OK = 0
 STAGE_MEL, STAGE_ENCODER, STAGE_PREFILL, STAGE_DECODE, STAGE_ALL = 1, 2, 4, 8, 15
 EPI_NORMAL, EPI_SWIGLU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 3
-EPI_SKINNY_PARTIAL, EPI_SKINNY_STORE, EPI_SKINNY_SWIGLU = 4, 5, 6  # decode-step weight-streaming kernel
+EPI_SKINNY_PARTIAL, EPI_SKINNY_STORE = 4, 5  # decode-step weight-streaming kernel
 
 
 class Q3Error(RuntimeError):
@@ -395,7 +395,7 @@ class Qwen3ASRModel:
             out = np.empty((M, N), dtype=np.float32)
         elif epi == EPI_ARGMAX:
             out = np.empty(M, dtype=np.int32)
-        elif epi in (EPI_SWIGLU, EPI_SKINNY_SWIGLU):
+        elif epi == EPI_SWIGLU:
             out = np.empty((M, N // 2), dtype=np.uint16)
         else:
             out = np.empty((M, N), dtype=np.uint16)

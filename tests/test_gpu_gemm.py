@@ -159,21 +159,3 @@ def test_skinny_partial_and_store(tiny_model, M, N, K):
     assert got.shape == (M, N)
     assert np.allclose(got, ref, rtol=2e-5, atol=2e-4), np.abs(got - ref).max()
     _close_bf16(tiny_model.debug_gemm(A, W, epi=5), ref, f"skinny store {M}x{N}x{K}")
-
-
-@pytest.mark.parametrize("M,I,bn", [(64, 3072, 128), (7, 256, 128), (40, 192, 64), (128, 512, 64), (16, 128, 128)])
-def test_skinny_swiglu(tiny_model, M, I, bn):
-    rng = np.random.default_rng(M + I + bn)
-    K = 1024 if I >= 3072 else 256  # the 0.6B shape splits K three ways (last-arriver fix-up); small ones split up to four ways
-    A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
-    Wi = _interleave_gate_up(G, U)
-    g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
-    u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
-    s = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
-    got = tiny_model.debug_gemm(A, Wi, epi=6, bn=bn)
-    # three bf16 roundings (g, silu(g), u) feed the product; with K = 1024 the fp32 summation order flips a few of them
-    _close_bf16(got, s * u, f"skinny swiglu {M}x{I} bn={bn}", ulps=3 if K == 256 else 6)
-    # the two SwiGLU kernels agree bit for bit when fed the same operands (same epilogue arithmetic)
-    if M <= 128:
-        same = tiny_model.debug_gemm(A, Wi, epi=1, bn=bn)
-        assert (np.abs(got - same) <= (1 if K == 256 else 4) * 2.0 ** -7 * np.maximum(np.abs(same), 1e-2)).all()
