@@ -283,19 +283,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll 1
                 for (int c = chalf; c < BN / 32; c += 2) {
+                    const int col = n0 + c * 32;
+                    // bias and residual do not depend on the accumulator: fetch them under the TMEM load's latency
+                    uint4 bvv[4], rvv[4];
+                    if (EPI == EPI_NORMAL || EPI == EPI_F32) {
+                        if (row_ok && p.bias != nullptr) {
+                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) bvv[j] = __ldg(bp + j);
+                        }
+                        if (EPI == EPI_NORMAL && row_ok && p.resid != nullptr) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) rvv[j] = __ldg(rp + j);
+                        }
+                    }
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_row + c * 32, v);
                     ptx::tmem_ld_wait();
                     if (row_ok) {
-                        const int col = n0 + c * 32;
                         float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
                         if (p.bias != nullptr) {
-                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const uint4 bv = __ldg(bp + j);
+                                const uint4 bv = bvv[j];
                                 float2 t;
                                 t = unpack_bf16x2(bv.x); f[8 * j + 0] += t.x; f[8 * j + 1] += t.y;
                                 t = unpack_bf16x2(bv.y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
@@ -325,10 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int j = 0; j < 32; j++) f[j] = 0.f;
                             }
                             if (p.resid != nullptr) {
-                                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
-                                    const uint4 rv = __ldg(rp + j);
+                                    const uint4 rv = rvv[j];
                                     float2 t;
                                     t = unpack_bf16x2(rv.x); f[8 * j + 0] = t.x + bf16_round(f[8 * j + 0]); f[8 * j + 1] = t.y + bf16_round(f[8 * j + 1]);
                                     t = unpack_bf16x2(rv.y); f[8 * j + 2] = t.x + bf16_round(f[8 * j + 2]); f[8 * j + 3] = t.y + bf16_round(f[8 * j + 3]);
