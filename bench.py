@@ -94,8 +94,9 @@ def make_clips(rank):
     return [synth.clip(rank * CLIPS_PER_GPU + i, n) for i in range(CLIPS_PER_GPU)]
 
 
-def cpu_sample(seconds, tokens, state_dict=None, threads=None):
-    """Times the CPU oracle (fp32, torch-CPU matmuls, all host threads) on one clip; returns (rtfx, cores, sample)."""
+def cpu_sample(seconds, tokens, clips=1, state_dict=None, threads=None):
+    """Times the CPU oracle (fp32, torch-CPU matmuls, all host threads) on `clips` clips one after the other, as the reference's
+    own serial loop does (TranscribeBatchCommand.swift:82); returns (callable -> seconds, cores, description)."""
     import torch
     from oracle import mel as omel
     from oracle import model as omodel
@@ -106,28 +107,30 @@ def cpu_sample(seconds, tokens, state_dict=None, threads=None):
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     orc = omodel.Oracle(cfg, state_dict, emulate_bf16=False)
-    x = synth.clip(0, seconds * 16000)
+    xs = [synth.clip(i, seconds * 16000) for i in range(clips)]
 
     def once():
         t0 = time.perf_counter()
-        feats = omel.mel(x)
-        emb = orc.encode(feats)
-        orc.greedy(emb, tokens, stop_on_eos=False)
+        for x in xs:
+            feats = omel.mel(x)
+            emb = orc.encode(feats)
+            orc.greedy(emb, tokens, stop_on_eos=False)
         return time.perf_counter() - t0
-    return once, cores, f"1 clip x {seconds} s, mel + encoder + prefill + {tokens} greedy tokens, fp32 torch-CPU, {cores} threads"
+    return once, cores, (f"{clips} clip(s) x {seconds} s one after the other, mel + encoder + prefill + {tokens} greedy tokens each, "
+                         f"fp32 torch-CPU, {cores} threads")
 
 
 def run_reference(args, rank):
     """The reference arm: the CPU restatement of the reference's algorithm (oracle/), all host threads, rank 0 only."""
     if rank != 0:
         return
-    seconds, tokens = 10, 16
-    once, cores, sample = cpu_sample(seconds, tokens)
+    seconds, tokens, clips = CLIP_SECONDS, 16, 2
+    once, cores, sample = cpu_sample(seconds, tokens, clips)
     for _ in range(args.warmup):
         once()
     t = [once() for _ in range(args.steps)]
     total = float(sum(t))
-    val = seconds * args.steps / total
+    val = clips * seconds * args.steps / total
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
@@ -283,7 +286,8 @@ def main():
             roof["in_graph"] = {"us_per_launch": (full - without) * 1000.0 / n_launch, "achieved": kv_avg / ((full - without) / n_launch) / 1e6,
                                 "frac": kv_avg / ((full - without) / n_launch) / 1e6 / pk["hbm"],
                                 "how": "decode stage time minus the same with attention launches dropped, / launches"}
-        tens = [k for _, k in ranked if rep[k]["flops"] > 0]
+        # the top dense tensor-core family (encoder / prefill GEMMs and convolutions; the decode-step products are weight streaming)
+        tens = [k for _, k in ranked if rep[k]["flops"] > 0 and not k.startswith("dec_") and k != "lm_head" and not k.endswith("attn")]
         roof_gemm = roof_of(tens[0]) if tens else None
         roof_mel = roof_of("mel") if "mel" in rep else None
 
@@ -291,9 +295,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = model.state_dict()  # the same bf16 weights, read back through the C ABI
-        once, cores, sample = cpu_sample(CLIP_SECONDS, 16, state_dict=sd)
+        n_cpu = 8
+        once, cores, sample = cpu_sample(CLIP_SECONDS, 16, n_cpu, state_dict=sd)
         sec = once()
-        cpu = {"value": CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s)"}
+        cpu = {"value": n_cpu * CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s of CPU time)",
+               "note": "16 decode tokens per clip instead of 128: the CPU number is flattered, the GPU/CPU ratio is a lower bound"}
     model.close()
 
     if rank == 0:
