@@ -167,6 +167,25 @@ int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size
 /* the scheduler's assignment alone (host logic; no GPU needed): gpu_out[i] = GPU of utterance i */
 int q3asr_schedule(const size_t* n_samples, int batch, int n_gpus, int* gpu_out);
 
+/* ---- tokenizer (host only; replaces Qwen3Tokenizer, Sources/AudioCommon/Tokenizer.swift:17-328) ---- */
+typedef struct q3asr_tokenizer q3asr_tokenizer;
+/* path: a directory holding vocab.json (+ optional tokenizer_config.json, merges.txt) or the vocab.json itself (Tokenizer.swift:38-62).
+ * *out is set even on failure (read q3asr_tokenizer_last_error, then destroy). */
+int q3asr_tokenizer_load(const char* path, q3asr_tokenizer** out);
+/* the reference's test-only initialiser (Tokenizer.swift:31-35): explicit id -> token pairs, no merges */
+int q3asr_tokenizer_from_pairs(const int32_t* ids, const char* const* tokens, int n, q3asr_tokenizer** out);
+/* appends one merge rule (rank = number of rules so far); tests build small BPE tables with it */
+int q3asr_tokenizer_add_merge(q3asr_tokenizer* t, const char* first, const char* second);
+void q3asr_tokenizer_destroy(q3asr_tokenizer* t);
+const char* q3asr_tokenizer_last_error(const q3asr_tokenizer* t);
+int q3asr_tokenizer_size(const q3asr_tokenizer* t, int* n_tokens, int* n_merges);
+/* ids -> UTF-8 text (Tokenizer.swift:111-142).  out may be NULL to query *needed (bytes incl. the terminator). */
+int q3asr_tokenizer_decode(const q3asr_tokenizer* t, const int32_t* ids, int n, char* out, size_t cap, size_t* needed);
+/* UTF-8 text -> ids (Tokenizer.swift:195-278).  ids may be NULL to query *n. */
+int q3asr_tokenizer_encode(const q3asr_tokenizer* t, const char* text, int32_t* ids, int cap, int* n);
+/* id of a token string, or -1 (Tokenizer.swift:281-283) */
+int q3asr_tokenizer_token_id(const q3asr_tokenizer* t, const char* token);
+
 /* ---- debug / test hooks (exercise single kernels through the C ABI) ---- */
 /* C[M,N] = A[M,K] W[N,K]^T with bf16 (uint16) host operands; epi: 0 store(+bias,+gelu), 1 swiglu (W rows alternate
  * 32 gate / 32 up rows), 2 fp32, 3 argmax.

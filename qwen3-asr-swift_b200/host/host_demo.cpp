@@ -22,6 +22,22 @@ int main(int argc, char** argv) {
         } catch (const AudioModelError& e) {
             printf("load error (expected without a GPU): %s\n", e.what());
         }
+        // tokenizer through the host mirror: a two-token vocabulary written to a temp directory
+        if (argc > 2) {
+            const std::string dir = argv[2];
+            FILE* f = fopen((dir + "/vocab.json").c_str(), "w");
+            if (!f) return 7;
+            fputs("{\"Hello\": 5, \"\u0120world\": 6, \"<asr_text>\": 7}", f);
+            fclose(f);
+            Tokenizer t = Tokenizer::fromDirectory(dir);
+            if (t.decode({7, 5, 6}) != "<asr_text>Hello world") return 8;
+            try {
+                Tokenizer::fromDirectory(dir + "/nope");
+                return 9;
+            } catch (const AudioModelError&) {
+            }
+            printf("tokenizer ok\n");
+        }
         printf("%s\n", q3asr_version());
         return 0;
     }

@@ -56,10 +56,36 @@ struct AudioModelError : std::runtime_error {  // AudioCommon/AudioModelError.sw
     AudioModelError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-// token-id <-> text is the host's business (the reference keeps Qwen3Tokenizer in Swift); a caller plugs one in here
+// token-id <-> text: any pair of functions, or the library's own byte-level BPE tokenizer (Qwen3Tokenizer,
+// AudioCommon/Tokenizer.swift) loaded from the checkpoint directory's vocab.json / tokenizer_config.json / merges.txt
 struct Tokenizer {
     std::function<std::vector<int32_t>(const std::string&)> encode;
     std::function<std::string(const std::vector<int32_t>&)> decode;
+
+    static Tokenizer fromDirectory(const std::string& dir) {
+        q3asr_tokenizer* raw = nullptr;
+        const int rc = q3asr_tokenizer_load(dir.c_str(), &raw);
+        std::shared_ptr<q3asr_tokenizer> t(raw, q3asr_tokenizer_destroy);
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("tokenizer: ") + q3asr_tokenizer_last_error(raw));
+        Tokenizer out;
+        out.encode = [t](const std::string& text) {
+            int n = 0;
+            q3asr_tokenizer_encode(t.get(), text.c_str(), nullptr, 0, &n);
+            std::vector<int32_t> ids((size_t)std::max(n, 1));
+            q3asr_tokenizer_encode(t.get(), text.c_str(), ids.data(), (int)ids.size(), &n);
+            ids.resize((size_t)n);
+            return ids;
+        };
+        out.decode = [t](const std::vector<int32_t>& ids) {
+            size_t need = 0;
+            q3asr_tokenizer_decode(t.get(), ids.data(), (int)ids.size(), nullptr, 0, &need);
+            std::string s(need, '\0');
+            q3asr_tokenizer_decode(t.get(), ids.data(), (int)ids.size(), &s[0], need, nullptr);
+            s.resize(need ? need - 1 : 0);
+            return s;
+        };
+        return out;
+    }
 };
 
 class Qwen3ASRModel;
@@ -99,6 +125,10 @@ class Qwen3ASRModel {
         std::unique_ptr<Qwen3ASRModel> m(new Qwen3ASRModel(detectModelSize(modelId), device));
         int rc = q3asr_load_safetensors(m->h_, modelDir.c_str());
         if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("weightLoadingFailed: ") + q3asr_last_error(m->h_));
+        try {  // Qwen3ASR.swift:643-649: the tokenizer is optional (ids are returned as text without it, :288-289)
+            m->tok_ = Tokenizer::fromDirectory(modelDir);
+        } catch (const AudioModelError&) {
+        }
         if (progressHandler) progressHandler(1.0, "Ready");
         return m;
     }

@@ -59,6 +59,8 @@ EXPORTS = [
     "q3asr_profile", "q3asr_profile_report",
     "q3asr_pool_create", "q3asr_pool_destroy", "q3asr_pool_last_error", "q3asr_pool_transcribe_ids", "q3asr_schedule",
     "q3asr_debug_gemm", "q3asr_debug_conv", "q3asr_debug_attention",
+    "q3asr_tokenizer_load", "q3asr_tokenizer_from_pairs", "q3asr_tokenizer_add_merge", "q3asr_tokenizer_destroy",
+    "q3asr_tokenizer_last_error", "q3asr_tokenizer_size", "q3asr_tokenizer_decode", "q3asr_tokenizer_encode", "q3asr_tokenizer_token_id",
 ]
 
 _lib = None
@@ -120,6 +122,17 @@ def lib():
         L.q3asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, ci, ci, ctypes.c_float, ci, vp]
+        L.q3asr_tokenizer_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.q3asr_tokenizer_from_pairs.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
+        L.q3asr_tokenizer_add_merge.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+        L.q3asr_tokenizer_destroy.argtypes = [vp]
+        L.q3asr_tokenizer_destroy.restype = None
+        L.q3asr_tokenizer_last_error.argtypes = [vp]
+        L.q3asr_tokenizer_last_error.restype = ctypes.c_char_p
+        L.q3asr_tokenizer_size.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.q3asr_tokenizer_decode.argtypes = [vp, vp, ci, ctypes.c_char_p, cs, ctypes.POINTER(cs)]
+        L.q3asr_tokenizer_encode.argtypes = [vp, ctypes.c_char_p, vp, ci, ctypes.POINTER(ci)]
+        L.q3asr_tokenizer_token_id.argtypes = [vp, ctypes.c_char_p]
         _lib = L
     return _lib
 
@@ -209,6 +222,8 @@ class Qwen3ASRModel:
     def from_pretrained(cls, model_dir, size="0.6B", device=0):
         m = cls(size=size, device=device)
         m._ck(lib().q3asr_load_safetensors(m._h, os.fspath(model_dir).encode()))
+        if os.path.exists(os.path.join(model_dir, "vocab.json")):  # Qwen3ASR.swift:643-649
+            m.tokenizer = Qwen3Tokenizer(path=os.fspath(model_dir))
         return m
 
     @classmethod
@@ -308,14 +323,25 @@ class Qwen3ASRModel:
                                             int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
         return [ids[i, :lens[i]].copy() for i in range(len(clips))]
 
-    def transcribe(self, audio, sample_rate=16000, language_ids=None, max_tokens=448, context_ids=None):
-        """Signature of Qwen3ASRModel.transcribe(audio:sampleRate:language:maxTokens:context:); returns the ids
-        joined by spaces, the reference's own no-tokenizer fallback."""
+    tokenizer = None  # a Qwen3Tokenizer; set by from_pretrained when the checkpoint directory has a vocab.json
+
+    def transcribe(self, audio, sample_rate=16000, language=None, max_tokens=448, context=None, language_ids=None, context_ids=None):
+        """Qwen3ASRModel.transcribe(audio:sampleRate:language:maxTokens:context:) (Qwen3ASR.swift:131-164, 181-289): with a tokenizer
+        the text after "<asr_text>", else the ids joined by spaces (the reference's own fallback)."""
         if sample_rate != 16000:
             raise Q3Error(1, "resampling is outside the B200 path: feed 16 kHz audio (AudioPreprocessing.swift:323-337)")
+        tok = self.tokenizer
+        if tok is not None:
+            if context is not None and context_ids is None:
+                context_ids = tok.encode(context)                    # Qwen3ASR.swift:203-206
+            if language is not None and language_ids is None:
+                language_ids = tok.encode("language " + language)    # Qwen3ASR.swift:228-232
         pr = [{"context": context_ids, "language": language_ids}]
         ids = self.transcribe_ids([audio], max_tokens=max_tokens, stop_on_eos=True, prompts=pr)[0]
-        return " ".join(str(int(t)) for t in ids)
+        if tok is None:
+            return " ".join(str(int(t)) for t in ids)
+        raw = tok.decode([int(t) for t in ids])
+        return raw.split("<asr_text>", 1)[1].strip(" ") if "<asr_text>" in raw else raw
 
     def decode_forced(self, audio, forced, prompt=None):
         audio = np.ascontiguousarray(audio, dtype=np.float32)
@@ -430,6 +456,69 @@ class Qwen3ASRModel:
         self._ck(lib().q3asr_debug_conv(self._h, xb.ctypes.data, wb.ctypes.data, bbias.ctypes.data, B, H, Wd, C, O, bw, bh, bb,
                                         int(bool(simt)), out.ctypes.data))
         return bf16_bits_to_f32(out)
+
+
+class Qwen3Tokenizer:
+    """Mirror of the reference's Qwen3Tokenizer (Sources/AudioCommon/Tokenizer.swift) over q3asr_tokenizer_*."""
+
+    def __init__(self, path=None, id_to_token=None, merges=()):
+        self._t = ctypes.c_void_p()
+        if path is not None:
+            rc = lib().q3asr_tokenizer_load(os.fsencode(path), ctypes.byref(self._t))
+            if rc != OK:
+                msg = lib().q3asr_tokenizer_last_error(self._t).decode("utf-8", "replace")
+                lib().q3asr_tokenizer_destroy(self._t)
+                self._t = ctypes.c_void_p()
+                raise Q3Error(rc, msg)
+        else:
+            items = sorted((id_to_token or {}).items())
+            ids = np.ascontiguousarray([k for k, _ in items], dtype=np.int32)
+            toks = (ctypes.c_char_p * len(items))(*[v.encode("utf-8") for _, v in items])
+            rc = lib().q3asr_tokenizer_from_pairs(ids.ctypes.data, ctypes.cast(toks, ctypes.c_void_p), len(items), ctypes.byref(self._t))
+            if rc != OK:
+                raise Q3Error(rc, "tokenizer_from_pairs failed")
+        for a, b in merges:
+            lib().q3asr_tokenizer_add_merge(self._t, a.encode("utf-8"), b.encode("utf-8"))
+
+    def close(self):
+        if self._t:
+            lib().q3asr_tokenizer_destroy(self._t)
+            self._t = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        lib().q3asr_tokenizer_size(self._t, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def decode(self, tokens):
+        ids = np.ascontiguousarray(tokens, dtype=np.int32)
+        need = ctypes.c_size_t()
+        lib().q3asr_tokenizer_decode(self._t, ids.ctypes.data, ids.size, None, 0, ctypes.byref(need))
+        buf = ctypes.create_string_buffer(need.value)
+        rc = lib().q3asr_tokenizer_decode(self._t, ids.ctypes.data, ids.size, buf, need.value, None)
+        if rc != OK:
+            raise Q3Error(rc, "tokenizer decode failed")
+        return buf.value.decode("utf-8")
+
+    def encode(self, text):
+        n = ctypes.c_int()
+        raw = text.encode("utf-8")
+        lib().q3asr_tokenizer_encode(self._t, raw, None, 0, ctypes.byref(n))
+        out = np.zeros(max(n.value, 1), dtype=np.int32)
+        rc = lib().q3asr_tokenizer_encode(self._t, raw, out.ctypes.data, out.size, ctypes.byref(n))
+        if rc != OK:
+            raise Q3Error(rc, "tokenizer encode failed")
+        return out[:n.value].tolist()
+
+    def token_id(self, token):
+        v = lib().q3asr_tokenizer_token_id(self._t, token.encode("utf-8"))
+        return None if v < 0 else v
 
 
 class Pool:
