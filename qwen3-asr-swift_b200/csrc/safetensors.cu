@@ -1,8 +1,8 @@
 // safetensors.cu — reads the checkpoint format the reference loads through MLX.loadArrays
 // (/root/reference/Sources/MLXCommon/WeightLoading.swift:9-11; key filtering in
 // /root/reference/Sources/Qwen3ASR/WeightLoading.swift:17-126): every *.safetensors file of a directory,
-// keys under audio_tower.* and model.*, dtypes F32 / F16 / BF16.  Quantised (U32-packed) tensors of the
-// MLX 4-/8-bit repos are rejected with a clear message (bf16 build; dequant-at-load is a later row).
+// keys under audio_tower.* and model.*, dtypes F32 / F16 / BF16, plus the U32-packed tensors of the MLX 4-/8-bit
+// repos (weight + scales + biases), which are dequantised to bf16 at load.
 //
 // File layout: u64 little-endian header length, JSON header {name: {dtype, shape, data_offsets:[a,b]}},
 // then the raw tensor bytes.
@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 
 #include "model.h"
 
@@ -115,6 +116,53 @@ std::vector<Entry> parse_header(const std::string& hdr) {
 
 }  // namespace
 
+namespace {
+
+struct Located {
+    Entry e;
+    int file = -1;
+    uint64_t base = 0;  // file offset of the data section
+};
+
+void read_entry(FILE* fp, const Located& l, std::vector<char>* buf) {
+    Q3_CHECK(l.e.end >= l.e.begin, Q3ASR_ERR_IO, "load_safetensors: bad entry " + l.e.name);
+    buf->resize(l.e.end - l.e.begin);
+    Q3_CHECK(fseek(fp, (long)(l.base + l.e.begin), SEEK_SET) == 0 && fread(buf->data(), 1, buf->size(), fp) == buf->size(), Q3ASR_ERR_IO,
+             "load_safetensors: truncated data for " + l.e.name);
+}
+
+float half_to_float(uint16_t hbits) {
+    const uint32_t sign = (uint32_t)(hbits & 0x8000) << 16;
+    uint32_t exp = (hbits >> 10) & 0x1F, man = hbits & 0x3FF, out;
+    if (exp == 0) {
+        if (man == 0) out = sign;
+        else {
+            exp = 127 - 15 + 1;
+            while (!(man & 0x400)) { man <<= 1; exp--; }
+            out = sign | (exp << 23) | ((man & 0x3FF) << 13);
+        }
+    } else if (exp == 31) out = sign | 0x7F800000u | (man << 13);
+    else out = sign | ((exp - 15 + 127) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &out, 4);
+    return f;
+}
+
+// element i of a scales / biases tensor as float
+float scalar_at(const std::vector<char>& buf, const std::string& dtype, size_t i) {
+    if (dtype == "F32") { float f; memcpy(&f, buf.data() + 4 * i, 4); return f; }
+    uint16_t u;
+    memcpy(&u, buf.data() + 2 * i, 2);
+    if (dtype == "BF16") { const uint32_t w = (uint32_t)u << 16; float f; memcpy(&f, &w, 4); return f; }
+    return half_to_float(u);
+}
+
+}  // namespace
+
+// MLX affine quantisation (mlx-swift `dequantized`, used through PreQuantizedEmbedding / QuantizedLinear,
+// /root/reference/Sources/MLXCommon/PreQuantizedEmbedding.swift:12-49, group size 64, Configuration.swift:61-63): a row of
+// `in` features is stored as in*bits/32 little-endian uint32 words (value j of a word at bits [j*bits, (j+1)*bits)) plus one
+// (scale, bias) pair per group of 64 features; w = scale * q + bias.  Dequantised at load: the B200 path computes in bf16.
 void model_load_safetensors(Handle* h, const char* dir) {
     Q3_CHECK(dir != nullptr, Q3ASR_ERR_INVALID, "load_safetensors: null directory");
     DIR* d = opendir(dir);
@@ -130,47 +178,91 @@ void model_load_safetensors(Handle* h, const char* dir) {
     Q3_CHECK(!files.empty(), Q3ASR_ERR_IO, std::string("load_safetensors: no .safetensors files in ") + dir);
     std::vector<std::pair<std::string, std::vector<int64_t>>> specs;
     model_tensor_specs(h->cfg, &specs);
-    size_t loaded = 0;
-    std::vector<char> buf;
-    for (const std::string& path : files) {
-        FILE* fp = fopen(path.c_str(), "rb");
-        Q3_CHECK(fp != nullptr, Q3ASR_ERR_IO, "load_safetensors: cannot open " + path);
-        try {
+
+    // pass 1: index every audio_tower.* / model.* entry of every file
+    std::map<std::string, Located> index;
+    std::vector<FILE*> fps(files.size(), nullptr);
+    auto close_all = [&]() {
+        for (FILE* f : fps)
+            if (f) fclose(f);
+    };
+    try {
+        for (size_t fi = 0; fi < files.size(); fi++) {
+            fps[fi] = fopen(files[fi].c_str(), "rb");
+            Q3_CHECK(fps[fi] != nullptr, Q3ASR_ERR_IO, "load_safetensors: cannot open " + files[fi]);
             uint64_t hl = 0;
-            Q3_CHECK(fread(&hl, 8, 1, fp) == 1 && hl > 1 && hl < (1ull << 30), Q3ASR_ERR_IO, "load_safetensors: bad header length in " + path);
+            Q3_CHECK(fread(&hl, 8, 1, fps[fi]) == 1 && hl > 1 && hl < (1ull << 30), Q3ASR_ERR_IO, "load_safetensors: bad header length in " + files[fi]);
             std::string hdr(hl, 0);
-            Q3_CHECK(fread(&hdr[0], 1, hl, fp) == hl, Q3ASR_ERR_IO, "load_safetensors: truncated header in " + path);
-            for (const Entry& e : parse_header(hdr)) {
-                const bool ours = e.name.compare(0, 12, "audio_tower.") == 0 || e.name.compare(0, 6, "model.") == 0;
-                if (!ours) continue;
-                bool known = false;
-                for (auto& s : specs)
-                    if (s.first == e.name) { known = true; break; }
-                if (!known) {
-                    Q3_CHECK(e.name.find(".scales") == std::string::npos && e.name.find(".biases") == std::string::npos, Q3ASR_ERR_INVALID,
-                             "load_safetensors: " + e.name + " belongs to a quantised MLX checkpoint; this build loads fp32/fp16/bf16 weights");
-                    continue;
-                }
-                int dt = e.dtype == "F32" ? 0 : e.dtype == "BF16" ? 1 : e.dtype == "F16" ? 2 : -1;
+            Q3_CHECK(fread(&hdr[0], 1, hl, fps[fi]) == hl, Q3ASR_ERR_IO, "load_safetensors: truncated header in " + files[fi]);
+            for (Entry& e : parse_header(hdr)) {
+                if (e.name.compare(0, 12, "audio_tower.") != 0 && e.name.compare(0, 6, "model.") != 0) continue;
+                Located l;
+                l.e = e;
+                l.file = (int)fi;
+                l.base = 8 + hl;
+                index[e.name] = l;
+            }
+        }
+        // pass 2: every tensor the model needs, dequantising MLX-packed ones
+        size_t loaded = 0;
+        std::vector<char> buf, sbuf, bbuf;
+        std::vector<float> deq;
+        for (auto& spec : specs) {
+            auto it = index.find(spec.first);
+            if (it == index.end()) continue;
+            const Located& l = it->second;
+            const Entry& e = l.e;
+            Q3_CHECK(!e.shape.empty() && e.shape.size() <= 4, Q3ASR_ERR_IO, "load_safetensors: bad entry " + e.name);
+            read_entry(fps[l.file], l, &buf);
+            size_t numel = 1;
+            for (int64_t v : e.shape) numel *= (size_t)v;
+            if (e.dtype == "U32") {
+                const std::string stem = e.name.substr(0, e.name.size() - 7);  // strip ".weight"
+                auto si = index.find(stem + ".scales"), bi = index.find(stem + ".biases");
+                Q3_CHECK(e.shape.size() == 2 && e.name.size() > 7 && si != index.end() && bi != index.end(), Q3ASR_ERR_INVALID,
+                         "load_safetensors: " + e.name + " is packed (U32) but its .scales / .biases are missing");
+                const Entry& se = si->second.e;
+                Q3_CHECK(se.shape.size() == 2 && se.shape[0] == e.shape[0] && bi->second.e.shape == se.shape && bi->second.e.dtype == se.dtype,
+                         Q3ASR_ERR_INVALID, "load_safetensors: scales / biases of " + e.name + " do not match it");
+                const int64_t rows = e.shape[0], words = e.shape[1], groups = se.shape[1], cols = groups * 64;
+                Q3_CHECK(buf.size() == numel * 4 && cols > 0 && (words * 32) % cols == 0, Q3ASR_ERR_IO, "load_safetensors: size mismatch for " + e.name);
+                const int bits = (int)(words * 32 / cols);
+                Q3_CHECK(bits == 2 || bits == 4 || bits == 8, Q3ASR_ERR_INVALID, "load_safetensors: unsupported quantisation width for " + e.name);
+                read_entry(fps[si->second.file], si->second, &sbuf);
+                read_entry(fps[bi->second.file], bi->second, &bbuf);
+                const size_t sb = se.dtype == "F32" ? 4 : 2;
+                Q3_CHECK(se.dtype == "F32" || se.dtype == "BF16" || se.dtype == "F16", Q3ASR_ERR_INVALID, "load_safetensors: unsupported scales dtype for " + e.name);
+                Q3_CHECK(sbuf.size() == (size_t)(rows * groups) * sb && bbuf.size() == sbuf.size(), Q3ASR_ERR_IO, "load_safetensors: scales size mismatch for " + e.name);
+                deq.resize((size_t)rows * cols);
+                const uint32_t mask = (1u << bits) - 1;
+                const int per = 32 / bits;
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(buf.data());
+                for (int64_t r = 0; r < rows; r++)
+                    for (int64_t g = 0; g < groups; g++) {
+                        const float sc = scalar_at(sbuf, se.dtype, (size_t)(r * groups + g)), bs = scalar_at(bbuf, se.dtype, (size_t)(r * groups + g));
+                        for (int c = 0; c < 64; c++) {
+                            const int64_t col = g * 64 + c;
+                            const uint32_t q = (w32[r * words + col / per] >> ((col % per) * bits)) & mask;
+                            deq[(size_t)(r * cols + col)] = (float)((double)sc * (double)q + (double)bs);  // exact product, one rounding
+                        }
+                    }
+                const int64_t shape[2] = {rows, cols};
+                model_set_tensor(h, e.name.c_str(), deq.data(), 0, shape, 2);
+            } else {
+                const int dt = e.dtype == "F32" ? 0 : e.dtype == "BF16" ? 1 : e.dtype == "F16" ? 2 : -1;
                 Q3_CHECK(dt >= 0, Q3ASR_ERR_INVALID, "load_safetensors: unsupported dtype " + e.dtype + " for " + e.name);
-                Q3_CHECK(e.end >= e.begin && !e.shape.empty() && e.shape.size() <= 4, Q3ASR_ERR_IO, "load_safetensors: bad entry " + e.name);
-                buf.resize(e.end - e.begin);
-                Q3_CHECK(fseek(fp, (long)(8 + hl + e.begin), SEEK_SET) == 0 && fread(buf.data(), 1, buf.size(), fp) == buf.size(), Q3ASR_ERR_IO,
-                         "load_safetensors: truncated data for " + e.name);
-                size_t numel = 1;
-                for (int64_t v : e.shape) numel *= (size_t)v;
                 Q3_CHECK(buf.size() == numel * (dt == 0 ? 4 : 2), Q3ASR_ERR_IO, "load_safetensors: size mismatch for " + e.name);
                 model_set_tensor(h, e.name.c_str(), buf.data(), dt, e.shape.data(), (int)e.shape.size());
-                loaded++;
             }
-        } catch (...) {
-            fclose(fp);
-            throw;
+            loaded++;
         }
-        fclose(fp);
+        Q3_CHECK(loaded == specs.size(), Q3ASR_ERR_IO,
+                 "load_safetensors: found " + std::to_string(loaded) + " of " + std::to_string(specs.size()) + " expected tensors in " + dir);
+    } catch (...) {
+        close_all();
+        throw;
     }
-    Q3_CHECK(loaded == specs.size(), Q3ASR_ERR_IO,
-             "load_safetensors: found " + std::to_string(loaded) + " of " + std::to_string(specs.size()) + " expected tensors in " + dir);
+    close_all();
     model_commit(h);
 }
 
