@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "model.h"
 
@@ -163,10 +164,10 @@ void plan_decoder(Handle* h, BatchState* bs, const q3asr_prompt* prompts, int ma
 
 void upload_ints(Handle* h, BatchState* bs, const std::vector<int>& ints) {
     bs->ints.reserve(ints.size() * sizeof(int) + 16);
-    bs->h_stage.reserve(ints.size() * sizeof(int) + 16);
-    memcpy(bs->h_stage.p, ints.data(), ints.size() * sizeof(int));
-    Q3_CUDA(cudaMemcpyAsync(bs->ints.p, bs->h_stage.p, ints.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    Q3_CUDA(cudaStreamSynchronize(h->stream));  // h_stage is reused by the next upload
+    bs->h_ints.reserve(ints.size() * sizeof(int) + 16);  // its own pinned buffer: sample copies from h_stage may still be in flight
+    memcpy(bs->h_ints.p, ints.data(), ints.size() * sizeof(int));
+    Q3_CUDA(cudaMemcpyAsync(bs->ints.p, bs->h_ints.p, ints.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));  // the staging buffers are reused by the next upload
 }
 
 void reserve_encoder(Handle* h, BatchState* bs) {
@@ -680,10 +681,27 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch
     bs->mel_tmin.reserve(sizeof(float) * bs->mel.total_tiles);
     bs->h_stage.reserve(sizeof(float) * bs->mel.pcm_floats);
     float* stage = bs->h_stage.as<float>();
-    for (int b = 0; b < batch; b++) memcpy(stage + bs->mel.clips[b].in_off, pcm[b], sizeof(float) * n[b]);
-    Q3_CUDA(cudaMemcpyAsync(bs->pcm.p, stage, sizeof(float) * bs->mel.pcm_floats, cudaMemcpyHostToDevice, h->stream));
+    // The caller's buffers are pageable: copy each clip into the pinned staging area and queue its H2D copy at once, from a
+    // few host threads, so the staging memcpy (the slow leg, ~10 GB/s per thread) overlaps the PCIe transfers and the planning
+    // below.  Clips are independent, so the order of the copies on the stream does not matter.
+    const int n_workers = std::max(1, std::min({batch, 6, (int)std::thread::hardware_concurrency() / 2}));
+    std::vector<std::thread> workers;
+    std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
+    for (int w = 0; w < n_workers; w++)
+        workers.emplace_back([&, w]() {
+            cudaError_t e = cudaSetDevice(h->device);
+            for (int b = w; b < batch && e == cudaSuccess; b += n_workers) {
+                const long long off = bs->mel.clips[b].in_off;
+                memcpy(stage + off, pcm[b], sizeof(float) * n[b]);
+                e = cudaMemcpyAsync(bs->pcm.as<float>() + off, stage + off, sizeof(float) * n[b], cudaMemcpyHostToDevice, h->stream);
+            }
+            werr[(size_t)w] = e;
+        });
+    struct Joiner {  // the threads borrow the caller's buffers: never leave without joining
+        std::vector<std::thread>& t;
+        ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
+    } joiner{workers};
     Q3_CUDA(cudaMemcpyAsync(bs->mel_clips.p, bs->mel.clips.data(), sizeof(MelClip) * batch, cudaMemcpyHostToDevice, h->stream));
-    Q3_CUDA(cudaStreamSynchronize(h->stream));
     // plan
     std::vector<int> frames(batch);
     std::vector<long long> mel_off(batch);
@@ -698,7 +716,9 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch
     // and let batch_run re-plan if a larger value is requested
     const int reserve_tokens = std::max(1, env_int("Q3ASR_RESERVE_TOKENS", 448));
     plan_decoder(h, bs, prompts, reserve_tokens, &ints);
-    upload_ints(h, bs, ints);
+    for (auto& t : workers) t.join();
+    for (cudaError_t e : werr) Q3_CUDA(e);
+    upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
     bs->prompt_ids.clear();
 }
 

@@ -83,7 +83,7 @@ struct BatchState {
     DevBuf amax_val, amax_idx, logits;
     // decode state (device)
     DevBuf st_next_tok, st_next_val, st_cur_tok, st_pos, st_kv_len, st_out_ids, st_out_val, st_out_len, st_finished, st_scalars, st_forced;
-    HostBuf h_stage, h_out;
+    HostBuf h_stage, h_ints, h_out;
     cudaGraphExec_t step_graph = nullptr;
     int graph_B = 0;
     cudaEvent_t ev[5] = {nullptr};
@@ -100,6 +100,7 @@ struct BatchState {
     ~BatchState() {
         for (DevBuf* b : all()) b->release();
         h_stage.release();
+        h_ints.release();
         h_out.release();
         if (step_graph) cudaGraphExecDestroy(step_graph);
         for (auto& e : ev)
