@@ -88,10 +88,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def clip_indices(rank, per_gpu=CLIPS_PER_GPU):
+    """Utterance sharding: rank r owns clips [r * per_gpu, (r + 1) * per_gpu) — disjoint, no data-path collective."""
+    return list(range(rank * per_gpu, (rank + 1) * per_gpu))
+
+
 def make_clips(rank):
     from oracle import synth  # input data generator shared with the tests (not oracle arithmetic)
     n = CLIP_SECONDS * 16000
-    return [synth.clip(rank * CLIPS_PER_GPU + i, n) for i in range(CLIPS_PER_GPU)]
+    return [synth.clip(i, n) for i in clip_indices(rank)]
+
+
+def max_over_ranks_cpu(x, world):
+    """The timing reduction of the N > 1 path on a CPU (gloo) group; bench.main uses the same all_reduce(MAX) on CUDA tensors."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def cpu_sample(seconds, tokens, clips=1, state_dict=None, threads=None):

@@ -1,0 +1,54 @@
+"""The utterance-batching scheduler (q3asr_pool_*, csrc/pool.cu) and the 1.7B configuration on a real GPU.  The pool is built
+over the devices that exist: with one GPU it runs two workers on device 0, which exercises the same threads, dealing and
+host-side gather as an 8-GPU box (the data path has no collective)."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _devices():
+    import torch
+    n = torch.cuda.device_count()
+    return tuple(range(n)) if n >= 2 else (0, 0)
+
+
+def test_pool_matches_single_handle_and_keeps_order(built_lib):
+    lens = [48000, 16000, 33333, 5000, 48000, 1600, 80000, 24000, 9000]
+    clips = [synth.clip(i, n) for i, n in enumerate(lens)]
+    single = built_lib.Qwen3ASRModel.random_init("tiny", seed=20260418)
+    pool = built_lib.Pool("tiny", devices=_devices(), seed=20260418)
+    try:
+        want = [single.transcribe_ids([c], max_tokens=12, stop_on_eos=False)[0].tolist() for c in clips]
+        got = pool.transcribe_ids(clips, max_tokens=12, stop_on_eos=False, max_batch_per_gpu=3)  # several sub-batches per worker
+        assert [g.tolist() for g in got] == want
+        again = pool.transcribe_ids(clips[::-1], max_tokens=12, stop_on_eos=False)
+        assert [g.tolist() for g in again[::-1]] == want
+        with pytest.raises(built_lib.Q3Error):
+            pool.transcribe_ids([np.zeros(10, np.float32)], max_tokens=4)  # shorter than one mel frame
+    finally:
+        pool.close()
+        single.close()
+
+
+def test_1p7b_configuration(built_lib, monkeypatch):
+    """Qwen3-ASR-1.7B dimensions (encoder d 1024 / 24 layers, decoder hidden 2048): batch invariance, fixed length, and the two
+    decode schedules (weight-streaming split-K path vs one kernel per op) agree."""
+    m = built_lib.Qwen3ASRModel.random_init("1.7B", seed=3)
+    try:
+        clips = [synth.clip(i, 240000) for i in range(3)]  # 15 s utterances (BASELINE config 4)
+        a = m.transcribe_ids(clips, max_tokens=10, stop_on_eos=False)
+        assert all(len(t) == 10 for t in a)
+        one = m.transcribe_ids([clips[2]], max_tokens=10, stop_on_eos=False)[0]
+        assert one.tolist() == a[2].tolist()
+        forced = np.arange(100, 108, dtype=np.int32)
+        f_ids, f_top = m.decode_forced(clips[0], forced)
+        monkeypatch.setenv("Q3ASR_NO_SKINNY", "1")
+        p_ids, p_top = m.decode_forced(clips[0], forced)
+        monkeypatch.delenv("Q3ASR_NO_SKINNY")
+        assert np.abs(f_top - p_top).max() <= 4 * np.abs(p_top).max() * 2.0 ** -8
+        assert m.memory_footprint > 4e9
+    finally:
+        m.close()
