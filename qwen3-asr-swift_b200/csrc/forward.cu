@@ -475,7 +475,10 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
             // M = B <= 128 fits one M tile of the general kernel; 64-column tiles give N/64 CTAs, each streaming its weight rows once
             GemmEpiArgs eg;
             eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
-            if (!(skip & 16)) gemm(xn, H, B, H, w.gu_w, 2 * c.dec_inter, eg, st, false, 64);
+            // narrowest 64-multiple tile that still gives one CTA per SM at most (0.6B: 96 tiles of 64, 1.7B: 96 tiles of 128)
+            int gu_bn = 64;
+            while ((2 * c.dec_inter) / gu_bn > h->num_sms && gu_bn < 256 && (2 * c.dec_inter) % (2 * gu_bn) == 0) gu_bn *= 2;
+            if (!(skip & 16)) gemm(xn, H, B, H, w.gu_w, 2 * c.dec_inter, eg, st, false, gu_bn);
         }
         {
             ProfScope ps(h, "dec_down", 2.0 * B * H * c.dec_inter, 2.0 * H * c.dec_inter);
