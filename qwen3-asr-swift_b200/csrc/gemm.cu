@@ -36,22 +36,24 @@ void make_tmap(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 }
 
 template <int BN, int EPI>
-void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, GemmDev p, int max_stages, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
         attr_set = true;
     }
-    launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, gemm_smem_bytes(BN), st, ta, tb, p);
+    p.stages = max_stages > 0 ? std::min(max_stages, gemm_stages(BN)) : gemm_stages(BN);
+    const int smem = p.stages * gemm_stage_bytes(BN) + 1024 + 256;
+    launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, smem, st, ta, tb, p);
 }
 
 template <int BN>
-void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int ms, int grid, cudaStream_t st) {
     switch (epi) {
-        case EPI_NORMAL: launch_tc<BN, EPI_NORMAL>(ta, tb, p, grid, st); break;
-        case EPI_SWIGLU: launch_tc<BN, EPI_SWIGLU>(ta, tb, p, grid, st); break;
-        case EPI_F32: launch_tc<BN, EPI_F32>(ta, tb, p, grid, st); break;
-        case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, p, grid, st); break;
+        case EPI_NORMAL: launch_tc<BN, EPI_NORMAL>(ta, tb, p, ms, grid, st); break;
+        case EPI_SWIGLU: launch_tc<BN, EPI_SWIGLU>(ta, tb, p, ms, grid, st); break;
+        case EPI_F32: launch_tc<BN, EPI_F32>(ta, tb, p, ms, grid, st); break;
+        case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, p, ms, grid, st); break;
         default: throw Error(1, "gemm: bad epilogue");
     }
 }
@@ -286,12 +288,12 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     const long tiles = m_tiles * p.tiles_n;
     const int grid = (int)std::min<long>(tiles, g_num_sms);
     switch (bn) {
-        case 32: launch_bn<32>(e.epi, ta, tb, p, grid, st); break;
-        case 64: launch_bn<64>(e.epi, ta, tb, p, grid, st); break;
-        case 128: launch_bn<128>(e.epi, ta, tb, p, grid, st); break;
-        case 160: launch_bn<160>(e.epi, ta, tb, p, grid, st); break;
-        case 224: launch_bn<224>(e.epi, ta, tb, p, grid, st); break;
-        case 256: launch_bn<256>(e.epi, ta, tb, p, grid, st); break;
+        case 32: launch_bn<32>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 64: launch_bn<64>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 128: launch_bn<128>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 160: launch_bn<160>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 224: launch_bn<224>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 256: launch_bn<256>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
         default: throw Error(1, "gemm: unsupported tile width " + std::to_string(bn));
     }
     Q3_CUDA(cudaGetLastError());

@@ -57,6 +57,7 @@ struct GemmDev {  // by-value kernel parameter
     const int* row_map;    // [rows] destination row or -1, or null (identity)
     const int* valid_w;    // [OB] columns w >= valid_w[b] are stored as zero, or null
     int gelu;
+    int stages;            // smem ring depth actually used (<= gemm_stages(BN))
     float* amax_val;       // [rows, tiles_n]
     int* amax_idx;
 };
@@ -92,7 +93,8 @@ __device__ __forceinline__ TileCoord gemm_tile_coord(const GemmDev& p, int tile)
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-    constexpr int STAGES = gemm_stages(BN);
+    constexpr int MAX_STAGES = gemm_stages(BN);
+    const int STAGES = p.stages;  // <= MAX_STAGES; the decode step asks for a shallow ring so the next kernel's CTAs fit beside this one
     constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
     constexpr int ACC_STRIDE = gemm_acc_stride(BN);
     constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -103,8 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2]
     uint64_t* tempty_bar = tfull_bar + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -396,6 +398,7 @@ struct GemmEpiArgs {
     const int* row_map = nullptr;
     const int* valid_w = nullptr;
     int gelu = 0;
+    int max_stages = 0;  // 0: as deep as shared memory allows
     float* amax_val = nullptr;
     int* amax_idx = nullptr;
 };

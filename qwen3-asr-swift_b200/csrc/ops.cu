@@ -634,51 +634,71 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
 
     ptx::grid_dep_wait();
 
-    // ---- 1. new-token q / k / v (slots 0,1 = q heads, 2 = k, 3 = v) ----
-    for (int slot = warp; slot < GROUP + 2; slot += NW) {
-        const int d0 = lane * 4;
+    // ---- 1. new-token q / k / v (slots 0,1 = q heads, 2 = k, 3 = v): one half-warp per slot, 8 dims per lane, so all four
+    //         are done in one pass by the first two warps (the other warps keep their prefetches in flight) ----
+    if (threadIdx.x < 16 * (GROUP + 2)) {
+        const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
+        const unsigned half_mask = 0xffffu << (threadIdx.x & 16);  // the two halves of a warp hold different slots and diverge (v skips the norm)
+        const int d0 = hl * 8;
         const int col = slot < GROUP ? (kvh * GROUP + slot) * 128
                                      : slot == GROUP ? heads * 128 + kvh * 128 : (heads + cache.kv_heads) * 128 + kvh * 128;
         const float* src = qkv_part + (size_t)seq * nqkv + col + d0;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < splits; s0 += 4) {  // fixed summation order, four loads in flight
-            float4 b[4];
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s0 = 0; s0 < splits; s0 += 4) {  // fixed summation order, eight loads in flight
+            float4 b[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                b[i] = s0 + i < splits ? *reinterpret_cast<const float4*>(src + (size_t)(s0 + i) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; i++) {
+                const bool on = s0 + i < splits;
+                const float4* sp = reinterpret_cast<const float4*>(src + (size_t)(s0 + i) * split_stride);
+                b[i][0] = on ? sp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[i][1] = on ? sp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
+            for (int i = 0; i < 4; i++) {
+                x[0] += b[i][0].x; x[1] += b[i][0].y; x[2] += b[i][0].z; x[3] += b[i][0].w;
+                x[4] += b[i][1].x; x[5] += b[i][1].y; x[6] += b[i][1].z; x[7] += b[i][1].w;
+            }
         }
-        float x[4] = {bf16_round(a.x), bf16_round(a.y), bf16_round(a.z), bf16_round(a.w)};
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = bf16_round(x[j]);
         const int p = pos[seq];
         if (slot <= GROUP) {
-            float q = fmaf(x[0], x[0], fmaf(x[1], x[1], fmaf(x[2], x[2], x[3] * x[3])));
-            const float r = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
-            const uint2 wu = ld8((slot < GROUP ? qw : kw) + d0);
-            const float2 w0 = unpack_bf16x2(wu.x), w1 = unpack_bf16x2(wu.y);
-            x[0] = bf16_round(x[0] * r * w0.x);
-            x[1] = bf16_round(x[1] * r * w0.y);
-            x[2] = bf16_round(x[2] * r * w1.x);
-            x[3] = bf16_round(x[3] * r * w1.y);
-            float y[4];
+            float q = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; j++) y[j] = __shfl_xor_sync(0xffffffffu, x[j], 16);
-            const int i0 = d0 & 63;
-            const float sgn = lane < 16 ? -1.f : 1.f;
-            const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + i0);
-            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-            const float cs[4] = {t0.x, t0.z, t1.x, t1.z}, sn[4] = {t0.y, t0.w, t1.y, t1.w};
+            for (int j = 0; j < 8; j++) q = fmaf(x[j], x[j], q);
 #pragma unroll
-            for (int j = 0; j < 4; j++) x[j] = fmaf(x[j], cs[j], sgn * y[j] * sn[j]);  // rounded to bf16 by the stores below
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(half_mask, q, o);  // stays inside the half-warp
+            const float r = rsqrtf(q * (1.0f / 128.0f) + eps);
+            const uint4 wu = *reinterpret_cast<const uint4*>((slot < GROUP ? qw : kw) + d0);
+            const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 wf = unpack_bf16x2(ww[j]);
+                x[2 * j] = bf16_round(x[2 * j] * r * wf.x);
+                x[2 * j + 1] = bf16_round(x[2 * j + 1] * r * wf.y);
+            }
+            // split-half rotation: dims (i, i+64); the partner values live 8 lanes away
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) y[j] = __shfl_xor_sync(half_mask, x[j], 8);
+            const float sgn = hl < 8 ? -1.f : 1.f;
+            const float4* tp = reinterpret_cast<const float4*>(rope_tab + (size_t)p * 64 + (d0 & 63));  // (cos, sin) pairs
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 t = __ldg(tp + j);
+                x[2 * j] = fmaf(x[2 * j], t.x, sgn * y[2 * j] * t.y);
+                x[2 * j + 1] = fmaf(x[2 * j + 1], t.z, sgn * y[2 * j + 1] * t.w);
+            }
         }
+        const uint4 packed = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
         if (slot < GROUP) {
-            st8(&s_qb[slot][d0], x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<uint4*>(&s_qb[slot][d0]) = packed;
         } else {
             const int page = pt[p / KV_PAGE];
             bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (slot == GROUP ? 0 : 1)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
                         (p % KV_PAGE) * 128 + d0;
-            st8(dst, x[0], x[1], x[2], x[3]);
-            st8(&s_new[slot - GROUP][d0], x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<uint4*>(dst) = packed;
+            *reinterpret_cast<uint4*>(&s_new[slot - GROUP][d0]) = packed;
         }
     }
     __syncthreads();  // s_qb and s_new ready

@@ -4,11 +4,11 @@ mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 for t in "$@"; do
   name=$(basename "$t" .py)
-  timeout 300 python -m pytest "$t" -q -m gpu -x --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
+  timeout 240 python -m pytest "$t" -q -m gpu -x --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
   echo "$name exit $?" | tee -a gpurun_out/summary.txt
   tail -n 12 "gpurun_out/${name}.log"
 done
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+timeout 240 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 tail -c 1500 gpurun_out/bench.err
 python - <<'PY'
 import json
