@@ -6,6 +6,7 @@
 #include <atomic>
 #include <vector>
 
+#include "gemm2.cuh"
 #include "skinny.cuh"
 
 namespace q3 {
@@ -56,6 +57,21 @@ void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
         case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, p, ms, grid, st); break;
         default: throw Error(1, "gemm: bad epilogue");
     }
+}
+
+template <int BN, int EPI>
+void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        Q3_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(BN)));
+        attr_set = true;
+    }
+    launch_kernel(gemm_tc2_kernel<BN, EPI>, grid, GEMM_THREADS, gemm2_smem_bytes(BN), st, ta, tb, p);
+}
+template <int BN>
+void launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+    if (epi == EPI_SWIGLU) launch_tc2<BN, EPI_SWIGLU>(ta, tb, p, grid, st);
+    else launch_tc2<BN, EPI_NORMAL>(ta, tb, p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -277,13 +293,34 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
         cuuint32_t es[4] = {1, (cuuint32_t)s.sw, (cuuint32_t)s.sh, 1};
         make_tmap(&ta, a.ptr, 4, dims, str, box, es);
     }
+    // CTA pairs (gemm2.cuh) for the big dense products: each CTA stages half of the weight tile
+    const char* env2 = getenv("Q3ASR_2CTA");  // "0" never, "1" whenever the tile shape allows (tests), unset: large problems only
+    const int mode2 = env2 && *env2 ? atoi(env2) : -1;
+    // measured (profiles/): pairing lifts the plain products (q/k/v, o, down, fc2, conv_out: +9..19 %, 1.2-1.3 PFLOP/s) to the cuBLAS
+    // ceiling; GELU / SwiGLU tiles are bound by their epilogues and the stride-2 convolutions by their TMA boxes, where it does not pay
+    const bool plain = e.epi == EPI_NORMAL && !e.gelu && s.sw == 1 && s.sh == 1;
+    const bool pair = mode2 != 0 && !simt && (e.epi == EPI_NORMAL || e.epi == EPI_SWIGLU) && (bn == 128 || bn == 160 || bn == 224 || bn == 256) &&
+                      (mode2 == 1 || (plain && m_tiles * p.tiles_n >= 4L * g_num_sms)) && (e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0);
     {
         const long K = (long)s.taps * a.C;
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
-        cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)bn};
+        cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)(pair ? bn / 2 : bn)};
         cuuint32_t es[2] = {1, 1};
         make_tmap(&tb, W, 2, dims, str, box, es);
+    }
+    if (pair) {
+        const long super = ((m_tiles + 1) / 2) * p.tiles_n;
+        const int grid2 = 2 * (int)std::min<long>(super, g_num_sms / 2);
+        switch (bn) {
+            case 128: launch_bn2<128>(e.epi, ta, tb, p, grid2, st); break;
+            case 160: launch_bn2<160>(e.epi, ta, tb, p, grid2, st); break;
+            case 224: launch_bn2<224>(e.epi, ta, tb, p, grid2, st); break;
+            default: launch_bn2<256>(e.epi, ta, tb, p, grid2, st); break;
+        }
+        Q3_CUDA(cudaGetLastError());
+        g_launches++;
+        return;
     }
     const long tiles = m_tiles * p.tiles_n;
     const int grid = (int)std::min<long>(tiles, g_num_sms);

@@ -90,6 +90,150 @@ __device__ __forceinline__ TileCoord gemm_tile_coord(const GemmDev& p, int tile)
     return t;
 }
 
+// One tile's epilogue for one thread: TMEM row -> registers -> bias / PE / GELU / residual / SwiGLU / argmax -> global.
+// `tfull` is the barrier the accumulator's completion is committed to (waited on here, after the index arithmetic).
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileCoord tc, uint32_t tmem_acc, uint64_t* tfull, uint32_t aphase,
+                                                   int q, int lane, int chalf, int tile_rows) {
+    const int n0 = tc.tn * BN;
+    const int r = q * 32 + lane;
+    const int w = tc.w0 + r % p.Wb;
+    const int h = tc.h0 + (r / p.Wb) % p.Hb;
+    const int b = tc.b0 + r / (p.Wb * p.Hb);
+    bool row_ok = r < tile_rows && w < p.OW && h < p.OH && b < p.OB;
+    long row = row_ok ? ((long)b * p.OH + h) * p.OW + w : 0;
+    bool zero = false;
+    if (row_ok && p.valid_w != nullptr) zero = w >= __ldg(p.valid_w + b);
+    if (row_ok && p.row_map != nullptr) {
+        row = __ldg(p.row_map + row);
+        row_ok = row >= 0;
+    }
+    ptx::mbar_wait(tfull, aphase);
+    ptx::tc_fence_after();
+    const uint32_t t_row = tmem_acc + (uint32_t(q * 32) << 16);
+
+    if constexpr (EPI == EPI_SWIGLU) {
+        // weight rows alternate GU_UNIT gate rows / GU_UNIT up rows, so every 64 accumulator columns hold 32 outputs
+        if constexpr (BN % (2 * GU_UNIT) == 0) {
+            bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * (BN / 2);
+#pragma unroll 1
+            for (int c = chalf; c < BN / 32; c += 2) {  // 16 outputs per step
+                const int col = (c >> 1) * (2 * GU_UNIT) + (c & 1) * 16;
+                uint32_t g[16], u[16];
+                ptx::tmem_ld_32x16(t_row + col, g);
+                ptx::tmem_ld_32x16(t_row + col + GU_UNIT, u);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float a = epi_swiglu(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
+                        const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
+                        pk[j] = pack_bf16x2(a, bb);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        }
+    } else if constexpr (EPI == EPI_ARGMAX) {
+        float best = -INFINITY;
+        int best_i = 0;
+#pragma unroll 1
+        for (int c = 0; c < (chalf == 0 ? BN / 32 : 0); c++) {  // one warp per quadrant scans the whole row (weight-streaming bound)
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_row + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float x = bf16_round(__uint_as_float(v[j]));
+                if (x > best) { best = x; best_i = n0 + c * 32 + j; }
+            }
+        }
+        if (row_ok && chalf == 0) {
+            p.amax_val[(size_t)row * p.tiles_n + tc.tn] = best;
+            p.amax_idx[(size_t)row * p.tiles_n + tc.tn] = best_i;
+        }
+    } else {
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+            const int col = n0 + c * 32;
+            // bias and residual do not depend on the accumulator: fetch them under the TMEM load's latency
+            uint4 bvv[4], rvv[4];
+            if (EPI == EPI_NORMAL || EPI == EPI_F32) {
+                if (row_ok && p.bias != nullptr) {
+                    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) bvv[j] = __ldg(bp + j);
+                }
+                if (EPI == EPI_NORMAL && row_ok && p.resid != nullptr) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) rvv[j] = __ldg(rp + j);
+                }
+            }
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_row + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 bv = bvv[j];
+                        float2 t;
+                        t = unpack_bf16x2(bv.x); f[8 * j + 0] += t.x; f[8 * j + 1] += t.y;
+                        t = unpack_bf16x2(bv.y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
+                        t = unpack_bf16x2(bv.z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
+                        t = unpack_bf16x2(bv.w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
+                    }
+                }
+                if constexpr (EPI == EPI_F32) {
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    if (p.row_add != nullptr) {
+                        const float4* ap = reinterpret_cast<const float4*>(p.row_add + (size_t)w * p.N + col);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float4 a = __ldg(ap + j);
+                            f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
+                        }
+                    }
+                    if (p.gelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = gelu_erf(f[j]);
+                    }
+                    if (zero) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = 0.f;
+                    }
+                    if (p.resid != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 rv = rvv[j];
+                            float2 t;
+                            t = unpack_bf16x2(rv.x); f[8 * j + 0] = t.x + bf16_round(f[8 * j + 0]); f[8 * j + 1] = t.y + bf16_round(f[8 * j + 1]);
+                            t = unpack_bf16x2(rv.y); f[8 * j + 2] = t.x + bf16_round(f[8 * j + 2]); f[8 * j + 3] = t.y + bf16_round(f[8 * j + 3]);
+                            t = unpack_bf16x2(rv.z); f[8 * j + 4] = t.x + bf16_round(f[8 * j + 4]); f[8 * j + 5] = t.y + bf16_round(f[8 * j + 5]);
+                            t = unpack_bf16x2(rv.w); f[8 * j + 6] = t.x + bf16_round(f[8 * j + 6]); f[8 * j + 7] = t.y + bf16_round(f[8 * j + 7]);
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                }
+            }
+        }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -221,144 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const TileCoord tc = gemm_tile_coord(p, tile);
-            const int n0 = tc.tn * BN;
-            const int r = q * 32 + lane;
-            const int w = tc.w0 + r % p.Wb;
-            const int h = tc.h0 + (r / p.Wb) % p.Hb;
-            const int b = tc.b0 + r / (p.Wb * p.Hb);
-            bool row_ok = r < tile_rows && w < p.OW && h < p.OH && b < p.OB;
-            long row = row_ok ? ((long)b * p.OH + h) * p.OW + w : 0;
-            bool zero = false;
-            if (row_ok && p.valid_w != nullptr) zero = w >= __ldg(p.valid_w + b);
-            if (row_ok && p.row_map != nullptr) {
-                row = __ldg(p.row_map + row);
-                row_ok = row >= 0;
-            }
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
-
-            if constexpr (EPI == EPI_SWIGLU) {
-                // weight rows alternate GU_UNIT gate rows / GU_UNIT up rows, so every 64 accumulator columns hold 32 outputs
-                if constexpr (BN % (2 * GU_UNIT) == 0) {
-                    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * (BN / 2);
-#pragma unroll 1
-                    for (int c = chalf; c < BN / 32; c += 2) {  // 16 outputs per step
-                        const int col = (c >> 1) * (2 * GU_UNIT) + (c & 1) * 16;
-                        uint32_t g[16], u[16];
-                        ptx::tmem_ld_32x16(t_row + col, g);
-                        ptx::tmem_ld_32x16(t_row + col + GU_UNIT, u);
-                        ptx::tmem_ld_wait();
-                        if (row_ok) {
-                            uint32_t pk[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const float a = epi_swiglu(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
-                                const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
-                                pk[j] = pack_bf16x2(a, bb);
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
-                            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                        }
-                    }
-                }
-            } else if constexpr (EPI == EPI_ARGMAX) {
-                float best = -INFINITY;
-                int best_i = 0;
-#pragma unroll 1
-                for (int c = 0; c < (chalf == 0 ? BN / 32 : 0); c++) {  // one warp per quadrant scans the whole row (weight-streaming bound)
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_row + c * 32, v);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float x = bf16_round(__uint_as_float(v[j]));
-                        if (x > best) { best = x; best_i = n0 + c * 32 + j; }
-                    }
-                }
-                if (row_ok && chalf == 0) {
-                    p.amax_val[(size_t)row * p.tiles_n + tc.tn] = best;
-                    p.amax_idx[(size_t)row * p.tiles_n + tc.tn] = best_i;
-                }
-            } else {
-#pragma unroll 1
-                for (int c = chalf; c < BN / 32; c += 2) {
-                    const int col = n0 + c * 32;
-                    // bias and residual do not depend on the accumulator: fetch them under the TMEM load's latency
-                    uint4 bvv[4], rvv[4];
-                    if (EPI == EPI_NORMAL || EPI == EPI_F32) {
-                        if (row_ok && p.bias != nullptr) {
-                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) bvv[j] = __ldg(bp + j);
-                        }
-                        if (EPI == EPI_NORMAL && row_ok && p.resid != nullptr) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) rvv[j] = __ldg(rp + j);
-                        }
-                    }
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_row + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    if (row_ok) {
-                        float f[32];
-#pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-                        if (p.bias != nullptr) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const uint4 bv = bvv[j];
-                                float2 t;
-                                t = unpack_bf16x2(bv.x); f[8 * j + 0] += t.x; f[8 * j + 1] += t.y;
-                                t = unpack_bf16x2(bv.y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
-                                t = unpack_bf16x2(bv.z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
-                                t = unpack_bf16x2(bv.w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
-                            }
-                        }
-                        if constexpr (EPI == EPI_F32) {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col);
-#pragma unroll
-                            for (int j = 0; j < 8; j++) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        } else {
-                            if (p.row_add != nullptr) {
-                                const float4* ap = reinterpret_cast<const float4*>(p.row_add + (size_t)w * p.N + col);
-#pragma unroll
-                                for (int j = 0; j < 8; j++) {
-                                    const float4 a = __ldg(ap + j);
-                                    f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
-                                }
-                            }
-                            if (p.gelu) {
-#pragma unroll
-                                for (int j = 0; j < 32; j++) f[j] = gelu_erf(f[j]);
-                            }
-                            if (zero) {
-#pragma unroll
-                                for (int j = 0; j < 32; j++) f[j] = 0.f;
-                            }
-                            if (p.resid != nullptr) {
-#pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const uint4 rv = rvv[j];
-                                    float2 t;
-                                    t = unpack_bf16x2(rv.x); f[8 * j + 0] = t.x + bf16_round(f[8 * j + 0]); f[8 * j + 1] = t.y + bf16_round(f[8 * j + 1]);
-                                    t = unpack_bf16x2(rv.y); f[8 * j + 2] = t.x + bf16_round(f[8 * j + 2]); f[8 * j + 3] = t.y + bf16_round(f[8 * j + 3]);
-                                    t = unpack_bf16x2(rv.z); f[8 * j + 4] = t.x + bf16_round(f[8 * j + 4]); f[8 * j + 5] = t.y + bf16_round(f[8 * j + 5]);
-                                    t = unpack_bf16x2(rv.w); f[8 * j + 6] = t.x + bf16_round(f[8 * j + 6]); f[8 * j + 7] = t.y + bf16_round(f[8 * j + 7]);
-                                }
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col);
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_tile<BN, EPI>(p, gemm_tile_coord(p, tile), tmem_base + as * ACC_STRIDE, &tfull_bar[as], aphase, q, lane, chalf, tile_rows);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }

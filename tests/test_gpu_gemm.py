@@ -159,3 +159,38 @@ def test_skinny_partial_and_store(tiny_model, M, N, K):
     assert got.shape == (M, N)
     assert np.allclose(got, ref, rtol=2e-5, atol=2e-4), np.abs(got - ref).max()
     _close_bf16(tiny_model.debug_gemm(A, W, epi=5), ref, f"skinny store {M}x{N}x{K}")
+
+
+# ---- CTA-pair (cta_group::2) variant, csrc/gemm2.cuh: forced on for small shapes, incl. an odd number of M tiles ----
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 128, 256), (300, 512, 320, 256), (1000, 896, 896, 224), (130, 480, 192, 160),
+                                      (640, 384, 1024, 128), (77, 256, 64, 128)])
+def test_gemm_cta_pair(tiny_model, monkeypatch, M, N, K, bn):
+    monkeypatch.setenv("Q3ASR_2CTA", "1")
+    rng = np.random.default_rng(M + N + K)
+    A, W, b, R = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05), _rand(rng, (N,)), _rand(rng, (M, N))
+    acc = A.astype(np.float64) @ W.astype(np.float64).T + b
+    _close_bf16(tiny_model.debug_gemm(A, W, bias=b, bn=bn), acc, f"pair store {M}x{N}x{K} bn={bn}")
+    _close_bf16(tiny_model.debug_gemm(A, W, bias=b, gelu=True, bn=bn), _gelu(acc), "pair gelu")
+    got = tiny_model.debug_gemm(A, W, bias=b, resid=R, bn=bn)
+    ref = R + bf16_round(acc.astype(np.float32))
+    # two roundings (the product, then the sum), each up to one bf16 ulp (2^-8 relative at worst) of the larger magnitude
+    tol = 2.5 * np.maximum(np.maximum(np.abs(ref), np.abs(acc)), 1e-2) * 2.0 ** -8
+    assert (np.abs(got - ref) <= tol).all()
+    # same arithmetic as the single-CTA kernel: bit-identical outputs
+    pair_out = tiny_model.debug_gemm(A, W, bias=b, resid=R, gelu=True, bn=bn)
+    monkeypatch.setenv("Q3ASR_2CTA", "0")
+    assert np.array_equal(pair_out, tiny_model.debug_gemm(A, W, bias=b, resid=R, gelu=True, bn=bn))
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_cta_pair_swiglu_and_conv(tiny_model, monkeypatch, bn):
+    monkeypatch.setenv("Q3ASR_2CTA", "1")
+    rng = np.random.default_rng(bn)
+    M, I, K = 300, 512, 192
+    A, G, U = _rand(rng, (M, K)), _rand(rng, (I, K), 0.1), _rand(rng, (I, K), 0.1)
+    g = bf16_round((A.astype(np.float64) @ G.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    u = bf16_round((A.astype(np.float64) @ U.astype(np.float64).T).astype(np.float32)).astype(np.float64)
+    sg = bf16_round((g / (1.0 + np.exp(-g))).astype(np.float32)).astype(np.float64)
+    _close_bf16(tiny_model.debug_gemm(A, _interleave_gate_up(G, U), epi=1, bn=bn), sg * u, f"pair swiglu bn={bn}", ulps=3)
+    x, w, b = _rand(rng, (11, 32, 25, 480)), _rand(rng, (160, 3, 3, 480), 0.05), _rand(rng, (160,))
+    _close_bf16(tiny_model.debug_conv(x, w, b, box=(13, 1, 9)), _conv_ref(x, w, b), "pair conv", ulps=2)
