@@ -186,6 +186,32 @@ int q3asr_tokenizer_encode(const q3asr_tokenizer* t, const char* text, int32_t* 
 /* id of a token string, or -1 (Tokenizer.swift:281-283) */
 int q3asr_tokenizer_token_id(const q3asr_tokenizer* t, const char* token);
 
+/* ---- front door of the batched path: WAV, sample-rate conversion, long-form windows ---- */
+/* message of the last failed q3asr_wav_* / q3asr_resample_design / q3asr_longform_plan call on this thread */
+const char* q3asr_io_last_error(void);
+/* AudioFileLoader.loadWAV (Sources/AudioCommon/AudioFileLoader.swift:70-157): RIFF/WAVE, PCM, 16-bit, any channel count (first
+ * channel kept), samples / 32768.  Same rejections, in the same order, as the reference ("Invalid WAV file format",
+ * "Unsupported audio format: Not PCM format" / "Not 16-bit").  samples may be NULL to query *n_samples (frames). */
+int q3asr_wav_parse(const uint8_t* data, size_t size, float* samples, size_t cap, size_t* n_samples, int* sample_rate);
+int q3asr_wav_load(const char* path, float* samples, size_t cap, size_t* n_samples, int* sample_rate);
+/* AudioFileLoader.resample (AudioFileLoader.swift:159-213).  Output length floor(n * out / in) as the reference computes it
+ * (:190-191); the filter is a polyphase Kaiser-windowed sinc (csrc/audio_io.cu states the design; AVAudioConverter's own filter is
+ * not part of the reference), evaluated on the GPU.  out may be NULL to query *n_out. */
+size_t q3asr_resample_len(size_t n_samples, int in_rate, int out_rate);
+int q3asr_resample(q3asr_handle* h, const float* in, size_t n_samples, int in_rate, int out_rate, float* out, size_t cap, size_t* n_out);
+/* the filter bank itself (host only; parity tests): L = out/g, M = in/g, K, taps [L][2K+2] */
+int q3asr_resample_design(int in_rate, int out_rate, int* L, int* M, int* K, float* taps, size_t cap, size_t* n_taps);
+/* Qwen3ASRModel.transcribe(audio:sampleRate:...) resamples to 16 kHz first (AudioPreprocessing.swift:323-337; the reference's
+ * batch command feeds 24 kHz, TranscribeBatchCommand.swift:73, 92): sample_rates[i] != 16000 clips are converted on the device,
+ * straight into the packed sample buffer.  sample_rates may be NULL (all 16 kHz). */
+int q3asr_batch_upload_sr(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                          const q3asr_prompt* prompts);
+int q3asr_transcribe_ids_sr(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                            const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out);
+/* Long-form audio (BASELINE config 5): windows [k*window, min((k+1)*window, n)), each an independent utterance for the scheduler;
+ * a tail shorter than min_tail samples joins the previous window.  starts/lens may be NULL (or cap too small) to query *count. */
+int q3asr_longform_plan(size_t n_samples, size_t window, size_t min_tail, size_t* starts, size_t* lens, int cap, int* count);
+
 /* ---- debug / test hooks (exercise single kernels through the C ABI) ---- */
 /* C[M,N] = A[M,K] W[N,K]^T with bf16 (uint16) host operands; epi: 0 store(+bias,+gelu), 1 swiglu (W rows alternate
  * 32 gate / 32 up rows), 2 fp32, 3 argmax.

@@ -145,7 +145,9 @@ void q3asr_destroy(q3asr_handle* hh) {
         if (h.stream) cudaStreamSynchronize(h.stream);
         model_unload(&h);
         if (h.mel_ready) mel_tables_destroy(&h.mel_tables);
-        for (DevBuf* b : {&h.mel_pcm, &h.mel_out, &h.mel_clips, &h.mel_gmax, &h.mel_tmin, &h.flush_buf}) b->release();
+        for (DevBuf* b : {&h.mel_pcm, &h.mel_out, &h.mel_clips, &h.mel_gmax, &h.mel_tmin, &h.flush_buf, &h.rs_in, &h.rs_out}) b->release();
+        for (auto& kv : h.resample_tabs) kv.second.taps.release();
+        h.rs_stage.release();
         h.mel_stage.release();
         for (int i = 0; i < 16; i++)
             if (h.timer[i]) cudaEventDestroy(h.timer[i]);
@@ -258,6 +260,22 @@ int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t*
         batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
         batch_download(&x, ids_out, max_tokens, lens_out);
     });
+}
+int q3asr_batch_upload_sr(q3asr_handle* h, const float* const* pcm, const size_t* n, const int* sample_rates, int batch,
+                          const q3asr_prompt* prompts) {
+    return guarded(h, [&](Handle& x) { batch_upload(&x, pcm, n, batch, prompts, sample_rates); });
+}
+int q3asr_transcribe_ids_sr(q3asr_handle* h, const float* const* pcm, const size_t* n, const int* sample_rates, int batch,
+                            const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
+        batch_upload(&x, pcm, n, batch, prompts, sample_rates);
+        batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
+        batch_download(&x, ids_out, max_tokens, lens_out);
+    });
+}
+int q3asr_resample(q3asr_handle* h, const float* in, size_t n, int in_rate, int out_rate, float* out, size_t cap, size_t* n_out) {
+    return guarded(h, [&](Handle& x) { resample_host(&x, in, n, in_rate, out_rate, out, cap, n_out); });
 }
 int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
                         int32_t* argmax_out, float* top_out) {

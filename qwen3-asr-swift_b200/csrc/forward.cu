@@ -664,12 +664,26 @@ int encoder_tokens_for(int frames) {
     return full * 13 + (rem > 0 ? std::max(conv_len3(rem), 1) : 0);
 }
 
-void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts) {
-    Q3_CHECK(pcm != nullptr && n != nullptr && batch > 0, Q3ASR_ERR_INVALID, "batch_upload: null argument / empty batch");
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int batch, const q3asr_prompt* prompts, const int* rates) {
+    Q3_CHECK(pcm != nullptr && n_in != nullptr && batch > 0, Q3ASR_ERR_INVALID, "batch_upload: null argument / empty batch");
     Q3_CHECK(batch <= 1024, Q3ASR_ERR_INVALID, "batch_upload: at most 1024 utterances per call");
-    for (int b = 0; b < batch; b++)
-        Q3_CHECK(pcm[b] != nullptr && n[b] >= (size_t)MEL_HOP && n[b] < (size_t)1 << 30, Q3ASR_ERR_INVALID,
-                 "batch_upload: every clip needs at least 160 samples (one mel frame)");
+    // clips at another rate are converted to 16 kHz on the device (Qwen3ASRModel.transcribe resamples first,
+    // AudioPreprocessing.swift:323-337): n16[b] samples reach the mel kernel
+    std::vector<size_t> n16(n_in, n_in + batch);
+    size_t raw_floats = 0;
+    std::vector<size_t> raw_off((size_t)batch, 0);
+    for (int b = 0; b < batch; b++) {
+        Q3_CHECK(pcm[b] != nullptr && n_in[b] < (size_t)1 << 30, Q3ASR_ERR_INVALID, "batch_upload: null clip / clip too long");
+        if (rates != nullptr && rates[b] != 16000) {
+            Q3_CHECK(rates[b] > 0, Q3ASR_ERR_INVALID, "batch_upload: bad sample rate");
+            n16[b] = resample_len(n_in[b], rates[b], 16000);
+            raw_off[(size_t)b] = raw_floats;
+            raw_floats += (n_in[b] + 3) & ~size_t(3);
+        }
+        Q3_CHECK(n16[b] >= (size_t)MEL_HOP && n16[b] < (size_t)1 << 30, Q3ASR_ERR_INVALID,
+                 "batch_upload: every clip needs at least 160 samples at 16 kHz (one mel frame)");
+    }
+    const size_t* n = n16.data();
     BatchState* bs = fresh_batch(h);
     bs->B = batch;
     bs->mel = mel_plan(n, batch);
@@ -682,8 +696,10 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch
     bs->mel_clips.reserve(sizeof(MelClip) * batch);
     bs->mel_gmax.reserve(sizeof(int) * batch);
     bs->mel_tmin.reserve(sizeof(float) * bs->mel.total_tiles);
-    bs->h_stage.reserve(sizeof(float) * bs->mel.pcm_floats);
+    bs->h_stage.reserve(sizeof(float) * (bs->mel.pcm_floats + raw_floats));
     float* stage = bs->h_stage.as<float>();
+    float* stage_raw = stage + bs->mel.pcm_floats;  // clips awaiting conversion
+    if (raw_floats) bs->raw_pcm.reserve(sizeof(float) * raw_floats);
     // The caller's buffers are pageable: copy each clip into the pinned staging area and queue its H2D copy at once, from a
     // few host threads, so the staging memcpy (the slow leg, ~10 GB/s per thread) overlaps the PCIe transfers and the planning
     // below.  Clips are independent, so the order of the copies on the stream does not matter.
@@ -695,6 +711,13 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch
             cudaError_t e = cudaSetDevice(h->device);
             for (int b = w; b < batch && e == cudaSuccess; b += n_workers) {
                 const long long off = bs->mel.clips[b].in_off;
+                if (rates != nullptr && rates[b] != 16000) {
+                    float* sr = stage_raw + raw_off[(size_t)b];
+                    memcpy(sr, pcm[b], sizeof(float) * n_in[b]);
+                    e = cudaMemcpyAsync(bs->raw_pcm.as<float>() + raw_off[(size_t)b], sr, sizeof(float) * n_in[b], cudaMemcpyHostToDevice,
+                                        h->stream);
+                    continue;
+                }
                 memcpy(stage + off, pcm[b], sizeof(float) * n[b]);
                 e = cudaMemcpyAsync(bs->pcm.as<float>() + off, stage + off, sizeof(float) * n[b], cudaMemcpyHostToDevice, h->stream);
             }
@@ -721,6 +744,11 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch
     plan_decoder(h, bs, prompts, reserve_tokens, &ints);
     for (auto& t : workers) t.join();
     for (cudaError_t e : werr) Q3_CUDA(e);
+    if (raw_floats)  // the copies are queued on the stream; the conversions follow them in stream order
+        for (int b = 0; b < batch; b++)
+            if (rates[b] != 16000)
+                resample_device(h, bs->raw_pcm.as<float>() + raw_off[(size_t)b], n_in[b], rates[b], 16000,
+                                bs->pcm.as<float>() + bs->mel.clips[b].in_off, n[b], h->stream);
     upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
     bs->prompt_ids.clear();
 }

@@ -77,6 +77,12 @@ struct Tensor {
     bf16* d = nullptr;  // canonical copy, bf16, device
 };
 
+// polyphase filter of one (input rate, output rate) pair (audio_io.cu)
+struct ResampleTab {
+    int L = 1, M = 1, K = 0;
+    DevBuf taps;  // [L][2K + 2] fp32
+};
+
 struct Model;      // weights in kernel-ready layouts (model.cu)
 struct BatchState; // resident batch: plan + activations (model.cu)
 
@@ -115,9 +121,13 @@ struct Handle {
     cudaEvent_t timer[16] = {nullptr};
     float stage_ms[4] = {0, 0, 0, 0};
     DevBuf flush_buf;
+    // sample-rate conversion (audio_io.cu): filter tables per rate pair, scratch of q3asr_resample
+    std::map<std::pair<int, int>, ResampleTab> resample_tabs;
+    DevBuf rs_in, rs_out;
+    HostBuf rs_stage;
 
     Handle() {
-        for (DevBuf* b : {&mel_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &flush_buf}) b->total = &dev_bytes;
+        for (DevBuf* b : {&mel_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &flush_buf, &rs_in, &rs_out}) b->total = &dev_bytes;
     }
 };
 
@@ -172,7 +182,8 @@ void model_unload(Handle* h);
 void model_load_safetensors(Handle* h, const char* dir);
 int encoder_tokens_for(int frames);
 
-void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts);
+// rates: per-clip sample rates or null (all 16 kHz); other rates are converted on the device (audio_io.cu)
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts, const int* rates = nullptr);
 void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos);
 void batch_download(Handle* h, int32_t* ids, int max_tokens, int* lens);
 void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens);
@@ -180,5 +191,13 @@ void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* pr
                    int32_t* argmax_out, float* top_out);
 void prefill_logits(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits);
 void config_validate(const q3asr_config& c);
+
+// ---- front door (audio_io.cu) ----
+size_t wav_parse(const uint8_t* data, size_t size, float* out, size_t cap, int* sample_rate);
+size_t resample_len(size_t n, int in_rate, int out_rate);
+void resample_design(int in_rate, int out_rate, int* L, int* M, int* K, std::vector<float>* taps);
+void resample_device(Handle* h, const float* d_in, size_t n, int in_rate, int out_rate, float* d_out, size_t n_out, cudaStream_t st);
+void resample_host(Handle* h, const float* in, size_t n, int in_rate, int out_rate, float* out, size_t cap, size_t* n_out);
+int longform_plan(size_t n, size_t window, size_t min_tail, size_t* starts, size_t* lens, int cap);
 
 }  // namespace q3

@@ -70,6 +70,7 @@ struct BatchState {
 
     // device buffers
     DevBuf pcm, mel_out, mel_clips, mel_gmax, mel_tmin;
+    DevBuf raw_pcm;  // clips at other sample rates, before the conversion to 16 kHz
     DevBuf ints;  // all small int arrays, one upload
     // offsets into `ints` (in ints)
     size_t o_conv_chunks = 0;  // Conv1Chunk[] (as bytes, see model.cu)
@@ -92,7 +93,7 @@ struct BatchState {
         for (DevBuf* b : all()) b->total = total;
     }
     std::vector<DevBuf*> all() {
-        return {&pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
+        return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
                 &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};

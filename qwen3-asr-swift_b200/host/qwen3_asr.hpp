@@ -10,6 +10,8 @@
 //   Qwen3ASRModel::transcribe (2 overloads)  Sources/Qwen3ASR/Qwen3ASR.swift:107-164  (inference: never throws)
 //   isLoaded / unload / memoryFootprint      Sources/Qwen3ASR/Qwen3ASR+Memory.swift:3-17
 //   inputSampleRate                          Sources/Qwen3ASR/Qwen3ASR+Protocols.swift:5-11
+//   AudioFileLoader::loadWAV / resample      Sources/AudioCommon/AudioFileLoader.swift:70-213 (AudioLoadError :216-234)
+//   TranscriptionSegment                     Sources/Qwen3ASR/StreamingASR.swift:7-21 (long-form windows instead of VAD segments)
 // Header-only; link with -lq3asr.  Not thread-safe per instance (Qwen3ASR.swift:67).
 #pragma once
 #include <algorithm>
@@ -88,7 +90,39 @@ struct Tokenizer {
     }
 };
 
+struct AudioLoadError : std::runtime_error {  // AudioFileLoader.swift:216-234
+    int code;
+    AudioLoadError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct TranscriptionSegment {  // StreamingASR.swift:7-21
+    std::string text;
+    float startTime = 0.f, endTime = 0.f;
+    bool isFinal = true;
+    int segmentIndex = 0;
+};
+
 class Qwen3ASRModel;
+
+struct AudioFileLoader {
+    struct Wav {
+        std::vector<float> samples;
+        int sampleRate = 0;
+    };
+    // AudioFileLoader.loadWAV: 16-bit PCM, first channel; throws AudioLoadError like the reference
+    static Wav loadWAV(const std::string& path) {
+        Wav w;
+        size_t n = 0;
+        int rc = q3asr_wav_load(path.c_str(), nullptr, 0, &n, &w.sampleRate);
+        if (rc != Q3ASR_OK) throw AudioLoadError(rc, q3asr_io_last_error());
+        w.samples.assign(n, 0.f);
+        rc = q3asr_wav_load(path.c_str(), w.samples.data(), n, &n, &w.sampleRate);
+        if (rc != Q3ASR_OK) throw AudioLoadError(rc, q3asr_io_last_error());
+        return w;
+    }
+    // AudioFileLoader.resample: returns the input unchanged when the conversion cannot run (the reference's own fallback, :175, :207)
+    static std::vector<float> resample(const Qwen3ASRModel& model, const std::vector<float>& samples, int from, int to);
+};
 
 class WhisperFeatureExtractor {
   public:
@@ -145,11 +179,11 @@ class Qwen3ASRModel {
 
     void setTokenizer(Tokenizer t) { tok_ = std::move(t); }
 
-    // Qwen3ASR.swift:131-137.  16 kHz input only (resampling is the caller's, §8a3).  Never throws.
+    // Qwen3ASR.swift:131-137.  Other sample rates are converted to 16 kHz on the device first (AudioPreprocessing.swift:323-337).
+    // Never throws.
     std::string transcribe(const std::vector<float>& audio, int sampleRate = 16000, const std::optional<std::string>& language = {},
                            int maxTokens = 448, const std::optional<std::string>& context = {}) {
-        if (sampleRate != 16000) return "[Qwen3-ASR B200 error: resample to 16 kHz before calling]";
-        return transcribeBatch({&audio}, language, maxTokens, context)[0];
+        return transcribeBatch({&audio}, language, maxTokens, context, {sampleRate})[0];
     }
     // Qwen3ASR.swift:107-111
     std::string transcribe(const std::vector<float>& audio, int sampleRate, const Qwen3DecodingOptions& options) {
@@ -164,8 +198,13 @@ class Qwen3ASRModel {
     // the batched entry the utterance scheduler enables; ids per utterance (EOS included when hit, like the reference loop)
     std::vector<std::vector<int32_t>> transcribeIds(const std::vector<const std::vector<float>*>& audio, int maxTokens = 448,
                                                     bool stopOnEos = true, const std::vector<int32_t>& contextIds = {},
-                                                    const std::vector<int32_t>& languageIds = {}, std::string* error = nullptr) {
+                                                    const std::vector<int32_t>& languageIds = {}, std::string* error = nullptr,
+                                                    const std::vector<int>& sampleRates = {}) {
         const int n = (int)audio.size();
+        if (!sampleRates.empty() && (int)sampleRates.size() != n) {
+            if (error) *error = "sampleRates must have one entry per utterance";
+            return std::vector<std::vector<int32_t>>(n);
+        }
         std::vector<const float*> pcm(n);
         std::vector<size_t> len(n);
         for (int i = 0; i < n; i++) {
@@ -177,7 +216,8 @@ class Qwen3ASRModel {
         std::vector<int32_t> ids((size_t)n * maxTokens);
         std::vector<int> lens(n);
         std::vector<std::vector<int32_t>> out(n);
-        int rc = q3asr_transcribe_ids(h_, pcm.data(), len.data(), n, prompts.data(), maxTokens, stopOnEos ? 1 : 0, ids.data(), lens.data());
+        int rc = q3asr_transcribe_ids_sr(h_, pcm.data(), len.data(), sampleRates.empty() ? nullptr : sampleRates.data(), n, prompts.data(),
+                                         maxTokens, stopOnEos ? 1 : 0, ids.data(), lens.data());
         if (rc != Q3ASR_OK) {
             if (error) *error = q3asr_last_error(h_);
             return out;
@@ -187,7 +227,8 @@ class Qwen3ASRModel {
     }
 
     std::vector<std::string> transcribeBatch(const std::vector<const std::vector<float>*>& audio, const std::optional<std::string>& language = {},
-                                             int maxTokens = 448, const std::optional<std::string>& context = {}) {
+                                             int maxTokens = 448, const std::optional<std::string>& context = {},
+                                             const std::vector<int>& sampleRates = {}) {
         const size_t n = audio.size();
         if (!isLoaded()) return std::vector<std::string>(n, "[Audio encoded] - Text decoder not loaded");  // Qwen3ASR.swift:116-119
         std::vector<int32_t> ctx, lang;
@@ -196,7 +237,7 @@ class Qwen3ASRModel {
             if (language) lang = tok_.encode("language " + *language);  // Qwen3ASR.swift:228-232
         }
         std::string err;
-        auto ids = transcribeIds(audio, maxTokens, true, ctx, lang, &err);
+        auto ids = transcribeIds(audio, maxTokens, true, ctx, lang, &err, sampleRates);
         std::vector<std::string> out(n);
         for (size_t i = 0; i < n; i++) {
             if (!err.empty()) {
@@ -212,6 +253,37 @@ class Qwen3ASRModel {
                 out[i] = a == std::string::npos ? std::string() : raw.substr(a, b - a + 1);
             } else {  // id-string fallback, Qwen3ASR.swift:288-289
                 for (size_t j = 0; j < t.size(); j++) out[i] += (j ? " " : "") + std::to_string(t[j]);
+            }
+        }
+        return out;
+    }
+
+    // Long-form audio (BASELINE config 5): fixed windows of windowSeconds, each an independent utterance, `batch` windows per pass.
+    std::vector<TranscriptionSegment> transcribeLong(const std::vector<float>& audio, int sampleRate = 16000, float windowSeconds = 30.f,
+                                                     int maxTokens = 448, int batch = 64, const std::optional<std::string>& language = {}) {
+        std::vector<TranscriptionSegment> out;
+        const size_t window = (size_t)((double)windowSeconds * sampleRate + 0.5);
+        const size_t minTail = std::max<size_t>(160, ((size_t)160 * sampleRate + 15999) / 16000);
+        int count = 0;
+        if (window == 0 || q3asr_longform_plan(audio.size(), window, minTail, nullptr, nullptr, 0, &count) != Q3ASR_OK || count == 0) return out;
+        std::vector<size_t> starts((size_t)count), lens((size_t)count);
+        q3asr_longform_plan(audio.size(), window, minTail, starts.data(), lens.data(), count, &count);
+        for (int b0 = 0; b0 < count; b0 += std::max(batch, 1)) {
+            const int nb = std::min(std::max(batch, 1), count - b0);
+            std::vector<std::vector<float>> clips((size_t)nb);
+            std::vector<const std::vector<float>*> ptrs((size_t)nb);
+            for (int i = 0; i < nb; i++) {
+                clips[i].assign(audio.begin() + starts[b0 + i], audio.begin() + starts[b0 + i] + lens[b0 + i]);
+                ptrs[i] = &clips[i];
+            }
+            auto texts = transcribeBatch(ptrs, language, maxTokens, {}, std::vector<int>((size_t)nb, sampleRate));
+            for (int i = 0; i < nb; i++) {
+                TranscriptionSegment seg;
+                seg.text = texts[i];
+                seg.startTime = (float)((double)starts[b0 + i] / sampleRate);
+                seg.endTime = (float)((double)(starts[b0 + i] + lens[b0 + i]) / sampleRate);
+                seg.segmentIndex = b0 + i;
+                out.push_back(seg);
             }
         }
         return out;
@@ -234,5 +306,14 @@ class Qwen3ASRModel {
     q3asr_handle* h_ = nullptr;
     Tokenizer tok_;
 };
+
+inline std::vector<float> AudioFileLoader::resample(const Qwen3ASRModel& model, const std::vector<float>& samples, int from, int to) {
+    if (from == to || samples.empty()) return samples;
+    size_t n = q3asr_resample_len(samples.size(), from, to);
+    std::vector<float> out(n);
+    if (q3asr_resample(model.handle(), samples.data(), samples.size(), from, to, out.data(), out.size(), &n) != Q3ASR_OK) return samples;
+    out.resize(n);
+    return out;
+}
 
 }  // namespace qwen3asr

@@ -61,6 +61,8 @@ EXPORTS = [
     "q3asr_debug_gemm", "q3asr_debug_conv", "q3asr_debug_attention",
     "q3asr_tokenizer_load", "q3asr_tokenizer_from_pairs", "q3asr_tokenizer_add_merge", "q3asr_tokenizer_destroy",
     "q3asr_tokenizer_last_error", "q3asr_tokenizer_size", "q3asr_tokenizer_decode", "q3asr_tokenizer_encode", "q3asr_tokenizer_token_id",
+    "q3asr_io_last_error", "q3asr_wav_parse", "q3asr_wav_load", "q3asr_resample_len", "q3asr_resample", "q3asr_resample_design",
+    "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
 ]
 
 _lib = None
@@ -133,6 +135,16 @@ def lib():
         L.q3asr_tokenizer_decode.argtypes = [vp, vp, ci, ctypes.c_char_p, cs, ctypes.POINTER(cs)]
         L.q3asr_tokenizer_encode.argtypes = [vp, ctypes.c_char_p, vp, ci, ctypes.POINTER(ci)]
         L.q3asr_tokenizer_token_id.argtypes = [vp, ctypes.c_char_p]
+        L.q3asr_io_last_error.restype = ctypes.c_char_p
+        L.q3asr_wav_parse.argtypes = [vp, cs, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
+        L.q3asr_wav_load.argtypes = [ctypes.c_char_p, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
+        L.q3asr_resample_len.argtypes = [cs, ci, ci]
+        L.q3asr_resample_len.restype = cs
+        L.q3asr_resample.argtypes = [vp, vp, cs, ci, ci, vp, cs, ctypes.POINTER(cs)]
+        L.q3asr_resample_design.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci), vp, cs, ctypes.POINTER(cs)]
+        L.q3asr_batch_upload_sr.argtypes = [vp, vp, vp, vp, ci, vp]
+        L.q3asr_transcribe_ids_sr.argtypes = [vp, vp, vp, vp, ci, vp, ci, ci, vp, vp]
+        L.q3asr_longform_plan.argtypes = [cs, cs, cs, vp, vp, ci, ctypes.POINTER(ci)]
         _lib = L
     return _lib
 
@@ -165,6 +177,64 @@ def schedule(n_samples, n_gpus):
     if rc != OK:
         raise Q3Error(rc, "schedule: bad argument")
     return out
+
+
+class AudioLoadError(Q3Error):
+    """AudioLoadError of the reference (AudioFileLoader.swift:216-234): invalidWAVFile / unsupportedFormat."""
+
+
+class AudioFileLoader:
+    """AudioFileLoader.loadWAV / resample of the reference (Sources/AudioCommon/AudioFileLoader.swift:70-213)."""
+
+    @staticmethod
+    def _finish(rc):
+        if rc != OK:
+            raise AudioLoadError(rc, lib().q3asr_io_last_error().decode())
+
+    @staticmethod
+    def parse_wav(data):
+        """bytes of a RIFF/WAVE PCM16 file -> (float32 samples of the first channel, sample rate)."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        n, rate = ctypes.c_size_t(), ctypes.c_int()
+        ptr = buf.ctypes.data if buf.size else None
+        AudioFileLoader._finish(lib().q3asr_wav_parse(ptr, buf.size, None, 0, ctypes.byref(n), ctypes.byref(rate)))
+        out = np.empty(n.value, dtype=np.float32)
+        AudioFileLoader._finish(lib().q3asr_wav_parse(ptr, buf.size, out.ctypes.data, out.size, ctypes.byref(n), ctypes.byref(rate)))
+        return out, int(rate.value)
+
+    @staticmethod
+    def load_wav(path):
+        with open(path, "rb") as f:
+            return AudioFileLoader.parse_wav(f.read())
+
+    @staticmethod
+    def resample_len(n, in_rate, out_rate):
+        return int(lib().q3asr_resample_len(int(n), int(in_rate), int(out_rate)))
+
+    @staticmethod
+    def resample_design(in_rate, out_rate):
+        """(L, M, K, taps [L, 2K+2]) of the polyphase converter (csrc/audio_io.cu)."""
+        L, M, K, nt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        AudioFileLoader._finish(lib().q3asr_resample_design(int(in_rate), int(out_rate), ctypes.byref(L), ctypes.byref(M), ctypes.byref(K),
+                                                            None, 0, ctypes.byref(nt)))
+        taps = np.empty(nt.value, dtype=np.float32)
+        AudioFileLoader._finish(lib().q3asr_resample_design(int(in_rate), int(out_rate), ctypes.byref(L), ctypes.byref(M), ctypes.byref(K),
+                                                            taps.ctypes.data, taps.size, ctypes.byref(nt)))
+        return L.value, M.value, K.value, taps.reshape(L.value, 2 * K.value + 2)
+
+
+def longform_plan(n_samples, window, min_tail=160):
+    """[(start, length)] windows of a long recording (each an independent utterance for the scheduler)."""
+    cnt = ctypes.c_int()
+    rc = lib().q3asr_longform_plan(int(n_samples), int(window), int(min_tail), None, None, 0, ctypes.byref(cnt))
+    if rc != OK:
+        raise Q3Error(rc, lib().q3asr_io_last_error().decode())
+    starts = np.zeros(max(cnt.value, 1), dtype=np.uint64)
+    lens = np.zeros(max(cnt.value, 1), dtype=np.uint64)
+    rc = lib().q3asr_longform_plan(int(n_samples), int(window), int(min_tail), starts.ctypes.data, lens.ctypes.data, cnt.value, ctypes.byref(cnt))
+    if rc != OK:
+        raise Q3Error(rc, lib().q3asr_io_last_error().decode())
+    return [(int(starts[i]), int(lens[i])) for i in range(cnt.value)]
 
 
 def f32_to_bf16_bits(x):
@@ -312,24 +382,64 @@ class Qwen3ASRModel:
         self._ck(lib().q3asr_encode(self._h, mel.ctypes.data, T, out.ctypes.data, ctypes.byref(ntok)))
         return out[:ntok.value].copy()
 
-    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, prompts=None):
-        """Batched greedy transcription -> list of int32 id arrays (EOS included when it stops the loop)."""
+    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, prompts=None, sample_rates=None):
+        """Batched greedy transcription -> list of int32 id arrays (EOS included when it stops the loop).  sample_rates: per-clip
+        rates; clips not at 16 kHz are converted on the device (AudioPreprocessing.swift:323-337)."""
         clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
         n = np.array([c.size for c in clips], dtype=np.uint64)
         ids = np.zeros((len(clips), max_tokens), dtype=np.int32)
         lens = np.zeros(len(clips), dtype=np.int32)
         pp = _PromptPack(prompts, len(clips))
-        self._ck(lib().q3asr_transcribe_ids(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), pp.ptr,
-                                            int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
+        if sample_rates is None:
+            self._ck(lib().q3asr_transcribe_ids(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), pp.ptr,
+                                                int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
+        else:
+            sr = np.ascontiguousarray(sample_rates, dtype=np.int32)
+            assert sr.size == len(clips)
+            self._ck(lib().q3asr_transcribe_ids_sr(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, sr.ctypes.data,
+                                                   len(clips), pp.ptr, int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data,
+                                                   lens.ctypes.data))
         return [ids[i, :lens[i]].copy() for i in range(len(clips))]
+
+    def resample(self, samples, in_rate, out_rate):
+        """AudioFileLoader.resample (AudioFileLoader.swift:159-213) on the GPU: float32 [n] -> float32 [floor(n * out / in)]."""
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        out = np.empty(AudioFileLoader.resample_len(x.size, in_rate, out_rate), dtype=np.float32)
+        n_out = ctypes.c_size_t()
+        self._ck(lib().q3asr_resample(self._h, x.ctypes.data, x.size, int(in_rate), int(out_rate), out.ctypes.data, out.size,
+                                      ctypes.byref(n_out)))
+        return out[:n_out.value]
+
+    def _text_of(self, ids):
+        tok = self.tokenizer
+        if tok is None:
+            return " ".join(str(int(t)) for t in ids)
+        raw = tok.decode([int(t) for t in ids])
+        return raw.split("<asr_text>", 1)[1].strip(" ") if "<asr_text>" in raw else raw
+
+    def transcribe_long(self, audio, sample_rate=16000, window_seconds=30.0, max_tokens=448, batch=64, language_ids=None, context_ids=None):
+        """Long-form transcription (BASELINE config 5): fixed windows, each an independent utterance, `batch` windows per pass.
+        Returns [dict(text, ids, start_time, end_time, segment_index)] in the shape of the reference's TranscriptionSegment
+        (StreamingASR.swift:7-21); " ".join of the texts is the transcript."""
+        x = np.ascontiguousarray(audio, dtype=np.float32)
+        wins = longform_plan(x.size, int(round(window_seconds * sample_rate)), min_tail=max(160, (160 * sample_rate + 15999) // 16000))
+        segs = []
+        for b0 in range(0, len(wins), batch):
+            part = wins[b0:b0 + batch]
+            clips = [x[s:s + ln] for s, ln in part]
+            pr = [{"context": context_ids, "language": language_ids}] * len(part)
+            out = self.transcribe_ids(clips, max_tokens=max_tokens, stop_on_eos=True, prompts=pr,
+                                      sample_rates=None if sample_rate == 16000 else [sample_rate] * len(part))
+            for (s, ln), ids in zip(part, out):
+                segs.append(dict(text=self._text_of(ids), ids=ids, start_time=s / sample_rate, end_time=(s + ln) / sample_rate,
+                                 segment_index=len(segs)))
+        return segs
 
     tokenizer = None  # a Qwen3Tokenizer; set by from_pretrained when the checkpoint directory has a vocab.json
 
     def transcribe(self, audio, sample_rate=16000, language=None, max_tokens=448, context=None, language_ids=None, context_ids=None):
         """Qwen3ASRModel.transcribe(audio:sampleRate:language:maxTokens:context:) (Qwen3ASR.swift:131-164, 181-289): with a tokenizer
         the text after "<asr_text>", else the ids joined by spaces (the reference's own fallback)."""
-        if sample_rate != 16000:
-            raise Q3Error(1, "resampling is outside the B200 path: feed 16 kHz audio (AudioPreprocessing.swift:323-337)")
         tok = self.tokenizer
         if tok is not None:
             if context is not None and context_ids is None:
@@ -337,11 +447,9 @@ class Qwen3ASRModel:
             if language is not None and language_ids is None:
                 language_ids = tok.encode("language " + language)    # Qwen3ASR.swift:228-232
         pr = [{"context": context_ids, "language": language_ids}]
-        ids = self.transcribe_ids([audio], max_tokens=max_tokens, stop_on_eos=True, prompts=pr)[0]
-        if tok is None:
-            return " ".join(str(int(t)) for t in ids)
-        raw = tok.decode([int(t) for t in ids])
-        return raw.split("<asr_text>", 1)[1].strip(" ") if "<asr_text>" in raw else raw
+        ids = self.transcribe_ids([audio], max_tokens=max_tokens, stop_on_eos=True, prompts=pr,
+                                  sample_rates=None if sample_rate == 16000 else [sample_rate])[0]
+        return self._text_of(ids)
 
     def decode_forced(self, audio, forced, prompt=None):
         audio = np.ascontiguousarray(audio, dtype=np.float32)
