@@ -120,6 +120,29 @@ typedef struct q3asr_prompt {
 int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch,
                          const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out);
 
+/* Decoder knobs of Qwen3DecodingOptions (Qwen3ASR.swift:13-51).  The default values are the greedy fast path
+ * (isGreedyFastPath, Qwen3ASR.swift:300-304: the fused argmax epilogue); anything else runs pickNextToken
+ * (Qwen3ASR.swift:449-520) as a device kernel over the full logits: sign-aware repetition penalty on the tokens generated so far,
+ * no-repeat-n-gram mask, logits / temperature + Gumbel(0,1) noise, first maximum.  The reference draws its noise from the system
+ * RNG; here it is a counter-based stream keyed by (seed, sequence, step, vocabulary index), so runs are reproducible. */
+typedef struct q3asr_sampling {
+    float repetition_penalty;  /* 1.0 = off */
+    int no_repeat_ngram_size;  /* 0 = off */
+    float temperature;         /* 0 = argmax */
+    uint64_t seed;
+    int force_device_sampler;  /* != 0: run the sampling kernel even for the greedy configuration (parity tests) */
+} q3asr_sampling;
+/* q3asr_transcribe_ids_sr with decoder knobs (one setting for the whole batch; sampling == NULL is greedy) */
+int q3asr_transcribe_ids_opts(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                              const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos,
+                              int32_t* ids_out, int* lens_out);
+/* resident-batch form: call between q3asr_batch_upload and the prefill stage */
+int q3asr_batch_set_sampling(q3asr_handle* h, const q3asr_sampling* sampling);
+/* pickNextToken on caller-provided logits ([vocab] fp32; the reference's own unit tests drive it this way,
+ * Tests/Qwen3ASRTests/Qwen3DecodingOptionsTests.swift:47-235).  draw selects the noise draw (the decode step). */
+int q3asr_pick_next_token(q3asr_handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated,
+                          const q3asr_sampling* sampling, int draw, int32_t* token);
+
 /* Teacher-forced scoring (parity on a prescribed token stream): the decoder consumes forced[0..n) as its
  * own outputs; argmax_out[i] / top_out[i] are the argmax id and its bf16 logit at step i (i = 0 is the
  * prefill position), n_forced + 1 entries. */

@@ -262,6 +262,27 @@ class Oracle:
             logits = self._logits(last)
         return np.array(ids, dtype=np.int32), np.array(tops, dtype=np.float32), np.array(margins, dtype=np.float32)
 
+    def generate_slow(self, audio_embeds, max_tokens, repetition_penalty=1.0, no_repeat_ngram_size=0, stop_on_eos=True):
+        """Qwen3ASR.swift:396-447 (generateSlow) with pickNextToken (oracle/sampler.py) on every step's logits; temperature 0
+        (the noise stream is the library's own, see oracle/sampler.py).  Returns (ids, per-step margin between the two best
+        adjusted scores, per-step best adjusted score)."""
+        from . import sampler
+        E = self.w["model.embed_tokens.weight"]
+        logits, cache, _ = self.prefill(audio_embeds)
+        ids, margins, tops = [], [], []
+        for step in range(max_tokens):
+            sc = sampler.adjusted_scores(logits.numpy(), ids, repetition_penalty, no_repeat_ngram_size)
+            tok = sampler.pick_next_token(logits.numpy(), ids, repetition_penalty, no_repeat_ngram_size)
+            top = np.sort(sc[np.isfinite(sc)])[-2:]
+            margins.append(float(top[-1] - top[0]) if top.size == 2 else np.inf)
+            tops.append(float(top[-1]) if top.size else 0.0)
+            ids.append(tok)
+            if (stop_on_eos and tok == self.cfg["tok_eos"]) or step + 1 == max_tokens:
+                break
+            last, cache = self._decoder_forward(E[tok:tok + 1].clone(), cache)
+            logits = self._logits(last)
+        return np.array(ids, dtype=np.int32), np.array(margins, dtype=np.float32), np.array(tops, dtype=np.float32)
+
     def transcribe_ids(self, pcm, max_tokens=448, stop_on_eos=True):
         from . import mel as mel_mod
         feats = mel_mod.mel(pcm)

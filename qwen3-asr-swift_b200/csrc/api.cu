@@ -274,6 +274,24 @@ int q3asr_transcribe_ids_sr(q3asr_handle* h, const float* const* pcm, const size
         batch_download(&x, ids_out, max_tokens, lens_out);
     });
 }
+int q3asr_batch_set_sampling(q3asr_handle* h, const q3asr_sampling* opts) {
+    return guarded(h, [&](Handle& x) { batch_set_sampling(&x, opts); });
+}
+int q3asr_transcribe_ids_opts(q3asr_handle* h, const float* const* pcm, const size_t* n, const int* sample_rates, int batch,
+                              const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos,
+                              int32_t* ids_out, int* lens_out) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
+        batch_upload(&x, pcm, n, batch, prompts, sample_rates);
+        batch_set_sampling(&x, sampling);
+        batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
+        batch_download(&x, ids_out, max_tokens, lens_out);
+    });
+}
+int q3asr_pick_next_token(q3asr_handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated,
+                          const q3asr_sampling* opts, int draw, int32_t* token) {
+    return guarded(h, [&](Handle& x) { pick_next_token(&x, logits, vocab, generated, n_generated, opts, draw, token); });
+}
 int q3asr_resample(q3asr_handle* h, const float* in, size_t n, int in_rate, int out_rate, float* out, size_t cap, size_t* n_out) {
     return guarded(h, [&](Handle& x) { resample_host(&x, in, n, in_rate, out_rate, out, cap, n_out); });
 }

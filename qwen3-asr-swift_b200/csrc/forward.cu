@@ -505,6 +505,21 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed
         rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
         h->launches++;
     }
+    if (bs->sampler_on) {
+        // decoder knobs (Qwen3ASR.swift:396-520): bf16 logits of every sequence, then penalty / n-gram mask / Gumbel noise / argmax
+        // in one kernel over the tokens decode_advance has recorded so far
+        bs->logits_bf.reserve((size_t)B * c.dec_vocab * sizeof(bf16));
+        GemmEpiArgs e;
+        e.epi = EPI_NORMAL;
+        e.out = bs->logits_bf.p;
+        e.ldo = c.dec_vocab;
+        gemm(bs->dlast.as<bf16>(), H, B, H, m.embed, c.dec_vocab, e, st);
+        sample_launch(bs->logits_bf.as<bf16>(), nullptr, c.dec_vocab, c.dec_vocab, bs->st_out_ids.as<int32_t>(), bs->max_tokens,
+                      bs->st_out_len.as<int>(), bs->sampling, bs->st_scalars.as<int>() + 1, B, bs->st_next_tok.as<int32_t>(),
+                      bs->st_next_val.as<float>(), st);
+        h->launches++;
+        return;
+    }
     const int bn = gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
     GemmEpiArgs e;
     e.epi = EPI_ARGMAX;
@@ -690,6 +705,7 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     bs->mel_done = bs->enc_done = bs->prefill_done = false;
     bs->steps_done = 0;
     bs->has_audio = true;
+    bs->sampler_on = false;  // every batch starts greedy; batch_set_sampling turns the decoder knobs on
     // samples: pinned staging -> device
     bs->pcm.reserve(sizeof(float) * (bs->mel.pcm_floats + 64));
     bs->mel_out.reserve(sizeof(float) * std::max<long long>(bs->mel.out_floats, 1));
@@ -751,6 +767,59 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
                                 bs->pcm.as<float>() + bs->mel.clips[b].in_off, n[b], h->stream);
     upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
     bs->prompt_ids.clear();
+}
+
+void batch_set_sampling(Handle* h, const q3asr_sampling* opts) {
+    BatchState* bs = h->batch.get();
+    Q3_CHECK(bs != nullptr && bs->B > 0, Q3ASR_ERR_STATE, "batch_set_sampling: no batch uploaded");
+    Q3_CHECK(!bs->prefill_done, Q3ASR_ERR_STATE, "batch_set_sampling: the first token of this batch has already been chosen");
+    if (opts == nullptr) {
+        bs->sampler_on = false;
+        return;
+    }
+    Q3_CHECK(opts->repetition_penalty > 0.f && opts->no_repeat_ngram_size >= 0 && opts->temperature >= 0.f, Q3ASR_ERR_INVALID,
+             "sampling: repetition_penalty > 0, no_repeat_ngram_size >= 0, temperature >= 0");
+    // Qwen3ASRModel.isGreedyFastPath (Qwen3ASR.swift:300-304): the default configuration keeps the fused argmax epilogue
+    const bool greedy = opts->repetition_penalty == 1.0f && opts->no_repeat_ngram_size == 0 && opts->temperature == 0.0f;
+    bs->sampler_on = !greedy || opts->force_device_sampler != 0;
+    bs->sampling.repetition_penalty = opts->repetition_penalty;
+    bs->sampling.no_repeat_ngram = opts->no_repeat_ngram_size;
+    bs->sampling.temperature = opts->temperature;
+    bs->sampling.seed = opts->seed;
+}
+
+void pick_next_token(Handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated, const q3asr_sampling* opts,
+                     int draw, int32_t* token) {
+    Q3_CHECK(logits != nullptr && vocab > 0 && n_generated >= 0 && (generated != nullptr || n_generated == 0) && opts != nullptr &&
+                 token != nullptr,
+             Q3ASR_ERR_INVALID, "pick_next_token: bad argument");
+    SamplingParams sp;
+    sp.repetition_penalty = opts->repetition_penalty;
+    sp.no_repeat_ngram = opts->no_repeat_ngram_size;
+    sp.temperature = opts->temperature;
+    sp.seed = opts->seed;
+    float* d_logits = nullptr;
+    int32_t* d_gen = nullptr;
+    int* d_small = nullptr;  // [gen_len, step, token]
+    cudaStream_t st = h->stream;
+    auto release = [&]() { cudaFree(d_logits); cudaFree(d_gen); cudaFree(d_small); };
+    try {
+        Q3_CUDA(cudaMalloc(&d_logits, sizeof(float) * vocab));
+        Q3_CUDA(cudaMalloc(&d_gen, sizeof(int32_t) * std::max(n_generated, 1)));
+        Q3_CUDA(cudaMalloc(&d_small, sizeof(int) * 4));
+        const int small[4] = {n_generated, draw, 0, 0};
+        Q3_CUDA(cudaMemcpyAsync(d_logits, logits, sizeof(float) * vocab, cudaMemcpyHostToDevice, st));
+        if (n_generated) Q3_CUDA(cudaMemcpyAsync(d_gen, generated, sizeof(int32_t) * n_generated, cudaMemcpyHostToDevice, st));
+        Q3_CUDA(cudaMemcpyAsync(d_small, small, sizeof(small), cudaMemcpyHostToDevice, st));
+        sample_launch(nullptr, d_logits, vocab, vocab, d_gen, std::max(n_generated, 1), d_small, sp, d_small + 1, 1, d_small + 2, nullptr, st);
+        h->launches++;
+        Q3_CUDA(cudaMemcpyAsync(token, d_small + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        Q3_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        release();
+        throw;
+    }
+    release();
 }
 
 void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos) {

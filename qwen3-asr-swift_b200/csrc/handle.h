@@ -184,6 +184,9 @@ int encoder_tokens_for(int frames);
 
 // rates: per-clip sample rates or null (all 16 kHz); other rates are converted on the device (audio_io.cu)
 void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts, const int* rates = nullptr);
+void batch_set_sampling(Handle* h, const q3asr_sampling* opts);
+void pick_next_token(Handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated, const q3asr_sampling* opts,
+                     int draw, int32_t* token);
 void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos);
 void batch_download(Handle* h, int32_t* ids, int max_tokens, int* lens);
 void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens);

@@ -66,6 +66,8 @@ struct BatchState {
     int max_tokens = 0;      // decode capacity the KV pages were reserved for
     int pages_per_seq = 0;
     bool has_audio = false, mel_done = false, enc_done = false, prefill_done = false;
+    bool sampler_on = false;   // decoder knobs active: full logits + sample_kernel instead of the fused argmax epilogue
+    SamplingParams sampling;
     int steps_done = 0;
 
     // device buffers
@@ -81,7 +83,7 @@ struct BatchState {
     DevBuf dx, dxn, dqkv, dq, dkc, datt, dact, dlast, dws; // decoder activations (dws: fp32 split-K partials of the decode step)
     DevBuf kv_pool, rope_tab;
     int rope_n = 0;          // positions tabulated in rope_tab
-    DevBuf amax_val, amax_idx, logits;
+    DevBuf amax_val, amax_idx, logits, logits_bf;
     // decode state (device)
     DevBuf st_next_tok, st_next_val, st_cur_tok, st_pos, st_kv_len, st_out_ids, st_out_val, st_out_len, st_finished, st_scalars, st_forced;
     HostBuf h_stage, h_ints, h_out;
@@ -94,7 +96,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }

@@ -889,6 +889,94 @@ __global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
     if (i == 0) *s.step = step + 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// pickNextToken on the device (Qwen3ASR.swift:449-520).  Order of the edits as in the reference: penalty, n-gram mask,
+// temperature + Gumbel noise, then the first maximum (lowest index on ties; index 0 when every score is -inf).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64_dev(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logits, int ld, int vocab, const int32_t* __restrict__ gen_ids,
+                                                       int gen_stride, const int* __restrict__ gen_len, SamplingParams sp,
+                                                       const int* __restrict__ step, int32_t* __restrict__ next_tok,
+                                                       float* __restrict__ next_val) {
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
+    extern __shared__ unsigned int s_bits[];
+    const int words = (vocab + 31) / 32;
+    unsigned int* seen = s_bits;            // tokens generated so far
+    unsigned int* forbidden = s_bits + words;  // tokens that would complete a repeated n-gram
+    __shared__ float s_best[32];
+    __shared__ int s_idx[32];
+    const int seq = blockIdx.x, tid = threadIdx.x;
+    const int32_t* gen = gen_ids + (size_t)seq * gen_stride;
+    const int g = gen_len[seq];
+    const bool penal = sp.repetition_penalty > 1.0f && g > 0;
+    const int n = sp.no_repeat_ngram;
+    for (int i = tid; i < 2 * words; i += blockDim.x) s_bits[i] = 0u;
+    __syncthreads();
+    if (penal)
+        for (int i = tid; i < g; i += blockDim.x) {
+            const int t = gen[i];
+            if (t >= 0 && t < vocab) atomicOr(&seen[t >> 5], 1u << (t & 31));
+        }
+    if (n > 0 && g >= n) {
+        const int32_t* last = gen + g - (n - 1);  // the n-1 most recent tokens
+        for (int i = tid; i <= g - n; i += blockDim.x) {
+            bool same = true;
+            for (int k = 0; k < n - 1 && same; k++) same = gen[i + k] == last[k];
+            if (same) {
+                const int t = gen[i + n - 1];
+                if (t >= 0 && t < vocab) atomicOr(&forbidden[t >> 5], 1u << (t & 31));
+            }
+        }
+    }
+    __syncthreads();
+    const T* row = logits + (size_t)seq * ld;
+    const float inv_t = sp.temperature > 0.f ? 1.0f / sp.temperature : 1.0f;
+    const unsigned long long key = splitmix64_dev(sp.seed ^ ((unsigned long long)(step ? *step : 0) << 32) ^ (unsigned long long)seq);
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int i = tid; i < vocab; i += blockDim.x) {
+        float v = (float)row[i];
+        const unsigned int bit = 1u << (i & 31);
+        if (seen[i >> 5] & bit) v = v > 0.f ? v / sp.repetition_penalty : v * sp.repetition_penalty;
+        if (forbidden[i >> 5] & bit) v = -INFINITY;
+        if (sp.temperature > 0.f) {
+            const unsigned int r = (unsigned int)(splitmix64_dev(key + (unsigned long long)i) >> 40);  // 24 bits
+            const float u = 1e-6f + (float)r * (1.0f / 16777216.0f) * (1.0f - 1e-6f);                  // [1e-6, 1)
+            v = v * inv_t - __logf(-__logf(u));
+        }
+        if (v > best) { best = v; bidx = i; }  // ascending i per thread: the first maximum is kept
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_idx[tid >> 5] = bidx; }
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = blockDim.x >> 5;
+        best = tid < nw ? s_best[tid] : -INFINITY;
+        bidx = tid < nw ? s_idx[tid] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (tid == 0) {
+            next_tok[seq] = bidx == 0x7fffffff ? 0 : bidx;
+            if (next_val) next_val[seq] = best;
+        }
+    }
+}
+
 __global__ void fill_i32_kernel(int* p, int v, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1044,6 +1132,21 @@ void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_
 void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st) {
     Q3_CHECK(n_seqs <= 1024, 1, "decode_advance: at most 1024 sequences per handle");
     launch_kernel(decode_advance_kernel, 1, 1024, 0, st, s, n_seqs);
+}
+
+void sample_launch(const bf16* logits_bf16, const float* logits_f32, int ld, int vocab, const int32_t* gen_ids, int gen_stride,
+                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, int32_t* next_tok, float* next_val,
+                   cudaStream_t st) {
+    if (n_seqs <= 0) return;
+    Q3_CHECK(vocab > 0 && vocab <= 160 * 1024, 1, "sample: vocabulary too large for the shared-memory bitmaps");
+    Q3_CHECK((logits_bf16 != nullptr) != (logits_f32 != nullptr), 1, "sample: exactly one logits pointer");
+    const size_t smem = (size_t)2 * ((vocab + 31) / 32) * sizeof(unsigned int);
+    if (logits_bf16)
+        launch_kernel(sample_kernel<bf16>, n_seqs, 1024, smem, st, logits_bf16, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, next_tok,
+                      next_val);
+    else
+        launch_kernel(sample_kernel<float>, n_seqs, 1024, smem, st, logits_f32, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, next_tok,
+                      next_val);
 }
 
 void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st) {

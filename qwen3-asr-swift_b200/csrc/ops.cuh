@@ -94,6 +94,22 @@ struct DecodeState {
 };
 void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st);
 
+// Decoder knobs of Qwen3DecodingOptions (Qwen3ASR.swift:13-51) applied on the device: the reference pulls the [vocab] logits to
+// the CPU every token (pickNextToken, Qwen3ASR.swift:449-520); here one CTA per sequence applies the same three edits while it
+// scans the row for the argmax — sign-aware repetition penalty over the tokens generated so far, the no-repeat-n-gram mask,
+// logits / T + Gumbel(0,1) — with the generated set and the forbidden set as vocabulary bitmaps in shared memory.
+struct SamplingParams {
+    float repetition_penalty = 1.0f;
+    int no_repeat_ngram = 0;
+    float temperature = 0.0f;
+    unsigned long long seed = 0;
+};
+// logits: [n_seqs, ld] (bf16 or fp32); gen_ids: [n_seqs, gen_stride] with gen_len[seq] valid entries; step: device counter that
+// varies the noise per decode step (may be null); writes next_tok[seq] (and next_val[seq], the adjusted score, if non-null).
+void sample_launch(const bf16* logits_bf16, const float* logits_f32, int ld, int vocab, const int32_t* gen_ids, int gen_stride,
+                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, int32_t* next_tok, float* next_val,
+                   cudaStream_t st);
+
 void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st);
 void bf16_to_f32_launch(const bf16* in, float* out, size_t n, cudaStream_t st);
 void f32_to_bf16_launch(const float* in, bf16* out, size_t n, cudaStream_t st);

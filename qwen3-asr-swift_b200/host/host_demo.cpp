@@ -53,6 +53,21 @@ int main(int argc, char** argv) {
     printf("text(ids) %s\n", t.c_str());
     auto both = m->transcribeBatch({&x, &x}, {}, 8);
     if (both[0] != both[1] || both[0] != t) return 4;
+    // decoder knobs: a no-repeat-bigram mask must leave no bigram twice in the id stream (printed as ids: no tokenizer here)
+    Qwen3DecodingOptions knobs;
+    knobs.maxTokens = 12;
+    knobs.noRepeatNgramSize = 2;
+    knobs.repetitionPenalty = 1.2f;
+    std::string k = m->transcribe(x, 16000, knobs);
+    printf("knobs(ids) %s\n", k.c_str());
+    if (k == t || k.empty() || k[0] == '[') return 10;
+    // 24 kHz input is converted on the device; long-form windows
+    std::vector<float> x24((size_t)seconds * 24000);
+    for (size_t i = 0; i < x24.size(); i++) x24[i] = 0.4f * sinf(2.f * 3.14159265f * 440.f * (float)i / 24000.f);
+    if (m->transcribe(x24, 24000, {}, 8).empty()) return 11;
+    if (AudioFileLoader::resample(*m, x24, 24000, 16000).size() != x.size()) return 12;
+    auto segs = m->transcribeLong(x, 16000, 1.0f, 4, 2);
+    if ((int)segs.size() != seconds || segs.back().segmentIndex != seconds - 1) return 13;
     m->unload();
     if (m->isLoaded() || m->transcribe(x).find("not loaded") == std::string::npos) return 5;
     return f.timeFrames == seconds * 100 ? 0 : 6;

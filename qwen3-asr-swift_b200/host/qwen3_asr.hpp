@@ -35,6 +35,7 @@ struct Qwen3DecodingOptions {
     float repetitionPenalty = 1.0f;
     int noRepeatNgramSize = 0;
     float temperature = 0.0f;
+    uint64_t seed = 0;  // keys the reproducible Gumbel noise stream of the device sampler (the reference uses the system RNG)
     bool isGreedyFastPath() const {  // Qwen3ASR.swift:300-304
         return temperature == 0.0f && repetitionPenalty == 1.0f && noRepeatNgramSize == 0;
     }
@@ -187,8 +188,8 @@ class Qwen3ASRModel {
     }
     // Qwen3ASR.swift:107-111
     std::string transcribe(const std::vector<float>& audio, int sampleRate, const Qwen3DecodingOptions& options) {
-        if (!options.isGreedyFastPath()) return "[Qwen3-ASR B200 error: only greedy decoding is implemented on this path]";
-        return transcribe(audio, sampleRate, options.language, options.maxTokens, options.context);
+        // the decoder knobs (repetition penalty, no-repeat n-gram, temperature) run as a device kernel (Qwen3ASR.swift:396-520)
+        return transcribeBatch({&audio}, options.language, options.maxTokens, options.context, {sampleRate}, &options)[0];
     }
     // SpeechRecognitionModel.transcribe(audio:sampleRate:language:)
     std::string transcribe(const std::vector<float>& audio, int sampleRate, const std::optional<std::string>& language) {
@@ -199,7 +200,7 @@ class Qwen3ASRModel {
     std::vector<std::vector<int32_t>> transcribeIds(const std::vector<const std::vector<float>*>& audio, int maxTokens = 448,
                                                     bool stopOnEos = true, const std::vector<int32_t>& contextIds = {},
                                                     const std::vector<int32_t>& languageIds = {}, std::string* error = nullptr,
-                                                    const std::vector<int>& sampleRates = {}) {
+                                                    const std::vector<int>& sampleRates = {}, const Qwen3DecodingOptions* options = nullptr) {
         const int n = (int)audio.size();
         if (!sampleRates.empty() && (int)sampleRates.size() != n) {
             if (error) *error = "sampleRates must have one entry per utterance";
@@ -216,8 +217,10 @@ class Qwen3ASRModel {
         std::vector<int32_t> ids((size_t)n * maxTokens);
         std::vector<int> lens(n);
         std::vector<std::vector<int32_t>> out(n);
-        int rc = q3asr_transcribe_ids_sr(h_, pcm.data(), len.data(), sampleRates.empty() ? nullptr : sampleRates.data(), n, prompts.data(),
-                                         maxTokens, stopOnEos ? 1 : 0, ids.data(), lens.data());
+        q3asr_sampling samp{1.0f, 0, 0.0f, 0, 0};
+        if (options) samp = q3asr_sampling{options->repetitionPenalty, options->noRepeatNgramSize, options->temperature, options->seed, 0};
+        int rc = q3asr_transcribe_ids_opts(h_, pcm.data(), len.data(), sampleRates.empty() ? nullptr : sampleRates.data(), n, prompts.data(),
+                                           options ? &samp : nullptr, maxTokens, stopOnEos ? 1 : 0, ids.data(), lens.data());
         if (rc != Q3ASR_OK) {
             if (error) *error = q3asr_last_error(h_);
             return out;
@@ -228,7 +231,7 @@ class Qwen3ASRModel {
 
     std::vector<std::string> transcribeBatch(const std::vector<const std::vector<float>*>& audio, const std::optional<std::string>& language = {},
                                              int maxTokens = 448, const std::optional<std::string>& context = {},
-                                             const std::vector<int>& sampleRates = {}) {
+                                             const std::vector<int>& sampleRates = {}, const Qwen3DecodingOptions* options = nullptr) {
         const size_t n = audio.size();
         if (!isLoaded()) return std::vector<std::string>(n, "[Audio encoded] - Text decoder not loaded");  // Qwen3ASR.swift:116-119
         std::vector<int32_t> ctx, lang;
@@ -237,7 +240,7 @@ class Qwen3ASRModel {
             if (language) lang = tok_.encode("language " + *language);  // Qwen3ASR.swift:228-232
         }
         std::string err;
-        auto ids = transcribeIds(audio, maxTokens, true, ctx, lang, &err, sampleRates);
+        auto ids = transcribeIds(audio, maxTokens, true, ctx, lang, &err, sampleRates, options);
         std::vector<std::string> out(n);
         for (size_t i = 0; i < n; i++) {
             if (!err.empty()) {

@@ -48,6 +48,29 @@ class Prompt(ctypes.Structure):
                 ("language_ids", ctypes.POINTER(ctypes.c_int32)), ("n_language", ctypes.c_int)]
 
 
+class Sampling(ctypes.Structure):
+    """q3asr_sampling: the decoder knobs of Qwen3DecodingOptions (Qwen3ASR.swift:13-51)."""
+    _fields_ = [("repetition_penalty", ctypes.c_float), ("no_repeat_ngram_size", ctypes.c_int), ("temperature", ctypes.c_float),
+                ("seed", ctypes.c_uint64), ("force_device_sampler", ctypes.c_int)]
+
+
+class Qwen3DecodingOptions:
+    """Qwen3DecodingOptions (Qwen3ASR.swift:13-51), same names and defaults; `seed` keys the reproducible Gumbel noise stream."""
+
+    def __init__(self, max_tokens=448, language=None, context=None, repetition_penalty=1.0, no_repeat_ngram_size=0, temperature=0.0,
+                 seed=0):
+        self.max_tokens, self.language, self.context = max_tokens, language, context
+        self.repetition_penalty, self.no_repeat_ngram_size, self.temperature, self.seed = repetition_penalty, no_repeat_ngram_size, temperature, seed
+
+    @property
+    def is_greedy_fast_path(self):  # Qwen3ASR.swift:300-304
+        return self.repetition_penalty == 1.0 and self.no_repeat_ngram_size == 0 and self.temperature == 0.0
+
+    def c_struct(self, force_device_sampler=False):
+        return Sampling(float(self.repetition_penalty), int(self.no_repeat_ngram_size), float(self.temperature), int(self.seed),
+                        int(bool(force_device_sampler)))
+
+
 # every symbol include/q3asr.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
@@ -63,6 +86,7 @@ EXPORTS = [
     "q3asr_tokenizer_last_error", "q3asr_tokenizer_size", "q3asr_tokenizer_decode", "q3asr_tokenizer_encode", "q3asr_tokenizer_token_id",
     "q3asr_io_last_error", "q3asr_wav_parse", "q3asr_wav_load", "q3asr_resample_len", "q3asr_resample", "q3asr_resample_design",
     "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
+    "q3asr_transcribe_ids_opts", "q3asr_batch_set_sampling", "q3asr_pick_next_token",
 ]
 
 _lib = None
@@ -145,6 +169,9 @@ def lib():
         L.q3asr_batch_upload_sr.argtypes = [vp, vp, vp, vp, ci, vp]
         L.q3asr_transcribe_ids_sr.argtypes = [vp, vp, vp, vp, ci, vp, ci, ci, vp, vp]
         L.q3asr_longform_plan.argtypes = [cs, cs, cs, vp, vp, ci, ctypes.POINTER(ci)]
+        L.q3asr_transcribe_ids_opts.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(Sampling), ci, ci, vp, vp]
+        L.q3asr_batch_set_sampling.argtypes = [vp, ctypes.POINTER(Sampling)]
+        L.q3asr_pick_next_token.argtypes = [vp, vp, ci, vp, ci, ctypes.POINTER(Sampling), ci, ctypes.POINTER(ctypes.c_int32)]
         _lib = L
     return _lib
 
@@ -382,15 +409,23 @@ class Qwen3ASRModel:
         self._ck(lib().q3asr_encode(self._h, mel.ctypes.data, T, out.ctypes.data, ctypes.byref(ntok)))
         return out[:ntok.value].copy()
 
-    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, prompts=None, sample_rates=None):
-        """Batched greedy transcription -> list of int32 id arrays (EOS included when it stops the loop).  sample_rates: per-clip
-        rates; clips not at 16 kHz are converted on the device (AudioPreprocessing.swift:323-337)."""
+    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, prompts=None, sample_rates=None, options=None,
+                       force_device_sampler=False):
+        """Batched transcription -> list of int32 id arrays (EOS included when it stops the loop).  sample_rates: per-clip
+        rates; clips not at 16 kHz are converted on the device (AudioPreprocessing.swift:323-337).  options: a
+        Qwen3DecodingOptions whose decoder knobs (repetition penalty, no-repeat n-gram, temperature) run as a device kernel."""
         clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
         n = np.array([c.size for c in clips], dtype=np.uint64)
         ids = np.zeros((len(clips), max_tokens), dtype=np.int32)
         lens = np.zeros(len(clips), dtype=np.int32)
         pp = _PromptPack(prompts, len(clips))
-        if sample_rates is None:
+        if options is not None:
+            sr = None if sample_rates is None else np.ascontiguousarray(sample_rates, dtype=np.int32)
+            samp = options.c_struct(force_device_sampler)
+            self._ck(lib().q3asr_transcribe_ids_opts(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data,
+                                                     sr.ctypes.data if sr is not None else None, len(clips), pp.ptr, ctypes.byref(samp),
+                                                     int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
+        elif sample_rates is None:
             self._ck(lib().q3asr_transcribe_ids(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), pp.ptr,
                                                 int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data, lens.ctypes.data))
         else:
@@ -400,6 +435,16 @@ class Qwen3ASRModel:
                                                    len(clips), pp.ptr, int(max_tokens), int(bool(stop_on_eos)), ids.ctypes.data,
                                                    lens.ctypes.data))
         return [ids[i, :lens[i]].copy() for i in range(len(clips))]
+
+    def pick_next_token(self, logits, generated_so_far, options, draw=0):
+        """Qwen3ASRModel.pickNextToken (Qwen3ASR.swift:449-520) through the device kernel, on caller-provided logits."""
+        lg = np.ascontiguousarray(logits, dtype=np.float32).reshape(-1)
+        gen = np.ascontiguousarray(generated_so_far, dtype=np.int32).reshape(-1)
+        samp = options.c_struct(True)
+        tok = ctypes.c_int32()
+        self._ck(lib().q3asr_pick_next_token(self._h, lg.ctypes.data, lg.size, gen.ctypes.data if gen.size else None, gen.size,
+                                             ctypes.byref(samp), int(draw), ctypes.byref(tok)))
+        return int(tok.value)
 
     def resample(self, samples, in_rate, out_rate):
         """AudioFileLoader.resample (AudioFileLoader.swift:159-213) on the GPU: float32 [n] -> float32 [floor(n * out / in)]."""
@@ -437,10 +482,13 @@ class Qwen3ASRModel:
 
     tokenizer = None  # a Qwen3Tokenizer; set by from_pretrained when the checkpoint directory has a vocab.json
 
-    def transcribe(self, audio, sample_rate=16000, language=None, max_tokens=448, context=None, language_ids=None, context_ids=None):
+    def transcribe(self, audio, sample_rate=16000, language=None, max_tokens=448, context=None, language_ids=None, context_ids=None,
+                   options=None):
         """Qwen3ASRModel.transcribe(audio:sampleRate:language:maxTokens:context:) (Qwen3ASR.swift:131-164, 181-289): with a tokenizer
         the text after "<asr_text>", else the ids joined by spaces (the reference's own fallback)."""
         tok = self.tokenizer
+        if options is not None:  # transcribe(audio:sampleRate:options:), Qwen3ASR.swift:107-111
+            language, context, max_tokens = options.language, options.context, options.max_tokens
         if tok is not None:
             if context is not None and context_ids is None:
                 context_ids = tok.encode(context)                    # Qwen3ASR.swift:203-206
@@ -448,7 +496,8 @@ class Qwen3ASRModel:
                 language_ids = tok.encode("language " + language)    # Qwen3ASR.swift:228-232
         pr = [{"context": context_ids, "language": language_ids}]
         ids = self.transcribe_ids([audio], max_tokens=max_tokens, stop_on_eos=True, prompts=pr,
-                                  sample_rates=None if sample_rate == 16000 else [sample_rate])[0]
+                                  sample_rates=None if sample_rate == 16000 else [sample_rate],
+                                  options=None if options is None or options.is_greedy_fast_path else options)[0]
         return self._text_of(ids)
 
     def decode_forced(self, audio, forced, prompt=None):
