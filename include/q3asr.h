@@ -64,9 +64,14 @@ typedef struct q3asr_config {
     /* prompt token ids (Qwen3ASR.swift:181-195); only the tests' tiny vocabulary changes them */
     int32_t tok_im_start, tok_im_end, tok_audio_start, tok_audio_end, tok_audio_pad, tok_asr_text, tok_newline, tok_system,
         tok_user, tok_assistant, tok_eos;
+    /* forced aligner (ForcedAligner.swift:57-85, Configuration.swift:132-133): > 0 adds the timestamp classification head
+     * lm_head.{weight,bias} [classify_num, dec_hidden]; 0 for the ASR models */
+    int classify_num;     /* 5000 */
+    int32_t tok_timestamp; /* <|timestamp|> 151705, Qwen3ASR.swift:62 */
 } q3asr_config;
 
-/* name: "0.6B", "1.7B", or "tiny" (a small configuration used by the parity tests) */
+/* name: "0.6B", "1.7B", "aligner" (Qwen3-ForcedAligner-0.6B: the large encoder projecting to the 1024-wide decoder, 5000 classes),
+ * or "tiny" / "tiny-aligner" (small configurations used by the parity tests) */
 int q3asr_config_preset(const char* name, q3asr_config* cfg);
 
 const char* q3asr_version(void);
@@ -112,6 +117,9 @@ typedef struct q3asr_prompt {
     int n_context;
     const int32_t* language_ids;
     int n_language;
+    /* != 0: language_ids are appended verbatim after "<|im_start|>assistant\n" and the <asr_text> token is NOT added — the forced
+     * aligner's template (ForcedAligner.swift:338-378), whose suffix is the timestamp-slotted text */
+    int raw_suffix;
 } q3asr_prompt;
 
 /* Batched greedy transcription.  ids_out: [batch, max_tokens] int32; lens_out: [batch].
@@ -142,6 +150,23 @@ int q3asr_batch_set_sampling(q3asr_handle* h, const q3asr_sampling* sampling);
  * Tests/Qwen3ASRTests/Qwen3DecodingOptionsTests.swift:47-235).  draw selects the noise draw (the decode step). */
 int q3asr_pick_next_token(q3asr_handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated,
                           const q3asr_sampling* sampling, int draw, int32_t* token);
+
+/* ---- forced aligner (Qwen3ForcedAligner.align, ForcedAligner.swift:226-331) ---- */
+/* One prefill pass per utterance over "<system><user><audio><assistant>" + slotted text, no decode loop: the classification head
+ * (bf16 logits = h W^T + b over classify_num classes) is applied at the given positions of the slotted text (indices into
+ * slotted_ids, normally the <|timestamp|> slots) and the argmax class (lowest index on ties) is written to
+ * raw_indices_out[i][0..n_positions[i]).  Needs a configuration with classify_num > 0.  Time = index * 0.08 s after
+ * q3asr_enforce_monotonicity. */
+int q3asr_align_indices(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                        const int32_t* const* slotted_ids, const int* n_slotted, const int* const* positions, const int* n_positions,
+                        int32_t* const* raw_indices_out);
+/* TimestampCorrection (Sources/Qwen3ASR/TimestampCorrection.swift:15-145), host only: LIS anchors, nearest-neighbour / linear
+ * fill of the other positions, final non-decreasing pass.  Pinned by the reference's ForcedAlignerTests.swift:213-259. */
+int q3asr_enforce_monotonicity(const int* raw, int n, int* corrected);
+int q3asr_lis_positions(const int* values, int n, int* positions, int* count);
+/* Qwen3ForcedAligner.findTrailingPlateauStart (ForcedAligner.swift:191-216): first word of the trailing run of >= min_size words
+ * whose start times differ by < tolerance, or n when there is none */
+int q3asr_trailing_plateau_start(const float* start_times, int n, float tolerance, int min_size);
 
 /* Teacher-forced scoring (parity on a prescribed token stream): the decoder consumes forced[0..n) as its
  * own outputs; argmax_out[i] / top_out[i] are the argmax id and its bf16 logit at step i (i = 0 is the

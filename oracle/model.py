@@ -189,7 +189,7 @@ class Oracle:
         out = torch.cat([a * cs - b * sn, b * cs + a * sn], dim=-1)
         return self.r(out.reshape(x.shape[0], heads * hd))
 
-    def _decoder_forward(self, x, cache):
+    def _decoder_forward(self, x, cache, rows=None):
         """x [T, h] new token embeddings; cache: list of (K, V) per layer (or None).  Returns final-norm hidden
         of the LAST position and the new cache."""
         c = self.cfg
@@ -223,6 +223,8 @@ class Oracle:
             u = r(xn @ W("mlp.up_proj.weight").t())
             act = r(r(F.silu(g)) * u)
             x = r(x + r(act @ W("mlp.down_proj.weight").t()))
+        if rows is not None:  # final norm of the requested rows (the forced aligner classifies several positions of one pass)
+            return self._rmsnorm(x[torch.tensor(list(rows), dtype=torch.long)], self.w["model.norm.weight"], eps), new_cache
         last = self._rmsnorm(x[-1:], self.w["model.norm.weight"], eps)
         return last, new_cache
 
@@ -261,6 +263,32 @@ class Oracle:
             last, cache = self._decoder_forward(E[nxt:nxt + 1].clone(), cache)
             logits = self._logits(last)
         return np.array(ids, dtype=np.int32), np.array(tops, dtype=np.float32), np.array(margins, dtype=np.float32)
+
+    def align_indices(self, audio_embeds, slotted_ids, positions):
+        """Qwen3ForcedAligner.align steps 3-7 (ForcedAligner.swift:257-299): the aligner template (:338-378: empty system turn,
+        audio, assistant turn, then the slotted text and no <asr_text>), one causal pass, classification head (Linear with bias,
+        WeightLoading.swift:229) at the given positions of the slotted text, first-maximum class.
+        Returns (raw indices, per-position margin between the two best logits, best logit)."""
+        c = self.cfg
+        n_audio = audio_embeds.shape[0]
+        ids = [c["tok_im_start"], c["tok_system"], c["tok_newline"], c["tok_im_end"], c["tok_newline"],
+               c["tok_im_start"], c["tok_user"], c["tok_newline"], c["tok_audio_start"]]
+        at = len(ids)
+        ids += [c["tok_audio_pad"]] * n_audio
+        ids += [c["tok_audio_end"], c["tok_im_end"], c["tok_newline"], c["tok_im_start"], c["tok_assistant"], c["tok_newline"]]
+        start = len(ids)
+        ids += [int(t) for t in slotted_ids]
+        E = self.w["model.embed_tokens.weight"]
+        x = E[torch.tensor(ids, dtype=torch.long)].clone()
+        x[at:at + n_audio] = self.r(torch.from_numpy(np.ascontiguousarray(audio_embeds, dtype=np.float32)))
+        hsel, _ = self._decoder_forward(x, None, rows=[start + int(p) for p in positions])
+        logits = self.r(hsel @ self.w["lm_head.weight"].t() + self.w["lm_head.bias"])
+        top2 = torch.topk(logits, 2, dim=-1).values
+        raw = []
+        for r in range(logits.shape[0]):
+            mx = logits[r].max()
+            raw.append(int(torch.nonzero(logits[r] == mx).min()))
+        return np.array(raw, dtype=np.int32), (top2[:, 0] - top2[:, 1]).numpy(), top2[:, 0].numpy()
 
     def generate_slow(self, audio_embeds, max_tokens, repetition_penalty=1.0, no_repeat_ngram_size=0, stop_on_eos=True):
         """Qwen3ASR.swift:396-447 (generateSlow) with pickNextToken (oracle/sampler.py) on every step's logits; temperature 0

@@ -88,6 +88,8 @@ def tensor_specs(cfg):
                 (p + "input_layernorm.weight", (h,)), (p + "post_attention_layernorm.weight", (h,)),
                 (p + "mlp.gate_proj.weight", (I, h)), (p + "mlp.up_proj.weight", (I, h)), (p + "mlp.down_proj.weight", (h, I))]
     out.append(("model.norm.weight", (h,)))
+    if cfg.get("classify_num", 0) > 0:  # the forced aligner's classification head keeps the lm_head.* keys (WeightLoading.swift:177-179)
+        out += [("lm_head.weight", (cfg["classify_num"], h)), ("lm_head.bias", (cfg["classify_num"],))]
     return out
 
 
@@ -109,16 +111,21 @@ def preset(name):
     c = dict(enc_conv_ch=480, enc_n_window=50, enc_n_window_infer=800, enc_ln_eps=1e-5, dec_vocab=151936, dec_layers=28,
              dec_heads=16, dec_kv_heads=8, dec_head_dim=128, dec_rope_theta=1e6, dec_rms_eps=1e-6,
              tok_im_start=151644, tok_im_end=151645, tok_audio_start=151669, tok_audio_end=151670, tok_audio_pad=151676,
-             tok_asr_text=151704, tok_newline=198, tok_system=8948, tok_user=872, tok_assistant=77091, tok_eos=151645)
+             tok_asr_text=151704, tok_newline=198, tok_system=8948, tok_user=872, tok_assistant=77091, tok_eos=151645,
+             classify_num=0, tok_timestamp=151705)
     if name == "0.6B":
         c.update(enc_d_model=896, enc_heads=14, enc_ffn=3584, enc_layers=18, enc_out_dim=1024, dec_hidden=1024, dec_inter=3072)
     elif name == "1.7B":
         c.update(enc_d_model=1024, enc_heads=16, enc_ffn=4096, enc_layers=24, enc_out_dim=2048, dec_hidden=2048, dec_inter=6144)
-    elif name == "tiny":
+    elif name == "aligner":  # AudioEncoder.swift:71-88 + TextDecoderConfig.small + 5000 classes (Configuration.swift:132)
+        c.update(enc_d_model=1024, enc_heads=16, enc_ffn=4096, enc_layers=24, enc_out_dim=1024, dec_hidden=1024, dec_inter=3072,
+                 classify_num=5000)
+    elif name in ("tiny", "tiny-aligner"):
         c.update(enc_d_model=128, enc_heads=2, enc_ffn=256, enc_layers=2, enc_out_dim=128, enc_conv_ch=32, dec_vocab=2048,
                  dec_hidden=128, dec_layers=2, dec_heads=4, dec_kv_heads=2, dec_inter=256, tok_im_start=2001, tok_im_end=2002,
                  tok_audio_start=2003, tok_audio_end=2004, tok_audio_pad=2005, tok_asr_text=2006, tok_newline=198,
-                 tok_system=1948, tok_user=872, tok_assistant=1091, tok_eos=2002)
+                 tok_system=1948, tok_user=872, tok_assistant=1091, tok_eos=2002, tok_timestamp=2007,
+                 classify_num=70 if name == "tiny-aligner" else 0)
     else:
         raise ValueError(name)
     return c

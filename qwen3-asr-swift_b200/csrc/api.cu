@@ -51,6 +51,7 @@ void set_common_tokens(q3asr_config* c) {
     c->tok_user = 872;
     c->tok_assistant = 77091;
     c->tok_eos = Q3ASR_EOS_TOKEN;
+    c->tok_timestamp = 151705;
 }
 
 }  // namespace
@@ -81,7 +82,11 @@ int q3asr_config_preset(const char* name, q3asr_config* c) {
     } else if (n == "1.7B" || n == "large") {
         c->enc_d_model = 1024; c->enc_heads = 16; c->enc_ffn = 4096; c->enc_layers = 24; c->enc_out_dim = 2048;
         c->dec_hidden = 2048; c->dec_inter = 6144;
-    } else if (n == "tiny") {
+    } else if (n == "aligner") {  // Qwen3AudioEncoderConfig.forcedAligner (AudioEncoder.swift:71-88) + TextDecoderConfig.small + 5000 classes
+        c->enc_d_model = 1024; c->enc_heads = 16; c->enc_ffn = 4096; c->enc_layers = 24; c->enc_out_dim = 1024;
+        c->dec_hidden = 1024; c->dec_inter = 3072;
+        c->classify_num = 5000;
+    } else if (n == "tiny" || n == "tiny-aligner") {
         // small enough for the CPU oracle to finish in seconds; same graph, same kernels
         c->enc_d_model = 128; c->enc_heads = 2; c->enc_ffn = 256; c->enc_layers = 2; c->enc_out_dim = 128;
         c->enc_conv_ch = 32;
@@ -89,7 +94,8 @@ int q3asr_config_preset(const char* name, q3asr_config* c) {
         c->dec_inter = 256;
         c->tok_im_start = 2001; c->tok_im_end = 2002; c->tok_audio_start = 2003; c->tok_audio_end = 2004;
         c->tok_audio_pad = 2005; c->tok_asr_text = 2006; c->tok_newline = 198; c->tok_system = 1948; c->tok_user = 872;
-        c->tok_assistant = 1091; c->tok_eos = 2002;
+        c->tok_assistant = 1091; c->tok_eos = 2002; c->tok_timestamp = 2007;
+        if (n == "tiny-aligner") c->classify_num = 70;  // not a multiple of the GEMM tile: exercises the padded head
     } else {
         return Q3ASR_ERR_INVALID;
     }
@@ -291,6 +297,11 @@ int q3asr_transcribe_ids_opts(q3asr_handle* h, const float* const* pcm, const si
 int q3asr_pick_next_token(q3asr_handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated,
                           const q3asr_sampling* opts, int draw, int32_t* token) {
     return guarded(h, [&](Handle& x) { pick_next_token(&x, logits, vocab, generated, n_generated, opts, draw, token); });
+}
+int q3asr_align_indices(q3asr_handle* h, const float* const* pcm, const size_t* n, const int* sample_rates, int batch,
+                        const int32_t* const* slotted_ids, const int* n_slotted, const int* const* positions, const int* n_positions,
+                        int32_t* const* raw_out) {
+    return guarded(h, [&](Handle& x) { align_indices(&x, pcm, n, sample_rates, batch, slotted_ids, n_slotted, positions, n_positions, raw_out); });
 }
 int q3asr_resample(q3asr_handle* h, const float* in, size_t n, int in_rate, int out_rate, float* out, size_t cap, size_t* n_out) {
     return guarded(h, [&](Handle& x) { resample_host(&x, in, n, in_rate, out_rate, out, cap, n_out); });

@@ -49,7 +49,7 @@ void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::
     ids->insert(ids->end(), (size_t)ntok, c.tok_audio_pad);
     ids->insert(ids->end(), {c.tok_audio_end, c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_assistant, c.tok_newline});
     if (pr && pr->language_ids && pr->n_language > 0) ids->insert(ids->end(), pr->language_ids, pr->language_ids + pr->n_language);
-    ids->push_back(c.tok_asr_text);
+    if (!(pr && pr->raw_suffix)) ids->push_back(c.tok_asr_text);  // the aligner's template ends with the slotted text (ForcedAligner.swift:338-378)
 }
 
 BatchState* fresh_batch(Handle* h) {
@@ -767,6 +767,73 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
                                 bs->pcm.as<float>() + bs->mel.clips[b].in_off, n[b], h->stream);
     upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
     bs->prompt_ids.clear();
+}
+
+// Qwen3ForcedAligner.align (ForcedAligner.swift:226-331), batched: mel -> encoder -> one causal prefill over the aligner template ->
+// final RMSNorm of the requested rows only -> classification head (+bias, bf16 logits) -> first-maximum class per row.
+void align_indices(Handle* h, const float* const* pcm, const size_t* n, const int* rates, int batch, const int32_t* const* slotted_ids,
+                   const int* n_slotted, const int* const* positions, const int* n_positions, int32_t* const* raw_out) {
+    const q3asr_config& c = h->cfg;
+    Q3_CHECK(c.classify_num > 0, Q3ASR_ERR_STATE, "align: this configuration has no classification head (classify_num == 0)");
+    Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded");
+    Q3_CHECK(slotted_ids && n_slotted && positions && n_positions && raw_out && batch > 0, Q3ASR_ERR_INVALID, "align: null argument");
+    std::vector<q3asr_prompt> prompts((size_t)batch);
+    for (int b = 0; b < batch; b++) {
+        Q3_CHECK(slotted_ids[b] != nullptr && n_slotted[b] > 0 && n_positions[b] >= 0 && (n_positions[b] == 0 || (positions[b] && raw_out[b])),
+                 Q3ASR_ERR_INVALID, "align: empty slotted text / null positions");
+        for (int i = 0; i < n_positions[b]; i++)
+            Q3_CHECK(positions[b][i] >= 0 && positions[b][i] < n_slotted[b], Q3ASR_ERR_INVALID, "align: position outside the slotted text");
+        prompts[(size_t)b] = q3asr_prompt{nullptr, 0, slotted_ids[b], n_slotted[b], 1};
+    }
+    batch_upload(h, pcm, n, batch, prompts.data(), rates);
+    BatchState* bs = h->batch.get();
+    cudaStream_t st = h->stream;
+    run_mel(h, bs);
+    reserve_encoder(h, bs);
+    run_encoder(h, bs, bs->mel_out.as<float>());
+    reserve_decoder(h, bs);
+    const Model& m = *h->model;
+    embed_splice_launch(bs->ints.as<int>() + bs->o_ids, bs->ints.as<int>() + bs->o_audio_src, m.embed, bs->audio.as<bf16>(), bs->dx.as<bf16>(),
+                        bs->R, c.dec_hidden, st);
+    h->launches++;
+    decoder_layers(h, bs, bs->R, true);
+    // rows of the requested positions: prompt row0 + (prompt_len - n_slotted) + position
+    std::vector<int> rows;
+    for (int b = 0; b < batch; b++)
+        for (int i = 0; i < n_positions[b]; i++) rows.push_back(bs->clips[b].row0 + bs->clips[b].prompt_len - n_slotted[b] + positions[b][i]);
+    const int P = (int)rows.size();
+    if (P == 0) {
+        Q3_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    const int H = c.dec_hidden, NP = m.cls_pad;
+    // scratch: [rows | gen_len zeros | tokens] ints, normed rows, bf16 logits
+    bs->amax_idx.reserve(sizeof(int) * (size_t)(3 * P + 4));
+    int* d_rows = bs->amax_idx.as<int>();
+    int* d_zero = d_rows + P;
+    int32_t* d_tok = reinterpret_cast<int32_t*>(d_zero + P);
+    bs->h_ints.reserve(sizeof(int) * (size_t)(3 * P + 4));
+    int* hrows = bs->h_ints.as<int>();
+    for (int i = 0; i < P; i++) { hrows[i] = rows[(size_t)i]; hrows[P + i] = 0; }
+    Q3_CUDA(cudaMemcpyAsync(d_rows, hrows, sizeof(int) * 2 * P, cudaMemcpyHostToDevice, st));
+    bs->dlast.reserve((size_t)P * H * sizeof(bf16));
+    bs->logits_bf.reserve((size_t)P * NP * sizeof(bf16));
+    rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), P, H, c.dec_rms_eps, d_rows, st);
+    h->launches++;
+    GemmEpiArgs e;
+    e.epi = EPI_NORMAL;
+    e.out = bs->logits_bf.p;
+    e.ldo = NP;
+    e.bias = m.cls_b;
+    gemm(bs->dlast.as<bf16>(), H, P, H, m.cls_w, NP, e, st);
+    SamplingParams greedy;
+    sample_launch(bs->logits_bf.as<bf16>(), nullptr, NP, c.classify_num, d_tok, 1, d_zero, greedy, nullptr, P, d_tok, nullptr, st);
+    h->launches++;
+    Q3_CUDA(cudaMemcpyAsync(hrows + 2 * P, d_tok, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, st));
+    Q3_CUDA(cudaStreamSynchronize(st));
+    int k = 0;
+    for (int b = 0; b < batch; b++)
+        for (int i = 0; i < n_positions[b]; i++) raw_out[b][i] = hrows[2 * P + k++];
 }
 
 void batch_set_sampling(Handle* h, const q3asr_sampling* opts) {

@@ -194,6 +194,8 @@ void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* pr
                    int32_t* argmax_out, float* top_out);
 void prefill_logits(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits);
 void config_validate(const q3asr_config& c);
+void align_indices(Handle* h, const float* const* pcm, const size_t* n, const int* rates, int batch, const int32_t* const* slotted_ids,
+                   const int* n_slotted, const int* const* positions, const int* n_positions, int32_t* const* raw_out);
 
 // ---- front door (audio_io.cu) ----
 size_t wav_parse(const uint8_t* data, size_t size, float* out, size_t cap, int* sample_rate);

@@ -23,6 +23,9 @@ struct Model {
     bf16* embed;
     std::vector<DecLayerW> dec;
     bf16* final_norm;
+    // forced aligner: classification head padded with zero rows to a multiple of 64 classes (GEMM tile width)
+    bf16 *cls_w = nullptr, *cls_b = nullptr;
+    int cls_pad = 0;
     float* inv_freq = nullptr;  // [head_dim/2]
     std::vector<void*> owned;   // derived device buffers
     size_t owned_bytes = 0;

@@ -121,6 +121,7 @@ void config_validate(const q3asr_config& c) {
     Q3_CHECK(c.dec_hidden == c.enc_out_dim, Q3ASR_ERR_INVALID, "encoder output dim must equal decoder hidden size");
     Q3_CHECK(c.dec_heads % c.dec_kv_heads == 0 && (c.dec_heads / c.dec_kv_heads) <= 2, Q3ASR_ERR_INVALID, "GQA group must be 1 or 2");
     Q3_CHECK(c.dec_vocab % 128 == 0 && c.dec_layers > 0, Q3ASR_ERR_INVALID, "vocab must be a multiple of 128");
+    Q3_CHECK(c.classify_num >= 0 && c.classify_num <= 65536, Q3ASR_ERR_INVALID, "classify_num out of range");
 }
 
 void model_tensor_specs(const q3asr_config& c, std::vector<std::pair<std::string, std::vector<int64_t>>>* out) {
@@ -172,6 +173,10 @@ void model_tensor_specs(const q3asr_config& c, std::vector<std::pair<std::string
         add(p + "mlp.down_proj.weight", {h, I});
     }
     add("model.norm.weight", {h});
+    if (c.classify_num > 0) {  // WeightLoading.swift:177-179, 229: the aligner's head keeps the lm_head.* keys
+        add("lm_head.weight", {(int64_t)c.classify_num, h});
+        add("lm_head.bias", {(int64_t)c.classify_num});
+    }
 }
 
 // bf16(0.02 * approx-normal) for weights and biases, 1 for norm scales.  The generator is integer-only up
@@ -358,6 +363,15 @@ void model_commit(Handle* h) {
         // rows of tile t: a 2-D copy with destination pitch 2*half rows
         copy_rows(e.gu_w, (size_t)2 * half * hdim, gw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
         copy_rows(e.gu_w + (size_t)half * hdim, (size_t)2 * half * hdim, uw, (size_t)half * hdim, I / half, (size_t)half * hdim, st);
+    }
+    if (c.classify_num > 0) {
+        m->cls_pad = (c.classify_num + 63) / 64 * 64;
+        m->cls_w = dev_alloc<bf16>(m, (size_t)m->cls_pad * hdim, &h->dev_bytes);
+        m->cls_b = dev_alloc<bf16>(m, (size_t)m->cls_pad, &h->dev_bytes);
+        Q3_CUDA(cudaMemsetAsync(m->cls_w, 0, (size_t)m->cls_pad * hdim * 2, st));
+        Q3_CUDA(cudaMemsetAsync(m->cls_b, 0, (size_t)m->cls_pad * 2, st));
+        Q3_CUDA(cudaMemcpyAsync(m->cls_w, W("lm_head.weight"), (size_t)c.classify_num * hdim * 2, cudaMemcpyDeviceToDevice, st));
+        Q3_CUDA(cudaMemcpyAsync(m->cls_b, W("lm_head.bias"), (size_t)c.classify_num * 2, cudaMemcpyDeviceToDevice, st));
     }
     {
         std::vector<float> inv(hd / 2);

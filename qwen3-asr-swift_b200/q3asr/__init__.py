@@ -37,7 +37,8 @@ class Config(ctypes.Structure):
             "dec_vocab", "dec_hidden", "dec_layers", "dec_heads", "dec_kv_heads", "dec_head_dim", "dec_inter")] + [
                 ("dec_rope_theta", ctypes.c_float), ("dec_rms_eps", ctypes.c_float)] + [(n, ctypes.c_int32) for n in (
                     "tok_im_start", "tok_im_end", "tok_audio_start", "tok_audio_end", "tok_audio_pad", "tok_asr_text",
-                    "tok_newline", "tok_system", "tok_user", "tok_assistant", "tok_eos")]
+                    "tok_newline", "tok_system", "tok_user", "tok_assistant", "tok_eos")] + [
+                        ("classify_num", ctypes.c_int), ("tok_timestamp", ctypes.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -45,7 +46,7 @@ class Config(ctypes.Structure):
 
 class Prompt(ctypes.Structure):
     _fields_ = [("context_ids", ctypes.POINTER(ctypes.c_int32)), ("n_context", ctypes.c_int),
-                ("language_ids", ctypes.POINTER(ctypes.c_int32)), ("n_language", ctypes.c_int)]
+                ("language_ids", ctypes.POINTER(ctypes.c_int32)), ("n_language", ctypes.c_int), ("raw_suffix", ctypes.c_int)]
 
 
 class Sampling(ctypes.Structure):
@@ -87,6 +88,7 @@ EXPORTS = [
     "q3asr_io_last_error", "q3asr_wav_parse", "q3asr_wav_load", "q3asr_resample_len", "q3asr_resample", "q3asr_resample_design",
     "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
     "q3asr_transcribe_ids_opts", "q3asr_batch_set_sampling", "q3asr_pick_next_token",
+    "q3asr_align_indices", "q3asr_enforce_monotonicity", "q3asr_lis_positions", "q3asr_trailing_plateau_start",
 ]
 
 _lib = None
@@ -171,6 +173,10 @@ def lib():
         L.q3asr_longform_plan.argtypes = [cs, cs, cs, vp, vp, ci, ctypes.POINTER(ci)]
         L.q3asr_transcribe_ids_opts.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(Sampling), ci, ci, vp, vp]
         L.q3asr_batch_set_sampling.argtypes = [vp, ctypes.POINTER(Sampling)]
+        L.q3asr_align_indices.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+        L.q3asr_enforce_monotonicity.argtypes = [vp, ci, vp]
+        L.q3asr_lis_positions.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
+        L.q3asr_trailing_plateau_start.argtypes = [vp, ci, ctypes.c_float, ci]
         L.q3asr_pick_next_token.argtypes = [vp, vp, ci, vp, ci, ctypes.POINTER(Sampling), ci, ctypes.POINTER(ctypes.c_int32)]
         _lib = L
     return _lib
@@ -248,6 +254,33 @@ class AudioFileLoader:
         AudioFileLoader._finish(lib().q3asr_resample_design(int(in_rate), int(out_rate), ctypes.byref(L), ctypes.byref(M), ctypes.byref(K),
                                                             taps.ctypes.data, taps.size, ctypes.byref(nt)))
         return L.value, M.value, K.value, taps.reshape(L.value, 2 * K.value + 2)
+
+
+def enforce_monotonicity(raw_indices):
+    """TimestampCorrection.enforceMonotonicity (TimestampCorrection.swift:15-98)."""
+    a = np.ascontiguousarray(raw_indices, dtype=np.int32)
+    out = np.empty_like(a)
+    rc = lib().q3asr_enforce_monotonicity(a.ctypes.data if a.size else None, a.size, out.ctypes.data if a.size else None)
+    if rc != OK:
+        raise Q3Error(rc, "enforce_monotonicity: bad argument")
+    return out.tolist()
+
+
+def lis_positions(values):
+    """TimestampCorrection.longestIncreasingSubsequencePositions (TimestampCorrection.swift:101-144)."""
+    a = np.ascontiguousarray(values, dtype=np.int32)
+    out = np.empty(max(a.size, 1), dtype=np.int32)
+    cnt = ctypes.c_int()
+    rc = lib().q3asr_lis_positions(a.ctypes.data if a.size else None, a.size, out.ctypes.data, ctypes.byref(cnt))
+    if rc != OK:
+        raise Q3Error(rc, "lis_positions: bad argument")
+    return out[:cnt.value].tolist()
+
+
+def trailing_plateau_start(start_times, tolerance=0.1, min_size=5):
+    """Qwen3ForcedAligner.findTrailingPlateauStart (ForcedAligner.swift:191-216)."""
+    a = np.ascontiguousarray(start_times, dtype=np.float32)
+    return int(lib().q3asr_trailing_plateau_start(a.ctypes.data if a.size else None, a.size, float(tolerance), int(min_size)))
 
 
 def longform_plan(n_samples, window, min_tail=160):
@@ -445,6 +478,46 @@ class Qwen3ASRModel:
         self._ck(lib().q3asr_pick_next_token(self._h, lg.ctypes.data, lg.size, gen.ctypes.data if gen.size else None, gen.size,
                                              ctypes.byref(samp), int(draw), ctypes.byref(tok)))
         return int(tok.value)
+
+    TIMESTAMP_SEGMENT_TIME = 0.08  # Configuration.swift:133
+
+    def align_indices(self, clips, slotted_ids, positions, sample_rates=None):
+        """Qwen3ForcedAligner.align, steps 1-7 (ForcedAligner.swift:226-299), batched: one prefill per clip over the aligner template
+        ending in slotted_ids[i]; the classification head's argmax at positions[i] (indices into slotted_ids[i])."""
+        clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        B = len(clips)
+        n = np.array([c.size for c in clips], dtype=np.uint64)
+        sl = [np.ascontiguousarray(x, dtype=np.int32) for x in slotted_ids]
+        ps = [np.ascontiguousarray(x, dtype=np.int32) for x in positions]
+        outs = [np.zeros(max(p.size, 1), dtype=np.int32) for p in ps]
+        nsl = np.array([x.size for x in sl], dtype=np.int32)
+        nps = np.array([x.size for x in ps], dtype=np.int32)
+        sr = None if sample_rates is None else np.ascontiguousarray(sample_rates, dtype=np.int32)
+        self._ck(lib().q3asr_align_indices(self._h, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data,
+                                           sr.ctypes.data if sr is not None else None, B, ctypes.cast(_ptr_array(sl), ctypes.c_void_p),
+                                           nsl.ctypes.data, ctypes.cast(_ptr_array(ps), ctypes.c_void_p), nps.ctypes.data,
+                                           ctypes.cast(_ptr_array(outs), ctypes.c_void_p)))
+        return [o[:p.size].copy() for o, p in zip(outs, ps)]
+
+    def align(self, audio, word_token_ids, words=None, sample_rate=16000):
+        """Qwen3ForcedAligner.align for text already split into words and tokenised (the reference's word splitter needs Apple's
+        NaturalLanguage framework, TextPreprocessing.swift:2): <|timestamp|> slots around every word (TextPreprocessing.swift:48-80),
+        argmax classes, LIS fix-up, 0.08 s per class, end >= start (ForcedAligner.swift:301-330).
+        Returns [dict(text, start_time, end_time)]."""
+        ts = int(self.cfg.tok_timestamp)
+        ids, pos = [], []
+        for w in word_token_ids:
+            pos.append(len(ids)); ids.append(ts)
+            ids.extend(int(t) for t in w)
+            pos.append(len(ids)); ids.append(ts)
+        raw = self.align_indices([audio], [ids], [pos], None if sample_rate == 16000 else [sample_rate])[0]
+        fixed = enforce_monotonicity(raw)
+        out = []
+        for i in range(len(word_token_ids)):
+            st = np.float32(fixed[2 * i]) * np.float32(self.TIMESTAMP_SEGMENT_TIME)
+            en = np.float32(fixed[2 * i + 1]) * np.float32(self.TIMESTAMP_SEGMENT_TIME)
+            out.append(dict(text=words[i] if words else "", start_time=float(st), end_time=float(max(en, st))))
+        return out
 
     def resample(self, samples, in_rate, out_rate):
         """AudioFileLoader.resample (AudioFileLoader.swift:159-213) on the GPU: float32 [n] -> float32 [floor(n * out / in)]."""

@@ -1,0 +1,117 @@
+"""Forced aligner: the timestamp-correction integer code against the reference's own unit tests
+(Tests/Qwen3ASRTests/ForcedAlignerTests.swift:213-259, 441-492; C ABI and oracle restatement, no GPU), and the device path
+(one prefill + classification head + argmax at the timestamp slots) against the oracle."""
+import numpy as np
+import pytest
+
+import q3asr
+from oracle import mel as omel
+from oracle import synth
+from oracle import timestamps as ots
+
+IMPLS = [("c_abi", q3asr.enforce_monotonicity, q3asr.lis_positions, q3asr.trailing_plateau_start),
+         ("oracle", ots.enforce_monotonicity, ots.lis_positions, ots.trailing_plateau_start)]
+
+
+@pytest.mark.parametrize("name,fix,lis,plateau", IMPLS)
+def test_timestamp_correction_reference_cases(name, fix, lis, plateau):
+    assert fix([1, 3, 5, 7, 9, 11]) == [1, 3, 5, 7, 9, 11]                    # testTimestampCorrectionAlreadyMonotonic
+    out = fix([1, 3, 2, 7, 9, 11])                                             # testTimestampCorrectionSingleOutOfOrder
+    assert all(b >= a for a, b in zip(out, out[1:]))
+    assert fix([5, 5, 5, 5]) == [5, 5, 5, 5]                                   # testTimestampCorrectionAllSame
+    out = fix([10, 8, 6, 4, 2])                                                # testTimestampCorrectionDescending
+    assert all(b >= a for a, b in zip(out, out[1:]))
+    arr = [3, 1, 4, 1, 5, 9, 2, 6]                                             # testLISBasic
+    pos = lis(arr)
+    assert len(pos) >= 4 and all(arr[a] < arr[b] for a, b in zip(pos, pos[1:]))
+    assert fix([]) == [] and fix([7]) == [7] and lis([]) == []
+
+
+@pytest.mark.parametrize("name,fix,lis,plateau", IMPLS)
+def test_trailing_plateau_reference_cases(name, fix, lis, plateau):
+    healthy = [0.5 * i for i in range(20)]                                     # testNoPlateauOnHealthyAlignment
+    assert plateau(healthy, 0.1, 5) == 20
+    assert plateau([0.5 * i for i in range(15)] + [12.0] * 10, 0.1, 5) == 15   # testTrailingPlateauDetected
+    assert plateau([0.5 * i for i in range(10)] + [6.0] * 3, 0.1, 5) == 13     # testPlateauBelowMinSizeIgnored
+    assert plateau([0.5 * i for i in range(10)] + [6.0 + 0.05 * i for i in range(8)], 0.1, 5) == 10  # testToleranceAcceptsTinyDrift
+
+
+def test_timestamp_correction_c_matches_oracle_on_random_input():
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n = int(rng.integers(0, 60))
+        mode = int(rng.integers(0, 3))
+        if mode == 0:
+            raw = rng.integers(0, 5000, size=n)
+        elif mode == 1:   # mostly increasing with outliers: what the aligner produces
+            raw = np.sort(rng.integers(0, 5000, size=n))
+            k = rng.integers(0, n + 1, size=max(1, n // 5))
+            raw[k[k < n]] = rng.integers(0, 5000, size=int((k < n).sum()))
+        else:             # a good prefix, then garbage (the plateau case of alignLong)
+            raw = np.concatenate([np.sort(rng.integers(0, 3000, size=n // 2)), rng.integers(0, 50, size=n - n // 2)])
+        raw = [int(v) for v in raw]
+        c, o = q3asr.enforce_monotonicity(raw), ots.enforce_monotonicity(raw)
+        assert c == o, (raw, c, o)
+        assert all(b >= a for a, b in zip(c, c[1:]))
+        assert q3asr.lis_positions(raw) == ots.lis_positions(raw)
+        t = (np.array(c, dtype=np.float32) * np.float32(0.08)).tolist()
+        assert q3asr.trailing_plateau_start(t, 0.1, 5) == ots.trailing_plateau_start(t, 0.1, 5)
+
+
+# ---- GPU: the classification pass ----
+@pytest.fixture(scope="module")
+def aligner(built_lib):
+    m = built_lib.Qwen3ASRModel.random_init("tiny-aligner", seed=20260418)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def aligner_oracle():
+    from oracle import model, weights
+    cfg = weights.preset("tiny-aligner")
+    return model.Oracle(cfg, weights.random_state_dict(cfg, 20260418))
+
+
+def _slotted(rng, n_words, ts):
+    ids, pos = [], []
+    for _ in range(n_words):
+        pos.append(len(ids)); ids.append(ts)
+        ids += rng.integers(3, 1900, size=int(rng.integers(1, 4))).tolist()
+        pos.append(len(ids)); ids.append(ts)
+    return ids, pos
+
+
+@pytest.mark.gpu
+def test_gpu_align_indices_match_oracle(aligner, aligner_oracle):
+    rng = np.random.default_rng(3)
+    clips = [synth.clip(i, n) for i, n in enumerate([16000 * 3 + 500, 16000, 16000 * 2])]
+    sl = [_slotted(rng, k, 2007) for k in (7, 3, 12)]
+    got = aligner.align_indices(clips, [s[0] for s in sl], [s[1] for s in sl])
+    checked = 0
+    for x, (ids, pos), g in zip(clips, sl, got):
+        raw, margins, tops = aligner_oracle.align_indices(aligner_oracle.encode(omel.mel(x)), ids, pos)
+        assert g.shape == raw.shape and (g >= 0).all() and (g < 70).all()
+        ulp2 = np.maximum(np.abs(tops), 2.0 ** -6) * 2.0 ** -6   # two bf16 ulps of the winning logit: closer calls are not defined by the contract
+        safe = margins > ulp2
+        assert np.array_equal(g[safe], raw[safe]), (g.tolist(), raw.tolist(), margins.tolist())
+        checked += int(safe.sum())
+    assert checked >= 30, checked
+    # a clip alone gives the same classes as inside the batch; other sample rates are converted on the device
+    solo = aligner.align_indices(clips[1:2], [sl[1][0]], [sl[1][1]])[0]
+    assert solo.tolist() == got[1].tolist()
+
+
+@pytest.mark.gpu
+def test_gpu_align_words_and_errors(aligner, tiny_model):
+    rng = np.random.default_rng(4)
+    words = [rng.integers(3, 1900, size=2).tolist() for _ in range(6)]
+    out = aligner.align(synth.clip(2, 16000 * 4), words, words=[f"w{i}" for i in range(6)])
+    assert [w["text"] for w in out] == [f"w{i}" for i in range(6)]
+    starts = [w["start_time"] for w in out]
+    assert all(b >= a for a, b in zip(starts, starts[1:])) and all(w["end_time"] >= w["start_time"] for w in out)
+    assert all(abs(w["start_time"] / 0.08 - round(w["start_time"] / 0.08)) < 1e-3 for w in out)
+    with pytest.raises(q3asr.Q3Error, match="classification head"):
+        tiny_model.align_indices([synth.clip(0, 16000)], [[2007, 5, 2007]], [[0, 2]])
+    with pytest.raises(q3asr.Q3Error, match="outside the slotted text"):
+        aligner.align_indices([synth.clip(0, 16000)], [[2007, 5, 2007]], [[0, 3]])
