@@ -355,10 +355,11 @@ template <int NB, int EPI>
 void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB)));
+        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     std::min(227 * 1024, sk_smem_bytes(NB, SK_MAX_STAGES))));
         attr_set = true;
     }
-    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB), st, tw, tx, p);
+    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB, p.stages), st, tw, tx, p);
 }
 template <int NB>
 void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
@@ -389,6 +390,18 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
     p.num_kb = cdiv(K, SK_BK);
     const int splits = gemm_skinny_splits(N, K, epi);
     p.kb_per_split = cdiv(p.num_kb, splits);
+    {
+        // ring depth: see skinny.cuh.  Q3ASR_SK_STAGES / Q3ASR_SK_DEEP_KB override the policy (tuning)
+        static const int force = getenv("Q3ASR_SK_STAGES") ? atoi(getenv("Q3ASR_SK_STAGES")) : 0;
+        static const int deep_kb = getenv("Q3ASR_SK_DEEP_KB") ? atoi(getenv("Q3ASR_SK_DEEP_KB")) : 8;
+        const int max_fit = std::min(SK_MAX_STAGES, (200 * 1024) / sk_stage_bytes(nb));
+        int stages = sk_stages(nb);
+        // a long K slice is bandwidth-bound: half as many bytes again in flight (measured on 1.7B, 64 sequences: 63.3 -> 60.8 us per
+        // layer with 6 stages, 61.5 with 8; 0.6B, whose slices are 2-4 blocks, is fastest at 4)
+        if (p.kb_per_split >= deep_kb) stages = std::min(max_fit, stages + stages / 2);
+        if (force > 0) stages = force;
+        p.stages = std::max(1, std::min(std::min(stages, max_fit), std::max(p.kb_per_split, 1)));
+    }
     p.out = out;
     p.ldo = ldo;
     p.split_stride = (long long)Mtok * N;

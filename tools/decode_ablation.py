@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timing ablation of the decode step (debug): drops one kernel of the layer at a time (Q3ASR_DEC_SKIP bit mask; results
-are wrong while a bit is set) and reports the decode-stage time per step.  Usage: python tools/decode_ablation.py [clips] [tokens]"""
+are wrong while a bit is set) and reports the decode-stage time per step.  Usage: python tools/decode_ablation.py [clips] [tokens] [size] [seconds]"""
 import os
 import sys
 
@@ -12,8 +12,10 @@ from oracle import synth  # noqa: E402
 
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-m = q3asr.Qwen3ASRModel.random_init("0.6B")
-x = [synth.clip(i, 480000) for i in range(clips)]
+size = sys.argv[3] if len(sys.argv) > 3 else "0.6B"
+seconds = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+m = q3asr.Qwen3ASRModel.random_init(size)
+x = [synth.clip(i, 16000 * seconds) for i in range(clips)]
 m.batch_upload(x)
 names = ["none", "qkv", "attn", "o", "norm1", "gateup", "down", "norm2", "all-gemm", "all-but-attn", "everything"]
 masks = [0, 1, 2, 4, 8, 16, 32, 64, 1 | 4 | 16 | 32, 1 | 4 | 8 | 16 | 32 | 64, 127]
