@@ -96,7 +96,8 @@ public final class Qwen3ASRB200Model {
     }
 
     /// Batched greedy transcription: utterances are independent, the library batches them on the GPU.
-    public func transcribeBatch(audio: [[Float]], language: String? = nil, maxTokens: Int = 448, context: String? = nil) -> [String] {
+    public func transcribeBatch(audio: [[Float]], language: String? = nil, maxTokens: Int = 448, context: String? = nil,
+                                sampleRates: [Int]? = nil, options: Qwen3DecodingOptions? = nil) -> [String] {
         guard q3asr_is_loaded(handle) != 0 else {
             return audio.map { _ in "[Audio encoded] - Text decoder not loaded" }   // Qwen3ASR.swift:116-119
         }
@@ -114,9 +115,17 @@ public final class Qwen3ASRB200Model {
         let rc: Int32 = ctx.withUnsafeBufferPointer { c in
             lang.withUnsafeBufferPointer { l in
                 var prompts = [q3asr_prompt](repeating: q3asr_prompt(context_ids: c.baseAddress, n_context: Int32(c.count),
-                                                                    language_ids: l.baseAddress, n_language: Int32(l.count)), count: n)
+                                                                    language_ids: l.baseAddress, n_language: Int32(l.count),
+                                                                    raw_suffix: 0), count: n)
+                // clips at other sample rates are converted to 16 kHz on the device (AudioPreprocessing.swift:323-337); the decoder
+                // knobs of Qwen3DecodingOptions run as a device kernel (pickNextToken, Qwen3ASR.swift:449-520)
+                var rates = (sampleRates ?? [Int](repeating: 16000, count: n)).map(Int32.init)
+                var samp = q3asr_sampling(repetition_penalty: options?.repetitionPenalty ?? 1.0,
+                                          no_repeat_ngram_size: Int32(options?.noRepeatNgramSize ?? 0),
+                                          temperature: options?.temperature ?? 0.0,
+                                          seed: UInt64.random(in: 0 ... UInt64.max), force_device_sampler: 0)
                 return withAll(0) {
-                    q3asr_transcribe_ids(handle, &ptrs, &sizes, Int32(n), &prompts, Int32(maxTokens), 1, &ids, &lens)
+                    q3asr_transcribe_ids_opts(handle, &ptrs, &sizes, &rates, Int32(n), &prompts, &samp, Int32(maxTokens), 1, &ids, &lens)
                 }
             }
         }
@@ -136,16 +145,12 @@ public final class Qwen3ASRB200Model {
 
     public func transcribe(audio: [Float], sampleRate: Int = 16000, language: String? = nil, maxTokens: Int = 448,
                            context: String? = nil) -> String {
-        let pcm = sampleRate == 16000 ? audio : AudioFileLoader.resample(audio, from: sampleRate, to: 16000)
-        return transcribeBatch(audio: [pcm], language: language, maxTokens: maxTokens, context: context)[0]
+        return transcribeBatch(audio: [audio], language: language, maxTokens: maxTokens, context: context, sampleRates: [sampleRate])[0]
     }
 
     public func transcribe(audio: [Float], sampleRate: Int = 16000, options: Qwen3DecodingOptions) -> String {
-        // the B200 path is the greedy fast path (isGreedyFastPath, Qwen3ASR.swift:300-304); sampler knobs fall back to the MLX model
-        precondition(options.repetitionPenalty == 1.0 && options.noRepeatNgramSize == 0 && options.temperature == 0.0,
-                     "Qwen3ASRB200Model implements greedy decoding only")
-        return transcribe(audio: audio, sampleRate: sampleRate, language: options.language, maxTokens: options.maxTokens,
-                          context: options.context)
+        return transcribeBatch(audio: [audio], language: options.language, maxTokens: options.maxTokens, context: options.context,
+                               sampleRates: [sampleRate], options: options)[0]
     }
 }
 
