@@ -68,6 +68,19 @@ int main(int argc, char** argv) {
     if (AudioFileLoader::resample(*m, x24, 24000, 16000).size() != x.size()) return 12;
     auto segs = m->transcribeLong(x, 16000, 1.0f, 4, 2);
     if ((int)segs.size() != seconds || segs.back().segmentIndex != seconds - 1) return 13;
+    {   // forced aligner through the host mirror: tiny configuration, a toy tokenizer (one id per word length)
+        auto al = Qwen3ForcedAligner::randomInit(20260418, 0, "tiny-aligner");
+        Tokenizer toy;
+        toy.encode = [](const std::string& w) { return std::vector<int32_t>{(int32_t)(10 + w.size()), (int32_t)(100 + (unsigned char)w[0])}; };
+        al->setTokenizer(toy);
+        auto words = al->align(x, "Hello, brave new world -- it's 9 o'clock .");
+        if (words.size() != 7 || words[0].text != "Hello," || words[3].text != "world--" || words[6].text != "o'clock.") return 14;
+        for (size_t i = 0; i < words.size(); i++) {
+            if (words[i].endTime < words[i].startTime || (i && words[i].startTime < words[i - 1].startTime)) return 15;
+        }
+        if (al->alignLong(x, "one two three").size() != 3) return 16;
+        printf("aligner ok: %zu words, last at %.2f s\n", words.size(), words.back().startTime);
+    }
     m->unload();
     if (m->isLoaded() || m->transcribe(x).find("not loaded") == std::string::npos) return 5;
     return f.timeFrames == seconds * 100 ? 0 : 6;

@@ -310,6 +310,146 @@ class Qwen3ASRModel {
     Tokenizer tok_;
 };
 
+struct AlignedWord {  // AudioCommon/Protocols.swift (AlignedWord)
+    std::string text;
+    float startTime = 0.f, endTime = 0.f;
+};
+
+// Qwen3ForcedAligner (ForcedAligner.swift:50-331) over q3asr_align_indices.  Word splitting: the whitespace path of
+// TextPreprocessor.splitIntoWordPairs (TextPreprocessing.swift: letters, digits and the ASCII apostrophe are kept, other ASCII
+// punctuation is stripped from the form the tokenizer sees; non-ASCII bytes are kept as they are).  The Japanese / Korean / per-Han
+// paths of the reference need Apple's NaturalLanguage framework and are not reproduced.
+class Qwen3ForcedAligner {
+  public:
+    static constexpr float timestampSegmentTime = 0.08f;  // Configuration.swift:133
+    static std::unique_ptr<Qwen3ForcedAligner> randomInit(uint64_t seed = 20260418, int device = 0, const char* preset = "aligner") {
+        std::unique_ptr<Qwen3ForcedAligner> m(new Qwen3ForcedAligner(preset, device));
+        if (q3asr_init_random(m->h_, seed) != Q3ASR_OK) throw AudioModelError(1, std::string("modelLoadFailed: ") + q3asr_last_error(m->h_));
+        return m;
+    }
+    static std::unique_ptr<Qwen3ForcedAligner> fromPretrained(const std::string& modelDir, int device = 0) {
+        std::unique_ptr<Qwen3ForcedAligner> m(new Qwen3ForcedAligner("aligner", device));
+        int rc = q3asr_load_safetensors(m->h_, modelDir.c_str());
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("weightLoadingFailed: ") + q3asr_last_error(m->h_));
+        m->tok_ = Tokenizer::fromDirectory(modelDir);  // the aligner cannot work without one (ForcedAligner.swift:232-235)
+        return m;
+    }
+    ~Qwen3ForcedAligner() { q3asr_destroy(h_); }
+    Qwen3ForcedAligner(const Qwen3ForcedAligner&) = delete;
+    Qwen3ForcedAligner& operator=(const Qwen3ForcedAligner&) = delete;
+    void setTokenizer(Tokenizer t) { tok_ = std::move(t); }
+    int timestampTokenId = 151705;  // Qwen3ASR.swift:62 (the tests' tiny vocabulary overrides it)
+
+    struct WordPair { std::string surface, cleaned; };
+    static std::vector<WordPair> splitIntoWordPairs(const std::string& text) {
+        std::vector<WordPair> out;
+        size_t i = 0;
+        while (i < text.size()) {
+            while (i < text.size() && std::isspace((unsigned char)text[i])) i++;
+            size_t j = i;
+            while (j < text.size() && !std::isspace((unsigned char)text[j])) j++;
+            if (j > i) {
+                WordPair w;
+                w.surface = text.substr(i, j - i);
+                for (unsigned char c : w.surface)
+                    if (std::isalnum(c) || c == '\'' || c >= 0x80) w.cleaned += (char)c;
+                if (!w.cleaned.empty()) out.push_back(w);
+                else if (!out.empty()) out.back().surface += w.surface;  // punctuation-only token: keep it on the previous word
+            }
+            i = j;
+        }
+        return out;
+    }
+
+    // ForcedAligner.swift:226-331.  Returns [] when no tokenizer is set or the text has no words (like the reference).
+    std::vector<AlignedWord> align(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000) {
+        std::vector<AlignedWord> out;
+        if (!tok_.encode) return out;
+        std::vector<int32_t> ids;
+        std::vector<int> pos;
+        std::vector<std::string> words;
+        for (const WordPair& w : splitIntoWordPairs(text)) {  // TextPreprocessing.swift:48-80: <timestamp> word tokens <timestamp>
+            const std::vector<int32_t> t = tok_.encode(w.cleaned);
+            if (t.empty()) {
+                if (!words.empty()) words.back() += w.surface;
+                continue;
+            }
+            pos.push_back((int)ids.size());
+            ids.push_back(timestampTokenId);
+            ids.insert(ids.end(), t.begin(), t.end());
+            pos.push_back((int)ids.size());
+            ids.push_back(timestampTokenId);
+            words.push_back(w.surface);
+        }
+        if (words.empty()) return out;
+        const float* pcm = audio.data();
+        const size_t n = audio.size();
+        const int32_t* sl = ids.data();
+        const int nsl = (int)ids.size(), np = (int)pos.size();
+        const int* pp = pos.data();
+        std::vector<int32_t> raw((size_t)np);
+        int32_t* rp = raw.data();
+        if (q3asr_align_indices(h_, &pcm, &n, &sampleRate, 1, &sl, &nsl, &pp, &np, &rp) != Q3ASR_OK) return out;
+        std::vector<int> r(raw.begin(), raw.end()), fixed((size_t)np);
+        q3asr_enforce_monotonicity(r.data(), np, fixed.data());
+        for (size_t w = 0; w < words.size(); w++) {
+            const float st = (float)fixed[2 * w] * timestampSegmentTime, en = (float)fixed[2 * w + 1] * timestampSegmentTime;
+            out.push_back(AlignedWord{words[w], st, std::max(en, st)});
+        }
+        return out;
+    }
+
+    // ForcedAligner.swift:104-176: re-align the remainder when the tail of a long recording collapses onto one timestamp
+    std::vector<AlignedWord> alignLong(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000) {
+        const float bypassThresholdSeconds = 240.f, minChunkSeconds = 5.f, plateauTolerance = 0.1f;
+        const int plateauMinWords = 5;
+        std::vector<AlignedWord> all;
+        std::vector<float> remAudio = audio;
+        std::string remText = text;
+        float offset = 0.f;
+        for (int pass = 1; !remAudio.empty() && !remText.empty() && pass <= 10; pass++) {
+            const float duration = (float)remAudio.size() / (float)sampleRate;
+            std::vector<AlignedWord> a = align(remAudio, remText, sampleRate);
+            if (a.empty()) break;
+            auto append = [&](size_t count) {
+                for (size_t i = 0; i < count; i++) all.push_back(AlignedWord{a[i].text, a[i].startTime + offset, a[i].endTime + offset});
+            };
+            if (duration <= bypassThresholdSeconds || (int)a.size() < plateauMinWords * 2) { append(a.size()); break; }
+            std::vector<float> starts;
+            for (const AlignedWord& w : a) starts.push_back(w.startTime);
+            const int plateau = q3asr_trailing_plateau_start(starts.data(), (int)starts.size(), plateauTolerance, plateauMinWords);
+            if (plateau == (int)a.size()) { append(a.size()); break; }
+            if (plateau == 0) break;
+            append((size_t)plateau);
+            const float splitTime = a[(size_t)plateau - 1].endTime;
+            const size_t splitSample = (size_t)(splitTime * (float)sampleRate);
+            if (splitSample >= remAudio.size()) break;
+            std::vector<float> next(remAudio.begin() + splitSample, remAudio.end());
+            if ((float)next.size() / (float)sampleRate < minChunkSeconds) break;
+            const std::vector<WordPair> wordsAll = splitIntoWordPairs(remText);
+            if (plateau >= (int)wordsAll.size()) break;
+            std::string nextText;
+            for (size_t i = (size_t)plateau; i < wordsAll.size(); i++) nextText += (i > (size_t)plateau ? " " : "") + wordsAll[i].surface;
+            remAudio.swap(next);
+            remText.swap(nextText);
+            offset += splitTime;
+        }
+        return all;
+    }
+    q3asr_handle* handle() const { return h_; }
+
+  private:
+    Qwen3ForcedAligner(const char* preset, int device) {
+        q3asr_config cfg;
+        if (q3asr_config_preset(preset, &cfg) != Q3ASR_OK) throw AudioModelError(1, "modelLoadFailed: unknown aligner preset");
+        timestampTokenId = cfg.tok_timestamp;
+        int rc = q3asr_create(&cfg, device, &h_);
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("modelLoadFailed: ") + q3asr_last_error(nullptr));
+    }
+    q3asr_handle* h_ = nullptr;
+    Tokenizer tok_;
+};
+
 inline std::vector<float> AudioFileLoader::resample(const Qwen3ASRModel& model, const std::vector<float>& samples, int from, int to) {
     if (from == to || samples.empty()) return samples;
     size_t n = q3asr_resample_len(samples.size(), from, to);
