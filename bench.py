@@ -137,6 +137,30 @@ def cpu_sample(seconds, tokens, clips=1, state_dict=None, threads=None):
                          f"fp32 torch-CPU, {cores} threads")
 
 
+def cpu_mel_gbs(clips):
+    """The reference's CPU mel path (AudioPreprocessing.swift:209-293: serial frame loop, dense 257 x 128 product) as restated in
+    oracle/mel_oracle.c, timed (i) on one thread, as the reference runs it, and (ii) over clips on all host cores.  Algorithmic
+    bytes as for the GPU kernel: 7.2 B per input sample."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import mel as omel
+    omel.mel(clips[0][:16000])  # builds / loads the C library
+    by = lambda xs: sum(4.0 * x.size + 4.0 * 128 * (x.size // 160) for x in xs)
+    def best_of(fn, reps=3):
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            t.append(time.perf_counter() - t0)
+        return min(t)
+    one = by(clips[:1]) / best_of(lambda: omel.mel(clips[0])) / 1e9
+    cores = os.cpu_count() or 1
+    sample = (clips * (1 + cores // max(len(clips), 1)))[:max(1, cores)]  # one clip per thread
+    with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL for the duration of the C call
+        allc = by(sample) / best_of(lambda: list(ex.map(omel.mel, sample))) / 1e9
+    return {"gbs_1_thread": one, "gbs_all_cores": allc, "cores": cores, "kind": "port",
+            "sample": f"1 clip on one thread; {len(sample)} clips of {CLIP_SECONDS} s over {cores} threads (oracle/mel_oracle.c)"}
+
+
 def workload_config(world):
     """The workload both arms name (the reference arm runs a bounded sample of it, described in its cpu_baseline.sample)."""
     return {"workload": f"Qwen3-ASR-{MODEL}: {CLIPS_PER_GPU} x {CLIP_SECONDS} s clips per GPU, mel -> encoder -> prefill -> "
@@ -333,7 +357,8 @@ def main():
         n_cpu = 1  # one clip of the workload with the full decode length: 10-30 s on the box's host cores
         once, cores, sample = cpu_sample(CLIP_SECONDS, MAX_TOKENS, n_cpu, state_dict=sd)
         sec = once()
-        cpu = {"value": n_cpu * CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s of CPU time)"}
+        cpu = {"value": n_cpu * CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s of CPU time)",
+               "mel": cpu_mel_gbs(clips)}
     model.close()
 
     if rank == 0:
