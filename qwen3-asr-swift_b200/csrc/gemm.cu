@@ -351,21 +351,24 @@ unsigned long long gemm_launch_count() { return g_launches.load(); }
 // decode-step weight-streaming GEMM
 // ------------------------------------------------------------------------------------------
 namespace {
-template <int NB, int EPI>
+template <int NB, int EPI, bool DEEP>
 void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     std::min(227 * 1024, sk_smem_bytes(NB, SK_MAX_STAGES))));
+        Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB, DEEP)));
         attr_set = true;
     }
-    launch_kernel(gemm_skinny_kernel<NB, EPI>, grid, 256, sk_smem_bytes(NB, p.stages), st, tw, tx, p);
+    launch_kernel(gemm_skinny_kernel<NB, EPI, DEEP>, grid, 256, sk_smem_bytes(NB, DEEP), st, tw, tx, p);
 }
 template <int NB>
-void launch_skinny_nb(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
+void launch_skinny_nb(int epi, bool deep, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
     switch (epi) {
-        case SK_PARTIAL: launch_skinny<NB, SK_PARTIAL>(tw, tx, p, grid, st); break;
-        case SK_STORE: launch_skinny<NB, SK_STORE>(tw, tx, p, grid, st); break;
+        case SK_PARTIAL:
+            if (deep) launch_skinny<NB, SK_PARTIAL, true>(tw, tx, p, grid, st); else launch_skinny<NB, SK_PARTIAL, false>(tw, tx, p, grid, st);
+            break;
+        case SK_STORE:
+            if (deep) launch_skinny<NB, SK_STORE, true>(tw, tx, p, grid, st); else launch_skinny<NB, SK_STORE, false>(tw, tx, p, grid, st);
+            break;
         default: throw Error(1, "gemm_skinny: bad epilogue");
     }
 }
@@ -390,18 +393,10 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
     p.num_kb = cdiv(K, SK_BK);
     const int splits = gemm_skinny_splits(N, K, epi);
     p.kb_per_split = cdiv(p.num_kb, splits);
-    {
-        // ring depth: see skinny.cuh.  Q3ASR_SK_STAGES / Q3ASR_SK_DEEP_KB override the policy (tuning)
-        static const int force = getenv("Q3ASR_SK_STAGES") ? atoi(getenv("Q3ASR_SK_STAGES")) : 0;
-        static const int deep_kb = getenv("Q3ASR_SK_DEEP_KB") ? atoi(getenv("Q3ASR_SK_DEEP_KB")) : 8;
-        const int max_fit = std::min(SK_MAX_STAGES, (200 * 1024) / sk_stage_bytes(nb));
-        int stages = sk_stages(nb);
-        // a long K slice is bandwidth-bound: half as many bytes again in flight (measured on 1.7B, 64 sequences: 63.3 -> 60.8 us per
-        // layer with 6 stages, 61.5 with 8; 0.6B, whose slices are 2-4 blocks, is fastest at 4)
-        if (p.kb_per_split >= deep_kb) stages = std::min(max_fit, stages + stages / 2);
-        if (force > 0) stages = force;
-        p.stages = std::max(1, std::min(std::min(stages, max_fit), std::max(p.kb_per_split, 1)));
-    }
+    // ring depth: see skinny.cuh.  A long K slice is bandwidth-bound: half as many bytes again in flight (measured on 1.7B, 64
+    // sequences: 63.3 -> 60.8 us per layer; 0.6B, whose slices are 2-4 blocks, is fastest with the 96 KB ring)
+    static const int deep_kb = getenv("Q3ASR_SK_DEEP_KB") ? atoi(getenv("Q3ASR_SK_DEEP_KB")) : 8;
+    const bool deep = p.kb_per_split >= deep_kb;
     p.out = out;
     p.ldo = ldo;
     p.split_stride = (long long)Mtok * N;
@@ -422,10 +417,10 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
     }
     const dim3 grid(cdiv(N, SK_BM), splits);
     switch (nb) {
-        case 16: launch_skinny_nb<16>(epi, tw, tx, p, grid, st); break;
-        case 32: launch_skinny_nb<32>(epi, tw, tx, p, grid, st); break;
-        case 64: launch_skinny_nb<64>(epi, tw, tx, p, grid, st); break;
-        default: launch_skinny_nb<128>(epi, tw, tx, p, grid, st); break;
+        case 16: launch_skinny_nb<16>(epi, deep, tw, tx, p, grid, st); break;
+        case 32: launch_skinny_nb<32>(epi, deep, tw, tx, p, grid, st); break;
+        case 64: launch_skinny_nb<64>(epi, deep, tw, tx, p, grid, st); break;
+        default: launch_skinny_nb<128>(epi, deep, tw, tx, p, grid, st); break;
     }
     Q3_CUDA(cudaGetLastError());
     g_launches++;

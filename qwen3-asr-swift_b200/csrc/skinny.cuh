@@ -19,7 +19,6 @@ namespace q3 {
 struct SkinnyDev {
     int N, Mtok;
     int num_kb, kb_per_split;
-    int stages;             // ring depth, 1..SK_MAX_STAGES
     void* out;
     int ldo;                // bf16 outputs: row pitch in elements
     long long split_stride; // SK_PARTIAL: elements between split slabs
@@ -28,18 +27,21 @@ struct SkinnyDev {
 constexpr int SK_BM = 128;  // weight rows per CTA
 constexpr int SK_BK = 64;
 __host__ __device__ constexpr int sk_stage_bytes(int NB) { return SK_BM * 128 + NB * 128; }
-// Ring depth (runtime): bytes in flight per SM set the streaming rate (Little's law: ~2 us loaded latency), but a CTA that holds
-// more than ~96 KB keeps the next kernel's CTAs from becoming resident early (programmatic dependent launch).  Short K slices
-// (0.6B: latency-bound phases) use 96 KB; long ones (1.7B: bandwidth-bound phases) use up to 192 KB.
-constexpr int SK_MAX_STAGES = 8;
-__host__ __device__ constexpr int sk_stages(int NB) { return (96 * 1024) / sk_stage_bytes(NB) > 6 ? 6 : (96 * 1024) / sk_stage_bytes(NB); }
+// Ring depth: bytes in flight per SM set the streaming rate (Little's law: ~2 us loaded latency), but a CTA that holds more than
+// ~96 KB keeps the next kernel's CTAs from becoming resident early (programmatic dependent launch).  Short K slices (0.6B:
+// latency-bound phases) use 96 KB; long ones (DEEP; 1.7B: bandwidth-bound phases) half as much again.  A compile-time constant:
+// a run-time depth cost 5 % of the 0.6B decode step (measured).
+__host__ __device__ constexpr int sk_stages(int NB, bool deep = false) {
+    const int s = (96 * 1024) / sk_stage_bytes(NB) > 6 ? 6 : (96 * 1024) / sk_stage_bytes(NB);
+    return deep ? s + s / 2 : s;
+}
 __host__ __device__ constexpr int sk_tmem_cols(int NB) { return NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256; }
-__host__ __device__ constexpr int sk_smem_bytes(int NB, int stages) { return stages * sk_stage_bytes(NB) + 1024 + 256; }
+__host__ __device__ constexpr int sk_smem_bytes(int NB, bool deep = false) { return sk_stages(NB, deep) * sk_stage_bytes(NB) + 1024 + 256; }
 
-template <int NB, int EPI>
+template <int NB, int EPI, bool DEEP>
 __global__ void __launch_bounds__(256, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkinnyDev p) {
-    const int STAGES = p.stages;
+    constexpr int STAGES = sk_stages(NB, DEEP);
     constexpr int STAGE_BYTES = sk_stage_bytes(NB);
     constexpr int TMEM_COLS = sk_tmem_cols(NB);
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(SK_BM, NB);
@@ -49,8 +51,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + SK_MAX_STAGES;
-    uint64_t* tfull_bar = empty_bar + SK_MAX_STAGES;
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -73,3 +73,14 @@ def test_mel_properties_full_size(tiny_model):
     a = tiny_model.extract_features(clips[3][:48000])
     b = tiny_model.extract_features((2.0 * clips[3][:48000]).astype(np.float32))
     assert np.allclose(b - a, np.log10(4.0) / 4.0, atol=2e-4)
+
+
+def test_mel_maximum_size_frame_cap(tiny_model):
+    # AudioPreprocessing.swift:304: at most 120000 frames are kept (20 min); the maximum runs over every computed frame, kept or not
+    n = 160 * 120000 + 160 * 37 + 5
+    x = synth.clip(9, n)
+    x[-2000:] *= 40.0  # the loudest frames are beyond the cap: they still set the max-8 clamp
+    x = np.clip(x, -1.0, 1.0).astype(np.float32)
+    got = tiny_model.extract_features(x)
+    assert got.shape == (128, 120000)
+    _check(got, omel.mel(x), "frame cap")

@@ -6,7 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
+sys.path.insert(0, os.environ.get("Q3ASR_PKG") or os.path.join(ROOT, "qwen3-asr-swift_b200"))  # Q3ASR_PKG: A/B against another build
 import q3asr  # noqa: E402
 from oracle import synth  # noqa: E402  (input generator only)
 
