@@ -212,6 +212,11 @@ const char* q3asr_pool_last_error(const q3asr_pool* p);
 int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, int batch,
                               const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int max_batch_per_gpu,
                               int32_t* ids_out, int* lens_out);
+/* the same with per-utterance sample rates (NULL = 16 kHz) and decoder knobs (NULL = greedy); the noise stream of a sampled run is
+ * keyed by the position inside the sub-batch an utterance lands in, so sampled output depends on the schedule */
+int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                                   const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos,
+                                   int max_batch_per_gpu, int32_t* ids_out, int* lens_out);
 /* the scheduler's assignment alone (host logic; no GPU needed): gpu_out[i] = GPU of utterance i */
 int q3asr_schedule(const size_t* n_samples, int batch, int n_gpus, int* gpu_out);
 

@@ -70,10 +70,25 @@ const char* q3asr_pool_last_error(const q3asr_pool* p) { return p ? p->last_erro
 
 int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, int batch, const q3asr_prompt* prompts,
                               int max_tokens, int stop_on_eos, int max_batch_per_gpu, int32_t* ids_out, int* lens_out) {
-    if (p == nullptr || pcm == nullptr || n_samples == nullptr || ids_out == nullptr || lens_out == nullptr || batch <= 0)
+    return q3asr_pool_transcribe_ids_opts(p, pcm, n_samples, nullptr, batch, prompts, nullptr, max_tokens, stop_on_eos, max_batch_per_gpu,
+                                          ids_out, lens_out);
+}
+
+int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const size_t* n_in, const int* sample_rates, int batch,
+                                   const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos,
+                                   int max_batch_per_gpu, int32_t* ids_out, int* lens_out) {
+    if (p == nullptr || pcm == nullptr || n_in == nullptr || ids_out == nullptr || lens_out == nullptr || batch <= 0)
         return Q3ASR_ERR_INVALID;
     const int G = (int)p->handles.size();
     if (max_batch_per_gpu <= 0) max_batch_per_gpu = 64;
+    // the scheduler's cost model and the length sort work on 16 kHz-equivalent lengths
+    std::vector<size_t> n16(n_in, n_in + batch);
+    if (sample_rates)
+        for (int i = 0; i < batch; i++) {
+            if (sample_rates[i] <= 0) return Q3ASR_ERR_INVALID;
+            n16[i] = q3asr_resample_len(n_in[i], sample_rates[i], 16000);
+        }
+    const size_t* n_samples = n16.data();
     std::vector<int> gpu(batch);
     q3asr_schedule(n_samples, batch, G, gpu.data());
     std::vector<int> rc(G, Q3ASR_OK);
@@ -89,16 +104,18 @@ int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size
                 const int nb = (int)std::min<size_t>(max_batch_per_gpu, mine.size() - s);
                 std::vector<const float*> pp(nb);
                 std::vector<size_t> nn(nb);
+                std::vector<int> rr(nb, 16000);
                 std::vector<q3asr_prompt> pr(nb);
                 for (int j = 0; j < nb; j++) {
                     pp[j] = pcm[mine[s + j]];
-                    nn[j] = n_samples[mine[s + j]];
+                    nn[j] = n_in[mine[s + j]];
+                    if (sample_rates) rr[j] = sample_rates[mine[s + j]];
                     if (prompts) pr[j] = prompts[mine[s + j]];
                 }
                 std::vector<int32_t> ids((size_t)nb * max_tokens);
                 std::vector<int> lens(nb);
-                rc[g] = q3asr_transcribe_ids(p->handles[g], pp.data(), nn.data(), nb, prompts ? pr.data() : nullptr, max_tokens,
-                                             stop_on_eos, ids.data(), lens.data());
+                rc[g] = q3asr_transcribe_ids_opts(p->handles[g], pp.data(), nn.data(), sample_rates ? rr.data() : nullptr, nb,
+                                                  prompts ? pr.data() : nullptr, sampling, max_tokens, stop_on_eos, ids.data(), lens.data());
                 if (rc[g] != Q3ASR_OK) break;
                 for (int j = 0; j < nb; j++) {  // host-side result gather, original order
                     const int i = mine[s + j];

@@ -89,6 +89,7 @@ EXPORTS = [
     "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
     "q3asr_transcribe_ids_opts", "q3asr_batch_set_sampling", "q3asr_pick_next_token",
     "q3asr_align_indices", "q3asr_enforce_monotonicity", "q3asr_lis_positions", "q3asr_trailing_plateau_start",
+    "q3asr_pool_transcribe_ids_opts",
 ]
 
 _lib = None
@@ -147,6 +148,7 @@ def lib():
         L.q3asr_pool_destroy.restype = None
         L.q3asr_pool_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, vp, vp]
         L.q3asr_schedule.argtypes = [vp, ci, ci, vp]
+        L.q3asr_pool_transcribe_ids_opts.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(Sampling), ci, ci, ci, vp, vp]
         L.q3asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, ci, ci, ctypes.c_float, ci, vp]
@@ -763,14 +765,17 @@ class Pool:
         if rc != OK:
             raise Q3Error(rc, "pool_create failed: " + lib().q3asr_last_error(None).decode())
 
-    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, max_batch_per_gpu=64):
+    def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, max_batch_per_gpu=64, sample_rates=None, options=None):
         clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
         n = np.array([c.size for c in clips], dtype=np.uint64)
         ids = np.zeros((len(clips), max_tokens), dtype=np.int32)
         lens = np.zeros(len(clips), dtype=np.int32)
-        rc = lib().q3asr_pool_transcribe_ids(self._p, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data, len(clips), None,
-                                             int(max_tokens), int(bool(stop_on_eos)), int(max_batch_per_gpu), ids.ctypes.data,
-                                             lens.ctypes.data)
+        sr = None if sample_rates is None else np.ascontiguousarray(sample_rates, dtype=np.int32)
+        samp = None if options is None else options.c_struct()
+        rc = lib().q3asr_pool_transcribe_ids_opts(self._p, ctypes.cast(_ptr_array(clips), ctypes.c_void_p), n.ctypes.data,
+                                                  sr.ctypes.data if sr is not None else None, len(clips), None,
+                                                  ctypes.byref(samp) if samp is not None else None, int(max_tokens),
+                                                  int(bool(stop_on_eos)), int(max_batch_per_gpu), ids.ctypes.data, lens.ctypes.data)
         if rc != OK:
             raise Q3Error(rc, lib().q3asr_pool_last_error(self._p).decode())
         return [ids[i, :lens[i]].copy() for i in range(len(clips))]

@@ -33,6 +33,26 @@ def test_pool_matches_single_handle_and_keeps_order(built_lib):
         single.close()
 
 
+def test_pool_with_sample_rates_and_decoder_knobs(built_lib):
+    """q3asr_pool_transcribe_ids_opts: mixed sample rates are converted on each worker's device, and the deterministic decoder knobs
+    (penalty + n-gram mask) give what a single handle gives, whatever the schedule."""
+    rates = [16000, 24000, 8000, 24000, 16000, 48000]
+    clips = [synth.clip(i, r * 2 + 100 * i) for i, r in enumerate(rates)]
+    opts = built_lib.Qwen3DecodingOptions(repetition_penalty=1.3, no_repeat_ngram_size=2)
+    single = built_lib.Qwen3ASRModel.random_init("tiny", seed=20260418)
+    pool = built_lib.Pool("tiny", devices=_devices(), seed=20260418)
+    try:
+        want = [single.transcribe_ids([c], max_tokens=10, stop_on_eos=False, sample_rates=[r], options=opts)[0].tolist()
+                for c, r in zip(clips, rates)]
+        got = pool.transcribe_ids(clips, max_tokens=10, stop_on_eos=False, max_batch_per_gpu=2, sample_rates=rates, options=opts)
+        assert [g.tolist() for g in got] == want
+        plain = pool.transcribe_ids(clips, max_tokens=10, stop_on_eos=False, sample_rates=rates)
+        assert [g.tolist() for g in plain] != want  # the knobs are really on
+    finally:
+        pool.close()
+        single.close()
+
+
 def test_1p7b_configuration(built_lib, monkeypatch):
     """Qwen3-ASR-1.7B dimensions (encoder d 1024 / 24 layers, decoder hidden 2048): batch invariance, fixed length, and the two
     decode schedules (weight-streaming split-K path vs one kernel per op) agree."""
