@@ -215,7 +215,7 @@ int q3asr_mel_batch(q3asr_handle* hh, const float* const* pcm, const size_t* n, 
         h.mel_out.reserve(sizeof(float) * std::max<long long>(plan.out_floats, 1));
         h.mel_clips.reserve(sizeof(MelClip) * batch);
         h.mel_gmax.reserve(sizeof(int) * batch);
-        h.mel_tmin.reserve(sizeof(float) * plan.total_tiles);
+        h.mel_tmin.reserve(sizeof(float) * 2 * plan.total_tiles);  // per-tile minimum + per-tile clip
         h.mel_stage.reserve(sizeof(float) * std::max<long long>(plan.pcm_floats, plan.out_floats));
         float* stage = h.mel_stage.as<float>();
         for (int b = 0; b < batch; b++) memcpy(stage + plan.clips[b].in_off, pcm[b], sizeof(float) * n[b]);

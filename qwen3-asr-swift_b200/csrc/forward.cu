@@ -711,7 +711,7 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     bs->mel_out.reserve(sizeof(float) * std::max<long long>(bs->mel.out_floats, 1));
     bs->mel_clips.reserve(sizeof(MelClip) * batch);
     bs->mel_gmax.reserve(sizeof(int) * batch);
-    bs->mel_tmin.reserve(sizeof(float) * bs->mel.total_tiles);
+    bs->mel_tmin.reserve(sizeof(float) * 2 * bs->mel.total_tiles);  // per-tile minimum + per-tile clip
     bs->h_stage.reserve(sizeof(float) * (bs->mel.pcm_floats + raw_floats));
     float* stage = bs->h_stage.as<float>();
     float* stage_raw = stage + bs->mel.pcm_floats;  // clips awaiting conversion

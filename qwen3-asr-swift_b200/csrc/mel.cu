@@ -19,6 +19,7 @@
 // max-8 clamp only to tiles whose minimum is below it (exact, because clamp and the monotone affine
 // map commute), so in the common case the features are written once and never re-read.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -53,10 +54,36 @@ struct MelParams {
     int total_tiles;
     int* gmax;
     float* tmin;
+    int* tclip;  // clip of every tile (for the clamp pass)
 };
 
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
     return (SX_FLOATS + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + FR_PER_IT * SCR_FLOATS + MEL_BINS * OUT_STRIDE + 32) * 4;
+}
+
+// Widths (taps) of the eight filterbank rounds: a property of the slaney filterbank at 16 kHz / 512 points / 128 bins, checked
+// against the computed table in mel_tables_create.  Compile-time constants let the tap loops unroll completely (the loop control
+// was 15 % of the kernel's instructions).
+template <int J> struct FbRound;
+template <> struct FbRound<0> { static constexpr int W = 2, OFF = 0; };
+template <> struct FbRound<1> { static constexpr int W = 2, OFF = 2; };
+template <> struct FbRound<2> { static constexpr int W = 2, OFF = 4; };
+template <> struct FbRound<3> { static constexpr int W = 3, OFF = 6; };
+template <> struct FbRound<4> { static constexpr int W = 4, OFF = 9; };
+template <> struct FbRound<5> { static constexpr int W = 6, OFF = 13; };
+template <> struct FbRound<6> { static constexpr int W = 9, OFF = 19; };
+template <> struct FbRound<7> { static constexpr int W = 12, OFF = 28; };
+constexpr int FB_ROWS = 40;
+constexpr int FB_WIDTHS[MEL_ROUNDS] = {2, 2, 2, 3, 4, 6, 9, 12};
+
+template <int J>
+__device__ __forceinline__ float fb_round(const float* __restrict__ scr, const float* __restrict__ s_fbw, const int* __restrict__ s_fbstart, int t) {
+    const float* pp = scr + s_fbstart[t + 16 * J];
+    const float* wp = s_fbw + FbRound<J>::OFF * 16 + t;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < FbRound<J>::W; w++) acc = fmaf(pp[w], wp[w * 16], acc);
+    return acc;
 }
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -242,14 +269,19 @@ __global__ void __launch_bounds__(MEL_THREADS, 4) mel_kernel(const MelParams p) 
             // ---- sparse filterbank, log10, scale; lane t owns mel bins t, t+16, ... ----
             const bool in_max = (f0 + fl) < nF;
             const bool in_out = (f0 + fl) < c.frames;
+            float accs[MEL_ROUNDS];
+            accs[0] = fb_round<0>(scr, s_fbw, s_fbstart, t);
+            accs[1] = fb_round<1>(scr, s_fbw, s_fbstart, t);
+            accs[2] = fb_round<2>(scr, s_fbw, s_fbstart, t);
+            accs[3] = fb_round<3>(scr, s_fbw, s_fbstart, t);
+            accs[4] = fb_round<4>(scr, s_fbw, s_fbstart, t);
+            accs[5] = fb_round<5>(scr, s_fbw, s_fbstart, t);
+            accs[6] = fb_round<6>(scr, s_fbw, s_fbstart, t);
+            accs[7] = fb_round<7>(scr, s_fbw, s_fbstart, t);
 #pragma unroll
             for (int j = 0; j < MEL_ROUNDS; j++) {
                 const int m = t + 16 * j;
-                const float* pp = scr + s_fbstart[m];
-                const float* wp = s_fbw + p.fb_round_off[j] * 16 + t;
-                const int wn = p.fb_round_off[j + 1] - p.fb_round_off[j];
-                float acc = 0.f;
-                for (int w = 0; w < wn; w++) acc = fmaf(pp[w], wp[w * 16], acc);
+                const float acc = accs[j];
                 const float L = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
                 s_out[m * OUT_STRIDE + fl] = fmaf(0.25f, L, 1.0f);
                 if (in_max) lmax = fmaxf(lmax, L);
@@ -268,6 +300,7 @@ __global__ void __launch_bounds__(MEL_THREADS, 4) mel_kernel(const MelParams p) 
             const float tm = fminf(fminf(s_red[4], s_red[5]), fminf(s_red[6], s_red[7]));
             atomicMax(p.gmax + ci, enc_ordered(gm));
             p.tmin[tile] = tm;
+            p.tclip[tile] = ci;
         }
         const int T = c.frames;
         if (lane < MEL_TILE && f0 + lane < T) {
@@ -279,21 +312,44 @@ __global__ void __launch_bounds__(MEL_THREADS, 4) mel_kernel(const MelParams p) 
     }
 }
 
-// Second pass: clip to (clip max - 8) where a tile needs it (AudioPreprocessing.swift:281-293).
-__global__ void __launch_bounds__(128) mel_clamp_kernel(float* out, const MelClip* clips, int batch, int total_tiles,
-                                                        const int* gmax, const float* tmin) {
-    const int tile = blockIdx.x;
-    if (tile >= total_tiles) return;
-    const int ci = find_clip(clips, batch, tile);
-    const float lo = mel_decode_max(gmax[ci]) - 8.0f;
-    if (tmin[tile] >= lo) return;
-    const MelClip c = clips[ci];
-    const int f0 = (tile - c.tile0) * MEL_TILE;
-    const float lo_s = fmaf(0.25f, lo, 1.0f);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= MEL_TILE || f0 + lane >= c.frames) return;
-    float* o = out + c.out_off + f0 + lane;
-    for (int m = warp; m < MEL_BINS; m += 4) o[(size_t)m * c.frames] = fmaxf(o[(size_t)m * c.frames], lo_s);
+// Second pass: clip to (clip max - 8) where a tile needs it (AudioPreprocessing.swift:281-293).  One THREAD per tile decides from
+// three coalesced loads (the tile's clip, recorded by the first pass; the clip's maximum; the tile's minimum); almost every tile is
+// already above the floor (1-2 % of the tiles of the bench clips are not).  The tiles that need the clamp are collected in shared
+// memory and then handled by the whole CTA, one tile at a time: warp w takes 16 mel rows, lane f frame f, all 16 rows in flight.
+constexpr int CLAMP_TILES = 64;
+__global__ void __launch_bounds__(256) mel_clamp_kernel(float* out, const MelClip* clips, int total_tiles, const int* gmax,
+                                                        const float* tmin, const int* tclip) {
+    __shared__ int s_tile[CLAMP_TILES], s_clip[CLAMP_TILES];
+    __shared__ float s_lo[CLAMP_TILES];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int tile = blockIdx.x * CLAMP_TILES + threadIdx.x;  // CLAMP_TILES deciders per CTA: about one tile to clamp per CTA
+    if (threadIdx.x < CLAMP_TILES && tile < total_tiles) {
+        const int ci = tclip[tile];
+        const float lo = mel_decode_max(gmax[ci]) - 8.0f;
+        if (tmin[tile] < lo) {
+            const int k = atomicAdd(&s_n, 1);
+            s_tile[k] = tile;
+            s_clip[k] = ci;
+            s_lo[k] = lo;
+        }
+    }
+    __syncthreads();
+    const int n = s_n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < n; k++) {
+        const MelClip c = clips[s_clip[k]];
+        const int f0 = (s_tile[k] - c.tile0) * MEL_TILE;
+        const float lo_s = fmaf(0.25f, s_lo[k], 1.0f);
+        if (lane < MEL_TILE && f0 + lane < c.frames) {
+            float* o = out + c.out_off + f0 + lane + (size_t)(warp * 16) * c.frames;
+            float v[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = o[(size_t)m * c.frames];
+#pragma unroll
+            for (int m = 0; m < 16; m++) o[(size_t)m * c.frames] = fmaxf(v[m], lo_s);
+        }
+    }
 }
 
 // slaney mel scale helpers, Float arithmetic like the reference (AudioPreprocessing.swift:61-164)
@@ -360,6 +416,9 @@ void mel_tables_create(MelTables* t) {
         t->fb_round_off[j + 1] = t->fb_round_off[j] + mw;
     }
     t->fb_rows = t->fb_round_off[MEL_ROUNDS];
+    for (int j = 0; j < MEL_ROUNDS; j++)  // the kernel's tap loops are unrolled for exactly these widths
+        Q3_CHECK(t->fb_round_off[j + 1] - t->fb_round_off[j] == FB_WIDTHS[j] && t->fb_rows == FB_ROWS, 2,
+                 "mel filterbank round widths differ from the kernel's compile-time table");
     std::vector<float> fbw((size_t)t->fb_rows * 16, 0.0f);
     for (int j = 0; j < MEL_ROUNDS; j++) {
         const int mw = t->fb_round_off[j + 1] - t->fb_round_off[j];
@@ -408,10 +467,11 @@ void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelC
     p.total_tiles = total_tiles;
     p.gmax = d_gmax;
     p.tmin = d_tmin;
+    p.tclip = reinterpret_cast<int*>(d_tmin + total_tiles);  // d_tmin holds 2 * total_tiles words: [minimum | clip]
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
     const int grid = std::min(total_tiles, num_sms * 4);
     mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
-    mel_clamp_kernel<<<total_tiles, 128, 0, st>>>(d_out, d_clips, batch, total_tiles, d_gmax, d_tmin);
+    mel_clamp_kernel<<<(total_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, total_tiles, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());
 }
 

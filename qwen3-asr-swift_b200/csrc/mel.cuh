@@ -46,7 +46,7 @@ void mel_filterbank_host(float* fb);
 //   d_pcm    packed samples
 //   d_out    packed [128, frames_b] fp32 blocks
 //   d_gmax   [batch] int scratch (ordered-int encoded clip maxima)
-//   d_tmin   [total_tiles] float scratch (per-tile minima)
+//   d_tmin   [2 * total_tiles] words of scratch: per-tile minima (float), then per-tile clip indices (int)
 // total_tiles = sum of ntiles.  Two launches: main kernel, clamp pass (exits early per tile).
 void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelClip* d_clips, int batch,
                 int total_tiles, int* d_gmax, float* d_tmin, int num_sms, cudaStream_t st);
