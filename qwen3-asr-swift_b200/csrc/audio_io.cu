@@ -77,7 +77,7 @@ size_t wav_parse(const uint8_t* data, size_t size, float* out, size_t cap, int* 
 //   h(t) = fc * sinc(fc * t) * I0(10 * sqrt(1 - (t/half)^2)) / I0(10)      |t| < half      (Kaiser, beta = 10)
 //   y[j] = sum_{k=-K}^{K+1} tap[p][k] * x[i0 + k],  i0 = floor(j*M/L), p = (j*M) mod L, tap[p][k] = h(p/L - k) / sum_k h(p/L - k)
 // (x = 0 outside the clip; K = ceil(half); taps in double, stored as float; the sum runs in ascending k with fp32 FMAs).
-// oracle/resample.py restates exactly this.
+// oracle/audio_io.py restates exactly this.
 // ------------------------------------------------------------------------------------------
 size_t resample_len(size_t n, int in_rate, int out_rate) {
     if (in_rate == out_rate) return n;
@@ -144,10 +144,22 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
     const float* tp = taps + (size_t)p * nt;
     float acc = 0.f;
     const long long lo = i0 - K;
-    for (int t = 0; t < nt; t++) {
-        const long long i = lo + t;
-        const float v = (i >= 0 && i < n) ? __ldg(x + i) : 0.f;
-        acc = fmaf(__ldg(tp + t), v, acc);
+    if (lo >= 0 && lo + nt <= n) {  // interior: no bounds checks, four taps per step (nt = 2K + 2 is even)
+        const float* xp = x + lo;
+        int t = 0;
+        for (; t + 4 <= nt; t += 4) {
+            acc = fmaf(__ldg(tp + t), __ldg(xp + t), acc);
+            acc = fmaf(__ldg(tp + t + 1), __ldg(xp + t + 1), acc);
+            acc = fmaf(__ldg(tp + t + 2), __ldg(xp + t + 2), acc);
+            acc = fmaf(__ldg(tp + t + 3), __ldg(xp + t + 3), acc);
+        }
+        for (; t < nt; t++) acc = fmaf(__ldg(tp + t), __ldg(xp + t), acc);
+    } else {
+        for (int t = 0; t < nt; t++) {
+            const long long i = lo + t;
+            const float v = (i >= 0 && i < n) ? __ldg(x + i) : 0.f;
+            acc = fmaf(__ldg(tp + t), v, acc);
+        }
     }
     y[j] = acc;
 }

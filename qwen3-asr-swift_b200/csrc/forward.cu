@@ -515,9 +515,11 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed
         e.ldo = c.dec_vocab;
         gemm(bs->dlast.as<bf16>(), H, B, H, m.embed, c.dec_vocab, e, st);
         sample_launch(bs->logits_bf.as<bf16>(), nullptr, c.dec_vocab, c.dec_vocab, bs->st_out_ids.as<int32_t>(), bs->max_tokens,
-                      bs->st_out_len.as<int>(), bs->sampling, bs->st_scalars.as<int>() + 1, B, bs->st_next_tok.as<int32_t>(),
+                      bs->st_out_len.as<int>(), bs->sampling, bs->st_scalars.as<int>() + 1, B, bs->amax_val.as<float>(), bs->amax_idx.as<int>(),
+                      st);
+        argmax_reduce(bs->amax_val.as<float>(), bs->amax_idx.as<int>(), B, sample_parts(c.dec_vocab), bs->st_next_tok.as<int32_t>(),
                       bs->st_next_val.as<float>(), st);
-        h->launches++;
+        h->launches += 2;
         return;
     }
     const int bn = env_int("Q3ASR_LM_BN", 0) > 0 ? env_int("Q3ASR_LM_BN", 0) : gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
@@ -808,10 +810,13 @@ void align_indices(Handle* h, const float* const* pcm, const size_t* n, const in
     }
     const int H = c.dec_hidden, NP = m.cls_pad;
     // scratch: [rows | gen_len zeros | tokens] ints, normed rows, bf16 logits
-    bs->amax_idx.reserve(sizeof(int) * (size_t)(3 * P + 4));
+    const int parts = sample_parts(c.classify_num);
+    bs->amax_idx.reserve(sizeof(int) * (size_t)((3 + 2 * parts) * P + 4));
     int* d_rows = bs->amax_idx.as<int>();
     int* d_zero = d_rows + P;
     int32_t* d_tok = reinterpret_cast<int32_t*>(d_zero + P);
+    int* d_pidx = reinterpret_cast<int*>(d_tok + P);
+    float* d_pval = reinterpret_cast<float*>(d_pidx + (size_t)parts * P);
     bs->h_ints.reserve(sizeof(int) * (size_t)(3 * P + 4));
     int* hrows = bs->h_ints.as<int>();
     for (int i = 0; i < P; i++) { hrows[i] = rows[(size_t)i]; hrows[P + i] = 0; }
@@ -827,8 +832,9 @@ void align_indices(Handle* h, const float* const* pcm, const size_t* n, const in
     e.bias = m.cls_b;
     gemm(bs->dlast.as<bf16>(), H, P, H, m.cls_w, NP, e, st);
     SamplingParams greedy;
-    sample_launch(bs->logits_bf.as<bf16>(), nullptr, NP, c.classify_num, d_tok, 1, d_zero, greedy, nullptr, P, d_tok, nullptr, st);
-    h->launches++;
+    sample_launch(bs->logits_bf.as<bf16>(), nullptr, NP, c.classify_num, d_tok, 1, d_zero, greedy, nullptr, P, d_pval, d_pidx, st);
+    argmax_reduce(d_pval, d_pidx, P, parts, d_tok, nullptr, st);
+    h->launches += 2;
     Q3_CUDA(cudaMemcpyAsync(hrows + 2 * P, d_tok, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, st));
     Q3_CUDA(cudaStreamSynchronize(st));
     int k = 0;
@@ -867,19 +873,21 @@ void pick_next_token(Handle* h, const float* logits, int vocab, const int32_t* g
     sp.seed = opts->seed;
     float* d_logits = nullptr;
     int32_t* d_gen = nullptr;
-    int* d_small = nullptr;  // [gen_len, step, token]
+    int* d_small = nullptr;  // [gen_len, step, token, -, slice indices (8), slice values (8)]
     cudaStream_t st = h->stream;
     auto release = [&]() { cudaFree(d_logits); cudaFree(d_gen); cudaFree(d_small); };
     try {
         Q3_CUDA(cudaMalloc(&d_logits, sizeof(float) * vocab));
         Q3_CUDA(cudaMalloc(&d_gen, sizeof(int32_t) * std::max(n_generated, 1)));
-        Q3_CUDA(cudaMalloc(&d_small, sizeof(int) * 4));
+        Q3_CUDA(cudaMalloc(&d_small, sizeof(int) * 20));
         const int small[4] = {n_generated, draw, 0, 0};
         Q3_CUDA(cudaMemcpyAsync(d_logits, logits, sizeof(float) * vocab, cudaMemcpyHostToDevice, st));
         if (n_generated) Q3_CUDA(cudaMemcpyAsync(d_gen, generated, sizeof(int32_t) * n_generated, cudaMemcpyHostToDevice, st));
         Q3_CUDA(cudaMemcpyAsync(d_small, small, sizeof(small), cudaMemcpyHostToDevice, st));
-        sample_launch(nullptr, d_logits, vocab, vocab, d_gen, std::max(n_generated, 1), d_small, sp, d_small + 1, 1, d_small + 2, nullptr, st);
-        h->launches++;
+        sample_launch(nullptr, d_logits, vocab, vocab, d_gen, std::max(n_generated, 1), d_small, sp, d_small + 1, 1,
+                      reinterpret_cast<float*>(d_small + 12), d_small + 4, st);
+        argmax_reduce(reinterpret_cast<float*>(d_small + 12), d_small + 4, 1, sample_parts(vocab), d_small + 2, nullptr, st);
+        h->launches += 2;
         Q3_CUDA(cudaMemcpyAsync(token, d_small + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         Q3_CUDA(cudaStreamSynchronize(st));
     } catch (...) {

@@ -903,8 +903,10 @@ __device__ __forceinline__ unsigned long long splitmix64_dev(unsigned long long 
 template <typename T>
 __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logits, int ld, int vocab, const int32_t* __restrict__ gen_ids,
                                                        int gen_stride, const int* __restrict__ gen_len, SamplingParams sp,
-                                                       const int* __restrict__ step, int32_t* __restrict__ next_tok,
-                                                       float* __restrict__ next_val) {
+                                                       const int* __restrict__ step, float* __restrict__ part_val,
+                                                       int* __restrict__ part_idx) {
+    // grid (sequence, slice): gridDim.y CTAs share a row's vocabulary scan (the bitmaps are rebuilt by each, they are tiny);
+    // argmax_reduce_kernel merges the slices (first maximum)
     ptx::grid_dep_launch();
     ptx::grid_dep_wait();
     extern __shared__ unsigned int s_bits[];
@@ -942,7 +944,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logi
     const unsigned long long key = splitmix64_dev(sp.seed ^ ((unsigned long long)(step ? *step : 0) << 32) ^ (unsigned long long)seq);
     float best = -INFINITY;
     int bidx = 0x7fffffff;
-    for (int i = tid; i < vocab; i += blockDim.x) {
+    const int per = (vocab + gridDim.y - 1) / gridDim.y;
+    const int i_end = min(vocab, ((int)blockIdx.y + 1) * per);
+    for (int i = blockIdx.y * per + tid; i < i_end; i += blockDim.x) {
         float v = (float)row[i];
         const unsigned int bit = 1u << (i & 31);
         if (seen[i >> 5] & bit) v = v > 0.f ? v / sp.repetition_penalty : v * sp.repetition_penalty;
@@ -970,9 +974,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const T* __restrict__ logi
             const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
             if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
         }
-        if (tid == 0) {
-            next_tok[seq] = bidx == 0x7fffffff ? 0 : bidx;
-            if (next_val) next_val[seq] = best;
+        if (tid == 0) {  // an all -inf slice reports index 0 of ITS slice start only through the value: the reducer keeps the first maximum
+            part_val[(size_t)seq * gridDim.y + blockIdx.y] = best;
+            part_idx[(size_t)seq * gridDim.y + blockIdx.y] = bidx == 0x7fffffff ? 0 : bidx;
         }
     }
 }
@@ -1134,19 +1138,22 @@ void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st) {
     launch_kernel(decode_advance_kernel, 1, 1024, 0, st, s, n_seqs);
 }
 
+int sample_parts(int vocab) { return vocab >= 32768 ? 4 : 1; }
+
 void sample_launch(const bf16* logits_bf16, const float* logits_f32, int ld, int vocab, const int32_t* gen_ids, int gen_stride,
-                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, int32_t* next_tok, float* next_val,
+                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, float* part_val, int* part_idx,
                    cudaStream_t st) {
     if (n_seqs <= 0) return;
     Q3_CHECK(vocab > 0 && vocab <= 160 * 1024, 1, "sample: vocabulary too large for the shared-memory bitmaps");
     Q3_CHECK((logits_bf16 != nullptr) != (logits_f32 != nullptr), 1, "sample: exactly one logits pointer");
+    Q3_CHECK(part_val != nullptr && part_idx != nullptr, 1, "sample: null scratch");
     const size_t smem = (size_t)2 * ((vocab + 31) / 32) * sizeof(unsigned int);
+    const int parts = sample_parts(vocab);
+    const dim3 grid(n_seqs, parts);
     if (logits_bf16)
-        launch_kernel(sample_kernel<bf16>, n_seqs, 1024, smem, st, logits_bf16, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, next_tok,
-                      next_val);
+        launch_kernel(sample_kernel<bf16>, grid, 1024, smem, st, logits_bf16, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, part_val, part_idx);
     else
-        launch_kernel(sample_kernel<float>, n_seqs, 1024, smem, st, logits_f32, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, next_tok,
-                      next_val);
+        launch_kernel(sample_kernel<float>, grid, 1024, smem, st, logits_f32, ld, vocab, gen_ids, gen_stride, gen_len, sp, step, part_val, part_idx);
 }
 
 void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st) {

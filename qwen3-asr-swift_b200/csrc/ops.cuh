@@ -105,9 +105,12 @@ struct SamplingParams {
     unsigned long long seed = 0;
 };
 // logits: [n_seqs, ld] (bf16 or fp32); gen_ids: [n_seqs, gen_stride] with gen_len[seq] valid entries; step: device counter that
-// varies the noise per decode step (may be null); writes next_tok[seq] (and next_val[seq], the adjusted score, if non-null).
+// varies the noise per decode step (may be null).  A row's vocabulary is scanned by sample_parts(vocab) CTAs; each writes its best
+// adjusted score and index to part_val / part_idx [n_seqs, sample_parts(vocab)], to be merged by argmax_reduce (gemm.cuh), which
+// keeps the first maximum.
+int sample_parts(int vocab);
 void sample_launch(const bf16* logits_bf16, const float* logits_f32, int ld, int vocab, const int32_t* gen_ids, int gen_stride,
-                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, int32_t* next_tok, float* next_val,
+                   const int* gen_len, const SamplingParams& sp, const int* step, int n_seqs, float* part_val, int* part_idx,
                    cudaStream_t st);
 
 void fill_i32_launch(int* p, int v, size_t n, cudaStream_t st);
