@@ -719,9 +719,10 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     float* stage_raw = stage + bs->mel.pcm_floats;  // clips awaiting conversion
     if (raw_floats) bs->raw_pcm.reserve(sizeof(float) * raw_floats);
     // The caller's buffers are pageable: copy each clip into the pinned staging area and queue its H2D copy at once, from a
-    // few host threads, so the staging memcpy (the slow leg, ~10 GB/s per thread) overlaps the PCIe transfers and the planning
+    // few host threads (4: as fast as 6 or 8 for one rank, and 8 ranks x 4 do not oversubscribe a 32-core box), so the staging memcpy
+    // (the slow leg, ~10 GB/s per thread) overlaps the PCIe transfers and the planning
     // below.  Clips are independent, so the order of the copies on the stream does not matter.
-    const int n_workers = std::max(1, std::min({batch, 6, (int)std::thread::hardware_concurrency() / 2}));
+    const int n_workers = std::max(1, std::min({batch, env_int("Q3ASR_UPLOAD_THREADS", 4), (int)std::thread::hardware_concurrency() / 2}));
     std::vector<std::thread> workers;
     std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
     for (int w = 0; w < n_workers; w++)
