@@ -115,3 +115,30 @@ def test_gpu_align_words_and_errors(aligner, tiny_model):
         tiny_model.align_indices([synth.clip(0, 16000)], [[2007, 5, 2007]], [[0, 2]])
     with pytest.raises(q3asr.Q3Error, match="outside the slotted text"):
         aligner.align_indices([synth.clip(0, 16000)], [[2007, 5, 2007]], [[0, 3]])
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_aligner_properties(built_lib):
+    """Qwen3-ForcedAligner-0.6B dimensions (24-layer 1024-wide encoder projecting to the 1024-wide decoder, 5000 classes,
+    ForcedAligner.swift:57-85): a 20 s clip with 40 words — class range, batch invariance, monotone word times."""
+    import time
+    m = built_lib.Qwen3ASRModel.random_init("aligner", seed=7)
+    try:
+        rng = np.random.default_rng(8)
+        words = [rng.integers(1000, 100000, size=int(rng.integers(1, 4))).tolist() for _ in range(40)]
+        x = synth.clip(4, 16000 * 20)
+        t0 = time.perf_counter()
+        out = m.align(x, words, words=[str(i) for i in range(40)])
+        dt = time.perf_counter() - t0
+        assert len(out) == 40 and all(0.0 <= w["start_time"] <= w["end_time"] <= 5000 * 0.08 for w in out)
+        starts = [w["start_time"] for w in out]
+        assert all(b >= a for a, b in zip(starts, starts[1:]))
+        ids, pos = [], []
+        for w in words:
+            pos.append(len(ids)); ids.append(151705); ids += w; pos.append(len(ids)); ids.append(151705)
+        a = m.align_indices([x, x[:16000 * 7]], [ids, ids[:30]], [pos, [p for p in pos if p < 30]])
+        b = m.align_indices([x], [ids], [pos])
+        assert a[0].tolist() == b[0].tolist() and (a[0] >= 0).all() and (a[0] < 5000).all() and len(a[1]) == len([p for p in pos if p < 30])
+        print(f"align of 20 s / 40 words: {dt * 1000:.1f} ms (first call, includes buffer allocation)")
+    finally:
+        m.close()
