@@ -95,7 +95,7 @@ def clip_indices(rank, per_gpu=None):
 
 
 def make_clips(rank):
-    from oracle import synth  # input data generator shared with the tests (not oracle arithmetic)
+    from q3asr import synth  # input data generator shared with the tests (not oracle arithmetic)
     n = CLIP_SECONDS * 16000
     return [synth.clip(i, n) for i in clip_indices(rank)]
 
@@ -117,7 +117,8 @@ def cpu_sample(seconds, tokens, clips=1, state_dict=None, threads=None):
     import torch
     from oracle import mel as omel
     from oracle import model as omodel
-    from oracle import synth, weights
+    from oracle import weights
+    from q3asr import synth
     cfg = weights.preset(MODEL)
     if state_dict is None:
         state_dict = weights.random_state_dict(cfg, SEED)

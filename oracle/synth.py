@@ -1,18 +1,11 @@
-"""Synthetic 16 kHz audio for parity and benchmarks.
+"""The shared synthetic-audio recipe (qwen3-asr-swift_b200/q3asr/synth.py: input data, not oracle arithmetic), re-exported so the
+tests can keep writing `from oracle import synth`."""
+import importlib.util
+import os
 
-Recipe of the reference's own fixture generator
-(/root/reference/scripts/kws/generate_fbank_reference.py:33-40):
-0.4*sin(2*pi*440 t) + 0.2*sin(2*pi*1200 t) + 0.05*N(0,1), default_rng(20260418 + i).
-This is input data, not oracle arithmetic; bench.py and the tests share it.
-"""
-import numpy as np
-
-SEED = 20260418
-
-
-def clip(i, n_samples, sr=16000):
-    rng = np.random.default_rng(SEED + int(i))
-    t = np.arange(n_samples, dtype=np.float64) / sr
-    x = 0.4 * np.sin(2 * np.pi * 440.0 * t) + 0.2 * np.sin(2 * np.pi * 1200.0 * t)
-    x = x + 0.05 * rng.standard_normal(n_samples)
-    return np.clip(x, -1.0, 1.0).astype(np.float32)
+_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qwen3-asr-swift_b200", "q3asr", "synth.py")
+_spec = importlib.util.spec_from_file_location("_q3asr_synth", _path)
+_mod = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mod)
+SEED = _mod.SEED
+clip = _mod.clip

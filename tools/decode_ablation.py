@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
 import q3asr  # noqa: E402
-from oracle import synth  # noqa: E402
+from q3asr import synth  # noqa: E402  (input data only)
 
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 64

@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
 import q3asr  # noqa: E402
-from oracle import synth  # noqa: E402  (input generator only)
+from q3asr import synth  # noqa: E402  (input data only)
 
 m = q3asr.Qwen3ASRModel("tiny")
 clips = [synth.clip(i, 480000) for i in range(64)]
