@@ -40,7 +40,7 @@ def test_presets_match_reference_configs(built_lib):
         built_lib.preset("7B")
     # the NumPy twin of the presets used by the oracle agrees
     from oracle import weights
-    for name in ("0.6B", "1.7B", "tiny"):
+    for name in ("0.6B", "1.7B", "tiny", "aligner", "tiny-aligner"):
         c, o = built_lib.preset(name).as_dict(), weights.preset(name)
         for k, v in o.items():
             assert abs(c[k] - v) <= 1e-6 * max(1.0, abs(v)), (name, k)
