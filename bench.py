@@ -343,9 +343,18 @@ def main():
             n_launch = (MAX_TOKENS - 1) * 28  # both model sizes have 28 decoder layers (Configuration.swift:47-100)
             prompt = q3asr.encoder_tokens(CLIP_SECONDS * 100) + 16
             kv_avg = CLIPS_PER_GPU * (prompt + (MAX_TOKENS + 1) / 2.0) * 4096.0  # mean K+V bytes one layer's attention reads per step
-            roof["in_graph"] = {"us_per_launch": (full - without) * 1000.0 / n_launch, "achieved": kv_avg / ((full - without) / n_launch) / 1e6,
-                                "frac": kv_avg / ((full - without) / n_launch) / 1e6 / pk["hbm"],
-                                "how": "decode stage time minus the same with attention launches dropped, / launches"}
+            # The timed region replays the decode step as a CUDA graph with programmatic dependent launch, so the duration that
+            # matters is the kernel's duration THERE; a lone launch bracketed by events (no prologue overlap, launch latency inside
+            # the bracket) is kept beside it as "standalone".
+            us = (full - without) * 1000.0 / n_launch
+            roof["standalone"] = {k: roof[k] for k in ("achieved", "frac", "ms_per_launch", "algorithmic_per_launch")}
+            roof["standalone"]["how"] = "CUDA events around each eager launch in extra profiled steps (no PDL overlap)"
+            roof.update({"achieved": kv_avg / us / 1e3, "frac": kv_avg / us / 1e3 / pk["hbm"], "ms_per_launch": us / 1000.0,
+                         "algorithmic_per_launch": kv_avg, "launches_per_step": n_launch,
+                         "est_share_of_step": us * n_launch / 1000.0 / (dev_ms / args.steps),
+                         "how": "CUDA events around the decode stage of the same workload with and without the attention launches "
+                                "(Q3ASR_DEC_SKIP), difference / launches: the kernel's duration inside the replayed graph"})
+            roof["in_graph"] = {"us_per_launch": us, "achieved": roof["achieved"], "frac": roof["frac"]}
         # the top dense tensor-core family (encoder / prefill GEMMs and convolutions; the decode-step products are weight streaming)
         tens = [k for _, k in ranked if rep[k]["flops"] > 0 and not k.startswith("dec_") and k != "lm_head" and not k.endswith("attn")]
         roof_gemm = roof_of(tens[0]) if tens else None
