@@ -179,7 +179,7 @@ void model_load_safetensors(Handle* h, const char* dir) {
     std::vector<std::pair<std::string, std::vector<int64_t>>> specs;
     model_tensor_specs(h->cfg, &specs);
 
-    // pass 1: index every audio_tower.* / model.* entry of every file
+    // pass 1: index every audio_tower.* / model.* / lm_head.* entry of every file
     std::map<std::string, Located> index;
     std::vector<FILE*> fps(files.size(), nullptr);
     auto close_all = [&]() {
@@ -195,7 +195,11 @@ void model_load_safetensors(Handle* h, const char* dir) {
             std::string hdr(hl, 0);
             Q3_CHECK(fread(&hdr[0], 1, hl, fps[fi]) == hl, Q3ASR_ERR_IO, "load_safetensors: truncated header in " + files[fi]);
             for (Entry& e : parse_header(hdr)) {
-                if (e.name.compare(0, 12, "audio_tower.") != 0 && e.name.compare(0, 6, "model.") != 0) continue;
+                // the forced-aligner checkpoints carry a "thinker." prefix and keep the classification head under lm_head.*
+                // (WeightLoading.swift:162-179); everything else is ignored
+                if (e.name.compare(0, 8, "thinker.") == 0) e.name = e.name.substr(8);
+                if (e.name.compare(0, 12, "audio_tower.") != 0 && e.name.compare(0, 6, "model.") != 0 && e.name.compare(0, 8, "lm_head.") != 0)
+                    continue;
                 Located l;
                 l.e = e;
                 l.file = (int)fi;

@@ -116,3 +116,25 @@ def test_load_errors(built_lib, tmp_path):
         assert not m.is_loaded
     finally:
         m.close()
+
+
+def test_load_forced_aligner_checkpoint(built_lib, tmp_path):
+    """The aligner checkpoints prefix every key with "thinker." and keep the classification head under lm_head.*
+    (WeightLoading.swift:162-179, 229)."""
+    src = built_lib.Qwen3ASRModel.random_init("tiny-aligner", seed=5)
+    try:
+        names = src.tensor_names()
+        assert ("lm_head.weight", (70, 128)) in names and ("lm_head.bias", (70,)) in names
+        sd = {n: src.get_tensor(n, shp) for n, shp in names}
+        x = synth.clip(2, 30000)
+        ids, pos = [2007, 11, 12, 2007, 2007, 13, 2007], [0, 3, 4, 6]
+        want = src.align_indices([x], [ids], [pos])[0]
+    finally:
+        src.close()
+    write_safetensors(tmp_path / "model.safetensors", {"thinker." + n: ("BF16", _bf16_bits(w)) for n, w in sd.items()})
+    m = built_lib.Qwen3ASRModel.from_pretrained(str(tmp_path), size="tiny-aligner")
+    try:
+        assert m.is_loaded
+        assert m.align_indices([x], [ids], [pos])[0].tolist() == want.tolist()
+    finally:
+        m.close()
