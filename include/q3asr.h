@@ -270,7 +270,8 @@ int q3asr_longform_plan(size_t n_samples, size_t window, size_t min_tail, size_t
  * 32 gate / 32 up rows), 2 fp32, 3 argmax.
  * use_simt != 0 runs the CUDA-core checker kernel instead of tcgen05.  out: bf16 as uint16 (epi 0,1: [M,N] / [M,N/2]),
  * fp32 (epi 2) or int32 argmax ids [M] (epi 3). bn = 0 picks the tile width.
- * epi 4,5 run the decode-step weight-streaming kernel (M <= 128): 4 split-K fp32 partials summed -> fp32 [M,N]; 5 bf16 [M,N]. */
+ * epi 4,5 run the decode-step weight-streaming kernel (M <= 128): 4 split-K fp32 partials summed -> fp32 [M,N]; 5 bf16 [M,N];
+ * epi 7 runs the decode-step LM-head kernel (M <= 128): int32 argmax ids [M]. */
 int q3asr_debug_gemm(q3asr_handle* h, const uint16_t* A, const uint16_t* W, const uint16_t* bias, const uint16_t* resid, int M,
                      int N, int K, int epi, int gelu, int bn, int use_simt, void* out);
 /* 3x3 stride-2 pad-1 NHWC convolution as implicit GEMM: in [B,H,W,C] bf16, w [O,3,3,C] bf16, out [B,OH,OW,O] bf16 (+bias, GELU) */

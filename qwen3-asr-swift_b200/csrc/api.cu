@@ -389,6 +389,33 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
                      int K, int epi, int gelu, int bn, int use_simt, void* out) {
     return guarded(hh, [&](Handle& h) {
         Q3_CHECK(A && W && out && M > 0 && N > 0 && K > 0, Q3ASR_ERR_INVALID, "debug_gemm: bad argument");
+        if (epi == 7) {  // decode-step LM head (lmhead.cuh): int32 argmax ids [M]
+            bf16 *dA, *dW;
+            float* dv;
+            int* di;
+            int32_t* dtok;
+            const int tiles = lmhead_tiles(N);
+            Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
+            Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
+            Q3_CUDA(cudaMalloc(&dv, sizeof(float) * (size_t)M * tiles));
+            Q3_CUDA(cudaMalloc(&di, sizeof(int) * (size_t)M * tiles));
+            Q3_CUDA(cudaMalloc(&dtok, sizeof(int32_t) * (size_t)M));
+            cudaError_t se = cudaSuccess;
+            try {
+                Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
+                Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+                lmhead_argmax(dA, K, M, K, dW, N, dv, di, h.stream);
+                argmax_reduce(dv, di, M, tiles, dtok, nullptr, h.stream);
+                se = cudaStreamSynchronize(h.stream);
+                if (se == cudaSuccess) se = cudaMemcpy(out, dtok, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost);
+            } catch (...) {
+                cudaFree(dA); cudaFree(dW); cudaFree(dv); cudaFree(di); cudaFree(dtok);
+                throw;
+            }
+            cudaFree(dA); cudaFree(dW); cudaFree(dv); cudaFree(di); cudaFree(dtok);
+            Q3_CUDA(se);
+            return;
+        }
         if (epi >= 4) {  // decode-step weight-streaming kernel (skinny.cuh): 4 split-K partials (summed here), 5 store
             Q3_CHECK(epi <= 5, Q3ASR_ERR_INVALID, "debug_gemm: bad epilogue");
             const int sk = epi - 4;

@@ -522,6 +522,14 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed
         h->launches += 2;
         return;
     }
+    if (B <= SKINNY_MAX_ROWS && env_int("Q3ASR_LM_GENERAL", 0) == 0) {
+        // decode-step shape (few token rows): the persistent weight-streaming kernel of lmhead.cuh
+        lmhead_argmax(bs->dlast.as<bf16>(), H, B, H, m.embed, c.dec_vocab, bs->amax_val.as<float>(), bs->amax_idx.as<int>(), st);
+        argmax_reduce(bs->amax_val.as<float>(), bs->amax_idx.as<int>(), B, lmhead_tiles(c.dec_vocab), bs->st_next_tok.as<int32_t>(),
+                      bs->st_next_val.as<float>(), st);
+        h->launches++;
+        return;
+    }
     const int bn = env_int("Q3ASR_LM_BN", 0) > 0 ? env_int("Q3ASR_LM_BN", 0) : gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
     GemmEpiArgs e;
     e.epi = EPI_ARGMAX;

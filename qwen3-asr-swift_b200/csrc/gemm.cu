@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "gemm2.cuh"
+#include "lmhead.cuh"
 #include "skinny.cuh"
 
 namespace q3 {
@@ -421,6 +422,58 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
         case 32: launch_skinny_nb<32>(epi, deep, tw, tx, p, grid, st); break;
         case 64: launch_skinny_nb<64>(epi, deep, tw, tx, p, grid, st); break;
         default: launch_skinny_nb<128>(epi, deep, tw, tx, p, grid, st); break;
+    }
+    Q3_CUDA(cudaGetLastError());
+    g_launches++;
+}
+
+namespace {
+template <int NB>
+void launch_lmhead(const CUtensorMap& tw, const CUtensorMap& tx, const LmHeadDev& p, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        Q3_CUDA(cudaFuncSetAttribute(lmhead_argmax_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lmh_smem_bytes(NB)));
+        attr_set = true;
+    }
+    launch_kernel(lmhead_argmax_kernel<NB>, grid, 256, lmh_smem_bytes(NB), st, tw, tx, p);
+}
+}  // namespace
+
+int lmhead_tiles(int N) { return cdiv(N, SK_BM); }
+
+void lmhead_argmax(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, float* amax_val, int* amax_idx, cudaStream_t st) {
+    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "lmhead_argmax: 1..128 token rows per launch");
+    Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0 && amax_val && amax_idx, 1, "lmhead_argmax: bad argument");
+    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
+    LmHeadDev p;
+    memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.Mtok = Mtok;
+    p.num_kb = cdiv(K, SK_BK);
+    p.tiles = lmhead_tiles(N);
+    p.amax_val = amax_val;
+    p.amax_idx = amax_idx;
+    CUtensorMap tw, tx;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)SK_BK, (cuuint32_t)SK_BM};
+        cuuint32_t es[2] = {1, 1};
+        make_tmap(&tw, W, 2, dims, str, box, es);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Mtok};
+        cuuint64_t str[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {(cuuint32_t)SK_BK, (cuuint32_t)nb};
+        cuuint32_t es[2] = {1, 1};
+        make_tmap(&tx, X, 2, dims, str, box, es);
+    }
+    const int grid = std::min(p.tiles, g_num_sms);
+    switch (nb) {
+        case 16: launch_lmhead<16>(tw, tx, p, grid, st); break;
+        case 32: launch_lmhead<32>(tw, tx, p, grid, st); break;
+        case 64: launch_lmhead<64>(tw, tx, p, grid, st); break;
+        default: launch_lmhead<128>(tw, tx, p, grid, st); break;
     }
     Q3_CUDA(cudaGetLastError());
     g_launches++;

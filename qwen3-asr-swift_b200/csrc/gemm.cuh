@@ -433,6 +433,10 @@ enum SkinnyEpi : int {
 int gemm_skinny_splits(int N, int K, int epi);
 // SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo]
 void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, cudaStream_t st);
+// Decode-step LM head (lmhead.cuh): per 128-row vocabulary tile the (value, index) of the first maximum of bf16(X E^T) for every token
+// row, amax_val / amax_idx [Mtok, lmhead_tiles(N)], to be merged by argmax_reduce.  Mtok <= 128.
+int lmhead_tiles(int N);
+void lmhead_argmax(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, float* amax_val, int* amax_idx, cudaStream_t st);
 // final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
 void argmax_reduce(const float* val, const int* idx, int rows, int tiles, int32_t* out, float* out_val, cudaStream_t st);
 

@@ -4,6 +4,7 @@
 // Key contract: /root/reference/Sources/Qwen3ASR/WeightLoading.swift:17-126 (audio_tower.* / model.*
 // prefixes), :235-323 (per-module names).  Linear.weight is [out, in]; Conv2d.weight is MLX layout
 // [O, kH, kW, I] (:54-56).  The ASR model has no lm_head: the embedding is tied (Qwen3ASR.swift:253-256).
+#include <stdlib.h>
 #include <string.h>
 
 #include "model.h"

@@ -651,7 +651,7 @@ class Qwen3ASRModel:
         r = f32_to_bf16_bits(resid) if resid is not None else None
         if epi in (EPI_F32, EPI_SKINNY_PARTIAL):
             out = np.empty((M, N), dtype=np.float32)
-        elif epi == EPI_ARGMAX:
+        elif epi in (EPI_ARGMAX, 7):  # 7: the decode-step LM-head kernel (lmhead.cuh)
             out = np.empty(M, dtype=np.int32)
         elif epi == EPI_SWIGLU:
             out = np.empty((M, N // 2), dtype=np.uint16)

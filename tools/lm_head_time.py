@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""LM-head time per launch (profiling mode, CUDA events) for the tile widths in Q3ASR_LM_BN.  Usage: python tools/lm_head_time.py [size]"""
+"""LM-head time per launch (profiling mode, CUDA events): general kernel vs lmhead.cuh.
+Usage: python tools/lm_head_time.py [size]"""
 import os
 import sys
 
@@ -13,8 +14,8 @@ size = sys.argv[1] if len(sys.argv) > 1 else "0.6B"
 m = q3asr.Qwen3ASRModel.random_init(size)
 m.batch_upload([synth.clip(i, 16000 * 5) for i in range(64)])
 ref = None
-for bn in (0, 128, 64, 32, 0):
-    os.environ["Q3ASR_LM_BN"] = str(bn)
+for name, env in (("general kernel", dict(Q3ASR_LM_GENERAL="1")), ("lmhead.cuh", dict(Q3ASR_LM_GENERAL="0")), ("general kernel", dict(Q3ASR_LM_GENERAL="1"))):
+    os.environ.update(env)
     m.profile(True)
     for _ in range(5):
         m.batch_run(q3asr.STAGE_ALL, 3, False)
@@ -25,5 +26,5 @@ for bn in (0, 128, 64, 32, 0):
     flat = [t.tolist() for t in ids]
     ref = ref or flat
     r = rep["lm_head"]
-    print(f"{size} bn={bn:4d} lm_head {r['ms'] / r['launches'] * 1000:7.2f} us/launch ({r['launches']} launches)  ids_same {flat == ref}", flush=True)
+    print(f"{size} {name:18s} lm_head {r['ms'] / r['launches'] * 1000:7.2f} us/launch ({r['launches']} launches)  ids_same {flat == ref}", flush=True)
 m.close()
