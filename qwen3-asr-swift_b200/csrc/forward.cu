@@ -530,7 +530,7 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed
         h->launches++;
         return;
     }
-    const int bn = env_int("Q3ASR_LM_BN", 0) > 0 ? env_int("Q3ASR_LM_BN", 0) : gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
+    const int bn = gemm_pick_bn(c.dec_vocab, EPI_ARGMAX, 1);
     GemmEpiArgs e;
     e.epi = EPI_ARGMAX;
     e.amax_val = bs->amax_val.as<float>();
