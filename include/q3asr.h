@@ -217,6 +217,18 @@ int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size
 int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
                                    const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos,
                                    int max_batch_per_gpu, int32_t* ids_out, int* lens_out);
+/* Submit / wait form of the call above (the "optional submit/poll pair" of the scheduler): the batch runs on a thread of the
+ * library while the caller prepares the next one.  The sample, prompt-id and sample-rate arrays are borrowed until q3asr_job_wait
+ * returns (the pointer tables themselves are copied); jobs of one pool run one after the other.  q3asr_job_wait blocks, copies
+ * ids [batch, max_tokens] / lens [batch] out and may be called once; q3asr_job_free joins if needed. */
+typedef struct q3asr_job q3asr_job;
+int q3asr_pool_submit(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                      const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos, int max_batch_per_gpu,
+                      q3asr_job** job);
+int q3asr_job_done(const q3asr_job* job);
+int q3asr_job_wait(q3asr_job* job, int32_t* ids_out, int* lens_out);
+const char* q3asr_job_last_error(const q3asr_job* job);
+void q3asr_job_free(q3asr_job* job);
 /* the scheduler's assignment alone (host logic; no GPU needed): gpu_out[i] = GPU of utterance i */
 int q3asr_schedule(const size_t* n_samples, int batch, int n_gpus, int* gpu_out);
 

@@ -7,6 +7,8 @@
 // GPU, lets one worker thread per GPU run its share in length-sorted sub-batches, and gathers the ids on
 // the host.  No collective touches the data path.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <numeric>
 #include <thread>
 
@@ -17,6 +19,22 @@ using namespace q3;
 struct q3asr_pool {
     std::vector<q3asr_handle*> handles;
     std::string last_error;
+    std::mutex run_mu;  // one batch at a time on the pool's handles (submitted jobs queue on it in submission order of their threads)
+};
+
+// an asynchronous q3asr_pool_transcribe_ids_opts call: the worker thread owns the result buffers until q3asr_job_wait copies them out
+struct q3asr_job {
+    std::thread worker;
+    std::atomic<int> done{0};
+    int rc = Q3ASR_OK;
+    int batch = 0, max_tokens = 0;
+    std::vector<int32_t> ids;
+    std::vector<int> lens;
+    std::vector<q3asr_prompt> prompts;
+    std::vector<int> rates;
+    bool has_sampling = false;
+    q3asr_sampling sampling{};
+    std::string error;
 };
 
 extern "C" {
@@ -79,6 +97,7 @@ int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const
                                    int max_batch_per_gpu, int32_t* ids_out, int* lens_out) {
     if (p == nullptr || pcm == nullptr || n_in == nullptr || ids_out == nullptr || lens_out == nullptr || batch <= 0)
         return Q3ASR_ERR_INVALID;
+    std::lock_guard<std::mutex> run_lock(p->run_mu);
     const int G = (int)p->handles.size();
     if (max_batch_per_gpu <= 0) max_batch_per_gpu = 64;
     // the scheduler's cost model and the length sort work on 16 kHz-equivalent lengths
@@ -133,6 +152,51 @@ int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const
             return rc[g];
         }
     return Q3ASR_OK;
+}
+
+// ---- submit / wait: the blocking call on a thread of its own, so the caller can load the next files meanwhile ----
+int q3asr_pool_submit(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, const int* sample_rates, int batch,
+                      const q3asr_prompt* prompts, const q3asr_sampling* sampling, int max_tokens, int stop_on_eos, int max_batch_per_gpu,
+                      q3asr_job** out) {
+    if (p == nullptr || pcm == nullptr || n_samples == nullptr || batch <= 0 || max_tokens <= 0 || out == nullptr) return Q3ASR_ERR_INVALID;
+    q3asr_job* j = new q3asr_job();
+    j->batch = batch;
+    j->max_tokens = max_tokens;
+    j->ids.assign((size_t)batch * max_tokens, 0);
+    j->lens.assign((size_t)batch, 0);
+    if (prompts) j->prompts.assign(prompts, prompts + batch);          // the id arrays they point to stay the caller's, like the samples
+    if (sample_rates) j->rates.assign(sample_rates, sample_rates + batch);
+    if (sampling) { j->has_sampling = true; j->sampling = *sampling; }
+    std::vector<const float*> pp(pcm, pcm + batch);
+    std::vector<size_t> nn(n_samples, n_samples + batch);
+    j->worker = std::thread([p, j, pp, nn, stop_on_eos, max_batch_per_gpu]() {
+        j->rc = q3asr_pool_transcribe_ids_opts(p, pp.data(), nn.data(), j->rates.empty() ? nullptr : j->rates.data(), j->batch,
+                                               j->prompts.empty() ? nullptr : j->prompts.data(), j->has_sampling ? &j->sampling : nullptr,
+                                               j->max_tokens, stop_on_eos, max_batch_per_gpu, j->ids.data(), j->lens.data());
+        if (j->rc != Q3ASR_OK) j->error = q3asr_pool_last_error(p);
+        j->done.store(1, std::memory_order_release);
+    });
+    *out = j;
+    return Q3ASR_OK;
+}
+
+int q3asr_job_done(const q3asr_job* j) { return j != nullptr && j->done.load(std::memory_order_acquire) != 0; }
+
+int q3asr_job_wait(q3asr_job* j, int32_t* ids_out, int* lens_out) {
+    if (j == nullptr || ids_out == nullptr || lens_out == nullptr) return Q3ASR_ERR_INVALID;
+    if (j->worker.joinable()) j->worker.join();
+    if (j->rc != Q3ASR_OK) return j->rc;
+    std::copy(j->ids.begin(), j->ids.end(), ids_out);
+    std::copy(j->lens.begin(), j->lens.end(), lens_out);
+    return Q3ASR_OK;
+}
+
+const char* q3asr_job_last_error(const q3asr_job* j) { return j ? j->error.c_str() : ""; }
+
+void q3asr_job_free(q3asr_job* j) {
+    if (j == nullptr) return;
+    if (j->worker.joinable()) j->worker.join();
+    delete j;
 }
 
 }  // extern "C"

@@ -89,7 +89,7 @@ EXPORTS = [
     "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
     "q3asr_transcribe_ids_opts", "q3asr_batch_set_sampling", "q3asr_pick_next_token",
     "q3asr_align_indices", "q3asr_enforce_monotonicity", "q3asr_lis_positions", "q3asr_trailing_plateau_start",
-    "q3asr_pool_transcribe_ids_opts",
+    "q3asr_pool_transcribe_ids_opts", "q3asr_pool_submit", "q3asr_job_done", "q3asr_job_wait", "q3asr_job_last_error", "q3asr_job_free",
 ]
 
 _lib = None
@@ -148,6 +148,13 @@ def lib():
         L.q3asr_pool_destroy.restype = None
         L.q3asr_pool_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, vp, vp]
         L.q3asr_schedule.argtypes = [vp, ci, ci, vp]
+        L.q3asr_pool_submit.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(Sampling), ci, ci, ci, ctypes.POINTER(vp)]
+        L.q3asr_job_done.argtypes = [vp]
+        L.q3asr_job_wait.argtypes = [vp, vp, vp]
+        L.q3asr_job_last_error.argtypes = [vp]
+        L.q3asr_job_last_error.restype = ctypes.c_char_p
+        L.q3asr_job_free.argtypes = [vp]
+        L.q3asr_job_free.restype = None
         L.q3asr_pool_transcribe_ids_opts.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(Sampling), ci, ci, ci, vp, vp]
         L.q3asr_debug_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.q3asr_debug_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
@@ -780,6 +787,10 @@ class Pool:
             raise Q3Error(rc, lib().q3asr_pool_last_error(self._p).decode())
         return [ids[i, :lens[i]].copy() for i in range(len(clips))]
 
+    def submit(self, clips, max_tokens=448, stop_on_eos=True, max_batch_per_gpu=64, sample_rates=None, options=None):
+        """Asynchronous transcribe_ids: returns a PoolJob whose wait() gives the ids; the clips are kept alive by the job."""
+        return PoolJob(self, clips, max_tokens, stop_on_eos, max_batch_per_gpu, sample_rates, options)
+
     def close(self):
         if self._p:
             lib().q3asr_pool_destroy(self._p)
@@ -788,5 +799,49 @@ class Pool:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class PoolJob:
+    """q3asr_pool_submit / q3asr_job_wait: a batch running on the library's own thread."""
+
+    def __init__(self, pool, clips, max_tokens, stop_on_eos, max_batch_per_gpu, sample_rates, options):
+        self._clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        self._n = np.array([c.size for c in self._clips], dtype=np.uint64)
+        self._sr = None if sample_rates is None else np.ascontiguousarray(sample_rates, dtype=np.int32)
+        self._samp = None if options is None else options.c_struct()
+        self._max_tokens = int(max_tokens)
+        self._j = ctypes.c_void_p()
+        rc = lib().q3asr_pool_submit(pool._p, ctypes.cast(_ptr_array(self._clips), ctypes.c_void_p), self._n.ctypes.data,
+                                     self._sr.ctypes.data if self._sr is not None else None, len(self._clips), None,
+                                     ctypes.byref(self._samp) if self._samp is not None else None, self._max_tokens, int(bool(stop_on_eos)),
+                                     int(max_batch_per_gpu), ctypes.byref(self._j))
+        if rc != OK:
+            raise Q3Error(rc, "pool_submit: bad argument")
+
+    @property
+    def done(self):
+        return bool(lib().q3asr_job_done(self._j))
+
+    def wait(self):
+        ids = np.zeros((len(self._clips), self._max_tokens), dtype=np.int32)
+        lens = np.zeros(len(self._clips), dtype=np.int32)
+        rc = lib().q3asr_job_wait(self._j, ids.ctypes.data, lens.ctypes.data)
+        if rc != OK:
+            msg = lib().q3asr_job_last_error(self._j).decode()
+            self.free()
+            raise Q3Error(rc, msg)
+        self.free()
+        return [ids[i, :lens[i]].copy() for i in range(len(self._clips))]
+
+    def free(self):
+        if self._j:
+            lib().q3asr_job_free(self._j)
+            self._j = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass

@@ -53,6 +53,27 @@ def test_pool_with_sample_rates_and_decoder_knobs(built_lib):
         single.close()
 
 
+def test_pool_submit_wait(built_lib):
+    """q3asr_pool_submit / q3asr_job_wait: two batches queued back to back give what the blocking call gives; errors surface at wait."""
+    a = [synth.clip(i, 16000 + 700 * i) for i in range(5)]
+    b = [synth.clip(10 + i, 24000 * 2) for i in range(3)]
+    pool = built_lib.Pool("tiny", devices=_devices(), seed=20260418)
+    try:
+        want_a = pool.transcribe_ids(a, max_tokens=8, stop_on_eos=False)
+        want_b = pool.transcribe_ids(b, max_tokens=6, stop_on_eos=False, sample_rates=[24000] * 3)
+        ja = pool.submit(a, max_tokens=8, stop_on_eos=False, max_batch_per_gpu=2)
+        jb = pool.submit(b, max_tokens=6, stop_on_eos=False, sample_rates=[24000] * 3)
+        got_b, got_a = jb.wait(), ja.wait()
+        assert [t.tolist() for t in got_a] == [t.tolist() for t in want_a]
+        assert [t.tolist() for t in got_b] == [t.tolist() for t in want_b]
+        bad = pool.submit([np.zeros(10, np.float32)], max_tokens=4)
+        with pytest.raises(built_lib.Q3Error):
+            bad.wait()
+        assert pool.transcribe_ids(a[:1], max_tokens=8, stop_on_eos=False)[0].tolist() == want_a[0].tolist()  # the pool survives
+    finally:
+        pool.close()
+
+
 def test_1p7b_configuration(built_lib, monkeypatch):
     """Qwen3-ASR-1.7B dimensions (encoder d 1024 / 24 layers, decoder hidden 2048): batch invariance, fixed length, and the two
     decode schedules (weight-streaming split-K path vs one kernel per op) agree."""
