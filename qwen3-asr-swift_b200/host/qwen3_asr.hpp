@@ -247,16 +247,23 @@ class Qwen3ASRModel {
                 out[i] = "[Qwen3-ASR B200 error: " + err + "]";
                 continue;
             }
-            std::vector<int32_t> t = ids[i];
-            if (tok_.decode) {
-                std::string raw = tok_.decode(t);
-                const size_t at = raw.find("<asr_text>");  // Qwen3ASR.swift:283-287
-                if (at != std::string::npos) raw = raw.substr(at + 10);
-                const size_t a = raw.find_first_not_of(' '), b = raw.find_last_not_of(' ');
-                out[i] = a == std::string::npos ? std::string() : raw.substr(a, b - a + 1);
-            } else {  // id-string fallback, Qwen3ASR.swift:288-289
-                for (size_t j = 0; j < t.size(); j++) out[i] += (j ? " " : "") + std::to_string(t[j]);
-            }
+            out[i] = textFromIds(tok_, ids[i]);
+        }
+        return out;
+    }
+
+    // generated ids -> transcript (Qwen3ASR.swift:283-289): decode, keep what follows "<asr_text>", trim; without a tokenizer the ids
+    // joined by spaces (the reference's own fallback)
+    static std::string textFromIds(const Tokenizer& tok, const std::vector<int32_t>& t) {
+        std::string out;
+        if (tok.decode) {
+            std::string raw = tok.decode(t);
+            const size_t at = raw.find("<asr_text>");
+            if (at != std::string::npos) raw = raw.substr(at + 10);
+            const size_t a = raw.find_first_not_of(' '), b = raw.find_last_not_of(' ');
+            out = a == std::string::npos ? std::string() : raw.substr(a, b - a + 1);
+        } else {
+            for (size_t j = 0; j < t.size(); j++) out += (j ? " " : "") + std::to_string(t[j]);
         }
         return out;
     }

@@ -86,8 +86,9 @@ def test_transcribe_batch_jsonl(transcribe_batch, tmp_path):
     _write_wav(tmp_path / "d_long.wav", synth.clip(3, 16000 * 5), 16000)
     (tmp_path / "e_bad.wav").write_bytes(b"RIFF" + bytes(100))
     out = tmp_path / "txt"
+    # two pool workers (both on device 0 when the box has one GPU), groups of 2 x 3 utterances, file loading overlapped with the GPU work
     r = subprocess.run([transcribe_batch, str(tmp_path), "--jsonl", "--max-tokens", "6", "--window-seconds", "2", "--batch", "3",
-                        "--output-dir", str(out)], capture_output=True, text=True, timeout=600)
+                        "--devices", "0,0", "--output-dir", str(out)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     recs = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
     assert [x["file"] for x in recs] == ["a16", "b24", "c8_stereo", "d_long", "e_bad"]
