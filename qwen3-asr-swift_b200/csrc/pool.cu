@@ -99,7 +99,7 @@ int q3asr_pool_transcribe_ids_opts(q3asr_pool* p, const float* const* pcm, const
         return Q3ASR_ERR_INVALID;
     std::lock_guard<std::mutex> run_lock(p->run_mu);
     const int G = (int)p->handles.size();
-    if (max_batch_per_gpu <= 0) max_batch_per_gpu = 64;
+    if (max_batch_per_gpu <= 0) max_batch_per_gpu = 128;  // the widest batch the weight-streaming decode kernels take (measured: +23 % over 64)
     // the scheduler's cost model and the length sort work on 16 kHz-equivalent lengths
     std::vector<size_t> n16(n_in, n_in + batch);
     if (sample_rates)

@@ -14,17 +14,18 @@ from q3asr import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 workers = [int(a) for a in sys.argv[2:]] or [1, 2, 3]
+max_batch = int(os.environ.get("POOL_MAX_BATCH", "64"))
 clips = [synth.clip(i % 64, 480000) for i in range(n)]
 ref = None
 for w in workers:
     pool = q3asr.Pool("0.6B", devices=(0,) * w)
-    pool.transcribe_ids(clips[:64 * w], max_tokens=128, stop_on_eos=False)  # warm-up
+    pool.transcribe_ids(clips[:max_batch * w], max_tokens=128, stop_on_eos=False, max_batch_per_gpu=max_batch)  # warm-up
     best = 1e9
     for _ in range(2):
         t0 = time.perf_counter()
-        out = pool.transcribe_ids(clips, max_tokens=128, stop_on_eos=False, max_batch_per_gpu=64)
+        out = pool.transcribe_ids(clips, max_tokens=128, stop_on_eos=False, max_batch_per_gpu=max_batch)
         best = min(best, time.perf_counter() - t0)
     pool.close()
     ids = [t.tolist() for t in out]
     ref = ref or ids
-    print(f"workers {w}: {n} clips in {best * 1000:.0f} ms = {n * 30 / best:.0f} audio-s/s  ids_same {ids == ref}", flush=True)
+    print(f"max_batch {max_batch} workers {w}: {n} clips in {best * 1000:.0f} ms = {n * 30 / best:.0f} audio-s/s  ids_same {ids == ref}", flush=True)
