@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--max-tokens", type=int, default=MAX_TOKENS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-pipelined", action="store_true")
     args = ap.parse_args()
     MODEL, CLIP_SECONDS, CLIPS_PER_GPU, MAX_TOKENS = args.model, args.clip_seconds, args.clips_per_gpu, args.max_tokens
     METRIC = f"RTFx (audio-sec/sec) Qwen3-ASR-{MODEL} batched"
@@ -282,6 +283,28 @@ def main():
     e2e = world * audio_s * args.steps / e2e_s
     h2d = int(sum(c.nbytes for c in clips))
     d2h = int(CLIPS_PER_GPU * MAX_TOKENS * 4 + CLIPS_PER_GPU * 4)
+
+    # ---- the same K steps through the scheduler's submit / wait calls with two steps in flight per GPU (extra key, not the headline):
+    #      the decode steps of two batches interleave on one GPU, and step k + 1's upload overlaps step k's compute ----
+    e2e_pipe = None
+    if not args.no_pipelined:
+        pools = [q3asr.Pool(MODEL, devices=(local_rank,), seed=SEED) for _ in range(2)]
+        try:
+            for p_ in pools:
+                p_.transcribe_ids(clips, MAX_TOKENS, stop_on_eos=False, max_batch_per_gpu=CLIPS_PER_GPU)  # warm-up: buffers, graphs
+            barrier()
+            t0 = time.perf_counter()
+            jobs = [pools[k % 2].submit(clips, MAX_TOKENS, stop_on_eos=False, max_batch_per_gpu=CLIPS_PER_GPU) for k in range(args.steps)]
+            outs = [j.wait() for j in jobs]
+            pipe_s = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            assert all([t.tolist() for t in o] == [t.tolist() for t in ids_ref] for o in outs), "pipelined ids differ"
+            e2e_pipe = {"value": world * audio_s * args.steps / pipe_s, "unit": UNIT, "in_flight_per_gpu": 2,
+                        "how": "q3asr_pool_submit / q3asr_job_wait on two single-worker pools per GPU, steps alternating between them; "
+                               "host buffers in, ids out, same K steps"}
+        finally:
+            for p_ in pools:
+                p_.close()
 
     # ---- per-kernel-family timing (extra steps, CUDA events around the launches) ----
     pk = peaks()
@@ -379,6 +402,7 @@ def main():
             "config": workload_config(world),
             "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(("mel", "encoder", "prefill", "decode"), stage)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_pipelined": e2e_pipe,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_mel": roof_mel, "kernel_families": families,
             "cpu_baseline": cpu,
         }
