@@ -1105,7 +1105,11 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(8)));
         attr = true;
     }
-    const bool many = (long)n_seqs * cache.kv_heads >= 2L * num_sms;  // few (sequence, head) pairs: more warps per CTA share the key loop
+    bool many = (long)n_seqs * cache.kv_heads >= 2L * num_sms;  // few (sequence, head) pairs: more warps per CTA share the key loop
+    if (const char* f = getenv("Q3ASR_DECODE_ATTN_WARPS")) {        // tests force either variant on small batches (2 or 8 warps)
+        if (atoi(f) == 2) many = true;
+        else if (atoi(f) == 8) many = false;
+    }
     static const bool simt = getenv("Q3ASR_DECODE_ATTN_SIMT") != nullptr && atoi(getenv("Q3ASR_DECODE_ATTN_SIMT")) != 0;
     if (!simt) {
         if (many)

@@ -63,6 +63,18 @@ def test_greedy_ids_bit_exact(tiny_model, tiny_oracle):
         assert got.tolist() == ref.tolist(), (n, got.tolist(), ref.tolist(), margins.tolist())
 
 
+@pytest.mark.parametrize("warps", ["2", "8"])
+def test_greedy_ids_bit_exact_both_decode_attention_variants(tiny_model, tiny_oracle, monkeypatch, warps):
+    """The decode attention keeps two warps per (sequence, kv head) for large batches (the bench regime) and eight for small ones; both
+    variants are checked against the oracle here by forcing them on a small batch."""
+    monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
+    clips = [synth.clip(i, n) for i, n in enumerate([16000 * 3 + 777, 16000, 5000])]
+    got = tiny_model.transcribe_ids(clips, max_tokens=32, stop_on_eos=False)
+    for x, g in zip(clips, got):
+        ref, _, margins = tiny_oracle.greedy(tiny_oracle.encode(omel.mel(x)), 32, stop_on_eos=False)
+        assert g.tolist() == ref.tolist(), (warps, x.size, g.tolist(), ref.tolist(), margins.tolist())
+
+
 def test_teacher_forced_argmax_and_logits(tiny_model, tiny_oracle):
     x = synth.clip(1, 40000)
     rng = np.random.default_rng(11)
