@@ -203,10 +203,13 @@ def test_tcgen05_attention_matches_mma_sync_checker(built_lib, monkeypatch):
         m.close()
 
 
-def test_golden_0p6b(built_lib):
+@pytest.mark.parametrize("warps", ["8", "2"])
+def test_golden_0p6b(built_lib, monkeypatch, warps):
     """Greedy ids and encoder statistics of the 0.6B configuration on one 5 s clip, against the fixture the
-    CPU oracle produced (tests/golden/make_golden.py)."""
+    CPU oracle produced (tests/golden/make_golden.py); with either decode-attention variant (8 warps per (sequence, head): what a
+    batch of one uses; 2 warps: what the bench's batches of 64 use)."""
     import os
+    monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
     path = os.path.join(os.path.dirname(__file__), "golden", "q06b_clip5s.npz")
     if not os.path.exists(path):
         pytest.skip("golden fixture not generated")
