@@ -130,6 +130,21 @@ def test_batch_equals_single_and_order(tiny_model):
     assert [r.tolist() for r in rev[::-1]] == [b.tolist() for b in batch]
 
 
+@pytest.mark.parametrize("n_clips", [70, 128, 140])
+def test_wide_batches_equal_single(tiny_model, tiny_oracle, n_clips):
+    """Batches wider than 64 take the 128-column variants of the decode GEMMs and the LM head (<= 128 sequences) or the general
+    schedule (> 128): the ids of every utterance equal those of the utterance alone, and a sample equals the oracle."""
+    rng = np.random.default_rng(n_clips)
+    clips = [synth.clip(i, int(rng.integers(1600, 12000))) for i in range(n_clips)]
+    batch = tiny_model.transcribe_ids(clips, max_tokens=10, stop_on_eos=False)
+    for i in range(0, n_clips, 9):
+        single = tiny_model.transcribe_ids([clips[i]], max_tokens=10, stop_on_eos=False)[0]
+        assert batch[i].tolist() == single.tolist(), i
+    for i in (0, n_clips - 1):
+        ref = tiny_oracle.greedy(tiny_oracle.encode(omel.mel(clips[i])), 10, stop_on_eos=False)[0]
+        assert batch[i].tolist() == ref.tolist(), i
+
+
 def test_eos_stops_and_is_included(built_lib, tiny_oracle):
     # make the token the model settles on the EOS token: the loop must append it, then stop (Qwen3ASR.swift:378-379)
     x = synth.clip(0, 30000)
