@@ -569,6 +569,16 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) decode_attn_fused_ke
 // ------------------------------------------------------------------------------------------
 constexpr int DM_CHUNK = 16;
 constexpr int DM_STAGES = 3;
+constexpr int DM_STREAMS = 8;  // canonical number of key streams (see the kernel)
+
+// scales of the online-softmax merge of two partials with maxima am, bm: returns max(am, bm), *fa = 2^(am - m), *fb = 2^(bm - m)
+// (0 for an empty partial, whose maximum is -inf)
+__device__ __forceinline__ float dm_merge_scales(float am, float bm, float* fa, float* fb) {
+    const float m = fmaxf(am, bm);
+    *fa = am == -INFINITY ? 0.f : exp2f(am - m);
+    *fb = bm == -INFINITY ? 0.f : exp2f(bm - m);
+    return m;
+}
 constexpr int decode_attn_mma_smem(int nw) { return nw * DM_STAGES * 2 * DM_CHUNK * 128 * 2; }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_ptr) {
@@ -629,8 +639,23 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // Canonical key partition (independent of NW, so a sequence's result does not depend on the batch it is decoded in): chunk c
+    // belongs to stream c % DM_STREAMS; a stream is accumulated in chunk order; streams are merged by dm_merge as
+    // ((s0 + s2) + s4) + s6, ((s1 + s3) + s5) + s7, then even + odd.  Warp w walks the streams w, w + NW, ... one after the other.
+    auto seq_next = [&](int& sj, int& sc) {  // next chunk of this warp's sequence after (stream sj, chunk sc); sc >= n_chunks: done
+        sc += DM_STREAMS;
+        while (sc >= n_chunks && sj + NW < DM_STREAMS) {
+            sj += NW;
+            sc = sj;
+        }
+    };
+    int ij = warp, ic = warp;  // issue cursor
+    while (ic >= n_chunks && ij + NW < DM_STREAMS) { ij += NW; ic = ij; }
 #pragma unroll
-    for (int s = 0; s < DM_STAGES - 1; s++) issue(warp + s * NW, s);
+    for (int s = 0; s < DM_STAGES - 1; s++) {
+        issue(ic, s);  // chunks >= n_chunks are skipped inside issue (the group is still committed)
+        seq_next(ij, ic);
+    }
 
     ptx::grid_dep_wait();
 
@@ -712,13 +737,45 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
         qa[ks][1] = lane < 8 ? *reinterpret_cast<const uint32_t*>(&s_qb[g & 1][ks * 16 + 8 + t * 2]) : 0u;
     }
     float o[16][4];
-#pragma unroll
-    for (int i = 0; i < 16; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const int mi = lane >> 3, r8 = lane & 7;
     int stage = 0;
-    for (int chunk = warp; chunk < n_chunks; chunk += NW) {
-        issue(chunk + (DM_STAGES - 1) * NW, (stage + DM_STAGES - 1) % DM_STAGES);
+    int cj = warp, chunk = warp;  // consume cursor
+    while (chunk >= n_chunks && cj + NW < DM_STREAMS) { cj += NW; chunk = cj; }
+    int cur_stream = -1;
+    bool first_stream = true;
+    // folds the finished stream (m_run, l_run, o) into this warp's running partial in shared memory (lanes 0-7 hold the two rows)
+    auto flush_stream = [&]() {
+        float l = l_run;
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        if (lane < 8) {
+            float am = first_stream ? -INFINITY : s_m[g][warp], al = first_stream ? 0.f : s_l[g][warp];
+            float fa, fb;
+            const float mm = dm_merge_scales(am, m_run, &fa, &fb);
+#pragma unroll
+            for (int nt = 0; nt < 16; nt++) {
+                float* dst = &s_acc[g][warp][nt * 8 + t * 2];
+                const float a0 = first_stream ? 0.f : dst[0], a1 = first_stream ? 0.f : dst[1];
+                dst[0] = fmaf(fb, o[nt][0], fa * a0);
+                dst[1] = fmaf(fb, o[nt][1], fa * a1);
+            }
+            __syncwarp(0xffu);
+            if (t == 0) { s_m[g][warp] = mm; s_l[g][warp] = fmaf(fb, l, fa * al); }
+        }
+        first_stream = false;
+    };
+    for (; chunk < n_chunks; seq_next(cj, chunk)) {
+        if (cj != cur_stream) {  // a new stream starts: fold the previous one away, start from an empty accumulator
+            if (cur_stream >= 0) flush_stream();
+            cur_stream = cj;
+#pragma unroll
+            for (int i = 0; i < 16; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+            m_run = -INFINITY;
+            l_run = 0.f;
+        }
+        issue(ic, (stage + DM_STAGES - 1) % DM_STAGES);
+        seq_next(ij, ic);
         asm volatile("cp.async.wait_group %0;" ::"n"(DM_STAGES - 1) : "memory");
         __syncwarp();
         bf16* sk = ring + (size_t)stage * 2 * DM_CHUNK * 128;
@@ -775,30 +832,30 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-    // ---- 3. merge the warps ----
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-    if (lane < 8) {
-        if (t == 0) { s_m[g][warp] = m_run; s_l[g][warp] = l_run; }
+    // ---- 3. merge the streams: each warp's partial already holds its streams folded in order; across warps the same fixed tree ----
+    if (cur_stream >= 0) {
+        flush_stream();
+    } else if (lane < 8) {  // a warp whose streams are all empty (very short contexts) contributes the neutral element
+        if (t == 0) { s_m[g][warp] = -INFINITY; s_l[g][warp] = 0.f; }
 #pragma unroll
-        for (int nt = 0; nt < 16; nt++) {
-            s_acc[g][warp][nt * 8 + t * 2] = o[nt][0];
-            s_acc[g][warp][nt * 8 + t * 2 + 1] = o[nt][1];
-        }
+        for (int nt = 0; nt < 16; nt++) s_acc[g][warp][nt * 8 + t * 2] = s_acc[g][warp][nt * 8 + t * 2 + 1] = 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < GROUP * 128; i += NW * 32) {
         const int gg = i >> 7, d = i & 127;
-        float mm = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < NW; w++) mm = fmaxf(mm, s_m[gg][w]);
-        float num = 0.f, den = 0.f;
+        // even chain (warps 0, 2, ...), odd chain (warps 1, 3, ...), then even + odd: for NW == 2 that is just warp 0 + warp 1
+        float cm[2] = {-INFINITY, -INFINITY}, cl[2] = {0.f, 0.f}, ca[2] = {0.f, 0.f};
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            const float f = s_m[gg][w] == -INFINITY ? 0.f : exp2f(s_m[gg][w] - mm);
-            num = fmaf(f, s_acc[gg][w][d], num);
-            den = fmaf(f, s_l[gg][w], den);
+            float fa, fb;
+            const float mm = dm_merge_scales(cm[w & 1], s_m[gg][w], &fa, &fb);
+            ca[w & 1] = fmaf(fb, s_acc[gg][w][d], fa * ca[w & 1]);
+            cl[w & 1] = fmaf(fb, s_l[gg][w], fa * cl[w & 1]);
+            cm[w & 1] = mm;
         }
+        float fa, fb;
+        dm_merge_scales(cm[0], cm[1], &fa, &fb);
+        const float num = fmaf(fb, ca[1], fa * ca[0]), den = fmaf(fb, cl[1], fa * cl[0]);
         out[((size_t)seq * heads + kvh * GROUP + gg) * 128 + d] = __float2bfloat16_rn(num / den);
     }
 }
