@@ -75,6 +75,20 @@ def test_greedy_ids_bit_exact_both_decode_attention_variants(tiny_model, tiny_or
         assert g.tolist() == ref.tolist(), (warps, x.size, g.tolist(), ref.tolist(), margins.tolist())
 
 
+def test_decode_attention_variants_are_bit_identical(tiny_model, monkeypatch):
+    """Both variants walk the same canonical key streams and merge tree (csrc/ops.cu), so the ids (and the top logits) are identical:
+    this is what makes an utterance's result independent of the batch size."""
+    clips = [synth.clip(i, n) for i, n in enumerate([16000 * 4 + 5, 1600, 16000 * 2, 700 * 16, 161])]
+    forced = np.arange(50, 90, dtype=np.int32)
+    res = {}
+    for warps in ("2", "8"):
+        monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
+        ids = tiny_model.transcribe_ids(clips, max_tokens=48, stop_on_eos=False)
+        am, top = tiny_model.decode_forced(clips[0], forced)
+        res[warps] = ([t.tolist() for t in ids], am.tolist(), top.tolist())
+    assert res["2"] == res["8"]
+
+
 def test_teacher_forced_argmax_and_logits(tiny_model, tiny_oracle):
     x = synth.clip(1, 40000)
     rng = np.random.default_rng(11)
