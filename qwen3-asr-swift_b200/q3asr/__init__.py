@@ -528,6 +528,24 @@ class Qwen3ASRModel:
             out.append(dict(text=words[i] if words else "", start_time=float(st), end_time=float(max(en, st))))
         return out
 
+    def align_text(self, audio, text, language="English", sample_rate=16000):
+        """Qwen3ForcedAligner.align(audio:text:sampleRate:language:) (ForcedAligner.swift:226-331): word splitting and timestamp slots
+        by q3asr.text (TextPreprocessing.swift), the rest by `align`.  [] without a tokenizer or without words, like the reference."""
+        from . import text as _text
+        if self.tokenizer is None:
+            return []
+        st = _text.prepare_for_alignment(text, self.tokenizer, language, int(self.cfg.tok_timestamp))
+        if not st.words:
+            return []
+        raw = self.align_indices([audio], [st.token_ids], [st.timestamp_positions], None if sample_rate == 16000 else [sample_rate])[0]
+        fixed = enforce_monotonicity(raw)
+        seg = np.float32(self.TIMESTAMP_SEGMENT_TIME)
+        out = []
+        for i, w in enumerate(st.words):
+            a, b = np.float32(fixed[2 * i]) * seg, np.float32(fixed[2 * i + 1]) * seg
+            out.append(dict(text=w, start_time=float(a), end_time=float(max(a, b))))
+        return out
+
     def resample(self, samples, in_rate, out_rate):
         """AudioFileLoader.resample (AudioFileLoader.swift:159-213) on the GPU: float32 [n] -> float32 [floor(n * out / in)]."""
         x = np.ascontiguousarray(samples, dtype=np.float32)

@@ -118,6 +118,24 @@ def test_gpu_align_words_and_errors(aligner, tiny_model):
 
 
 @pytest.mark.gpu
+def test_gpu_align_text_end_to_end(aligner):
+    """align(audio, text): TextPreprocessor word pairs -> slots -> classes -> LIS fix-up -> AlignedWord-like dicts."""
+    class Tok:  # toy tokenizer inside the tiny vocabulary
+        def encode(self, w):
+            return [10 + (ord(c) % 1500) for c in w]
+    assert aligner.align_text(synth.clip(1, 32000), "no tokenizer yet") == []
+    aligner.tokenizer = Tok()
+    try:
+        out = aligner.align_text(synth.clip(1, 16000 * 3), "Hello, world! 你好 don't stop.", "English")
+        assert [w["text"] for w in out] == ["Hello,", "world!", "你", "好", "don't", "stop."]
+        starts = [w["start_time"] for w in out]
+        assert all(b >= a for a, b in zip(starts, starts[1:])) and all(w["end_time"] >= w["start_time"] for w in out)
+        assert aligner.align_text(synth.clip(1, 32000), "?!") == []
+    finally:
+        aligner.tokenizer = None
+
+
+@pytest.mark.gpu
 def test_gpu_full_size_aligner_properties(built_lib):
     """Qwen3-ForcedAligner-0.6B dimensions (24-layer 1024-wide encoder projecting to the 1024-wide decoder, 5000 classes,
     ForcedAligner.swift:57-85): a 20 s clip with 40 words — class range, batch invariance, monotone word times."""
