@@ -122,6 +122,14 @@ typedef struct q3asr_prompt {
     int raw_suffix;
 } q3asr_prompt;
 
+/* Host-only (no GPU work): the chat-template ids the prefill runs on for an utterance with n_audio_tokens audio tokens —
+ * <|im_start|>system\n[context]<|im_end|>\n<|im_start|>user\n<|audio_start|><|audio_pad|>*n<|audio_end|><|im_end|>\n
+ * <|im_start|>assistant\n[language]<asr_text>  (Qwen3ASR.swift:196-233; raw_suffix: ForcedAligner.swift:338-378).
+ * *n_ids = ids needed, *audio_at = index of the first <|audio_pad|> (may be NULL).  Q3ASR_ERR_INVALID with *n_ids set when
+ * cap is too small (call with cap 0 to size the buffer). */
+int q3asr_prompt_ids(const q3asr_config* cfg, int n_audio_tokens, const q3asr_prompt* prompt, int32_t* ids_out, int cap, int* n_ids,
+                     int* audio_at);
+
 /* Batched greedy transcription.  ids_out: [batch, max_tokens] int32; lens_out: [batch].
  * stop_on_eos != 0 reproduces the reference loop (EOS appended, then stop, Qwen3ASR.swift:378-379);
  * stop_on_eos == 0 decodes exactly max_tokens ids (fixed-length parity runs).  prompts may be NULL. */

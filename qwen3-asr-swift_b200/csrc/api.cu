@@ -244,6 +244,22 @@ int q3asr_mel(q3asr_handle* h, const float* pcm, size_t n, float* out, int* fram
 
 int q3asr_encoder_tokens(int frames) { return encoder_tokens_for(frames); }
 
+int q3asr_prompt_ids(const q3asr_config* cfg, int n_audio_tokens, const q3asr_prompt* prompt, int32_t* ids_out, int cap, int* n_ids,
+                     int* audio_at) {
+    if (!cfg || n_audio_tokens < 0 || !n_ids || cap < 0 || (cap > 0 && !ids_out)) return Q3ASR_ERR_INVALID;
+    if (prompt && ((prompt->n_context > 0 && !prompt->context_ids) || (prompt->n_language > 0 && !prompt->language_ids) ||
+                   prompt->n_context < 0 || prompt->n_language < 0))
+        return Q3ASR_ERR_INVALID;
+    std::vector<int32_t> ids;
+    int at = 0;
+    build_prompt(*cfg, prompt, n_audio_tokens, &ids, &at);
+    *n_ids = (int)ids.size();
+    if (audio_at) *audio_at = at;
+    if ((int)ids.size() > cap) return Q3ASR_ERR_INVALID;  // *n_ids says how much room is needed
+    std::copy(ids.begin(), ids.end(), ids_out);
+    return Q3ASR_OK;
+}
+
 int q3asr_encode(q3asr_handle* h, const float* mel, int frames, float* out, int* tokens) {
     return guarded(h, [&](Handle& x) { encode_one(&x, mel, frames, out, tokens); });
 }

@@ -21,6 +21,18 @@
 
 namespace q3 {
 
+void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at) {
+    // Qwen3ASR.swift:196-233
+    ids->insert(ids->end(), {c.tok_im_start, c.tok_system, c.tok_newline});
+    if (pr && pr->context_ids && pr->n_context > 0) ids->insert(ids->end(), pr->context_ids, pr->context_ids + pr->n_context);
+    ids->insert(ids->end(), {c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_user, c.tok_newline, c.tok_audio_start});
+    *audio_at = (int)ids->size();
+    ids->insert(ids->end(), (size_t)ntok, c.tok_audio_pad);
+    ids->insert(ids->end(), {c.tok_audio_end, c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_assistant, c.tok_newline});
+    if (pr && pr->language_ids && pr->n_language > 0) ids->insert(ids->end(), pr->language_ids, pr->language_ids + pr->n_language);
+    if (!(pr && pr->raw_suffix)) ids->push_back(c.tok_asr_text);  // the aligner's template ends with the slotted text (ForcedAligner.swift:338-378)
+}
+
 namespace {
 
 int env_int(const char* name, int def) {
@@ -38,18 +50,6 @@ size_t push_ints(std::vector<int>& buf, const std::vector<T>& v) {
     buf.resize(off + n);
     if (n) memcpy(buf.data() + off, v.data(), n * sizeof(int));
     return off;
-}
-
-void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at) {
-    // Qwen3ASR.swift:196-233
-    ids->insert(ids->end(), {c.tok_im_start, c.tok_system, c.tok_newline});
-    if (pr && pr->context_ids && pr->n_context > 0) ids->insert(ids->end(), pr->context_ids, pr->context_ids + pr->n_context);
-    ids->insert(ids->end(), {c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_user, c.tok_newline, c.tok_audio_start});
-    *audio_at = (int)ids->size();
-    ids->insert(ids->end(), (size_t)ntok, c.tok_audio_pad);
-    ids->insert(ids->end(), {c.tok_audio_end, c.tok_im_end, c.tok_newline, c.tok_im_start, c.tok_assistant, c.tok_newline});
-    if (pr && pr->language_ids && pr->n_language > 0) ids->insert(ids->end(), pr->language_ids, pr->language_ids + pr->n_language);
-    if (!(pr && pr->raw_suffix)) ids->push_back(c.tok_asr_text);  // the aligner's template ends with the slotted text (ForcedAligner.swift:338-378)
 }
 
 BatchState* fresh_batch(Handle* h) {

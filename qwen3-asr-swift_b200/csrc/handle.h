@@ -181,6 +181,8 @@ void model_commit(Handle* h);
 void model_unload(Handle* h);
 void model_load_safetensors(Handle* h, const char* dir);
 int encoder_tokens_for(int frames);
+// chat-template ids around `ntok` audio placeholders; *audio_at = index of the first placeholder (Qwen3ASR.swift:196-233)
+void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at);
 
 // rates: per-clip sample rates or null (all 16 kHz); other rates are converted on the device (audio_io.cu)
 void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts, const int* rates = nullptr);

@@ -77,7 +77,7 @@ EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
     "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
     "q3asr_load_safetensors", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
-    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
+    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
@@ -127,6 +127,7 @@ def lib():
         L.q3asr_mel.argtypes = [vp, vp, cs, vp, ctypes.POINTER(ci)]
         L.q3asr_mel_batch.argtypes = [vp, vp, vp, ci, vp, vp]
         L.q3asr_encoder_tokens.argtypes = [ci]
+        L.q3asr_prompt_ids.argtypes = [vp, ci, vp, vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.q3asr_encode.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
         L.q3asr_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp]
         L.q3asr_decode_forced.argtypes = [vp, vp, cs, vp, vp, ci, vp, vp]
@@ -209,6 +210,22 @@ def mel_frames(n):
 
 def encoder_tokens(frames):
     return lib().q3asr_encoder_tokens(int(frames))
+
+
+def prompt_ids(config, n_audio_tokens, context=None, language=None, raw_suffix=False):
+    """The chat-template ids the prefill runs on (Qwen3ASR.swift:196-233) and the index of the first <|audio_pad|>; host logic,
+    no GPU needed."""
+    pack = _PromptPack([{"context": context, "language": language, "raw_suffix": raw_suffix}], 1)
+    n, at = ctypes.c_int(0), ctypes.c_int(0)
+    cfg = ctypes.byref(config)
+    rc = lib().q3asr_prompt_ids(cfg, int(n_audio_tokens), pack.ptr, None, 0, ctypes.byref(n), ctypes.byref(at))
+    if n.value == 0:
+        raise ValueError(f"q3asr_prompt_ids: invalid argument (code {rc})")
+    out = np.empty(n.value, dtype=np.int32)
+    rc = lib().q3asr_prompt_ids(cfg, int(n_audio_tokens), pack.ptr, out.ctypes.data, out.size, ctypes.byref(n), ctypes.byref(at))
+    if rc != 0:
+        raise ValueError(f"q3asr_prompt_ids failed with code {rc}")
+    return out, at.value
 
 
 def schedule(n_samples, n_gpus):
@@ -338,6 +355,7 @@ class _PromptPack:
                     self.keep.append(a)
                     setattr(self.arr[i], f"{key}_ids", a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
                     setattr(self.arr[i], f"n_{key}", a.size)
+            self.arr[i].raw_suffix = int(bool((p or {}).get("raw_suffix", False)))
 
     @property
     def ptr(self):
