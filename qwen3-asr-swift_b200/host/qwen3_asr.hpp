@@ -433,10 +433,15 @@ class Qwen3ForcedAligner {
             if (splitSample >= remAudio.size()) break;
             std::vector<float> next(remAudio.begin() + splitSample, remAudio.end());
             if ((float)next.size() / (float)sampleRate < minChunkSeconds) break;
-            const std::vector<WordPair> wordsAll = splitIntoWordPairs(remText);
+            std::vector<std::string> wordsAll;  // the reference splits the text on the space character only (:161)
+            for (size_t i = 0; i < remText.size();) {
+                const size_t j = std::min(remText.find(' ', i), remText.size());
+                if (j > i) wordsAll.push_back(remText.substr(i, j - i));
+                i = j + 1;
+            }
             if (plateau >= (int)wordsAll.size()) break;
             std::string nextText;
-            for (size_t i = (size_t)plateau; i < wordsAll.size(); i++) nextText += (i > (size_t)plateau ? " " : "") + wordsAll[i].surface;
+            for (size_t i = (size_t)plateau; i < wordsAll.size(); i++) nextText += (i > (size_t)plateau ? " " : "") + wordsAll[i];
             remAudio.swap(next);
             remText.swap(nextText);
             offset += splitTime;

@@ -564,6 +564,58 @@ class Qwen3ASRModel:
             out.append(dict(text=w, start_time=float(a), end_time=float(max(a, b))))
         return out
 
+    @staticmethod
+    def offset_words(words, seconds):
+        """Qwen3ForcedAligner.offsetWords (ForcedAligner.swift:183-188), float32 arithmetic like the reference's Float."""
+        if seconds == 0:
+            return words
+        sec = np.float32(seconds)
+        return [dict(text=w["text"], start_time=float(np.float32(w["start_time"]) + sec), end_time=float(np.float32(w["end_time"]) + sec))
+                for w in words]
+
+    def align_long(self, audio, text, language="English", sample_rate=16000, progress=None):
+        """Qwen3ForcedAligner.alignLong (ForcedAligner.swift:100-181): align everything, find the trailing plateau (the words the
+        monotonicity pass collapsed onto one timestamp once the classification head saturates), keep the reliable prefix, re-align the
+        remaining audio and words, offset.  One `align_text` pass for recordings up to 240 s."""
+        bypass_s, min_chunk_s, tol, min_words = np.float32(240.0), np.float32(5.0), 0.1, 5
+        x = np.ascontiguousarray(audio, dtype=np.float32)
+        out, rem_text, offset, npass = [], text, np.float32(0.0), 1
+        while x.size and rem_text:
+            duration = np.float32(x.size) / np.float32(sample_rate)
+            aligned = self.align_text(x, rem_text, language, sample_rate)
+            if not aligned:
+                break
+            if duration <= bypass_s or len(aligned) < 2 * min_words:
+                out += self.offset_words(aligned, offset)
+                break
+            plateau = trailing_plateau_start([w["start_time"] for w in aligned], tol, min_words)
+            if plateau == len(aligned):
+                out += self.offset_words(aligned, offset)
+                break
+            if plateau == 0:  # the reference force-unwraps the last reliable word here; nothing reliable means nothing to keep
+                break
+            split_time = np.float32(aligned[plateau - 1]["end_time"])
+            out += self.offset_words(aligned[:plateau], offset)
+            split_sample = int(split_time * np.float32(sample_rate))
+            if split_sample >= x.size:
+                break
+            nxt = x[split_sample:]
+            remaining = np.float32(nxt.size) / np.float32(sample_rate)
+            if remaining < min_chunk_s:
+                break
+            words_all = [w for w in rem_text.split(" ") if w]  # the reference splits on the space character only (:161)
+            if plateau >= len(words_all):
+                break
+            if progress is not None:
+                progress(f"Audio {duration:.1f}s saturated after word {plateau} ({split_time:.1f}s); chunking remaining "
+                         f"{remaining:.1f}s (pass {npass + 1})")
+            x, rem_text = nxt, " ".join(words_all[plateau:])
+            offset = np.float32(offset + split_time)
+            npass += 1
+            if npass > 10:
+                break
+        return out
+
     def resample(self, samples, in_rate, out_rate):
         """AudioFileLoader.resample (AudioFileLoader.swift:159-213) on the GPU: float32 [n] -> float32 [floor(n * out / in)]."""
         x = np.ascontiguousarray(samples, dtype=np.float32)

@@ -58,6 +58,73 @@ def test_timestamp_correction_c_matches_oracle_on_random_input():
         assert q3asr.trailing_plateau_start(t, 0.1, 5) == ots.trailing_plateau_start(t, 0.1, 5)
 
 
+def test_offset_words_reference_cases():
+    """testOffsetWordsByZeroNoOp / testOffsetWordsAddsConstant (ForcedAlignerTests.swift:494-511)"""
+    words = [dict(text="w", start_time=1.0, end_time=1.5), dict(text="w", start_time=2.0, end_time=2.5)]
+    assert q3asr.Qwen3ASRModel.offset_words(words, 0) is words
+    moved = q3asr.Qwen3ASRModel.offset_words(words, 10)
+    assert [(w["start_time"], w["end_time"]) for w in moved] == [(11.0, 11.5), (12.0, 12.5)]
+    assert words[0]["start_time"] == 1.0  # the input is not modified
+
+
+class _ScriptedAligner(q3asr.Qwen3ASRModel):
+    """align_long's loop without a GPU: align_text is scripted — every word gets `step` seconds, and words whose start would pass
+    `reliable_s` collapse onto the last reliable timestamp (what the monotonicity pass makes of a saturated head)."""
+
+    def __init__(self, reliable_s, step=1.0):
+        self.reliable_s, self.step, self.calls = reliable_s, step, []
+
+    def align_text(self, audio, text, language="English", sample_rate=16000):
+        words = [w for w in text.split(" ") if w]
+        self.calls.append((len(audio), len(words)))
+        out, t = [], 0.0
+        for w in words:
+            if t < self.reliable_s:
+                out.append(dict(text=w, start_time=t, end_time=t + self.step))
+                t += self.step
+            else:
+                out.append(dict(text=w, start_time=t, end_time=t))
+        return out
+
+
+def test_align_long_loop():
+    """Qwen3ForcedAligner.alignLong (ForcedAligner.swift:100-181) around a scripted align."""
+    sr = 100  # samples per second: keeps the arrays small, the loop only looks at counts
+    text = " ".join(f"w{i}" for i in range(600))
+    # short audio: one pass, no plateau detection even though the tail is flat
+    a = _ScriptedAligner(reliable_s=50.0)
+    got = a.align_long(np.zeros(200 * sr, np.float32), text, sample_rate=sr)
+    assert a.calls == [(200 * sr, 600)] and len(got) == 600 and got[-1]["start_time"] == 50.0
+    # long and healthy: one pass
+    a = _ScriptedAligner(reliable_s=1e9)
+    got = a.align_long(np.zeros(600 * sr, np.float32), text, sample_rate=sr)
+    assert a.calls == [(600 * sr, 600)] and [w["start_time"] for w in got] == [float(i) for i in range(600)]
+    # long, saturating after 250 s: the first 250 words are kept, the rest re-aligned on the audio from 250 s on, then once more
+    a = _ScriptedAligner(reliable_s=250.0)
+    msgs = []
+    got = a.align_long(np.zeros(600 * sr, np.float32), text, sample_rate=sr, progress=msgs.append)
+    assert a.calls == [(600 * sr, 600), (350 * sr, 350), (100 * sr, 100)]
+    assert [w["text"] for w in got] == [f"w{i}" for i in range(600)]
+    assert [w["start_time"] for w in got] == [float(i) for i in range(600)]
+    assert msgs == ["Audio 600.0s saturated after word 250 (250.0s); chunking remaining 350.0s (pass 2)",
+                    "Audio 350.0s saturated after word 250 (250.0s); chunking remaining 100.0s (pass 3)"]
+    # the remainder shorter than 5 s is dropped with its words (:158)
+    a = _ScriptedAligner(reliable_s=250.0)
+    got = a.align_long(np.zeros(253 * sr, np.float32), text, sample_rate=sr)
+    assert len(a.calls) == 1 and len(got) == 250
+    # fewer than 10 words: never split
+    a = _ScriptedAligner(reliable_s=2.0)
+    got = a.align_long(np.zeros(300 * sr, np.float32), "a b c d e f g h i", sample_rate=sr)
+    assert len(a.calls) == 1 and len(got) == 9
+    # nothing aligned / empty inputs
+    assert _ScriptedAligner(1.0).align_long(np.zeros(0, np.float32), text, sample_rate=sr) == []
+    assert _ScriptedAligner(1.0).align_long(np.zeros(10, np.float32), "", sample_rate=sr) == []
+    # at most 10 passes
+    a = _ScriptedAligner(reliable_s=241.0)
+    a.align_long(np.zeros(5000 * sr, np.float32), " ".join(["w"] * 6000), sample_rate=sr)
+    assert len(a.calls) == 10
+
+
 # ---- GPU: the classification pass ----
 @pytest.fixture(scope="module")
 def aligner(built_lib):
