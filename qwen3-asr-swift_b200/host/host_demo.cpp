@@ -16,6 +16,12 @@ int main(int argc, char** argv) {
         if (o.maxTokens != 448 || !o.isGreedyFastPath() || o.language || o.context) return 1;
         if (detectModelSize("aufklarer/Qwen3-ASR-1.7B-MLX-8bit") != ASRModelSize::large) return 2;
         if (detectModelSize("aufklarer/Qwen3-ASR-0.6B-MLX-4bit") != ASRModelSize::small) return 3;
+        if (detectModelSize("some-custom/model") != ASRModelSize::small) return 3;
+        // testASRModelSizeBitsDetection (Qwen3ASRTests.swift:61-69)
+        if (detectModelBits("aufklarer/Qwen3-ASR-0.6B-MLX-8bit") != 8 || detectModelBits("aufklarer/Qwen3-ASR-0.6B-MLX-4bit") != 4 ||
+            detectModelBits("aufklarer/Qwen3-ASR-1.7B-MLX-4bit") != 4 || detectModelBits("some-custom/small-model") != 4 ||
+            detectModelBits("some/1.7B-model") != 8)
+            return 4;
         try {
             auto m = Qwen3ASRModel::randomInit(ASRModelSize::small);
             printf("created on GPU, footprint %zu\n", m->memoryFootprint());

@@ -47,6 +47,15 @@ inline ASRModelSize detectModelSize(const std::string& modelId) {  // Qwen3ASR.s
     std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
     return s.find("1.7b") != std::string::npos ? ASRModelSize::large : ASRModelSize::small;
 }
+// Qwen3ASR.swift:588-600: "8bit"/"8-bit" or "4bit"/"4-bit" in the id, else 4 for the small model and 8 for the large one.  The
+// loader itself reads the packing from the tensor shapes (csrc/safetensors.cu); this is the id convention of the reference.
+inline int detectModelBits(const std::string& modelId) {
+    std::string s = modelId;
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (s.find("8bit") != std::string::npos || s.find("8-bit") != std::string::npos) return 8;
+    if (s.find("4bit") != std::string::npos || s.find("4-bit") != std::string::npos) return 4;
+    return detectModelSize(modelId) == ASRModelSize::large ? 8 : 4;
+}
 
 struct MelFeatures {  // row-major [melBins, timeFrames]
     std::vector<float> data;

@@ -337,6 +337,22 @@ def _ptr_array(arrs):
     return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
 
 
+def detect_model_size(model_id):
+    """ASRModelSize.detect (Qwen3ASR.swift:581-586): the preset name for a model id."""
+    return "1.7B" if ("1.7B" in model_id or "1.7b" in model_id) else "0.6B"
+
+
+def detect_bits(model_id):
+    """ASRModelSize.detectBits (Qwen3ASR.swift:588-600).  The loader reads the packing from the tensor shapes; this is the reference's
+    id convention, kept for callers that pick a checkpoint directory by id."""
+    low = model_id.lower()
+    if "8bit" in low or "8-bit" in low:
+        return 8
+    if "4bit" in low or "4-bit" in low:
+        return 4
+    return 8 if detect_model_size(model_id) == "1.7B" else 4
+
+
 class _PromptPack:
     """Keeps the numpy arrays behind an array of q3asr_prompt alive."""
 
@@ -376,7 +392,10 @@ class Qwen3ASRModel:
 
     # -- lifecycle ---------------------------------------------------------------------------
     @classmethod
-    def from_pretrained(cls, model_dir, size="0.6B", device=0):
+    def from_pretrained(cls, model_dir, size=None, device=0):
+        """size None: decided from the directory name like ASRModelSize.detect does from the model id (Qwen3ASR.swift:615)."""
+        if size is None:
+            size = detect_model_size(os.path.basename(os.path.normpath(os.fspath(model_dir))))
         m = cls(size=size, device=device)
         m._ck(lib().q3asr_load_safetensors(m._h, os.fspath(model_dir).encode()))
         if os.path.exists(os.path.join(model_dir, "vocab.json")):  # Qwen3ASR.swift:643-649

@@ -79,3 +79,16 @@ def test_create_fails_loudly_without_gpu(built_lib):
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
     with pytest.raises(built_lib.Q3Error):
         built_lib.Pool("tiny", devices=(0,))
+
+
+def test_model_size_and_bits_detection(built_lib):
+    """testASRModelSizeDetection / testASRModelSizeBitsDetection (Qwen3ASRTests.swift:61-69, 93-103)"""
+    import q3asr
+    assert q3asr.detect_model_size("aufklarer/Qwen3-ASR-0.6B-MLX-4bit") == "0.6B"
+    assert q3asr.detect_model_size("aufklarer/Qwen3-ASR-1.7B-MLX-8bit") == "1.7B"
+    assert q3asr.detect_model_size("some-custom/model") == "0.6B"
+    assert q3asr.detect_bits("aufklarer/Qwen3-ASR-0.6B-MLX-8bit") == 8
+    assert q3asr.detect_bits("aufklarer/Qwen3-ASR-0.6B-MLX-4bit") == 4
+    assert q3asr.detect_bits("aufklarer/Qwen3-ASR-1.7B-MLX-4bit") == 4
+    assert q3asr.detect_bits("some-custom/small-model") == 4
+    assert q3asr.detect_bits("some/1.7B-model") == 8
