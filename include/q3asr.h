@@ -216,6 +216,7 @@ int q3asr_flush_l2(q3asr_handle* h);
 int q3asr_pool_create(const q3asr_config* cfg, const int* devices, int n_devices, uint64_t random_seed, const char* weights_dir,
                       q3asr_pool** out);
 void q3asr_pool_destroy(q3asr_pool* p);
+/* message of the last failed call on this pool; p == NULL: why the last q3asr_pool_create on the calling thread failed */
 const char* q3asr_pool_last_error(const q3asr_pool* p);
 /* max_batch_per_gpu <= 0 picks the default sub-batch (128 utterances).  The device list of q3asr_pool_create may name a GPU more than
  * once: every entry is a worker with its own handle and stream, and two workers per GPU interleave the latency-bound decode steps of

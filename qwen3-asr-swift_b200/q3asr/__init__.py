@@ -877,7 +877,7 @@ class Pool:
         rc = lib().q3asr_pool_create(ctypes.byref(self.cfg), dev.ctypes.data, dev.size, int(seed),
                                      os.fspath(weights_dir).encode() if weights_dir else None, ctypes.byref(self._p))
         if rc != OK:
-            raise Q3Error(rc, "pool_create failed: " + lib().q3asr_last_error(None).decode())
+            raise Q3Error(rc, "pool_create failed: " + lib().q3asr_pool_last_error(None).decode())
 
     def transcribe_ids(self, clips, max_tokens=448, stop_on_eos=True, max_batch_per_gpu=64, sample_rates=None, options=None):
         clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]

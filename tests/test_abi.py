@@ -77,8 +77,25 @@ def test_create_fails_loudly_without_gpu(built_lib):
     with pytest.raises(built_lib.Q3Error) as e:
         built_lib.Qwen3ASRModel("tiny")
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
-    with pytest.raises(built_lib.Q3Error):
+    with pytest.raises(built_lib.Q3Error) as e:
         built_lib.Pool("tiny", devices=(0,))
+    assert "device 0" in str(e.value) and "no CPU fallback" in str(e.value)  # the reason survives although no pool came back
+
+
+def test_pool_and_job_argument_checks(built_lib):
+    """Bad arguments come back as Q3ASR_ERR_INVALID (1) before any GPU work, and no call leaves a dangling out-pointer."""
+    import ctypes
+    L = built_lib.lib()
+    cfg = built_lib.preset("tiny")
+    out = ctypes.c_void_p(0xdead)
+    assert L.q3asr_pool_create(ctypes.byref(cfg), None, 0, 1, None, ctypes.byref(out)) == 1 and not out.value
+    assert b"no devices" in L.q3asr_pool_last_error(None)
+    assert L.q3asr_pool_transcribe_ids_opts(None, None, None, None, 1, None, None, 8, 1, 0, None, None) == 1
+    job = ctypes.c_void_p(0xdead)
+    assert L.q3asr_pool_submit(None, None, None, None, 1, None, None, 8, 1, 0, ctypes.byref(job)) == 1 and not job.value
+    assert L.q3asr_job_done(None) == 0 and L.q3asr_job_wait(None, None, None) == 1 and L.q3asr_job_last_error(None) == b""
+    L.q3asr_job_free(None)
+    L.q3asr_pool_destroy(None)
 
 
 def test_model_size_and_bits_detection(built_lib):
