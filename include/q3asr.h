@@ -94,6 +94,11 @@ int q3asr_commit_weights(q3asr_handle* h);
 /* reads every *.safetensors in dir (audio_tower.* and model.* keys; fp32/fp16/bf16; conv weights in
  * MLX [O,kH,kW,I] or PyTorch [O,I,kH,kW] layout) and commits */
 int q3asr_load_safetensors(q3asr_handle* h, const char* dir);
+/* Host-only (no GPU): the tensors q3asr_load_safetensors would see in dir after validating every header against its file —
+ * one line per tensor, "name\tdtype\tshape\tbytes\n" (shape as 1024x128; U32 = MLX-packed, WeightLoading.swift:17-126).  buf == NULL
+ * sizes the buffer through *needed.  On Q3ASR_ERR_IO the buffer holds the reason instead (malformed header, offsets outside the
+ * file, oversized dimensions, unreadable directory). */
+int q3asr_checkpoint_list(const char* dir, char* buf, size_t cap, size_t* needed);
 int q3asr_is_loaded(const q3asr_handle* h);
 int q3asr_unload(q3asr_handle* h);
 size_t q3asr_memory_footprint(const q3asr_handle* h);

@@ -196,6 +196,29 @@ int q3asr_commit_weights(q3asr_handle* h) {
 int q3asr_load_safetensors(q3asr_handle* h, const char* dir) {
     return guarded(h, [&](Handle& x) { model_load_safetensors(&x, dir); });
 }
+int q3asr_checkpoint_list(const char* dir, char* buf, size_t cap, size_t* needed) {
+    static thread_local std::string err;
+    try {
+        const std::string s = checkpoint_list(dir);
+        if (needed) *needed = s.size() + 1;
+        if (buf == nullptr) return needed ? Q3ASR_OK : Q3ASR_ERR_INVALID;
+        if (cap < s.size() + 1) return Q3ASR_ERR_NOMEM;
+        memcpy(buf, s.c_str(), s.size() + 1);
+        return Q3ASR_OK;
+    } catch (const Error& e) {
+        err = e.what();
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    // the message instead of the list, as far as it fits
+    if (needed) *needed = err.size() + 1;
+    if (buf && cap > 0) {
+        const size_t n = std::min(cap - 1, err.size());
+        memcpy(buf, err.data(), n);
+        buf[n] = 0;
+    }
+    return Q3ASR_ERR_IO;
+}
 int q3asr_is_loaded(const q3asr_handle* h) { return h != nullptr && h->h.loaded ? 1 : 0; }
 int q3asr_unload(q3asr_handle* h) {
     return guarded(h, [&](Handle& x) { model_unload(&x); });

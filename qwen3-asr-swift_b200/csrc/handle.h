@@ -180,6 +180,8 @@ void model_get_tensor(const Handle* h, const char* name, float* out, size_t n);
 void model_commit(Handle* h);
 void model_unload(Handle* h);
 void model_load_safetensors(Handle* h, const char* dir);
+// validated tensor index of a checkpoint directory as text (name \t dtype \t shape \t bytes per line); host only
+std::string checkpoint_list(const char* dir);
 int encoder_tokens_for(int frames);
 // chat-template ids around `ntok` audio placeholders; *audio_at = index of the first placeholder (Qwen3ASR.swift:196-233)
 void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at);

@@ -51,9 +51,12 @@ struct Parser {  // just enough JSON for a safetensors header
     int64_t num() {
         ws();
         int64_t v = 0;
-        bool any = false;
-        while (i < n && s[i] >= '0' && s[i] <= '9') { v = v * 10 + (s[i++] - '0'); any = true; }
-        if (!any) throw Error(Q3ASR_ERR_IO, "safetensors header: expected a number at byte " + std::to_string(i));
+        int digits = 0;
+        while (i < n && s[i] >= '0' && s[i] <= '9') {
+            if (++digits > 18) throw Error(Q3ASR_ERR_IO, "safetensors header: number too long at byte " + std::to_string(i));
+            v = v * 10 + (s[i++] - '0');
+        }
+        if (digits == 0) throw Error(Q3ASR_ERR_IO, "safetensors header: expected a number at byte " + std::to_string(i));
         return v;
     }
     void skip_value() {
@@ -124,12 +127,81 @@ struct Located {
     uint64_t base = 0;  // file offset of the data section
 };
 
-void read_entry(FILE* fp, const Located& l, std::vector<char>* buf) {
-    Q3_CHECK(l.e.end >= l.e.begin, Q3ASR_ERR_IO, "load_safetensors: bad entry " + l.e.name);
-    buf->resize(l.e.end - l.e.begin);
-    Q3_CHECK(fseek(fp, (long)(l.base + l.e.begin), SEEK_SET) == 0 && fread(buf->data(), 1, buf->size(), fp) == buf->size(), Q3ASR_ERR_IO,
-             "load_safetensors: truncated data for " + l.e.name);
+// Elements of a tensor, with every dimension and the product bounded so that no later size computation can wrap.
+size_t checked_numel(const Entry& e) {
+    Q3_CHECK(!e.shape.empty() && e.shape.size() <= 4, Q3ASR_ERR_IO, "load_safetensors: bad rank for " + e.name);
+    uint64_t numel = 1;
+    for (int64_t v : e.shape) {
+        Q3_CHECK(v >= 0 && v <= (int64_t)1 << 31, Q3ASR_ERR_IO, "load_safetensors: bad dimension in " + e.name);
+        numel *= (uint64_t)v;
+        Q3_CHECK(numel <= (uint64_t)1 << 36, Q3ASR_ERR_IO, "load_safetensors: tensor too large: " + e.name);
+    }
+    return (size_t)numel;
 }
+
+// Every audio_tower.* / model.* / lm_head.* entry of every *.safetensors file of a directory, each checked against the size of the
+// file that holds it (a header may claim anything).  Owns the open files.
+struct CheckpointIndex {
+    std::vector<std::string> files;
+    std::vector<FILE*> fps;
+    std::map<std::string, Located> index;
+    CheckpointIndex() = default;
+    CheckpointIndex(const CheckpointIndex&) = delete;
+    CheckpointIndex& operator=(const CheckpointIndex&) = delete;
+    ~CheckpointIndex() {
+        for (FILE* f : fps)
+            if (f) fclose(f);
+    }
+
+    void open(const char* dir) {
+        Q3_CHECK(dir != nullptr, Q3ASR_ERR_INVALID, "load_safetensors: null directory");
+        DIR* d = opendir(dir);
+        Q3_CHECK(d != nullptr, Q3ASR_ERR_IO, std::string("load_safetensors: cannot open directory ") + dir);
+        while (dirent* ent = readdir(d)) {
+            const std::string f = ent->d_name;
+            if (f.size() > 12 && f.compare(f.size() - 12, 12, ".safetensors") == 0) files.push_back(std::string(dir) + "/" + f);
+        }
+        closedir(d);
+        std::sort(files.begin(), files.end());
+        // "noWeightsFound" of the reference (MLXCommon/WeightLoading.swift:224-239)
+        Q3_CHECK(!files.empty(), Q3ASR_ERR_IO, std::string("load_safetensors: no .safetensors files in ") + dir);
+        fps.assign(files.size(), nullptr);
+        for (size_t fi = 0; fi < files.size(); fi++) {
+            FILE* fp = fps[fi] = fopen(files[fi].c_str(), "rb");
+            Q3_CHECK(fp != nullptr, Q3ASR_ERR_IO, "load_safetensors: cannot open " + files[fi]);
+            Q3_CHECK(fseeko(fp, 0, SEEK_END) == 0, Q3ASR_ERR_IO, "load_safetensors: cannot seek in " + files[fi]);
+            const off_t fsize = ftello(fp);
+            Q3_CHECK(fsize >= 8 && fseeko(fp, 0, SEEK_SET) == 0, Q3ASR_ERR_IO, "load_safetensors: " + files[fi] + " is too small");
+            uint64_t hl = 0;
+            Q3_CHECK(fread(&hl, 8, 1, fp) == 1 && hl > 1 && hl < (1ull << 30) && hl <= (uint64_t)fsize - 8, Q3ASR_ERR_IO,
+                     "load_safetensors: bad header length in " + files[fi]);
+            std::string hdr(hl, 0);
+            Q3_CHECK(fread(&hdr[0], 1, hl, fp) == hl, Q3ASR_ERR_IO, "load_safetensors: truncated header in " + files[fi]);
+            const uint64_t data_bytes = (uint64_t)fsize - 8 - hl;
+            for (Entry& e : parse_header(hdr)) {
+                // the forced-aligner checkpoints carry a "thinker." prefix and keep the classification head under lm_head.*
+                // (WeightLoading.swift:162-179); everything else is ignored
+                if (e.name.compare(0, 8, "thinker.") == 0) e.name = e.name.substr(8);
+                if (e.name.compare(0, 12, "audio_tower.") != 0 && e.name.compare(0, 6, "model.") != 0 && e.name.compare(0, 8, "lm_head.") != 0)
+                    continue;
+                Q3_CHECK(e.begin <= e.end && e.end <= data_bytes, Q3ASR_ERR_IO, "load_safetensors: data of " + e.name + " lies outside " + files[fi]);
+                checked_numel(e);
+                Located l;
+                l.e = e;
+                l.file = (int)fi;
+                l.base = 8 + hl;
+                index[e.name] = l;
+            }
+        }
+    }
+
+    void read(const Located& l, std::vector<char>* buf) const {  // offsets were checked against the file size in open()
+        buf->resize((size_t)(l.e.end - l.e.begin));
+        Q3_CHECK(fseeko(fps[l.file], (off_t)(l.base + l.e.begin), SEEK_SET) == 0 &&
+                     fread(buf->data(), 1, buf->size(), fps[l.file]) == buf->size(),
+                 Q3ASR_ERR_IO, "load_safetensors: truncated data for " + l.e.name);
+    }
+};
 
 float half_to_float(uint16_t hbits) {
     const uint32_t sign = (uint32_t)(hbits & 0x8000) << 16;
@@ -164,49 +236,12 @@ float scalar_at(const std::vector<char>& buf, const std::string& dtype, size_t i
 // `in` features is stored as in*bits/32 little-endian uint32 words (value j of a word at bits [j*bits, (j+1)*bits)) plus one
 // (scale, bias) pair per group of 64 features; w = scale * q + bias.  Dequantised at load: the B200 path computes in bf16.
 void model_load_safetensors(Handle* h, const char* dir) {
-    Q3_CHECK(dir != nullptr, Q3ASR_ERR_INVALID, "load_safetensors: null directory");
-    DIR* d = opendir(dir);
-    Q3_CHECK(d != nullptr, Q3ASR_ERR_IO, std::string("load_safetensors: cannot open directory ") + dir);
-    std::vector<std::string> files;
-    while (dirent* ent = readdir(d)) {
-        const std::string f = ent->d_name;
-        if (f.size() > 12 && f.compare(f.size() - 12, 12, ".safetensors") == 0) files.push_back(std::string(dir) + "/" + f);
-    }
-    closedir(d);
-    std::sort(files.begin(), files.end());
-    // "noWeightsFound" of the reference (MLXCommon/WeightLoading.swift:224-239)
-    Q3_CHECK(!files.empty(), Q3ASR_ERR_IO, std::string("load_safetensors: no .safetensors files in ") + dir);
+    CheckpointIndex ck;
+    ck.open(dir);  // pass 1
+    const std::map<std::string, Located>& index = ck.index;
     std::vector<std::pair<std::string, std::vector<int64_t>>> specs;
     model_tensor_specs(h->cfg, &specs);
-
-    // pass 1: index every audio_tower.* / model.* / lm_head.* entry of every file
-    std::map<std::string, Located> index;
-    std::vector<FILE*> fps(files.size(), nullptr);
-    auto close_all = [&]() {
-        for (FILE* f : fps)
-            if (f) fclose(f);
-    };
-    try {
-        for (size_t fi = 0; fi < files.size(); fi++) {
-            fps[fi] = fopen(files[fi].c_str(), "rb");
-            Q3_CHECK(fps[fi] != nullptr, Q3ASR_ERR_IO, "load_safetensors: cannot open " + files[fi]);
-            uint64_t hl = 0;
-            Q3_CHECK(fread(&hl, 8, 1, fps[fi]) == 1 && hl > 1 && hl < (1ull << 30), Q3ASR_ERR_IO, "load_safetensors: bad header length in " + files[fi]);
-            std::string hdr(hl, 0);
-            Q3_CHECK(fread(&hdr[0], 1, hl, fps[fi]) == hl, Q3ASR_ERR_IO, "load_safetensors: truncated header in " + files[fi]);
-            for (Entry& e : parse_header(hdr)) {
-                // the forced-aligner checkpoints carry a "thinker." prefix and keep the classification head under lm_head.*
-                // (WeightLoading.swift:162-179); everything else is ignored
-                if (e.name.compare(0, 8, "thinker.") == 0) e.name = e.name.substr(8);
-                if (e.name.compare(0, 12, "audio_tower.") != 0 && e.name.compare(0, 6, "model.") != 0 && e.name.compare(0, 8, "lm_head.") != 0)
-                    continue;
-                Located l;
-                l.e = e;
-                l.file = (int)fi;
-                l.base = 8 + hl;
-                index[e.name] = l;
-            }
-        }
+    {
         // pass 2: every tensor the model needs, dequantising MLX-packed ones
         size_t loaded = 0;
         std::vector<char> buf, sbuf, bbuf;
@@ -216,10 +251,8 @@ void model_load_safetensors(Handle* h, const char* dir) {
             if (it == index.end()) continue;
             const Located& l = it->second;
             const Entry& e = l.e;
-            Q3_CHECK(!e.shape.empty() && e.shape.size() <= 4, Q3ASR_ERR_IO, "load_safetensors: bad entry " + e.name);
-            read_entry(fps[l.file], l, &buf);
-            size_t numel = 1;
-            for (int64_t v : e.shape) numel *= (size_t)v;
+            ck.read(l, &buf);
+            const size_t numel = checked_numel(e);
             if (e.dtype == "U32") {
                 const std::string stem = e.name.substr(0, e.name.size() - 7);  // strip ".weight"
                 auto si = index.find(stem + ".scales"), bi = index.find(stem + ".biases");
@@ -232,8 +265,8 @@ void model_load_safetensors(Handle* h, const char* dir) {
                 Q3_CHECK(buf.size() == numel * 4 && cols > 0 && (words * 32) % cols == 0, Q3ASR_ERR_IO, "load_safetensors: size mismatch for " + e.name);
                 const int bits = (int)(words * 32 / cols);
                 Q3_CHECK(bits == 2 || bits == 4 || bits == 8, Q3ASR_ERR_INVALID, "load_safetensors: unsupported quantisation width for " + e.name);
-                read_entry(fps[si->second.file], si->second, &sbuf);
-                read_entry(fps[bi->second.file], bi->second, &bbuf);
+                ck.read(si->second, &sbuf);
+                ck.read(bi->second, &bbuf);
                 const size_t sb = se.dtype == "F32" ? 4 : 2;
                 Q3_CHECK(se.dtype == "F32" || se.dtype == "BF16" || se.dtype == "F16", Q3ASR_ERR_INVALID, "load_safetensors: unsupported scales dtype for " + e.name);
                 Q3_CHECK(sbuf.size() == (size_t)(rows * groups) * sb && bbuf.size() == sbuf.size(), Q3ASR_ERR_IO, "load_safetensors: scales size mismatch for " + e.name);
@@ -262,12 +295,27 @@ void model_load_safetensors(Handle* h, const char* dir) {
         }
         Q3_CHECK(loaded == specs.size(), Q3ASR_ERR_IO,
                  "load_safetensors: found " + std::to_string(loaded) + " of " + std::to_string(specs.size()) + " expected tensors in " + dir);
-    } catch (...) {
-        close_all();
-        throw;
     }
-    close_all();
     model_commit(h);
+}
+
+// q3asr_checkpoint_list: the validated index as text, one tensor per line (host only)
+std::string checkpoint_list(const char* dir) {
+    CheckpointIndex ck;
+    ck.open(dir);
+    std::string out;
+    for (const auto& kv : ck.index) {
+        const Entry& e = kv.second.e;
+        auto printable = [](std::string v) {  // the names come from the file: keep the line format intact whatever they hold
+            for (char& c : v)
+                if ((unsigned char)c < 0x20) c = '?';
+            return v;
+        };
+        out += printable(e.name) + "\t" + printable(e.dtype) + "\t";
+        for (size_t i = 0; i < e.shape.size(); i++) out += (i ? "x" : "") + std::to_string(e.shape[i]);
+        out += "\t" + std::to_string(e.end - e.begin) + "\n";
+    }
+    return out;
 }
 
 }  // namespace q3

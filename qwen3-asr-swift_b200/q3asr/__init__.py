@@ -76,7 +76,7 @@ class Qwen3DecodingOptions:
 EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
     "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
-    "q3asr_load_safetensors", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
+    "q3asr_load_safetensors", "q3asr_checkpoint_list", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
     "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
@@ -119,6 +119,7 @@ def lib():
         L.q3asr_get_tensor.argtypes = [vp, ctypes.c_char_p, vp, cs]
         L.q3asr_commit_weights.argtypes = [vp]
         L.q3asr_load_safetensors.argtypes = [vp, ctypes.c_char_p]
+        L.q3asr_checkpoint_list.argtypes = [ctypes.c_char_p, ctypes.c_char_p, cs, ctypes.POINTER(cs)]
         L.q3asr_is_loaded.argtypes = [vp]
         L.q3asr_unload.argtypes = [vp]
         L.q3asr_memory_footprint.argtypes = [vp]
@@ -335,6 +336,23 @@ def bf16_bits_to_f32(b):
 
 def _ptr_array(arrs):
     return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def checkpoint_list(model_dir):
+    """[(name, dtype, shape, bytes)] of the tensors q3asr_load_safetensors would read from model_dir (host only; raises Q3Error with
+    the loader's message when a header is malformed or points outside its file)."""
+    need = ctypes.c_size_t()
+    d = os.fsencode(model_dir)
+    rc = lib().q3asr_checkpoint_list(d, None, 0, ctypes.byref(need))
+    buf = ctypes.create_string_buffer(max(need.value, 1))
+    rc = lib().q3asr_checkpoint_list(d, buf, len(buf), ctypes.byref(need))
+    if rc != OK:
+        raise Q3Error(rc, buf.value.decode("utf-8", "replace"))
+    out = []
+    for line in buf.value.decode("utf-8", "replace").splitlines():
+        name, dtype, shape, nbytes = line.split("\t")
+        out.append((name, dtype, tuple(int(v) for v in shape.split("x")), int(nbytes)))
+    return out
 
 
 def detect_model_size(model_id):
