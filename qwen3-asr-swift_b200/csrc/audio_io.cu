@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -265,13 +266,13 @@ int q3asr_wav_parse(const uint8_t* data, size_t size, float* samples, size_t cap
 int q3asr_wav_load(const char* path, float* samples, size_t cap, size_t* n_samples, int* sample_rate) {
     return io_guarded([&]() {
         Q3_CHECK(path != nullptr, Q3ASR_ERR_INVALID, "wav_load: null path");
-        FILE* f = fopen(path, "rb");
+        std::unique_ptr<FILE, int (*)(FILE*)> f(fopen(path, "rb"), fclose);  // closed on every path out, bad_alloc included
         if (!f) throw q3::Error(Q3ASR_ERR_IO, std::string("wav_load: cannot open ") + path);
         std::vector<uint8_t> buf;
         uint8_t tmp[1 << 16];
         size_t r;
-        while ((r = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + r);
-        fclose(f);
+        while ((r = fread(tmp, 1, sizeof(tmp), f.get())) > 0) buf.insert(buf.end(), tmp, tmp + r);
+        f.reset();
         const size_t n = q3::wav_parse(buf.data(), buf.size(), samples, cap, sample_rate);
         if (n_samples) *n_samples = n;
     });
