@@ -127,6 +127,14 @@ typedef struct q3asr_prompt {
     int raw_suffix;
 } q3asr_prompt;
 
+/* Host-only: TextPreprocessor.splitIntoWordPairs, default path (TextPreprocessing.swift:97-115, 163-243, 262-306) — split UTF-8 text on
+ * Unicode white space, one word per Han ideograph, punctuation kept on the surface form only.  buf receives n_pairs records
+ * "surface\0cleaned\0"; *needed = bytes required (call with buf == NULL to size).  language NULL = "English".  Japanese, Korean, Thai,
+ * Lao, Khmer, Burmese and Tibetan return Q3ASR_ERR_INVALID: the reference segments them with Apple's NLTokenizer (:101-160), which
+ * stays on the Swift side.  Errors: q3asr_text_last_error(). */
+int q3asr_text_word_pairs(const char* text, const char* language, char* buf, size_t cap, size_t* needed, int* n_pairs);
+const char* q3asr_text_last_error(void);
+
 /* Host-only (no GPU work): the chat-template ids the prefill runs on for an utterance with n_audio_tokens audio tokens —
  * <|im_start|>system\n[context]<|im_end|>\n<|im_start|>user\n<|audio_start|><|audio_pad|>*n<|audio_end|><|im_end|>\n
  * <|im_start|>assistant\n[language]<asr_text>  (Qwen3ASR.swift:196-233; raw_suffix: ForcedAligner.swift:338-378).

@@ -180,6 +180,12 @@ void model_get_tensor(const Handle* h, const char* name, float* out, size_t n);
 void model_commit(Handle* h);
 void model_unload(Handle* h);
 void model_load_safetensors(Handle* h, const char* dir);
+// the forced aligner's word splitter (csrc/text.cu; TextPreprocessing.swift:97-115, 163-243): surface keeps the punctuation, cleaned
+// is what the tokenizer sees
+struct WordPair {
+    std::string surface, cleaned;
+};
+std::vector<WordPair> split_into_word_pairs(const std::string& text, const std::string& language);
 // validated tensor index of a checkpoint directory as text (name \t dtype \t shape \t bytes per line); host only
 std::string checkpoint_list(const char* dir);
 int encoder_tokens_for(int frames);

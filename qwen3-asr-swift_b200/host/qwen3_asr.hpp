@@ -357,34 +357,37 @@ class Qwen3ForcedAligner {
     int timestampTokenId = 151705;  // Qwen3ASR.swift:62 (the tests' tiny vocabulary overrides it)
 
     struct WordPair { std::string surface, cleaned; };
-    static std::vector<WordPair> splitIntoWordPairs(const std::string& text) {
+    // TextPreprocessor.splitIntoWordPairs (TextPreprocessing.swift:97-115) through the library's Unicode-aware splitter.  Throws
+    // AudioModelError for the languages the reference hands to NLTokenizer (Japanese, Korean, Thai, ...).
+    static std::vector<WordPair> splitIntoWordPairs(const std::string& text, const std::string& language = "English") {
+        size_t need = 0;
+        int n = 0;
+        int rc = q3asr_text_word_pairs(text.c_str(), language.c_str(), nullptr, 0, &need, &n);
+        std::string flat(need, '\0');
+        if (rc == Q3ASR_OK && need) rc = q3asr_text_word_pairs(text.c_str(), language.c_str(), &flat[0], flat.size(), &need, &n);
+        if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("text: ") + q3asr_text_last_error());
         std::vector<WordPair> out;
-        size_t i = 0;
-        while (i < text.size()) {
-            while (i < text.size() && std::isspace((unsigned char)text[i])) i++;
-            size_t j = i;
-            while (j < text.size() && !std::isspace((unsigned char)text[j])) j++;
-            if (j > i) {
-                WordPair w;
-                w.surface = text.substr(i, j - i);
-                for (unsigned char c : w.surface)
-                    if (std::isalnum(c) || c == '\'' || c >= 0x80) w.cleaned += (char)c;
-                if (!w.cleaned.empty()) out.push_back(w);
-                else if (!out.empty()) out.back().surface += w.surface;  // punctuation-only token: keep it on the previous word
-            }
-            i = j;
+        const char* p = flat.data();
+        for (int i = 0; i < n; i++) {
+            WordPair w;
+            w.surface = p;
+            p += w.surface.size() + 1;
+            w.cleaned = p;
+            p += w.cleaned.size() + 1;
+            out.push_back(std::move(w));
         }
         return out;
     }
 
     // ForcedAligner.swift:226-331.  Returns [] when no tokenizer is set or the text has no words (like the reference).
-    std::vector<AlignedWord> align(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000) {
+    std::vector<AlignedWord> align(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000,
+                                   const std::string& language = "English") {
         std::vector<AlignedWord> out;
         if (!tok_.encode) return out;
         std::vector<int32_t> ids;
         std::vector<int> pos;
         std::vector<std::string> words;
-        for (const WordPair& w : splitIntoWordPairs(text)) {  // TextPreprocessing.swift:48-80: <timestamp> word tokens <timestamp>
+        for (const WordPair& w : splitIntoWordPairs(text, language)) {  // TextPreprocessing.swift:48-80: <timestamp> word tokens <timestamp>
             const std::vector<int32_t> t = tok_.encode(w.cleaned);
             if (t.empty()) {
                 if (!words.empty()) words.back() += w.surface;
@@ -416,7 +419,8 @@ class Qwen3ForcedAligner {
     }
 
     // ForcedAligner.swift:104-176: re-align the remainder when the tail of a long recording collapses onto one timestamp
-    std::vector<AlignedWord> alignLong(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000) {
+    std::vector<AlignedWord> alignLong(const std::vector<float>& audio, const std::string& text, int sampleRate = 16000,
+                                       const std::string& language = "English") {
         const float bypassThresholdSeconds = 240.f, minChunkSeconds = 5.f, plateauTolerance = 0.1f;
         const int plateauMinWords = 5;
         std::vector<AlignedWord> all;
@@ -425,7 +429,7 @@ class Qwen3ForcedAligner {
         float offset = 0.f;
         for (int pass = 1; !remAudio.empty() && !remText.empty() && pass <= 10; pass++) {
             const float duration = (float)remAudio.size() / (float)sampleRate;
-            std::vector<AlignedWord> a = align(remAudio, remText, sampleRate);
+            std::vector<AlignedWord> a = align(remAudio, remText, sampleRate, language);
             if (a.empty()) break;
             auto append = [&](size_t count) {
                 for (size_t i = 0; i < count; i++) all.push_back(AlignedWord{a[i].text, a[i].startTime + offset, a[i].endTime + offset});

@@ -77,7 +77,7 @@ EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
     "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
     "q3asr_load_safetensors", "q3asr_checkpoint_list", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
-    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
+    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
@@ -128,6 +128,8 @@ def lib():
         L.q3asr_mel.argtypes = [vp, vp, cs, vp, ctypes.POINTER(ci)]
         L.q3asr_mel_batch.argtypes = [vp, vp, vp, ci, vp, vp]
         L.q3asr_encoder_tokens.argtypes = [ci]
+        L.q3asr_text_word_pairs.argtypes = [ctypes.c_char_p, ctypes.c_char_p, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
+        L.q3asr_text_last_error.restype = ctypes.c_char_p
         L.q3asr_prompt_ids.argtypes = [vp, ci, vp, vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.q3asr_encode.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
         L.q3asr_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp]
@@ -336,6 +338,25 @@ def bf16_bits_to_f32(b):
 
 def _ptr_array(arrs):
     return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def text_word_pairs(text, language="English"):
+    """TextPreprocessor.splitIntoWordPairs through the library (csrc/text.cu): [(surface, cleaned)].  `text` may be str or UTF-8 bytes."""
+    raw = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    if b"\0" in raw:
+        raise ValueError("text_word_pairs: embedded NUL")
+    need, n = ctypes.c_size_t(), ctypes.c_int()
+    lang = language.encode("utf-8") if language is not None else None
+    rc = lib().q3asr_text_word_pairs(raw, lang, None, 0, ctypes.byref(need), ctypes.byref(n))
+    if rc != OK:
+        raise Q3Error(rc, lib().q3asr_text_last_error().decode("utf-8", "replace"))
+    buf = ctypes.create_string_buffer(max(need.value, 1))
+    rc = lib().q3asr_text_word_pairs(raw, lang, buf, need.value, ctypes.byref(need), ctypes.byref(n))
+    if rc != OK:
+        raise Q3Error(rc, lib().q3asr_text_last_error().decode("utf-8", "replace"))
+    parts = buf.raw[:need.value].split(b"\0")[:2 * n.value]
+    dec = (lambda b: b.decode("utf-8")) if isinstance(text, str) else (lambda b: b)
+    return [(dec(parts[2 * i]), dec(parts[2 * i + 1])) for i in range(n.value)]
 
 
 def checkpoint_list(model_dir):

@@ -34,6 +34,25 @@ def is_han_ideograph(ch):
             or 0x2B740 <= v <= 0x2B81F or 0x2B820 <= v <= 0x2CEAF or 0xF900 <= v <= 0xFAFF)
 
 
+_WHITE_SPACE = frozenset([*range(9, 14), 0x20, 0x85, 0xA0, 0x1680, *range(0x2000, 0x200B), 0x2028, 0x2029, 0x202F, 0x205F, 0x3000])
+
+
+def _segments(text):
+    """text.split(whereSeparator: \\.isWhitespace) (TextPreprocessing.swift:166): the Unicode White_Space property (str.split() would
+    also break on U+001C..U+001F)."""
+    out, cur = [], ""
+    for ch in text:
+        if ord(ch) in _WHITE_SPACE:
+            if cur:
+                out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur:
+        out.append(cur)
+    return out
+
+
 def _pairs_for_segment(seg):
     """TextPreprocessing.swift:191-243."""
     if not any(is_han_ideograph(ch) for ch in seg):
@@ -73,7 +92,7 @@ def _pairs_for_segment(seg):
 def tokenize_space_lang_pairs(text):
     """TextPreprocessing.swift:163-184."""
     pairs = []
-    for segment in text.split():
+    for segment in _segments(text):
         seg_pairs = _pairs_for_segment(segment)
         if not seg_pairs:
             if pairs:

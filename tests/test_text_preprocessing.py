@@ -87,3 +87,81 @@ def test_prepare_for_alignment_slots():
     assert st.token_ids[0] == 7 and st.token_ids.count(7) == 4
     assert st.timestamp_positions == [0, 3, 4, 8]
     assert all(st.token_ids[p] == 7 for p in st.timestamp_positions)
+
+
+# ---- the library's splitter (csrc/text.cu, q3asr_text_word_pairs): same reference cases, then agreement with the Python one ----
+REFERENCE_CASES = [  # (text, language, surfaces, cleaned) — ForcedAlignerTests.swift:14-48, 140-211
+    ("Hello world test", "English", ["Hello", "world", "test"], ["Hello", "world", "test"]),
+    ("你好世界", "Chinese", ["你", "好", "世", "界"], ["你", "好", "世", "界"]),
+    ("Hello你好world", "Chinese", ["Hello", "你", "好", "world"], ["Hello", "你", "好", "world"]),
+    ("Hello, world!", "English", ["Hello,", "world!"], ["Hello", "world"]),
+    ("don't stop", "English", ["don't", "stop"], ["don't", "stop"]),
+    ("नमस्ते दोस्त", "hindi", ["नमस्ते", "दोस्त"], ["नमस्ते", "दोस्त"]),
+    ("Guten Morgen, Donaudampfschifffahrtsgesellschaft!", "german", ["Guten", "Morgen,", "Donaudampfschifffahrtsgesellschaft!"],
+     ["Guten", "Morgen", "Donaudampfschifffahrtsgesellschaft"]),
+    ("Hello, world! How are you?", "English", ["Hello,", "world!", "How", "are", "you?"], ["Hello", "world", "How", "are", "you"]),
+    ("you're great.", "English", ["you're", "great."], ["you're", "great"]),
+    ('"Hello" she said.', "English", ['"Hello"', "she", "said."], ["Hello", "she", "said"]),
+    ("你好，世界。", "Chinese", ["你", "好，", "世", "界。"], ["你", "好", "世", "界"]),
+    ("Hello, 你好world.", "Chinese", ["Hello,", "你", "好", "world."], ["Hello", "你", "好", "world"]),
+    ("wait — what", "English", ["wait—", "what"], ["wait", "what"]),
+    ("「你好」", "Chinese", ["「你", "好」"], ["你", "好"]),
+    ("  ", "English", [], []),
+    ("!!!", "English", [], []),
+]
+
+
+@pytest.fixture(scope="module")
+def q3(built_lib):
+    return built_lib
+
+
+@pytest.mark.parametrize("text,lang,surfaces,cleaned", REFERENCE_CASES)
+def test_c_splitter_reference_cases(q3, text, lang, surfaces, cleaned):
+    got = q3.text_word_pairs(text, lang)
+    assert [s for s, _ in got] == surfaces and [c for _, c in got] == cleaned
+
+
+def test_c_splitter_refuses_nltokenizer_languages(q3):
+    for lang in ("Japanese", "ja", "korean", "Thai", "lo", "khmer", "myanmar", "bo"):
+        with pytest.raises(q3.Q3Error) as e:
+            q3.text_word_pairs("x", lang)
+        assert e.value.code == 1 and "NLTokenizer" in str(e.value)
+    assert q3.text_word_pairs("x y", None) == [("x", "x"), ("y", "y")]     # NULL language = English
+
+
+def test_c_splitter_matches_python_on_mixed_scripts(q3):
+    """Random text over many scripts, punctuation, combining marks, astral code points and every kind of white space."""
+    import random
+    rnd = random.Random(11)
+    alphabet = (list("abcXYZ019'’\".,!?-—()[]«»…·") + list("äöüßéñçøåğİıșț") + list("привет") + list("Ελληνικά") + list("שלוםمرحبا")
+                + list("नमस्तेবন্ধু") + list("你好世界漢字㐀𠀀𪜀") + list("かなカナ한글") + list("ᠮᠣᠩ") + list("́̈⃝ा")
+                + list("①Ⅷ½٣") + list("😀𝒜€©™°") + list(" \t\n\r\x0b\x0c\x85       　") + list("\x1c\x1f​﻿"))
+    for _ in range(600):
+        text = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 40)))
+        want = [(p.surface, p.cleaned) for p in tp.split_into_word_pairs(text, "English")]
+        assert q3.text_word_pairs(text, "English") == want, repr(text)
+
+
+def test_c_splitter_every_code_point_classified_like_python(q3):
+    """The generated category table (csrc/unicode_kept.inc) against unicodedata, one probe per code point in bulk: the cleaned form of a
+    string holding every code point of a block keeps exactly the letters, numbers and marks."""
+    import unicodedata
+    for base in range(0, 0x110000, 0x1000):
+        cps = [cp for cp in range(max(base, 1), base + 0x1000) if not 0xD800 <= cp <= 0xDFFF and cp not in tp._WHITE_SPACE
+               and not tp.is_han_ideograph(chr(cp))]
+        if not cps:
+            continue
+        s = "".join(map(chr, cps))
+        got = q3.text_word_pairs(s, "English")
+        want = "".join(c for c in s if c == "'" or unicodedata.category(c) in tp._KEPT)
+        assert (got[0][1] if got else "") == want, hex(base)
+
+
+def test_c_splitter_invalid_utf8_is_carried_on_the_surface_only(q3):
+    got = q3.text_word_pairs(b"ab\xff\xfecd \xe4\xbd x\xc0\xaf \xed\xa0\x80y \xf4\x90\x80\x80z", "English")
+    # stray 0xFF/0xFE, a truncated 3-byte sequence (rides on the previous word like punctuation), an overlong "/", a surrogate, > U+10FFFF
+    assert got == [(b"ab\xff\xfecd\xe4\xbd", b"abcd"), (b"x\xc0\xaf", b"x"), (b"\xed\xa0\x80y", b"y"), (b"\xf4\x90\x80\x80z", b"z")]
+    # a truncated sequence at the very end of the text must not be read past
+    assert q3.text_word_pairs(b"ok \xe4\xbd", "English") == [(b"ok\xe4\xbd", b"ok")]
+    assert q3.text_word_pairs(b"\xf0\x9f", "English") == []
