@@ -75,7 +75,7 @@ typedef struct q3asr_config {
 int q3asr_config_preset(const char* name, q3asr_config* cfg);
 
 const char* q3asr_version(void);
-/* message of the last failed call on this handle (handle may be NULL: last failed create) */
+/* message of the last failed call on this handle (handle may be NULL: the calling thread's last failed q3asr_create) */
 const char* q3asr_last_error(const q3asr_handle* h);
 
 int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out);

@@ -17,8 +17,7 @@ struct q3asr_handle {
 
 namespace {
 
-std::string g_create_error;
-std::mutex g_create_mu;
+thread_local std::string g_create_error;  // q3asr_last_error(NULL): the calling thread's last failed q3asr_create
 
 template <typename F>
 int guarded(q3asr_handle* hh, F&& fn) {
@@ -135,7 +134,6 @@ int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out) {
         *out = hh;
         return Q3ASR_OK;
     } catch (const std::exception& e) {
-        std::lock_guard<std::mutex> lk(g_create_mu);
         g_create_error = e.what();
         const Error* qe = dynamic_cast<const Error*>(&e);
         if (hh) q3asr_destroy(hh);

@@ -733,6 +733,11 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     const int n_workers = std::max(1, std::min({batch, env_int("Q3ASR_UPLOAD_THREADS", 4), (int)std::thread::hardware_concurrency() / 2}));
     std::vector<std::thread> workers;
     std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
+    workers.reserve((size_t)n_workers);
+    struct Joiner {  // the threads borrow the caller's buffers and the locals above: never leave without joining (a failed thread start included)
+        std::vector<std::thread>& t;
+        ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
+    } joiner{workers};
     for (int w = 0; w < n_workers; w++)
         workers.emplace_back([&, w]() {
             cudaError_t e = cudaSetDevice(h->device);
@@ -750,10 +755,6 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
             }
             werr[(size_t)w] = e;
         });
-    struct Joiner {  // the threads borrow the caller's buffers: never leave without joining
-        std::vector<std::thread>& t;
-        ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
-    } joiner{workers};
     Q3_CUDA(cudaMemcpyAsync(bs->mel_clips.p, bs->mel.clips.data(), sizeof(MelClip) * batch, cudaMemcpyHostToDevice, h->stream));
     // plan
     std::vector<int> frames(batch);
