@@ -74,16 +74,23 @@ typedef struct q3asr_config {
  * or "tiny" / "tiny-aligner" (small configurations used by the parity tests) */
 int q3asr_config_preset(const char* name, q3asr_config* cfg);
 
+/* library identification (no reference equivalent; the Swift shim logs it next to the model id) */
 const char* q3asr_version(void);
-/* message of the last failed call on this handle (handle may be NULL: the calling thread's last failed q3asr_create) */
+/* message of the last failed call on this handle (handle may be NULL: the calling thread's last failed q3asr_create) — the text the
+ * Swift shim puts into AudioModelError.modelLoadFailed / weightLoadingFailed (Sources/AudioCommon/AudioModelError.swift:4-34) */
 const char* q3asr_last_error(const q3asr_handle* h);
 
+/* Qwen3ASRModel.init(audioConfig:textConfig:) (Qwen3ASR.swift:82-91): an empty model of the given dimensions on one GPU, weights to
+ * follow; q3asr_destroy is its deinit.  Fails with Q3ASR_ERR_CUDA when there is no sm_100 device (no CPU fallback). */
 int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out);
 void q3asr_destroy(q3asr_handle* h);
 
 /* ---- weights (names are the reference's safetensors keys, WeightLoading.swift:17-126, 235-323) ---- */
-/* deterministic random initialisation: bf16(0.02 * approx-normal) keyed by (seed, tensor name); norm weights 1 */
+/* deterministic random initialisation: bf16(0.02 * approx-normal) keyed by (seed, tensor name); norm weights 1.  No reference
+ * equivalent: it stands in for the checkpoints (no network here); oracle/weights.py generates the same values. */
 int q3asr_init_random(q3asr_handle* h, uint64_t seed);
+/* the tensors of the model by the reference's key names — what Qwen3ASRWeightLoader.loadWeights walks (WeightLoading.swift:17-126):
+ * enumerate, set one by one (any of the dtypes MLX.loadArrays yields), read back, then commit */
 int q3asr_tensor_count(const q3asr_handle* h);
 int q3asr_tensor_info(const q3asr_handle* h, int index, char* name, int name_cap, int64_t* shape4, int* ndim);
 /* dtype: 0 = fp32, 1 = bf16, 2 = fp16; converted to bf16 on upload */
@@ -91,8 +98,9 @@ int q3asr_set_tensor(q3asr_handle* h, const char* name, const void* data, int dt
 int q3asr_get_tensor(const q3asr_handle* h, const char* name, float* out, size_t out_elems);
 /* builds the fused / permuted device layouts from the named tensors; required after q3asr_set_tensor */
 int q3asr_commit_weights(q3asr_handle* h);
-/* reads every *.safetensors in dir (audio_tower.* and model.* keys; fp32/fp16/bf16; conv weights in
- * MLX [O,kH,kW,I] or PyTorch [O,I,kH,kW] layout) and commits */
+/* Qwen3ASRWeightLoader.loadWeights / CommonWeightLoader.loadAllSafetensors (WeightLoading.swift:17-126, MLXCommon/WeightLoading.swift:
+ * 9-11, 48-95): reads every *.safetensors in dir (audio_tower.* and model.* keys, the aligner's thinker.* / lm_head.*; fp32/fp16/bf16
+ * and MLX U32-packed 4-/8-bit tensors, dequantised; conv weights in MLX [O,kH,kW,I] or PyTorch [O,I,kH,kW] layout) and commits */
 int q3asr_load_safetensors(q3asr_handle* h, const char* dir);
 /* Host-only (no GPU): the tensors q3asr_load_safetensors would see in dir after validating every header against its file —
  * one line per tensor, "name\tdtype\tshape\tbytes\n" (shape as 1024x128; U32 = MLX-packed, WeightLoading.swift:17-126).  buf == NULL
@@ -198,7 +206,9 @@ int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n_samples, con
 int q3asr_prefill_logits(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt, float* logits);
 
 /* ---- resident-batch interface (what q3asr_transcribe_ids is made of; lets a caller time the stages
- * with inputs already in HBM) ---- */
+ * with inputs already in HBM).  upload = the audio hand-over of transcribe (Qwen3ASR.swift:131-141), run = featureExtractor.process ->
+ * audioEncoder -> generateText (:141-164, 181-390) by stage, download = the generated ids (:283-293).  The timing / profiling / L2
+ * helpers below have no reference equivalent: they exist for bench.py. ---- */
 int q3asr_batch_upload(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch,
                        const q3asr_prompt* prompts);
 /* stages: bit 0 mel, bit 1 encoder, bit 2 prefill (+ first token), bit 3 greedy decode */
@@ -225,7 +235,9 @@ int q3asr_profile_report(q3asr_handle* h, char* buf, size_t cap);
 int q3asr_flush_l2(q3asr_handle* h);
 
 /* ---- utterance-batching scheduler over several GPUs of one box (one worker thread + handle per GPU,
- * weights replicated, utterances dealt longest-first; no collective on the data path) ---- */
+ * weights replicated, utterances dealt longest-first; no collective on the data path).  Replaces the serial file loop of
+ * `speech transcribe-batch` (Sources/AudioCLILib/TranscribeBatchCommand.swift:82-125); every utterance is independent because
+ * transcribe builds a fresh cache per call (Qwen3ASR.swift:246-251). ---- */
 int q3asr_pool_create(const q3asr_config* cfg, const int* devices, int n_devices, uint64_t random_seed, const char* weights_dir,
                       q3asr_pool** out);
 void q3asr_pool_destroy(q3asr_pool* p);
