@@ -166,3 +166,91 @@ extension Qwen3ASRB200Model: ModelMemoryManageable {
     public func unload() { _ = q3asr_unload(handle) }
     public var memoryFootprint: Int { Int(q3asr_memory_footprint(handle)) }
 }
+
+// Because Qwen3ASRB200Model is a SpeechRecognitionModel, the reference's own C bridge takes it unchanged: VoicePipeline's
+// STTBridge(model:) -> makeSTTVtable (Sources/SpeechCore/VoicePipeline.swift:374-411) wraps any SpeechRecognitionModel into a
+// sc_stt_vtable_t, and keeps the "pointers valid until the next transcribe call" ownership on the bridge object.
+
+/// Qwen3ForcedAligner (Sources/Qwen3ASR/ForcedAligner.swift:50-331) over q3asr_align_indices.  The text side stays the reference's
+/// own Swift: TextPreprocessor.prepareForAlignment (NLTokenizer for Japanese / Korean / Thai ..., TextPreprocessing.swift:48-160)
+/// produces the slotted ids and the <timestamp> positions; the library runs mel -> encoder -> one prefill over the aligner template ->
+/// classification head -> first-maximum class at those positions; TimestampCorrection finishes on the host (either the Swift
+/// original or q3asr_enforce_monotonicity, which restates it line by line).
+public final class Qwen3ForcedAlignerB200 {
+    private var handle: OpaquePointer?
+    private let tokenizer: Qwen3Tokenizer
+    public static let timestampSegmentTime: Float = 0.08   // Configuration.swift:133
+
+    private init(handle: OpaquePointer?, tokenizer: Qwen3Tokenizer) {
+        self.handle = handle
+        self.tokenizer = tokenizer
+    }
+
+    deinit { if let h = handle { q3asr_destroy(h) } }
+
+    /// `dir`: the snapshot directory the reference's downloader filled (ForcedAligner.swift:394-452): *.safetensors with the
+    /// thinker.* / lm_head.* keys (MLX 4-bit or bf16), vocab.json, merges.txt, tokenizer_config.json.
+    public static func fromPretrained(directory dir: URL, device: Int32 = 0) throws -> Qwen3ForcedAlignerB200 {
+        var cfg = q3asr_config()
+        guard q3asr_config_preset("aligner", &cfg) == Q3ASR_OK else {
+            throw Q3ASRB200Error.library(code: 1, message: "unknown preset")
+        }
+        var h: OpaquePointer?
+        var rc = q3asr_create(&cfg, device, &h)
+        guard rc == Q3ASR_OK else { throw Q3ASRB200Error.library(code: rc, message: String(cString: q3asr_last_error(nil))) }
+        rc = q3asr_load_safetensors(h, dir.path)
+        guard rc == Q3ASR_OK else {
+            let msg = String(cString: q3asr_last_error(h))
+            q3asr_destroy(h)
+            throw Q3ASRB200Error.library(code: rc, message: msg)
+        }
+        let tok = Qwen3Tokenizer()
+        try tok.load(from: dir.appendingPathComponent("vocab.json"))
+        return Qwen3ForcedAlignerB200(handle: h, tokenizer: tok)
+    }
+
+    /// ForcedAligner.swift:226-331, same signature and the same empty result when the text has no words.
+    public func align(audio: [Float], text: String, sampleRate: Int = 16000, language: String = "English") -> [AlignedWord] {
+        let slotted = TextPreprocessor.prepareForAlignment(text: text, tokenizer: tokenizer, language: language)
+        guard !slotted.words.isEmpty else { return [] }
+        let ids = slotted.tokenIds.map { Int32($0) }
+        let pos = slotted.timestampPositions.map { Int32($0) }
+        var raw = [Int32](repeating: 0, count: pos.count)
+        let rc: Int32 = audio.withUnsafeBufferPointer { a in
+            ids.withUnsafeBufferPointer { i in
+                pos.withUnsafeBufferPointer { p in
+                    raw.withUnsafeMutableBufferPointer { r in
+                        var pcm: UnsafePointer<Float>? = a.baseAddress
+                        var n = audio.count
+                        var rate = Int32(sampleRate)
+                        var idp: UnsafePointer<Int32>? = i.baseAddress
+                        var nid = Int32(ids.count)
+                        var pp: UnsafePointer<Int32>? = p.baseAddress
+                        var np = Int32(pos.count)
+                        var out: UnsafeMutablePointer<Int32>? = r.baseAddress
+                        return q3asr_align_indices(handle, &pcm, &n, &rate, 1, &idp, &nid, &pp, &np, &out)
+                    }
+                }
+            }
+        }
+        guard rc == Q3ASR_OK else {
+            print("Error: \(String(cString: q3asr_last_error(handle)))")   // the reference prints and returns [] (:232-235)
+            return []
+        }
+        let corrected = TimestampCorrection.enforceMonotonicity(raw.map { Int($0) })
+        var words: [AlignedWord] = []
+        for (w, word) in slotted.words.enumerated() where 2 * w + 1 < corrected.count {
+            let start = Float(corrected[2 * w]) * Self.timestampSegmentTime
+            let end = Float(corrected[2 * w + 1]) * Self.timestampSegmentTime
+            words.append(AlignedWord(text: word, startTime: start, endTime: max(end, start)))
+        }
+        return words
+    }
+    // alignLong (ForcedAligner.swift:100-181) is host logic over align(): the reference's body applies unchanged.
+}
+
+extension Qwen3ForcedAlignerB200: ForcedAlignmentModel {   // AudioCommon/Protocols.swift:170-173
+    public func align(audio: [Float], text: String, sampleRate: Int, language: String?) -> [AlignedWord] {
+        align(audio: audio, text: text, sampleRate: sampleRate, language: language ?? "English")
+    }
+}
