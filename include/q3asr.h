@@ -288,6 +288,15 @@ int q3asr_tokenizer_encode(const q3asr_tokenizer* t, const char* text, int32_t* 
 /* id of a token string, or -1 (Tokenizer.swift:281-283) */
 int q3asr_tokenizer_token_id(const q3asr_tokenizer* t, const char* token);
 
+/* Host-only: TextPreprocessor.prepareForAlignment (TextPreprocessing.swift:48-87) — q3asr_text_word_pairs, then per word
+ * <timestamp> tokens(cleaned) <timestamp>; a word the tokenizer cannot encode hands its surface form to the previous word.
+ * ids[0..*n_ids) is the slotted text q3asr_align_indices takes, positions[0..*n_positions) the indices of the <timestamp> slots in it
+ * (two per word), words receives *n_positions / 2 NUL-terminated surface forms (*words_needed bytes).  All three buffers NULL =
+ * sizing call.  timestamp_id: q3asr_config.tok_timestamp.  Errors: q3asr_text_last_error(). */
+int q3asr_text_prepare_for_alignment(const q3asr_tokenizer* tok, const char* text, const char* language, int32_t timestamp_id, int32_t* ids,
+                                     int ids_cap, int* n_ids, int* positions, int pos_cap, int* n_positions, char* words, size_t words_cap,
+                                     size_t* words_needed);
+
 /* ---- front door of the batched path: WAV, sample-rate conversion, long-form windows ---- */
 /* message of the last failed q3asr_wav_* / q3asr_resample_design / q3asr_longform_plan call on this thread */
 const char* q3asr_io_last_error(void);

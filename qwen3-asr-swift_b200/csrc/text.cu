@@ -10,6 +10,7 @@
 // the cleaned form (Swift strings cannot hold one, so the reference has no behaviour to match there).
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -199,6 +200,59 @@ int q3asr_text_word_pairs(const char* text, const char* language, char* buf, siz
             return Q3ASR_ERR_NOMEM;
         }
         if (!flat.empty()) memcpy(buf, flat.data(), flat.size());
+        return Q3ASR_OK;
+    } catch (const q3::Error& e) {
+        g_text_error = e.what();
+        return e.code > 0 ? e.code : Q3ASR_ERR_INVALID;
+    } catch (const std::exception& e) {
+        g_text_error = e.what();
+        return Q3ASR_ERR_NOMEM;
+    }
+}
+
+int q3asr_text_prepare_for_alignment(const q3asr_tokenizer* tok, const char* text, const char* language, int32_t timestamp_id, int32_t* ids,
+                                     int ids_cap, int* n_ids, int* positions, int pos_cap, int* n_positions, char* words, size_t words_cap,
+                                     size_t* words_needed) {
+    if (tok == nullptr || text == nullptr || n_ids == nullptr || n_positions == nullptr || words_needed == nullptr || ids_cap < 0 ||
+        pos_cap < 0) {
+        g_text_error = "text_prepare_for_alignment: null argument";
+        return Q3ASR_ERR_INVALID;
+    }
+    try {  // TextPreprocessing.swift:48-87
+        const std::vector<q3::WordPair> pairs = q3::split_into_word_pairs(text, language ? language : "English");
+        std::vector<int32_t> out_ids, word_ids;
+        std::vector<int> out_pos;
+        std::vector<std::string> out_words;
+        for (const q3::WordPair& p : pairs) {
+            int n = 0;
+            int rc = q3asr_tokenizer_encode(tok, p.cleaned.c_str(), nullptr, 0, &n);
+            word_ids.assign((size_t)(n > 0 ? n : 0), 0);
+            if (rc == Q3ASR_OK && n > 0) rc = q3asr_tokenizer_encode(tok, p.cleaned.c_str(), word_ids.data(), n, &n);
+            if (rc != Q3ASR_OK) throw q3::Error(rc, "text_prepare_for_alignment: tokenizer failed on a word");
+            if (n <= 0) {  // unencodable: its surface joins the previous word (:63-70)
+                if (!out_words.empty()) out_words.back() += p.surface;
+                continue;
+            }
+            out_pos.push_back((int)out_ids.size());
+            out_ids.push_back(timestamp_id);
+            out_ids.insert(out_ids.end(), word_ids.begin(), word_ids.begin() + n);
+            out_pos.push_back((int)out_ids.size());
+            out_ids.push_back(timestamp_id);
+            out_words.push_back(p.surface);
+        }
+        std::string flat;
+        for (const std::string& w : out_words) flat.append(w).push_back('\0');
+        *n_ids = (int)out_ids.size();
+        *n_positions = (int)out_pos.size();
+        *words_needed = flat.size();
+        if (ids == nullptr && positions == nullptr && words == nullptr) return Q3ASR_OK;  // sizing call
+        if (ids == nullptr || positions == nullptr || words == nullptr || ids_cap < *n_ids || pos_cap < *n_positions || words_cap < flat.size()) {
+            g_text_error = "text_prepare_for_alignment: buffer missing or too small";
+            return Q3ASR_ERR_NOMEM;
+        }
+        std::copy(out_ids.begin(), out_ids.end(), ids);
+        std::copy(out_pos.begin(), out_pos.end(), positions);
+        if (!flat.empty()) memcpy(words, flat.data(), flat.size());
         return Q3ASR_OK;
     } catch (const q3::Error& e) {
         g_text_error = e.what();

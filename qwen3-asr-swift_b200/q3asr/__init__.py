@@ -77,7 +77,7 @@ EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
     "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
     "q3asr_load_safetensors", "q3asr_checkpoint_list", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
-    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
+    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_text_prepare_for_alignment", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
@@ -130,6 +130,8 @@ def lib():
         L.q3asr_encoder_tokens.argtypes = [ci]
         L.q3asr_text_word_pairs.argtypes = [ctypes.c_char_p, ctypes.c_char_p, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
         L.q3asr_text_last_error.restype = ctypes.c_char_p
+        L.q3asr_text_prepare_for_alignment.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, vp, ci, ctypes.POINTER(ci), vp, ci,
+                                                       ctypes.POINTER(ci), vp, cs, ctypes.POINTER(cs)]
         L.q3asr_prompt_ids.argtypes = [vp, ci, vp, vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.q3asr_encode.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
         L.q3asr_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp]
@@ -357,6 +359,29 @@ def text_word_pairs(text, language="English"):
     parts = buf.raw[:need.value].split(b"\0")[:2 * n.value]
     dec = (lambda b: b.decode("utf-8")) if isinstance(text, str) else (lambda b: b)
     return [(dec(parts[2 * i]), dec(parts[2 * i + 1])) for i in range(n.value)]
+
+
+def text_prepare_for_alignment(tokenizer, text, language="English", timestamp_token_id=151705):
+    """TextPreprocessor.prepareForAlignment through the library: (token_ids, timestamp_positions, words), the tuple q3asr.text's
+    pure-Python twin returns.  `tokenizer` is a Qwen3Tokenizer (the native one)."""
+    n_ids, n_pos, need = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+    raw = text.encode("utf-8")
+    lang = language.encode("utf-8") if language is not None else None
+
+    def call(ids, pos, words):
+        rc = lib().q3asr_text_prepare_for_alignment(tokenizer._t, raw, lang, int(timestamp_token_id), ids.ctypes.data if ids is not None else None,
+                                                    ids.size if ids is not None else 0, ctypes.byref(n_ids),
+                                                    pos.ctypes.data if pos is not None else None, pos.size if pos is not None else 0,
+                                                    ctypes.byref(n_pos), words, len(words) if words is not None else 0, ctypes.byref(need))
+        if rc != OK:
+            raise Q3Error(rc, lib().q3asr_text_last_error().decode("utf-8", "replace"))
+
+    call(None, None, None)
+    ids, pos = np.zeros(max(n_ids.value, 1), dtype=np.int32), np.zeros(max(n_pos.value, 1), dtype=np.int32)
+    words = ctypes.create_string_buffer(max(need.value, 1))
+    call(ids, pos, words)
+    surf = [w.decode("utf-8") for w in words.raw[:need.value].split(b"\0")[:n_pos.value // 2]]
+    return [int(v) for v in ids[:n_ids.value]], [int(v) for v in pos[:n_pos.value]], surf
 
 
 def checkpoint_list(model_dir):

@@ -165,3 +165,29 @@ def test_c_splitter_invalid_utf8_is_carried_on_the_surface_only(q3):
     # a truncated sequence at the very end of the text must not be read past
     assert q3.text_word_pairs(b"ok \xe4\xbd", "English") == [(b"ok\xe4\xbd", b"ok")]
     assert q3.text_word_pairs(b"\xf0\x9f", "English") == []
+
+
+def test_c_prepare_for_alignment_matches_python(q3):
+    """q3asr_text_prepare_for_alignment (native splitter + native tokenizer) against q3asr.text.prepare_for_alignment driving the same
+    tokenizer: slotted ids, <timestamp> positions and surface words."""
+    import random
+    # a character-level vocabulary without digits: "42" is unencodable and must ride on the previous word (TextPreprocessing.swift:63-70)
+    # (Han and accented letters are missing too: "你" is a word of its own that cannot be encoded)
+    vocab = {i + 10: c for i, c in enumerate("abcdefghijklmnopqrstuvwxyzHW'")}
+    tok = q3.Qwen3Tokenizer(id_to_token=vocab)
+    try:
+        ids, pos, words = q3.text_prepare_for_alignment(tok, "Hi, 42 you!", "English", timestamp_token_id=7)
+        assert words == ["Hi,42", "you!"] and pos == [0, 3, 4, 8] and ids.count(7) == 4 and all(ids[p] == 7 for p in pos)
+        assert q3.text_prepare_for_alignment(tok, "  ...  ", "English", 7) == ([], [], [])
+        assert q3.text_prepare_for_alignment(tok, "12 34", "English", 7) == ([], [], [])          # nothing encodable, no previous word
+        rnd = random.Random(3)
+        alphabet = list("abcxyzHW'") + list(" ,.!?-—\t\n") + list("0123") + ["你", "好", "。", "，", "ä", "😀"]
+        for _ in range(300):
+            text = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 30)))
+            want = tp.prepare_for_alignment(text, tok, "English", timestamp_token_id=7)
+            got = q3.text_prepare_for_alignment(tok, text, "English", timestamp_token_id=7)
+            assert got == (want.token_ids, want.timestamp_positions, want.words), repr(text)
+        with pytest.raises(q3.Q3Error):
+            q3.text_prepare_for_alignment(tok, "x", "Japanese", 7)
+    finally:
+        tok.close()
