@@ -109,3 +109,14 @@ def test_model_size_and_bits_detection(built_lib):
     assert q3asr.detect_bits("aufklarer/Qwen3-ASR-1.7B-MLX-4bit") == 4
     assert q3asr.detect_bits("some-custom/small-model") == 4
     assert q3asr.detect_bits("some/1.7B-model") == 8
+
+
+def test_missing_library_fails_loudly(built_lib, tmp_path):
+    """No CPU fallback anywhere above the C ABI either: without libq3asr.so the mirror raises on first use, naming the build command."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import q3asr; q3asr.LIB_PATH = %r\n"
+            "try:\n    q3asr.mel_frames(16000)\nexcept q3asr.Q3Error as e:\n    print('RAISED', e)\n"
+            % (os.path.dirname(os.path.dirname(built_lib.__file__)), str(tmp_path / "libq3asr.so")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "RAISED" in r.stdout and "no CPU fallback" in r.stdout and "g.build()" in r.stdout, r.stdout + r.stderr
