@@ -43,6 +43,30 @@ int main(int argc, char** argv) {
             } catch (const AudioModelError&) {
             }
             printf("tokenizer ok\n");
+            // preset detection from a checkpoint's own tensor index: header-only safetensors files written here
+            auto write_ck = [&](const std::string& sub, const std::string& header, size_t payload) {
+                const std::string d = dir + "/" + sub;
+                if (system(("mkdir -p '" + d + "'").c_str()) != 0) return false;
+                FILE* g = fopen((d + "/model.safetensors").c_str(), "wb");
+                if (!g) return false;
+                const uint64_t hl = header.size();
+                fwrite(&hl, 8, 1, g);
+                fwrite(header.data(), 1, header.size(), g);
+                const std::string zeros(payload, '\0');
+                fwrite(zeros.data(), 1, zeros.size(), g);
+                fclose(g);
+                return true;
+            };
+            if (!write_ck("small", "{\"model.norm.weight\":{\"dtype\":\"BF16\",\"shape\":[1024],\"data_offsets\":[0,2048]}}", 2048)) return 10;
+            if (!write_ck("large", "{\"model.norm.weight\":{\"dtype\":\"BF16\",\"shape\":[2048],\"data_offsets\":[0,4096]}}", 4096)) return 10;
+            if (!write_ck("align", "{\"thinker.lm_head.weight\":{\"dtype\":\"BF16\",\"shape\":[2,4],\"data_offsets\":[0,16]},"
+                                   "\"thinker.model.norm.weight\":{\"dtype\":\"BF16\",\"shape\":[1024],\"data_offsets\":[16,2064]}}", 2064)) return 10;
+            if (!write_ck("odd", "{\"model.norm.weight\":{\"dtype\":\"BF16\",\"shape\":[128],\"data_offsets\":[0,256]}}", 256)) return 10;
+            if (detectPresetFromCheckpoint(dir + "/small") != "0.6B" || detectPresetFromCheckpoint(dir + "/large") != "1.7B" ||
+                detectPresetFromCheckpoint(dir + "/align") != "aligner" || detectPresetFromCheckpoint(dir + "/odd") != "" ||
+                detectPresetFromCheckpoint(dir + "/nope") != "")
+                return 11;
+            printf("checkpoint detection ok\n");
         }
         printf("%s\n", q3asr_version());
         return 0;

@@ -57,6 +57,21 @@ inline int detectModelBits(const std::string& modelId) {
     return detectModelSize(modelId) == ASRModelSize::large ? 8 : 4;
 }
 
+// The preset a checkpoint directory holds, from its validated tensor index (q3asr_checkpoint_list, host only): "aligner" when it
+// carries lm_head.*, else "0.6B" / "1.7B" by the width of model.norm.weight; "" when the index does not say.
+inline std::string detectPresetFromCheckpoint(const std::string& dir) {
+    size_t need = 0;
+    if (q3asr_checkpoint_list(dir.c_str(), nullptr, 0, &need) != Q3ASR_OK || need == 0) return "";
+    std::string list(need, '\0');
+    if (q3asr_checkpoint_list(dir.c_str(), &list[0], list.size(), &need) != Q3ASR_OK) return "";
+    if (list.find("\nlm_head.weight\t") != std::string::npos || list.compare(0, 15, "lm_head.weight\t") == 0) return "aligner";
+    const size_t at = list.find("model.norm.weight\t");
+    if (at == std::string::npos || (at != 0 && list[at - 1] != '\n')) return "";
+    const size_t shape = list.find('\t', list.find('\t', at) + 1) + 1;  // name \t dtype \t shape \t bytes
+    const std::string dims = list.substr(shape, list.find('\t', shape) - shape);
+    return dims == "1024" ? "0.6B" : dims == "2048" ? "1.7B" : "";
+}
+
 struct MelFeatures {  // row-major [melBins, timeFrames]
     std::vector<float> data;
     int melBins = 128;
@@ -162,11 +177,16 @@ class Qwen3ASRModel {
     static constexpr int inputSampleRate = 16000;
 
     // modelDir: a directory holding the checkpoint's *.safetensors (the reference resolves it from the HF cache);
-    // modelId decides the size like ASRModelSize.detect.  Throws AudioModelError on load failure.
+    // modelId decides the size like ASRModelSize.detect unless the checkpoint's own tensor index says otherwise.  Throws
+    // AudioModelError on load failure.
     static std::unique_ptr<Qwen3ASRModel> fromPretrained(const std::string& modelId, const std::string& modelDir, int device = 0,
                                                          std::function<void(double, const std::string&)> progressHandler = nullptr) {
         if (progressHandler) progressHandler(0.0, "Loading model...");
-        std::unique_ptr<Qwen3ASRModel> m(new Qwen3ASRModel(detectModelSize(modelId), device));
+        ASRModelSize size = detectModelSize(modelId);
+        const std::string held = detectPresetFromCheckpoint(modelDir);  // what the files say wins over the name
+        if (held == "1.7B") size = ASRModelSize::large;
+        else if (held == "0.6B") size = ASRModelSize::small;
+        std::unique_ptr<Qwen3ASRModel> m(new Qwen3ASRModel(size, device));
         int rc = q3asr_load_safetensors(m->h_, modelDir.c_str());
         if (rc != Q3ASR_OK) throw AudioModelError(rc, std::string("weightLoadingFailed: ") + q3asr_last_error(m->h_));
         try {  // Qwen3ASR.swift:643-649: the tokenizer is optional (ids are returned as text without it, :288-289)

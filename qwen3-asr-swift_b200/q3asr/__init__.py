@@ -401,6 +401,16 @@ def checkpoint_list(model_dir):
     return out
 
 
+def detect_preset_from_checkpoint(model_dir):
+    """The preset a checkpoint directory holds, read from its tensor index (host only): "aligner" when it carries the classification
+    head (lm_head.*, WeightLoading.swift:177-179), else "0.6B" / "1.7B" by the decoder width (model.norm.weight: 1024 / 2048,
+    Configuration.swift:47-100).  None when the index does not say (the caller falls back to the model id, like the reference)."""
+    shapes = {name: shape for name, _, shape, _ in checkpoint_list(model_dir)}
+    if "lm_head.weight" in shapes:
+        return "aligner"
+    return {(1024,): "0.6B", (2048,): "1.7B"}.get(shapes.get("model.norm.weight"))
+
+
 def detect_model_size(model_id):
     """ASRModelSize.detect (Qwen3ASR.swift:581-586): the preset name for a model id."""
     return "1.7B" if ("1.7B" in model_id or "1.7b" in model_id) else "0.6B"
@@ -457,9 +467,10 @@ class Qwen3ASRModel:
     # -- lifecycle ---------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, model_dir, size=None, device=0):
-        """size None: decided from the directory name like ASRModelSize.detect does from the model id (Qwen3ASR.swift:615)."""
-        if size is None:
-            size = detect_model_size(os.path.basename(os.path.normpath(os.fspath(model_dir))))
+        """size None: decided from the checkpoint's own tensor index, else from the directory name like ASRModelSize.detect does from
+        the model id (Qwen3ASR.swift:615)."""
+        if size is None:  # what the files say first, then the directory name
+            size = detect_preset_from_checkpoint(model_dir) or detect_model_size(os.path.basename(os.path.normpath(os.fspath(model_dir))))
         m = cls(size=size, device=device)
         m._ck(lib().q3asr_load_safetensors(m._h, os.fspath(model_dir).encode()))
         if os.path.exists(os.path.join(model_dir, "vocab.json")):  # Qwen3ASR.swift:643-649

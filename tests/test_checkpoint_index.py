@@ -150,3 +150,18 @@ def test_sizing_protocol(built_lib, tmp_path):
     assert L.q3asr_checkpoint_list(d, small, 4, ctypes.byref(need)) == 4          # Q3ASR_ERR_NOMEM, nothing written past the buffer
     assert L.q3asr_checkpoint_list(d, None, 0, None) == 1
     assert L.q3asr_checkpoint_list(None, small, 4, ctypes.byref(need)) == 5 and small.value == b"loa"   # message, truncated to fit
+
+
+def test_preset_detection_from_the_index(built_lib, tmp_path):
+    """detect_preset_from_checkpoint: the decoder width / the classification head decide, not the directory name."""
+    for sub, hdr, want in [
+        ("a", {"model.norm.weight": _entry("BF16", [1024], 0, 2048)}, "0.6B"),
+        ("Qwen3-ASR-0.6B-named-but-large", {"model.norm.weight": _entry("BF16", [2048], 0, 4096)}, "1.7B"),
+        ("c", {"thinker.model.norm.weight": _entry("BF16", [1024], 0, 2048), "thinker.lm_head.weight": _entry("BF16", [2, 4], 2048, 2064)}, "aligner"),
+        ("d", {"model.norm.weight": _entry("BF16", [128], 0, 256)}, None),
+        ("e", {"audio_tower.ln_post.weight": _entry("F32", [4], 0, 16)}, None),
+    ]:
+        d = tmp_path / sub
+        d.mkdir()
+        _write(d / "model.safetensors", hdr, bytes(max(e["data_offsets"][1] for e in hdr.values())))
+        assert built_lib.detect_preset_from_checkpoint(d) == want, sub
