@@ -195,7 +195,15 @@ struct JsonParser {
         i++;
         return true;
     }
+    int depth = 0;
+    struct Nest {  // a file of a million '[' must not turn into a million stack frames
+        int& d;
+        explicit Nest(int& x) : d(x) { d++; }
+        ~Nest() { d--; }
+    };
     bool value(Json* v) {
+        Nest nest(depth);
+        if (depth > 64) return fail("nesting too deep");
         ws();
         if (i >= s.size()) return fail("unexpected end");
         const char c = s[i];

@@ -150,3 +150,22 @@ def test_load_from_directory(tmp_path, built_lib):
     with pytest.raises(built_lib.Q3Error) as e:
         built_lib.Qwen3Tokenizer(path=str(tmp_path / "bad"))
     assert "Invalid tokenizer format" in str(e.value)
+
+
+def test_hostile_tokenizer_files_are_refused_not_crashed_on(tmp_path, built_lib):
+    """A vocab.json of a million '[' must not become a million stack frames; truncated escapes and lone surrogates must not read past the end."""
+    for name, body in [("deep", '{"a":' + "[" * 1_000_000), ("deep_obj", '{"a":' * 200_000), ("esc", '{"a\\'), ("uni", '{"\\u12'),
+                       ("sur", '{"\\ud83d\\u": 1}'), ("num", '{"a": 1e99999, "b": -}'), ("empty", "")]:
+        d = tmp_path / name
+        d.mkdir()
+        (d / "vocab.json").write_text(body)
+        with pytest.raises(built_lib.Q3Error) as e:
+            built_lib.Qwen3Tokenizer(path=str(d))
+        assert "Invalid tokenizer format" in str(e.value) or "vocab" in str(e.value), (name, str(e.value))
+    # a lone high surrogate followed by a normal escape is tolerated (garbage in the token, nothing else)
+    d = tmp_path / "lone"
+    d.mkdir()
+    (d / "vocab.json").write_text('{"\\ud83dx": 1, "ok": 2}')
+    t = built_lib.Qwen3Tokenizer(path=str(d))
+    assert t.token_id("ok") == 2
+    t.close()
