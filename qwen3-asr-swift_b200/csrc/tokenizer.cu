@@ -386,7 +386,11 @@ struct q3asr_tokenizer {
             Json root;
             if (!jp.value(&root) || root.kind != Json::Obj) { last_error = "Invalid tokenizer format: Expected {token: id} dictionary (" + jp.err + ")"; return false; }
             for (auto& kv : root.obj) {
-                if (kv.second.kind != Json::Num) { last_error = "Invalid tokenizer format: Expected {token: id} dictionary"; return false; }
+                // ids are Ints in the reference; a value outside the int range (or NaN) cannot be one, and casting it would be undefined
+                if (kv.second.kind != Json::Num || !(kv.second.num >= -2147483648.0 && kv.second.num <= 2147483647.0)) {
+                    last_error = "Invalid tokenizer format: Expected {token: id} dictionary";
+                    return false;
+                }
                 add((int)kv.second.num, kv.first);
             }
         }
@@ -399,7 +403,7 @@ struct q3asr_tokenizer {
                         char* end = nullptr;
                         const long id = strtol(kv.first.c_str(), &end, 10);
                         const Json* content = kv.second.get("content");
-                        if (end == kv.first.c_str() || *end || !content || content->kind != Json::Str) continue;
+                        if (end == kv.first.c_str() || *end || id < INT_MIN || id > INT_MAX || !content || content->kind != Json::Str) continue;
                         add((int)id, content->str);
                     }
         }

@@ -155,7 +155,7 @@ def test_load_from_directory(tmp_path, built_lib):
 def test_hostile_tokenizer_files_are_refused_not_crashed_on(tmp_path, built_lib):
     """A vocab.json of a million '[' must not become a million stack frames; truncated escapes and lone surrogates must not read past the end."""
     for name, body in [("deep", '{"a":' + "[" * 1_000_000), ("deep_obj", '{"a":' * 200_000), ("esc", '{"a\\'), ("uni", '{"\\u12'),
-                       ("sur", '{"\\ud83d\\u": 1}'), ("num", '{"a": 1e99999, "b": -}'), ("empty", "")]:
+                       ("sur", '{"\\ud83d\\u": 1}'), ("num", '{"a": 1e99999, "b": -}'), ("inf", '{"a": 1e999}'), ("big", '{"a": 4294967296}'), ("empty", "")]:
         d = tmp_path / name
         d.mkdir()
         (d / "vocab.json").write_text(body)
