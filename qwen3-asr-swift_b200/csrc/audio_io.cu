@@ -216,6 +216,7 @@ void resample_host(Handle* h, const float* in, size_t n, int in_rate, int out_ra
 // ------------------------------------------------------------------------------------------
 int longform_plan(size_t n, size_t window, size_t min_tail, size_t* starts, size_t* lens, int cap) {
     Q3_CHECK(window > 0, Q3ASR_ERR_INVALID, "longform_plan: window must be positive");
+    Q3_CHECK(n / window < ((size_t)1 << 24), Q3ASR_ERR_INVALID, "longform_plan: more than 2^24 windows");  // the count is an int; no endless loop
     int count = 0;
     size_t pos = 0;
     while (pos < n) {

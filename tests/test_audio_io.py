@@ -139,6 +139,10 @@ def test_longform_plan():
         assert sum(ln for _, ln in wins) == n and all(s == sum(l for _, l in wins[:i]) for i, (s, _) in enumerate(wins))
     # BASELINE config 5: 60 minutes -> 120 windows of 30 s
     assert len(q3asr.longform_plan(3600 * 16000, 480000)) == 120
+    # absurd arguments are refused instead of looping for 2^60 windows
+    for n, w in [(1 << 60, 1), (1 << 40, 16), (100, 0)]:
+        with pytest.raises(q3asr.Q3Error):
+            q3asr.longform_plan(n, w)
 
 
 # ---- GPU ----
