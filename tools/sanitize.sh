@@ -1,12 +1,12 @@
 #!/bin/bash
 # Builds AddressSanitizer and UndefinedBehaviorSanitizer variants of libq3asr.so (host code instrumented; device code unchanged) into
-# /tmp/q3asr_san/{asan,ubsan}/ and runs the host-only tests and tools/fuzz_host.py against each.  No GPU needed.
+# $Q3ASR_SAN_DIR/{address,undefined}/ (default: a scratch directory under /tmp) and runs the host-only tests and tools/fuzz_host.py against each.  No GPU needed.
 # Usage: tools/sanitize.sh [iterations]
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 PKG=$ROOT/qwen3-asr-swift_b200
 IT=${1:-800}
-OUT=/tmp/q3asr_san
+OUT=${Q3ASR_SAN_DIR:-/tmp/q3asr_san}
 TESTS="tests/test_tokenizer.py tests/test_audio_io.py tests/test_aligner.py tests/test_checkpoint_index.py tests/test_prompt.py tests/test_text_preprocessing.py tests/test_abi.py tests/test_sampler.py"
 mkdir -p $OUT/site
 cat > $OUT/site/sitecustomize.py <<PY
