@@ -305,6 +305,9 @@ const char* q3asr_io_last_error(void);
  * "Unsupported audio format: Not PCM format" / "Not 16-bit").  samples may be NULL to query *n_samples (frames). */
 int q3asr_wav_parse(const uint8_t* data, size_t size, float* samples, size_t cap, size_t* n_samples, int* sample_rate);
 int q3asr_wav_load(const char* path, float* samples, size_t cap, size_t* n_samples, int* sample_rate);
+/* WAVWriter.write(samples:sampleRate:to:) (Sources/AudioCommon/WAVWriter.swift:11-47), the writer on the other side of this format:
+ * mono 16-bit PCM, 44-byte header, samples clamped to [-1, 1] and truncated toward zero after * 32767.  Host only. */
+int q3asr_wav_write(const char* path, const float* samples, size_t n_samples, int sample_rate);
 /* AudioFileLoader.resample (AudioFileLoader.swift:159-213).  Output length floor(n * out / in) as the reference computes it
  * (:190-191); the filter is a polyphase Kaiser-windowed sinc (csrc/audio_io.cu states the design; AVAudioConverter's own filter is
  * not part of the reference), evaluated on the GPU.  out may be NULL to query *n_out. */

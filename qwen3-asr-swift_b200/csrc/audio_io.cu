@@ -279,6 +279,37 @@ int q3asr_wav_load(const char* path, float* samples, size_t cap, size_t* n_sampl
     });
 }
 
+int q3asr_wav_write(const char* path, const float* samples, size_t n_samples, int sample_rate) {
+    return io_guarded([&]() {  // WAVWriter.write (Sources/AudioCommon/WAVWriter.swift:11-47): mono, 16-bit PCM, 44-byte header
+        Q3_CHECK(path != nullptr && (samples != nullptr || n_samples == 0), Q3ASR_ERR_INVALID, "wav_write: null argument");
+        Q3_CHECK(sample_rate > 0 && n_samples <= 0x7FFFFFEDull / 2, Q3ASR_ERR_INVALID, "wav_write: bad sample rate or too many samples for a RIFF file");
+        const uint32_t data_size = (uint32_t)(n_samples * 2);
+        std::vector<uint8_t> buf(44 + (size_t)data_size);
+        auto put16 = [&](size_t at, uint32_t v) { buf[at] = (uint8_t)v; buf[at + 1] = (uint8_t)(v >> 8); };
+        auto put32 = [&](size_t at, uint32_t v) { put16(at, v & 0xFFFF); put16(at + 2, v >> 16); };
+        memcpy(&buf[0], "RIFF", 4);
+        put32(4, 36 + data_size);
+        memcpy(&buf[8], "WAVEfmt ", 8);
+        put32(16, 16);
+        put16(20, 1);  // PCM
+        put16(22, 1);  // mono
+        put32(24, (uint32_t)sample_rate);
+        put32(28, (uint32_t)sample_rate * 2);
+        put16(32, 2);
+        put16(34, 16);
+        memcpy(&buf[36], "data", 4);
+        put32(40, data_size);
+        for (size_t i = 0; i < n_samples; i++) {
+            float v = samples[i];
+            v = !(v >= -1.0f) ? -1.0f : (v > 1.0f ? 1.0f : v);  // max(-1, min(1, x)); NaN (Swift would trap on it) is written as -1
+            put16(44 + 2 * i, (uint32_t)(uint16_t)(int16_t)(v * 32767.0f));  // Int16(Float): truncation toward zero (:42)
+        }
+        std::unique_ptr<FILE, int (*)(FILE*)> f(fopen(path, "wb"), fclose);
+        if (!f) throw q3::Error(Q3ASR_ERR_IO, std::string("wav_write: cannot open ") + path);
+        if (fwrite(buf.data(), 1, buf.size(), f.get()) != buf.size()) throw q3::Error(Q3ASR_ERR_IO, std::string("wav_write: short write to ") + path);
+    });
+}
+
 size_t q3asr_resample_len(size_t n_samples, int in_rate, int out_rate) {
     if (in_rate <= 0 || out_rate <= 0) return 0;
     return q3::resample_len(n_samples, in_rate, out_rate);

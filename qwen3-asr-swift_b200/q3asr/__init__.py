@@ -85,7 +85,7 @@ EXPORTS = [
     "q3asr_debug_gemm", "q3asr_debug_conv", "q3asr_debug_attention",
     "q3asr_tokenizer_load", "q3asr_tokenizer_from_pairs", "q3asr_tokenizer_add_merge", "q3asr_tokenizer_destroy",
     "q3asr_tokenizer_last_error", "q3asr_tokenizer_size", "q3asr_tokenizer_decode", "q3asr_tokenizer_encode", "q3asr_tokenizer_token_id",
-    "q3asr_io_last_error", "q3asr_wav_parse", "q3asr_wav_load", "q3asr_resample_len", "q3asr_resample", "q3asr_resample_design",
+    "q3asr_io_last_error", "q3asr_wav_parse", "q3asr_wav_load", "q3asr_wav_write", "q3asr_resample_len", "q3asr_resample", "q3asr_resample_design",
     "q3asr_batch_upload_sr", "q3asr_transcribe_ids_sr", "q3asr_longform_plan",
     "q3asr_transcribe_ids_opts", "q3asr_batch_set_sampling", "q3asr_pick_next_token",
     "q3asr_align_indices", "q3asr_enforce_monotonicity", "q3asr_lis_positions", "q3asr_trailing_plateau_start",
@@ -178,6 +178,7 @@ def lib():
         L.q3asr_tokenizer_token_id.argtypes = [vp, ctypes.c_char_p]
         L.q3asr_io_last_error.restype = ctypes.c_char_p
         L.q3asr_wav_parse.argtypes = [vp, cs, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
+        L.q3asr_wav_write.argtypes = [ctypes.c_char_p, vp, cs, ci]
         L.q3asr_wav_load.argtypes = [ctypes.c_char_p, vp, cs, ctypes.POINTER(cs), ctypes.POINTER(ci)]
         L.q3asr_resample_len.argtypes = [cs, ci, ci]
         L.q3asr_resample_len.restype = cs
@@ -270,6 +271,12 @@ class AudioFileLoader:
     def load_wav(path):
         with open(path, "rb") as f:
             return AudioFileLoader.parse_wav(f.read())
+
+    @staticmethod
+    def write_wav(path, samples, sample_rate=24000):
+        """WAVWriter.write (Sources/AudioCommon/WAVWriter.swift:11-47): mono PCM16."""
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        AudioFileLoader._finish(lib().q3asr_wav_write(os.fsencode(path), x.ctypes.data if x.size else None, x.size, int(sample_rate)))
 
     @staticmethod
     def resample_len(n, in_rate, out_rate):

@@ -179,3 +179,51 @@ def test_gpu_transcribe_long_windows(tiny_model):
     wins = q3asr.longform_plan(x.size, 32000)
     solo = tiny_model.transcribe_ids([x[s:s + n] for s, n in wins], max_tokens=5)
     assert [s["ids"].tolist() for s in segs] == [t.tolist() for t in solo]
+
+
+# ---- WAVWriter (Sources/AudioCommon/WAVWriter.swift:11-47): the reference's WAVWriterTests.swift ported, and the write -> load round trip ----
+def test_wav_write_and_read_back(tmp_path):                                   # testWriteAndReadBack
+    p = tmp_path / "a.wav"
+    q3asr.AudioFileLoader.write_wav(p, [0.0, 0.5, -0.5, 1.0, -1.0], 16000)
+    data = p.read_bytes()
+    assert len(data) > 44 and data[:4] == b"RIFF" and data[8:12] == b"WAVE"
+    x, rate = q3asr.AudioFileLoader.load_wav(p)
+    assert rate == 16000 and x.tolist() == [0.0, 16383 / 32768, -16383 / 32768, 32767 / 32768, -32767 / 32768]   # Int16(x * 32767) truncates
+
+
+def test_wav_write_empty_samples(tmp_path):                                   # testWriteEmptySamples
+    p = tmp_path / "empty.wav"
+    q3asr.AudioFileLoader.write_wav(p, [], 16000)
+    assert len(p.read_bytes()) == 44
+
+
+def test_wav_round_trip_preserves_length_and_values(tmp_path):                # testRoundTripPreservesLength (+ values)
+    x = np.sin(np.arange(1000) * 0.1).astype(np.float32)
+    p = tmp_path / "rt.wav"
+    q3asr.AudioFileLoader.write_wav(p, x, 24000)
+    y, rate = q3asr.AudioFileLoader.load_wav(p)
+    assert rate == 24000 and y.size == 1000
+    assert np.array_equal(y, np.trunc(x * np.float32(32767.0)).astype(np.float32) / np.float32(32768.0))
+    assert np.abs(y - x).max() <= 2.0 / 32768
+    # the oracle's parser reads the same file the same way
+    yo, ro = oio.wav_parse(p.read_bytes())
+    assert ro == 24000 and np.array_equal(np.asarray(yo, dtype=np.float32), y)
+
+
+@pytest.mark.parametrize("rate", [8000, 16000, 22050, 24000, 44100, 48000])  # testDifferentSampleRates
+def test_wav_write_sample_rates(tmp_path, rate):
+    p = tmp_path / f"r{rate}.wav"
+    q3asr.AudioFileLoader.write_wav(p, [0.1, 0.2, 0.3], rate)
+    data = p.read_bytes()
+    assert len(data) == 50 and struct.unpack("<I", data[24:28])[0] == rate and struct.unpack("<I", data[28:32])[0] == 2 * rate
+    assert q3asr.AudioFileLoader.load_wav(p)[1] == rate
+
+
+def test_wav_write_clamps_and_refuses_bad_arguments(tmp_path):
+    p = tmp_path / "c.wav"
+    q3asr.AudioFileLoader.write_wav(p, [2.0, -3.0, float("inf"), float("-inf"), 1e-9], 16000)
+    assert q3asr.AudioFileLoader.load_wav(p)[0].tolist() == [32767 / 32768, -32767 / 32768, 32767 / 32768, -32767 / 32768, 0.0]
+    with pytest.raises(q3asr.AudioLoadError):
+        q3asr.AudioFileLoader.write_wav(p, [0.0], 0)
+    with pytest.raises(q3asr.AudioLoadError):
+        q3asr.AudioFileLoader.write_wav(tmp_path / "no" / "such" / "dir.wav", [0.0], 16000)
