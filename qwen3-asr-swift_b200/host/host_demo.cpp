@@ -67,6 +67,15 @@ int main(int argc, char** argv) {
                 detectPresetFromCheckpoint(dir + "/nope") != "")
                 return 11;
             printf("checkpoint detection ok\n");
+            // WAVWriter -> AudioFileLoader round trip on the PCM16 grid (WAVWriterTests.swift:38-52)
+            std::vector<float> tone(1000);
+            for (size_t i = 0; i < tone.size(); i++) tone[i] = std::sin(0.1f * (float)i);
+            WAVWriter::write(tone, 24000, dir + "/tone.wav");
+            const AudioFileLoader::Wav back = AudioFileLoader::loadWAV(dir + "/tone.wav");
+            if (back.sampleRate != 24000 || back.samples.size() != tone.size()) return 12;
+            for (size_t i = 0; i < tone.size(); i++)
+                if (back.samples[i] != (float)(int)(tone[i] * 32767.0f) / 32768.0f) return 13;
+            printf("wav round trip ok\n");
         }
         printf("%s\n", q3asr_version());
         return 0;

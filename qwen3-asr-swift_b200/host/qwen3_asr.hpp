@@ -149,6 +149,13 @@ struct AudioFileLoader {
     static std::vector<float> resample(const Qwen3ASRModel& model, const std::vector<float>& samples, int from, int to);
 };
 
+struct WAVWriter {  // Sources/AudioCommon/WAVWriter.swift:11-47: mono 16-bit PCM; throws AudioLoadError when the file cannot be written
+    static void write(const std::vector<float>& samples, int sampleRate, const std::string& path) {
+        const int rc = q3asr_wav_write(path.c_str(), samples.data(), samples.size(), sampleRate);
+        if (rc != Q3ASR_OK) throw AudioLoadError(rc, q3asr_io_last_error());
+    }
+};
+
 class WhisperFeatureExtractor {
   public:
     static constexpr int sampleRate = 16000, nFFT = 400, hopLength = 160, nMels = 128;  // AudioPreprocessing.swift:24-30

@@ -25,7 +25,7 @@ def host_demo(built_lib):
 def test_host_mirror_compiles_links_and_reports(host_demo, tmp_path):
     r = subprocess.run([host_demo, "symbols", str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "sm_100a" in r.stdout and "tokenizer ok" in r.stdout and "checkpoint detection ok" in r.stdout
+    assert "sm_100a" in r.stdout and "tokenizer ok" in r.stdout and "checkpoint detection ok" in r.stdout and "wav round trip ok" in r.stdout
     # without a GPU the load must fail loudly (no CPU fallback), with one it must succeed
     assert ("load error" in r.stdout) or ("created on GPU" in r.stdout)
 
