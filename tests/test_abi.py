@@ -120,3 +120,24 @@ def test_missing_library_fails_loudly(built_lib, tmp_path):
             % (os.path.dirname(os.path.dirname(built_lib.__file__)), str(tmp_path / "libq3asr.so")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "RAISED" in r.stdout and "no CPU fallback" in r.stdout and "g.build()" in r.stdout, r.stdout + r.stderr
+
+
+def test_header_is_plain_c99_and_links_from_c(built_lib, tmp_path):
+    """The boundary is a C ABI: include/q3asr.h must compile as strict C99 (cgo / Swift's Clang importer / ctypes read it as C, not C++)
+    and a C program must link against the library and call a host-only entry point."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "q3asr.h"\n#include <stdio.h>\n#include <string.h>\n'
+                   "int main(void) {\n"
+                   "    q3asr_config c; int ids[64]; int n = 0, at = 0;\n"
+                   '    if (q3asr_config_preset("0.6B", &c) != Q3ASR_OK) return 1;\n'
+                   "    if (q3asr_prompt_ids(&c, 3, NULL, ids, 64, &n, &at) != Q3ASR_OK || n != 19 || at != 9) return 2;\n"
+                   "    if (q3asr_encoder_tokens(3000) != 390 || q3asr_mel_frames(480000) != 3000) return 3;\n"
+                   '    printf("%s\\n", q3asr_version());\n'
+                   "    return 0;\n}\n")
+    exe = tmp_path / "use"
+    lib_dir = os.path.join(ROOT, "qwen3-asr-swift_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-L", lib_dir,
+                    "-lq3asr", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "sm_100a" in r.stdout, (r.returncode, r.stdout, r.stderr)
