@@ -19,6 +19,7 @@
 #include <climits>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <unordered_map>
@@ -430,27 +431,52 @@ struct q3asr_tokenizer {
     }
 };
 
+namespace {
+// Nothing may leave through the C boundary: host allocation failures come back as Q3ASR_ERR_NOMEM.
+template <typename F>
+int tok_guarded(F&& fn) {
+    try {
+        return fn();
+    } catch (const std::bad_alloc&) {
+        return Q3ASR_ERR_NOMEM;
+    } catch (const std::exception&) {
+        return Q3ASR_ERR_INVALID;
+    }
+}
+}  // namespace
+
 extern "C" {
 
 int q3asr_tokenizer_load(const char* path, q3asr_tokenizer** out) {
     if (path == nullptr || out == nullptr) return Q3ASR_ERR_INVALID;
-    q3asr_tokenizer* t = new q3asr_tokenizer();
-    *out = t;  // returned even on failure so the caller can read the message, then destroy it
-    return t->load_dir(path) ? Q3ASR_OK : Q3ASR_ERR_IO;
+    *out = nullptr;
+    return tok_guarded([&]() {
+        std::unique_ptr<q3asr_tokenizer> t(new q3asr_tokenizer());
+        const bool ok = t->load_dir(path);
+        *out = t.release();  // returned even on failure so the caller can read the message, then destroy it
+        return ok ? Q3ASR_OK : Q3ASR_ERR_IO;
+    });
 }
 
 int q3asr_tokenizer_from_pairs(const int32_t* ids, const char* const* tokens, int n, q3asr_tokenizer** out) {
     if ((n > 0 && (ids == nullptr || tokens == nullptr)) || n < 0 || out == nullptr) return Q3ASR_ERR_INVALID;
-    q3asr_tokenizer* t = new q3asr_tokenizer();
-    for (int i = 0; i < n; i++) t->add(ids[i], tokens[i]);
-    *out = t;
-    return Q3ASR_OK;
+    *out = nullptr;
+    for (int i = 0; i < n; i++)
+        if (tokens[i] == nullptr) return Q3ASR_ERR_INVALID;
+    return tok_guarded([&]() {
+        std::unique_ptr<q3asr_tokenizer> t(new q3asr_tokenizer());
+        for (int i = 0; i < n; i++) t->add(ids[i], tokens[i]);
+        *out = t.release();
+        return Q3ASR_OK;
+    });
 }
 
 int q3asr_tokenizer_add_merge(q3asr_tokenizer* t, const char* first, const char* second) {
     if (t == nullptr || first == nullptr || second == nullptr) return Q3ASR_ERR_INVALID;
-    t->merge_rank[std::string(first) + " " + second] = (int)t->n_merges++;
-    return Q3ASR_OK;
+    return tok_guarded([&]() {
+        t->merge_rank[std::string(first) + " " + second] = (int)t->n_merges++;
+        return Q3ASR_OK;
+    });
 }
 
 void q3asr_tokenizer_destroy(q3asr_tokenizer* t) { delete t; }
@@ -466,27 +492,35 @@ int q3asr_tokenizer_size(const q3asr_tokenizer* t, int* n_tokens, int* n_merges)
 
 int q3asr_tokenizer_decode(const q3asr_tokenizer* t, const int32_t* ids, int n, char* out, size_t cap, size_t* needed) {
     if (t == nullptr || (n > 0 && ids == nullptr) || n < 0) return Q3ASR_ERR_INVALID;
-    const std::string s = t->decode(ids, n);
-    if (needed) *needed = s.size() + 1;
-    if (out == nullptr || cap < s.size() + 1) return out == nullptr && needed ? Q3ASR_OK : Q3ASR_ERR_NOMEM;
-    memcpy(out, s.c_str(), s.size() + 1);
-    return Q3ASR_OK;
+    return tok_guarded([&]() {
+        const std::string s = t->decode(ids, n);
+        if (needed) *needed = s.size() + 1;
+        if (out == nullptr || cap < s.size() + 1) return out == nullptr && needed ? Q3ASR_OK : Q3ASR_ERR_NOMEM;
+        memcpy(out, s.c_str(), s.size() + 1);
+        return Q3ASR_OK;
+    });
 }
 
 int q3asr_tokenizer_encode(const q3asr_tokenizer* t, const char* text, int32_t* ids, int cap, int* n) {
     if (t == nullptr || text == nullptr || n == nullptr) return Q3ASR_ERR_INVALID;
-    const std::vector<int32_t> v = t->encode(text);
-    *n = (int)v.size();
-    if (ids == nullptr) return Q3ASR_OK;
-    if (cap < (int)v.size()) return Q3ASR_ERR_NOMEM;
-    if (!v.empty()) memcpy(ids, v.data(), sizeof(int32_t) * v.size());
-    return Q3ASR_OK;
+    return tok_guarded([&]() {
+        const std::vector<int32_t> v = t->encode(text);
+        *n = (int)v.size();
+        if (ids == nullptr) return Q3ASR_OK;
+        if (cap < (int)v.size()) return Q3ASR_ERR_NOMEM;
+        if (!v.empty()) memcpy(ids, v.data(), sizeof(int32_t) * v.size());
+        return Q3ASR_OK;
+    });
 }
 
 int q3asr_tokenizer_token_id(const q3asr_tokenizer* t, const char* token) {
     if (t == nullptr || token == nullptr) return -1;
-    auto it = t->token_to_id.find(token);
-    return it == t->token_to_id.end() ? -1 : it->second;
+    try {
+        auto it = t->token_to_id.find(token);
+        return it == t->token_to_id.end() ? -1 : it->second;
+    } catch (const std::exception&) {
+        return -1;
+    }
 }
 
 }  // extern "C"

@@ -169,3 +169,21 @@ def test_hostile_tokenizer_files_are_refused_not_crashed_on(tmp_path, built_lib)
     t = built_lib.Qwen3Tokenizer(path=str(d))
     assert t.token_id("ok") == 2
     t.close()
+
+
+def test_from_pairs_argument_checks(built_lib):
+    import ctypes
+    import numpy as np
+    L = built_lib.lib()
+    ids = np.array([1, 2], dtype=np.int32)
+    toks = (ctypes.c_char_p * 2)(b"a", None)                      # a NULL token string
+    out = ctypes.c_void_p(0xdead)
+    assert L.q3asr_tokenizer_from_pairs(ids.ctypes.data, ctypes.cast(toks, ctypes.c_void_p), 2, ctypes.byref(out)) == 1 and not out.value
+    assert L.q3asr_tokenizer_from_pairs(None, None, 2, ctypes.byref(out)) == 1
+    assert L.q3asr_tokenizer_from_pairs(None, None, -1, ctypes.byref(out)) == 1
+    assert L.q3asr_tokenizer_from_pairs(None, None, 0, ctypes.byref(out)) == 0 and out.value    # an empty tokenizer is fine
+    n = ctypes.c_int(-1)
+    assert L.q3asr_tokenizer_encode(out, b"abc", None, 0, ctypes.byref(n)) == 0 and n.value == 0
+    assert L.q3asr_tokenizer_add_merge(out, None, b"b") == 1 and L.q3asr_tokenizer_token_id(out, None) == -1
+    L.q3asr_tokenizer_destroy(out)
+    L.q3asr_tokenizer_destroy(None)
