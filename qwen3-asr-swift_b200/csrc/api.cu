@@ -271,14 +271,19 @@ int q3asr_prompt_ids(const q3asr_config* cfg, int n_audio_tokens, const q3asr_pr
     if (prompt && ((prompt->n_context > 0 && !prompt->context_ids) || (prompt->n_language > 0 && !prompt->language_ids) ||
                    prompt->n_context < 0 || prompt->n_language < 0))
         return Q3ASR_ERR_INVALID;
-    std::vector<int32_t> ids;
-    int at = 0;
-    build_prompt(*cfg, prompt, n_audio_tokens, &ids, &at);
-    *n_ids = (int)ids.size();
-    if (audio_at) *audio_at = at;
-    if ((int)ids.size() > cap) return Q3ASR_ERR_INVALID;  // *n_ids says how much room is needed
-    std::copy(ids.begin(), ids.end(), ids_out);
-    return Q3ASR_OK;
+    if (n_audio_tokens > (1 << 24)) return Q3ASR_ERR_INVALID;  // 120 000 frames give 15 600 tokens (AudioPreprocessing.swift:304)
+    try {
+        std::vector<int32_t> ids;
+        int at = 0;
+        build_prompt(*cfg, prompt, n_audio_tokens, &ids, &at);
+        *n_ids = (int)ids.size();
+        if (audio_at) *audio_at = at;
+        if ((int)ids.size() > cap) return Q3ASR_ERR_INVALID;  // *n_ids says how much room is needed
+        std::copy(ids.begin(), ids.end(), ids_out);
+        return Q3ASR_OK;
+    } catch (const std::exception&) {  // host allocation failure: nothing may cross the C boundary
+        return Q3ASR_ERR_NOMEM;
+    }
 }
 
 int q3asr_encode(q3asr_handle* h, const float* mel, int frames, float* out, int* tokens) {

@@ -46,15 +46,29 @@ extern "C" {
 
 int q3asr_lis_positions(const int* values, int n, int* positions, int* count) {
     if (n < 0 || (n > 0 && values == nullptr) || count == nullptr) return Q3ASR_ERR_INVALID;
-    const std::vector<int> p = lis_positions(values, n);
-    *count = (int)p.size();
-    if (positions)
-        for (size_t i = 0; i < p.size(); i++) positions[i] = p[i];
-    return Q3ASR_OK;
+    try {
+        const std::vector<int> p = lis_positions(values, n);
+        *count = (int)p.size();
+        if (positions)
+            for (size_t i = 0; i < p.size(); i++) positions[i] = p[i];
+        return Q3ASR_OK;
+    } catch (const std::exception&) {  // host allocation failure: nothing may cross the C boundary
+        return Q3ASR_ERR_NOMEM;
+    }
 }
+
+static int enforce_monotonicity_impl(const int* raw, int n, int* corrected);
 
 int q3asr_enforce_monotonicity(const int* raw, int n, int* corrected) {
     if (n < 0 || (n > 0 && (raw == nullptr || corrected == nullptr))) return Q3ASR_ERR_INVALID;
+    try {
+        return enforce_monotonicity_impl(raw, n, corrected);
+    } catch (const std::exception&) {
+        return Q3ASR_ERR_NOMEM;
+    }
+}
+
+static int enforce_monotonicity_impl(const int* raw, int n, int* corrected) {
     for (int i = 0; i < n; i++) corrected[i] = raw[i];
     if (n <= 1) return Q3ASR_OK;                                             // :16
     const std::vector<int> anchors = lis_positions(raw, n);                  // :19-26 (anchor value = raw[pos])

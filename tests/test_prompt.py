@@ -86,6 +86,7 @@ def test_sizing_protocol_and_errors(q3):
     # bad arguments
     assert L.q3asr_prompt_ids(None, 10, None, buf.ctypes.data, 64, ctypes.byref(n), None) == 1
     assert L.q3asr_prompt_ids(ctypes.byref(cfg), -1, None, buf.ctypes.data, 64, ctypes.byref(n), None) == 1
+    assert L.q3asr_prompt_ids(ctypes.byref(cfg), 2 ** 31 - 1, None, buf.ctypes.data, 64, ctypes.byref(n), None) == 1   # no 8 GB vector
     assert L.q3asr_prompt_ids(ctypes.byref(cfg), 10, None, buf.ctypes.data, 64, None, None) == 1
     bad = q3.Prompt()
     bad.n_context = 3  # count without a pointer
