@@ -141,3 +141,45 @@ def test_header_is_plain_c99_and_links_from_c(built_lib, tmp_path):
                     "-lq3asr", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "sm_100a" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_host_entry_points_are_reentrant(built_lib, tmp_path):
+    """The host-only entry points keep no shared mutable state (their error strings are per thread): eight threads calling them at once
+    (ctypes drops the GIL during a call) get what a serial run gets, and a failure on one thread does not leak its message into another."""
+    import threading
+    q = built_lib
+    wav = tmp_path / "t.wav"
+    q.AudioFileLoader.write_wav(wav, np.sin(np.arange(4000) * 0.05), 16000)
+    data = wav.read_bytes()
+    tok = q.Qwen3Tokenizer(id_to_token={i + 10: c for i, c in enumerate("abcdefghijklmnopqrstuvwxyz")})
+    text = "the quick brown fox, 你好 jumps over the lazy dog! " * 20
+
+    def work(k):
+        out = []
+        for it in range(40):
+            out.append(q.text_word_pairs(text, "English"))
+            out.append(q.AudioFileLoader.parse_wav(data)[0].tobytes())
+            out.append(tok.encode("quick brown fox"))
+            out.append(q.enforce_monotonicity([1, 3, 2, 7, 9, 11, 4, 12] * 5))
+            out.append(q.prompt_ids(q.preset("0.6B"), 50 + k % 2)[0].tobytes())
+            if k % 2:                                   # odd threads also fail on purpose, with a thread-specific message
+                try:
+                    q.text_word_pairs("x", "Japanese")
+                except q.Q3Error as e:
+                    out.append("NLTokenizer" in str(e))
+                try:
+                    q.AudioFileLoader.parse_wav(b"RIFF" + bytes(60))
+                except q.AudioLoadError as e:
+                    out.append("Invalid WAV" in str(e))
+        return out
+
+    want = {k: work(k) for k in (0, 1)}
+    got = {}
+    threads = [threading.Thread(target=lambda k=k: got.__setitem__(k, work(k))) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    tok.close()
+    assert all(got[k] == want[k % 2] for k in range(8))
+    assert all(v is True for v in want[1] if isinstance(v, bool))
