@@ -183,3 +183,14 @@ def test_host_entry_points_are_reentrant(built_lib, tmp_path):
     tok.close()
     assert all(got[k] == want[k % 2] for k in range(8))
     assert all(v is True for v in want[1] if isinstance(v, bool))
+
+
+def test_integration_appendix_lists_every_entry_point():
+    """INTEGRATION.md's appendix and include/q3asr.h name the same symbols."""
+    header = open(os.path.join(ROOT, "include", "q3asr.h")).read()
+    declared = set(re.findall(r"\b(q3asr_[a-z0-9_]+)\s*\(", header))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    appendix = doc[doc.index("## Appendix: every entry point"):]
+    listed = set(re.findall(r"`(q3asr_[a-z0-9_]+)`", appendix))
+    assert declared - listed == set(), sorted(declared - listed)
+    assert listed - declared == set(), sorted(listed - declared)
