@@ -194,3 +194,11 @@ def test_integration_appendix_lists_every_entry_point():
     listed = set(re.findall(r"`(q3asr_[a-z0-9_]+)`", appendix))
     assert declared - listed == set(), sorted(declared - listed)
     assert listed - declared == set(), sorted(listed - declared)
+
+
+def test_every_binding_declares_its_argument_types(built_lib):
+    """A ctypes call without argtypes passes Python ints as 32-bit C ints — a truncated pointer on the first 64-bit address.  Only the
+    entry points that take no argument may go without."""
+    L = built_lib.lib()
+    bare = [n for n in built_lib.EXPORTS if getattr(L, n).argtypes is None]
+    assert sorted(bare) == ["q3asr_io_last_error", "q3asr_text_last_error", "q3asr_version"]
