@@ -202,3 +202,19 @@ def test_every_binding_declares_its_argument_types(built_lib):
     L = built_lib.lib()
     bare = [n for n in built_lib.EXPORTS if getattr(L, n).argtypes is None]
     assert sorted(bare) == ["q3asr_io_last_error", "q3asr_text_last_error", "q3asr_version"]
+
+
+def test_binding_arity_matches_the_header(built_lib):
+    """Number of parameters of every declaration in include/q3asr.h against the length of the ctypes argtypes of its binding."""
+    header = open(os.path.join(ROOT, "include", "q3asr.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    L = built_lib.lib()
+    checked = 0
+    for m in re.finditer(r"\b(q3asr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        arity = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(L, name)
+        got = 0 if fn.argtypes is None else len(fn.argtypes)
+        assert got == arity, (name, got, arity)
+        checked += 1
+    assert checked == len(built_lib.EXPORTS)
