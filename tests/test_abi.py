@@ -218,3 +218,24 @@ def test_binding_arity_matches_the_header(built_lib):
         assert got == arity, (name, got, arity)
         checked += 1
     assert checked == len(built_lib.EXPORTS)
+
+
+def test_struct_layouts_match_the_header(built_lib, tmp_path):
+    """sizeof / offsetof of the three structs of the ABI as a C compiler sees them against the ctypes mirrors."""
+    import ctypes
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include "q3asr.h"\n#include <stddef.h>\n#include <stdio.h>\nint main(void) {\n'
+                   '    printf("%zu %zu %zu %zu\\n", sizeof(q3asr_config), offsetof(q3asr_config, dec_rope_theta), offsetof(q3asr_config, tok_eos),'
+                   " offsetof(q3asr_config, tok_timestamp));\n"
+                   '    printf("%zu %zu %zu\\n", sizeof(q3asr_prompt), offsetof(q3asr_prompt, language_ids), offsetof(q3asr_prompt, raw_suffix));\n'
+                   '    printf("%zu %zu %zu\\n", sizeof(q3asr_sampling), offsetof(q3asr_sampling, seed), offsetof(q3asr_sampling, force_device_sampler));\n'
+                   "    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    C, P, S = built_lib.Config, built_lib.Prompt, built_lib.Sampling
+    want = [ctypes.sizeof(C), C.dec_rope_theta.offset, C.tok_eos.offset, C.tok_timestamp.offset,
+            ctypes.sizeof(P), P.language_ids.offset, P.raw_suffix.offset,
+            ctypes.sizeof(S), S.seed.offset, S.force_device_sampler.offset]
+    assert [int(v) for v in out] == want
