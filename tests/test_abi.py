@@ -239,3 +239,35 @@ def test_struct_layouts_match_the_header(built_lib, tmp_path):
             ctypes.sizeof(P), P.language_ids.offset, P.raw_suffix.offset,
             ctypes.sizeof(S), S.seed.offset, S.force_device_sampler.offset]
     assert [int(v) for v in out] == want
+
+
+def test_swift_shim_calls_only_declared_entry_points():
+    """The Swift shim cannot be compiled here (no toolchain); at least every q3asr_* it calls must exist in the header, with as many
+    arguments as it passes (top-level commas of the call)."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "q3asr.h")).read(), flags=re.S)
+    arity = {}
+    for m in re.finditer(r"\b(q3asr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        params = m.group(2).strip()
+        arity[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    structs = set(re.findall(r"typedef struct (q3asr_\w+)", header))
+    swift = open(os.path.join(ROOT, "qwen3-asr-swift_b200", "swift", "Qwen3ASRB200.swift")).read()
+    swift = re.sub(r"//.*", "", swift)
+    calls = 0
+    for m in re.finditer(r"\b(q3asr_[a-z0-9_]+)\s*\(", swift):
+        name = m.group(1)
+        if name in structs:          # q3asr_config(), q3asr_prompt(...): struct initialisers
+            continue
+        assert name in arity, name
+        depth, i, commas, empty = 1, m.end(), 0, True
+        while depth:
+            ch = swift[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if depth == 1 and ch == ",":
+                commas += 1
+            if depth >= 1 and not ch.isspace():
+                empty = False
+            i += 1
+        assert (0 if empty else commas + 1) == arity[name], (name, commas + 1, arity[name])
+        calls += 1
+    assert calls >= 15
