@@ -42,6 +42,10 @@ int main(int argc, char** argv) {
                 return 9;
             } catch (const AudioModelError&) {
             }
+            // transcript extraction (Qwen3ASR.swift:283-289): what follows <asr_text>, trimmed of spaces / tabs / Unicode space separators
+            if (Qwen3ASRModel::textFromIds(t, {5, 7, 6, 5}) != "worldHello") return 9;  // "Hello<asr_text> worldHello" -> after the marker, trimmed
+            if (Qwen3ASRModel::trimSwiftWhitespaces(" \t\xC2\xA0\xE3\x80\x80 a b\n \xE2\x80\x89") != "a b\n") return 9;
+            if (Qwen3ASRModel::trimSwiftWhitespaces("  \t ") != "") return 9;
             printf("tokenizer ok\n");
             // preset detection from a checkpoint's own tensor index: header-only safetensors files written here
             auto write_ck = [&](const std::string& sub, const std::string& header, size_t payload) {

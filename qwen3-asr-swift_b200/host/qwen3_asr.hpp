@@ -288,6 +288,23 @@ class Qwen3ASRModel {
         return out;
     }
 
+    // trimmingCharacters(in: .whitespaces): Unicode space separators (Zs) and TAB at either end, not line breaks
+    static std::string trimSwiftWhitespaces(const std::string& s) {
+        static const char* const ws[] = {" ", "\t", "\xC2\xA0", "\xE1\x9A\x80", "\xE2\x80\x80", "\xE2\x80\x81", "\xE2\x80\x82", "\xE2\x80\x83",
+                                         "\xE2\x80\x84", "\xE2\x80\x85", "\xE2\x80\x86", "\xE2\x80\x87", "\xE2\x80\x88", "\xE2\x80\x89",
+                                         "\xE2\x80\x8A", "\xE2\x80\xAF", "\xE2\x81\x9F", "\xE3\x80\x80"};
+        size_t a = 0, b = s.size();
+        for (bool again = true; again;) {
+            again = false;
+            for (const char* w : ws) {
+                const size_t n = strlen(w);
+                if (b - a >= n && s.compare(a, n, w) == 0) { a += n; again = true; }
+                if (b - a >= n && s.compare(b - n, n, w) == 0) { b -= n; again = true; }
+            }
+        }
+        return s.substr(a, b - a);
+    }
+
     // generated ids -> transcript (Qwen3ASR.swift:283-289): decode, keep what follows "<asr_text>", trim; without a tokenizer the ids
     // joined by spaces (the reference's own fallback)
     static std::string textFromIds(const Tokenizer& tok, const std::vector<int32_t>& t) {
@@ -296,8 +313,7 @@ class Qwen3ASRModel {
             std::string raw = tok.decode(t);
             const size_t at = raw.find("<asr_text>");
             if (at != std::string::npos) raw = raw.substr(at + 10);
-            const size_t a = raw.find_first_not_of(' '), b = raw.find_last_not_of(' ');
-            out = a == std::string::npos ? std::string() : raw.substr(a, b - a + 1);
+            out = trimSwiftWhitespaces(raw);
         } else {
             for (size_t j = 0; j < t.size(); j++) out += (j ? " " : "") + std::to_string(t[j]);
         }

@@ -434,6 +434,9 @@ def detect_bits(model_id):
     return 8 if detect_model_size(model_id) == "1.7B" else 4
 
 
+_SWIFT_WHITESPACES = " \t\u00a0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u202f\u205f\u3000"  # CharacterSet.whitespaces
+
+
 class _PromptPack:
     """Keeps the numpy arrays behind an array of q3asr_prompt alive."""
 
@@ -731,7 +734,8 @@ class Qwen3ASRModel:
         if tok is None:
             return " ".join(str(int(t)) for t in ids)
         raw = tok.decode([int(t) for t in ids])
-        return raw.split("<asr_text>", 1)[1].strip(" ") if "<asr_text>" in raw else raw
+        # trimmingCharacters(in: .whitespaces) (Qwen3ASR.swift:286): Unicode space separators and TAB, not line breaks
+        return raw.split("<asr_text>", 1)[1].strip(_SWIFT_WHITESPACES) if "<asr_text>" in raw else raw
 
     def transcribe_long(self, audio, sample_rate=16000, window_seconds=30.0, max_tokens=448, batch=64, language_ids=None, context_ids=None):
         """Long-form transcription (BASELINE config 5): fixed windows, each an independent utterance, `batch` windows per pass.

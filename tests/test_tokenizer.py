@@ -187,3 +187,26 @@ def test_from_pairs_argument_checks(built_lib):
     assert L.q3asr_tokenizer_add_merge(out, None, b"b") == 1 and L.q3asr_tokenizer_token_id(out, None) == -1
     L.q3asr_tokenizer_destroy(out)
     L.q3asr_tokenizer_destroy(None)
+
+
+def test_transcript_extraction_from_generated_ids(built_lib):
+    """Qwen3ASRModel.transcribe's tail (Qwen3ASR.swift:283-293): decode, keep what follows "<asr_text>" trimmed of CharacterSet.whitespaces
+    (space separators and TAB, not line breaks); without the marker the decoded text as it is; without a tokenizer the ids joined by
+    spaces.  The layout is the one testTokenizerDecodeWithASRMarker builds: "language English<asr_text>Hello"."""
+    m = built_lib.Qwen3ASRModel.__new__(built_lib.Qwen3ASRModel)      # no GPU handle needed for this host logic
+    m._h = None
+    m.tokenizer = None
+    assert m._text_of([11528, 6364, 151704, 9707]) == "11528 6364 151704 9707"
+    tok = built_lib.Qwen3Tokenizer(id_to_token={1: "language", 2: "ĠEnglish", 3: "<asr_text>", 4: "Hello", 5: "Ġworld", 6: "ĉ", 7: "Ċ",
+                                                8: "Âł", 9: "<|im_end|>"})
+    m.tokenizer = tok
+    try:
+        assert tok.decode([1, 2, 3, 4]) == "language English<asr_text>Hello"
+        assert m._text_of([1, 2, 3, 4, 5, 9]) == "Hello world"
+        assert m._text_of([1, 2, 3, 5, 4]) == "worldHello"               # the space of "Ġworld" right after the marker is trimmed
+        assert m._text_of([3, 6, 8, 4, 7]) == "Hello\n"                   # TAB and NBSP go, the trailing line break stays
+        assert m._text_of([4, 5]) == "Hello world"                        # no marker: the decoded text
+        assert m._text_of([3]) == "" and m._text_of([]) == ""
+    finally:
+        m.tokenizer = None
+        tok.close()
