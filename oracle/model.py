@@ -64,9 +64,13 @@ def sinusoid_positions(n, d):
 
 
 class Oracle:
-    def __init__(self, cfg, weights, emulate_bf16=True, threads=None):
+    def __init__(self, cfg, weights, emulate_bf16=True, threads=None, decoder_fp64=False):
+        """decoder_fp64: the decoder's products and attention accumulate in float64 (rounded to fp32, then to bf16 at the same
+        points) — a second accumulation order, used by tests/golden/make_golden.py to keep only fixtures whose greedy ids do
+        not depend on it."""
         self.cfg = dict(cfg)
         self.emu = emulate_bf16
+        self.fp64 = decoder_fp64
         if threads:
             torch.set_num_threads(threads)
         self.w = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in weights.items()}
@@ -80,8 +84,16 @@ class Oracle:
         b = self.w[f"audio_tower.{name}.bias"]
         return self.r(F.gelu(F.conv2d(x, w, b, stride=2, padding=1)))
 
-    def _attention(self, q, k, v, heads, kv_heads, scale, causal):
+    def _mm(self, a, w):
+        """a @ w.T for the decoder (fp32, or float64 accumulation when decoder_fp64)."""
+        if self.fp64:
+            return (a.double() @ w.double().t()).float()
+        return a @ w.t()
+
+    def _attention(self, q, k, v, heads, kv_heads, scale, causal, fp64=False):
         """q [T, heads*hd], k/v [S, kv_heads*hd]; one segment."""
+        if fp64:
+            return self._attention64(q, k, v, heads, kv_heads, scale, causal)
         T, S = q.shape[0], k.shape[0]
         hd = q.shape[1] // heads
         qh = q.view(T, heads, hd).transpose(0, 1)
@@ -96,6 +108,23 @@ class Oracle:
         p = torch.exp(s - m)
         l = p.sum(dim=-1, keepdim=True)
         o = torch.matmul(self.r(p), vh) / l
+        return self.r(o.transpose(0, 1).reshape(T, heads * hd))
+
+    def _attention64(self, q, k, v, heads, kv_heads, scale, causal):
+        T, S = q.shape[0], k.shape[0]
+        hd = q.shape[1] // heads
+        qh = q.double().view(T, heads, hd).transpose(0, 1)
+        kh = k.double().view(S, kv_heads, hd).transpose(0, 1).repeat_interleave(heads // kv_heads, dim=0)
+        vh = v.double().view(S, kv_heads, hd).transpose(0, 1).repeat_interleave(heads // kv_heads, dim=0)
+        s = (torch.matmul(qh, kh.transpose(1, 2)) * scale).float()
+        if causal:
+            i = torch.arange(T)[:, None] + (S - T)
+            j = torch.arange(S)[None, :]
+            s = s.masked_fill(j > i, float("-inf"))
+        m = s.max(dim=-1, keepdim=True).values
+        p = torch.exp(s - m)
+        l = p.double().sum(dim=-1, keepdim=True)
+        o = (torch.matmul(self.r(p).double(), vh) / l).float()
         return self.r(o.transpose(0, 1).reshape(T, heads * hd))
 
     def encode(self, mel, return_stages=False):
@@ -205,9 +234,9 @@ class Oracle:
             p = f"model.layers.{l}."
             W = lambda s: self.w[p + s]
             xn = self._rmsnorm(x, W("input_layernorm.weight"), eps)
-            q = r(xn @ W("self_attn.q_proj.weight").t())
-            k = r(xn @ W("self_attn.k_proj.weight").t())
-            v = r(xn @ W("self_attn.v_proj.weight").t())
+            q = r(self._mm(xn, W("self_attn.q_proj.weight")))
+            k = r(self._mm(xn, W("self_attn.k_proj.weight")))
+            v = r(self._mm(xn, W("self_attn.v_proj.weight")))
             q = self._rmsnorm(q.view(T, nh, hd), W("self_attn.q_norm.weight"), eps).reshape(T, nh * hd)
             k = self._rmsnorm(k.view(T, nkv, hd), W("self_attn.k_norm.weight"), eps).reshape(T, nkv * hd)
             q = self._rope(q, pos, nh)
@@ -216,20 +245,20 @@ class Oracle:
                 k = torch.cat([cache[l][0], k], dim=0)
                 v = torch.cat([cache[l][1], v], dim=0)
             new_cache.append((k, v))
-            att = self._attention(q, k, v, nh, nkv, scale, causal=T > 1)
-            x = r(x + r(att @ W("self_attn.o_proj.weight").t()))
+            att = self._attention(q, k, v, nh, nkv, scale, causal=T > 1, fp64=self.fp64)
+            x = r(x + r(self._mm(att, W("self_attn.o_proj.weight"))))
             xn = self._rmsnorm(x, W("post_attention_layernorm.weight"), eps)
-            g = r(xn @ W("mlp.gate_proj.weight").t())
-            u = r(xn @ W("mlp.up_proj.weight").t())
+            g = r(self._mm(xn, W("mlp.gate_proj.weight")))
+            u = r(self._mm(xn, W("mlp.up_proj.weight")))
             act = r(r(F.silu(g)) * u)
-            x = r(x + r(act @ W("mlp.down_proj.weight").t()))
+            x = r(x + r(self._mm(act, W("mlp.down_proj.weight"))))
         if rows is not None:  # final norm of the requested rows (the forced aligner classifies several positions of one pass)
             return self._rmsnorm(x[torch.tensor(list(rows), dtype=torch.long)], self.w["model.norm.weight"], eps), new_cache
         last = self._rmsnorm(x[-1:], self.w["model.norm.weight"], eps)
         return last, new_cache
 
     def _logits(self, last):
-        return self.r(last @ self.w["model.embed_tokens.weight"].t())[0]
+        return self.r(self._mm(last, self.w["model.embed_tokens.weight"]))[0]
 
     def prefill(self, audio_embeds, context=None, language=None):
         ids, at = self.prompt_ids(audio_embeds.shape[0], context, language)
@@ -241,10 +270,12 @@ class Oracle:
 
     def greedy(self, audio_embeds, max_tokens, stop_on_eos=True, forced=None, context=None, language=None):
         """Qwen3ASR.swift:317-390.  forced: optional token stream fed instead of the argmax (teacher forcing).
-        Returns (ids, top1 logit per step, top1-top2 margin per step)."""
+        Returns (ids, top1 logit per step, top1-top2 margin per step); self.runner_up holds the id of the second-best logit of
+        every step (lowest index among equals, after excluding the winner)."""
         E = self.w["model.embed_tokens.weight"]
         logits, cache, _ = self.prefill(audio_embeds, context, language)
         ids, tops, margins = [], [], []
+        self.runner_up = []
         steps = max_tokens if forced is None else len(forced) + 1
         for step in range(steps):
             top2 = torch.topk(logits, 2)
@@ -255,6 +286,10 @@ class Oracle:
             ids.append(best)
             tops.append(mx)
             margins.append(float(top2.values[0] - top2.values[1]))
+            second = float(top2.values[1])
+            cand2 = torch.nonzero(logits == second).flatten()
+            cand2 = cand2[cand2 != best]
+            self.runner_up.append(int(cand2.min()) if cand2.numel() else best)
             if forced is None and stop_on_eos and best == self.cfg["tok_eos"]:
                 break
             if step + 1 == steps:

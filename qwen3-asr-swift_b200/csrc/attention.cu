@@ -184,11 +184,10 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 template <int HD, bool CAUSAL>
 void launch(const AttnParams& p, const AttnSegs& segs, int heads, cudaStream_t st) {
     constexpr int smem = (BQ + 2 * BKV) * (HD + 8) * 2;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    });
     dim3 grid((segs.max_len + BQ - 1) / BQ, heads, segs.n_segs);
     flash_attn_kernel<HD, CAUSAL><<<grid, 128, smem, st>>>(p);
     Q3_CUDA(cudaGetLastError());

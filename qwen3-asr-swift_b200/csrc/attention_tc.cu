@@ -350,11 +350,10 @@ template <int HD, bool CAUSAL, int NQ>
 void launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FaParams& p, const AttnSegs& segs, int heads,
             cudaStream_t st) {
     using C = FaCfg<HD, NQ>;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(fa_tc_kernel<HD, CAUSAL, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr = true;
-    }
+    });
     dim3 grid((segs.max_len + FA_BQ - 1) / FA_BQ, heads / NQ, segs.n_segs);
     fa_tc_kernel<HD, CAUSAL, NQ><<<grid, C::THREADS, C::SMEM, st>>>(tq, tk, tv, p);
     Q3_CUDA(cudaGetLastError());

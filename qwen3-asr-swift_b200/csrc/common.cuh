@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -31,6 +32,22 @@ struct Error : public std::runtime_error {
     } while (0)
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) is per device: a process that drives several GPUs
+// (q3asr_pool, one worker thread per device) has to opt in on each of them.  One flag bit per device ordinal; the action is
+// idempotent, so two threads racing on the same device are harmless.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    template <typename F>
+    void operator()(F&& f) {
+        int dev = 0;
+        Q3_CUDA(cudaGetDevice(&dev));
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return;
+        f();
+        done.fetch_or(bit, std::memory_order_release);
+    }
+};
 
 // Kernel launch with optional programmatic stream serialization (PDL): the kernel may start while its predecessor
 // in the stream is still draining; it must call ptx::grid_dep_wait() before touching the predecessor's outputs.

@@ -146,10 +146,7 @@ void plan_decoder(Handle* h, BatchState* bs, const q3asr_prompt* prompts, int ma
     }
     bs->R = row;
     bs->max_prompt = max_prompt;
-    bs->max_tokens = max_tokens;
-    bs->pages_per_seq = (max_prompt + max_tokens + KV_PAGE - 1) / KV_PAGE;
-    std::vector<int> table((size_t)B * bs->pages_per_seq);
-    for (size_t i = 0; i < table.size(); i++) table[i] = (int)i;  // pages handed out in order; freed with the batch
+    (void)max_tokens;  // the KV pages are planned separately (plan_pages): the decode capacity may grow until the prefill runs
     bs->o_ids = push_ints(*ints, ids);
     bs->o_audio_src = push_ints(*ints, audio_src);
     bs->o_pos = push_ints(*ints, pos);
@@ -159,7 +156,21 @@ void plan_decoder(Handle* h, BatchState* bs, const q3asr_prompt* prompts, int ma
     bs->o_last_row = push_ints(*ints, last_row);
     bs->o_ident = push_ints(*ints, ident);
     bs->o_pos0 = push_ints(*ints, pos0);
-    bs->o_page_table = push_ints(*ints, table);
+}
+
+// KV page table for a decode capacity of max_tokens per sequence: pages are handed out in order and freed with the batch.
+// Its own device buffer, so that batch_run can re-plan for a larger max_tokens than the upload reserved (the reference's
+// transcribe(maxTokens:) takes any value, Qwen3ASR.swift:131-136) as long as the prefill has not written any page yet.
+void plan_pages(Handle* h, BatchState* bs, int max_tokens) {
+    bs->max_tokens = max_tokens;
+    bs->pages_per_seq = (bs->max_prompt + max_tokens + KV_PAGE - 1) / KV_PAGE;
+    const size_t n = (size_t)bs->B * bs->pages_per_seq;
+    bs->page_tab.reserve(n * sizeof(int));
+    bs->h_pages.reserve(n * sizeof(int));
+    int* t = bs->h_pages.as<int>();
+    for (size_t i = 0; i < n; i++) t[i] = (int)i;
+    Q3_CUDA(cudaMemcpyAsync(bs->page_tab.p, t, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));  // h_pages is reused by the next plan
 }
 
 void upload_ints(Handle* h, BatchState* bs, const std::vector<int>& ints) {
@@ -363,7 +374,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
 KvCache kv_cache(Handle* h, BatchState* bs) {
     KvCache kc;
     kc.pool = bs->kv_pool.as<bf16>();
-    kc.page_table = bs->ints.as<int>() + bs->o_page_table;
+    kc.page_table = bs->page_tab.as<int>();
     kc.max_pages = bs->pages_per_seq;
     kc.layers = h->cfg.dec_layers;
     kc.kv_heads = h->cfg.dec_kv_heads;
@@ -442,7 +453,11 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
     const KvCache kc = kv_cache(h, bs);
     const int s_qkv = gemm_skinny_splits(nqkv, H, SK_PARTIAL), s_o = gemm_skinny_splits(H, nq, SK_PARTIAL),
               s_dn = gemm_skinny_splits(H, c.dec_inter, SK_PARTIAL);
-    const int skip = env_int("Q3ASR_DEC_SKIP", 0);  // timing ablation only (results are wrong when set): bit i drops kernel i of the layer
+#ifdef Q3ASR_ABLATION  // `make ablation` only (tools/decode_ablation.py): the shipped library has no switch that changes results
+    const int skip = env_int("Q3ASR_DEC_SKIP", 0);  // bit i drops kernel i of the layer
+#else
+    constexpr int skip = 0;
+#endif
     double kv_bytes = 0;  // keys + values read by one layer's attention
     for (const ClipInfo& ci : bs->clips) kv_bytes += 2.0 * 2.0 * nkv * (ci.prompt_len + bs->steps_done);
     {
@@ -766,8 +781,8 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     std::vector<int> ints;
     plan_encoder(h, bs, frames, mel_off, &ints);
     for (int b = 0; b < batch; b++) bs->clips[b].n = (int)n[b];
-    // the decoder plan needs max_tokens for the page reservation; use the largest the API allows by default
-    // and let batch_run re-plan if a larger value is requested
+    // the KV pages are reserved for the reference's default decode length (maxTokens = 448, Qwen3ASR.swift:135); batch_run
+    // re-plans them when a larger value is asked for
     const int reserve_tokens = std::max(1, env_int("Q3ASR_RESERVE_TOKENS", 448));
     plan_decoder(h, bs, prompts, reserve_tokens, &ints);
     for (auto& t : workers) t.join();
@@ -778,6 +793,7 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
                 resample_device(h, bs->raw_pcm.as<float>() + raw_off[(size_t)b], n_in[b], rates[b], 16000,
                                 bs->pcm.as<float>() + bs->mel.clips[b].in_off, n[b], h->stream);
     upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
+    plan_pages(h, bs, reserve_tokens);
     bs->prompt_ids.clear();
 }
 
@@ -910,8 +926,12 @@ void pick_next_token(Handle* h, const float* logits, int vocab, const int32_t* g
 void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos) {
     BatchState* bs = h->batch.get();
     Q3_CHECK(bs != nullptr && bs->B > 0 && bs->has_audio, Q3ASR_ERR_STATE, "batch_run: no batch uploaded");
-    Q3_CHECK(max_tokens >= 0 && max_tokens <= bs->max_tokens, Q3ASR_ERR_INVALID,
-             "batch_run: max_tokens exceeds the reserved decode capacity (Q3ASR_RESERVE_TOKENS, default 448)");
+    Q3_CHECK(max_tokens >= 0 && max_tokens <= (1 << 20), Q3ASR_ERR_INVALID, "batch_run: max_tokens out of range");
+    if (max_tokens > bs->max_tokens) {
+        Q3_CHECK(!bs->prefill_done, Q3ASR_ERR_STATE,
+                 "batch_run: max_tokens exceeds the decode capacity this batch was prefilled with (pass the larger value to the prefill stage)");
+        plan_pages(h, bs, max_tokens);
+    }
     if (stages & (Q3ASR_STAGE_ENCODER | Q3ASR_STAGE_PREFILL | Q3ASR_STAGE_DECODE))
         Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded (q3asr_init_random / q3asr_load_safetensors)");
     cudaStream_t st = h->stream;
@@ -1001,7 +1021,8 @@ void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* pr
     batch_upload(h, pp, &n, 1, prompt);
     BatchState* bs = h->batch.get();
     const int steps = n_forced + 1;
-    Q3_CHECK(steps <= bs->max_tokens, Q3ASR_ERR_INVALID, "decode_forced: too many forced tokens");
+    Q3_CHECK(steps <= (1 << 20), Q3ASR_ERR_INVALID, "decode_forced: too many forced tokens");
+    if (steps > bs->max_tokens) plan_pages(h, bs, steps);
     for (int i = 0; i < n_forced; i++) Q3_CHECK(forced[i] >= 0 && forced[i] < h->cfg.dec_vocab, Q3ASR_ERR_INVALID, "forced id out of range");
     cudaStream_t st = h->stream;
     run_mel(h, bs);

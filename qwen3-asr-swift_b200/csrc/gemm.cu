@@ -39,11 +39,10 @@ void make_tmap(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 
 template <int BN, int EPI>
 void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, GemmDev p, int max_stages, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
-        attr_set = true;
-    }
+    });
     p.stages = max_stages > 0 ? std::min(max_stages, gemm_stages(BN)) : gemm_stages(BN);
     const int smem = p.stages * gemm_stage_bytes(BN) + 1024 + 256;
     launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, smem, st, ta, tb, p);
@@ -62,11 +61,10 @@ void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 
 template <int BN, int EPI>
 void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(BN)));
-        attr_set = true;
-    }
+    });
     launch_kernel(gemm_tc2_kernel<BN, EPI>, grid, GEMM_THREADS, gemm2_smem_bytes(BN), st, ta, tb, p);
 }
 template <int BN>
@@ -354,11 +352,10 @@ unsigned long long gemm_launch_count() { return g_launches.load(); }
 namespace {
 template <int NB, int EPI, bool DEEP>
 void launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyDev& p, dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NB, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(NB, DEEP)));
-        attr_set = true;
-    }
+    });
     launch_kernel(gemm_skinny_kernel<NB, EPI, DEEP>, grid, 256, sk_smem_bytes(NB, DEEP), st, tw, tx, p);
 }
 template <int NB>
@@ -430,11 +427,10 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
 namespace {
 template <int NB>
 void launch_lmhead(const CUtensorMap& tw, const CUtensorMap& tx, const LmHeadDev& p, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(lmhead_argmax_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lmh_smem_bytes(NB)));
-        attr_set = true;
-    }
+    });
     launch_kernel(lmhead_argmax_kernel<NB>, grid, 256, lmh_smem_bytes(NB), st, tw, tx, p);
 }
 }  // namespace

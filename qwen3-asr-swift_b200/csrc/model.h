@@ -80,16 +80,16 @@ struct BatchState {
     // offsets into `ints` (in ints)
     size_t o_conv_chunks = 0;  // Conv1Chunk[] (as bytes, see model.cu)
     size_t o_vw1 = 0, o_vw2 = 0, o_vw3 = 0, o_rowmap = 0, o_win_row0 = 0, o_win_len = 0;
-    size_t o_ids = 0, o_audio_src = 0, o_pos = 0, o_row_seq = 0, o_seq_row0 = 0, o_seq_len = 0, o_last_row = 0, o_page_table = 0,
+    size_t o_ids = 0, o_audio_src = 0, o_pos = 0, o_row_seq = 0, o_seq_row0 = 0, o_seq_len = 0, o_last_row = 0,
            o_ident = 0, o_pos0 = 0;
     DevBuf a1, a2, a3, ex, exn, eqkv, eatt, effn, audio;        // encoder activations
     DevBuf dx, dxn, dqkv, dq, dkc, datt, dact, dlast, dws; // decoder activations (dws: fp32 split-K partials of the decode step)
-    DevBuf kv_pool, rope_tab;
+    DevBuf kv_pool, rope_tab, page_tab;  // page_tab: [B][pages_per_seq] (plan_pages)
     int rope_n = 0;          // positions tabulated in rope_tab
     DevBuf amax_val, amax_idx, logits, logits_bf;
     // decode state (device)
     DevBuf st_next_tok, st_next_val, st_cur_tok, st_pos, st_kv_len, st_out_ids, st_out_val, st_out_len, st_finished, st_scalars, st_forced;
-    HostBuf h_stage, h_ints, h_out;
+    HostBuf h_stage, h_ints, h_out, h_pages;
     cudaGraphExec_t step_graph = nullptr;
     int graph_B = 0;
     cudaEvent_t ev[5] = {nullptr};
@@ -99,7 +99,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &amax_val, &amax_idx, &logits, &logits_bf,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &page_tab, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }
@@ -108,6 +108,7 @@ struct BatchState {
         h_stage.release();
         h_ints.release();
         h_out.release();
+        h_pages.release();
         if (step_graph) cudaGraphExecDestroy(step_graph);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);

@@ -1064,12 +1064,21 @@ __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
-__global__ void random_init_kernel(bf16* out, size_t n, unsigned long long seed, float mult) {
+// row_len > 0: "loud rows" — row r of the matrix is multiplied by 2^min(ctz(splitmix(row_seed + r)) / 4, 4) after the bf16
+// rounding (exact), i.e. one row in 16 is twice as large, one in 256 four times, ...: a heavy-tailed logit distribution
+// through the tied head, so that greedy ids on random weights have margins well above bf16 noise
+__global__ void random_init_kernel(bf16* out, size_t n, unsigned long long seed, float mult, unsigned long long row_seed, int row_len) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long z = splitmix(seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL);
     const int s = (int)(z & 0xFFFF) + (int)((z >> 16) & 0xFFFF) + (int)((z >> 32) & 0xFFFF) + (int)(z >> 48) - 131070;
-    out[i] = __float2bfloat16_rn(__fmul_rn(__int2float_rn(s), mult));
+    float v = __bfloat162float(__float2bfloat16_rn(__fmul_rn(__int2float_rn(s), mult)));
+    if (row_len > 0) {
+        const unsigned long long hz = splitmix(row_seed + (unsigned long long)(i / (size_t)row_len));
+        const int tz = hz ? __ffsll((long long)hz) - 1 : 64;
+        v *= (float)(1 << min(tz >> 2, 4));
+    }
+    out[i] = __float2bfloat16_rn(v);
 }
 
 // (cos, sin)(pos * inv_freq[i]) for pos < n_pos, i < 64: the fp32 product and sincosf of the per-element kernels, tabulated
@@ -1154,14 +1163,13 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
     const float sl2 = scale * 1.4426950408889634f;
     dim3 grid(n_seqs, cache.kv_heads);
     // few (sequence, head) pairs: more warps per CTA so that short batches still spread the key loop
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(4)));
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(16)));
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(2)));
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(8)));
-        attr = true;
-    }
+    });
     bool many = (long)n_seqs * cache.kv_heads >= 2L * num_sms;  // few (sequence, head) pairs: more warps per CTA share the key loop
     if (const char* f = getenv("Q3ASR_DECODE_ATTN_WARPS")) {        // tests force either variant on small batches (2 or 8 warps)
         if (atoi(f) == 2) many = true;
@@ -1229,10 +1237,10 @@ void f32_to_bf16_launch(const float* in, bf16* out, size_t n, cudaStream_t st) {
 void f16_to_bf16_launch(const uint16_t* in, bf16* out, size_t n, cudaStream_t st) {
     if (n) f16_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
 }
-void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st) {
+void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st, uint64_t row_seed, int row_len) {
     // std of the 4x16-bit Irwin-Hall sum is sqrt((65536^2 - 1) / 3)
     const float mult = (float)((double)scale / 37837.22668596909);
-    if (n) random_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, (unsigned long long)seed, mult);
+    if (n) random_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, (unsigned long long)seed, mult, (unsigned long long)row_seed, row_len);
 }
 void fill_bf16_launch(bf16* out, size_t n, float v, cudaStream_t st) {
     if (n) fill_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, v);

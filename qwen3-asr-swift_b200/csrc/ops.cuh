@@ -118,7 +118,7 @@ void bf16_to_f32_launch(const bf16* in, float* out, size_t n, cudaStream_t st);
 void f32_to_bf16_launch(const float* in, bf16* out, size_t n, cudaStream_t st);
 void f16_to_bf16_launch(const uint16_t* in, bf16* out, size_t n, cudaStream_t st);
 // deterministic random init (see model.cu / oracle/weights.py): out[i] = bf16(scale * irwin_hall4(seed, i))
-void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st);
+void random_init_launch(bf16* out, size_t n, uint64_t seed, float scale, cudaStream_t st, uint64_t row_seed = 0, int row_len = 0);
 void fill_bf16_launch(bf16* out, size_t n, float v, cudaStream_t st);
 
 }  // namespace q3

@@ -1,12 +1,25 @@
 """Generates the committed golden fixtures from the CPU oracle (run here, on CPU):
-    python tests/golden/make_golden.py [--big]
+    python tests/golden/make_golden.py            small fixtures (seconds)
+    python tests/golden/make_golden.py --big      + the full-size fixtures below (tens of minutes: it screens clips)
 mel_golden.npz      inputs + oracle log-mel for four small clips
 tiny_golden.npz     encoder output + greedy ids + teacher-forced argmax of the tiny configuration
-q06b_clip5s.npz     (--big) greedy ids + encoder slice of Qwen3-ASR-0.6B dims on one 5 s clip
+q06b_clip30s.npz    (--big) Qwen3-ASR-0.6B dims, one 30 s clip (BASELINE configs 1/2): full [390,1024] encoder output of the
+                    bf16-emulating and of the plain fp32 oracle, 128 free-running greedy ids, 128 teacher-forced steps on a
+                    pseudo-random token stream (ids, best logit, margin)
+q06b_ragged.npz     (--big) 0.6B, a 17.3 s clip (1730 frames: ragged last chunk, windows [104,104,17]): encoder + 32 ids
+q17b_clip15s.npz    (--big) Qwen3-ASR-1.7B dims, one 15 s clip (BASELINE config 4's shape): the same contents as q06b_clip30s
 The reference itself cannot be imported (Swift + MLX); these are outputs of the restatement in oracle/.
+
+A full-size fixture is only written when its free-running ids are a meaningful parity target: at least
+32 distinct tokens among the 128, at least 90 % of the steps with a top-1/top-2 margin above two bf16 ulps of the best logit,
+and ids that a second accumulation order reproduces exactly (the oracle run again with float64 accumulation in the decoder:
+a clip whose ids hinge on an exact bf16 tie of the two best logits fails this).  Clips are screened in index order until one
+passes; the chosen index is stored in the fixture, with the runner-up id of every step (a test may only accept a deviation
+at a step whose margin is at most one ulp, and only towards the runner-up).
 """
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -15,6 +28,71 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import mel as omel  # noqa: E402
 from oracle import model as omodel  # noqa: E402
 from oracle import synth, weights  # noqa: E402
+
+SEED = 20260418
+
+
+def bf16_ulp(x):
+    """Spacing of bf16 numbers at |x| (8 significant bits)."""
+    x = np.maximum(np.abs(np.asarray(x, dtype=np.float64)), 1e-30)
+    return np.exp2(np.floor(np.log2(x)) - 7)
+
+
+def to_bf16_bits(x):
+    """bf16-representable float32 -> uint16 (the fixtures store encoder states this way: half the bytes, exact)."""
+    return (np.ascontiguousarray(weights.bf16_round(x), dtype=np.float32).view(np.uint32) >> 16).astype(np.uint16)
+
+
+def margin_report(ids, tops, margins):
+    ulp = bf16_ulp(tops)
+    return dict(distinct=len(set(ids.tolist())), frac_gt2=float((margins > 2 * ulp).mean()), n_le1=int((margins <= ulp).sum()),
+                min_margin_ulps=float((margins / ulp).min()))
+
+
+def acceptable(rep, n):
+    return rep["distinct"] >= min(32, n // 4) and rep["frac_gt2"] >= 0.9 and rep["n_le1"] <= n // 10
+
+
+def full_size_fixture(path, preset, n_samples, n_free, n_forced, first_clip, max_trials, fp32_weights_too=True):
+    cfg = weights.preset(preset)
+    t0 = time.time()
+    sd = weights.random_state_dict(cfg, SEED)
+    print(f"{preset}: weights in {time.time() - t0:.0f} s", flush=True)
+    orc = omodel.Oracle(cfg, sd)
+    orc64 = omodel.Oracle(cfg, sd, decoder_fp64=True)
+    chosen = None
+    for clip in range(first_clip, first_clip + max_trials):
+        x = synth.clip(clip, n_samples)
+        feats = omel.mel(x)
+        enc = orc.encode(feats)
+        ids, tops, margins = orc.greedy(enc, n_free, stop_on_eos=False)
+        rep = margin_report(ids, tops, margins)
+        runner = np.array(orc.runner_up, dtype=np.int32)
+        print(f"  clip {clip}: {rep}", flush=True)
+        if not acceptable(rep, n_free):
+            continue
+        ids64 = orc64.greedy(enc, n_free, stop_on_eos=False)[0]
+        same = int((ids64 == ids).sum()) if ids64.shape == ids.shape else -1
+        print(f"    float64 accumulation: {same} of {n_free} ids equal", flush=True)
+        if same == n_free:
+            chosen = clip
+            break
+    assert chosen is not None, "no clip passed the screening: widen max_trials"
+    out = dict(seed=SEED, clip_index=chosen, n_samples=n_samples, encoder_bf16=to_bf16_bits(enc), ids=ids, tops=tops, margins=margins,
+               runner_up=runner)
+    if n_forced:
+        forced = np.random.default_rng(1000 + chosen).integers(0, cfg["dec_vocab"] - 2000, size=n_forced).astype(np.int32)
+        fids, ftops, fmargins = orc.greedy(enc, 0, forced=forced)
+        frunner = np.array(orc.runner_up, dtype=np.int32)
+        frep = margin_report(fids, ftops, fmargins)
+        print(f"  teacher-forced: {frep}", flush=True)
+        assert frep["n_le1"] <= n_forced // 10, frep
+        out.update(forced=forced, forced_ids=fids, forced_tops=ftops, forced_margins=fmargins, forced_runner_up=frunner)
+    if fp32_weights_too:  # the reference's encoder runs in fp32 on an fp32 mel: the plain fp32 oracle states the bf16 tolerance
+        o32 = omodel.Oracle(cfg, sd, emulate_bf16=False)
+        out["encoder_fp32_as_bf16"] = to_bf16_bits(o32.encode(feats))
+    np.savez_compressed(path, **out)
+    print(f"  wrote {os.path.basename(path)} ({os.path.getsize(path) / 1e6:.2f} MB) ids[:16] {ids[:16].tolist()}", flush=True)
 
 
 def main():
@@ -28,24 +106,24 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mel_golden.npz"), **out)
 
     cfg = weights.preset("tiny")
-    orc = omodel.Oracle(cfg, weights.random_state_dict(cfg, 20260418))
+    orc = omodel.Oracle(cfg, weights.random_state_dict(cfg, SEED))
     x = synth.clip(0, 16000 * 3 + 777)
     enc = orc.encode(omel.mel(x))
     ids, tops, margins = orc.greedy(enc, 32, stop_on_eos=False)
     forced = np.random.default_rng(11).integers(0, 2000, size=24).astype(np.int32)
     fids, ftops, fmargins = orc.greedy(enc, 0, forced=forced)
-    np.savez_compressed(os.path.join(HERE, "tiny_golden.npz"), seed=20260418, clip_index=0, n_samples=x.size, encoder=enc, ids=ids,
+    np.savez_compressed(os.path.join(HERE, "tiny_golden.npz"), seed=SEED, clip_index=0, n_samples=x.size, encoder=enc, ids=ids,
                         tops=tops, margins=margins, forced=forced, forced_ids=fids, forced_tops=ftops, forced_margins=fmargins)
+    print("tiny ids", ids.tolist(), margin_report(ids, tops, margins))
 
     if "--big" in sys.argv:
-        cfg = weights.preset("0.6B")
-        orc = omodel.Oracle(cfg, weights.random_state_dict(cfg, 20260418))
-        x = synth.clip(7, 80000)
-        enc = orc.encode(omel.mel(x))
-        ids, tops, margins = orc.greedy(enc, 24, stop_on_eos=False)
-        np.savez_compressed(os.path.join(HERE, "q06b_clip5s.npz"), seed=20260418, clip_index=7, n_samples=x.size,
-                            encoder_first64=enc[:, :64], ids=ids, tops=tops, margins=margins)
-        print("0.6B ids", ids.tolist(), "min margin", margins.min())
+        which = [a for a in sys.argv[1:] if not a.startswith("--")]
+        if not which or "q06b_clip30s" in which:
+            full_size_fixture(os.path.join(HERE, "q06b_clip30s.npz"), "0.6B", 480000, 128, 128, 0, 60)
+        if not which or "q06b_ragged" in which:
+            full_size_fixture(os.path.join(HERE, "q06b_ragged.npz"), "0.6B", 1730 * 160 + 57, 32, 0, 100, 40, fp32_weights_too=False)
+        if not which or "q17b_clip15s" in which:
+            full_size_fixture(os.path.join(HERE, "q17b_clip15s.npz"), "1.7B", 240000, 128, 128, 200, 60)
 
 
 if __name__ == "__main__":

@@ -26,9 +26,18 @@ def test_random_init_is_stable(tiny):
     cfg, sd = tiny
     w = sd["model.embed_tokens.weight"]
     assert w.shape == (2048, 128)
-    # values are bf16-representable, ~N(0, 0.02), and fixed by (seed, name)
+    # values are bf16-representable and fixed by (seed, name); the embedding is ~N(0, 0.15) with "loud" rows (x 2^level, one row in
+    # 16^level), decoder matrices ~N(0, 0.08) (o_proj 0.04), the audio tower ~N(0, 0.02) (oracle/weights.py)
     assert np.array_equal(weights.bf16_round(w), w)
-    assert abs(float(w.std()) - 0.02) < 1e-3 and abs(float(w.mean())) < 1e-3
+    lev = weights.loud_levels(20260418, "model.embed_tokens.weight", 2048)
+    assert lev.min() == 0 and lev.max() <= 4 and 0.03 < (lev >= 1).mean() < 0.1
+    quiet = w[lev == 0]
+    assert abs(float(quiet.std()) - 0.15) < 5e-3 and abs(float(quiet.mean())) < 5e-3
+    loud = w[lev == 1]
+    assert abs(float(loud.std()) - 0.30) < 3e-2
+    assert abs(float(sd["model.layers.0.mlp.up_proj.weight"].std()) - 0.08) < 3e-3
+    assert abs(float(sd["model.layers.0.self_attn.o_proj.weight"].std()) - 0.04) < 2e-3
+    assert (sd["model.layers.0.self_attn.q_norm.weight"] == 2).all() and (sd["model.layers.1.self_attn.k_norm.weight"] == 2).all()
     assert np.array_equal(weights.random_tensor(20260418, "model.embed_tokens.weight", (2048, 128)), w)
     assert not np.array_equal(weights.random_tensor(20260419, "model.embed_tokens.weight", (2048, 128)), w)
     assert (sd["model.norm.weight"] == 1).all() and (sd["audio_tower.ln_post.weight"] == 1).all()

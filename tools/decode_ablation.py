@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Timing ablation of the decode step (debug): drops one kernel of the layer at a time (Q3ASR_DEC_SKIP bit mask; results
-are wrong while a bit is set) and reports the decode-stage time per step.  Usage: python tools/decode_ablation.py [clips] [tokens] [size] [seconds]"""
+are wrong while a bit is set) and reports the decode-stage time per step.  Needs the ablation build of the library
+(`make -C qwen3-asr-swift_b200 ablation` -> lib/libq3asr_ablation.so): the shipped libq3asr.so has no such switch.
+Usage: python tools/decode_ablation.py [clips] [tokens] [size] [seconds]"""
 import os
 import sys
 
@@ -8,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "qwen3-asr-swift_b200"))
 import q3asr  # noqa: E402
+q3asr.LIB_PATH = os.path.join(os.path.dirname(q3asr.LIB_PATH), "libq3asr_ablation.so")  # before the first call loads the library
 from q3asr import synth  # noqa: E402  (input data only)
 
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
