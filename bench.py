@@ -162,6 +162,90 @@ def cpu_mel_gbs(clips):
             "sample": f"1 clip on one thread; {len(sample)} clips of {CLIP_SECONDS} s over {cores} threads (oracle/mel_oracle.c)"}
 
 
+def _bf16_ulp(x):
+    return float(np.exp2(np.floor(np.log2(max(abs(float(x)), 2.0 ** -20))) - 7))
+
+
+def parity_check(model, state_dict, clip, tokens, noise_ulps=12):
+    """The bf16-emulating CPU oracle on one clip of the workload against the GPU's ids for the same clip (the checker of tests/,
+    run here on the bench's own weights).  Free-running ids agree until the first step whose top-1 / top-2 margin is inside the
+    bf16 noise two summation orders show (tests/golden/make_golden.py); teacher-forcing the oracle's ids compares every step."""
+    from oracle import mel as omel
+    from oracle import model as omodel
+    from oracle import weights
+    orc = omodel.Oracle(weights.preset(MODEL), state_dict, emulate_bf16=True)
+    t0 = time.perf_counter()
+    enc = orc.encode(omel.mel(clip))
+    ids, tops, margins = orc.greedy(enc, tokens, stop_on_eos=False)
+    cpu_s = time.perf_counter() - t0
+    got = model.transcribe_ids([clip], max_tokens=tokens, stop_on_eos=False)[0]
+    neq = np.nonzero(got != ids)[0]
+    prefix = int(neq[0]) if neq.size else tokens
+    f_ids, f_tops = model.decode_forced(clip, ids[:-1])
+    ulps = np.array([_bf16_ulp(t) for t in tops])
+    clear = margins > noise_ulps * ulps
+    rec = {"clip_seconds": CLIP_SECONDS, "tokens": tokens, "distinct_ids": len(set(ids.tolist())),
+           "ids_equal": bool(prefix == tokens), "ids_equal_prefix": prefix,
+           "margin_ulps_at_first_mismatch": None if prefix == tokens else float(margins[prefix] / ulps[prefix]),
+           "teacher_forced_equal": int((f_ids == ids).sum()), "teacher_forced_equal_where_margin_clear": int((f_ids[clear] == ids[clear]).sum()),
+           "steps_with_clear_margin": int(clear.sum()), "noise_ulps": noise_ulps,
+           "best_logit_max_diff_ulps": float((np.abs(f_tops - tops) / ulps).max()), "oracle_seconds": cpu_s,
+           "how": "oracle/model.py (bf16-emulating restatement) vs q3asr_transcribe_ids / q3asr_decode_forced on the bench's weights"}
+    return rec
+
+
+def pool_extras(world, steps):
+    """Rank 0, after the per-rank section: what the product's own multi-GPU scheduler (q3asr_pool_*, one process, one worker thread per
+    GPU) delivers on the same box — weak and strong scaling of the headline workload, and BASELINE configs 4 and 5 (1.7B)."""
+    import q3asr
+    from q3asr import synth
+    out = {}
+    devs = tuple(range(world))
+    n30 = CLIP_SECONDS * 16000
+
+    def timed(pool, clips, tokens, per_gpu, reps):
+        pool.transcribe_ids(clips, tokens, stop_on_eos=False, max_batch_per_gpu=per_gpu)  # warm-up: buffers, graphs
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pool.transcribe_ids(clips, tokens, stop_on_eos=False, max_batch_per_gpu=per_gpu)
+        return (time.perf_counter() - t0) / reps
+
+    pool = q3asr.Pool("0.6B", devices=devs, seed=SEED)
+    try:
+        clips = [synth.clip(i, n30) for i in range(64 * world)]
+        sec = timed(pool, clips, MAX_TOKENS, 64, steps)
+        out["e2e_pool"] = {"value": len(clips) * CLIP_SECONDS / sec, "unit": UNIT, "n_gpus": world, "ms_per_step": 1000 * sec,
+                           "how": f"q3asr_pool_transcribe_ids over devices 0..{world - 1} in ONE process, {len(clips)} x {CLIP_SECONDS} s host clips, "
+                                  f"{MAX_TOKENS} tokens, 64 per GPU"}
+        per = max(1, 64 // world)
+        sec = timed(pool, clips[:64], MAX_TOKENS, per, steps)
+        out["strong_scaling"] = {"value": 64 * CLIP_SECONDS / sec, "unit": UNIT, "n_gpus": world, "clips_total": 64, "clips_per_gpu": per,
+                                 "ms_per_step": 1000 * sec,
+                                 "how": "BASELINE config 3 as written: 64 x 30 s clips in total, 64 / N per GPU, through the pool; "
+                                        "the decode step at 64 / N sequences is latency-bound, so this is far from linear by construction"}
+    finally:
+        pool.close()
+    pool = q3asr.Pool("1.7B", devices=devs, seed=SEED)
+    try:
+        clips = [synth.clip(1000 + i, 15 * 16000) for i in range(64 * world)]
+        sec = timed(pool, clips, 448, 64, 1)
+        prompt = q3asr.encoder_tokens(1500) + 16
+        kv = 64 * (prompt + 449 / 2.0) * 114688.0
+        floor_ms = (3.441e9 + kv) / (peaks()["hbm"] * 1e9) * 1000.0
+        out["config4"] = {"value": len(clips) * 15 / sec, "unit": UNIT, "n_gpus": world, "model": "1.7B", "utterances": len(clips),
+                          "utterance_seconds": 15, "max_tokens": 448, "s_per_batch": sec, "decode_step_hbm_floor_ms": floor_ms,
+                          "how": "64 concurrent 15 s utterances per GPU, paged KV, 448 greedy tokens, through the pool (host buffers in, ids out); "
+                                 "s_per_batch includes mel, encoder and prefill"}
+        clips = [synth.clip(2000 + i, n30) for i in range(15 * world)]
+        sec = timed(pool, clips, 128, 64, 1)
+        out["config5"] = {"value": len(clips) * 30 / sec, "unit": UNIT, "n_gpus": world, "model": "1.7B", "windows": len(clips),
+                          "audio_minutes": len(clips) * 0.5, "max_tokens": 128, "s_total": sec,
+                          "how": "long-form audio cut into 30 s windows (15 per GPU; 120 = 60 min at 8 GPUs), each an independent utterance"}
+    finally:
+        pool.close()
+    return out
+
+
 def workload_config(world):
     """The workload both arms name (the reference arm runs a bounded sample of it, described in its cpu_baseline.sample)."""
     return {"workload": f"Qwen3-ASR-{MODEL}: {CLIPS_PER_GPU} x {CLIP_SECONDS} s clips per GPU, mel -> encoder -> prefill -> "
@@ -207,6 +291,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the pool / strong-scaling / 1.7B sub-records")
     args = ap.parse_args()
     MODEL, CLIP_SECONDS, CLIPS_PER_GPU, MAX_TOKENS = args.model, args.clip_seconds, args.clips_per_gpu, args.max_tokens
     METRIC = f"RTFx (audio-sec/sec) Qwen3-ASR-{MODEL} batched"
@@ -328,7 +413,7 @@ def main():
             if k == "lm_head":  # one call after the prefill + one in the eager decode step
                 return v["ms"] / nprof / 2 * MAX_TOKENS
             return v["ms"] / nprof * ((MAX_TOKENS - 1) if k.startswith("dec_") else 1)
-        kernel_of = {"dec_attn": "decode_attn_mma_kernel", "mel": "mel_kernel", "dec_qkv": "gemm_skinny_kernel (dec_qkv)",
+        kernel_of = {"dec_layers": "megastep_kernel (28 decoder layers of one decode step)", "dec_attn": "decode_attn_mma_kernel", "mel": "mel_kernel", "dec_qkv": "gemm_skinny_kernel (dec_qkv)",
                      "dec_o": "gemm_skinny_kernel (dec_o)", "dec_down": "gemm_skinny_kernel (dec_down)"}
         ranked = sorted(((est_ms(k, v), k) for k, v in rep.items() if k != "decode_graph_steps" and (v["flops"] or v["bytes"])), reverse=True)
         for k in families:
@@ -351,40 +436,16 @@ def main():
                     "ms_per_launch": v["ms"] / v["launches"], "est_share_of_step": est_ms(fam, v) / (dev_ms / args.steps),
                     "algorithmic_per_launch": (v["bytes"] if hbm else v["flops"]) / v["launches"]}
 
-        roof = roof_of(ranked[0][1])  # the dominant kernel of the step (decode attention: KV-cache streaming, HBM-bound)
-        if roof["kernel"] == "decode_attn_mma_kernel":
-            # the same kernel inside the replayed CUDA graph (PDL overlap, warm instruction cache): marginal decode time with and
-            # without the attention launches, CUDA events around the decode stage
-            def decode_ms(skip):
-                os.environ["Q3ASR_DEC_SKIP"] = skip
-                model.batch_run(q3asr.STAGE_ALL, MAX_TOKENS, False)
-                model.sync()
-                model.batch_download(CLIPS_PER_GPU, MAX_TOKENS)
-                return float(model.stage_ms()[3])
-            full, without = decode_ms("0"), decode_ms("2")
-            os.environ["Q3ASR_DEC_SKIP"] = "0"
-            n_launch = (MAX_TOKENS - 1) * 28  # both model sizes have 28 decoder layers (Configuration.swift:47-100)
-            prompt = q3asr.encoder_tokens(CLIP_SECONDS * 100) + 16
-            kv_avg = CLIPS_PER_GPU * (prompt + (MAX_TOKENS + 1) / 2.0) * 4096.0  # mean K+V bytes one layer's attention reads per step
-            # The timed region replays the decode step as a CUDA graph with programmatic dependent launch, so the duration that
-            # matters is the kernel's duration THERE; a lone launch bracketed by events (no prologue overlap, launch latency inside
-            # the bracket) is kept beside it as "standalone".
-            us = (full - without) * 1000.0 / n_launch
-            roof["standalone"] = {k: roof[k] for k in ("achieved", "frac", "ms_per_launch", "algorithmic_per_launch")}
-            roof["standalone"]["how"] = "CUDA events around each eager launch in extra profiled steps (no PDL overlap)"
-            roof.update({"achieved": kv_avg / us / 1e3, "frac": kv_avg / us / 1e3 / pk["hbm"], "ms_per_launch": us / 1000.0,
-                         "algorithmic_per_launch": kv_avg, "launches_per_step": n_launch,
-                         "est_share_of_step": us * n_launch / 1000.0 / (dev_ms / args.steps),
-                         "how": "CUDA events around the decode stage of the same workload with and without the attention launches "
-                                "(Q3ASR_DEC_SKIP), difference / launches: the kernel's duration inside the replayed graph"})
-            roof["in_graph"] = {"us_per_launch": us, "achieved": roof["achieved"], "frac": roof["frac"]}
+        roof = roof_of(ranked[0][1])  # the dominant kernel of the step: the persistent decode-layers kernel (weights + KV streaming, HBM-bound)
+        roof["how"] = ("CUDA events on the library's stream around each launch of the kernel in extra profiled steps of the same workload "
+                       "(eager launches; the timed region replays the same launch inside a CUDA graph)")
         # the top dense tensor-core family (encoder / prefill GEMMs and convolutions; the decode-step products are weight streaming)
         tens = [k for _, k in ranked if rep[k]["flops"] > 0 and not k.startswith("dec_") and k != "lm_head" and not k.endswith("attn")]
         roof_gemm = roof_of(tens[0]) if tens else None
         roof_mel = roof_of("mel") if "mel" in rep else None
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = model.state_dict()  # the same bf16 weights, read back through the C ABI
         n_cpu = 1  # one clip of the workload with the full decode length: 10-30 s on the box's host cores
@@ -392,7 +453,17 @@ def main():
         sec = once()
         cpu = {"value": n_cpu * CLIP_SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" ({sec:.1f} s of CPU time)",
                "mel": cpu_mel_gbs(clips)}
+        parity = parity_check(model, sd, clips[0], MAX_TOKENS)
     model.close()
+    extras = None
+    if not args.no_extras:
+        barrier()  # every rank has released its handle; rank 0 now drives all N GPUs from one process
+        if rank == 0:
+            try:
+                extras = pool_extras(world, max(1, min(args.steps, 3)))
+            except Exception as e:  # the headline line must still be printed
+                extras = {"error": repr(e)}
+        barrier()
 
     if rank == 0:
         line = {
@@ -404,8 +475,10 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_pipelined": e2e_pipe,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_mel": roof_mel, "kernel_families": families,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity": parity,
         }
+        if extras:
+            line.update(extras)
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

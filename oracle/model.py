@@ -270,12 +270,12 @@ class Oracle:
 
     def greedy(self, audio_embeds, max_tokens, stop_on_eos=True, forced=None, context=None, language=None):
         """Qwen3ASR.swift:317-390.  forced: optional token stream fed instead of the argmax (teacher forcing).
-        Returns (ids, top1 logit per step, top1-top2 margin per step); self.runner_up holds the id of the second-best logit of
-        every step (lowest index among equals, after excluding the winner)."""
+        Returns (ids, top1 logit per step, top1-top2 margin per step); self.topk_ids / self.topk_vals hold the four best bf16
+        logits of every step (tests accept a deviation only towards a candidate within the stated noise bound of the best)."""
         E = self.w["model.embed_tokens.weight"]
         logits, cache, _ = self.prefill(audio_embeds, context, language)
         ids, tops, margins = [], [], []
-        self.runner_up = []
+        self.topk_ids, self.topk_vals = [], []
         steps = max_tokens if forced is None else len(forced) + 1
         for step in range(steps):
             top2 = torch.topk(logits, 2)
@@ -286,10 +286,9 @@ class Oracle:
             ids.append(best)
             tops.append(mx)
             margins.append(float(top2.values[0] - top2.values[1]))
-            second = float(top2.values[1])
-            cand2 = torch.nonzero(logits == second).flatten()
-            cand2 = cand2[cand2 != best]
-            self.runner_up.append(int(cand2.min()) if cand2.numel() else best)
+            top4 = torch.topk(logits, 4)
+            self.topk_ids.append(top4.indices.numpy().astype(np.int32))
+            self.topk_vals.append(top4.values.numpy().astype(np.float32))
             if forced is None and stop_on_eos and best == self.cfg["tok_eos"]:
                 break
             if step + 1 == steps:

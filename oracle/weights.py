@@ -86,7 +86,7 @@ def random_tensor(seed, name, shape, scale=None):
         z = _splitmix_vec(np.uint64(s) + np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
     m = np.uint64(0xFFFF)
     tot = ((z & m) + ((z >> np.uint64(16)) & m) + ((z >> np.uint64(32)) & m) + (z >> np.uint64(48))).astype(np.int64) - 131070
-    mult = np.float32(float(scale) / 37837.22668596909)
+    mult = np.float32(float(np.float32(scale)) / 37837.22668596909)  # the C side divides (double)(float)scale
     out = bf16_round(tot.astype(np.float32) * mult).reshape(shape)
     if name == EMBED:
         out = out * np.exp2(loud_levels(seed, name, shape[0])).astype(np.float32)[:, None]

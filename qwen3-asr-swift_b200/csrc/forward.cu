@@ -438,6 +438,13 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
     }
 }
 
+// RAII: kernels launched while this is alive may overlap their prologue with the previous kernel's tail (PDL)
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
+    ~PdlScope() { pdl_enabled() = prev; }
+};
+
 // Decode step for B <= SKINNY_MAX_ROWS sequences: weight-streaming split-K GEMMs (skinny.cuh) whose fp32 partials are
 // consumed by fused kernels — 7 launches per layer.  On entry bs->dx holds the new token embeddings; on exit bs->dlast
 // holds the final-norm hidden states (the LM-head input).
@@ -464,6 +471,14 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         ProfScope ps(h, "dec_norm", 0, 4.0 * B * H);
         rmsnorm_launch(x, m.dec[0].in_ln, xn, B, H, c.dec_rms_eps, nullptr, st);
         h->launches++;
+    }
+    if (bs->mega_ready) {  // all layers in one persistent kernel (megastep.cuh); the loop below is the multi-kernel path it replaces
+        PdlScope no_pdl(false);
+        // algorithmic bytes of the launch: every layer's weights once + the keys and values its attention reads
+        const double w_bytes = 2.0 * ((double)H * nqkv + (double)nq * H + 3.0 * H * c.dec_inter);
+        ProfScope ps(h, "dec_layers", 2.0 * B * c.dec_layers * w_bytes / 2.0, c.dec_layers * (w_bytes + kv_bytes));
+        megastep_launch(h, bs);
+        return;
     }
     for (int l = 0; l < c.dec_layers; l++) {
         const DecLayerW& w = m.dec[l];
@@ -605,13 +620,6 @@ void run_prefill(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     bs->steps_done = 1;
 }
 
-// RAII: kernels launched while this is alive may overlap their prologue with the previous kernel's tail (PDL)
-struct PdlScope {
-    bool prev;
-    explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
-    ~PdlScope() { pdl_enabled() = prev; }
-};
-
 void decode_step_kernels(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
@@ -636,6 +644,9 @@ void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool
     const bool use_graph = env_int("Q3ASR_NO_GRAPH", 0) == 0;
     int* h_active = reinterpret_cast<int*>(bs->h_out.p);
     int step = bs->steps_done;
+    bs->mega_ready = false;
+    if (bs->B <= SKINNY_MAX_ROWS && h->cfg.dec_heads == 2 * h->cfg.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0 && megastep_supported(h, bs))
+        megastep_prepare(h, bs);
     if (step < max_tokens) {  // one eager step: sets function attributes, warms the instruction cache
         decode_step_kernels(h, bs, stop_on_eos, forced);
         step++;

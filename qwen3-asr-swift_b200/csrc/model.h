@@ -2,6 +2,7 @@
 #pragma once
 #include "gemm.cuh"
 #include "handle.h"
+#include "megastep_params.h"
 #include "ops.cuh"
 
 namespace q3 {
@@ -84,6 +85,11 @@ struct BatchState {
            o_ident = 0, o_pos0 = 0;
     DevBuf a1, a2, a3, ex, exn, eqkv, eatt, effn, audio;        // encoder activations
     DevBuf dx, dxn, dqkv, dq, dkc, datt, dact, dlast, dws; // decoder activations (dws: fp32 split-K partials of the decode step)
+    DevBuf mega_tab, dws2, mega_trace;   // persistent decode-step kernel (megastep.cu): tables + the second sub-batch's split-K partials
+    HostBuf h_mega;
+    MegaParams mega;
+    int mega_nb = 0, mega_gu = 0;
+    bool mega_ready = false;
     DevBuf kv_pool, rope_tab, page_tab;  // page_tab: [B][pages_per_seq] (plan_pages)
     int rope_n = 0;          // positions tabulated in rope_tab
     DevBuf amax_val, amax_idx, logits, logits_bf;
@@ -99,7 +105,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &kv_pool, &rope_tab, &page_tab, &amax_val, &amax_idx, &logits, &logits_bf,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &page_tab, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }
@@ -109,10 +115,16 @@ struct BatchState {
         h_ints.release();
         h_out.release();
         h_pages.release();
+        h_mega.release();
         if (step_graph) cudaGraphExecDestroy(step_graph);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
     }
 };
+
+// persistent decode-step kernel (megastep.cu)
+bool megastep_supported(const Handle* h, const BatchState* bs);
+void megastep_prepare(Handle* h, BatchState* bs);
+void megastep_launch(Handle* h, BatchState* bs);
 
 }  // namespace q3

@@ -10,12 +10,22 @@ q06b_ragged.npz     (--big) 0.6B, a 17.3 s clip (1730 frames: ragged last chunk,
 q17b_clip15s.npz    (--big) Qwen3-ASR-1.7B dims, one 15 s clip (BASELINE config 4's shape): the same contents as q06b_clip30s
 The reference itself cannot be imported (Swift + MLX); these are outputs of the restatement in oracle/.
 
-A full-size fixture is only written when its free-running ids are a meaningful parity target: at least
-32 distinct tokens among the 128, at least 90 % of the steps with a top-1/top-2 margin above two bf16 ulps of the best logit,
-and ids that a second accumulation order reproduces exactly (the oracle run again with float64 accumulation in the decoder:
-a clip whose ids hinge on an exact bf16 tie of the two best logits fails this).  Clips are screened in index order until one
-passes; the chosen index is stored in the fixture, with the runner-up id of every step (a test may only accept a deviation
-at a step whose margin is at most one ulp, and only towards the runner-up).
+Two correct bf16 implementations of a 28-layer decoder do not produce bit-identical logits: every op rounds its output to
+bf16, a different fp32 summation order moves a few values across a rounding boundary, and the flips spread.  Measured here with
+the oracle itself (the decoder run again with float64 accumulation, same rounding points): final hidden states differ by 1-4 %
+in relative L2 and the best logit by up to ~8 bf16 ulps, for these weights and equally for the plain 0.02-scaled ones.  Greedy ids
+are therefore bit-exact between implementations only where the top-1 / top-2 margin exceeds that noise.  NOISE_ULPS = 24 (2.4 x the
+largest deviation measured between the two CPU runs, 10 ulps; the B200 kernels against this oracle: median 3, 90th percentile 8-10,
+largest 14-34 ulps, every argmax disagreement at a margin of at most 16 ulps — tools/parity_diag.py) is the bound the tests use.
+
+A full-size fixture is only written when its ids are a meaningful parity target: at least 32 distinct
+tokens among the 128 free-running ids, at least 90 % of the steps with a margin above two bf16 ulps and at least 35 % above
+NOISE_ULPS (those steps are strict equality checks in the tests; on the rest the implementation under test must pick one of the
+oracle's four best tokens whose logit is within NOISE_ULPS of the best, and may differ from the oracle's id on at most 15 % of
+all steps).  The fixture also holds the full-vocabulary logits of the prefill position from the bf16-emulating and from the plain
+fp32 oracle: the tests require the kernels to be as close to the fp32 model as the bf16 restatement is (a noise-calibrated bound).  Clips are screened in index order until one passes.
+Each fixture also records how many leading ids the float64-accumulation run shares with the fp32 one (`cpu_cpu_prefix`): the
+length over which free-running ids are determined by the arithmetic contract at all.
 """
 import os
 import sys
@@ -43,14 +53,17 @@ def to_bf16_bits(x):
     return (np.ascontiguousarray(weights.bf16_round(x), dtype=np.float32).view(np.uint32) >> 16).astype(np.uint16)
 
 
+NOISE_ULPS = 24
+
+
 def margin_report(ids, tops, margins):
     ulp = bf16_ulp(tops)
-    return dict(distinct=len(set(ids.tolist())), frac_gt2=float((margins > 2 * ulp).mean()), n_le1=int((margins <= ulp).sum()),
-                min_margin_ulps=float((margins / ulp).min()))
+    return dict(distinct=len(set(ids.tolist())), frac_gt2=float((margins > 2 * ulp).mean()),
+                frac_gt_noise=float((margins > NOISE_ULPS * ulp).mean()), median_margin_ulps=float(np.median(margins / ulp)))
 
 
 def acceptable(rep, n):
-    return rep["distinct"] >= min(32, n // 4) and rep["frac_gt2"] >= 0.9 and rep["n_le1"] <= n // 10
+    return rep["distinct"] >= min(32, n // 4) and rep["frac_gt2"] >= 0.9 and rep["frac_gt_noise"] >= 0.35
 
 
 def full_size_fixture(path, preset, n_samples, n_free, n_forced, first_clip, max_trials, fp32_weights_too=True):
@@ -67,30 +80,39 @@ def full_size_fixture(path, preset, n_samples, n_free, n_forced, first_clip, max
         enc = orc.encode(feats)
         ids, tops, margins = orc.greedy(enc, n_free, stop_on_eos=False)
         rep = margin_report(ids, tops, margins)
-        runner = np.array(orc.runner_up, dtype=np.int32)
+        tk_ids, tk_vals = np.stack(orc.topk_ids), np.stack(orc.topk_vals)
         print(f"  clip {clip}: {rep}", flush=True)
-        if not acceptable(rep, n_free):
-            continue
-        ids64 = orc64.greedy(enc, n_free, stop_on_eos=False)[0]
-        same = int((ids64 == ids).sum()) if ids64.shape == ids.shape else -1
-        print(f"    float64 accumulation: {same} of {n_free} ids equal", flush=True)
-        if same == n_free:
+        if acceptable(rep, n_free):
             chosen = clip
             break
     assert chosen is not None, "no clip passed the screening: widen max_trials"
+    # the same decode with float64 accumulation: how far two CPU summation orders agree, and how far apart their logits are
+    ids64, tops64, _ = orc64.greedy(enc, n_free, stop_on_eos=False)
+    neq = np.nonzero(ids64 != ids)[0]
+    prefix = int(neq[0]) if neq.size else n_free
+    f64 = orc64.greedy(enc, 0, forced=ids[:-1])  # teacher-forced on the fp32 run's ids: logits of the same contexts
+    noise = float((np.abs(f64[1] - tops) / bf16_ulp(tops)).max())
+    print(f"    float64 accumulation: first {prefix} of {n_free} free-running ids equal; teacher-forced best logit differs by up to "
+          f"{noise:.1f} ulp, {int((f64[0] != ids).sum())} of {n_free} argmax differ", flush=True)
     out = dict(seed=SEED, clip_index=chosen, n_samples=n_samples, encoder_bf16=to_bf16_bits(enc), ids=ids, tops=tops, margins=margins,
-               runner_up=runner)
+               topk_ids=tk_ids, topk_vals=tk_vals, cpu_cpu_prefix=prefix, cpu_cpu_noise_ulps=noise, noise_ulps=NOISE_ULPS)
     if n_forced:
         forced = np.random.default_rng(1000 + chosen).integers(0, cfg["dec_vocab"] - 2000, size=n_forced).astype(np.int32)
         fids, ftops, fmargins = orc.greedy(enc, 0, forced=forced)
-        frunner = np.array(orc.runner_up, dtype=np.int32)
+        ftk_ids, ftk_vals = np.stack(orc.topk_ids), np.stack(orc.topk_vals)
         frep = margin_report(fids, ftops, fmargins)
-        print(f"  teacher-forced: {frep}", flush=True)
-        assert frep["n_le1"] <= n_forced // 10, frep
-        out.update(forced=forced, forced_ids=fids, forced_tops=ftops, forced_margins=fmargins, forced_runner_up=frunner)
-    if fp32_weights_too:  # the reference's encoder runs in fp32 on an fp32 mel: the plain fp32 oracle states the bf16 tolerance
-        o32 = omodel.Oracle(cfg, sd, emulate_bf16=False)
-        out["encoder_fp32_as_bf16"] = to_bf16_bits(o32.encode(feats))
+        print(f"  teacher-forced on a pseudo-random stream: {frep}", flush=True)
+        assert frep["frac_gt_noise"] >= 0.3, frep
+        out.update(forced=forced, forced_ids=fids, forced_tops=ftops, forced_margins=fmargins, forced_topk_ids=ftk_ids,
+                   forced_topk_vals=ftk_vals)
+    # the reference's encoder runs in fp32 on an fp32 mel: the plain fp32 oracle states the bf16 tolerance, for the encoder states and
+    # for the logits of the prefill position (stored as float16: 300 KB)
+    o32 = omodel.Oracle(cfg, sd, emulate_bf16=False)
+    enc32 = o32.encode(feats)
+    if fp32_weights_too:
+        out["encoder_fp32_as_bf16"] = to_bf16_bits(enc32)
+    out["prefill_logits_fp32"] = o32.prefill(enc32)[0].numpy().astype(np.float16)
+    out["prefill_logits_bf16emu"] = orc.prefill(enc)[0].numpy().astype(np.float16)
     np.savez_compressed(path, **out)
     print(f"  wrote {os.path.basename(path)} ({os.path.getsize(path) / 1e6:.2f} MB) ids[:16] {ids[:16].tolist()}", flush=True)
 
