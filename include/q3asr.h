@@ -227,6 +227,11 @@ int q3asr_timer_elapsed_ms(q3asr_handle* h, int slot_a, int slot_b, float* ms);
 int q3asr_stage_ms(q3asr_handle* h, float* ms4);
 /* kernels launched by this handle so far */
 uint64_t q3asr_launch_count(const q3asr_handle* h);
+/* the decode loop of the last q3asr_batch_run / q3asr_transcribe_ids*: out4 = {decode steps run, sum over the steps of the rows
+ * decoded in that step, compactions of the decode batch, rows at the end}.  With stop_on_eos the finished utterances leave the
+ * decode batch (the reference stops each utterance at EOS, Qwen3ASR.swift:378-379), so row-steps follow the tokens actually
+ * generated instead of batch x longest utterance. */
+int q3asr_decode_stats(const q3asr_handle* h, uint64_t* out4);
 /* per-kernel-family device timing (CUDA events around tagged launches of the encoder / prefill / decode stages).
  * report: one line per tag "tag,launches,total_ms,algorithmic_flops,algorithmic_bytes"; reading it resets the log. */
 int q3asr_profile(q3asr_handle* h, int enable);

@@ -270,7 +270,7 @@ class Oracle:
 
     def greedy(self, audio_embeds, max_tokens, stop_on_eos=True, forced=None, context=None, language=None):
         """Qwen3ASR.swift:317-390.  forced: optional token stream fed instead of the argmax (teacher forcing).
-        Returns (ids, top1 logit per step, top1-top2 margin per step); self.topk_ids / self.topk_vals hold the four best bf16
+        Returns (ids, top1 logit per step, top1-top2 margin per step); self.topk_ids / self.topk_vals hold the best bf16
         logits of every step (tests accept a deviation only towards a candidate within the stated noise bound of the best)."""
         E = self.w["model.embed_tokens.weight"]
         logits, cache, _ = self.prefill(audio_embeds, context, language)
@@ -286,7 +286,7 @@ class Oracle:
             ids.append(best)
             tops.append(mx)
             margins.append(float(top2.values[0] - top2.values[1]))
-            top4 = torch.topk(logits, 4)
+            top4 = torch.topk(logits, 8)
             self.topk_ids.append(top4.indices.numpy().astype(np.int32))
             self.topk_vals.append(top4.values.numpy().astype(np.float32))
             if forced is None and stop_on_eos and best == self.cfg["tok_eos"]:

@@ -381,6 +381,15 @@ uint64_t q3asr_launch_count(const q3asr_handle* h) {
     if (h == nullptr) return 0;
     return h->h.launches + (gemm_launch_count() - h->h.gemm_base);
 }
+int q3asr_decode_stats(const q3asr_handle* h, uint64_t* out4) {
+    if (h == nullptr || out4 == nullptr) return Q3ASR_ERR_INVALID;
+    const BatchState* bs = h->h.batch.get();
+    out4[0] = bs ? bs->stat_steps : 0;
+    out4[1] = bs ? bs->stat_row_steps : 0;
+    out4[2] = bs ? bs->stat_compactions : 0;
+    out4[3] = bs ? (uint64_t)bs->dec_rows : 0;
+    return Q3ASR_OK;
+}
 int q3asr_profile(q3asr_handle* h, int enable) {
     return guarded(h, [&](Handle& x) {
         Q3_CUDA(cudaStreamSynchronize(x.stream));

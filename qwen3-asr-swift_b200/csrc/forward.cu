@@ -166,6 +166,8 @@ void plan_pages(Handle* h, BatchState* bs, int max_tokens) {
     bs->pages_per_seq = (bs->max_prompt + max_tokens + KV_PAGE - 1) / KV_PAGE;
     const size_t n = (size_t)bs->B * bs->pages_per_seq;
     bs->page_tab.reserve(n * sizeof(int));
+    bs->page_tab2.reserve(n * sizeof(int));  // target of the next compaction of the decode rows
+    bs->page_cur = 0;
     bs->h_pages.reserve(n * sizeof(int));
     int* t = bs->h_pages.as<int>();
     for (size_t i = 0; i < n; i++) t[i] = (int)i;
@@ -241,6 +243,7 @@ void reserve_decoder(Handle* h, BatchState* bs) {
     bs->st_out_val.reserve(B * mt * 4);
     bs->st_out_len.reserve(B * 4);
     bs->st_finished.reserve(B * 4);
+    bs->st_slot_seq.reserve(B * 4);
     bs->st_scalars.reserve(64);
     bs->h_out.reserve(B * mt * 8 + B * 8 + 64);
 }
@@ -374,7 +377,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
 KvCache kv_cache(Handle* h, BatchState* bs) {
     KvCache kc;
     kc.pool = bs->kv_pool.as<bf16>();
-    kc.page_table = bs->page_tab.as<int>();
+    kc.page_table = (bs->page_cur ? bs->page_tab2 : bs->page_tab).as<int>();
     kc.max_pages = bs->pages_per_seq;
     kc.layers = h->cfg.dec_layers;
     kc.kv_heads = h->cfg.dec_kv_heads;
@@ -452,7 +455,7 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
-    const int B = bs->B;
+    const int B = bs->dec_rows;  // decode rows: the sequences still active
     const int H = c.dec_hidden, hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
     const float scale = 1.0f / sqrtf((float)hd);
     bf16 *x = bs->dx.as<bf16>(), *xn = bs->dxn.as<bf16>(), *att = bs->datt.as<bf16>(), *act = bs->dact.as<bf16>();
@@ -529,7 +532,7 @@ void lm_head_argmax(Handle* h, BatchState* bs, const int* row_index, bool normed
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
-    const int H = c.dec_hidden, B = bs->B;
+    const int H = c.dec_hidden, B = bs->prefill_done ? bs->dec_rows : bs->B;
     ProfScope ps(h, "lm_head", 2.0 * B * (double)H * c.dec_vocab, 2.0 * H * c.dec_vocab);
     if (!normed) {
         rmsnorm_launch(bs->dx.as<bf16>(), m.final_norm, bs->dlast.as<bf16>(), B, H, c.dec_rms_eps, row_index, st);
@@ -583,6 +586,7 @@ DecodeState decode_state(Handle* h, BatchState* bs, int stop_on_eos, bool forced
     s.finished = bs->st_finished.as<int>();
     s.n_active = bs->st_scalars.as<int>();
     s.step = bs->st_scalars.as<int>() + 1;
+    s.slot_seq = bs->slot_map_on ? bs->st_slot_seq.as<int>() : nullptr;
     s.forced = forced ? bs->st_forced.as<int32_t>() : nullptr;
     s.max_tokens = bs->max_tokens;
     s.eos = h->cfg.tok_eos;
@@ -596,6 +600,8 @@ void run_prefill(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     cudaStream_t st = h->stream;
     const int* ints = bs->ints.as<int>();
     const int B = bs->B;
+    if (bs->page_cur != 0 || bs->stat_compactions != 0) plan_pages(h, bs, bs->max_tokens);  // a previous run of this batch compacted its rows
+    bs->dec_rows = B;
     embed_splice_launch(ints + bs->o_ids, ints + bs->o_audio_src, m.embed, bs->audio.as<bf16>(), bs->dx.as<bf16>(), bs->R, c.dec_hidden,
                         st);
     h->launches++;
@@ -605,6 +611,10 @@ void run_prefill(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
     Q3_CUDA(cudaMemcpyAsync(bs->st_kv_len.p, ints + bs->o_seq_len, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
     Q3_CUDA(cudaMemsetAsync(bs->st_out_len.p, 0, sizeof(int) * B, st));
     Q3_CUDA(cudaMemsetAsync(bs->st_finished.p, 0, sizeof(int) * B, st));
+    Q3_CUDA(cudaMemcpyAsync(bs->st_slot_seq.p, ints + bs->o_ident, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    bs->dec_rows = B;
+    bs->slot_map_on = false;
+    bs->stat_row_steps = bs->stat_steps = bs->stat_compactions = 0;
     Q3_CUDA(cudaMemsetAsync(bs->st_out_ids.p, 0, sizeof(int32_t) * B * std::max(bs->max_tokens, 1), st));
     const int scal[2] = {B, 0};
     memcpy(bs->h_out.p, scal, sizeof(scal));
@@ -625,81 +635,124 @@ void decode_step_kernels(Handle* h, BatchState* bs, int stop_on_eos, bool forced
     const Model& m = *h->model;
     cudaStream_t st = h->stream;
     // the first kernel of a step is fully serialised against the previous step; the rest chain programmatically
-    embed_splice_launch(bs->st_cur_tok.as<int32_t>(), nullptr, m.embed, nullptr, bs->dx.as<bf16>(), bs->B, c.dec_hidden, st);
+    const int rows = bs->dec_rows;
+    embed_splice_launch(bs->st_cur_tok.as<int32_t>(), nullptr, m.embed, nullptr, bs->dx.as<bf16>(), rows, c.dec_hidden, st);
     h->launches++;
     PdlScope pdl(env_int("Q3ASR_NO_PDL", 0) == 0 && !h->prof_on);
-    if (bs->B <= SKINNY_MAX_ROWS && c.dec_heads == 2 * c.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0) {
+    if (rows <= SKINNY_MAX_ROWS && c.dec_heads == 2 * c.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0) {
         decoder_layers_decode(h, bs);
         lm_head_argmax(h, bs, nullptr, true);
     } else {
-        decoder_layers(h, bs, bs->B, false);
+        decoder_layers(h, bs, rows, false);
         lm_head_argmax(h, bs, nullptr);
     }
-    decode_advance_launch(decode_state(h, bs, stop_on_eos, forced), bs->B, st);
+    decode_advance_launch(decode_state(h, bs, stop_on_eos, forced), rows, st);
     h->launches++;
+}
+
+// Captures one decode step for the current decode rows into bs->step_graph; returns the launches one replay stands for.
+unsigned long long capture_step_graph(Handle* h, BatchState* bs, int stop_on_eos, bool forced) {
+    cudaStream_t st = h->stream;
+    if (bs->step_graph) {  // the graph bakes in buffer addresses, row counts and flags: rebuilt per batch and per compaction (~1 ms)
+        cudaGraphExecDestroy(bs->step_graph);
+        bs->step_graph = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long l0 = h->launches, g0 = gemm_launch_count();
+    const bool prof_was = h->prof_on;
+    h->prof_on = false;  // event records inside a captured graph cannot be read back per replay
+    Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+        decode_step_kernels(h, bs, stop_on_eos, forced);
+    } catch (...) {
+        h->prof_on = prof_was;
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    Q3_CUDA(cudaStreamEndCapture(st, &graph));
+    h->prof_on = prof_was;
+    const unsigned long long gper = gemm_launch_count() - g0;  // captured, not executed
+    const unsigned long long per_step = (h->launches - l0) + gper;
+    h->launches = l0;
+    h->gemm_base += gper;
+    Q3_CUDA(cudaGraphInstantiate(&bs->step_graph, graph, 0));
+    Q3_CUDA(cudaGraphDestroy(graph));
+    bs->graph_B = bs->dec_rows;
+    return per_step;
+}
+
+bool mega_wanted(Handle* h, BatchState* bs) {
+    return bs->dec_rows <= SKINNY_MAX_ROWS && h->cfg.dec_heads == 2 * h->cfg.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0 &&
+           megastep_supported(h, bs);
+}
+
+// Takes the finished sequences out of the decode rows (continuous-batching half of the scheduler: the reference stops an
+// utterance at EOS, Qwen3ASR.swift:378-379; here its KV pages and its column of every product stop being streamed).
+// n_active: the number of unfinished sequences the host has just read back.
+void compact_decode_rows(Handle* h, BatchState* bs, int n_active) {
+    cudaStream_t st = h->stream;
+    int* cur = (bs->page_cur ? bs->page_tab2 : bs->page_tab).as<int>();
+    int* nxt = (bs->page_cur ? bs->page_tab : bs->page_tab2).as<int>();
+    decode_compact_launch(bs->dec_rows, bs->st_finished.as<int>(), bs->st_slot_seq.as<int>(), bs->st_cur_tok.as<int32_t>(), bs->st_pos.as<int>(),
+                          bs->st_kv_len.as<int>(), cur, nxt, bs->pages_per_seq, st);
+    h->launches++;
+    bs->page_cur ^= 1;
+    bs->slot_map_on = true;
+    bs->dec_rows = n_active;
+    bs->stat_compactions++;
+    if (bs->mega_ready) megastep_prepare(h, bs);
 }
 
 void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool forced) {
     cudaStream_t st = h->stream;
     const bool use_graph = env_int("Q3ASR_NO_GRAPH", 0) == 0;
+    // rows are compacted when a quarter of them has finished (and at least four): each compaction costs a graph capture (~1 ms),
+    // each finished row a share of the step's KV and activation traffic.  Not with the decoder knobs (the sampler indexes the
+    // generated ids by row) nor when teacher forcing.
+    const bool may_compact = stop_on_eos && !forced && !bs->sampler_on && env_int("Q3ASR_NO_COMPACT", 0) == 0;
     int* h_active = reinterpret_cast<int*>(bs->h_out.p);
     int step = bs->steps_done;
     bs->mega_ready = false;
-    if (bs->B <= SKINNY_MAX_ROWS && h->cfg.dec_heads == 2 * h->cfg.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0 && megastep_supported(h, bs))
-        megastep_prepare(h, bs);
+    if (mega_wanted(h, bs)) megastep_prepare(h, bs);
+    auto account = [&]() { bs->stat_steps++; bs->stat_row_steps += (unsigned long long)bs->dec_rows; };
+    // after every 16th step with stop_on_eos: how many sequences are still active?  Returns false when the batch is done.
+    auto poll = [&](bool* recapture) {
+        Q3_CUDA(cudaMemcpyAsync(h_active, bs->st_scalars.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        Q3_CUDA(cudaStreamSynchronize(st));
+        const int n = *h_active;
+        if (n <= 0) return false;
+        if (may_compact && n < bs->dec_rows && bs->dec_rows - n >= std::max(4, bs->dec_rows / 4)) {
+            compact_decode_rows(h, bs, n);
+            *recapture = true;
+        }
+        return true;
+    };
     if (step < max_tokens) {  // one eager step: sets function attributes, warms the instruction cache
         decode_step_kernels(h, bs, stop_on_eos, forced);
+        account();
         step++;
     }
     if (step < max_tokens && use_graph) {
-        if (bs->step_graph && bs->graph_B != bs->B) {
-            cudaGraphExecDestroy(bs->step_graph);
-            bs->step_graph = nullptr;
-        }
-        // the graph bakes in buffer addresses and flags; rebuild it for every batch (cheap: ~1 ms)
-        if (bs->step_graph) {
-            cudaGraphExecDestroy(bs->step_graph);
-            bs->step_graph = nullptr;
-        }
-        cudaGraph_t graph = nullptr;
-        const unsigned long long l0 = h->launches, g0 = gemm_launch_count();
-        const bool prof_was = h->prof_on;
-        h->prof_on = false;  // event records inside a captured graph cannot be read back per replay
-        Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        try {
-            decode_step_kernels(h, bs, stop_on_eos, forced);
-        } catch (...) {
-            h->prof_on = prof_was;
-            cudaStreamEndCapture(st, &graph);
-            if (graph) cudaGraphDestroy(graph);
-            throw;
-        }
-        Q3_CUDA(cudaStreamEndCapture(st, &graph));
-        h->prof_on = prof_was;
-        const unsigned long long gper = gemm_launch_count() - g0;  // captured, not executed
-        const unsigned long long per_step = (h->launches - l0) + gper;
-        h->launches = l0;
-        h->gemm_base += gper;
-        Q3_CUDA(cudaGraphInstantiate(&bs->step_graph, graph, 0));
-        Q3_CUDA(cudaGraphDestroy(graph));
-        bs->graph_B = bs->B;
+        unsigned long long per_step = capture_step_graph(h, bs, stop_on_eos, forced);
         ProfScope ps(h, "decode_graph_steps", 0, 0);
         for (; step < max_tokens; step++) {
             Q3_CUDA(cudaGraphLaunch(bs->step_graph, st));
             h->launches += per_step;
+            account();
             if (stop_on_eos && (step & 15) == 15) {
-                Q3_CUDA(cudaMemcpyAsync(h_active, bs->st_scalars.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                Q3_CUDA(cudaStreamSynchronize(st));
-                if (*h_active <= 0) { step++; break; }
+                bool recapture = false;
+                if (!poll(&recapture)) { step++; break; }
+                if (recapture && step + 1 < max_tokens) per_step = capture_step_graph(h, bs, stop_on_eos, forced);
             }
         }
     } else {
         for (; step < max_tokens; step++) {
             decode_step_kernels(h, bs, stop_on_eos, forced);
+            account();
             if (stop_on_eos && (step & 15) == 15) {
-                Q3_CUDA(cudaMemcpyAsync(h_active, bs->st_scalars.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                Q3_CUDA(cudaStreamSynchronize(st));
-                if (*h_active <= 0) { step++; break; }
+                bool recapture = false;
+                if (!poll(&recapture)) { step++; break; }
             }
         }
     }

@@ -16,7 +16,9 @@ namespace {
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
-std::atomic<unsigned long long> g_launches{0};
+// per host thread: a handle is driven by one thread (pool workers each own theirs), so differencing the counter around a region
+// (forward.cu: the captured decode step) counts that handle's launches only
+thread_local unsigned long long g_launches = 0;
 
 void make_tmap(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr) {
@@ -344,7 +346,7 @@ void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const Gemm
     gemm_conv(a, s, W, N, e, st, simt, bn);
 }
 
-unsigned long long gemm_launch_count() { return g_launches.load(); }
+unsigned long long gemm_launch_count() { return g_launches; }
 
 // ------------------------------------------------------------------------------------------
 // decode-step weight-streaming GEMM

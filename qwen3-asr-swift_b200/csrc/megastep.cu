@@ -70,7 +70,7 @@ bool megastep_supported(const Handle* h, const BatchState* bs) {
     const char* env = getenv("Q3ASR_MEGA");
     if (!(env && atoi(env) != 0)) return false;
     const int gu = gu_bn_for(c, h->num_sms);
-    return bs->B >= 1 && bs->B <= SKINNY_MAX_ROWS && c.dec_head_dim == 128 && c.dec_heads == 2 * c.dec_kv_heads &&
+    return bs->dec_rows >= 1 && bs->dec_rows <= SKINNY_MAX_ROWS && c.dec_head_dim == 128 && c.dec_heads == 2 * c.dec_kv_heads &&
            c.dec_hidden % 1024 == 0 && c.dec_hidden <= 2048 && c.dec_inter % 64 == 0 && (gu == 64 || gu == 128) &&
            (2 * c.dec_inter) % gu == 0 && h->num_sms >= 64;
 }
@@ -80,7 +80,7 @@ bool megastep_supported(const Handle* h, const BatchState* bs) {
 void megastep_prepare(Handle* h, BatchState* bs) {
     const q3asr_config& c = h->cfg;
     const Model& m = *h->model;
-    const int B = bs->B, H = c.dec_hidden, hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
+    const int B = bs->dec_rows, H = c.dec_hidden, hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
     const int L = c.dec_layers, G = h->num_sms;
     MegaParams& P = bs->mega;
     memset(&P, 0, sizeof(P));
@@ -93,7 +93,9 @@ void megastep_prepare(Handle* h, BatchState* bs) {
     P.n_phases = L * 7 * P.n_sub;
     P.H = H; P.nq = nq; P.nkv = nkv; P.nqkv = nqkv; P.inter = c.dec_inter; P.heads = c.dec_heads; P.kv_heads = c.dec_kv_heads;
     const int items = P.sub[0].rows * c.dec_kv_heads;
-    P.nw_attn = items <= G ? 8 : items <= 2 * G ? 4 : 2;
+    // 2 or 8 warps per (sequence, kv head) only: those are the groupings whose fold order equals the canonical stream tree of
+    // decode_attn_mma_kernel (four warps would fold s0+s4 before s2: a different fp32 order, i.e. ids that depend on the batch size)
+    P.nw_attn = items <= G ? 8 : 2;
     P.eps = c.dec_rms_eps;
     P.scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
     bs->mega_nb = nb_for(P.sub[0].rows);
@@ -187,7 +189,7 @@ void megastep_prepare(Handle* h, BatchState* bs) {
     P.kv_len = bs->st_kv_len.as<int>();
     P.rope_tab = bs->rope_tab.as<float2>();
     P.cache.pool = bs->kv_pool.as<bf16>();
-    P.cache.page_table = bs->page_tab.as<int>();
+    P.cache.page_table = (bs->page_cur ? bs->page_tab2 : bs->page_tab).as<int>();
     P.cache.max_pages = bs->pages_per_seq;
     P.cache.layers = c.dec_layers;
     P.cache.kv_heads = c.dec_kv_heads;

@@ -26,7 +26,7 @@ struct MegaSub {
 struct MegaParams {
     int G, n_phases, layers, n_sub;
     int H, nq, nkv, nqkv, inter, heads, kv_heads;
-    int nw_attn;   // warps per attention item: 2, 4 or 8
+    int nw_attn;   // warps per attention item: 2 or 8 (the groupings that reproduce the canonical stream merge order)
     int sg1, sg2;  // split groups of the two reduce phases (the summation order of reduce_resid_rmsnorm_kernel)
     float eps, scale_log2;
     MegaGemm g[4];  // qkv, o, gate|up, down

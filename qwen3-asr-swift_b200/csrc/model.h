@@ -73,6 +73,11 @@ struct BatchState {
     bool sampler_on = false;   // decoder knobs active: full logits + sample_kernel instead of the fused argmax epilogue
     SamplingParams sampling;
     int steps_done = 0;
+    // decode rows: the sequences still being decoded (B until a compaction drops the finished ones; stop_on_eos only)
+    int dec_rows = 0;
+    int page_cur = 0;             // which of page_tab / page_tab2 the decode rows index through
+    bool slot_map_on = false;     // st_slot_seq holds the row -> sequence map (identity until the first compaction)
+    unsigned long long stat_row_steps = 0, stat_steps = 0, stat_compactions = 0;  // q3asr_decode_stats
 
     // device buffers
     DevBuf pcm, mel_out, mel_clips, mel_gmax, mel_tmin;
@@ -90,7 +95,7 @@ struct BatchState {
     MegaParams mega;
     int mega_nb = 0, mega_gu = 0;
     bool mega_ready = false;
-    DevBuf kv_pool, rope_tab, page_tab;  // page_tab: [B][pages_per_seq] (plan_pages)
+    DevBuf kv_pool, rope_tab, page_tab, page_tab2, st_slot_seq;  // page_tab: [B][pages_per_seq] (plan_pages)
     int rope_n = 0;          // positions tabulated in rope_tab
     DevBuf amax_val, amax_idx, logits, logits_bf;
     // decode state (device)
@@ -105,7 +110,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &page_tab, &amax_val, &amax_idx, &logits, &logits_bf,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &page_tab, &page_tab2, &st_slot_seq, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }

@@ -925,16 +925,17 @@ __global__ void __launch_bounds__(1024) reduce_resid_rmsnorm_kernel(const float*
 __global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
     ptx::grid_dep_launch();
     ptx::grid_dep_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // decode row
     const int step = *s.step;
     if (i < n_seqs) {
         const int32_t tok = s.next_tok[i];
-        if (!s.finished[i] && step < s.max_tokens) {
-            s.out_ids[(size_t)i * s.max_tokens + step] = tok;
-            if (s.out_val && s.next_val) s.out_val[(size_t)i * s.max_tokens + step] = s.next_val[i];
-            s.out_len[i] = step + 1;
+        const int q = s.slot_seq ? s.slot_seq[i] : i;  // the sequence this row decodes
+        if (!s.finished[q] && step < s.max_tokens) {
+            s.out_ids[(size_t)q * s.max_tokens + step] = tok;
+            if (s.out_val && s.next_val) s.out_val[(size_t)q * s.max_tokens + step] = s.next_val[i];
+            s.out_len[q] = step + 1;
             if (s.stop_on_eos && tok == s.eos) {
-                s.finished[i] = 1;
+                s.finished[q] = 1;
                 atomicSub(s.n_active, 1);
             }
         }
@@ -944,6 +945,38 @@ __global__ void decode_advance_kernel(DecodeState s, int n_seqs) {
     }
     __syncthreads();
     if (i == 0) *s.step = step + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Compaction of the decode rows: see decode_compact_launch (ops.cuh).
+__global__ void __launch_bounds__(1024) decode_compact_kernel(int rows, const int* __restrict__ finished, int* slot_seq, int32_t* cur_tok, int* pos,
+                                                              int* kv_len, const int* __restrict__ page_in, int* __restrict__ page_out,
+                                                              int max_pages) {
+    __shared__ int s_warp[32];
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    int q = 0, tok = 0, p = 0, kl = 0, alive = 0;
+    if (i < rows) {
+        q = slot_seq[i];
+        tok = cur_tok[i];
+        p = pos[i];
+        kl = kv_len[i];
+        alive = finished[q] ? 0 : 1;
+    }
+    // exclusive prefix sum of `alive` over the CTA: warp ballots, then the warp totals
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    const int in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();  // also: every row has been read before any is overwritten
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += s_warp[w];
+    if (alive) {
+        const int j = base + in_warp;
+        slot_seq[j] = q;
+        cur_tok[j] = tok;
+        pos[j] = p;
+        kv_len[j] = kl;
+        for (int k = 0; k < max_pages; k++) page_out[(size_t)j * max_pages + k] = page_in[(size_t)i * max_pages + k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1205,6 +1238,13 @@ void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_
 void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st) {
     Q3_CHECK(n_seqs <= 1024, 1, "decode_advance: at most 1024 sequences per handle");
     launch_kernel(decode_advance_kernel, 1, 1024, 0, st, s, n_seqs);
+}
+
+void decode_compact_launch(int rows, const int* finished, int* slot_seq, int32_t* cur_tok, int* pos, int* kv_len, const int* page_in,
+                           int* page_out, int max_pages, cudaStream_t st) {
+    Q3_CHECK(rows >= 1 && rows <= 1024, 1, "decode_compact: 1..1024 rows");
+    decode_compact_kernel<<<1, 1024, 0, st>>>(rows, finished, slot_seq, cur_tok, pos, kv_len, page_in, page_out, max_pages);
+    Q3_CUDA(cudaGetLastError());
 }
 
 int sample_parts(int vocab) { return vocab >= 32768 ? 4 : 1; }

@@ -86,6 +86,7 @@ struct DecodeState {
     int* out_len;         // [n_seqs]
     int* finished;        // [n_seqs]
     int* n_active;        // [1]
+    const int* slot_seq;  // [rows] sequence of every decode row, or null (identity): after a compaction the rows are the still-active sequences
     const int32_t* forced;  // [n_seqs? no: steps] or null
     int* step;            // [1] device-side step counter
     int max_tokens;
@@ -93,6 +94,12 @@ struct DecodeState {
     int stop_on_eos;
 };
 void decode_advance_launch(const DecodeState& s, int n_seqs, cudaStream_t st);
+// Drops the finished sequences from the decode rows (Qwen3ASR.swift:378-379 stops an utterance at EOS; a batched loop has to take it
+// out of the batch, or its KV pages and a column of every product keep being streamed): the rows whose sequence is still active
+// move to the front, in order, together with their token / position / cache length / page-table row.  One CTA; rows <= 1024.
+// page_in / page_out: [rows][max_pages] (distinct buffers).  slot_seq is updated in place (identity on entry if it was never set).
+void decode_compact_launch(int rows, const int* finished, int* slot_seq, int32_t* cur_tok, int* pos, int* kv_len, const int* page_in,
+                           int* page_out, int max_pages, cudaStream_t st);
 
 // Decoder knobs of Qwen3DecodingOptions (Qwen3ASR.swift:13-51) applied on the device: the reference pulls the [vocab] logits to
 // the CPU every token (pickNextToken, Qwen3ASR.swift:449-520); here one CTA per sequence applies the same three edits while it

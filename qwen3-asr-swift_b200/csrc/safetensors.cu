@@ -248,20 +248,36 @@ void model_load_safetensors(Handle* h, const char* dir) {
         std::vector<float> deq;
         for (auto& spec : specs) {
             auto it = index.find(spec.first);
-            if (it == index.end()) continue;
+            if (it == index.end()) {
+                // the reference's applyLinearWeights keeps a Linear's bias as it is when the checkpoint has none
+                // (MLXCommon/WeightLoading.swift:113-130): the aligner's classification bias then stays zero
+                if (spec.first == "lm_head.bias") {
+                    size_t n = 1;
+                    for (int64_t d : spec.second) n *= (size_t)d;
+                    std::vector<float> zeros(n, 0.f);
+                    model_set_tensor(h, spec.first.c_str(), zeros.data(), 0, spec.second.data(), (int)spec.second.size());
+                    loaded++;
+                }
+                continue;
+            }
             const Located& l = it->second;
             const Entry& e = l.e;
             ck.read(l, &buf);
             const size_t numel = checked_numel(e);
             if (e.dtype == "U32") {
+                Q3_CHECK(e.name.size() > 7, Q3ASR_ERR_INVALID, "load_safetensors: packed tensor with an unexpected name: " + e.name);
                 const std::string stem = e.name.substr(0, e.name.size() - 7);  // strip ".weight"
                 auto si = index.find(stem + ".scales"), bi = index.find(stem + ".biases");
-                Q3_CHECK(e.shape.size() == 2 && e.name.size() > 7 && si != index.end() && bi != index.end(), Q3ASR_ERR_INVALID,
+                Q3_CHECK(e.shape.size() == 2 && si != index.end() && bi != index.end(), Q3ASR_ERR_INVALID,
                          "load_safetensors: " + e.name + " is packed (U32) but its .scales / .biases are missing");
                 const Entry& se = si->second.e;
                 Q3_CHECK(se.shape.size() == 2 && se.shape[0] == e.shape[0] && bi->second.e.shape == se.shape && bi->second.e.dtype == se.dtype,
                          Q3ASR_ERR_INVALID, "load_safetensors: scales / biases of " + e.name + " do not match it");
-                const int64_t rows = e.shape[0], words = e.shape[1], groups = se.shape[1], cols = groups * 64;
+                // the group size follows from the columns the model expects (64 in the published checkpoints; MLX also writes 32 / 128)
+                Q3_CHECK(spec.second.size() == 2 && se.shape[1] > 0 && spec.second[1] % se.shape[1] == 0, Q3ASR_ERR_INVALID,
+                         "load_safetensors: quantisation groups of " + e.name + " do not divide its columns");
+                const int64_t rows = e.shape[0], words = e.shape[1], groups = se.shape[1], cols = spec.second[1], gsz = cols / groups;
+                Q3_CHECK(gsz == 32 || gsz == 64 || gsz == 128, Q3ASR_ERR_INVALID, "load_safetensors: unsupported quantisation group size for " + e.name);
                 Q3_CHECK(buf.size() == numel * 4 && cols > 0 && (words * 32) % cols == 0, Q3ASR_ERR_IO, "load_safetensors: size mismatch for " + e.name);
                 const int bits = (int)(words * 32 / cols);
                 Q3_CHECK(bits == 2 || bits == 4 || bits == 8, Q3ASR_ERR_INVALID, "load_safetensors: unsupported quantisation width for " + e.name);
@@ -277,8 +293,8 @@ void model_load_safetensors(Handle* h, const char* dir) {
                 for (int64_t r = 0; r < rows; r++)
                     for (int64_t g = 0; g < groups; g++) {
                         const float sc = scalar_at(sbuf, se.dtype, (size_t)(r * groups + g)), bs = scalar_at(bbuf, se.dtype, (size_t)(r * groups + g));
-                        for (int c = 0; c < 64; c++) {
-                            const int64_t col = g * 64 + c;
+                        for (int64_t c = 0; c < gsz; c++) {
+                            const int64_t col = g * gsz + c;
                             const uint32_t q = (w32[r * words + col / per] >> ((col % per) * bits)) & mask;
                             deq[(size_t)(r * cols + col)] = (float)((double)sc * (double)q + (double)bs);  // exact product, one rounding
                         }

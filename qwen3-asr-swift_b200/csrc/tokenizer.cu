@@ -355,8 +355,14 @@ struct q3asr_tokenizer {
         }
         std::vector<std::string> words;  // preTokenize, Tokenizer.swift:218-238
         std::string cur;
-        for (char ch : text) {
-            if (ch == ' ' || ch == '\n' || ch == '\t') {
+        // The reference walks Swift Characters (grapheme clusters): "\r\n" is ONE Character that is not equal to "\n", so a CRLF
+        // does not split; every other splitting character here is a single-byte cluster on its own.
+        for (size_t i = 0; i < text.size(); i++) {
+            const char ch = text[i];
+            if (ch == '\r' && i + 1 < text.size() && text[i + 1] == '\n') {
+                cur += "\r\n";
+                i++;
+            } else if (ch == ' ' || ch == '\n' || ch == '\t') {
                 if (!cur.empty()) words.push_back(byte_level(cur));
                 cur.assign(1, ch);
             } else {
@@ -409,12 +415,23 @@ struct q3asr_tokenizer {
                     }
         }
         if (read_file(dir + "/merges.txt", &src)) {
-            // components(separatedBy: .newlines): every line terminator starts a new line (so "\r\n" yields an empty line, skipped)
+            // components(separatedBy: .newlines): every scalar of CharacterSet.newlines (U+000A-U+000D, U+0085, U+2028, U+2029) starts
+            // a new line (so "\r\n" yields an empty line, skipped); the line INDEX is the merge rank, so all of them must count
+            auto newline_at = [&](size_t i) -> size_t {  // byte length of the line terminator at i, or 0
+                const unsigned char c0 = (unsigned char)src[i];
+                if (c0 >= 0x0A && c0 <= 0x0D) return 1;
+                if (c0 == 0xC2 && i + 1 < src.size() && (unsigned char)src[i + 1] == 0x85) return 2;
+                if (c0 == 0xE2 && i + 2 < src.size() && (unsigned char)src[i + 1] == 0x80 &&
+                    ((unsigned char)src[i + 2] == 0xA8 || (unsigned char)src[i + 2] == 0xA9))
+                    return 3;
+                return 0;
+            };
             size_t pos = 0;
             int index = 0;
             while (pos <= src.size()) {
-                size_t e = src.find_first_of("\n\r", pos);
-                if (e == std::string::npos) e = src.size();
+                size_t e = pos, nl = 0;
+                while (e < src.size() && (nl = newline_at(e)) == 0) e++;
+                if (e >= src.size()) nl = 1;
                 const std::string line = src.substr(pos, e - pos);
                 if (!line.empty() && line[0] != '#') {
                     const size_t sp = line.find(' ');
@@ -424,7 +441,7 @@ struct q3asr_tokenizer {
                     }
                 }
                 index++;
-                pos = e + 1;
+                pos = e + nl;
             }
         }
         return true;

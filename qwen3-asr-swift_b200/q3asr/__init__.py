@@ -79,7 +79,7 @@ EXPORTS = [
     "q3asr_load_safetensors", "q3asr_checkpoint_list", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
     "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_text_prepare_for_alignment", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
-    "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_flush_l2",
+    "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_decode_stats", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
     "q3asr_pool_create", "q3asr_pool_destroy", "q3asr_pool_last_error", "q3asr_pool_transcribe_ids", "q3asr_schedule",
     "q3asr_debug_gemm", "q3asr_debug_conv", "q3asr_debug_attention",
@@ -146,6 +146,7 @@ def lib():
         L.q3asr_stage_ms.argtypes = [vp, vp]
         L.q3asr_launch_count.argtypes = [vp]
         L.q3asr_launch_count.restype = ctypes.c_uint64
+        L.q3asr_decode_stats.argtypes = [vp, vp]
         L.q3asr_flush_l2.argtypes = [vp]
         L.q3asr_profile.argtypes = [vp, ci]
         L.q3asr_profile_report.argtypes = [vp, ctypes.c_char_p, cs]
@@ -522,6 +523,12 @@ class Qwen3ASRModel:
     @property
     def launch_count(self):
         return int(lib().q3asr_launch_count(self._h))
+
+    def decode_stats(self):
+        """{steps, row_steps, compactions, rows} of the last decode loop (q3asr_decode_stats)."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(lib().q3asr_decode_stats(self._h, out.ctypes.data))
+        return dict(steps=int(out[0]), row_steps=int(out[1]), compactions=int(out[2]), rows=int(out[3]))
 
     # -- weights -----------------------------------------------------------------------------
     def tensor_names(self):

@@ -28,6 +28,13 @@ public struct B200MelFeatures {
     public let timeFrames: Int
 }
 
+#if os(Linux)
+/// On Linux (no MLX / Metal) the reference's type names resolve to the B200 implementation, so code written against
+/// `Qwen3ASRModel` / `Qwen3ForcedAligner` (Qwen3ASR.swift:67, ForcedAligner.swift:226) builds and runs unchanged.
+public typealias Qwen3ASRModel = Qwen3ASRB200Model
+public typealias Qwen3ForcedAligner = Qwen3ForcedAlignerB200
+#endif
+
 public final class Qwen3ASRB200Model {
     private var handle: OpaquePointer?
     private let tokenizer: Qwen3Tokenizer?
@@ -49,12 +56,15 @@ public final class Qwen3ASRB200Model {
 
     /// Mirrors Qwen3ASRModel.fromPretrained: resolves / downloads the checkpoint directory with the
     /// reference's HuggingFaceDownloader, then hands the directory to the library (fp16/bf16/fp32 safetensors).
+    /// Same parameter names, order and defaults as the reference (Qwen3ASR.swift:608-613); `device` is the one addition and comes
+    /// last with a default, so every existing call site compiles unchanged.  The default model id is the reference's
+    /// (an MLX 4-bit checkpoint: the loader dequantises it to bf16, csrc/safetensors.cu).
     public static func fromPretrained(
-        modelId: String = "Qwen/Qwen3-ASR-0.6B",
+        modelId: String = "aufklarer/Qwen3-ASR-0.6B-MLX-4bit",
         cacheDir: URL? = nil,
         offlineMode: Bool = false,
-        device: Int32 = 0,
-        progressHandler: ((Double, String) -> Void)? = nil
+        progressHandler: ((Double, String) -> Void)? = nil,
+        device: Int32 = 0
     ) async throws -> Qwen3ASRB200Model {
         progressHandler?(0.0, "Downloading model...")
         let size = ASRModelSize.detect(from: modelId)

@@ -89,7 +89,7 @@ def test_1p7b_configuration(built_lib, monkeypatch):
         monkeypatch.setenv("Q3ASR_NO_SKINNY", "1")
         p_ids, p_top = m.decode_forced(clips[0], forced)
         monkeypatch.delenv("Q3ASR_NO_SKINNY")
-        assert np.abs(f_top - p_top).max() <= 4 * np.abs(p_top).max() * 2.0 ** -8
+        assert np.abs(f_top - p_top).max() <= 16 * np.abs(p_top).max() * 2.0 ** -8  # two bf16 schedules of 28 layers: see tests/test_gpu_golden.py
         assert m.memory_footprint > 4e9
     finally:
         m.close()

@@ -123,6 +123,25 @@ def test_encode_with_merges_and_character_fallback(tok):
     assert plain.encode("lone") == [0, 1, 11, 3]
 
 
+def test_crlf_is_one_character_and_every_newline_scalar_counts_a_merge_line(tmp_path, built_lib):
+    """Tokenizer.swift:218-238 walks Swift Characters: "\r\n" is ONE grapheme that is not equal to "\n", so a CRLF inside a
+    context string does not start a new word.  Tokenizer.swift:94: merges.txt is split on CharacterSet.newlines, which also holds
+    VT, FF, U+0085, U+2028 and U+2029 — the line index is the merge rank, so lines ended by those must be counted."""
+    vocab = {"a": 0, "b": 1, "c": 2, "ab": 3, "bc": 4, "ĊĊ": 5, "Ċ": 6, "č": 7, "čĊ": 8, "ačĊb": 9, "Ċb": 10}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab), encoding="utf-8")
+    # ranks: "b c" sits on line index 1 only if the U+2028 after the first line is a line break; then "bc" wins over "ab" for "abc"
+    # exactly when its rank is lower than that of "a b", which comes two (U+0085, FF) line breaks later
+    (tmp_path / "merges.txt").write_bytes("#v\u2028b c\u0085\x0ca b\nč Ċ\na čĊ\načĊ b\n".encode("utf-8"))
+    t = built_lib.Qwen3Tokenizer(path=str(tmp_path))
+    try:
+        assert t.size()[1] == 5
+        assert t.encode("abc") == [0, 4]           # "b c" (line 1) outranks "a b" (line 3): a + bc
+        assert t.encode("a\r\nb") == [9]            # one word: a, CR, LF, b merge all the way ("\r\n" did not split)
+        assert t.encode("a\nb") == [0, 6, 1]        # a bare LF does split: "a", then the word "\nb" (no merge for it: two pieces)
+    finally:
+        t.close()
+
+
 def test_load_from_directory(tmp_path, built_lib):
     vocab = {"Hello": 100, "Ġworld": 101, "!": 0, "Ċ": 1, "H": 2, "e": 3, "l": 4, "o": 5, "He": 6, "ll": 7, "Hell": 8}
     (tmp_path / "vocab.json").write_text(json.dumps(vocab), encoding="utf-8")
