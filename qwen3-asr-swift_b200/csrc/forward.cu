@@ -399,6 +399,7 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
     const int* pos = prefill ? ints + bs->o_pos : bs->st_pos.as<int>();
     const int* row_seq = prefill ? ints + bs->o_row_seq : ints + bs->o_ident;
     AttnSegs segs{ints + bs->o_seq_row0, ints + bs->o_seq_len, bs->B, bs->max_prompt};
+    const bool fuse_qkv = hd == 128 && env_int("Q3ASR_NO_QKV_FUSE", 0) == 0;  // "1": the separate norm + RoPE kernel (the checker)
     double causal_pairs = 0;  // sum over prompts of S(S+1)/2
     for (const ClipInfo& ci : bs->clips) causal_pairs += 0.5 * ci.prompt_len * (ci.prompt_len + 1.0);
     for (int l = 0; l < c.dec_layers; l++) {
@@ -412,11 +413,23 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
         tag("pre_norm", "dec_norm", 0, 4.0 * Rd * H);
         rmsnorm_launch(x, w.in_ln, xn, rows, H, c.dec_rms_eps, nullptr, st);
         tag("pre_qkv", "dec_qkv", 2.0 * Rd * H * nqkv, 2.0 * H * nqkv);
-        gemm(xn, H, rows, H, w.qkv_w, nqkv, epi_store(qkv, nqkv, nullptr), st);
-        tag("pre_rope", "dec_rope", 0, 4.0 * Rd * nqkv);
-        // v is not transformed: the prefill attention reads it straight from the QKV product, only k needs a contiguous copy
-        qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
-                              bs->rope_tab.as<float2>(), q, prefill ? bs->dkc.as<bf16>() : nullptr, nullptr, kc, l, st);
+        if (prefill && fuse_qkv) {
+            // per-head RMSNorm + RoPE + the paged-KV write happen in the product's epilogue (gemm.cuh EPI_QKV): q, k and the cache
+            // are written once, the raw product never reaches memory (v does, as is: the attention reads it from there)
+            GemmEpiArgs e;
+            e.epi = EPI_QKV;
+            e.out = qkv;
+            e.ldo = nqkv;
+            e.rp = QkvRope{pos, row_seq, bs->rope_tab.as<float2>(), w.q_norm, w.k_norm, q, bs->dkc.as<bf16>(), kc.pool, kc.page_table,
+                           kc.max_pages, kc.layers, l, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps};
+            gemm(xn, H, rows, H, w.qkv_w, nqkv, e, st);
+        } else {
+            gemm(xn, H, rows, H, w.qkv_w, nqkv, epi_store(qkv, nqkv, nullptr), st);
+            tag("pre_rope", "dec_rope", 0, 4.0 * Rd * nqkv);
+            // v is not transformed: the prefill attention reads it straight from the QKV product, only k needs a contiguous copy
+            qknorm_rope_kv_launch(qkv, nqkv, w.q_norm, w.k_norm, pos, row_seq, rows, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps,
+                                  bs->rope_tab.as<float2>(), q, prefill ? bs->dkc.as<bf16>() : nullptr, nullptr, kc, l, st);
+        }
         tag("pre_attn", "dec_attn", prefill ? 4.0 * causal_pairs * nq : 0, 0);
         if (prefill && env_int("Q3ASR_ATTN_MMASYNC", 0) == 0)
             flash_attn_tc_launch(q, nq, bs->dkc.as<bf16>(), nkv, qkv + nq + nkv, nqkv, att, nq, segs, rows, c.dec_heads,

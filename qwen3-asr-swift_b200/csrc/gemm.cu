@@ -57,6 +57,10 @@ void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
         case EPI_SWIGLU: launch_tc<BN, EPI_SWIGLU>(ta, tb, p, ms, grid, st); break;
         case EPI_F32: launch_tc<BN, EPI_F32>(ta, tb, p, ms, grid, st); break;
         case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, p, ms, grid, st); break;
+        case EPI_QKV:
+            if constexpr (BN % 128 == 0) launch_tc<BN, EPI_QKV>(ta, tb, p, ms, grid, st);
+            else throw Error(1, "gemm: the fused q/k/v epilogue needs tiles of whole heads (128 or 256 columns)");
+            break;
         default: throw Error(1, "gemm: bad epilogue");
     }
 }
@@ -72,7 +76,10 @@ void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, 
 template <int BN>
 void launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
     if (epi == EPI_SWIGLU) launch_tc2<BN, EPI_SWIGLU>(ta, tb, p, grid, st);
-    else launch_tc2<BN, EPI_NORMAL>(ta, tb, p, grid, st);
+    else if (epi == EPI_QKV) {
+        if constexpr (BN % 128 == 0) launch_tc2<BN, EPI_QKV>(ta, tb, p, grid, st);
+        else throw Error(1, "gemm: the fused q/k/v epilogue needs tiles of whole heads (128 or 256 columns)");
+    } else launch_tc2<BN, EPI_NORMAL>(ta, tb, p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -260,8 +267,11 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     p.out = e.out; p.ldo = e.ldo; p.bias = e.bias; p.resid = e.resid; p.ldr = e.ldr;
     p.row_add = e.row_add; p.row_map = e.row_map; p.valid_w = e.valid_w; p.gelu = e.gelu;
     p.amax_val = e.amax_val; p.amax_idx = e.amax_idx;
+    p.rp = e.rp;
     const long m_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_b;
+    if (bn == 0 && e.epi == EPI_QKV) bn = (N % 256 == 0 && m_tiles * (N / 256) >= g_num_sms) ? 256 : 128;  // tiles of whole heads
     if (bn == 0) bn = gemm_pick_bn(N, e.epi, m_tiles);
+    Q3_CHECK(e.epi != EPI_QKV || ((bn == 128 || bn == 256) && N % bn == 0 && e.rp.q != nullptr), 1, "gemm: fused q/k/v epilogue arguments");
     Q3_CHECK(N % bn == 0, 1, "gemm: N must be a multiple of the tile width");
     Q3_CHECK(e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0, 1, "gemm: SwiGLU tiles must be multiples of 64 columns");
     p.tiles_n = N / bn;
@@ -299,8 +309,8 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     const int mode2 = env2 && *env2 ? atoi(env2) : -1;
     // measured (profiles/): pairing lifts the plain products (q/k/v, o, down, fc2, conv_out: +9..19 %, 1.2-1.3 PFLOP/s) to the cuBLAS
     // ceiling; GELU / SwiGLU tiles are bound by their epilogues and the stride-2 convolutions by their TMA boxes, where it does not pay
-    const bool plain = e.epi == EPI_NORMAL && !e.gelu && s.sw == 1 && s.sh == 1;
-    const bool pair = mode2 != 0 && !simt && (e.epi == EPI_NORMAL || e.epi == EPI_SWIGLU) && (bn == 128 || bn == 160 || bn == 224 || bn == 256) &&
+    const bool plain = (e.epi == EPI_NORMAL || e.epi == EPI_QKV) && !e.gelu && s.sw == 1 && s.sh == 1;
+    const bool pair = mode2 != 0 && !simt && (e.epi == EPI_NORMAL || e.epi == EPI_SWIGLU || e.epi == EPI_QKV) && (bn == 128 || bn == 160 || bn == 224 || bn == 256) &&
                       (mode2 == 1 || (plain && m_tiles * p.tiles_n >= 4L * g_num_sms)) && (e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0);
     {
         const long K = (long)s.taps * a.C;

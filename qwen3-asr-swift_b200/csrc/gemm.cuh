@@ -33,6 +33,21 @@ enum GemmEpi : int {
     EPI_SWIGLU = 1,  // columns alternate 32 gate / 32 up (GU_UNIT): out = bf16( bf16(silu(bf16 g)) * bf16 u ), N/2 outputs
     EPI_F32 = 2,     // out(fp32) = acc + bias
     EPI_ARGMAX = 3,  // per (row, n-tile): max / lowest index of bf16(acc)
+    EPI_QKV = 4,     // decoder prefill: columns are q | k | v heads of 128; per-head RMSNorm + split-half RoPE on q and k, q -> its own
+                     // buffer, k -> a contiguous buffer + the paged cache, v -> out (as is) + the paged cache (FloatTextDecoder.swift:77-102)
+};
+
+// what EPI_QKV needs besides the accumulator (by value inside GemmDev)
+struct QkvRope {
+    const int* pos;        // [rows] position of every packed row
+    const int* row_seq;    // [rows] sequence (page-table row) of every packed row
+    const float2* rope;    // [pos][64] (cos, sin)
+    const bf16 *qw, *kw;   // per-head norm weights [128]
+    bf16 *q, *kc;          // q [rows, heads*128], k [rows, kv_heads*128]
+    bf16* pool;            // paged cache [pages][layers][2][kv_heads][32][128]
+    const int* page_table; // [seqs][max_pages]
+    int max_pages, layers, layer, heads, kv_heads;
+    float eps;
 };
 
 constexpr int GEMM_BM = 128;
@@ -60,6 +75,7 @@ struct GemmDev {  // by-value kernel parameter
     int stages;            // smem ring depth actually used (<= gemm_stages(BN))
     float* amax_val;       // [rows, tiles_n]
     int* amax_idx;
+    QkvRope rp;            // EPI_QKV only
 };
 
 __host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
@@ -134,6 +150,111 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                     uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        }
+    } else if constexpr (EPI == EPI_QKV) {
+        // One head (128 accumulator columns) at a time per thread = per token row; the two warps of a lane quadrant take alternate
+        // heads of the tile.  The raw product is rounded to bf16 first (the reference's Linear output), then normed, rounded,
+        // rotated, rounded — the rounding points of qknorm_rope_kv_kernel (ops.cu), which this epilogue replaces in the prefill:
+        // the QKV product is no longer written, re-read and re-written (436 MB per layer at 64 x 30 s).
+        if constexpr (BN % 128 == 0) {
+            const QkvRope& R = p.rp;
+            int pos = 0, page = 0;
+            if (row_ok) {
+                pos = __ldg(R.pos + row);
+                page = __ldg(R.page_table + (size_t)__ldg(R.row_seq + row) * R.max_pages + pos / 32);
+            }
+            bf16* page_base = R.pool + (((size_t)page * R.layers + R.layer) * 2) * R.kv_heads * (32 * 128) + (pos % 32) * 128;
+#pragma unroll 1
+            for (int hh = chalf; hh < BN / 128; hh += 2) {
+                const int slot = tc.tn * (BN / 128) + hh;  // [0, heads) q, [heads, heads + kv_heads) k, then v
+                const uint32_t t_head = t_row + hh * 128;
+                const bool is_q = slot < R.heads, is_v = slot >= R.heads + R.kv_heads;
+                const int kvh = is_v ? slot - R.heads - R.kv_heads : slot - R.heads;
+                if (is_v) {
+#pragma unroll 1
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(t_head + c * 32, v);
+                        ptx::tmem_ld_wait();
+                        if (row_ok) {
+                            uint4 pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                pk[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                                   pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                                   pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                                   pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                            uint4* d0 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + slot * 128 + c * 32);
+                            uint4* d1 = reinterpret_cast<uint4*>(page_base + ((size_t)R.kv_heads + kvh) * (32 * 128) + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) { d0[j] = pk[j]; d1[j] = pk[j]; }
+                        }
+                    }
+                    continue;
+                }
+                float ss = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_head + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float x = bf16_round(__uint_as_float(v[j]));
+                        ss = fmaf(x, x, ss);
+                    }
+                }
+                const float r = rsqrtf(ss * (1.0f / 128.0f) + R.eps);
+                const bf16* nw = is_q ? R.qw : R.kw;
+                bf16* dst = is_q ? R.q + (size_t)row * R.heads * 128 + slot * 128 : R.kc + (size_t)row * R.kv_heads * 128 + kvh * 128;
+                bf16* dst2 = page_base + (size_t)kvh * (32 * 128);  // K half of the page (k heads only)
+#pragma unroll 1
+                for (int c = 0; c < 2; c++) {  // dims [32c, 32c + 32) pair with [64 + 32c, ...)
+                    uint32_t a[32], b[32];
+                    ptx::tmem_ld_32x32(t_head + c * 32, a);
+                    ptx::tmem_ld_32x32(t_head + 64 + c * 32, b);
+                    ptx::tmem_ld_wait();
+                    if (row_ok) {
+                        const float4* tp = reinterpret_cast<const float4*>(R.rope + (size_t)pos * 64 + c * 32);  // (cos, sin) pairs
+                        const uint4* wa = reinterpret_cast<const uint4*>(nw + c * 32);
+                        const uint4* wb = reinterpret_cast<const uint4*>(nw + 64 + c * 32);
+                        uint32_t oa[16], ob[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const uint4 wua = __ldg(wa + j4), wub = __ldg(wb + j4);
+                            const uint32_t wwa[4] = {wua.x, wua.y, wua.z, wua.w}, wwb[4] = {wub.x, wub.y, wub.z, wub.w};
+#pragma unroll
+                            for (int j2 = 0; j2 < 4; j2++) {
+                                const int j = 8 * j4 + 2 * j2;
+                                const float4 t = __ldg(tp + (j >> 1));  // cos, sin of dims j and j + 1
+                                const float2 fa = unpack_bf16x2(wwa[j2]), fb = unpack_bf16x2(wwb[j2]);
+                                const float xa0 = bf16_round(bf16_round(__uint_as_float(a[j])) * r * fa.x);
+                                const float xa1 = bf16_round(bf16_round(__uint_as_float(a[j + 1])) * r * fa.y);
+                                const float xb0 = bf16_round(bf16_round(__uint_as_float(b[j])) * r * fb.x);
+                                const float xb1 = bf16_round(bf16_round(__uint_as_float(b[j + 1])) * r * fb.y);
+                                oa[j >> 1] = pack_bf16x2(fmaf(xa0, t.x, -1.f * xb0 * t.y), fmaf(xa1, t.z, -1.f * xb1 * t.w));
+                                ob[j >> 1] = pack_bf16x2(fmaf(xb0, t.x, xa0 * t.y), fmaf(xb1, t.z, xa1 * t.w));
+                            }
+                        }
+                        uint4* da = reinterpret_cast<uint4*>(dst + c * 32);
+                        uint4* db = reinterpret_cast<uint4*>(dst + 64 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            da[j] = make_uint4(oa[4 * j], oa[4 * j + 1], oa[4 * j + 2], oa[4 * j + 3]);
+                            db[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                        }
+                        if (!is_q) {
+                            uint4* ca = reinterpret_cast<uint4*>(dst2 + c * 32);
+                            uint4* cb = reinterpret_cast<uint4*>(dst2 + 64 + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                ca[j] = make_uint4(oa[4 * j], oa[4 * j + 1], oa[4 * j + 2], oa[4 * j + 3]);
+                                cb[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -408,6 +529,7 @@ struct GemmEpiArgs {
     int max_stages = 0;  // 0: as deep as shared memory allows
     float* amax_val = nullptr;
     int* amax_idx = nullptr;
+    QkvRope rp = {};  // EPI_QKV
 };
 
 void gemm_init(int device);  // resolves cuTensorMapEncodeTiled, sets smem attributes, reads the SM count

@@ -234,3 +234,24 @@ def test_tcgen05_attention_matches_mma_sync_checker(built_lib, monkeypatch):
         assert np.abs(log_tc - log_ms).max() <= 32 * np.abs(log_ms).max() * 2.0 ** -8
     finally:
         m.close()
+
+
+def test_prefill_qkv_fusion_matches_separate_kernel(tiny_model, monkeypatch):
+    """The prefill's q/k/v product with per-head RMSNorm + RoPE + paged-KV write in its epilogue (gemm.cuh EPI_QKV) against the
+    separate kernel it replaces (Q3ASR_NO_QKV_FUSE=1: qknorm_rope_kv_kernel).  Same rounding points; only the order of the 128-term
+    sum of squares differs, so on the two-layer model the logits agree to a few fp32 ulps' worth of bf16 flips and the ids — which
+    also exercise the K and V rows the epilogue wrote into the paged cache — are identical."""
+    clips = [synth.clip(40 + i, n) for i, n in enumerate([30000, 16000, 48000, 5000, 480000])]
+    fused = [t.tolist() for t in tiny_model.transcribe_ids(clips, max_tokens=24, stop_on_eos=False)]
+    lf = tiny_model.prefill_logits(clips[2])
+    forced = np.random.default_rng(9).integers(0, 2000, size=20).astype(np.int32)
+    f_ids, f_top = tiny_model.decode_forced(clips[0], forced)
+    monkeypatch.setenv("Q3ASR_NO_QKV_FUSE", "1")
+    plain = [t.tolist() for t in tiny_model.transcribe_ids(clips, max_tokens=24, stop_on_eos=False)]
+    lp = tiny_model.prefill_logits(clips[2])
+    p_ids, p_top = tiny_model.decode_forced(clips[0], forced)
+    monkeypatch.delenv("Q3ASR_NO_QKV_FUSE")
+    assert _rel_l2(lf, lp) <= 2e-3, _rel_l2(lf, lp)
+    assert np.abs(f_top - p_top).max() <= 2 * np.abs(p_top).max() * 2.0 ** -8
+    assert (f_ids == p_ids).mean() >= 0.9
+    assert fused == plain
