@@ -6,18 +6,26 @@
 // slaney filterbank product (:263-268), clip/log10/clip-to-(max-8)/scale (:275-293), drop of the
 // last frame and the 120000-frame cap (:296-313), [128, T] mel-major output (:315-316).
 //
-// B200 design.  One persistent CTA (128 threads, 4 per SM) walks 24-frame tiles.  A tile's samples
-// (4080 floats, reflect padding resolved while loading) are staged in shared memory with 128-bit
-// coalesced loads; sixteen lanes share one frame and two frames share a warp, so every
-// synchronisation inside the transform is a __syncwarp.  The 512-point real FFT is the 256-point
-// complex FFT of the even/odd packed frame, done as 16x16 (two in-register radix-16 passes with one
-// shared-memory transpose), followed by the real-split step that yields bins k and 256-k together.
-// The vDSP factor 2 cancels against the 1/2 of the split step (|2X|^2 = |e + w o|^2).  The filterbank
-// is applied as an ELL-packed sparse product (504 non-zeros instead of 32896 MACs per frame).  The
-// kernel writes 0.25*log10(mel)+1 unclamped through a shared-memory transpose tile (128-byte row
-// stores), an ordered-int atomicMax per clip and a per-tile minimum; the second kernel applies the
-// max-8 clamp only to tiles whose minimum is below it (exact, because clamp and the monotone affine
-// map commute), so in the common case the features are written once and never re-read.
+// B200 design.  The kernel is bound by instruction issue, not by bytes (7.2 B of traffic per sample against ~500 fp32
+// instructions per frame for a 512-point real FFT + 504 filter taps + 128 logarithms), so the design goal
+// is issue slots per frame:
+//   * Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2) processes two fp32 values per instruction.  Every value in the
+//     transform is held as a PAIR (frame A, frame B) of two neighbouring frames, so that EVERY arithmetic instruction of the FFT,
+//     the real-split step, the power spectrum and the filterbank is a packed one, with no shuffling inside a pair: half the
+//     arithmetic instructions per frame, and the shared-memory transposes move both frames with one 128-bit access.
+//   * Sixteen lanes share one frame pair (two pairs per warp, every synchronisation inside the transform is a __syncwarp); a CTA
+//     of 256 threads transforms the 32 frames of a tile in one pass.  A tile's samples (5360 floats, reflect padding resolved
+//     while loading) are staged once with 128-bit coalesced loads.
+//   * The 512-point real FFT is the 256-point complex FFT of the even/odd packed frame, done as 16 x 16 (two in-register
+//     radix-16 passes with one shared-memory transpose), followed by the real-split step that yields bins k and 256-k together.
+//     The vDSP factor 2 cancels against the 1/2 of the split step (|2X|^2 = |e + w o|^2).  The filterbank is an ELL-packed sparse
+//     product (504 non-zeros instead of 32896 MACs per frame).
+//   * 0.25*log10(mel)+1 is written unclamped straight from registers (the two frames of a pair are neighbours in a mel row), with
+//     an ordered-int atomicMax per clip and a per-tile minimum; the second kernel applies the max-8 clamp only to tiles whose
+//     minimum is below it (exact, because clamp and the monotone affine map commute), so in the common case the features are
+//     written once and never re-read.
+// The arithmetic per frame is operation for operation that of the scalar kernel this replaces (same products, same fused
+// multiply-adds, same order), so the results are bit-identical to it.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,14 +38,15 @@ namespace q3 {
 
 namespace {
 
-constexpr int TPF = 16;                                // lanes per frame
-constexpr int MEL_THREADS = 128;
-constexpr int FR_PER_IT = (MEL_THREADS / TPF);         // 8 frames in flight per CTA
+constexpr int TPF = 16;                                // lanes per frame pair
+constexpr int MEL_THREADS = 256;
+constexpr int PAIRS = MEL_THREADS / TPF;               // 16 frame pairs in flight per CTA = the 32 frames of a tile
+static_assert(MEL_TILE == 2 * PAIRS, "a CTA transforms a whole tile in one pass");
 constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 5360
 constexpr int SX_FLOATS = TILE_SAMPLES + 16;
-constexpr int XROW = 17;                               // padded row (float2) of the 16x16 transpose
-constexpr int SCR_FLOATS = 2 * TPF * XROW + 16;        // 544 floats per frame + 16: the two frames of a warp sit 16 banks apart
-constexpr int OUT_STRIDE = MEL_TILE + 1;
+constexpr int SCR_F4 = 256;                            // float4s of scratch per frame pair: the 16x16 transpose (XOR-swizzled columns,
+                                                       // no padding) and then the flat spectrum
+constexpr int HANN_PAD = 416;                          // window taps as (h, h) pairs, zero beyond 400
 
 struct MelParams {
     const float* hann;
@@ -57,8 +66,11 @@ struct MelParams {
     int* tclip;  // clip of every tile (for the clamp pass)
 };
 
+// samples | hann | tw256 | tw512 | filterbank weights | filter starts | scratch | reductions.  The tables are NOT stored as
+// (w, w) pairs: the kernel is bound by shared-memory wavefronts (ncu: LSU data pipe 80 % busy), not by issue slots, so a pair is
+// formed with a register move after an 8-byte load
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
-    return (SX_FLOATS + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + FR_PER_IT * SCR_FLOATS + MEL_BINS * OUT_STRIDE + 32) * 4;
+    return (SX_FLOATS + HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + 4 * PAIRS * SCR_F4 + 64) * 4;
 }
 
 // Widths (taps) of the eight filterbank rounds: a property of the slaney filterbank at 16 kHz / 512 points / 128 bins, checked
@@ -76,46 +88,85 @@ template <> struct FbRound<7> { static constexpr int W = 12, OFF = 28; };
 constexpr int FB_ROWS = 40;
 constexpr int FB_WIDTHS[MEL_ROUNDS] = {2, 2, 2, 3, 4, 6, 9, 12};
 
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c);
 template <int J>
-__device__ __forceinline__ float fb_round(const float* __restrict__ scr, const float* __restrict__ s_fbw, const int* __restrict__ s_fbstart, int t) {
-    const float* pp = scr + s_fbstart[t + 16 * J];
+__device__ __forceinline__ float2 fb_round(const float2* __restrict__ scr, const float* __restrict__ s_fbw, const int* __restrict__ s_fbstart, int t) {
+    const float2* pp = scr + s_fbstart[t + 16 * J];
     const float* wp = s_fbw + FbRound<J>::OFF * 16 + t;
-    float acc = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < FbRound<J>::W; w++) acc = fmaf(pp[w], wp[w * 16], acc);
+    for (int w = 0; w < FbRound<J>::W; w++) acc = fma2(pp[w], make_float2(wp[w * 16], wp[w * 16]), acc);
     return acc;
 }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+// Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot; add.rn.f32x2 etc. in PTX): a complex
+// add / subtract, or an element-wise product of two float2, is ONE instruction.  The kernel is bound by issue slots, not by bytes
+// (DESIGN.md section 4.1), so this is where its time goes down.  Same IEEE results as the scalar forms (round-to-nearest each).
+__device__ __forceinline__ unsigned long long& as_u64(float2& v) { return reinterpret_cast<unsigned long long&>(v); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(r)) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return r;
 }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(r)) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {  // element-wise
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(r)) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {  // element-wise a * b + c
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(as_u64(r)) : "l"(as_u64(a)), "l"(as_u64(b)), "l"(as_u64(c)));
+    return r;
+}
+// A complex value of both frames of a pair: re = (re_A, re_B), im = (im_A, im_B).
+struct C2 {
+    float2 re, im;
+};
+__device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
+// x * (wr + i wi) with the products and fused multiply-adds of the scalar form (fmaf(x.re, wr, -x.im * wi), fmaf(x.re, wi, x.im * wr));
+// nwi = -wi (an exact negation, so x.im * nwi = -(x.im * wi))
+__device__ __forceinline__ C2 cmul(C2 x, float2 wr, float2 wi, float2 nwi) {
+    C2 r;
+    r.re = fma2(x.re, wr, mul2(x.im, nwi));
+    r.im = fma2(x.re, wi, mul2(x.im, wr));
+    return r;
+}
+__device__ __forceinline__ C2 cmulc(C2 x, float wr, float wi) { return cmul(x, splat(wr), splat(wi), splat(-wi)); }
 
 // forward radix-4 butterfly, in place: (a,b,c,d) <- DFT4
-__device__ __forceinline__ void bfly4(float2& a, float2& b, float2& c, float2& d) {
-    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
-    a = cadd(t0, t2);
-    c = csub(t0, t2);
-    b = make_float2(t1.x + t3.y, t1.y - t3.x);
-    d = make_float2(t1.x - t3.y, t1.y + t3.x);
+__device__ __forceinline__ void bfly4(C2& a, C2& b, C2& c, C2& d) {
+    const float2 t0r = cadd(a.re, c.re), t0i = cadd(a.im, c.im), t1r = csub(a.re, c.re), t1i = csub(a.im, c.im);
+    const float2 t2r = cadd(b.re, d.re), t2i = cadd(b.im, d.im), t3r = csub(b.re, d.re), t3i = csub(b.im, d.im);
+    a.re = cadd(t0r, t2r); a.im = cadd(t0i, t2i);
+    c.re = csub(t0r, t2r); c.im = csub(t0i, t2i);
+    b.re = cadd(t1r, t3i); b.im = csub(t1i, t3r);
+    d.re = csub(t1r, t3i); d.im = cadd(t1i, t3r);
 }
 
 // forward 16-point DFT in registers.  Input x[n] natural order; on return X[k] is at x[4*(k&3) + (k>>2)].
-__device__ __forceinline__ void fft16(float2 (&x)[16]) {
+__device__ __forceinline__ void fft16(C2 (&x)[16]) {
     constexpr float C = 0.92387953251128674f, S = 0.38268343236508977f, R = 0.70710678118654752f;
 #pragma unroll
     for (int n1 = 0; n1 < 4; n1++) bfly4(x[n1], x[n1 + 4], x[n1 + 8], x[n1 + 12]);
     // x[n1 + 4*k2] *= W16^(n1*k2)
-    x[1 + 4] = cmul(x[1 + 4], make_float2(C, -S));    // W^1
-    x[1 + 8] = cmul(x[1 + 8], make_float2(R, -R));    // W^2
-    x[1 + 12] = cmul(x[1 + 12], make_float2(S, -C));  // W^3
-    x[2 + 4] = cmul(x[2 + 4], make_float2(R, -R));    // W^2
-    x[2 + 8] = make_float2(x[2 + 8].y, -x[2 + 8].x);  // W^4 = -i
-    x[2 + 12] = cmul(x[2 + 12], make_float2(-R, -R)); // W^6
-    x[3 + 4] = cmul(x[3 + 4], make_float2(S, -C));    // W^3
-    x[3 + 8] = cmul(x[3 + 8], make_float2(-R, -R));   // W^6
-    x[3 + 12] = cmul(x[3 + 12], make_float2(-C, S));  // W^9
+    x[1 + 4] = cmulc(x[1 + 4], C, -S);    // W^1
+    x[1 + 8] = cmulc(x[1 + 8], R, -R);    // W^2
+    x[1 + 12] = cmulc(x[1 + 12], S, -C);  // W^3
+    x[2 + 4] = cmulc(x[2 + 4], R, -R);    // W^2
+    {                                     // W^4 = -i: (re, im) <- (im, -re)
+        const float2 r = x[2 + 8].re;
+        x[2 + 8].re = x[2 + 8].im;
+        x[2 + 8].im = csub(make_float2(0.f, 0.f), r);
+    }
+    x[2 + 12] = cmulc(x[2 + 12], -R, -R); // W^6
+    x[3 + 4] = cmulc(x[3 + 4], S, -C);    // W^3
+    x[3 + 8] = cmulc(x[3 + 8], -R, -R);   // W^6
+    x[3 + 12] = cmulc(x[3 + 12], -C, S);  // W^9
 #pragma unroll
     for (int k2 = 0; k2 < 4; k2++) bfly4(x[4 * k2], x[4 * k2 + 1], x[4 * k2 + 2], x[4 * k2 + 3]);
 }
@@ -135,180 +186,199 @@ __device__ __forceinline__ int find_clip(const MelClip* clips, int batch, int ti
     return lo;
 }
 
-__global__ void __launch_bounds__(MEL_THREADS, 4) mel_kernel(const MelParams p) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// Stages one tile's padded samples (pad index p0 + i, i < SX_FLOATS) into dst: interior tiles with 16-byte cp.async copies, tiles
+// that touch a reflected edge with plain loads.  (Measured: prefetching the NEXT tile into a second buffer — one 512-thread CTA per
+// SM, 223 KB — is slower, 221 vs 203 us: the kernel is bound by shared-memory wavefronts, not by the staging latency, which the
+// second CTA of the SM already covers.)
+__device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const float* pcm, int f0, int tid) {
+    const float* x = pcm + c.in_off;
+    const int n = c.n;
+    const int p0 = f0 * MEL_HOP;
+    if (p0 >= MEL_NFFT / 2 && p0 + SX_FLOATS <= MEL_NFFT / 2 + n) {
+        const float4* src = reinterpret_cast<const float4*>(x + (p0 - MEL_NFFT / 2));
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < SX_FLOATS / 4; i += MEL_THREADS) cp_async16(d4 + i, src + i);
+    } else {
+        for (int i = tid; i < SX_FLOATS; i += MEL_THREADS) {
+            const int pp = p0 + i;
+            float v = 0.f;
+            if (pp < MEL_NFFT / 2) {
+                int s = MEL_NFFT / 2 - pp;
+                s = s > n - 1 ? n - 1 : s;
+                v = __ldg(x + s);
+            } else if (pp < MEL_NFFT / 2 + n) {
+                v = __ldg(x + (pp - MEL_NFFT / 2));
+            } else if (pp < MEL_NFFT + n) {
+                int s = n - 2 - (pp - MEL_NFFT / 2 - n);
+                s = s < 0 ? 0 : s;
+                v = __ldg(x + s);
+            }
+            dst[i] = v;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) {
     extern __shared__ float4 smem4[];
     float* s_x = reinterpret_cast<float*>(smem4);
-    float2* s_tw256 = reinterpret_cast<float2*>(s_x + SX_FLOATS);
-    float2* s_tw512 = s_tw256 + 256;
-    float* s_fbw = reinterpret_cast<float*>(s_tw512 + 130);
-    int* s_fbstart = reinterpret_cast<int*>(s_fbw + p.fb_rows * 16);
-    float* s_scr = reinterpret_cast<float*>(s_fbstart + 128);
-    float* s_out = s_scr + FR_PER_IT * SCR_FLOATS;
-    float* s_red = s_out + MEL_BINS * OUT_STRIDE;
-    int* s_next = reinterpret_cast<int*>(s_red + 8);  // clip of the tile this CTA takes next (searched one tile ahead)
+    float* s_hann = s_x + SX_FLOATS;                                      // [416], zero beyond 400
+    float2* s_tw256 = reinterpret_cast<float2*>(s_hann + HANN_PAD);       // [256] (wr, wi)
+    float2* s_tw512 = s_tw256 + 256;                                      // [130]
+    float* s_fbw = reinterpret_cast<float*>(s_tw512 + 130);               // [fb_rows * 16]
+    int* s_fbstart = reinterpret_cast<int*>(s_fbw + p.fb_rows * 16);      // [128]
+    float4* s_scr = reinterpret_cast<float4*>(s_fbstart + 128);           // [PAIRS][SCR_F4]
+    float* s_red = reinterpret_cast<float*>(s_scr + PAIRS * SCR_F4);      // [32]
+    int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip of the tile this CTA takes next (searched one tile ahead)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int t = lane & 15, half = lane >> 4;
+    const int t = tid & 15, pr = tid >> 4;  // lane within the frame pair, frame pair within the tile
 
+    for (int i = tid; i < HANN_PAD; i += MEL_THREADS) s_hann[i] = i < MEL_NFFT ? __ldg(&p.hann[i]) : 0.f;
     for (int i = tid; i < 256; i += MEL_THREADS) s_tw256[i] = __ldg(&p.tw256[i]);
     for (int i = tid; i < 129; i += MEL_THREADS) s_tw512[i] = __ldg(&p.tw512[i]);
     for (int i = tid; i < p.fb_rows * 16; i += MEL_THREADS) s_fbw[i] = __ldg(&p.fbw[i]);
     for (int i = tid; i < 128; i += MEL_THREADS) s_fbstart[i] = __ldg(&p.fb_start[i]);
 
-    // this lane's window taps: samples 2t + 32*n2 (+1), n2 = 0..12
-    float2 hw[13];
-#pragma unroll
-    for (int n2 = 0; n2 < 13; n2++) {
-        const int idx = 2 * t + 32 * n2;
-        hw[n2] = idx < MEL_NFFT ? make_float2(__ldg(&p.hann[idx]), __ldg(&p.hann[idx + 1])) : make_float2(0.f, 0.f);
-    }
-    float* scr = s_scr + (warp * 2 + half) * SCR_FLOATS;
-    float2* scr2 = reinterpret_cast<float2*>(scr);
-    __syncthreads();
-
-    if (tid == 0) *s_next = find_clip(p.clips, p.batch, min((int)blockIdx.x, p.total_tiles - 1));
+    float4* scr4 = s_scr + pr * SCR_F4;                    // complex pairs: (re_A, re_B, im_A, im_B)
+    float2* scrp = reinterpret_cast<float2*>(scr4);        // power spectrum pairs (P_A, P_B)
+    if (tid == 0) s_next[0] = find_clip(p.clips, p.batch, min((int)blockIdx.x, p.total_tiles - 1));
     __syncthreads();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ci = *s_next;
+        const int ci = s_next[0];
         const MelClip c = p.clips[ci];
         const int f0 = (tile - c.tile0) * MEL_TILE;
         const int nF = c.n / MEL_HOP + 1;  // frames incl. the one that is dropped (max runs over it, Q3)
-        const float* x = p.pcm + c.in_off;
-        const int n = c.n;
-
-        // ---- stage the tile's padded samples: pad index p0 + i, i < TILE_SAMPLES ----
-        const int p0 = f0 * MEL_HOP;
-        if (p0 >= MEL_NFFT / 2 && p0 + SX_FLOATS <= MEL_NFFT / 2 + n) {
-            const float4* src = reinterpret_cast<const float4*>(x + (p0 - MEL_NFFT / 2));
-            float4* dst = reinterpret_cast<float4*>(s_x);
-#pragma unroll 4
-            for (int i = tid; i < SX_FLOATS / 4; i += MEL_THREADS) dst[i] = __ldg(src + i);
-        } else {
-            for (int i = tid; i < SX_FLOATS; i += MEL_THREADS) {
-                const int pp = p0 + i;
-                float v = 0.f;
-                if (pp < MEL_NFFT / 2) {
-                    int s = MEL_NFFT / 2 - pp;
-                    s = s > n - 1 ? n - 1 : s;
-                    v = __ldg(x + s);
-                } else if (pp < MEL_NFFT / 2 + n) {
-                    v = __ldg(x + (pp - MEL_NFFT / 2));
-                } else if (pp < MEL_NFFT + n) {
-                    int s = n - 2 - (pp - MEL_NFFT / 2 - n);
-                    s = s < 0 ? 0 : s;
-                    v = __ldg(x + s);
-                }
-                s_x[i] = v;
-            }
-        }
+        stage_tile(s_x, c, p.pcm, f0, tid);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // the binary search for the next tile's clip (dependent L2 loads) overlaps this tile's transforms
-        if (tid == MEL_THREADS - 1 && tile + (int)gridDim.x < p.total_tiles) *s_next = find_clip(p.clips, p.batch, tile + gridDim.x);
+        if (tid == MEL_THREADS - 1 && tile + (int)gridDim.x < p.total_tiles) s_next[0] = find_clip(p.clips, p.batch, tile + gridDim.x);
 
+        const int fl = 2 * pr;  // local frames fl (A) and fl + 1 (B)
+        const float* xa = s_x + fl * MEL_HOP + 2 * t;
+        const float* xb = xa + MEL_HOP;
+
+        // ---- pass 1: 16-point DFTs over n2 for n1 = t  (z[n] = y[2n] + i y[2n+1], n = t + 16 n2) ----
+        C2 v[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 13; n2++) {
+            const float2 a = *reinterpret_cast<const float2*>(xa + 32 * n2);
+            const float2 b = *reinterpret_cast<const float2*>(xb + 32 * n2);
+            const float2 hw = *reinterpret_cast<const float2*>(s_hann + 2 * t + 32 * n2);  // taps of samples 2n and 2n + 1
+            v[n2].re = mul2(make_float2(a.x, b.x), splat(hw.x));
+            v[n2].im = mul2(make_float2(a.y, b.y), splat(hw.y));
+        }
+        v[13].re = v[13].im = v[14].re = v[14].im = v[15].re = v[15].im = make_float2(0.f, 0.f);
+        fft16(v);
+        // row t, column k2 lives at float4 index 16 t + (k2 ^ t): conflict-free for the row-wise stores and the column-wise loads
+        scr4[t * 16 + t] = make_float4(v[0].re.x, v[0].re.y, v[0].im.x, v[0].im.y);
+#pragma unroll
+        for (int k2 = 1; k2 < 16; k2++) {
+            const float2 tw = s_tw256[k2 * 16 + t];
+            const C2 z = cmulc(v[rev16(k2)], tw.x, tw.y);
+            scr4[t * 16 + (k2 ^ t)] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
+        }
+        __syncwarp();
+        // ---- pass 2: 16-point DFTs over n1 for k2 = t ----
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const float4 q = scr4[n1 * 16 + (t ^ n1)];
+            v[n1].re = make_float2(q.x, q.y);
+            v[n1].im = make_float2(q.z, q.w);
+        }
+        __syncwarp();
+        fft16(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) {
+            const C2 z = v[rev16(k1)];
+            scr4[16 * k1 + t] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);  // Z[16 k1 + t]
+        }
+        __syncwarp();
+        // ---- real split: bins k and 256-k from Z[k], Z[256-k];  P = |2 X|^2 ----
+        float2 pk[8], pm[8];
+        float2 p128 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = t + 16 * j;
+            const float4 zk = scr4[k];
+            const float4 zm = scr4[(256 - k) & 255];
+            const float2 w = s_tw512[k];
+            const float2 zkr = make_float2(zk.x, zk.y), zki = make_float2(zk.z, zk.w), zmr = make_float2(zm.x, zm.y), zmi = make_float2(zm.z, zm.w);
+            const float2 er = cadd(zkr, zmr), ei = csub(zki, zmi);
+            C2 o;
+            o.re = cadd(zki, zmi);
+            o.im = csub(zmr, zkr);
+            const C2 tw = cmulc(o, w.x, w.y);
+            const float2 ax = cadd(er, tw.re), ay = cadd(ei, tw.im), bx = csub(er, tw.re), by = csub(ei, tw.im);
+            pk[j] = fma2(ax, ax, mul2(ay, ay));
+            pm[j] = fma2(bx, bx, mul2(by, by));
+        }
+        if (t == 0) {
+            const float4 z0 = scr4[0];
+            const float2 z0r = make_float2(z0.x, z0.y), z0i = make_float2(z0.z, z0.w);
+            const float2 dc = mul2(splat(2.f), cadd(z0r, z0i)), ny = mul2(splat(2.f), csub(z0r, z0i));
+            pk[0] = mul2(dc, dc);
+            pm[0] = mul2(ny, ny);
+            const float4 zh = scr4[128];
+            const float2 zhr = make_float2(zh.x, zh.y), zhi = make_float2(zh.z, zh.w);
+            p128 = mul2(splat(4.f), fma2(zhr, zhr, mul2(zhi, zhi)));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = t + 16 * j;
+            scrp[k] = pk[j];
+            scrp[256 - k] = pm[j];
+        }
+        if (t == 0) scrp[128] = p128;
+        __syncwarp();
+        // ---- sparse filterbank, log10, scale; lane t owns mel bins t, t+16, ... of both frames ----
+        const bool in_max_a = (f0 + fl) < nF, in_max_b = (f0 + fl + 1) < nF;
+        const bool in_out_a = (f0 + fl) < c.frames, in_out_b = (f0 + fl + 1) < c.frames;
+        float2 accs[MEL_ROUNDS];
+        accs[0] = fb_round<0>(scrp, s_fbw, s_fbstart, t);
+        accs[1] = fb_round<1>(scrp, s_fbw, s_fbstart, t);
+        accs[2] = fb_round<2>(scrp, s_fbw, s_fbstart, t);
+        accs[3] = fb_round<3>(scrp, s_fbw, s_fbstart, t);
+        accs[4] = fb_round<4>(scrp, s_fbw, s_fbstart, t);
+        accs[5] = fb_round<5>(scrp, s_fbw, s_fbstart, t);
+        accs[6] = fb_round<6>(scrp, s_fbw, s_fbstart, t);
+        accs[7] = fb_round<7>(scrp, s_fbw, s_fbstart, t);
         float lmax = -INFINITY, lmin = INFINITY;
-#pragma unroll 1
-        for (int it = 0; it < MEL_TILE / FR_PER_IT; it++) {
-            const int fl = it * (FR_PER_IT / 2) + warp + half * (MEL_TILE / 2);  // local frame
-            const float* xs = s_x + fl * MEL_HOP + 2 * t;
-
-            // ---- pass 1: 16-point DFTs over n2 for n1 = t  (z[n] = y[2n] + i y[2n+1], n = t + 16 n2) ----
-            float2 v[16];
+        const int T = c.frames;
+        float* o = p.out + c.out_off + f0 + fl;
 #pragma unroll
-            for (int n2 = 0; n2 < 13; n2++) {
-                const float2 a = *reinterpret_cast<const float2*>(xs + 32 * n2);
-                v[n2] = make_float2(a.x * hw[n2].x, a.y * hw[n2].y);
-            }
-            v[13] = v[14] = v[15] = make_float2(0.f, 0.f);
-            fft16(v);
-            scr2[t * XROW] = v[0];
-#pragma unroll
-            for (int k2 = 1; k2 < 16; k2++) scr2[t * XROW + k2] = cmul(v[rev16(k2)], s_tw256[k2 * 16 + t]);
-            __syncwarp();
-            // ---- pass 2: 16-point DFTs over n1 for k2 = t ----
-#pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) v[n1] = scr2[n1 * XROW + t];
-            __syncwarp();
-            fft16(v);
-#pragma unroll
-            for (int k1 = 0; k1 < 16; k1++) scr2[16 * k1 + t] = v[rev16(k1)];  // Z[16 k1 + t]
-            __syncwarp();
-            // ---- real split: bins k and 256-k from Z[k], Z[256-k];  P = |2 X|^2 ----
-            float pk[8], pm[8];
-            float p128 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = t + 16 * j;
-                const float2 zk = scr2[k];
-                const float2 zm = scr2[(256 - k) & 255];
-                const float2 w = s_tw512[k];
-                const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
-                const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
-                const float2 tw = cmul(o, w);
-                const float ax = e.x + tw.x, ay = e.y + tw.y, bx = e.x - tw.x, by = e.y - tw.y;
-                pk[j] = fmaf(ax, ax, ay * ay);
-                pm[j] = fmaf(bx, bx, by * by);
-            }
-            if (t == 0) {
-                const float2 z0 = scr2[0];
-                const float dc = 2.f * (z0.x + z0.y), ny = 2.f * (z0.x - z0.y);
-                pk[0] = dc * dc;
-                pm[0] = ny * ny;
-                const float2 zh = scr2[128];
-                p128 = 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = t + 16 * j;
-                scr[k] = pk[j];
-                scr[256 - k] = pm[j];
-            }
-            if (t == 0) scr[128] = p128;
-            __syncwarp();
-            // ---- sparse filterbank, log10, scale; lane t owns mel bins t, t+16, ... ----
-            const bool in_max = (f0 + fl) < nF;
-            const bool in_out = (f0 + fl) < c.frames;
-            float accs[MEL_ROUNDS];
-            accs[0] = fb_round<0>(scr, s_fbw, s_fbstart, t);
-            accs[1] = fb_round<1>(scr, s_fbw, s_fbstart, t);
-            accs[2] = fb_round<2>(scr, s_fbw, s_fbstart, t);
-            accs[3] = fb_round<3>(scr, s_fbw, s_fbstart, t);
-            accs[4] = fb_round<4>(scr, s_fbw, s_fbstart, t);
-            accs[5] = fb_round<5>(scr, s_fbw, s_fbstart, t);
-            accs[6] = fb_round<6>(scr, s_fbw, s_fbstart, t);
-            accs[7] = fb_round<7>(scr, s_fbw, s_fbstart, t);
-#pragma unroll
-            for (int j = 0; j < MEL_ROUNDS; j++) {
-                const int m = t + 16 * j;
-                const float acc = accs[j];
-                const float L = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
-                s_out[m * OUT_STRIDE + fl] = fmaf(0.25f, L, 1.0f);
-                if (in_max) lmax = fmaxf(lmax, L);
-                if (in_out) lmin = fminf(lmin, L);
-            }
-            __syncwarp();
+        for (int j = 0; j < MEL_ROUNDS; j++) {
+            const int m = t + 16 * j;
+            const float La = 0.30102999566398120f * __log2f(fmaxf(accs[j].x, 1e-10f));
+            const float Lb = 0.30102999566398120f * __log2f(fmaxf(accs[j].y, 1e-10f));
+            if (in_out_a) o[(size_t)m * T] = fmaf(0.25f, La, 1.0f);
+            if (in_out_b) o[(size_t)m * T + 1] = fmaf(0.25f, Lb, 1.0f);
+            if (in_max_a) lmax = fmaxf(lmax, La);
+            if (in_max_b) lmax = fmaxf(lmax, Lb);
+            if (in_out_a) lmin = fminf(lmin, La);
+            if (in_out_b) lmin = fminf(lmin, Lb);
         }
 
-        // ---- tile reductions + transposed store ----
+        // ---- tile reductions ----
         lmax = warp_max(lmax);
         lmin = -warp_max(-lmin);
-        if (lane == 0) { s_red[warp] = lmax; s_red[4 + warp] = lmin; }
-        __syncthreads();
+        if (lane == 0) { s_red[warp] = lmax; s_red[16 + warp] = lmin; }
+        __syncthreads();  // also: every lane is done with s_x before the next tile is staged
         if (tid == 0) {
-            const float gm = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-            const float tm = fminf(fminf(s_red[4], s_red[5]), fminf(s_red[6], s_red[7]));
+            float gm = s_red[0], tm = s_red[16];
+#pragma unroll
+            for (int w = 1; w < MEL_THREADS / 32; w++) { gm = fmaxf(gm, s_red[w]); tm = fminf(tm, s_red[16 + w]); }
             atomicMax(p.gmax + ci, enc_ordered(gm));
             p.tmin[tile] = tm;
             p.tclip[tile] = ci;
         }
-        const int T = c.frames;
-        if (lane < MEL_TILE && f0 + lane < T) {
-            float* o = p.out + c.out_off + f0 + lane;
-#pragma unroll 4
-            for (int m = warp; m < MEL_BINS; m += MEL_THREADS / 32) o[(size_t)m * T] = s_out[m * OUT_STRIDE + lane];
-        }
-        __syncthreads();
     }
 }
 
@@ -341,8 +411,9 @@ __global__ void __launch_bounds__(256) mel_clamp_kernel(float* out, const MelCli
         const MelClip c = clips[s_clip[k]];
         const int f0 = (s_tile[k] - c.tile0) * MEL_TILE;
         const float lo_s = fmaf(0.25f, s_lo[k], 1.0f);
-        if (lane < MEL_TILE && f0 + lane < c.frames) {
-            float* o = out + c.out_off + f0 + lane + (size_t)(warp * 16) * c.frames;
+        for (int fr = lane; fr < MEL_TILE; fr += 32) {
+            if (f0 + fr >= c.frames) break;
+            float* o = out + c.out_off + f0 + fr + (size_t)(warp * 16) * c.frames;
             float v[16];
 #pragma unroll
             for (int m = 0; m < 16; m++) v[m] = o[(size_t)m * c.frames];
@@ -469,7 +540,7 @@ void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelC
     p.tmin = d_tmin;
     p.tclip = reinterpret_cast<int*>(d_tmin + total_tiles);  // d_tmin holds 2 * total_tiles words: [minimum | clip]
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
-    const int grid = std::min(total_tiles, num_sms * 4);
+    const int grid = std::min(total_tiles, num_sms * 2);  // 2 CTAs of 256 threads per SM (95 KB of shared memory each)
     mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
     mel_clamp_kernel<<<(total_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, total_tiles, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());
