@@ -202,6 +202,13 @@ int q3asr_trailing_plateau_start(const float* start_times, int n, float toleranc
  * prefill position), n_forced + 1 entries. */
 int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt,
                         const int32_t* forced, int n_forced, int32_t* argmax_out, float* top_out);
+/* The same with the audio encoder's output replaced by audio_embeds [n_audio_tokens, enc_out_dim] fp32 (rounded to bf16, like the
+ * splice of Qwen3ASR.swift:236-244 casts them): isolates the decoder in parity tests — both sides of a comparison then start
+ * from identical audio embeddings instead of two encoder outputs that differ by bf16 rounding noise.  n_audio_tokens must equal
+ * q3asr_encoder_tokens of the clip's frame count. */
+int q3asr_decode_forced_embeds(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt,
+                               const float* audio_embeds, int n_audio_tokens, const int32_t* forced, int n_forced,
+                               int32_t* argmax_out, float* top_out);
 /* full logits of the prefill's last position, [vocab] fp32 (debug / parity) */
 int q3asr_prefill_logits(q3asr_handle* h, const float* pcm, size_t n_samples, const q3asr_prompt* prompt, float* logits);
 

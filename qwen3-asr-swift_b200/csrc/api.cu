@@ -352,6 +352,13 @@ int q3asr_decode_forced(q3asr_handle* h, const float* pcm, size_t n, const q3asr
                         int32_t* argmax_out, float* top_out) {
     return guarded(h, [&](Handle& x) { decode_forced(&x, pcm, n, prompt, forced, n_forced, argmax_out, top_out); });
 }
+int q3asr_decode_forced_embeds(q3asr_handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const float* audio_embeds,
+                               int n_audio_tokens, const int32_t* forced, int n_forced, int32_t* argmax_out, float* top_out) {
+    return guarded(h, [&](Handle& x) {
+        Q3_CHECK(audio_embeds != nullptr && n_audio_tokens > 0, Q3ASR_ERR_INVALID, "decode_forced_embeds: null embeddings");
+        decode_forced(&x, pcm, n, prompt, forced, n_forced, argmax_out, top_out, audio_embeds, n_audio_tokens);
+    });
+}
 int q3asr_prefill_logits(q3asr_handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits) {
     return guarded(h, [&](Handle& x) { prefill_logits(&x, pcm, n, prompt, logits); });
 }

@@ -1091,7 +1091,7 @@ void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens
 }
 
 void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
-                   int32_t* argmax_out, float* top_out) {
+                   int32_t* argmax_out, float* top_out, const float* audio_embeds, int n_audio_tokens) {
     Q3_CHECK(forced != nullptr && n_forced >= 0 && argmax_out != nullptr, Q3ASR_ERR_INVALID, "decode_forced: bad argument");
     Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded");
     const float* pp[1] = {pcm};
@@ -1105,6 +1105,15 @@ void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* pr
     run_mel(h, bs);
     reserve_encoder(h, bs);
     run_encoder(h, bs, bs->mel_out.as<float>());
+    if (audio_embeds != nullptr) {  // parity hook: the caller's audio embeddings replace the encoder's (rounded to bf16 like the splice does)
+        Q3_CHECK(n_audio_tokens == bs->n_tok, Q3ASR_ERR_INVALID, "decode_forced_embeds: token count differs from the clip's encoder_tokens");
+        const size_t ne = (size_t)bs->n_tok * h->cfg.enc_out_dim;
+        bs->logits.reserve(ne * sizeof(float));
+        Q3_CUDA(cudaMemcpyAsync(bs->logits.p, audio_embeds, ne * sizeof(float), cudaMemcpyHostToDevice, st));
+        f32_to_bf16_launch(bs->logits.as<float>(), bs->audio.as<bf16>(), ne, st);
+        h->launches++;
+        Q3_CUDA(cudaStreamSynchronize(st));  // the caller's buffer is borrowed for the call only
+    }
     reserve_decoder(h, bs);
     std::vector<int32_t> f(forced, forced + n_forced);
     f.push_back(0);

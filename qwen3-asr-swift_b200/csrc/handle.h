@@ -201,7 +201,7 @@ void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos);
 void batch_download(Handle* h, int32_t* ids, int max_tokens, int* lens);
 void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens);
 void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, const int32_t* forced, int n_forced,
-                   int32_t* argmax_out, float* top_out);
+                   int32_t* argmax_out, float* top_out, const float* audio_embeds = nullptr, int n_audio_tokens = 0);
 void prefill_logits(Handle* h, const float* pcm, size_t n, const q3asr_prompt* prompt, float* logits);
 void config_validate(const q3asr_config& c);
 void align_indices(Handle* h, const float* const* pcm, const size_t* n, const int* rates, int batch, const int32_t* const* slotted_ids,

@@ -77,7 +77,7 @@ EXPORTS = [
     "q3asr_config_preset", "q3asr_version", "q3asr_last_error", "q3asr_create", "q3asr_destroy", "q3asr_init_random",
     "q3asr_tensor_count", "q3asr_tensor_info", "q3asr_set_tensor", "q3asr_get_tensor", "q3asr_commit_weights",
     "q3asr_load_safetensors", "q3asr_checkpoint_list", "q3asr_is_loaded", "q3asr_unload", "q3asr_memory_footprint", "q3asr_mel_frames", "q3asr_mel",
-    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_text_prepare_for_alignment", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced",
+    "q3asr_mel_batch", "q3asr_encoder_tokens", "q3asr_prompt_ids", "q3asr_text_word_pairs", "q3asr_text_last_error", "q3asr_text_prepare_for_alignment", "q3asr_encode", "q3asr_transcribe_ids", "q3asr_decode_forced", "q3asr_decode_forced_embeds",
     "q3asr_prefill_logits", "q3asr_batch_upload", "q3asr_batch_run", "q3asr_batch_download", "q3asr_sync",
     "q3asr_timer_record", "q3asr_timer_elapsed_ms", "q3asr_stage_ms", "q3asr_launch_count", "q3asr_decode_stats", "q3asr_flush_l2",
     "q3asr_profile", "q3asr_profile_report",
@@ -136,6 +136,7 @@ def lib():
         L.q3asr_encode.argtypes = [vp, vp, ci, vp, ctypes.POINTER(ci)]
         L.q3asr_transcribe_ids.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp]
         L.q3asr_decode_forced.argtypes = [vp, vp, cs, vp, vp, ci, vp, vp]
+        L.q3asr_decode_forced_embeds.argtypes = [vp, vp, cs, vp, vp, ci, vp, ci, vp, vp]
         L.q3asr_prefill_logits.argtypes = [vp, vp, cs, vp, vp]
         L.q3asr_batch_upload.argtypes = [vp, vp, vp, ci, vp]
         L.q3asr_batch_run.argtypes = [vp, ci, ci, ci]
@@ -790,6 +791,18 @@ class Qwen3ASRModel:
         pp = _PromptPack([prompt] if prompt else None, 1)
         self._ck(lib().q3asr_decode_forced(self._h, audio.ctypes.data, audio.size, pp.ptr, forced.ctypes.data, forced.size,
                                            am.ctypes.data, top.ctypes.data))
+        return am, top
+
+    def decode_forced_embeds(self, audio, audio_embeds, forced, prompt=None):
+        """decode_forced with the encoder's output replaced by audio_embeds [tokens, enc_out_dim] (parity hook: isolates the decoder)."""
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        emb = np.ascontiguousarray(audio_embeds, dtype=np.float32)
+        forced = np.ascontiguousarray(forced, dtype=np.int32)
+        am = np.zeros(forced.size + 1, dtype=np.int32)
+        top = np.zeros(forced.size + 1, dtype=np.float32)
+        pp = _PromptPack([prompt] if prompt else None, 1)
+        self._ck(lib().q3asr_decode_forced_embeds(self._h, audio.ctypes.data, audio.size, pp.ptr, emb.ctypes.data, emb.shape[0],
+                                                  forced.ctypes.data, forced.size, am.ctypes.data, top.ctypes.data))
         return am, top
 
     def prefill_logits(self, audio, prompt=None):

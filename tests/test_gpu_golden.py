@@ -11,20 +11,26 @@ from both the bf16-emulating and the plain fp32 oracle.
 
 Why not plain equality everywhere: two correct bf16 implementations of an 18-layer encoder + 28-layer decoder do not agree bit for
 bit.  Every op rounds to bf16; a different fp32 summation order moves a few values across a rounding boundary and the flips spread.
-Measured (tests/golden/make_golden.py, tools/parity_diag.py): the oracle against ITSELF with float64
-accumulation differs by up to 10 ulps in the best logit and disagrees on 4 % of the argmaxes; the bf16 oracle is 1.1e-2 (relative
-L2) away from the fp32 oracle on the encoder output, and the B200 kernels are 1.1e-2 away from the fp32 oracle too and 1.25e-2
-from the bf16 oracle — i.e. the kernels are as good a bf16 implementation as the restatement is.  An id is only determined by
-the arithmetic contract where its top-1 / top-2 margin exceeds that noise; NOISE = 24 ulps is the bound used here.
+Measured (tests/golden/make_golden.py, tools/parity_diag.py):
+  * the oracle against ITSELF with float64 accumulation in the decoder: best logit up to 10 ulps apart, 3-4 % of the argmaxes differ,
+    free-running ids diverge after 14-28 steps;
+  * the B200 decoder fed the ORACLE's encoder output (q3asr_decode_forced_embeds): best logit median 2-3 / 90th percentile 6-7 /
+    largest 9-20 ulps apart, 5-8 % of the argmaxes differ, every disagreement at a margin of at most 12 ulps — the same level;
+  * end to end (the kernels' own encoder output, which is 1.25e-2 in relative L2 from the bf16 oracle's — exactly as far as the bf16
+    oracle is from the fp32 oracle, 1.1e-2, and the kernels are from the fp32 oracle, 1.1e-2): 90th percentile 8-10, largest
+    15-44 ulps, disagreements up to a margin of 29 ulps.
+An id is only determined by the arithmetic contract where its top-1 / top-2 margin exceeds that noise.  The bounds used here:
+NOISE_DEC = 16 ulps with the decoder isolated, NOISE_E2E = 40 ulps end to end.
 
 What is asserted:
   * encoder, over the FULL output: relative L2 <= 2e-2 against the bf16-emulating oracle, and against the plain fp32 oracle at
     most 1.5 x what the bf16 oracle itself shows (noise-calibrated) and <= 3e-2;
   * prefill logits, full vocabulary: the same noise-calibrated bound against the fp32 oracle;
-  * teacher-forced steps (the oracle's own ids, and a pseudo-random token stream), EVERY step constrained: the chosen id equals
-    the oracle's wherever the oracle's margin exceeds NOISE; elsewhere it is one of the oracle's eight best tokens whose logit is
-    within NOISE of the best; the chosen token's logit is within 2 x NOISE of the oracle's logit for it (median <= 6 ulps); at
-    most 20 % of the steps differ from the oracle's id (measured: 8-16 %; the oracle against itself with float64 accumulation: 4-12 %);
+  * teacher-forced steps (the oracle's own ids, and a pseudo-random token stream), decoder isolated and end to end, EVERY step
+    constrained: the chosen id equals the oracle's wherever the oracle's margin exceeds the bound; elsewhere it is one of the
+    oracle's eight best tokens whose logit is within the bound of the best; the chosen token's logit is within 2 x the bound of the
+    oracle's logit for it (median <= 6 ulps); at most 15 % (decoder isolated) / 20 % (end to end) of the steps differ from the
+    oracle's id;
   * free-running greedy ids: equal to the oracle's on every step before the first in-noise step; a deviation is only accepted at
     such a step, towards an in-noise candidate (nothing after it can be compared).  The test prints the length of the common
     prefix next to the prefix two CPU summation orders share (`cpu_cpu_prefix`);
@@ -41,6 +47,8 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NOISE_DEC = 16.0   # bf16 ulps of the best logit: decoder isolated (both sides start from the oracle's audio embeddings)
+NOISE_E2E = 40.0   # end to end (each side behind its own encoder)
 FIXTURES = {"q06b_clip30s": "0.6B", "q06b_ragged": "0.6B", "q17b_clip15s": "1.7B"}
 
 
@@ -85,7 +93,7 @@ def _allowed(tk_ids, tk_vals, noise_ulps):
     return [int(i) for i, v in zip(tk_ids, tk_vals) if float(tk_vals[0]) - float(v) <= noise_ulps * u]  # includes every exact tie
 
 
-def check_forced(got_ids, got_tops, ids, tops, margins, tk_ids, tk_vals, noise_ulps, what):
+def check_forced(got_ids, got_tops, ids, tops, margins, tk_ids, tk_vals, noise_ulps, what, max_differ=0.2, min_strict=0.05):
     """Per-step check of a teacher-forced run; returns (steps that differ from the oracle's id, strict steps)."""
     assert len(got_ids) == len(ids), (what, len(got_ids), len(ids))
     differ = strict = 0
@@ -103,8 +111,8 @@ def check_forced(got_ids, got_tops, ids, tops, margins, tk_ids, tk_vals, noise_u
         diffs.append(abs(float(got_tops[s]) - ref_val) / u)
         assert diffs[-1] <= 2 * noise_ulps, (what, s, float(got_tops[s]), ref_val, u)
     assert np.median(diffs) <= 6, (what, float(np.median(diffs)))
-    assert strict >= 0.3 * len(ids), (what, strict)
-    assert differ <= 0.2 * len(ids), (what, differ)
+    assert strict >= min_strict * len(ids), (what, strict)  # the share of steps that are plain equality checks
+    assert differ <= max_differ * len(ids), (what, differ)
     return differ, strict
 
 
@@ -156,7 +164,7 @@ def test_prefill_logits_full_vocabulary(models, name):
     e_gpu, e_ref = _rel_l2(got, l32), _rel_l2(lbf, l32)
     assert e_gpu <= 1.5 * e_ref + 1e-3, (name, e_gpu, e_ref)
     assert _rel_l2(got, lbf) <= 2.0 * e_ref + 1e-3, (name, _rel_l2(got, lbf), e_ref)
-    assert int(np.argmax(got)) in _allowed(g["topk_ids"][0], g["topk_vals"][0], float(g["noise_ulps"]))
+    assert int(np.argmax(got)) in _allowed(g["topk_ids"][0], g["topk_vals"][0], NOISE_E2E)
     print(f"{name}: prefill logits relL2 vs fp32 oracle {e_gpu:.2e} (the bf16 oracle itself: {e_ref:.2e}), vs bf16 oracle {_rel_l2(got, lbf):.2e}")
 
 
@@ -168,7 +176,7 @@ def test_free_running_ids(models, name):
     m = models(FIXTURES[name], int(g["seed"]))
     x = synth.clip(int(g["clip_index"]), int(g["n_samples"]))
     got = m.transcribe_ids([x], max_tokens=len(ids), stop_on_eos=False)[0]
-    first = check_free_running(got, ids, g["tops"], g["margins"], g["topk_ids"], g["topk_vals"], float(g["noise_ulps"]), name)
+    first = check_free_running(got, ids, g["tops"], g["margins"], g["topk_ids"], g["topk_vals"], NOISE_E2E, name)
     print(f"{name}: first {first} of {len(ids)} free-running ids equal to the oracle's (two CPU summation orders share {int(g['cpu_cpu_prefix'])})")
     # the same clip inside a batch (other slots: other clips), at batch position 5: ids must not depend on the neighbours
     others = [synth.clip(900 + i, int(g["n_samples"]) - 1600 * i) for i in range(7)]
@@ -184,16 +192,20 @@ def test_teacher_forced(models, monkeypatch, name, warps):
     bench's batches of 64 use)."""
     monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
     g = _load(name)
-    noise = float(g["noise_ulps"])
     m = models(FIXTURES[name], int(g["seed"]))
     x = synth.clip(int(g["clip_index"]), int(g["n_samples"]))
     ids = g["ids"]
-    got_ids, got_tops = m.decode_forced(x, ids[:-1])  # the oracle's own ids as the forced stream
-    d1, s1 = check_forced(got_ids, got_tops, ids, g["tops"], g["margins"], g["topk_ids"], g["topk_vals"], noise, name + " own ids")
-    msg = f"{name} warps {warps}: own ids {len(ids) - d1}/{len(ids)} equal ({s1} strict steps)"
-    if "forced" in g:
-        got_ids, got_tops = m.decode_forced(x, g["forced"])
-        d2, s2 = check_forced(got_ids, got_tops, g["forced_ids"], g["forced_tops"], g["forced_margins"], g["forced_topk_ids"],
-                              g["forced_topk_vals"], noise, name + " random stream")
-        msg += f"; random stream {len(got_ids) - d2}/{len(got_ids)} equal ({s2} strict steps)"
+    ref_enc = _bf16_bits_to_f32(g["encoder_bf16"])
+    msg = f"{name} warps {warps}:"
+    for tag, noise, max_differ, min_strict in (("decoder isolated", NOISE_DEC, 0.15, 0.4), ("end to end", NOISE_E2E, 0.2, 0.05)):
+        run = (lambda f: m.decode_forced_embeds(x, ref_enc, f)) if tag == "decoder isolated" else (lambda f: m.decode_forced(x, f))
+        got_ids, got_tops = run(ids[:-1])  # the oracle's own ids as the forced stream
+        d1, s1 = check_forced(got_ids, got_tops, ids, g["tops"], g["margins"], g["topk_ids"], g["topk_vals"], noise, f"{name} own ids, {tag}",
+                              max_differ, min_strict)
+        msg += f" [{tag}] own ids {len(ids) - d1}/{len(ids)} equal ({s1} strict)"
+        if "forced" in g:
+            got_ids, got_tops = run(g["forced"])
+            d2, s2 = check_forced(got_ids, got_tops, g["forced_ids"], g["forced_tops"], g["forced_margins"], g["forced_topk_ids"],
+                                  g["forced_topk_vals"], noise, f"{name} random stream, {tag}", max_differ, min_strict)
+            msg += f", random stream {len(got_ids) - d2}/{len(got_ids)} equal ({s2} strict)"
     print(msg)

@@ -36,9 +36,10 @@ for name in (sys.argv[1:] or list(SIZES)):
         r32 = (np.asarray(g["encoder_fp32_as_bf16"], dtype=np.uint32) << 16).view(np.float32)
         msg += f", vs fp32 oracle {np.linalg.norm(enc - r32) / np.linalg.norm(r32):.3e}; bf16 oracle vs fp32 oracle {np.linalg.norm(ref - r32) / np.linalg.norm(r32):.3e}"
     print(msg)
-    for tag, forced, ids, tops, margins in (("own ids", g["ids"][:-1], g["ids"], g["tops"], g["margins"]),) + (
-            (("random stream", g["forced"], g["forced_ids"], g["forced_tops"], g["forced_margins"]),) if "forced" in g else ()):
-        got_ids, got_tops = m.decode_forced(x, forced)
+    streams = (("own ids", g["ids"][:-1], g["ids"], g["tops"], g["margins"]),) + (
+        (("random stream", g["forced"], g["forced_ids"], g["forced_tops"], g["forced_margins"]),) if "forced" in g else ())
+    for tag, forced, ids, tops, margins in [(t + " (GPU encoder)",) + tuple(r) for t, *r in streams] + [(t + " (ORACLE encoder output)",) + tuple(r) for t, *r in streams]:
+        got_ids, got_tops = m.decode_forced_embeds(x, ref, forced) if "ORACLE" in tag else m.decode_forced(x, forced)
         u = ulp(tops)
         d = np.abs(got_tops - tops) / u
         same = got_ids == ids
