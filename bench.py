@@ -309,8 +309,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a host-side group for the one long wait of the run (rank 0's single-process section): an NCCL barrier would leave a
+        # spinning kernel on every other rank's GPU, taking SMs from the very measurement it waits for
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if world > 1:
@@ -463,7 +467,8 @@ def main():
                 extras = pool_extras(world, max(1, min(args.steps, 3)))
             except Exception as e:  # the headline line must still be printed
                 extras = {"error": repr(e)}
-        barrier()
+        if world > 1:
+            dist.barrier(group=cpu_group)  # the other ranks wait on the host, their GPUs idle
 
     if rank == 0:
         line = {

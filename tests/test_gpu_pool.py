@@ -93,3 +93,27 @@ def test_1p7b_configuration(built_lib, monkeypatch):
         assert m.memory_footprint > 4e9
     finally:
         m.close()
+
+
+def test_pool_on_distinct_devices_full_size(built_lib):
+    """One process driving several GPUs at the 0.6B dimensions: every device needs its own > 48 KB dynamic-shared-memory opt-in of
+    every kernel (cudaFuncSetAttribute is per device; a process-wide flag let only the first device launch).  Skipped on a
+    one-GPU box; run with `gpurun --gpus 2` (tools/gpu_multi.sh)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    clips = [synth.clip(50 + i, 16000 * (2 + i % 3)) for i in range(3 * n)]
+    single = built_lib.Qwen3ASRModel.random_init("0.6B", seed=20260418, device=n - 1)  # the LAST device first: it is not device 0
+    try:
+        want = [t.tolist() for t in single.transcribe_ids(clips, max_tokens=12, stop_on_eos=False)]
+    finally:
+        single.close()
+    pool = built_lib.Pool("0.6B", devices=tuple(range(n)), seed=20260418)
+    try:
+        got = [t.tolist() for t in pool.transcribe_ids(clips, max_tokens=12, stop_on_eos=False, max_batch_per_gpu=2)]
+        assert got == want
+        got = [t.tolist() for t in pool.transcribe_ids(clips, max_tokens=12, stop_on_eos=True, max_batch_per_gpu=3)]
+        assert all(g == w[:len(g)] for g, w in zip(got, want))
+    finally:
+        pool.close()
