@@ -325,9 +325,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                             f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
                         }
                     }
-                    if (p.gelu) {
+                    if (p.gelu) {  // two values per instruction on the packed fp32 pipe (common.cuh)
 #pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = gelu_erf(f[j]);
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 gg = gelu_erf2(make_float2(f[j], f[j + 1]));
+                            f[j] = gg.x;
+                            f[j + 1] = gg.y;
+                        }
                     }
                     if (zero) {
 #pragma unroll

@@ -23,7 +23,7 @@ __device__ __forceinline__ void st8(bf16* p, float a, float b, float c, float d)
 __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ mel, const Conv1Chunk* __restrict__ chunks,
                                                     const bf16* __restrict__ w, const bf16* __restrict__ bias, int C, int chunk_w,
                                                     bf16* __restrict__ out) {
-    extern __shared__ float s_in[];  // [3][chunk_w + 2]
+    extern __shared__ float2 s_in[];  // [3][chunk_w + 2] as (x, x) pairs: the packed multiply-adds below take them as they are
     const int oh = blockIdx.x, g = blockIdx.y;
     const Conv1Chunk c = chunks[g];
     const int pitch = chunk_w + 2;
@@ -32,37 +32,29 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ me
         const int ih = 2 * oh + r - 1;
         float v = 0.f;
         if (ih >= 0 && ih < 128 && j >= 0 && j < c.len) v = __ldg(mel + c.mel_off + (long long)ih * c.T + c.f0 + j);
-        s_in[i] = v;
+        s_in[i] = make_float2(v, v);
     }
     __syncthreads();
     const int OW = chunk_w / 2;
     const int w1 = (c.w0 - 1) / 2 + 1;  // valid output columns of this chunk
     bf16* orow = out + ((size_t)g * 64 + oh) * OW * C;
     for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
-        float wa[9], wb[9];
+        // the thread's two output channels ride the two lanes of the packed fp32 pipe: 9 FFMA2 + one packed GELU per output pair
+        float2 wab[9];
 #pragma unroll
-        for (int t = 0; t < 9; t++) {
-            wa[t] = __bfloat162float(w[(2 * cp) * 9 + t]);
-            wb[t] = __bfloat162float(w[(2 * cp + 1) * 9 + t]);
-        }
-        const float ba = __bfloat162float(bias[2 * cp]), bb = __bfloat162float(bias[2 * cp + 1]);
+        for (int t = 0; t < 9; t++) wab[t] = make_float2(__bfloat162float(w[(2 * cp) * 9 + t]), __bfloat162float(w[(2 * cp + 1) * 9 + t]));
+        const float2 bab = make_float2(__bfloat162float(bias[2 * cp]), __bfloat162float(bias[2 * cp + 1]));
         for (int ow = 0; ow < OW; ow++) {
-            float a = 0.f, b = 0.f;
+            float2 ab = make_float2(0.f, 0.f);
             if (ow < w1) {
-                a = ba;
-                b = bb;
+                ab = bab;
 #pragma unroll
                 for (int r = 0; r < 3; r++)
 #pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        const float x = s_in[r * pitch + 2 * ow + q];  // column 2*ow + q - 1, stored at +1
-                        a = fmaf(x, wa[r * 3 + q], a);
-                        b = fmaf(x, wb[r * 3 + q], b);
-                    }
-                a = gelu_erf(a);
-                b = gelu_erf(b);
+                    for (int q = 0; q < 3; q++) ab = f2_fma(s_in[r * pitch + 2 * ow + q], wab[r * 3 + q], ab);  // column 2*ow + q - 1, stored at +1
+                ab = gelu_erf2(ab);
             }
-            *reinterpret_cast<uint32_t*>(orow + (size_t)ow * C + 2 * cp) = pack_bf16x2(a, b);
+            *reinterpret_cast<uint32_t*>(orow + (size_t)ow * C + 2 * cp) = pack_bf16x2(ab.x, ab.y);
         }
     }
 }
@@ -1131,7 +1123,7 @@ void conv1_launch(const float* mel, const Conv1Chunk* chunks, int n_chunks, cons
                   bf16* out, cudaStream_t st) {
     if (n_chunks <= 0) return;
     dim3 grid(64, n_chunks);
-    conv1_kernel<<<grid, 256, sizeof(float) * 3 * (chunk_w + 2), st>>>(mel, chunks, w, bias, C, chunk_w, out);
+    conv1_kernel<<<grid, 256, sizeof(float2) * 3 * (chunk_w + 2), st>>>(mel, chunks, w, bias, C, chunk_w, out);
     Q3_CUDA(cudaGetLastError());
 }
 
