@@ -419,6 +419,10 @@ def main():
             return v["ms"] / nprof * ((MAX_TOKENS - 1) if k.startswith("dec_") else 1)
         kernel_of = {"dec_layers": "megastep_kernel (28 decoder layers of one decode step)", "dec_attn": "decode_attn_mma_kernel", "mel": "mel_kernel", "dec_qkv": "gemm_skinny_kernel (dec_qkv)",
                      "dec_o": "gemm_skinny_kernel (dec_o)", "dec_down": "gemm_skinny_kernel (dec_down)"}
+        # "dec_attn_chain" is a measurement, not part of the step: the decode attention of all layers launched back to back (one
+        # event pair around the chain, programmatic dependent launch as in the step graph) after the last decode step
+        chain = rep.pop("dec_attn_chain", None)
+        families.pop("dec_attn_chain", None)
         ranked = sorted(((est_ms(k, v), k) for k, v in rep.items() if k != "decode_graph_steps" and (v["flops"] or v["bytes"])), reverse=True)
         for k in families:
             families[k]["est_ms_in_step"] = est_ms(k, rep[k])
@@ -443,6 +447,21 @@ def main():
         roof = roof_of(ranked[0][1])  # the dominant kernel of the step: the persistent decode-layers kernel (weights + KV streaming, HBM-bound)
         roof["how"] = ("CUDA events on the library's stream around each launch of the kernel in extra profiled steps of the same workload "
                        "(eager launches; the timed region replays the same launch inside a CUDA graph)")
+        if chain and ranked[0][1] == "dec_attn" and chain["ms"] > 0:
+            # the same kernel launched for every layer back to back behind ONE event pair (no event records and no launch ramp
+            # between the launches, as inside the replayed step): its sustained duration.  `frac` is that figure; the eager
+            # single-launch figure stays beside it as `standalone`.
+            n_layers = rep["dec_attn"]["launches"] // nprof  # one eager launch per decoder layer and profiled step
+            n_launch = (chain["launches"] or 1) * n_layers
+            ms_l = chain["ms"] / n_launch
+            standalone = {k: roof[k] for k in ("achieved", "frac", "ms_per_launch", "algorithmic_per_launch")}
+            roof.update({"achieved": chain["bytes"] / chain["ms"] / 1e6, "ms_per_launch": ms_l,
+                         "algorithmic_per_launch": chain["bytes"] / n_launch, "standalone": standalone})
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            roof["est_share_of_step"] = ms_l * n_layers * (MAX_TOKENS - 1) / (dev_ms / args.steps)
+            roof["how"] = ("one CUDA-event pair on the library's stream around the kernel launched for all decoder layers back to back "
+                           "(largest context of the step sequence, programmatic dependent launch as inside the replayed step graph), "
+                           "in extra profiled steps of the same workload; `standalone` = event pairs around single eager launches")
         # the top dense tensor-core family (encoder / prefill GEMMs and convolutions; the decode-step products are weight streaming)
         tens = [k for _, k in ranked if rep[k]["flops"] > 0 and not k.startswith("dec_") and k != "lm_head" and not k.endswith("attn")]
         roof_gemm = roof_of(tens[0]) if tens else None

@@ -37,6 +37,7 @@ struct FaParams {
     bf16* o;
     int ldo;
     int group;  // query heads per kv head
+    int o32;    // output rows are 32-byte aligned: 256-bit stores
     float scale_log2;
 };
 
@@ -79,7 +80,8 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const int seg = blockIdx.z;
     const int head0 = NQ == 1 ? blockIdx.y : blockIdx.y * NQ;
     const int len = p.len[seg];
-    const int q0 = blockIdx.x * FA_BQ;
+    // causal: the last query tile of a segment sees the most key blocks, so tiles are handed out heaviest first
+    const int q0 = (CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * FA_BQ;
     if (q0 >= len) return;
     const int row0 = p.row0[seg];
     const int kvh = head0 / p.group;
@@ -319,19 +321,20 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         bf16* orow = p.o + (size_t)(row0 + q_abs) * p.ldo + head * HD;
 #pragma unroll
-        for (int c = 0; c < HD / 32; c++) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem_pv + lane_addr + c * 32, v);
+        for (int c = 0; c < HD / 16; c++) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x16(tmem_pv + lane_addr + c * 16, v);
             ptx::tmem_ld_wait();
             if (q_abs < len) {
+                uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        w[e] = pack_bf16x2((o_acc[c * 32 + i * 8 + 2 * e] + __uint_as_float(v[i * 8 + 2 * e])) * inv,
-                                           (o_acc[c * 32 + i * 8 + 2 * e + 1] + __uint_as_float(v[i * 8 + 2 * e + 1])) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int e = 0; e < 8; e++)
+                    w[e] = pack_bf16x2((o_acc[c * 16 + 2 * e] + __uint_as_float(v[2 * e])) * inv, (o_acc[c * 16 + 2 * e + 1] + __uint_as_float(v[2 * e + 1])) * inv);
+                if (p.o32) {  // one 256-bit store per 16 dims (a thread owns a row: 32 lines per warp instruction either way)
+                    st_global_v8(orow + c * 16, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+                } else {
+                    *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
                 }
             }
         }
@@ -378,6 +381,7 @@ void flash_attn_tc_launch(const bf16* q, int ldq, const bf16* k, int ldk, const 
     p.o = o;
     p.ldo = ldo;
     p.group = group;
+    p.o32 = (reinterpret_cast<uintptr_t>(o) & 31) == 0 && ldo % 16 == 0 && head_dim % 16 == 0;
     p.scale_log2 = scale * 1.4426950408889634f;
     static const bool no_pair = getenv("Q3ASR_ATTN_NO_PAIR") != nullptr && atoi(getenv("Q3ASR_ATTN_NO_PAIR")) != 0;
     const bool pair = group == 2 && head_dim == 128 && !no_pair;  // GQA: both query heads of a kv head in one CTA

@@ -139,6 +139,25 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     const float2 h = f2_mul(x, f2_splat(0.5f));
     return f2_fma(h, e, h);
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  The GEMM / attention epilogues hold one output ROW per thread, so a warp's
+// 32 lanes touch 32 different lines per instruction: halving the instructions per row halves the L1 tag-stage work of an epilogue.
+// 32-byte aligned addresses only.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                             uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+struct U8 {
+    uint32_t v[8];
+};
+__device__ __forceinline__ U8 ld_global_nc_v8(const void* p) {
+    U8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
 // SiLU: x * sigmoid(x)
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 

@@ -213,7 +213,8 @@ void reserve_decoder(Handle* h, BatchState* bs) {
         const int n_pos = bs->pages_per_seq * KV_PAGE;
         if (bs->rope_n < n_pos) {
             bs->rope_tab.reserve((size_t)n_pos * 64 * sizeof(float2));
-            rope_table_launch(h->model->inv_freq, n_pos, bs->rope_tab.as<float2>(), h->stream);
+            bs->rope_tab_t.reserve((size_t)n_pos * 64 * sizeof(float2));
+            rope_table_launch(h->model->inv_freq, n_pos, bs->rope_tab.as<float2>(), bs->rope_tab_t.as<float2>(), h->stream);
             h->launches++;
             bs->rope_n = n_pos;
         }
@@ -420,7 +421,7 @@ void decoder_layers(Handle* h, BatchState* bs, int rows, bool prefill) {
             e.epi = EPI_QKV;
             e.out = qkv;
             e.ldo = nqkv;
-            e.rp = QkvRope{pos, row_seq, bs->rope_tab.as<float2>(), w.q_norm, w.k_norm, q, bs->dkc.as<bf16>(), kc.pool, kc.page_table,
+            e.rp = QkvRope{pos, row_seq, bs->rope_tab_t.as<float2>(), bs->rope_n, w.q_norm, w.k_norm, q, bs->dkc.as<bf16>(), kc.pool, kc.page_table,
                            kc.max_pages, kc.layers, l, c.dec_heads, c.dec_kv_heads, c.dec_rms_eps};
             gemm(xn, H, rows, H, w.qkv_w, nqkv, e, st);
         } else {
@@ -695,6 +696,31 @@ unsigned long long capture_step_graph(Handle* h, BatchState* bs, int stop_on_eos
     return per_step;
 }
 
+// Profiling only (q3asr_profile): the decode attention of every layer launched back to back, chained with programmatic dependent
+// launch as inside the step graph, bracketed by ONE pair of events ("dec_attn_chain": one entry per call, bytes = the keys and
+// values all the launches read).  A single eager launch between two event records also pays the launch ramp and the records
+// (bench.py reports that figure as `standalone`); the chain is the kernel's sustained duration, the state it runs in inside the
+// step.  Called after the last decode step of a batch: the launches re-read the cache and write the (by then meaningless) new-token
+// row of the next position, which nothing reads any more.
+void profile_attn_chain(Handle* h, BatchState* bs) {
+    const q3asr_config& c = h->cfg;
+    const Model& m = *h->model;
+    cudaStream_t st = h->stream;
+    const int B = bs->dec_rows;
+    const int hd = c.dec_head_dim, nq = c.dec_heads * hd, nkv = c.dec_kv_heads * hd, nqkv = nq + 2 * nkv;
+    const KvCache kc = kv_cache(h, bs);
+    const int s_qkv = gemm_skinny_splits(nqkv, c.dec_hidden, SK_PARTIAL);
+    const float scale = 1.0f / sqrtf((float)hd);
+    double kv_bytes = 0;
+    for (const ClipInfo& ci : bs->clips) kv_bytes += 2.0 * 2.0 * nkv * (ci.prompt_len + bs->steps_done);
+    ProfScope ps(h, "dec_attn_chain", 0, c.dec_layers * kv_bytes);
+    PdlScope pdl(env_int("Q3ASR_NO_PDL", 0) == 0);
+    for (int l = 0; l < c.dec_layers; l++)
+        decode_attn_fused_launch(bs->dws.as<float>(), s_qkv, (long long)B * nqkv, nqkv, m.dec[l].q_norm, m.dec[l].k_norm, bs->st_pos.as<int>(),
+                                 c.dec_rms_eps, bs->rope_tab.as<float2>(), kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale,
+                                 bs->datt.as<bf16>(), h->num_sms, st);
+}
+
 bool mega_wanted(Handle* h, BatchState* bs) {
     return bs->dec_rows <= SKINNY_MAX_ROWS && h->cfg.dec_heads == 2 * h->cfg.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0 &&
            megastep_supported(h, bs);
@@ -770,6 +796,9 @@ void run_decode(Handle* h, BatchState* bs, int max_tokens, int stop_on_eos, bool
         }
     }
     bs->steps_done = step;
+    if (h->prof_on && step >= max_tokens && !stop_on_eos && !bs->mega_ready && bs->dec_rows > 0 && bs->dec_rows <= SKINNY_MAX_ROWS &&
+        h->cfg.dec_heads == 2 * h->cfg.dec_kv_heads && env_int("Q3ASR_NO_SKINNY", 0) == 0)
+        profile_attn_chain(h, bs);
 }
 
 }  // namespace

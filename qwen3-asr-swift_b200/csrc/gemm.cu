@@ -272,6 +272,9 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     if (bn == 0 && e.epi == EPI_QKV) bn = (N % 256 == 0 && m_tiles * (N / 256) >= g_num_sms) ? 256 : 128;  // tiles of whole heads
     if (bn == 0) bn = gemm_pick_bn(N, e.epi, m_tiles);
     Q3_CHECK(e.epi != EPI_QKV || ((bn == 128 || bn == 256) && N % bn == 0 && e.rp.q != nullptr), 1, "gemm: fused q/k/v epilogue arguments");
+    Q3_CHECK(e.epi != EPI_QKV || (((reinterpret_cast<uintptr_t>(e.out) | reinterpret_cast<uintptr_t>(e.rp.q) | reinterpret_cast<uintptr_t>(e.rp.kc) |
+                                    reinterpret_cast<uintptr_t>(e.rp.pool)) & 31) == 0 && e.ldo % 16 == 0),
+             1, "gemm: the fused q/k/v epilogue stores 32 bytes at a time: buffers must be 32-byte aligned");
     Q3_CHECK(N % bn == 0, 1, "gemm: N must be a multiple of the tile width");
     Q3_CHECK(e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0, 1, "gemm: SwiGLU tiles must be multiples of 64 columns");
     p.tiles_n = N / bn;
@@ -308,8 +311,9 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     const char* env2 = getenv("Q3ASR_2CTA");  // "0" never, "1" whenever the tile shape allows (tests), unset: large problems only
     const int mode2 = env2 && *env2 ? atoi(env2) : -1;
     // measured (profiles/): pairing lifts the plain products (q/k/v, o, down, fc2, conv_out: +9..19 %, 1.2-1.3 PFLOP/s) to the cuBLAS
-    // ceiling; GELU / SwiGLU tiles are bound by their epilogues and the stride-2 convolutions by their TMA boxes, where it does not pay
-    const bool plain = (e.epi == EPI_NORMAL || e.epi == EPI_QKV) && !e.gelu && s.sw == 1 && s.sh == 1;
+    // ceiling; SwiGLU tiles are bound by their epilogues and the stride-2 convolutions by their TMA boxes, where it does not pay
+    // (round 2: with the packed-fp32 GELU the fc1 tiles are no longer epilogue-bound and pairing pays there too: 3.20 -> 3.08 ms)
+    const bool plain = (e.epi == EPI_NORMAL || e.epi == EPI_QKV) && s.sw == 1 && s.sh == 1;
     const bool pair = mode2 != 0 && !simt && (e.epi == EPI_NORMAL || e.epi == EPI_SWIGLU || e.epi == EPI_QKV) && (bn == 128 || bn == 160 || bn == 224 || bn == 256) &&
                       (mode2 == 1 || (plain && m_tiles * p.tiles_n >= 4L * g_num_sms)) && (e.epi != EPI_SWIGLU || bn % (2 * GU_UNIT) == 0);
     {

@@ -41,7 +41,9 @@ enum GemmEpi : int {
 struct QkvRope {
     const int* pos;        // [rows] position of every packed row
     const int* row_seq;    // [rows] sequence (page-table row) of every packed row
-    const float2* rope;    // [pos][64] (cos, sin)
+    const float2* rope;    // [64][rope_n] (cos, sin), dimension-major: lane = token row, so a warp's 32 loads of one dimension fall on
+                           // consecutive positions (2-3 cache lines instead of 32 with the [pos][64] table of the decode kernels)
+    int rope_n;
     const bf16 *qw, *kw;   // per-head norm weights [128]
     bf16 *q, *kc;          // q [rows, heads*128], k [rows, kv_heads*128]
     bf16* pool;            // paged cache [pages][layers][2][kv_heads][32][128]
@@ -124,14 +126,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
         row = __ldg(p.row_map + row);
         row_ok = row >= 0;
     }
-    ptx::mbar_wait(tfull, aphase);
-    ptx::tc_fence_after();
     const uint32_t t_row = tmem_acc + (uint32_t(q * 32) << 16);
+    int qkv_pos = 0, qkv_page = 0;  // EPI_QKV: the row's position and KV page, fetched under the wait for the accumulator
+    if constexpr (EPI == EPI_QKV) {
+        if (row_ok) {
+            qkv_pos = __ldg(p.rp.pos + row);
+            qkv_page = __ldg(p.rp.page_table + (size_t)__ldg(p.rp.row_seq + row) * p.rp.max_pages + qkv_pos / 32);
+        }
+    }
+    if constexpr (EPI != EPI_NORMAL && EPI != EPI_F32) {  // (the plain epilogue prefetches its bias / residual rows before it waits)
+        ptx::mbar_wait(tfull, aphase);
+        ptx::tc_fence_after();
+    }
 
     if constexpr (EPI == EPI_SWIGLU) {
         // weight rows alternate GU_UNIT gate rows / GU_UNIT up rows, so every 64 accumulator columns hold 32 outputs
         if constexpr (BN % (2 * GU_UNIT) == 0) {
             bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + tc.tn * (BN / 2);
+            const bool gu32 = (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && p.ldo % 16 == 0;
 #pragma unroll 1
             for (int c = chalf; c < BN / 32; c += 2) {  // 16 outputs per step
                 const int col = (c >> 1) * (2 * GU_UNIT) + (c & 1) * 16;
@@ -147,9 +159,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                         const float bb = epi_swiglu(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
                         pk[j] = pack_bf16x2(a, bb);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (gu32) {
+                        st_global_v8(out + c * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(out + c * 16);
+                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
                 }
             }
         }
@@ -160,11 +176,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
         // the QKV product is no longer written, re-read and re-written (436 MB per layer at 64 x 30 s).
         if constexpr (BN % 128 == 0) {
             const QkvRope& R = p.rp;
-            int pos = 0, page = 0;
-            if (row_ok) {
-                pos = __ldg(R.pos + row);
-                page = __ldg(R.page_table + (size_t)__ldg(R.row_seq + row) * R.max_pages + pos / 32);
-            }
+            const int pos = qkv_pos, page = qkv_page;
             bf16* page_base = R.pool + (((size_t)page * R.layers + R.layer) * 2) * R.kv_heads * (32 * 128) + (pos % 32) * 128;
 #pragma unroll 1
             for (int hh = chalf; hh < BN / 128; hh += 2) {
@@ -186,10 +198,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                                                    pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
                                                    pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
                                                    pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-                            uint4* d0 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + slot * 128 + c * 32);
-                            uint4* d1 = reinterpret_cast<uint4*>(page_base + ((size_t)R.kv_heads + kvh) * (32 * 128) + c * 32);
+                            bf16* d0 = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + slot * 128 + c * 32;
+                            bf16* d1 = page_base + ((size_t)R.kv_heads + kvh) * (32 * 128) + c * 32;
 #pragma unroll
-                            for (int j = 0; j < 4; j++) { d0[j] = pk[j]; d1[j] = pk[j]; }
+                            for (int j = 0; j < 4; j += 2) {  // 256-bit stores (all these rows are 256-byte aligned)
+                                st_global_v8(d0 + j * 8, pk[j].x, pk[j].y, pk[j].z, pk[j].w, pk[j + 1].x, pk[j + 1].y, pk[j + 1].z, pk[j + 1].w);
+                                st_global_v8(d1 + j * 8, pk[j].x, pk[j].y, pk[j].z, pk[j].w, pk[j + 1].x, pk[j + 1].y, pk[j + 1].z, pk[j + 1].w);
+                            }
                         }
                     }
                     continue;
@@ -217,7 +232,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                     ptx::tmem_ld_32x32(t_head + 64 + c * 32, b);
                     ptx::tmem_ld_wait();
                     if (row_ok) {
-                        const float4* tp = reinterpret_cast<const float4*>(R.rope + (size_t)pos * 64 + c * 32);  // (cos, sin) pairs
+                        const float2* tp = R.rope + (size_t)(c * 32) * R.rope_n + pos;  // (cos, sin) of dimension 32 c of this row's position
                         const uint4* wa = reinterpret_cast<const uint4*>(nw + c * 32);
                         const uint4* wb = reinterpret_cast<const uint4*>(nw + 64 + c * 32);
                         uint32_t oa[16], ob[16];
@@ -228,7 +243,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
 #pragma unroll
                             for (int j2 = 0; j2 < 4; j2++) {
                                 const int j = 8 * j4 + 2 * j2;
-                                const float4 t = __ldg(tp + (j >> 1));  // cos, sin of dims j and j + 1
+                                const float2 t0 = __ldg(tp + (size_t)j * R.rope_n), t1 = __ldg(tp + (size_t)(j + 1) * R.rope_n);
+                                const float4 t = make_float4(t0.x, t0.y, t1.x, t1.y);  // cos, sin of dims j and j + 1
                                 const float2 fa = unpack_bf16x2(wwa[j2]), fb = unpack_bf16x2(wwb[j2]);
                                 const float xa0 = bf16_round(bf16_round(__uint_as_float(a[j])) * r * fa.x);
                                 const float xa1 = bf16_round(bf16_round(__uint_as_float(a[j + 1])) * r * fa.y);
@@ -238,20 +254,20 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                                 ob[j >> 1] = pack_bf16x2(fmaf(xb0, t.x, xa0 * t.y), fmaf(xb1, t.z, xa1 * t.w));
                             }
                         }
-                        uint4* da = reinterpret_cast<uint4*>(dst + c * 32);
-                        uint4* db = reinterpret_cast<uint4*>(dst + 64 + c * 32);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            da[j] = make_uint4(oa[4 * j], oa[4 * j + 1], oa[4 * j + 2], oa[4 * j + 3]);
-                            db[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                        for (int j = 0; j < 2; j++) {  // 256-bit stores
+                            st_global_v8(dst + c * 32 + j * 16, oa[8 * j], oa[8 * j + 1], oa[8 * j + 2], oa[8 * j + 3], oa[8 * j + 4], oa[8 * j + 5],
+                                         oa[8 * j + 6], oa[8 * j + 7]);
+                            st_global_v8(dst + 64 + c * 32 + j * 16, ob[8 * j], ob[8 * j + 1], ob[8 * j + 2], ob[8 * j + 3], ob[8 * j + 4],
+                                         ob[8 * j + 5], ob[8 * j + 6], ob[8 * j + 7]);
                         }
                         if (!is_q) {
-                            uint4* ca = reinterpret_cast<uint4*>(dst2 + c * 32);
-                            uint4* cb = reinterpret_cast<uint4*>(dst2 + 64 + c * 32);
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                ca[j] = make_uint4(oa[4 * j], oa[4 * j + 1], oa[4 * j + 2], oa[4 * j + 3]);
-                                cb[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+                            for (int j = 0; j < 2; j++) {
+                                st_global_v8(dst2 + c * 32 + j * 16, oa[8 * j], oa[8 * j + 1], oa[8 * j + 2], oa[8 * j + 3], oa[8 * j + 4],
+                                             oa[8 * j + 5], oa[8 * j + 6], oa[8 * j + 7]);
+                                st_global_v8(dst2 + 64 + c * 32 + j * 16, ob[8 * j], ob[8 * j + 1], ob[8 * j + 2], ob[8 * j + 3], ob[8 * j + 4],
+                                             ob[8 * j + 5], ob[8 * j + 6], ob[8 * j + 7]);
                             }
                         }
                     }
@@ -277,23 +293,44 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
             p.amax_idx[(size_t)row * p.tiles_n + tc.tn] = best_i;
         }
     } else {
-#pragma unroll 1
-        for (int c = chalf; c < BN / 32; c += 2) {
-            const int col = n0 + c * 32;
-            // bias and residual do not depend on the accumulator: fetch them under the TMEM load's latency
-            uint4 bvv[4], rvv[4];
+        // Bias and residual do not depend on the accumulator: the loads of chunk c + 2 are issued before chunk c is processed (and
+        // those of the first chunk before the wait for the accumulator, see the top of the function), so their L2 / HBM latency
+        // (~1 us for a residual row that was written a layer ago) is not paid once per chunk.  Products with a short K loop
+        // (K = 896: 14 k-blocks, 4.5 us of MMAs per tile) were bound by exactly that: out-proj 35 % tensor-active (ncu, round 1).
+        uint4 bnx[4], rnx[4];
+        const bool resid32 = EPI == EPI_NORMAL && p.resid != nullptr && (reinterpret_cast<uintptr_t>(p.resid) & 31) == 0 && p.ldr % 16 == 0;
+        const bool out32 = EPI == EPI_NORMAL && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && p.ldo % 16 == 0;
+        auto fetch = [&](int c) {
             if (EPI == EPI_NORMAL || EPI == EPI_F32) {
+                const int col = n0 + c * 32;
                 if (row_ok && p.bias != nullptr) {
                     const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) bvv[j] = __ldg(bp + j);
+                    for (int j = 0; j < 4; j++) bnx[j] = __ldg(bp + j);
                 }
                 if (EPI == EPI_NORMAL && row_ok && p.resid != nullptr) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col);
+                    const bf16* rp = p.resid + (size_t)row * p.ldr + col;
+                    if (resid32) {  // 32-byte aligned rows: two 256-bit loads per row instead of four 128-bit ones
+                        const U8 lo = ld_global_nc_v8(rp), hi = ld_global_nc_v8(rp + 16);
+                        rnx[0] = make_uint4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]); rnx[1] = make_uint4(lo.v[4], lo.v[5], lo.v[6], lo.v[7]);
+                        rnx[2] = make_uint4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]); rnx[3] = make_uint4(hi.v[4], hi.v[5], hi.v[6], hi.v[7]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) rvv[j] = __ldg(rp + j);
+                        for (int j = 0; j < 4; j++) rnx[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+                    }
                 }
             }
+        };
+        if (chalf < BN / 32) fetch(chalf);
+        ptx::mbar_wait(tfull, aphase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+            const int col = n0 + c * 32;
+            uint4 bvv[4], rvv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { bvv[j] = bnx[j]; rvv[j] = rnx[j]; }
+            if (c + 2 < BN / 32) fetch(c + 2);
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_row + c * 32, v);
             ptx::tmem_ld_wait();
@@ -348,11 +385,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                             t = unpack_bf16x2(rv.w); f[8 * j + 6] = t.x + bf16_round(f[8 * j + 6]); f[8 * j + 7] = t.y + bf16_round(f[8 * j + 7]);
                         }
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col);
+                    bf16* dst = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col;
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    for (int j = 0; j < 16; j++) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    if (out32) {
+                        st_global_v8(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                        st_global_v8(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            reinterpret_cast<uint4*>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
                 }
             }
         }
@@ -487,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;          // TMEM lane quadrant this warp may access
         const int chalf = (warp - 4) >> 2;  // which of the quadrant's two warps: takes chunks chalf, chalf + 2, ...
         int it = 0;
+        ptx::grid_dep_wait();  // the epilogue prefetches residual rows (the previous kernel's output) before it sees the accumulator
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;

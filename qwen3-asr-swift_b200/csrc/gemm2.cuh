@@ -212,6 +212,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         const int chalf = (warp - 4) >> 2;
         int it = 0;
+        ptx::grid_dep_wait();  // gemm_epilogue_tile prefetches residual rows (the previous kernel's output) ahead of the accumulator
         for (int st = pair; st < num_super; st += n_pairs, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;

@@ -95,7 +95,8 @@ struct BatchState {
     MegaParams mega;
     int mega_nb = 0, mega_gu = 0;
     bool mega_ready = false;
-    DevBuf kv_pool, rope_tab, page_tab, page_tab2, st_slot_seq;  // page_tab: [B][pages_per_seq] (plan_pages)
+    DevBuf kv_pool, rope_tab, rope_tab_t, page_tab, page_tab2, st_slot_seq;  // rope_tab_t: the table dimension-major (EPI_QKV)
+     // page_tab: [B][pages_per_seq] (plan_pages)
     int rope_n = 0;          // positions tabulated in rope_tab
     DevBuf amax_val, amax_idx, logits, logits_bf;
     // decode state (device)
@@ -110,7 +111,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &page_tab, &page_tab2, &st_slot_seq, &amax_val, &amax_idx, &logits, &logits_bf,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &rope_tab_t, &page_tab, &page_tab2, &st_slot_seq, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }

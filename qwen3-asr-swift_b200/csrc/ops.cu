@@ -1107,12 +1107,13 @@ __global__ void random_init_kernel(bf16* out, size_t n, unsigned long long seed,
 }
 
 // (cos, sin)(pos * inv_freq[i]) for pos < n_pos, i < 64: the fp32 product and sincosf of the per-element kernels, tabulated
-__global__ void rope_table_kernel(const float* __restrict__ inv_freq, int n_pos, float2* __restrict__ tab) {
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, int n_pos, float2* __restrict__ tab, float2* __restrict__ tab_t) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pos * 64) return;
     float sn, cs;
     sincosf((float)(idx >> 6) * inv_freq[idx & 63], &sn, &cs);
     tab[idx] = make_float2(cs, sn);
+    if (tab_t != nullptr) tab_t[(size_t)(idx & 63) * n_pos + (idx >> 6)] = make_float2(cs, sn);  // the same values, [64][n_pos]
 }
 
 inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -1160,8 +1161,8 @@ void qknorm_rope_kv_launch(const bf16* qkv, int ld, const bf16* qw, const bf16* 
     Q3_CUDA(cudaGetLastError());
 }
 
-void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, cudaStream_t st) {
-    if (n_pos > 0) rope_table_kernel<<<blocks_for((size_t)n_pos * 64, 256), 256, 0, st>>>(inv_freq, n_pos, tab);
+void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, float2* tab_t, cudaStream_t st) {
+    if (n_pos > 0) rope_table_kernel<<<blocks_for((size_t)n_pos * 64, 256), 256, 0, st>>>(inv_freq, n_pos, tab, tab_t);
     Q3_CUDA(cudaGetLastError());
 }
 

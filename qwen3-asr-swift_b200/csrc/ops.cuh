@@ -53,7 +53,8 @@ struct KvCache {
     int layers, kv_heads, head_dim;
 };
 // rope_tab[pos][i] = (cos, sin)(pos * theta^(-2i/128)), i < 64 (head_dim 128), for pos < n_pos
-void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, cudaStream_t st);
+// tab_t (optional): the same table dimension-major, [64][n_pos]
+void rope_table_launch(const float* inv_freq, int n_pos, float2* tab, float2* tab_t, cudaStream_t st);
 // Per (row, head): q/k RMSNorm over head_dim, split-half RoPE at pos[row], v passthrough; writes q to qout
 // [rows, heads*hd], k/v to the paged cache (slot pos[row] of sequence row_seq[row]) and, if kc/vc != null, to
 // contiguous [rows, kv_heads*hd] buffers for the prefill attention.  FloatTextDecoder.swift:85-102.
