@@ -21,10 +21,10 @@ int g_num_sms = 148;
 thread_local unsigned long long g_launches = 0;
 
 void make_tmap(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, const cuuint32_t* estr) {
+               const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     Q3_CHECK(g_encode != nullptr, 2, "gemm_init() has not been called");
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         std::string s = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + "): rank " + std::to_string(rank) + " dims";
@@ -40,25 +40,25 @@ void make_tmap(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 }
 
 template <int BN, int EPI>
-void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, GemmDev p, int max_stages, int grid, cudaStream_t st) {
+void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmDev p, int max_stages, int grid, cudaStream_t st) {
     static PerDeviceOnce attr_once;
     attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
     });
     p.stages = max_stages > 0 ? std::min(max_stages, gemm_stages(BN)) : gemm_stages(BN);
-    const int smem = p.stages * gemm_stage_bytes(BN) + 1024 + 256;
-    launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, smem, st, ta, tb, p);
+    const int smem = p.stages * gemm_stage_bytes(BN) + (p.tma_out ? EPI_STAGE_BYTES : 0) + 1024 + 256;
+    launch_kernel(gemm_tc_kernel<BN, EPI>, grid, GEMM_THREADS, smem, st, ta, tb, tc, p);
 }
 
 template <int BN>
-void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int ms, int grid, cudaStream_t st) {
+void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& p, int ms, int grid, cudaStream_t st) {
     switch (epi) {
-        case EPI_NORMAL: launch_tc<BN, EPI_NORMAL>(ta, tb, p, ms, grid, st); break;
-        case EPI_SWIGLU: launch_tc<BN, EPI_SWIGLU>(ta, tb, p, ms, grid, st); break;
-        case EPI_F32: launch_tc<BN, EPI_F32>(ta, tb, p, ms, grid, st); break;
-        case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, p, ms, grid, st); break;
+        case EPI_NORMAL: launch_tc<BN, EPI_NORMAL>(ta, tb, tc, p, ms, grid, st); break;
+        case EPI_SWIGLU: launch_tc<BN, EPI_SWIGLU>(ta, tb, tc, p, ms, grid, st); break;
+        case EPI_F32: launch_tc<BN, EPI_F32>(ta, tb, tc, p, ms, grid, st); break;
+        case EPI_ARGMAX: launch_tc<BN, EPI_ARGMAX>(ta, tb, tc, p, ms, grid, st); break;
         case EPI_QKV:
-            if constexpr (BN % 128 == 0) launch_tc<BN, EPI_QKV>(ta, tb, p, ms, grid, st);
+            if constexpr (BN % 128 == 0) launch_tc<BN, EPI_QKV>(ta, tb, tc, p, ms, grid, st);
             else throw Error(1, "gemm: the fused q/k/v epilogue needs tiles of whole heads (128 or 256 columns)");
             break;
         default: throw Error(1, "gemm: bad epilogue");
@@ -66,20 +66,20 @@ void launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 }
 
 template <int BN, int EPI>
-void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
+void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& p, int grid, cudaStream_t st) {
     static PerDeviceOnce attr_once;
     attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(BN)));
     });
-    launch_kernel(gemm_tc2_kernel<BN, EPI>, grid, GEMM_THREADS, gemm2_smem_bytes(BN), st, ta, tb, p);
+    launch_kernel(gemm_tc2_kernel<BN, EPI>, grid, GEMM_THREADS, gemm2_smem_bytes(BN) - (p.tma_out ? 0 : EPI_STAGE_BYTES), st, ta, tb, tc, p);
 }
 template <int BN>
-void launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t st) {
-    if (epi == EPI_SWIGLU) launch_tc2<BN, EPI_SWIGLU>(ta, tb, p, grid, st);
+void launch_bn2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& p, int grid, cudaStream_t st) {
+    if (epi == EPI_SWIGLU) launch_tc2<BN, EPI_SWIGLU>(ta, tb, tc, p, grid, st);
     else if (epi == EPI_QKV) {
-        if constexpr (BN % 128 == 0) launch_tc2<BN, EPI_QKV>(ta, tb, p, grid, st);
+        if constexpr (BN % 128 == 0) launch_tc2<BN, EPI_QKV>(ta, tb, tc, p, grid, st);
         else throw Error(1, "gemm: the fused q/k/v epilogue needs tiles of whole heads (128 or 256 columns)");
-    } else launch_tc2<BN, EPI_NORMAL>(ta, tb, p, grid, st);
+    } else launch_tc2<BN, EPI_NORMAL>(ta, tb, tc, p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,14 +324,33 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
         cuuint32_t es[2] = {1, 1};
         make_tmap(&tb, W, 2, dims, str, box, es);
     }
+    // Output tensor map of the plain epilogue (gemm.cuh: tiles staged in shared memory, one TMA store per 128 x 32 chunk): the
+    // output rows are (b, h, w) positions in that order, so the map has the shape of the A map with N as the contiguous dimension
+    // and the M-tile box {32 columns, Wb, Hb, Bb}; rows outside the tensor are clipped by the copy.  Not for scattered rows.
+    CUtensorMap tc = ta;
+    // Opt-in (Q3ASR_TMA_STORE=1): measured on the bench batch against the default, row-per-thread 256-bit stores, it is no faster
+    // (encoder out-proj 0.89 vs 0.85 ms, fc1 3.11 vs 2.92, conv2 6.40 vs 6.22): once the stores are 32 bytes wide the epilogue is
+    // no longer what bounds these products, and the staging costs a barrier of four warps per chunk.
+    const char* env_ts = getenv("Q3ASR_TMA_STORE");
+    const bool want_tma_out = env_ts != nullptr && atoi(env_ts) != 0;
+    p.tma_out = 0;
+    if (e.epi == EPI_NORMAL && e.row_map == nullptr && want_tma_out && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && e.ldo % 8 == 0 &&
+        (e.max_stages == 0 || pair)) {
+        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)s.OW, (cuuint64_t)s.OH, (cuuint64_t)s.OB};
+        cuuint64_t str[3] = {(cuuint64_t)e.ldo * 2, (cuuint64_t)e.ldo * 2 * s.OW, (cuuint64_t)e.ldo * 2 * s.OW * s.OH};
+        cuuint32_t box[4] = {32u, (cuuint32_t)s.Wb, (cuuint32_t)s.Hb, (cuuint32_t)s.Bb};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        make_tmap(&tc, e.out, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+        p.tma_out = 1;
+    }
     if (pair) {
         const long super = ((m_tiles + 1) / 2) * p.tiles_n;
         const int grid2 = 2 * (int)std::min<long>(super, g_num_sms / 2);
         switch (bn) {
-            case 128: launch_bn2<128>(e.epi, ta, tb, p, grid2, st); break;
-            case 160: launch_bn2<160>(e.epi, ta, tb, p, grid2, st); break;
-            case 224: launch_bn2<224>(e.epi, ta, tb, p, grid2, st); break;
-            default: launch_bn2<256>(e.epi, ta, tb, p, grid2, st); break;
+            case 128: launch_bn2<128>(e.epi, ta, tb, tc, p, grid2, st); break;
+            case 160: launch_bn2<160>(e.epi, ta, tb, tc, p, grid2, st); break;
+            case 224: launch_bn2<224>(e.epi, ta, tb, tc, p, grid2, st); break;
+            default: launch_bn2<256>(e.epi, ta, tb, tc, p, grid2, st); break;
         }
         Q3_CUDA(cudaGetLastError());
         g_launches++;
@@ -340,12 +359,12 @@ void gemm_conv(const GemmA& a, const GemmShape& s, const bf16* W, int N, const G
     const long tiles = m_tiles * p.tiles_n;
     const int grid = (int)std::min<long>(tiles, g_num_sms);
     switch (bn) {
-        case 32: launch_bn<32>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
-        case 64: launch_bn<64>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
-        case 128: launch_bn<128>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
-        case 160: launch_bn<160>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
-        case 224: launch_bn<224>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
-        case 256: launch_bn<256>(e.epi, ta, tb, p, e.max_stages, grid, st); break;
+        case 32: launch_bn<32>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
+        case 64: launch_bn<64>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
+        case 128: launch_bn<128>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
+        case 160: launch_bn<160>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
+        case 224: launch_bn<224>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
+        case 256: launch_bn<256>(e.epi, ta, tb, tc, p, e.max_stages, grid, st); break;
         default: throw Error(1, "gemm: unsupported tile width " + std::to_string(bn));
     }
     Q3_CUDA(cudaGetLastError());

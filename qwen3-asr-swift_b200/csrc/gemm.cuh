@@ -75,6 +75,7 @@ struct GemmDev {  // by-value kernel parameter
     const int* valid_w;    // [OB] columns w >= valid_w[b] are stored as zero, or null
     int gelu;
     int stages;            // smem ring depth actually used (<= gemm_stages(BN))
+    int tma_out;           // EPI_NORMAL: output tiles are staged in shared memory and written with TMA stores (tmC is valid)
     float* amax_val;       // [rows, tiles_n]
     int* amax_idx;
     QkvRope rp;            // EPI_QKV only
@@ -85,7 +86,11 @@ __host__ __device__ constexpr int gemm_stage_bytes(int BN) { return GEMM_BM * 12
 __host__ __device__ constexpr int gemm_stages(int BN) {
     return (196 * 1024) / gemm_stage_bytes(BN) > 8 ? 8 : (196 * 1024) / gemm_stage_bytes(BN);
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int BN) { return gemm_stages(BN) * gemm_stage_bytes(BN) + 1024 + 256; }
+// Output staging of the plain epilogue: per group of four epilogue warps (one per TMEM lane quadrant) two buffers of 128 rows x 32
+// columns bf16 (64-byte rows, 64-byte swizzle), written row-per-thread and drained by one TMA store per 32-column chunk.
+constexpr int EPI_STAGE_BUF = GEMM_BM * 64;
+constexpr int EPI_STAGE_BYTES = 2 * 2 * EPI_STAGE_BUF;  // 32 KB
+__host__ __device__ constexpr int gemm_smem_bytes(int BN) { return gemm_stages(BN) * gemm_stage_bytes(BN) + EPI_STAGE_BYTES + 1024 + 256; }
 
 __device__ __forceinline__ float epi_swiglu(float g_acc, float u_acc) {
     const float g = bf16_round(g_acc);
@@ -110,9 +115,16 @@ __device__ __forceinline__ TileCoord gemm_tile_coord(const GemmDev& p, int tile)
 
 // One tile's epilogue for one thread: TMEM row -> registers -> bias / PE / GELU / residual / SwiGLU / argmax -> global.
 // `tfull` is the barrier the accumulator's completion is committed to (waited on here, after the index arithmetic).
+// Shared-memory staging of the plain epilogue's TMA stores: `buf` = this warp group's two buffers, `ctr` counts its stores.
+struct EpiStage {
+    const CUtensorMap* tmC;
+    uint8_t* buf;
+    uint32_t ctr;
+};
+
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileCoord tc, uint32_t tmem_acc, uint64_t* tfull, uint32_t aphase,
-                                                   int q, int lane, int chalf, int tile_rows) {
+                                                   int q, int lane, int chalf, int tile_rows, EpiStage& es) {
     const int n0 = tc.tn * BN;
     const int r = q * 32 + lane;
     const int w = tc.w0 + r % p.Wb;
@@ -389,7 +401,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    if (out32) {
+                    if (p.tma_out) {
+                        // this thread's row of the chunk: 64 bytes at row pitch 64, 16-byte pieces XOR-swizzled with bits 1-2 of the
+                        // row (the TMA 64-byte swizzle): the 32 lanes' stores spread over all banks
+                        uint8_t* srow = es.buf + (es.ctr & 1) * EPI_STAGE_BUF + r * 64;
+                        const int sw = (r >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    } else if (out32) {
                         st_global_v8(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                         st_global_v8(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                     } else {
@@ -399,13 +419,31 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmDev& p, const TileC
                     }
                 }
             }
+            if constexpr (EPI == EPI_NORMAL) {
+                if (p.tma_out) {
+                    // One store per (warp group, chunk): 128 rows x 32 columns leave as ONE bulk tensor copy instead of 256 row-strided
+                    // 32-byte stores.  The elected thread first makes sure the group's previous store has finished reading the
+                    // OTHER buffer (the next chunk will be written there), so the barrier below says both "this chunk is staged" and
+                    // "the other buffer is free".
+                    ptx::fence_proxy_async();
+                    const bool elected = q == 0 && lane == 0;
+                    if (elected) ptx::bulk_wait_group_read<0>();
+                    ptx::named_bar_sync(1 + chalf, 128);
+                    if (elected && tc.w0 < p.OW && tc.h0 < p.OH && tc.b0 < p.OB) {  // (the odd CTA of a pair may hold a tile past the end)
+                        ptx::tma_store_4d(es.tmC, col, tc.w0, tc.h0, tc.b0, es.buf + (es.ctr & 1) * EPI_STAGE_BUF);
+                        ptx::bulk_commit_group();
+                    }
+                    es.ctr++;
+                }
+            }
         }
     }
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const GemmDev p) {
     constexpr int MAX_STAGES = gemm_stages(BN);
     const int STAGES = p.stages;  // <= MAX_STAGES; the decode step asks for a shallow ring so the next kernel's CTAs fit beside this one
     constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
@@ -417,7 +455,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // [2 warp groups][2 buffers], only when p.tma_out
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (p.tma_out ? EPI_STAGE_BYTES : 0));
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2]
     uint64_t* tempty_bar = tfull_bar + 2;      // [2]
@@ -431,6 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
+        if (p.tma_out) ptx::prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -532,13 +572,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int chalf = (warp - 4) >> 2;  // which of the quadrant's two warps: takes chunks chalf, chalf + 2, ...
         int it = 0;
         ptx::grid_dep_wait();  // the epilogue prefetches residual rows (the previous kernel's output) before it sees the accumulator
+        EpiStage es{&tmC, epi_stage + chalf * 2 * EPI_STAGE_BUF, 0u};
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            gemm_epilogue_tile<BN, EPI>(p, gemm_tile_coord(p, tile), tmem_base + as * ACC_STRIDE, &tfull_bar[as], aphase, q, lane, chalf, tile_rows);
+            gemm_epilogue_tile<BN, EPI>(p, gemm_tile_coord(p, tile), tmem_base + as * ACC_STRIDE, &tfull_bar[as], aphase, q, lane, chalf, tile_rows, es);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
+        if (p.tma_out && q == 0 && lane == 0) ptx::bulk_wait_group<0>();  // the staged tiles have reached memory before the CTA leaves
     }
 
     ptx::tc_fence_before();

@@ -86,7 +86,7 @@ __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
 
 __host__ __device__ constexpr int gemm2_stage_bytes(int BN) { return GEMM_BM * 128 + (BN / 2) * 128; }
 __host__ __device__ constexpr int gemm2_stages(int BN) { return (196 * 1024) / gemm2_stage_bytes(BN) > 8 ? 8 : (196 * 1024) / gemm2_stage_bytes(BN); }
-__host__ __device__ constexpr int gemm2_smem_bytes(int BN) { return gemm2_stages(BN) * gemm2_stage_bytes(BN) + 1024 + 256; }
+__host__ __device__ constexpr int gemm2_smem_bytes(int BN) { return gemm2_stages(BN) * gemm2_stage_bytes(BN) + EPI_STAGE_BYTES + 1024 + 256; }
 
 // this CTA's M tile (index mt over tiles_w x tiles_h x tiles_b) of column tile tn
 __device__ __forceinline__ TileCoord gemm2_tile_coord(const GemmDev& p, int tn, int mt) {
@@ -102,7 +102,8 @@ __device__ __forceinline__ TileCoord gemm2_tile_coord(const GemmDev& p, int tn, 
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const GemmDev p) {
     constexpr int STAGES = gemm2_stages(BN);
     constexpr int STAGE_BYTES = gemm2_stage_bytes(BN);
     constexpr int ACC_STRIDE = gemm_acc_stride(BN);
@@ -112,7 +113,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader only
+    uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;                                // output staging of the plain epilogue (gemm.cuh)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (p.tma_out ? EPI_STAGE_BYTES : 0));  // used in the leader only
     uint64_t* empty_bar = full_bar + STAGES;                                         // per CTA
     uint64_t* tfull_bar = empty_bar + STAGES;                                        // [2] per CTA
     uint64_t* tempty_bar = tfull_bar + 2;                                            // [2] used in the leader only
@@ -131,6 +133,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
+        if (p.tma_out) ptx::prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -213,15 +216,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int chalf = (warp - 4) >> 2;
         int it = 0;
         ptx::grid_dep_wait();  // gemm_epilogue_tile prefetches residual rows (the previous kernel's output) ahead of the accumulator
+        EpiStage es{&tmC, epi_stage + chalf * 2 * EPI_STAGE_BUF, 0u};
         for (int st = pair; st < num_super; st += n_pairs, it++) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const TileCoord tc = gemm2_tile_coord(p, st % p.tiles_n, 2 * (st / p.tiles_n) + (int)rank);
-            gemm_epilogue_tile<BN, EPI>(p, tc, tmem_base + as * ACC_STRIDE, &tfull_bar[as], aphase, q, lane, chalf, tile_rows);
+            gemm_epilogue_tile<BN, EPI>(p, tc, tmem_base + as * ACC_STRIDE, &tfull_bar[as], aphase, q, lane, chalf, tile_rows, es);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tempty_bar[as], 0));
         }
+        if (p.tma_out && q == 0 && lane == 0) ptx::bulk_wait_group<0>();  // the staged tiles have reached memory before the CTA leaves
     }
 
     ptx::tc_fence_before();

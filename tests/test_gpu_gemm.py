@@ -217,3 +217,24 @@ def test_gemm_cta_pair_swiglu_and_conv(tiny_model, monkeypatch, bn):
     _close_bf16(tiny_model.debug_gemm(A, _interleave_gate_up(G, U), epi=1, bn=bn), sg * u, f"pair swiglu bn={bn}", ulps=3)
     x, w, b = _rand(rng, (11, 32, 25, 480)), _rand(rng, (160, 3, 3, 480), 0.05), _rand(rng, (160,))
     _close_bf16(tiny_model.debug_conv(x, w, b, box=(13, 1, 9)), _conv_ref(x, w, b), "pair conv", ulps=2)
+
+
+# ---- opt-in TMA-store epilogue (Q3ASR_TMA_STORE=1): tiles staged in shared memory, one bulk tensor store per 128 x 32 chunk ----
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_gemm_tma_store_epilogue_is_bit_identical(tiny_model, monkeypatch, pair):
+    monkeypatch.setenv("Q3ASR_2CTA", pair)
+    rng = np.random.default_rng(77)
+    for M, N, K, bn in [(1000, 896, 896, 224), (300, 512, 320, 256), (77, 256, 64, 128), (333, 480, 480, 160)]:
+        A, W, b, R = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05), _rand(rng, (N,)), _rand(rng, (M, N))
+        monkeypatch.setenv("Q3ASR_TMA_STORE", "0")
+        want = [tiny_model.debug_gemm(A, W, bias=b, bn=bn), tiny_model.debug_gemm(A, W, bias=b, resid=R, gelu=True, bn=bn)]
+        monkeypatch.setenv("Q3ASR_TMA_STORE", "1")
+        got = [tiny_model.debug_gemm(A, W, bias=b, bn=bn), tiny_model.debug_gemm(A, W, bias=b, resid=R, gelu=True, bn=bn)]
+        for w_, g_ in zip(want, got):
+            assert np.array_equal(w_, g_), (M, N, K, bn)
+    # implicit-GEMM convolution: the store box is the M tile's (w, h, b) box, rows outside the image are clipped by the copy
+    x, w, b = _rand(rng, (11, 32, 25, 480)), _rand(rng, (160, 3, 3, 480), 0.05), _rand(rng, (160,))
+    monkeypatch.setenv("Q3ASR_TMA_STORE", "0")
+    want = tiny_model.debug_conv(x, w, b, box=(13, 1, 9))
+    monkeypatch.setenv("Q3ASR_TMA_STORE", "1")
+    assert np.array_equal(want, tiny_model.debug_conv(x, w, b, box=(13, 1, 9)))
