@@ -110,32 +110,42 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float2 f2_splat(float c) { return make_float2(c, c); }
 
 // The same GELU for two values at once on the packed pipe.  erf by the two minimax polynomials of N. Juffa's erff (< 1 ulp each:
-// |z| <= 0.927734375: z + z p(z^2); above: 1 - exp(q(|z|)), sign restored), both evaluated for both lanes and selected — no
-// divergence, 19 packed + ~14 scalar instructions per PAIR against ~28 per value for erff.  Differs from erff by <= 2 fp32 ulps,
+// |z| <= 0.927734375: z + z p(z^2); above: 1 - exp(q(|z|)), sign restored): 10 packed instructions per PAIR, + 11 packed and ~8
+// scalar ones when a lane of the warp is in the tail, against ~28 per value for erff.  Differs from erff by <= 3 fp32 ulps,
 // i.e. from gelu_erf after the bf16 store in about one value in 10^4 (the exact-erf GELU is 70 % of conv1's instructions and the
 // reason the fc1 / conv epilogues are slower than their MMAs).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     const float2 z = f2_mul(x, f2_splat(0.70710678118654752440f));
     const float2 t = make_float2(fabsf(z.x), fabsf(z.y));
     const float2 s = f2_mul(z, z);
-    // |z| > 0.927734375
-    float2 r = f2_fma(f2_splat(-1.72853470e-5f), t, f2_splat(3.83197126e-4f));
-    const float2 u = f2_fma(f2_splat(-3.88396438e-3f), t, f2_splat(2.42546219e-2f));
-    r = f2_fma(r, s, u);
-    r = f2_fma(r, t, f2_splat(-1.06777877e-1f));
-    r = f2_fma(r, t, f2_splat(-6.34846687e-1f));
-    r = f2_fma(r, t, f2_splat(-1.28717512e-1f));
-    r = f2_fma(r, t, make_float2(-t.x, -t.y));
     // |z| <= 0.927734375
     float2 p = f2_fma(f2_splat(-5.96761703e-4f), s, f2_splat(4.99119423e-3f));
     p = f2_fma(p, s, f2_splat(-2.67681349e-2f));
     p = f2_fma(p, s, f2_splat(1.12819925e-1f));
     p = f2_fma(p, s, f2_splat(-3.76125336e-1f));
     p = f2_fma(p, s, f2_splat(1.28379166e-1f));
-    p = f2_fma(p, z, z);
-    float2 e;
-    e.x = t.x > 0.927734375f ? copysignf(1.0f - expf(r.x), z.x) : p.x;
-    e.y = t.y > 0.927734375f ? copysignf(1.0f - expf(r.y), z.y) : p.y;
+    float2 e = f2_fma(p, z, z);
+    // |z| > 0.927734375: evaluated (for both values, branch-free) only when some lane of the warp needs it — one warp-uniform
+    // branch instead of a divergent expf call per value.  exp(r) = 2^(r log2 e) on the SFU (ex2.approx: 2 ulps; r < 0 and the
+    // result is subtracted from 1).  The vote runs over the lanes that happen to be converged here (__activemask); that is only
+    // an optimisation hint: whichever way a lane gets here, it computes the same value.
+    const bool tail_x = t.x > 0.927734375f, tail_y = t.y > 0.927734375f;
+    if (__any_sync(__activemask(), tail_x || tail_y)) {
+        float2 r = f2_fma(f2_splat(-1.72853470e-5f), t, f2_splat(3.83197126e-4f));
+        const float2 u = f2_fma(f2_splat(-3.88396438e-3f), t, f2_splat(2.42546219e-2f));
+        r = f2_fma(r, s, u);
+        r = f2_fma(r, t, f2_splat(-1.06777877e-1f));
+        r = f2_fma(r, t, f2_splat(-6.34846687e-1f));
+        r = f2_fma(r, t, f2_splat(-1.28717512e-1f));
+        r = f2_fma(r, t, make_float2(-t.x, -t.y));
+        const float2 rl = f2_mul(r, f2_splat(1.4426950408889634f));
+        float2 ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(rl.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(rl.y));
+        const float2 om = f2_fma(ex, f2_splat(-1.0f), f2_splat(1.0f));
+        e.x = tail_x ? copysignf(om.x, z.x) : e.x;
+        e.y = tail_y ? copysignf(om.y, z.y) : e.y;
+    }
     const float2 h = f2_mul(x, f2_splat(0.5f));
     return f2_fma(h, e, h);
 }

@@ -118,6 +118,7 @@ struct Handle {
     std::vector<ProfRec> prof;
     size_t prof_used = 0;
 
+    bool decode_warm = false;  // a decode step has run eagerly on this handle (function attributes set): later batches go straight to the step graph
     cudaEvent_t timer[16] = {nullptr};
     float stage_ms[4] = {0, 0, 0, 0};
     DevBuf flush_buf;
