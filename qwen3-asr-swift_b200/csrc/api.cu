@@ -127,6 +127,7 @@ int q3asr_create(const q3asr_config* cfg, int device, q3asr_handle** out) {
         Q3_CUDA(cudaGetDeviceProperties(&prop, device));
         h.num_sms = prop.multiProcessorCount;
         Q3_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+        Q3_CUDA(cudaStreamCreateWithFlags(&h.copy_stream, cudaStreamNonBlocking));
         mel_tables_create(&h.mel_tables);
         h.mel_ready = true;
         for (int i = 0; i < 16; i++) Q3_CUDA(cudaEventCreate(&h.timer[i]));
@@ -146,6 +147,7 @@ void q3asr_destroy(q3asr_handle* hh) {
     Handle& h = hh->h;
     try {
         DeviceGuard g(h.device);
+        if (h.copy_stream) cudaStreamSynchronize(h.copy_stream);
         if (h.stream) cudaStreamSynchronize(h.stream);
         model_unload(&h);
         if (h.mel_ready) mel_tables_destroy(&h.mel_tables);
@@ -159,6 +161,8 @@ void q3asr_destroy(q3asr_handle* hh) {
             cudaEventDestroy(r.a);
             cudaEventDestroy(r.b);
         }
+        for (cudaEvent_t e : h.copy_ev) cudaEventDestroy(e);
+        if (h.copy_stream) cudaStreamDestroy(h.copy_stream);
         if (h.stream) cudaStreamDestroy(h.stream);
     } catch (...) {
     }
@@ -294,6 +298,19 @@ int q3asr_encode(q3asr_handle* h, const float* mel, int frames, float* out, int*
 int q3asr_batch_upload(q3asr_handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts) {
     return guarded(h, [&](Handle& x) { batch_upload(&x, pcm, n, batch, prompts); });
 }
+namespace {
+// joins a deferred upload on every way out of a transcribe call (errors of the threads were either reported by batch_run or
+// are secondary to the exception already in flight)
+struct UploadGuard {
+    Handle* h;
+    ~UploadGuard() {
+        try {
+            finish_upload(h->batch.get());
+        } catch (...) {
+        }
+    }
+};
+}  // namespace
 int q3asr_batch_run(q3asr_handle* h, int stages, int max_tokens, int stop_on_eos) {
     return guarded(h, [&](Handle& x) { batch_run(&x, stages, max_tokens, stop_on_eos); });
 }
@@ -304,7 +321,8 @@ int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t*
                          int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out) {
     return guarded(h, [&](Handle& x) {
         Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
-        batch_upload(&x, pcm, n, batch, prompts);
+        UploadGuard ug{&x};  // the staging threads never outlive this call (they read the caller's buffers)
+        batch_upload(&x, pcm, n, batch, prompts, nullptr, true);
         batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
         batch_download(&x, ids_out, max_tokens, lens_out);
     });
@@ -317,7 +335,8 @@ int q3asr_transcribe_ids_sr(q3asr_handle* h, const float* const* pcm, const size
                             const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out) {
     return guarded(h, [&](Handle& x) {
         Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
-        batch_upload(&x, pcm, n, batch, prompts, sample_rates);
+        UploadGuard ug{&x};
+        batch_upload(&x, pcm, n, batch, prompts, sample_rates, true);
         batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
         batch_download(&x, ids_out, max_tokens, lens_out);
     });
@@ -330,7 +349,8 @@ int q3asr_transcribe_ids_opts(q3asr_handle* h, const float* const* pcm, const si
                               int32_t* ids_out, int* lens_out) {
     return guarded(h, [&](Handle& x) {
         Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
-        batch_upload(&x, pcm, n, batch, prompts, sample_rates);
+        UploadGuard ug{&x};
+        batch_upload(&x, pcm, n, batch, prompts, sample_rates, true);
         batch_set_sampling(&x, sampling);
         batch_run(&x, Q3ASR_STAGE_ALL, max_tokens, stop_on_eos);
         batch_download(&x, ids_out, max_tokens, lens_out);

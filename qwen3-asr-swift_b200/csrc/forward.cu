@@ -252,14 +252,65 @@ void reserve_decoder(Handle* h, BatchState* bs) {
 // ---------------------------------------------------------------------------------------------
 // stages
 // ---------------------------------------------------------------------------------------------
-void run_mel(Handle* h, BatchState* bs) {
-    double mel_bytes = 0;
-    for (const MelClip& mc : bs->mel.clips) mel_bytes += 4.0 * mc.n + 4.0 * MEL_BINS * mc.frames;
-    ProfScope ps(h, "mel", 0, mel_bytes);
-    mel_launch(h->mel_tables, bs->pcm.as<float>(), bs->mel_out.as<float>(), bs->mel_clips.as<MelClip>(), bs->B, bs->mel.total_tiles,
-               bs->mel_gmax.as<int>(), bs->mel_tmin.as<float>(), h->num_sms, h->stream);
-    h->launches += 3;
-    bs->mel_done = true;
+}  // namespace
+
+// Joins the staging threads of the current upload (if any) and reports their first error.
+void finish_upload(BatchState* bs) {
+    if (bs == nullptr || !bs->upload) return;
+    std::unique_ptr<UploadJob> job = std::move(bs->upload);
+    for (auto& t : job->workers)
+        if (t.joinable()) t.join();
+    for (cudaError_t e : job->werr) Q3_CUDA(e);
+}
+
+namespace {
+
+// Host-side wait until clip b's copy has been queued on the copy stream and its event recorded.
+void wait_recorded(BatchState* bs, int b) {
+    if (!bs->upload) return;
+    std::atomic<int>& f = bs->upload->recorded[(size_t)b];
+    while (f.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+    if (f.load(std::memory_order_acquire) < 0) {
+        finish_upload(bs);  // throws the worker's error
+        throw Error(Q3ASR_ERR_CUDA, "batch_upload: a sample copy failed");
+    }
+}
+// true while some clip's host -> device copy (batch_upload, copy stream) has not been queued or has not landed yet
+bool copies_pending(Handle* h, BatchState* bs) {
+    if (!bs->copy_events || bs->B <= 0) return false;
+    if (bs->upload)
+        for (int b = 0; b < bs->B; b++)
+            if (bs->upload->recorded[(size_t)b].load(std::memory_order_acquire) == 0) return true;
+    return cudaEventQuery(h->copy_ev[(size_t)bs->B - 1]) == cudaErrorNotReady;
+}
+
+// Log-mel of the clips [bs->mel_next, upto) (upto < 0: all that remain).  While the upload is still in flight the batch is taken in
+// (up to) four groups of clips, each launch waiting only for its own clips' copies, so the caller (run_encoder) can interleave
+// the convolution stack of a group with the copies of the next; with the samples resident it is one launch for the whole batch.
+void run_mel(Handle* h, BatchState* bs, int upto = -1) {
+    const int B = bs->B;
+    if (upto < 0 || upto > B) upto = B;
+    const int gsz = copies_pending(h, bs) ? (B + 3) / 4 : B;
+    while (bs->mel_next < upto) {
+        const int c0 = bs->mel_next, c1 = std::min(B, (c0 / gsz + 1) * gsz);
+        if (bs->copy_events)
+            for (int b = c0; b < c1; b++)
+                if (!bs->copy_waited[(size_t)b]) {
+                    wait_recorded(bs, b);
+                    Q3_CUDA(cudaStreamWaitEvent(h->stream, h->copy_ev[(size_t)b], 0));
+                    bs->copy_waited[(size_t)b] = 1;
+                }
+        double mel_bytes = 0;
+        for (int b = c0; b < c1; b++) mel_bytes += 4.0 * bs->mel.clips[(size_t)b].n + 4.0 * MEL_BINS * bs->mel.clips[(size_t)b].frames;
+        const int tile_lo = bs->mel.clips[(size_t)c0].tile0;
+        const int tile_hi = c1 < B ? bs->mel.clips[(size_t)c1].tile0 : bs->mel.total_tiles;
+        ProfScope ps(h, "mel", 0, mel_bytes);
+        mel_launch_range(h->mel_tables, bs->pcm.as<float>(), bs->mel_out.as<float>(), bs->mel_clips.as<MelClip>(), c0, c1, tile_lo, tile_hi,
+                         bs->mel.total_tiles, bs->mel_gmax.as<int>(), bs->mel_tmin.as<float>(), h->num_sms, h->stream);
+        h->launches += 3;
+        bs->mel_next = c1;
+    }
+    bs->mel_done = bs->mel_next >= B;
 }
 
 GemmEpiArgs epi_store(void* out, int ldo, const bf16* bias, int gelu = 0, const bf16* resid = nullptr, int ldr = 0) {
@@ -291,6 +342,11 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
     }
     for (int c0 = 0; c0 < bs->n_chunks; c0 += grp) {
         const int n = std::min(grp, bs->n_chunks - c0);
+        if (d_mel == bs->mel_out.as<float>() && bs->mel_next < bs->B) {  // the mel stage was deferred: the upload is still in flight
+            int hi = bs->mel_next;
+            while (hi < bs->B && bs->clips[(size_t)hi].chunk0 < c0 + n) hi++;  // clips with a chunk in this group
+            run_mel(h, bs, hi);
+        }
         {
             ProfScope ps(h, "conv1", 2.0 * 9 * n * 64.0 * g.w1 * g.C, n * (128.0 * g.chunk * 4 + 64.0 * g.w1 * g.C * 2));
             conv1_launch(d_mel, chunks + c0, n, m.conv1_w, m.conv1_b, g.C, g.chunk, bs->a1.as<bf16>(), st);
@@ -307,6 +363,7 @@ void run_encoder(Handle* h, BatchState* bs, const float* d_mel) {
             gemm_conv(a, s2, m.conv2_w, g.C, e2, st);
         }
     }
+    if (d_mel == bs->mel_out.as<float>() && bs->mel_next < bs->B) run_mel(h, bs);
     // conv3 in one launch over every chunk: per group it would be 192 tiles on 148 SMs (two waves, the second 30 % full);
     // the conv2 output (24 MB per 32 chunks) is read back from HBM instead of L2, which costs far less than the idle SMs did.
     {
@@ -814,7 +871,9 @@ int encoder_tokens_for(int frames) {
     return full * 13 + (rem > 0 ? std::max(conv_len3(rem), 1) : 0);
 }
 
-void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int batch, const q3asr_prompt* prompts, const int* rates) {
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int batch, const q3asr_prompt* prompts, const int* rates,
+                  bool defer_join) {
+    finish_upload(h->batch.get());  // (a previous upload whose caller never ran it to the end)
     Q3_CHECK(pcm != nullptr && n_in != nullptr && batch > 0, Q3ASR_ERR_INVALID, "batch_upload: null argument / empty batch");
     Q3_CHECK(batch <= 1024, Q3ASR_ERR_INVALID, "batch_upload: at most 1024 utterances per call");
     // clips at another rate are converted to 16 kHz on the device (Qwen3ASRModel.transcribe resamples first,
@@ -856,30 +915,58 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     // (the slow leg, ~10 GB/s per thread) overlaps the PCIe transfers and the planning
     // below.  Clips are independent, so the order of the copies on the stream does not matter.
     const int n_workers = std::max(1, std::min({batch, env_int("Q3ASR_UPLOAD_THREADS", 4), (int)std::thread::hardware_concurrency() / 2}));
-    std::vector<std::thread> workers;
-    std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
-    workers.reserve((size_t)n_workers);
-    struct Joiner {  // the threads borrow the caller's buffers and the locals above: never leave without joining (a failed thread start included)
-        std::vector<std::thread>& t;
-        ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
-    } joiner{workers};
-    for (int w = 0; w < n_workers; w++)
-        workers.emplace_back([&, w]() {
-            cudaError_t e = cudaSetDevice(h->device);
-            for (int b = w; b < batch && e == cudaSuccess; b += n_workers) {
-                const long long off = bs->mel.clips[b].in_off;
-                if (rates != nullptr && rates[b] != 16000) {
-                    float* sr = stage_raw + raw_off[(size_t)b];
-                    memcpy(sr, pcm[b], sizeof(float) * n_in[b]);
-                    e = cudaMemcpyAsync(bs->raw_pcm.as<float>() + raw_off[(size_t)b], sr, sizeof(float) * n_in[b], cudaMemcpyHostToDevice,
-                                        h->stream);
-                    continue;
+    // the copies go on the copy stream, one event per clip (waited for by the mel launch of the clip's group, run_mel)
+    while (h->copy_ev.size() < (size_t)batch) {
+        cudaEvent_t e = nullptr;
+        Q3_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_ev.push_back(e);
+    }
+    bs->copy_events = true;
+    bs->copy_waited.assign((size_t)batch, 0);
+    bs->mel_next = 0;
+    Q3_CUDA(cudaEventRecord(bs->ev[0], h->stream));  // (any earlier work on the compute stream that still reads the sample buffer)
+    Q3_CUDA(cudaStreamWaitEvent(h->copy_stream, bs->ev[0], 0));
+    // The staging threads outlive this function when `defer_join` (q3asr_transcribe_ids*: the caller's buffers stay borrowed until
+    // the call returns): the planning below, the mel kernels and the convolution stack of the first clips then run while the last
+    // clips are still being copied into the staging area — the staging memcpy (123 MB at ~27 GB/s from four threads for 64 x 30 s)
+    // is the slow leg of an upload, not PCIe.  Everything the threads read lives in the job.
+    bs->upload.reset(new UploadJob());
+    UploadJob* J = bs->upload.get();
+    J->werr.assign((size_t)n_workers, cudaSuccess);
+    J->recorded.reset(new std::atomic<int>[(size_t)batch]);
+    for (int b = 0; b < batch; b++) J->recorded[(size_t)b].store(0, std::memory_order_relaxed);
+    J->pcm.assign(pcm, pcm + batch);
+    J->n_in.assign(n_in, n_in + batch);
+    J->n16 = n16;
+    J->raw_off = raw_off;
+    J->in_off.resize((size_t)batch);
+    for (int b = 0; b < batch; b++) J->in_off[(size_t)b] = bs->mel.clips[(size_t)b].in_off;
+    if (rates != nullptr) J->rates.assign(rates, rates + batch);
+    {
+        float* d_pcm = bs->pcm.as<float>();
+        float* d_raw = raw_floats ? bs->raw_pcm.as<float>() : nullptr;
+        const int device = h->device;
+        cudaStream_t cs = h->copy_stream;
+        const cudaEvent_t* evs = h->copy_ev.data();  // not resized while the job runs
+        J->workers.reserve((size_t)n_workers);
+        for (int w = 0; w < n_workers; w++)
+            J->workers.emplace_back([J, w, n_workers, batch, stage, stage_raw, d_pcm, d_raw, device, cs, evs]() {
+                cudaError_t e = cudaSetDevice(device);
+                for (int b = w; b < batch; b += n_workers) {
+                    if (e == cudaSuccess) {
+                        const bool raw = !J->rates.empty() && J->rates[(size_t)b] != 16000;
+                        float* sp = raw ? stage_raw + J->raw_off[(size_t)b] : stage + J->in_off[(size_t)b];
+                        float* dp = raw ? d_raw + J->raw_off[(size_t)b] : d_pcm + J->in_off[(size_t)b];
+                        const size_t bytes = sizeof(float) * (raw ? J->n_in[(size_t)b] : J->n16[(size_t)b]);
+                        memcpy(sp, J->pcm[(size_t)b], bytes);
+                        e = cudaMemcpyAsync(dp, sp, bytes, cudaMemcpyHostToDevice, cs);
+                        if (e == cudaSuccess) e = cudaEventRecord(evs[b], cs);
+                    }
+                    J->recorded[(size_t)b].store(e == cudaSuccess ? 1 : -1, std::memory_order_release);
                 }
-                memcpy(stage + off, pcm[b], sizeof(float) * n[b]);
-                e = cudaMemcpyAsync(bs->pcm.as<float>() + off, stage + off, sizeof(float) * n[b], cudaMemcpyHostToDevice, h->stream);
-            }
-            werr[(size_t)w] = e;
-        });
+                J->werr[(size_t)w] = e;
+            });
+    }
     Q3_CUDA(cudaMemcpyAsync(bs->mel_clips.p, bs->mel.clips.data(), sizeof(MelClip) * batch, cudaMemcpyHostToDevice, h->stream));
     // plan
     std::vector<int> frames(batch);
@@ -895,14 +982,18 @@ void batch_upload(Handle* h, const float* const* pcm, const size_t* n_in, int ba
     // re-plans them when a larger value is asked for
     const int reserve_tokens = std::max(1, env_int("Q3ASR_RESERVE_TOKENS", 448));
     plan_decoder(h, bs, prompts, reserve_tokens, &ints);
-    for (auto& t : workers) t.join();
-    for (cudaError_t e : werr) Q3_CUDA(e);
-    if (raw_floats)  // the copies are queued on the stream; the conversions follow them in stream order
+    if (!defer_join) finish_upload(bs);
+    if (raw_floats)  // the conversions follow their clip's copy (its event)
         for (int b = 0; b < batch; b++)
-            if (rates[b] != 16000)
+            if (rates[b] != 16000) {
+                wait_recorded(bs, b);
+                Q3_CUDA(cudaStreamWaitEvent(h->stream, h->copy_ev[(size_t)b], 0));
+                bs->copy_waited[(size_t)b] = 1;
                 resample_device(h, bs->raw_pcm.as<float>() + raw_off[(size_t)b], n_in[b], rates[b], 16000,
                                 bs->pcm.as<float>() + bs->mel.clips[b].in_off, n[b], h->stream);
-    upload_ints(h, bs, ints);  // ends with a stream synchronise: every sample copy has landed when this returns
+            }
+    upload_ints(h, bs, ints);  // (synchronises the COMPUTE stream; the sample copies may still be in flight on the copy stream: the
+                               // caller's buffers are free — they were copied to the staging area — and run_mel waits per clip)
     plan_pages(h, bs, reserve_tokens);
     bs->prompt_ids.clear();
 }
@@ -1046,12 +1137,20 @@ void batch_run(Handle* h, int stages, int max_tokens, int stop_on_eos) {
         Q3_CHECK(h->loaded && h->model, Q3ASR_ERR_STATE, "weights are not loaded (q3asr_init_random / q3asr_load_safetensors)");
     cudaStream_t st = h->stream;
     Q3_CUDA(cudaEventRecord(bs->ev[0], st));
-    if (stages & Q3ASR_STAGE_MEL) run_mel(h, bs);
+    if (stages & Q3ASR_STAGE_MEL) {
+        bs->mel_next = 0;
+        bs->mel_done = false;
+        // with the upload still in flight and the encoder to follow, the mel launches are interleaved with the convolution stack
+        // (run_encoder), group of clips by group of clips, as their copies land
+        if ((stages & Q3ASR_STAGE_ENCODER) && copies_pending(h, bs) && bs->n_tok > 0) bs->mel_done = true;
+        else run_mel(h, bs);
+    }
     Q3_CUDA(cudaEventRecord(bs->ev[1], st));
     if (stages & Q3ASR_STAGE_ENCODER) {
         Q3_CHECK(bs->mel_done, Q3ASR_ERR_STATE, "batch_run: encoder stage needs the mel stage first");
         reserve_encoder(h, bs);
         run_encoder(h, bs, bs->mel_out.as<float>());
+        finish_upload(bs);  // every clip's copy has been queued by now (run_mel waited for each): the staging threads are done
     }
     Q3_CUDA(cudaEventRecord(bs->ev[2], st));
     if (stages & Q3ASR_STAGE_PREFILL) {
@@ -1101,6 +1200,8 @@ void encode_one(Handle* h, const float* mel, int frames, float* out, int* tokens
     bs->B = 1;
     bs->has_audio = false;
     bs->mel_done = bs->enc_done = bs->prefill_done = false;
+    bs->copy_events = false;  // the features come from the caller: no sample copies to wait for, no mel launch pending
+    bs->mel_next = 1;
     const size_t nmel = (size_t)MEL_BINS * frames;
     bs->mel_out.reserve(nmel * 4);
     bs->h_stage.reserve(nmel * 4);

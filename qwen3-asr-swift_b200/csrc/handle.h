@@ -91,6 +91,10 @@ struct Handle {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    // Samples travel host -> device on their own stream, one event per clip: the mel kernel of a group of clips waits only for that
+    // group's copies, so the first groups' mel + convolution work overlaps the rest of the upload (forward.cu batch_upload / run_mel).
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_ev;
     std::string last_error;
     size_t dev_bytes = 0;          // bytes held in DevBufs + tensors
     unsigned long long launches = 0;  // kernels launched by this handle (non-GEMM; GEMMs are counted in gemm.cu)
@@ -194,7 +198,12 @@ int encoder_tokens_for(int frames);
 void build_prompt(const q3asr_config& c, const q3asr_prompt* pr, int ntok, std::vector<int32_t>* ids, int* audio_at);
 
 // rates: per-clip sample rates or null (all 16 kHz); other rates are converted on the device (audio_io.cu)
-void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts, const int* rates = nullptr);
+// defer_join: the staging threads keep running after the call returns (the caller's sample buffers stay borrowed) until
+// finish_upload; only for callers that run the batch inside the same API call (q3asr_transcribe_ids*)
+void batch_upload(Handle* h, const float* const* pcm, const size_t* n, int batch, const q3asr_prompt* prompts, const int* rates = nullptr,
+                  bool defer_join = false);
+struct BatchState;
+void finish_upload(BatchState* bs);
 void batch_set_sampling(Handle* h, const q3asr_sampling* opts);
 void pick_next_token(Handle* h, const float* logits, int vocab, const int32_t* generated, int n_generated, const q3asr_sampling* opts,
                      int draw, int32_t* token);

@@ -60,6 +60,7 @@ struct MelParams {
     float* out;
     const MelClip* clips;
     int batch;
+    int tile_lo;      // tiles [tile_lo, total_tiles) of the clips [0, batch) are transformed by this launch
     int total_tiles;
     int* gmax;
     float* tmin;
@@ -247,9 +248,9 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
 
     float4* scr4 = s_scr + pr * SCR_F4;                    // complex pairs: (re_A, re_B, im_A, im_B)
     float2* scrp = reinterpret_cast<float2*>(scr4);        // power spectrum pairs (P_A, P_B)
-    if (tid == 0) s_next[0] = find_clip(p.clips, p.batch, min((int)blockIdx.x, p.total_tiles - 1));
+    if (tid == 0) s_next[0] = find_clip(p.clips, p.batch, min(p.tile_lo + (int)blockIdx.x, p.total_tiles - 1));
     __syncthreads();
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = p.tile_lo + blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ci = s_next[0];
         const MelClip c = p.clips[ci];
         const int f0 = (tile - c.tile0) * MEL_TILE;
@@ -387,14 +388,14 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
 // already above the floor (1-2 % of the tiles of the bench clips are not).  The tiles that need the clamp are collected in shared
 // memory and then handled by the whole CTA, one tile at a time: warp w takes 16 mel rows, lane f frame f, all 16 rows in flight.
 constexpr int CLAMP_TILES = 64;
-__global__ void __launch_bounds__(256) mel_clamp_kernel(float* out, const MelClip* clips, int total_tiles, const int* gmax,
+__global__ void __launch_bounds__(256) mel_clamp_kernel(float* out, const MelClip* clips, int tile_lo, int total_tiles, const int* gmax,
                                                         const float* tmin, const int* tclip) {
     __shared__ int s_tile[CLAMP_TILES], s_clip[CLAMP_TILES];
     __shared__ float s_lo[CLAMP_TILES];
     __shared__ int s_n;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    const int tile = blockIdx.x * CLAMP_TILES + threadIdx.x;  // CLAMP_TILES deciders per CTA: about one tile to clamp per CTA
+    const int tile = tile_lo + blockIdx.x * CLAMP_TILES + threadIdx.x;  // CLAMP_TILES deciders per CTA: about one tile to clamp per CTA
     if (threadIdx.x < CLAMP_TILES && tile < total_tiles) {
         const int ci = tclip[tile];
         const float lo = mel_decode_max(gmax[ci]) - 8.0f;
@@ -522,7 +523,16 @@ void mel_tables_destroy(MelTables* t) {
 
 void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelClip* d_clips, int batch, int total_tiles,
                 int* d_gmax, float* d_tmin, int num_sms, cudaStream_t st) {
-    if (batch <= 0 || total_tiles <= 0) return;
+    mel_launch_range(t, d_pcm, d_out, d_clips, 0, batch, 0, total_tiles, total_tiles, d_gmax, d_tmin, num_sms, st);
+}
+
+// Clips [clip0, clip1) only: their tiles are [tile_lo, tile_hi) of the batch's `total_tiles` (MelClip::tile0 stays batch-wide).
+void mel_launch_range(const MelTables& t, const float* d_pcm, float* d_out, const MelClip* d_clips, int clip0, int clip1, int tile_lo,
+                      int tile_hi, int total_tiles, int* d_gmax, float* d_tmin, int num_sms, cudaStream_t st) {
+    const int batch = clip1 - clip0;
+    if (batch <= 0 || tile_hi <= tile_lo) return;
+    d_clips += clip0;  // clip indices inside the kernels are relative to the range, and so is the maximum array
+    d_gmax += clip0;
     MelParams p;
     p.hann = t.hann;
     p.tw256 = t.tw256;
@@ -535,14 +545,16 @@ void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelC
     p.out = d_out;
     p.clips = d_clips;
     p.batch = batch;
-    p.total_tiles = total_tiles;
+    p.tile_lo = tile_lo;
+    p.total_tiles = tile_hi;
     p.gmax = d_gmax;
     p.tmin = d_tmin;
     p.tclip = reinterpret_cast<int*>(d_tmin + total_tiles);  // d_tmin holds 2 * total_tiles words: [minimum | clip]
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
-    const int grid = std::min(total_tiles, num_sms * 2);  // 2 CTAs of 256 threads per SM (95 KB of shared memory each)
+    const int n_tiles = tile_hi - tile_lo;
+    const int grid = std::min(n_tiles, num_sms * 2);  // 2 CTAs of 256 threads per SM (95 KB of shared memory each)
     mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
-    mel_clamp_kernel<<<(total_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, total_tiles, d_gmax, d_tmin, p.tclip);
+    mel_clamp_kernel<<<(n_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, tile_lo, tile_hi, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());
 }
 

@@ -50,6 +50,10 @@ void mel_filterbank_host(float* fb);
 // total_tiles = sum of ntiles.  Two launches: main kernel, clamp pass (exits early per tile).
 void mel_launch(const MelTables& t, const float* d_pcm, float* d_out, const MelClip* d_clips, int batch,
                 int total_tiles, int* d_gmax, float* d_tmin, int num_sms, cudaStream_t st);
+// the same for the clips [clip0, clip1) of the batch only (their tiles are [tile_lo, tile_hi) of total_tiles): the upload overlaps
+// the first groups' transforms with the remaining copies
+void mel_launch_range(const MelTables& t, const float* d_pcm, float* d_out, const MelClip* d_clips, int clip0, int clip1, int tile_lo,
+                      int tile_hi, int total_tiles, int* d_gmax, float* d_tmin, int num_sms, cudaStream_t st);
 
 // Decoded clip maximum of log10(mel) (after mel_launch): used by consumers that fuse the clamp.
 __host__ __device__ inline float mel_decode_max(int key) {

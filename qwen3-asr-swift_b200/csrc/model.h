@@ -1,5 +1,9 @@
 // model.h — kernel-ready weights and the resident-batch state of one handle.
 #pragma once
+#include <atomic>
+#include <memory>
+#include <thread>
+
 #include "gemm.cuh"
 #include "handle.h"
 #include "megastep_params.h"
@@ -60,12 +64,34 @@ struct ClipInfo {
     int row0 = 0, prompt_len = 0, audio_at = 0;
 };
 
+// Host side of a batch upload that is still running (forward.cu batch_upload): worker threads copy the caller's clips into the
+// pinned staging area and queue their host -> device copies; `recorded[b]` turns 1 once clip b's copy is queued and its event
+// recorded (-1: it failed).  The threads borrow the caller's sample buffers, so the job is always joined before the API call that
+// started it returns (finish_upload / the destructor).
+struct UploadJob {
+    std::vector<std::thread> workers;
+    std::vector<cudaError_t> werr;
+    std::unique_ptr<std::atomic<int>[]> recorded;
+    std::vector<const float*> pcm;
+    std::vector<size_t> n_in, n16, raw_off;
+    std::vector<long long> in_off;
+    std::vector<int> rates;  // empty: every clip is 16 kHz
+    ~UploadJob() {
+        for (auto& t : workers)
+            if (t.joinable()) t.join();
+    }
+};
+
 struct BatchState {
+    std::unique_ptr<UploadJob> upload;  // non-null while the staging threads of the current batch may still be running
     int B = 0;
     MelPlan mel;
     std::vector<ClipInfo> clips;
     std::vector<int32_t> prompt_ids;  // packed
     int n_chunks = 0, n_tok = 0, n_win = 0, max_win = 0;
+    int mel_next = 0;              // clips [0, mel_next) have had their mel kernel launched in this run
+    bool copy_events = false;      // the clips of this batch were uploaded on the copy stream (one event per clip in Handle::copy_ev)
+    std::vector<char> copy_waited; // the compute stream already waits for this clip's copy
     int R = 0, max_prompt = 0;
     int max_tokens = 0;      // decode capacity the KV pages were reserved for
     int pages_per_seq = 0;
