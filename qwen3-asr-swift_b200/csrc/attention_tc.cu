@@ -219,9 +219,11 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const int q_abs = q0 + r;
         const uint32_t lane_addr = uint32_t(q * 32) << 16;
         const uint32_t tmem_pv = tmem_o(tq);
-        float o_acc[HD];
+        // the running output as (even, odd) pairs: the rescale-and-add of a block and the score scaling are packed fp32 operations
+        // (FADD2 / FMUL2 / FFMA2: the softmax warps are bound by their own instruction stream, ~10 per score)
+        float2 o_acc[HD / 2];
 #pragma unroll
-        for (int i = 0; i < HD; i++) o_acc[i] = 0.f;
+        for (int i = 0; i < HD / 2; i++) o_acc[i] = make_float2(0.f, 0.f);
         float m_run = -INFINITY, l_run = 0.f;
         uint8_t* p_row = sP + tq * C::P_BYTES + r * 128;
         for (int j = 0; j < nb; j++) {
@@ -272,7 +274,9 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                     ptx::tmem_ld_wait();
                     if (PIPE && c + 1 < HD / 32) ptx::tmem_ld_32x32(tmem_pv + lane_addr + (c + 1) * 32, v[(c + 1) & 1]);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(cur[i])) * alpha;
+                    for (int i = 0; i < 16; i++)
+                        o_acc[c * 16 + i] = f2_mul(f2_add(o_acc[c * 16 + i], make_float2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]))),
+                                                   make_float2(alpha, alpha));
                 }
             }
             // pass 2: P = exp2(s * scale - m), rounded to bf16 into the swizzled A-operand tile; row sum unrounded
@@ -288,8 +292,9 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                 if (c * 32 + 32 <= vis) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        const float a = fast_exp2(fmaf(__uint_as_float(cur[2 * i]), p.scale_log2, -m_new));
-                        const float b = fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), p.scale_log2, -m_new));
+                        const float2 sc = f2_fma(make_float2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])),
+                                                 make_float2(p.scale_log2, p.scale_log2), make_float2(-m_new, -m_new));
+                        const float a = fast_exp2(sc.x), b = fast_exp2(sc.y);
                         rs += a + b;
                         pk[i] = pack_bf16x2(a, b);
                     }
@@ -329,7 +334,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                 uint32_t w[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++)
-                    w[e] = pack_bf16x2((o_acc[c * 16 + 2 * e] + __uint_as_float(v[2 * e])) * inv, (o_acc[c * 16 + 2 * e + 1] + __uint_as_float(v[2 * e + 1])) * inv);
+                    w[e] = pack_bf16x2((o_acc[c * 8 + e].x + __uint_as_float(v[2 * e])) * inv, (o_acc[c * 8 + e].y + __uint_as_float(v[2 * e + 1])) * inv);
                 if (p.o32) {  // one 256-bit store per 16 dims (a thread owns a row: 32 lines per warp instruction either way)
                     st_global_v8(orow + c * 16, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
                 } else {
