@@ -6,24 +6,28 @@
 // slaney filterbank product (:263-268), clip/log10/clip-to-(max-8)/scale (:275-293), drop of the
 // last frame and the 120000-frame cap (:296-313), [128, T] mel-major output (:315-316).
 //
-// B200 design.  The kernel is bound by instruction issue, not by bytes (7.2 B of traffic per sample against ~500 fp32
-// instructions per frame for a 512-point real FFT + 504 filter taps + 128 logarithms), so the design goal
-// is issue slots per frame:
+// B200 design.  The stage moves 7.2 B per sample, but a 512-point FFT per 160 new samples makes it a shared-memory kernel: ncu
+// shows the LSU data pipe (one 128-byte wavefront per clock per SM) ~80 % busy while the SM is active, so
+// the design goal is wavefronts per frame, then issue slots:
 //   * Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2) processes two fp32 values per instruction.  Every value in the
 //     transform is held as a PAIR (frame A, frame B) of two neighbouring frames, so that EVERY arithmetic instruction of the FFT,
 //     the real-split step, the power spectrum and the filterbank is a packed one, with no shuffling inside a pair: half the
-//     arithmetic instructions per frame, and the shared-memory transposes move both frames with one 128-bit access.
+//     arithmetic instructions per frame, and the shared-memory transpose moves both frames with one 128-bit access.
 //   * Sixteen lanes share one frame pair (two pairs per warp, every synchronisation inside the transform is a __syncwarp); a CTA
-//     of 256 threads transforms the 32 frames of a tile in one pass.  A tile's samples (5360 floats, reflect padding resolved
-//     while loading) are staged once with 128-bit coalesced loads.
+//     of 8 * MEL_TILE threads transforms the frames of a tile in one pass, four (16-frame tiles) CTAs per SM.
 //   * The 512-point real FFT is the 256-point complex FFT of the even/odd packed frame, done as 16 x 16 (two in-register
-//     radix-16 passes with one shared-memory transpose), followed by the real-split step that yields bins k and 256-k together.
-//     The vDSP factor 2 cancels against the 1/2 of the split step (|2X|^2 = |e + w o|^2).  The filterbank is an ELL-packed sparse
-//     product (504 non-zeros instead of 32896 MACs per frame).
-//   * 0.25*log10(mel)+1 is written unclamped straight from registers (the two frames of a pair are neighbours in a mel row), with
-//     an ordered-int atomicMax per clip and a per-tile minimum; the second kernel applies the max-8 clamp only to tiles whose
-//     minimum is below it (exact, because clamp and the monotone affine map commute), so in the common case the features are
-//     written once and never re-read.
+//     radix-16 passes with ONE shared-memory transpose), followed by the real-split step that yields bins k and 256-k together;
+//     the partner value Z[256 - k] comes from lane 16 - t by warp shuffle, not through shared memory.  The vDSP factor 2 cancels
+//     against the 1/2 of the split step (|2X|^2 = |e + w o|^2).  The filterbank is an ELL-packed sparse product (504 non-zeros
+//     instead of 32896 MACs per frame).  (Measured and dropped in round 2: the filterbank as a banded bf16 hi/lo-split product on
+//     mma.sync — 20 % fewer wavefronts, but a latency-bound phase behind a third barrier: 188-200 us against 160.)
+//   * 0.25*log10(mel)+1 is written unclamped; the values are parked in shared memory and leave as whole mel rows (one 128-byte
+//     line per warp instruction instead of 16 scattered lines), with an ordered-int atomicMax per clip and a per-tile minimum;
+//     the second kernel applies the max-8 clamp only to tiles whose minimum is below it (exact, because clamp and the monotone
+//     affine map commute), so in the common case the features are written once and never re-read.
+//   * The tile loop is software-pipelined: the next tile's samples travel (cp.async) while this tile is transformed, the
+//     previous tile's rows are stored at the top of the next iteration; clip descriptors are looked up two tiles ahead by one
+//     thread and kept in shared memory.
 // The arithmetic per frame is operation for operation that of the scalar kernel this replaces (same products, same fused
 // multiply-adds, same order), so the results are bit-identical to it.
 #include <math.h>
@@ -39,13 +43,15 @@ namespace q3 {
 namespace {
 
 constexpr int TPF = 16;                                // lanes per frame pair
-constexpr int MEL_THREADS = 256;
+constexpr int MEL_THREADS = 8 * MEL_TILE;               // 16 lanes per frame pair
+constexpr int MEL_CTAS_PER_SM = MEL_TILE == 16 ? 4 : 2;
 constexpr int PAIRS = MEL_THREADS / TPF;               // 16 frame pairs in flight per CTA = the 32 frames of a tile
 static_assert(MEL_TILE == 2 * PAIRS, "a CTA transforms a whole tile in one pass");
 constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 5360
 constexpr int SX_FLOATS = TILE_SAMPLES + 16;
 constexpr int SCR_F4 = 256;                            // float4s of scratch per frame pair: the 16x16 transpose (XOR-swizzled columns,
                                                        // no padding) and then the flat spectrum
+constexpr int PARK_F2 = 384;                          // float2 offset of the parked features inside a pair's scratch block (the spectrum ends at 257)
 constexpr int HANN_PAD = 416;                          // window taps as (h, h) pairs, zero beyond 400
 
 struct MelParams {
@@ -71,7 +77,7 @@ struct MelParams {
 // (w, w) pairs: the kernel is bound by shared-memory wavefronts (ncu: LSU data pipe 80 % busy), not by issue slots, so a pair is
 // formed with a register move after an 8-byte load
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
-    return (SX_FLOATS + HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + 4 * PAIRS * SCR_F4 + 64) * 4;
+    return (SX_FLOATS + HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + 4 * PAIRS * SCR_F4 + 64) * 4;  // the last 64 words: reductions [32], next clips' indices [2], clips [2]
 }
 
 // Widths (taps) of the eight filterbank rounds: a property of the slaney filterbank at 16 kHz / 512 points / 128 bins, checked
@@ -224,7 +230,7 @@ __device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const f
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) {
+__global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const MelParams p) {
     extern __shared__ float4 smem4[];
     float* s_x = reinterpret_cast<float*>(smem4);
     float* s_hann = s_x + SX_FLOATS;                                      // [416], zero beyond 400
@@ -234,7 +240,8 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
     int* s_fbstart = reinterpret_cast<int*>(s_fbw + p.fb_rows * 16);      // [128]
     float4* s_scr = reinterpret_cast<float4*>(s_fbstart + 128);           // [PAIRS][SCR_F4]
     float* s_red = reinterpret_cast<float*>(s_scr + PAIRS * SCR_F4);      // [32]
-    int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip of the tile this CTA takes next (searched one tile ahead)
+    int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip index of the tiles this CTA takes next (searched two tiles ahead) ...
+    MelClip* s_clip = reinterpret_cast<MelClip*>(s_red + 36);  // ... and the clips themselves: one thread reads them from global memory
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -248,18 +255,45 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
 
     float4* scr4 = s_scr + pr * SCR_F4;                    // complex pairs: (re_A, re_B, im_A, im_B)
     float2* scrp = reinterpret_cast<float2*>(scr4);        // power spectrum pairs (P_A, P_B)
-    if (tid == 0) s_next[0] = find_clip(p.clips, p.batch, min(p.tile_lo + (int)blockIdx.x, p.total_tiles - 1));
+    // Software pipeline over the CTA's tiles.  Per tile: (A) the previous tile's features leave as whole rows, (B) this tile's
+    // windowed samples are read into registers, barrier, (C) the NEXT tile's samples start travelling into the same buffer
+    // (cp.async, landing during the transforms), (D) transforms, filterbank, parking of the features, barrier.  Two CTA barriers
+    // per tile, none of them waiting for global memory.
+    const int tile_first = p.tile_lo + blockIdx.x, tile_step = gridDim.x;
+    constexpr int ROWS_PER_INSTR = 32 / MEL_TILE, ROWS_PER_WARP = MEL_BINS / (MEL_THREADS / 32);
+    const int row_fr = lane % MEL_TILE, row_pq = row_fr >> 1;
+    const float* parked = reinterpret_cast<const float*>(s_scr) + (size_t)row_pq * (4 * SCR_F4) + 2 * PARK_F2 + (row_fr & 1);
+    float* prev_o = nullptr;  // row stores of the previous tile: first element of this lane's column, row stride, in-range flag
+    int prev_T = 0;
+    bool prev_on = false;
+    auto store_rows = [&]() {  // a warp instruction writes 32 / MEL_TILE whole mel rows of the tile, lane -> (row, frame)
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_WARP / ROWS_PER_INSTR; i++) {
+            const int m = ROWS_PER_WARP * warp + ROWS_PER_INSTR * i + lane / MEL_TILE;
+            const float val = parked[2 * ((m + row_pq) & 127)];
+            if (prev_on) prev_o[(size_t)m * prev_T] = val;
+        }
+    };
+    if (tid == 0) {  // clips of the first two tiles; later ones are searched two tiles ahead
+        s_next[0] = find_clip(p.clips, p.batch, min(tile_first, p.total_tiles - 1));
+        s_next[1] = find_clip(p.clips, p.batch, min(tile_first + tile_step, p.total_tiles - 1));
+        s_clip[0] = p.clips[s_next[0]];
+        s_clip[1] = p.clips[s_next[1]];
+    }
     __syncthreads();
-    for (int tile = p.tile_lo + blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ci = s_next[0];
-        const MelClip c = p.clips[ci];
+    if (tile_first < p.total_tiles) {
+        const MelClip c0 = s_clip[0];
+        stage_tile(s_x, c0, p.pcm, (tile_first - c0.tile0) * MEL_TILE, tid);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    int it = 0;
+    for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, it++) {
+        const int ci = s_next[it & 1];
+        const MelClip c = s_clip[it & 1];
         const int f0 = (tile - c.tile0) * MEL_TILE;
         const int nF = c.n / MEL_HOP + 1;  // frames incl. the one that is dropped (max runs over it, Q3)
-        stage_tile(s_x, c, p.pcm, f0, tid);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        // the binary search for the next tile's clip (dependent L2 loads) overlaps this tile's transforms
-        if (tid == MEL_THREADS - 1 && tile + (int)gridDim.x < p.total_tiles) s_next[0] = find_clip(p.clips, p.batch, tile + gridDim.x);
+        if (prev_o != nullptr) store_rows();
 
         const int fl = 2 * pr;  // local frames fl (A) and fl + 1 (B)
         const float* xa = s_x + fl * MEL_HOP + 2 * t;
@@ -276,6 +310,20 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
             v[n2].im = mul2(make_float2(a.y, b.y), splat(hw.y));
         }
         v[13].re = v[13].im = v[14].re = v[14].im = v[15].re = v[15].im = make_float2(0.f, 0.f);
+        __syncthreads();  // every lane has its samples (the buffer is free) and has read the previous tile's parked features
+        {
+            const int ntile = tile + tile_step;
+            if (ntile < p.total_tiles) {
+                const MelClip cn = s_clip[(it + 1) & 1];
+                stage_tile(s_x, cn, p.pcm, (ntile - cn.tile0) * MEL_TILE, tid);
+            }
+            // the binary search for the clip of the tile after that (dependent L2 loads) overlaps this tile's transforms
+            if (tid == MEL_THREADS - 1 && ntile + tile_step < p.total_tiles) {
+                const int cj = find_clip(p.clips, p.batch, ntile + tile_step);
+                s_next[it & 1] = cj;
+                s_clip[it & 1] = p.clips[cj];
+            }
+        }
         fft16(v);
         // row t, column k2 lives at float4 index 16 t + (k2 ^ t): conflict-free for the row-wise stores and the column-wise loads
         scr4[t * 16 + t] = make_float4(v[0].re.x, v[0].re.y, v[0].im.x, v[0].im.y);
@@ -294,23 +342,26 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
             v[n1].im = make_float2(q.z, q.w);
         }
         __syncwarp();
-        fft16(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) {
-            const C2 z = v[rev16(k1)];
-            scr4[16 * k1 + t] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);  // Z[16 k1 + t]
-        }
-        __syncwarp();
-        // ---- real split: bins k and 256-k from Z[k], Z[256-k];  P = |2 X|^2 ----
+        fft16(v);  // Z[16 k1 + t] is now v[rev16(k1)]
+        // ---- real split: bins k and 256-k from Z[k], Z[256-k];  P = |2 X|^2.  Lane t owns k = t + 16 j (j < 8): Z[k] is its own
+        //      v[rev16(j)]; the partner Z[256 - k] = Z[(16 - t) + 16 (15 - j)] lives in lane 16 - t at k1 = 15 - j (lane 0 pairs with
+        //      itself, at k1 = 16 - j) and comes over with warp shuffles instead of a second trip through shared memory (a 4 KB
+        //      store and 4 KB of gathers per frame pair: the kernel is bound by shared-memory wavefronts) ----
         float2 pk[8], pm[8];
         float2 p128 = make_float2(0.f, 0.f);
+        const int partner = (lane & 16) | ((16 - t) & 15);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int k = t + 16 * j;
-            const float4 zk = scr4[k];
-            const float4 zm = scr4[(256 - k) & 255];
+            const C2 mine = v[rev16(j)];
+            const C2 give0 = v[rev16((16 - j) & 15)], give = v[rev16(15 - j)];  // what this lane hands out: lane 0 / the others
+            float2 zmr, zmi;
+            zmr.x = __shfl_sync(0xffffffffu, t == 0 ? give0.re.x : give.re.x, partner);
+            zmr.y = __shfl_sync(0xffffffffu, t == 0 ? give0.re.y : give.re.y, partner);
+            zmi.x = __shfl_sync(0xffffffffu, t == 0 ? give0.im.x : give.im.x, partner);
+            zmi.y = __shfl_sync(0xffffffffu, t == 0 ? give0.im.y : give.im.y, partner);
             const float2 w = s_tw512[k];
-            const float2 zkr = make_float2(zk.x, zk.y), zki = make_float2(zk.z, zk.w), zmr = make_float2(zm.x, zm.y), zmi = make_float2(zm.z, zm.w);
+            const float2 zkr = mine.re, zki = mine.im;
             const float2 er = cadd(zkr, zmr), ei = csub(zki, zmi);
             C2 o;
             o.re = cadd(zki, zmi);
@@ -321,16 +372,14 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
             pm[j] = fma2(bx, bx, mul2(by, by));
         }
         if (t == 0) {
-            const float4 z0 = scr4[0];
-            const float2 z0r = make_float2(z0.x, z0.y), z0i = make_float2(z0.z, z0.w);
+            const float2 z0r = v[rev16(0)].re, z0i = v[rev16(0)].im;  // Z[0]
             const float2 dc = mul2(splat(2.f), cadd(z0r, z0i)), ny = mul2(splat(2.f), csub(z0r, z0i));
             pk[0] = mul2(dc, dc);
             pm[0] = mul2(ny, ny);
-            const float4 zh = scr4[128];
-            const float2 zhr = make_float2(zh.x, zh.y), zhi = make_float2(zh.z, zh.w);
+            const float2 zhr = v[rev16(8)].re, zhi = v[rev16(8)].im;  // Z[128]
             p128 = mul2(splat(4.f), fma2(zhr, zhr, mul2(zhi, zhi)));
         }
-        __syncwarp();
+        __syncwarp();  // every lane of the pair has read the transposed values (pass 2) before the spectrum overwrites them
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int k = t + 16 * j;
@@ -352,15 +401,18 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
         accs[6] = fb_round<6>(scrp, s_fbw, s_fbstart, t);
         accs[7] = fb_round<7>(scrp, s_fbw, s_fbstart, t);
         float lmax = -INFINITY, lmin = INFINITY;
-        const int T = c.frames;
-        float* o = p.out + c.out_off + f0 + fl;
+        // The features leave through shared memory: lane t holds mel rows t, t + 16, ... of two frames, and storing them from here
+        // touches 16 different 128-byte lines per warp instruction (16 wavefronts each, 64 per frame: a quarter of the kernel's
+        // shared-memory / L1 wavefronts).  They are parked in the unused tail of the pair's scratch block instead (row m of pair pr
+        // at word 2 ((m + pr) & 127), which makes both the parking stores and the row-wise reads below conflict-free) and written
+        // out after the tile barrier as whole rows: one 128-byte line per warp instruction.
+        float2* park = reinterpret_cast<float2*>(scr4) + PARK_F2;
 #pragma unroll
         for (int j = 0; j < MEL_ROUNDS; j++) {
             const int m = t + 16 * j;
             const float La = 0.30102999566398120f * __log2f(fmaxf(accs[j].x, 1e-10f));
             const float Lb = 0.30102999566398120f * __log2f(fmaxf(accs[j].y, 1e-10f));
-            if (in_out_a) o[(size_t)m * T] = fmaf(0.25f, La, 1.0f);
-            if (in_out_b) o[(size_t)m * T + 1] = fmaf(0.25f, Lb, 1.0f);
+            park[(m + pr) & 127] = make_float2(fmaf(0.25f, La, 1.0f), fmaf(0.25f, Lb, 1.0f));
             if (in_max_a) lmax = fmaxf(lmax, La);
             if (in_max_b) lmax = fmaxf(lmax, Lb);
             if (in_out_a) lmin = fminf(lmin, La);
@@ -371,7 +423,8 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
         lmax = warp_max(lmax);
         lmin = -warp_max(-lmin);
         if (lane == 0) { s_red[warp] = lmax; s_red[16 + warp] = lmin; }
-        __syncthreads();  // also: every lane is done with s_x before the next tile is staged
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the next tile's samples has landed (long ago)
+        __syncthreads();  // the tile's features are parked, its reductions written, the next tile's samples visible to every lane
         if (tid == 0) {
             float gm = s_red[0], tm = s_red[16];
 #pragma unroll
@@ -380,7 +433,11 @@ __global__ void __launch_bounds__(MEL_THREADS, 2) mel_kernel(const MelParams p) 
             p.tmin[tile] = tm;
             p.tclip[tile] = ci;
         }
+        prev_o = p.out + c.out_off + f0 + row_fr;
+        prev_T = c.frames;
+        prev_on = f0 + row_fr < c.frames;
     }
+    if (prev_o != nullptr) store_rows();
 }
 
 // Second pass: clip to (clip max - 8) where a tile needs it (AudioPreprocessing.swift:281-293).  One THREAD per tile decides from
@@ -552,7 +609,7 @@ void mel_launch_range(const MelTables& t, const float* d_pcm, float* d_out, cons
     p.tclip = reinterpret_cast<int*>(d_tmin + total_tiles);  // d_tmin holds 2 * total_tiles words: [minimum | clip]
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
     const int n_tiles = tile_hi - tile_lo;
-    const int grid = std::min(n_tiles, num_sms * 2);  // 2 CTAs of 256 threads per SM (95 KB of shared memory each)
+    const int grid = std::min(n_tiles, num_sms * MEL_CTAS_PER_SM);
     mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
     mel_clamp_kernel<<<(n_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, tile_lo, tile_hi, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());

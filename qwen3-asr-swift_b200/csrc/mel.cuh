@@ -13,7 +13,7 @@ constexpr int MEL_BINS = 128;
 constexpr int MEL_FFT = 512;       // zero-padded FFT length (reference quirk Q1)
 constexpr int MEL_NFREQ = 257;
 constexpr int MEL_MAX_FRAMES = 120000;
-constexpr int MEL_TILE = 32;       // frames per tile: one pass of a 256-thread CTA (16 frame pairs, 16 lanes each)
+constexpr int MEL_TILE = 16;       // frames per tile: one pass of a CTA of 8 * MEL_TILE threads (8 frame pairs, 16 lanes each); 16 or 32
 constexpr int MEL_ROUNDS = 8;      // 128 mel bins / 16 lanes per frame
 
 // One clip of a batch, all offsets in elements.
