@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <vector>
 
 #include "mel.cuh"
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
     auto store_rows = [&]() {  // a warp instruction writes 32 / MEL_TILE whole mel rows of the tile, lane -> (row, frame)
 #pragma unroll
         for (int i = 0; i < ROWS_PER_WARP / ROWS_PER_INSTR; i++) {
-            const int m = ROWS_PER_WARP * warp + ROWS_PER_INSTR * i + lane / MEL_TILE;
+            // two rows per instruction (16-frame tiles): rows m and m + 8, whose parked words fall in different banks
+            const int m = ROWS_PER_INSTR == 2 ? ROWS_PER_WARP * warp + (i & 7) + 16 * (i >> 3) + 8 * (lane / MEL_TILE) : ROWS_PER_WARP * warp + i;
             const float val = parked[2 * ((m + row_pq) & 127)];
             if (prev_on) prev_o[(size_t)m * prev_T] = val;
         }
@@ -287,10 +289,21 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    // Clip of the tile two steps ahead, found by the last warp without anybody waiting for it: the candidates' first-tile numbers
+    // are loaded (one per lane and 32 clips) while the transforms run, counted at the end of the tile, the clip's descriptor is
+    // fetched then and put into shared memory at the top of the next iteration.  (One thread's binary search, six dependent L2
+    // round trips per tile, made its warp the last at every tile barrier.)
+    constexpr int LOOKUP_WARP = MEL_THREADS / 32 - 1, LOOKUP_SLOTS = 4;
+    int pend_cj = -1, pend_word = 0;
     int it = 0;
     for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, it++) {
         const int ci = s_next[it & 1];
         const MelClip c = s_clip[it & 1];
+        if (warp == LOOKUP_WARP && pend_cj >= 0) {  // found during the previous tile: the clip of tile + tile_step
+            if (lane == 0) s_next[(it + 1) & 1] = pend_cj;
+            if (lane < (int)(sizeof(MelClip) / 4)) reinterpret_cast<int*>(&s_clip[(it + 1) & 1])[lane] = pend_word;
+            pend_cj = -1;
+        }
         const int f0 = (tile - c.tile0) * MEL_TILE;
         const int nF = c.n / MEL_HOP + 1;  // frames incl. the one that is dropped (max runs over it, Q3)
         if (prev_o != nullptr) store_rows();
@@ -317,11 +330,17 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
                 const MelClip cn = s_clip[(it + 1) & 1];
                 stage_tile(s_x, cn, p.pcm, (ntile - cn.tile0) * MEL_TILE, tid);
             }
-            // the binary search for the clip of the tile after that (dependent L2 loads) overlaps this tile's transforms
-            if (tid == MEL_THREADS - 1 && ntile + tile_step < p.total_tiles) {
-                const int cj = find_clip(p.clips, p.batch, ntile + tile_step);
-                s_next[it & 1] = cj;
-                s_clip[it & 1] = p.clips[cj];
+        }
+        const int tile2 = tile + 2 * tile_step;  // the tile whose clip is looked up during this one
+        const bool lookup = warp == LOOKUP_WARP && tile2 < p.total_tiles;
+        int first_tile[LOOKUP_SLOTS];  // candidates' first tiles, or (very large batches: one lane's dependent search after all) the answer
+        if (lookup) {
+            if (p.batch <= 32 * LOOKUP_SLOTS) {
+#pragma unroll
+                for (int k = 0; k < LOOKUP_SLOTS; k++)
+                    first_tile[k] = lane + 32 * k < p.batch ? __ldg(&p.clips[lane + 32 * k].tile0) : 0x7fffffff;
+            } else {
+                first_tile[0] = lane == 0 ? find_clip(p.clips, p.batch, tile2) : 0;
             }
         }
         fft16(v);
@@ -423,6 +442,19 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
         lmax = warp_max(lmax);
         lmin = -warp_max(-lmin);
         if (lane == 0) { s_red[warp] = lmax; s_red[16 + warp] = lmin; }
+        if (lookup) {  // clips are ordered by first tile: the clip of tile2 is the last one that starts at or before it
+            int cj;
+            if (p.batch <= 32 * LOOKUP_SLOTS) {
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < LOOKUP_SLOTS; k++) cnt += first_tile[k] <= tile2 ? 1 : 0;
+                cj = __reduce_add_sync(0xffffffffu, cnt) - 1;
+            } else {
+                cj = __shfl_sync(0xffffffffu, first_tile[0], 0);
+            }
+            pend_cj = cj;
+            pend_word = lane < (int)(sizeof(MelClip) / 4) ? __ldg(reinterpret_cast<const int*>(&p.clips[cj]) + lane) : 0;
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the next tile's samples has landed (long ago)
         __syncthreads();  // the tile's features are parked, its reductions written, the next tile's samples visible to every lane
         if (tid == 0) {
@@ -540,8 +572,33 @@ void mel_tables_create(MelTables* t) {
     for (int j = 0; j < MEL_ROUNDS; j++) {
         int mw = 1;
         for (int i = 0; i < 16; i++) mw = std::max(mw, width[16 * j + i]);
-        for (int i = 0; i < 16; i++)
-            if (start[16 * j + i] + mw > MEL_NFREQ) start[16 * j + i] = MEL_NFREQ - mw;  // keep padded taps in range
+        // A filter narrower than the round's width may start up to (mw - width) bins early (zero weights in front): the slack is
+        // used to give the 16 lanes of a round start bins that are distinct modulo 16 (or equal), so that the 8-byte gathers of a
+        // frame pair's spectrum touch each bank pair once: the gathers took 92 wavefronts per frame pair instead of 40 (ncu: 6 M
+        // bank conflicts, 20 % of the kernel's shared-memory wavefronts).  Leading zero taps leave the sums bit-identical.
+        int lo[16], hi[16], pick[16];
+        for (int i = 0; i < 16; i++) {
+            hi[i] = std::min(start[16 * j + i], MEL_NFREQ - mw);  // keep padded taps in range
+            lo[i] = std::max(0, start[16 * j + i] - (mw - width[16 * j + i]));
+            lo[i] = std::min(lo[i], hi[i]);
+        }
+        int owner[16];  // start bin that holds each residue, -1 = free
+        for (int r = 0; r < 16; r++) owner[r] = -1;
+        std::function<bool(int)> place = [&](int i) -> bool {
+            if (i == 16) return true;
+            for (int s0 = hi[i]; s0 >= lo[i]; s0--) {
+                const int r = s0 & 15;
+                if (owner[r] >= 0 && owner[r] != s0) continue;
+                const int was = owner[r];
+                owner[r] = s0;
+                pick[i] = s0;
+                if (place(i + 1)) return true;
+                owner[r] = was;
+            }
+            return false;
+        };
+        if (place(0)) for (int i = 0; i < 16; i++) start[16 * j + i] = pick[i];
+        else for (int i = 0; i < 16; i++) start[16 * j + i] = hi[i];
         t->fb_round_off[j + 1] = t->fb_round_off[j] + mw;
     }
     t->fb_rows = t->fb_round_off[MEL_ROUNDS];
