@@ -58,6 +58,20 @@ def test_mel_ragged_batch_equals_single(tiny_model):
         _check(o, omel.mel(c), f"batch n={c.size}")
 
 
+@pytest.mark.parametrize("count", [33, 128, 200])
+def test_mel_many_short_clips(tiny_model, count):
+    # Many clips of a few tiles each: every CTA changes clip at almost every tile, so the look-ahead clip lookup of the tile loop
+    # (csrc/mel.cu: candidates spread over a warp up to 128 clips, one lane's search above) is what this exercises.
+    rng = np.random.default_rng(count)
+    lens = [int(n) for n in rng.integers(160, 6000, size=count)]
+    clips = [synth.clip(1000 + i, n) for i, n in enumerate(lens)]
+    outs = tiny_model.extract_features_batch(clips)
+    for i in range(0, count, 7):
+        _check(outs[i], omel.mel(clips[i]), f"clip {i} of {count}, n={lens[i]}")
+    for i in (0, count // 2, count - 1):
+        assert np.array_equal(outs[i], tiny_model.extract_features(clips[i]))
+
+
 def test_mel_properties_full_size(tiny_model):
     # BASELINE config sizes (64 x 30 s): size-independent properties instead of a slow oracle pass
     clips = [synth.clip(i, 480000) for i in range(64)]
