@@ -45,7 +45,10 @@ namespace {
 
 constexpr int TPF = 16;                                // lanes per frame pair
 constexpr int MEL_THREADS = 8 * MEL_TILE;               // 16 lanes per frame pair
-constexpr int MEL_CTAS_PER_SM = MEL_TILE == 16 ? 4 : 2;
+// A CTA is GROUPS independent groups of MEL_THREADS threads: each walks its own tiles with its own sample buffer, scratch and named
+// barrier, and they share the constant tables.  One CTA per SM: 5 groups of 16-frame tiles (20 warps at <= 102 registers, 224 KB
+// of shared memory — both budgets nearly full) where four separate CTAs, each with its own copy of the tables, were the limit.
+constexpr int GROUPS = MEL_TILE == 16 ? 5 : 2;
 constexpr int PAIRS = MEL_THREADS / TPF;               // 16 frame pairs in flight per CTA = the 32 frames of a tile
 static_assert(MEL_TILE == 2 * PAIRS, "a CTA transforms a whole tile in one pass");
 constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 5360
@@ -74,11 +77,11 @@ struct MelParams {
     int* tclip;  // clip of every tile (for the clamp pass)
 };
 
-// samples | hann | tw256 | tw512 | filterbank weights | filter starts | scratch | reductions.  The tables are NOT stored as
+// hann | tw256 | tw512 | filterbank weights | filter starts | per group: samples | scratch | reductions.  The tables are NOT stored as
 // (w, w) pairs: the kernel is bound by shared-memory wavefronts (ncu: LSU data pipe 80 % busy), not by issue slots, so a pair is
 // formed with a register move after an 8-byte load
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
-    return (SX_FLOATS + HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + 4 * PAIRS * SCR_F4 + 64) * 4;  // the last 64 words: reductions [32], next clips' indices [2], clips [2]
+    return (HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + GROUPS * (SX_FLOATS + 4 * PAIRS * SCR_F4 + 64)) * 4;  // the last 64 words: reductions [32], next clips' indices [2], clips [2]
 }
 
 // Widths (taps) of the eight filterbank rounds: a property of the slaney filterbank at 16 kHz / 512 points / 128 bins, checked
@@ -231,28 +234,30 @@ __device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const f
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const MelParams p) {
+__global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelParams p) {
     extern __shared__ float4 smem4[];
-    float* s_x = reinterpret_cast<float*>(smem4);
-    float* s_hann = s_x + SX_FLOATS;                                      // [416], zero beyond 400
+    float* s_hann = reinterpret_cast<float*>(smem4);                      // [416], zero beyond 400
     float2* s_tw256 = reinterpret_cast<float2*>(s_hann + HANN_PAD);       // [256] (wr, wi)
     float2* s_tw512 = s_tw256 + 256;                                      // [130]
     float* s_fbw = reinterpret_cast<float*>(s_tw512 + 130);               // [fb_rows * 16]
     int* s_fbstart = reinterpret_cast<int*>(s_fbw + p.fb_rows * 16);      // [128]
-    float4* s_scr = reinterpret_cast<float4*>(s_fbstart + 128);           // [PAIRS][SCR_F4]
+    const int group = threadIdx.x / MEL_THREADS;                          // this thread's group and its private buffers
+    float* s_x = reinterpret_cast<float*>(s_fbstart + 128) + (size_t)group * (SX_FLOATS + 4 * PAIRS * SCR_F4 + 64);
+    float4* s_scr = reinterpret_cast<float4*>(s_x + SX_FLOATS);           // [PAIRS][SCR_F4]
     float* s_red = reinterpret_cast<float*>(s_scr + PAIRS * SCR_F4);      // [32]
-    int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip index of the tiles this CTA takes next (searched two tiles ahead) ...
-    MelClip* s_clip = reinterpret_cast<MelClip*>(s_red + 36);  // ... and the clips themselves: one thread reads them from global memory
+    int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip index of the tiles this group takes next (found two tiles ahead) ...
+    MelClip* s_clip = reinterpret_cast<MelClip*>(s_red + 36);  // ... and the clips themselves
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(MEL_THREADS) : "memory"); };
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % MEL_THREADS;  // within the group
     const int lane = tid & 31, warp = tid >> 5;
     const int t = tid & 15, pr = tid >> 4;  // lane within the frame pair, frame pair within the tile
 
-    for (int i = tid; i < HANN_PAD; i += MEL_THREADS) s_hann[i] = i < MEL_NFFT ? __ldg(&p.hann[i]) : 0.f;
-    for (int i = tid; i < 256; i += MEL_THREADS) s_tw256[i] = __ldg(&p.tw256[i]);
-    for (int i = tid; i < 129; i += MEL_THREADS) s_tw512[i] = __ldg(&p.tw512[i]);
-    for (int i = tid; i < p.fb_rows * 16; i += MEL_THREADS) s_fbw[i] = __ldg(&p.fbw[i]);
-    for (int i = tid; i < 128; i += MEL_THREADS) s_fbstart[i] = __ldg(&p.fb_start[i]);
+    for (int i = threadIdx.x; i < HANN_PAD; i += blockDim.x) s_hann[i] = i < MEL_NFFT ? __ldg(&p.hann[i]) : 0.f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tw256[i] = __ldg(&p.tw256[i]);
+    for (int i = threadIdx.x; i < 129; i += blockDim.x) s_tw512[i] = __ldg(&p.tw512[i]);
+    for (int i = threadIdx.x; i < p.fb_rows * 16; i += blockDim.x) s_fbw[i] = __ldg(&p.fbw[i]);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_fbstart[i] = __ldg(&p.fb_start[i]);
 
     float4* scr4 = s_scr + pr * SCR_F4;                    // complex pairs: (re_A, re_B, im_A, im_B)
     float2* scrp = reinterpret_cast<float2*>(scr4);        // power spectrum pairs (P_A, P_B)
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
     // windowed samples are read into registers, barrier, (C) the NEXT tile's samples start travelling into the same buffer
     // (cp.async, landing during the transforms), (D) transforms, filterbank, parking of the features, barrier.  Two CTA barriers
     // per tile, none of them waiting for global memory.
-    const int tile_first = p.tile_lo + blockIdx.x, tile_step = gridDim.x;
+    const int tile_first = p.tile_lo + GROUPS * blockIdx.x + group, tile_step = GROUPS * gridDim.x;
     constexpr int ROWS_PER_INSTR = 32 / MEL_TILE, ROWS_PER_WARP = MEL_BINS / (MEL_THREADS / 32);
     const int row_fr = lane % MEL_TILE, row_pq = row_fr >> 1;
     const float* parked = reinterpret_cast<const float*>(s_scr) + (size_t)row_pq * (4 * SCR_F4) + 2 * PARK_F2 + (row_fr & 1);
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
             v[n2].im = mul2(make_float2(a.y, b.y), splat(hw.y));
         }
         v[13].re = v[13].im = v[14].re = v[14].im = v[15].re = v[15].im = make_float2(0.f, 0.f);
-        __syncthreads();  // every lane has its samples (the buffer is free) and has read the previous tile's parked features
+        group_sync();  // every lane has its samples (the buffer is free) and has read the previous tile's parked features
         {
             const int ntile = tile + tile_step;
             if (ntile < p.total_tiles) {
@@ -366,8 +371,8 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
         //      v[rev16(j)]; the partner Z[256 - k] = Z[(16 - t) + 16 (15 - j)] lives in lane 16 - t at k1 = 15 - j (lane 0 pairs with
         //      itself, at k1 = 16 - j) and comes over with warp shuffles instead of a second trip through shared memory (a 4 KB
         //      store and 4 KB of gathers per frame pair: the kernel is bound by shared-memory wavefronts) ----
-        float2 pk[8], pm[8];
-        float2 p128 = make_float2(0.f, 0.f);
+        // The spectrum goes straight into the pair's scratch block (every lane of the pair has read its transposed values before
+        // the __syncwarp above), pair by pair of bins, so that the 32 power values are never all live in registers.
         const int partner = (lane & 16) | ((16 - t) & 15);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -387,25 +392,18 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
             o.im = csub(zmr, zkr);
             const C2 tw = cmulc(o, w.x, w.y);
             const float2 ax = cadd(er, tw.re), ay = cadd(ei, tw.im), bx = csub(er, tw.re), by = csub(ei, tw.im);
-            pk[j] = fma2(ax, ax, mul2(ay, ay));
-            pm[j] = fma2(bx, bx, mul2(by, by));
+            float2 pk = fma2(ax, ax, mul2(ay, ay)), pm = fma2(bx, bx, mul2(by, by));
+            if (j == 0 && t == 0) {  // bins 0, 256 (from Z[0]) and 128 (from Z[128]) are real-valued special cases
+                const float2 z0r = v[rev16(0)].re, z0i = v[rev16(0)].im;
+                const float2 dc = mul2(splat(2.f), cadd(z0r, z0i)), ny = mul2(splat(2.f), csub(z0r, z0i));
+                pk = mul2(dc, dc);
+                pm = mul2(ny, ny);
+                const float2 zhr = v[rev16(8)].re, zhi = v[rev16(8)].im;
+                scrp[128] = mul2(splat(4.f), fma2(zhr, zhr, mul2(zhi, zhi)));
+            }
+            scrp[k] = pk;
+            scrp[256 - k] = pm;
         }
-        if (t == 0) {
-            const float2 z0r = v[rev16(0)].re, z0i = v[rev16(0)].im;  // Z[0]
-            const float2 dc = mul2(splat(2.f), cadd(z0r, z0i)), ny = mul2(splat(2.f), csub(z0r, z0i));
-            pk[0] = mul2(dc, dc);
-            pm[0] = mul2(ny, ny);
-            const float2 zhr = v[rev16(8)].re, zhi = v[rev16(8)].im;  // Z[128]
-            p128 = mul2(splat(4.f), fma2(zhr, zhr, mul2(zhi, zhi)));
-        }
-        __syncwarp();  // every lane of the pair has read the transposed values (pass 2) before the spectrum overwrites them
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = t + 16 * j;
-            scrp[k] = pk[j];
-            scrp[256 - k] = pm[j];
-        }
-        if (t == 0) scrp[128] = p128;
         __syncwarp();
         // ---- sparse filterbank, log10, scale; lane t owns mel bins t, t+16, ... of both frames ----
         const bool in_max_a = (f0 + fl) < nF, in_max_b = (f0 + fl + 1) < nF;
@@ -456,7 +454,7 @@ __global__ void __launch_bounds__(MEL_THREADS, MEL_CTAS_PER_SM) mel_kernel(const
             pend_word = lane < (int)(sizeof(MelClip) / 4) ? __ldg(reinterpret_cast<const int*>(&p.clips[cj]) + lane) : 0;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the next tile's samples has landed (long ago)
-        __syncthreads();  // the tile's features are parked, its reductions written, the next tile's samples visible to every lane
+        group_sync();  // the tile's features are parked, its reductions written, the next tile's samples visible to every lane
         if (tid == 0) {
             float gm = s_red[0], tm = s_red[16];
 #pragma unroll
@@ -666,8 +664,8 @@ void mel_launch_range(const MelTables& t, const float* d_pcm, float* d_out, cons
     p.tclip = reinterpret_cast<int*>(d_tmin + total_tiles);  // d_tmin holds 2 * total_tiles words: [minimum | clip]
     Q3_CUDA(cudaMemsetAsync(d_gmax, 0x80, sizeof(int) * batch, st));
     const int n_tiles = tile_hi - tile_lo;
-    const int grid = std::min(n_tiles, num_sms * MEL_CTAS_PER_SM);
-    mel_kernel<<<grid, MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
+    const int grid = std::min((n_tiles + GROUPS - 1) / GROUPS, num_sms);  // one CTA of GROUPS groups per SM
+    mel_kernel<<<grid, GROUPS * MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
     mel_clamp_kernel<<<(n_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, tile_lo, tile_hi, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());
 }
