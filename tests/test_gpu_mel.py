@@ -72,6 +72,20 @@ def test_mel_many_short_clips(tiny_model, count):
         assert np.array_equal(outs[i], tiny_model.extract_features(clips[i]))
 
 
+def test_mel_repeatable_under_load(tiny_model):
+    # The tile loop is software-pipelined across five independent groups per CTA that alias their scratch blocks (transpose ->
+    # spectrum -> parked features): a missing barrier shows up as run-to-run differences.  (compute-sanitizer is not available on
+    # the GPU pool; this is the race check that is.)
+    lens = [48000, 1600, 4799, 16000, 24000, 161, 160, 5121] + [int(n) for n in np.random.default_rng(1).integers(160, 20000, size=140)]
+    clips = [synth.clip(i, n) for i, n in enumerate(lens)]
+    first = tiny_model.extract_features_batch(clips)
+    for _ in range(6):
+        again = tiny_model.extract_features_batch(clips)
+        assert all(np.array_equal(a, b) for a, b in zip(first, again))
+    for i in (0, 5, 6, 7, 50, 147):
+        _check(first[i], omel.mel(clips[i]), f"clip {i}, n={lens[i]}")
+
+
 def test_mel_properties_full_size(tiny_model):
     # BASELINE config sizes (64 x 30 s): size-independent properties instead of a slow oracle pass
     clips = [synth.clip(i, 480000) for i in range(64)]
