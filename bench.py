@@ -223,6 +223,17 @@ def pool_extras(world, steps):
                                  "ms_per_step": 1000 * sec,
                                  "how": "BASELINE config 3 as written: 64 x 30 s clips in total, 64 / N per GPU, through the pool; "
                                         "the decode step at 64 / N sequences is latency-bound, so this is far from linear by construction"}
+        one = [clips[0]]  # BASELINE config 2: one 30 s clip, 128 tokens, batch 1, on GPU 0 (latency, not throughput)
+        lat = []
+        pool.transcribe_ids(one, MAX_TOKENS, stop_on_eos=False, max_batch_per_gpu=1)
+        for _ in range(5):
+            t0 = time.perf_counter()
+            pool.transcribe_ids(one, MAX_TOKENS, stop_on_eos=False, max_batch_per_gpu=1)
+            lat.append(time.perf_counter() - t0)
+        sec = float(np.median(lat))
+        out["config2"] = {"value": CLIP_SECONDS / sec, "unit": UNIT, "n_gpus": 1, "ms_per_clip": 1000 * sec, "max_tokens": MAX_TOKENS,
+                          "how": "one 30 s host clip through the blocking pool call (mel, encoder, prefill, 128 greedy tokens), median of 5: the "
+                                 "decode chain at batch 1 is 196 dependent phases per token, latency-bound"}
     finally:
         pool.close()
     pool = q3asr.Pool("1.7B", devices=devs, seed=SEED)
