@@ -478,6 +478,26 @@ def main():
         roof_gemm = roof_of(tens[0]) if tens else None
         roof_mel = roof_of("mel") if "mel" in rep else None
 
+    # ---- the decode stage as a whole against its HBM floor (weights of every layer + LM head once per step, the keys and values
+    #      of every sequence once per layer and step): the number that governs the headline, next to the dominant kernel's ----
+    roof_dec = None
+    try:
+        cf = q3asr.preset(MODEL)
+        nq, nkv = cf.dec_heads * cf.dec_head_dim, cf.dec_kv_heads * cf.dec_head_dim
+        w_bytes = 2.0 * (cf.dec_layers * (cf.dec_hidden * (nq + 2 * nkv) + nq * cf.dec_hidden + 3 * cf.dec_hidden * cf.dec_inter)
+                         + cf.dec_vocab * cf.dec_hidden)
+        prompt = q3asr.encoder_tokens(CLIP_SECONDS * 100) + 16  # audio tokens + the chat template around them
+        kv_bytes = CLIPS_PER_GPU * (prompt + MAX_TOKENS / 2.0) * cf.dec_layers * 2 * nkv * 2.0
+        dec_ms = float(stage[3]) / args.steps / (MAX_TOKENS - 1)
+        ach = (w_bytes + kv_bytes) / dec_ms / 1e6
+        roof_dec = {"bound": "hbm", "what": "decode stage (all kernels of a decode step)", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "ms_per_decode_step": dec_ms, "floor_ms_per_decode_step": (w_bytes + kv_bytes) / pk["hbm"] / 1e6,
+                    "algorithmic_per_step": w_bytes + kv_bytes,
+                    "how": "bytes every decode step must move (bf16 weights of all decoder layers and the tied LM head, the cached keys and "
+                           "values at the mean context of the 128 steps) / the device-timed decode stage per step, timed region of `value`"}
+    except Exception as e:
+        roof_dec = {"error": repr(e)}
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -509,7 +529,8 @@ def main():
             "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(("mel", "encoder", "prefill", "decode"), stage)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_pipelined": e2e_pipe,
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_mel": roof_mel, "kernel_families": families,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_mel": roof_mel, "roofline_decode_stage": roof_dec,
+            "kernel_families": families,
             "cpu_baseline": cpu, "parity": parity,
         }
         if extras:
