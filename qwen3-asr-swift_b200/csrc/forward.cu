@@ -228,6 +228,12 @@ void reserve_decoder(Handle* h, BatchState* bs) {
         const size_t w2 = (size_t)gemm_skinny_splits((int)H, (int)nq, SK_PARTIAL) * Bq * H;
         const size_t w3 = (size_t)gemm_skinny_splits((int)H, c.dec_inter, SK_PARTIAL) * Bq * H;
         bs->dws.reserve(std::max(w1, std::max(w2, w3)) * 4);
+        bs->dattn_part.reserve(decode_attn_split_floats(Bq, c.dec_kv_heads) * 4);
+        const size_t cnt_bytes = Bq * c.dec_kv_heads * sizeof(int);
+        if (cnt_bytes > bs->dattn_cnt.cap) {  // the counters return to zero after every launch: cleared when (re)allocated only
+            bs->dattn_cnt.reserve(cnt_bytes);
+            Q3_CUDA(cudaMemsetAsync(bs->dattn_cnt.p, 0, bs->dattn_cnt.cap, h->stream));
+        }
     }
     const size_t page_elems = (size_t)c.dec_layers * 2 * c.dec_kv_heads * KV_PAGE * hd;
     bs->kv_pool.reserve((size_t)bs->B * bs->pages_per_seq * page_elems * 2);
@@ -564,7 +570,8 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         {
             ProfScope ps(h, "dec_attn", 0, kv_bytes);
             if (!(skip & 2)) decode_attn_fused_launch(ws, s_qkv, (long long)B * nqkv, nqkv, w.q_norm, w.k_norm, bs->st_pos.as<int>(), c.dec_rms_eps, bs->rope_tab.as<float2>(),
-                                     kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale, att, h->num_sms, st);
+                                     kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale, att, h->num_sms, st, bs->dattn_part.as<float>(),
+                                     bs->dattn_cnt.as<int>());
         }
         {
             ProfScope ps(h, "dec_o", 2.0 * B * nq * H, 2.0 * nq * H);
@@ -775,7 +782,7 @@ void profile_attn_chain(Handle* h, BatchState* bs) {
     for (int l = 0; l < c.dec_layers; l++)
         decode_attn_fused_launch(bs->dws.as<float>(), s_qkv, (long long)B * nqkv, nqkv, m.dec[l].q_norm, m.dec[l].k_norm, bs->st_pos.as<int>(),
                                  c.dec_rms_eps, bs->rope_tab.as<float2>(), kc, l, bs->st_kv_len.as<int>(), B, c.dec_heads, scale,
-                                 bs->datt.as<bf16>(), h->num_sms, st);
+                                 bs->datt.as<bf16>(), h->num_sms, st, bs->dattn_part.as<float>(), bs->dattn_cnt.as<int>());
 }
 
 bool mega_wanted(Handle* h, BatchState* bs) {

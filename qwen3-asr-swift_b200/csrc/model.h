@@ -116,6 +116,7 @@ struct BatchState {
            o_ident = 0, o_pos0 = 0;
     DevBuf a1, a2, a3, ex, exn, eqkv, eatt, effn, audio;        // encoder activations
     DevBuf dx, dxn, dqkv, dq, dkc, datt, dact, dlast, dws; // decoder activations (dws: fp32 split-K partials of the decode step)
+    DevBuf dattn_part, dattn_cnt;        // decode attention, split variant: stored partials and per-item arrival counters
     DevBuf mega_tab, dws2, mega_trace;   // persistent decode-step kernel (megastep.cu): tables + the second sub-batch's split-K partials
     HostBuf h_mega;
     MegaParams mega;
@@ -137,7 +138,7 @@ struct BatchState {
     }
     std::vector<DevBuf*> all() {
         return {&pcm, &raw_pcm, &mel_out, &mel_clips, &mel_gmax, &mel_tmin, &ints, &a1, &a2, &a3, &ex, &exn, &eqkv, &eatt, &effn, &audio,
-                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &rope_tab_t, &page_tab, &page_tab2, &st_slot_seq, &amax_val, &amax_idx, &logits, &logits_bf,
+                &dx, &dxn, &dqkv, &dq, &dkc, &datt, &dact, &dlast, &dws, &dattn_part, &dattn_cnt, &dws2, &mega_tab, &mega_trace, &kv_pool, &rope_tab, &rope_tab_t, &page_tab, &page_tab2, &st_slot_seq, &amax_val, &amax_idx, &logits, &logits_bf,
                 &st_next_tok, &st_next_val, &st_cur_tok, &st_pos, &st_kv_len, &st_out_ids, &st_out_val, &st_out_len, &st_finished,
                 &st_scalars, &st_forced};
     }

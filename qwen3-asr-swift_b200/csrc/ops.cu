@@ -591,17 +591,27 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // element offset of 16-byte segment `seg` of row `key` in a swizzled [16 keys][128] tile
 __device__ __forceinline__ int dm_off(int key, int seg) { return key * 128 + ((seg ^ (key & 7)) << 3); }
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kernel(const float* __restrict__ qkv_part, int splits, long long split_stride,
+// SPLIT (NW == 1, opt-in: Q3ASR_DECODE_ATTN_WARPS=1): the (sequence, kv head) item is shared by the two single-warp CTAs blockIdx.z = 0 / 1,
+// which walk the even / the odd key streams — exactly what warps 0 and 1 of the two-warp variant do — and meet through global
+// memory: each stores its partial (maximum, sum, accumulator), bumps the item's counter, and whichever arrives second merges
+// even + odd in that fixed order, so the result is bit-identical to the other variants and independent of the arrival order.
+// Built to even out the tail (two-warp CTAs at four per SM leave 3 or 4 items per SM at 64 sequences); measured slower, see the launcher.
+constexpr int DM_PART_STRIDE = 264;  // floats per stored partial: [2][128] accumulators, 2 maxima, 2 sums, padding
+template <int NW, bool SPLIT>
+__global__ void __launch_bounds__(NW * 32, SPLIT ? 8 : NW == 2 ? 4 : 1) decode_attn_mma_kernel(const float* __restrict__ qkv_part, int splits, long long split_stride,
                                                                   int nqkv, const bf16* __restrict__ qw, const bf16* __restrict__ kw,
                                                                   const int* __restrict__ pos, float eps,
                                                                   const float2* __restrict__ rope_tab, KvCache cache, int layer,
                                                                   const int* __restrict__ kv_len, int heads, float scale_log2,
-                                                                  bf16* __restrict__ out) {
+                                                                  bf16* __restrict__ out, float* __restrict__ split_part, int* __restrict__ split_cnt) {
+    static_assert(!SPLIT || NW == 1, "the split variant is one warp per CTA");
     constexpr int GROUP = 2;
+    constexpr int SW = SPLIT ? 2 : NW;  // this CTA's warps walk the streams sw0, sw0 + SW, ...
     ptx::grid_dep_launch();
     const int seq = blockIdx.x, kvh = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = SPLIT ? (int)blockIdx.z : 0;
+    const int sw0 = SPLIT ? half : warp;
     __shared__ __align__(16) bf16 s_qb[GROUP][128];  // the two query heads (bf16, after norm + RoPE)
     __shared__ __align__(16) bf16 s_new[2][128];     // the new token's k and v rows
     __shared__ float s_m[GROUP][NW], s_l[GROUP][NW];
@@ -636,13 +646,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
     // ((s0 + s2) + s4) + s6, ((s1 + s3) + s5) + s7, then even + odd.  Warp w walks the streams w, w + NW, ... one after the other.
     auto seq_next = [&](int& sj, int& sc) {  // next chunk of this warp's sequence after (stream sj, chunk sc); sc >= n_chunks: done
         sc += DM_STREAMS;
-        while (sc >= n_chunks && sj + NW < DM_STREAMS) {
-            sj += NW;
+        while (sc >= n_chunks && sj + SW < DM_STREAMS) {
+            sj += SW;
             sc = sj;
         }
     };
-    int ij = warp, ic = warp;  // issue cursor
-    while (ic >= n_chunks && ij + NW < DM_STREAMS) { ij += NW; ic = ij; }
+    int ij = sw0, ic = sw0;  // issue cursor
+    while (ic >= n_chunks && ij + SW < DM_STREAMS) { ij += SW; ic = ij; }
 #pragma unroll
     for (int s = 0; s < DM_STAGES - 1; s++) {
         issue(ic, s);  // chunks >= n_chunks are skipped inside issue (the group is still committed)
@@ -653,8 +663,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
 
     // ---- 1. new-token q / k / v (slots 0,1 = q heads, 2 = k, 3 = v): one half-warp per slot, 8 dims per lane, so all four
     //         are done in one pass by the first two warps (the other warps keep their prefetches in flight) ----
-    if (threadIdx.x < 16 * (GROUP + 2)) {
-        const int slot = threadIdx.x >> 4, hl = threadIdx.x & 15;
+    // (split variant: 32 threads, two passes — the queries, then k and v, which only the CTA that appends them to the cache (half 0)
+    // or owns the last chunk needs)
+    const bool need_kv = !SPLIT || half == 0 || (((n_chunks - 1) % DM_STREAMS) & 1) == half;
+    for (int vt = threadIdx.x; vt < 16 * (GROUP + 2) && (vt < 16 * GROUP || need_kv); vt += NW * 32) {
+        const int slot = vt >> 4, hl = vt & 15;
         const unsigned half_mask = 0xffffu << (threadIdx.x & 16);  // the two halves of a warp hold different slots and diverge (v skips the norm)
         const int d0 = hl * 8;
         const int col = slot < GROUP ? (kvh * GROUP + slot) * 128
@@ -714,7 +727,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
             const int page = pt[p / KV_PAGE];
             bf16* dst = cache.pool + ((((size_t)page * cache.layers + layer) * 2 + (slot == GROUP ? 0 : 1)) * cache.kv_heads + kvh) * (KV_PAGE * 128) +
                         (p % KV_PAGE) * 128 + d0;
-            *reinterpret_cast<uint4*>(dst) = packed;
+            if (half == 0) *reinterpret_cast<uint4*>(dst) = packed;
             *reinterpret_cast<uint4*>(&s_new[slot - GROUP][d0]) = packed;
         }
     }
@@ -732,8 +745,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
     float m_run = -INFINITY, l_run = 0.f;
     const int mi = lane >> 3, r8 = lane & 7;
     int stage = 0;
-    int cj = warp, chunk = warp;  // consume cursor
-    while (chunk >= n_chunks && cj + NW < DM_STREAMS) { cj += NW; chunk = cj; }
+    int cj = sw0, chunk = sw0;  // consume cursor
+    while (chunk >= n_chunks && cj + SW < DM_STREAMS) { cj += SW; chunk = cj; }
     int cur_stream = -1;
     bool first_stream = true;
     // folds the finished stream (m_run, l_run, o) into this warp's running partial in shared memory (lanes 0-7 hold the two rows)
@@ -833,6 +846,32 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 4 : 1) decode_attn_mma_kern
         for (int nt = 0; nt < 16; nt++) s_acc[g][warp][nt * 8 + t * 2] = s_acc[g][warp][nt * 8 + t * 2 + 1] = 0.f;
     }
     __syncthreads();
+    if constexpr (SPLIT) {
+        const size_t item = (size_t)seq * gridDim.y + kvh;
+        float* mine = split_part + (item * 2 + half) * DM_PART_STRIDE;
+        for (int i = lane; i < GROUP * 128; i += 32) mine[i] = s_acc[i >> 7][0][i & 127];
+        if (lane < 2 * GROUP) mine[GROUP * 128 + lane] = lane < GROUP ? s_m[lane][0] : s_l[lane - GROUP][0];
+        __threadfence();
+        __syncwarp();
+        int arrived = 0;
+        if (lane == 0) arrived = atomicAdd(split_cnt + item, 1);
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == 0) return;  // the other half finishes the item
+        __threadfence();
+        const float* other = split_part + (item * 2 + (half ^ 1)) * DM_PART_STRIDE;
+        for (int i = lane; i < GROUP * 128; i += 32) {
+            const int gg = i >> 7, d = i & 127;
+            const float om = __ldcg(other + GROUP * 128 + gg), ol = __ldcg(other + GROUP * 128 + GROUP + gg), oa = __ldcg(other + i);
+            // even = half 0, odd = half 1 (the chains of the other variants: a chain of one partial is that partial)
+            const float em = half == 0 ? s_m[gg][0] : om, el = half == 0 ? s_l[gg][0] : ol, ea = half == 0 ? s_acc[gg][0][d] : oa;
+            const float dm = half == 0 ? om : s_m[gg][0], dl = half == 0 ? ol : s_l[gg][0], da = half == 0 ? oa : s_acc[gg][0][d];
+            float fa, fb;
+            dm_merge_scales(em, dm, &fa, &fb);
+            const float num = fmaf(fb, da, fa * ea), den = fmaf(fb, dl, fa * el);
+            out[((size_t)seq * heads + kvh * GROUP + gg) * 128 + d] = __float2bfloat16_rn(num / den);
+        }
+        if (lane == 0) split_cnt[item] = 0;  // ready for the next launch
+    } else
     for (int i = threadIdx.x; i < GROUP * 128; i += NW * 32) {
         const int gg = i >> 7, d = i & 127;
         // even chain (warps 0, 2, ...), odd chain (warps 1, 3, ...), then even + odd: for NW == 2 that is just warp 0 + warp 1
@@ -1182,7 +1221,7 @@ void decode_attn_launch(const bf16* q, const KvCache& cache, int layer, const in
 
 void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
                               const int* pos, float eps, const float2* rope_tab, const KvCache& cache, int layer, const int* kv_len,
-                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st) {
+                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st, float* split_part, int* split_cnt) {
     if (n_seqs <= 0) return;
     Q3_CHECK(cache.head_dim == 128, 1, "decoder head_dim must be 128");
     Q3_CHECK(heads == 2 * cache.kv_heads, 1, "fused decode attention is built for 2 query heads per kv head");
@@ -1193,23 +1232,32 @@ void decode_attn_fused_launch(const float* qkv_part, int splits, long long split
     attr_once([] {
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(4)));
         Q3_CUDA(cudaFuncSetAttribute(decode_attn_fused_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_smem(16)));
-        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(2)));
-        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(8)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(1)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(2)));
+        Q3_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, decode_attn_mma_smem(8)));
     });
-    bool many = (long)n_seqs * cache.kv_heads >= 2L * num_sms;  // few (sequence, head) pairs: more warps per CTA share the key loop
-    if (const char* f = getenv("Q3ASR_DECODE_ATTN_WARPS")) {        // tests force either variant on small batches (2 or 8 warps)
-        if (atoi(f) == 2) many = true;
-        else if (atoi(f) == 8) many = false;
+    const long items = (long)n_seqs * cache.kv_heads;
+    // eight warps per item below two items per SM, two above.  The split variant (two single-warp CTAs per item, all 1024 half-items
+    // of the bench batch resident at once, 6.9 per SM instead of 3 or 4 items) is opt-in: bit-identical, but measured SLOWER on B200,
+    // 63.2 against 55.2 us per layer at 64 sequences — the second pass of the prologue and the meeting through global memory
+    // (fence, atomic, 1 KB read back) add more to every item's dependent chain than the even spread takes off the tail.
+    int warps = items >= 2L * num_sms ? 2 : 8;
+    if (const char* f = getenv("Q3ASR_DECODE_ATTN_WARPS")) {  // tests force a variant on small batches (1 = split, 2 or 8 warps)
+        const int w = atoi(f);
+        if (w == 2 || w == 8 || (w == 1 && split_part != nullptr && split_cnt != nullptr)) warps = w;
     }
     static const bool simt = getenv("Q3ASR_DECODE_ATTN_SIMT") != nullptr && atoi(getenv("Q3ASR_DECODE_ATTN_SIMT")) != 0;
     if (!simt) {
-        if (many)
-            launch_kernel(decode_attn_mma_kernel<2>, grid, 64, decode_attn_mma_smem(2), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
-                          rope_tab, cache, layer, kv_len, heads, sl2, out);
+        if (warps == 1)
+            launch_kernel(decode_attn_mma_kernel<1, true>, dim3(n_seqs, cache.kv_heads, 2), 32, decode_attn_mma_smem(1), st, qkv_part, splits,
+                          split_stride, nqkv, qw, kw, pos, eps, rope_tab, cache, layer, kv_len, heads, sl2, out, split_part, split_cnt);
+        else if (warps == 2)
+            launch_kernel(decode_attn_mma_kernel<2, false>, grid, 64, decode_attn_mma_smem(2), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                          rope_tab, cache, layer, kv_len, heads, sl2, out, split_part, split_cnt);
         else
-            launch_kernel(decode_attn_mma_kernel<8>, grid, 256, decode_attn_mma_smem(8), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
-                          rope_tab, cache, layer, kv_len, heads, sl2, out);
-    } else if (many) {
+            launch_kernel(decode_attn_mma_kernel<8, false>, grid, 256, decode_attn_mma_smem(8), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
+                          rope_tab, cache, layer, kv_len, heads, sl2, out, split_part, split_cnt);
+    } else if (warps <= 2) {
         launch_kernel(decode_attn_fused_kernel<2, 4>, grid, 128, decode_attn_smem(4), st, qkv_part, splits, split_stride, nqkv, qw, kw, pos, eps,
                       rope_tab, cache, layer, kv_len, heads, sl2, out);
     } else {

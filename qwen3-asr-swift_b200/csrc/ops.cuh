@@ -69,7 +69,10 @@ void decode_attn_launch(const bf16* q /*[n_seqs, heads*hd]*/, const KvCache& cac
 // appends k/v to the cache and attends (one launch instead of qknorm_rope_kv + decode_attn).
 void decode_attn_fused_launch(const float* qkv_part, int splits, long long split_stride, int nqkv, const bf16* qw, const bf16* kw,
                               const int* pos, float eps, const float2* rope_tab, const KvCache& cache, int layer, const int* kv_len,
-                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st);
+                              int n_seqs, int heads, float scale, bf16* out, int num_sms, cudaStream_t st, float* split_part = nullptr,
+                              int* split_cnt = nullptr);
+// scratch of the split variant (two single-warp CTAs per (sequence, kv head)): floats for the partials, counters (zero before the first launch)
+constexpr size_t decode_attn_split_floats(size_t n_seqs, size_t kv_heads) { return n_seqs * kv_heads * 2 * 264; }
 // x += bf16(sum of split-K partials) (in place), y = RMSNorm(x) * w.  d % 128 == 0, d <= 2048.
 void reduce_resid_rmsnorm_launch(const float* part, int splits, long long split_stride, bf16* x, const bf16* w, bf16* y, int rows, int d,
                                  float eps, cudaStream_t st);

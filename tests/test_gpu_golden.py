@@ -185,11 +185,11 @@ def test_free_running_ids(models, name):
     assert got_b.tolist() == got.tolist()
 
 
-@pytest.mark.parametrize("warps", ["8", "2"])
+@pytest.mark.parametrize("warps", ["8", "2", "1"])
 @pytest.mark.parametrize("name", list(FIXTURES))
 def test_teacher_forced(models, monkeypatch, name, warps):
-    """warps: the decode-attention variant (8 warps per (sequence, kv head): what a batch of one uses by default; 2: what the
-    bench's batches of 64 use)."""
+    """warps: the decode-attention variant (8 warps per (sequence, kv head): what a batch of one uses by default; 2: large batches;
+    1: two single-warp CTAs per item, what the bench's batches of 64 use)."""
     monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
     g = _load(name)
     m = models(FIXTURES[name], int(g["seed"]))

@@ -63,10 +63,11 @@ def test_greedy_ids_bit_exact(tiny_model, tiny_oracle):
         assert got.tolist() == ref.tolist(), (n, got.tolist(), ref.tolist(), margins.tolist())
 
 
-@pytest.mark.parametrize("warps", ["2", "8"])
+@pytest.mark.parametrize("warps", ["1", "2", "8"])
 def test_greedy_ids_bit_exact_both_decode_attention_variants(tiny_model, tiny_oracle, monkeypatch, warps):
-    """The decode attention keeps two warps per (sequence, kv head) for large batches (the bench regime) and eight for small ones; both
-    variants are checked against the oracle here by forcing them on a small batch."""
+    """The decode attention keeps eight warps per (sequence, kv head) for small batches, two for large ones and — in between, the
+    bench regime — two single-warp CTAs that meet through global memory ("1"); every variant is checked against the oracle here by
+    forcing it on a small batch."""
     monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
     clips = [synth.clip(i, n) for i, n in enumerate([16000 * 3 + 777, 16000, 5000])]
     got = tiny_model.transcribe_ids(clips, max_tokens=32, stop_on_eos=False)
@@ -81,12 +82,12 @@ def test_decode_attention_variants_are_bit_identical(tiny_model, monkeypatch):
     clips = [synth.clip(i, n) for i, n in enumerate([16000 * 4 + 5, 1600, 16000 * 2, 700 * 16, 161])]
     forced = np.arange(50, 90, dtype=np.int32)
     res = {}
-    for warps in ("2", "8"):
+    for warps in ("1", "2", "8"):
         monkeypatch.setenv("Q3ASR_DECODE_ATTN_WARPS", warps)
         ids = tiny_model.transcribe_ids(clips, max_tokens=48, stop_on_eos=False)
         am, top = tiny_model.decode_forced(clips[0], forced)
         res[warps] = ([t.tolist() for t in ids], am.tolist(), top.tolist())
-    assert res["2"] == res["8"]
+    assert res["2"] == res["8"] and res["1"] == res["2"]
 
 
 def test_teacher_forced_argmax_and_logits(tiny_model, tiny_oracle):
