@@ -38,6 +38,7 @@
 #include <vector>
 
 #include "mel.cuh"
+#include "ptx.cuh"
 
 namespace q3 {
 
@@ -197,22 +198,23 @@ __device__ __forceinline__ int find_clip(const MelClip* clips, int batch, int ti
     return lo;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 
-// Stages one tile's padded samples (pad index p0 + i, i < SX_FLOATS) into dst: interior tiles with 16-byte cp.async copies, tiles
-// that touch a reflected edge with plain loads.  (Measured: prefetching the NEXT tile into a second buffer — one 512-thread CTA per
-// SM, 223 KB — is slower, 221 vs 203 us: the kernel is bound by shared-memory wavefronts, not by the staging latency, which the
-// second CTA of the SM already covers.)
-__device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const float* pcm, int f0, int tid) {
+// Stages one tile's padded samples (pad index p0 + i, i < SX_FLOATS) into dst.  Interior tiles: ONE bulk copy (cp.async.bulk, the TMA
+// unit writes shared memory through the async proxy: no LSU wavefronts and one instruction instead of 704 LDGSTS per tile — the
+// staging writes were 9 % of the kernel's shared-memory wavefronts, the unit that bounds it), completion on the group's mbarrier.
+// Tiles that touch a reflected edge: plain loads and stores by every thread, and a plain arrival so that the barrier's phase
+// advances once per staged tile either way (their visibility comes from the group barrier that follows the wait).
+__device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const float* pcm, int f0, int tid, uint64_t* bar) {
     const float* x = pcm + c.in_off;
     const int n = c.n;
     const int p0 = f0 * MEL_HOP;
     if (p0 >= MEL_NFFT / 2 && p0 + SX_FLOATS <= MEL_NFFT / 2 + n) {
-        const float4* src = reinterpret_cast<const float4*>(x + (p0 - MEL_NFFT / 2));
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = tid; i < SX_FLOATS / 4; i += MEL_THREADS) cp_async16(d4 + i, src + i);
+        if (tid == 0) {
+            ptx::mbar_arrive_expect_tx(bar, SX_FLOATS * 4);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(dst)),
+                         "l"(x + (p0 - MEL_NFFT / 2)), "n"(SX_FLOATS * 4), "r"(ptx::smem_u32(bar))
+                         : "memory");
+        }
     } else {
         for (int i = tid; i < SX_FLOATS; i += MEL_THREADS) {
             const int pp = p0 + i;
@@ -230,9 +232,10 @@ __device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const f
             }
             dst[i] = v;
         }
+        if (tid == 0) ptx::mbar_arrive(bar);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
+static_assert((SX_FLOATS * 4) % 16 == 0 && (MEL_HOP * 4) % 16 == 0 && (MEL_NFFT / 2 * 4) % 16 == 0, "bulk copies need 16-byte aligned tiles");
 
 __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelParams p) {
     extern __shared__ float4 smem4[];
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
     float* s_red = reinterpret_cast<float*>(s_scr + PAIRS * SCR_F4);      // [32]
     int* s_next = reinterpret_cast<int*>(s_red + 32);  // clip index of the tiles this group takes next (found two tiles ahead) ...
     MelClip* s_clip = reinterpret_cast<MelClip*>(s_red + 36);  // ... and the clips themselves
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 56);  // completion of the sample tile in flight
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(MEL_THREADS) : "memory"); };
 
     const int tid = threadIdx.x % MEL_THREADS;  // within the group
@@ -282,6 +286,8 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
         }
     };
     if (tid == 0) {  // clips of the first two tiles; later ones are searched two tiles ahead
+        ptx::mbar_init(s_bar, 1);
+        ptx::fence_barrier_init();
         s_next[0] = find_clip(p.clips, p.batch, min(tile_first, p.total_tiles - 1));
         s_next[1] = find_clip(p.clips, p.batch, min(tile_first + tile_step, p.total_tiles - 1));
         s_clip[0] = p.clips[s_next[0]];
@@ -290,9 +296,10 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
     __syncthreads();
     if (tile_first < p.total_tiles) {
         const MelClip c0 = s_clip[0];
-        stage_tile(s_x, c0, p.pcm, (tile_first - c0.tile0) * MEL_TILE, tid);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        stage_tile(s_x, c0, p.pcm, (tile_first - c0.tile0) * MEL_TILE, tid, s_bar);
+        ptx::mbar_wait(s_bar, 0);
     }
+    uint32_t stage_phase = 1;  // parity of the next staged tile's completion
     __syncthreads();
     // Clip of the tile two steps ahead, found by the last warp without anybody waiting for it: the candidates' first-tile numbers
     // are loaded (one per lane and 32 clips) while the transforms run, counted at the end of the tile, the clip's descriptor is
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
             const int ntile = tile + tile_step;
             if (ntile < p.total_tiles) {
                 const MelClip cn = s_clip[(it + 1) & 1];
-                stage_tile(s_x, cn, p.pcm, (ntile - cn.tile0) * MEL_TILE, tid);
+                stage_tile(s_x, cn, p.pcm, (ntile - cn.tile0) * MEL_TILE, tid, s_bar);
             }
         }
         const int tile2 = tile + 2 * tile_step;  // the tile whose clip is looked up during this one
@@ -453,7 +460,10 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
             pend_cj = cj;
             pend_word = lane < (int)(sizeof(MelClip) / 4) ? __ldg(reinterpret_cast<const int*>(&p.clips[cj]) + lane) : 0;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the next tile's samples has landed (long ago)
+        if (tile + tile_step < p.total_tiles) {  // the next tile's samples have landed (long ago)
+            ptx::mbar_wait(s_bar, stage_phase);
+            stage_phase ^= 1;
+        }
         group_sync();  // the tile's features are parked, its reductions written, the next tile's samples visible to every lane
         if (tid == 0) {
             float gm = s_red[0], tm = s_red[16];
