@@ -154,7 +154,7 @@ int q3asr_prompt_ids(const q3asr_config* cfg, int n_audio_tokens, const q3asr_pr
 /* Batched greedy transcription.  ids_out: [batch, max_tokens] int32; lens_out: [batch].
  * stop_on_eos != 0 reproduces the reference loop (EOS appended, then stop, Qwen3ASR.swift:378-379);
  * stop_on_eos == 0 decodes exactly max_tokens ids (fixed-length parity runs).  prompts may be NULL.
- * Any batch size: more than 128 utterances are served as equal sub-batches of at most 128 one after the other (the decode
+ * Any batch size: more than 256 utterances are served as equal sub-batches of at most 256 one after the other (the decode
  * step's row capacity), so an utterance's ids do not depend on the size of the request; q3asr_stage_ms sums over them. */
 int q3asr_transcribe_ids(q3asr_handle* h, const float* const* pcm, const size_t* n_samples, int batch,
                          const q3asr_prompt* prompts, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out);

@@ -312,10 +312,11 @@ struct UploadGuard {
 };
 }  // namespace
 namespace {
-// A request larger than the decode step's row capacity is served as equal sub-batches one after the other: above SKINNY_MAX_ROWS the
-// decode falls back to the general GEMMs (measured: 160 clips in one batch 6 500 audio-s/s against 9 400 for 128; ids within bf16
-// noise of, but not bit-identical to, the weight-streaming path), so an utterance's ids would depend on the size of the request it
-// arrived in.  Utterances are independent; outputs land at their own offsets; stage times are summed over the sub-batches.
+// A request larger than the decode step's row capacity (SKINNY_MAX_ROWS = 256 token rows) is served as equal sub-batches one after
+// the other: above it the decode falls back to the general GEMMs (measured at the former capacity of 128: 160 clips in one batch
+// 6 500 audio-s/s against 9 400 for 128; ids within bf16 noise of, but not bit-identical to, the weight-streaming path), so an
+// utterance's ids would depend on the size of the request it arrived in.  Utterances are independent; outputs land at their own
+// offsets; stage times are summed over the sub-batches.
 void transcribe_chunked(Handle& x, const float* const* pcm, const size_t* n, const int* rates, int batch, const q3asr_prompt* prompts,
                         const q3asr_sampling* sampling, bool set_sampling, int max_tokens, int stop_on_eos, int32_t* ids_out, int* lens_out) {
     Q3_CHECK(ids_out != nullptr && lens_out != nullptr, Q3ASR_ERR_INVALID, "transcribe: null output");
@@ -486,8 +487,8 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
             Q3_CUDA(cudaMalloc(&dtok, sizeof(int32_t) * (size_t)M));
             cudaError_t se = cudaSuccess;
             try {
-                Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
-                Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+                Q3_H2D_SYNC(dA, A, 2 * (size_t)M * K);
+                Q3_H2D_SYNC(dW, W, 2 * (size_t)N * K);
                 lmhead_argmax(dA, K, M, K, dW, N, dv, di, h.stream);
                 argmax_reduce(dv, di, M, tiles, dtok, nullptr, h.stream);
                 se = cudaStreamSynchronize(h.stream);
@@ -511,8 +512,8 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
             Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
             Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
             Q3_CUDA(cudaMalloc(&dO, dev_bytes));
-            Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
-            Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+            Q3_H2D_SYNC(dA, A, 2 * (size_t)M * K);
+            Q3_H2D_SYNC(dW, W, 2 * (size_t)N * K);
             std::vector<float> part;
             cudaError_t se = cudaSuccess;
             try {
@@ -554,15 +555,15 @@ int q3asr_debug_gemm(q3asr_handle* hh, const uint16_t* A, const uint16_t* W, con
         Q3_CUDA(cudaMalloc(&dA, 2 * (size_t)M * K));
         Q3_CUDA(cudaMalloc(&dW, 2 * (size_t)N * K));
         Q3_CUDA(cudaMalloc(&dO, std::max<size_t>(out_bytes, 2 * (size_t)M * N)));
-        Q3_CUDA(cudaMemcpy(dA, A, 2 * (size_t)M * K, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dW, W, 2 * (size_t)N * K, cudaMemcpyHostToDevice));
+        Q3_H2D_SYNC(dA, A, 2 * (size_t)M * K);
+        Q3_H2D_SYNC(dW, W, 2 * (size_t)N * K);
         if (bias) {
             Q3_CUDA(cudaMalloc(&dB, 2 * (size_t)N));
-            Q3_CUDA(cudaMemcpy(dB, bias, 2 * (size_t)N, cudaMemcpyHostToDevice));
+            Q3_H2D_SYNC(dB, bias, 2 * (size_t)N);
         }
         if (resid) {
             Q3_CUDA(cudaMalloc(&dR, 2 * (size_t)M * N));
-            Q3_CUDA(cudaMemcpy(dR, resid, 2 * (size_t)M * N, cudaMemcpyHostToDevice));
+            Q3_H2D_SYNC(dR, resid, 2 * (size_t)M * N);
         }
         GemmEpiArgs e;
         e.epi = epi;
@@ -602,11 +603,11 @@ int q3asr_debug_conv(q3asr_handle* hh, const uint16_t* in, const uint16_t* w, co
         Q3_CUDA(cudaMalloc(&dI, 2 * in_n));
         Q3_CUDA(cudaMalloc(&dW, 2 * w_n));
         Q3_CUDA(cudaMalloc(&dO, 2 * out_n));
-        Q3_CUDA(cudaMemcpy(dI, in, 2 * in_n, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dW, w, 2 * w_n, cudaMemcpyHostToDevice));
+        Q3_H2D_SYNC(dI, in, 2 * in_n);
+        Q3_H2D_SYNC(dW, w, 2 * w_n);
         if (bias) {
             Q3_CUDA(cudaMalloc(&dB, 2 * (size_t)O));
-            Q3_CUDA(cudaMemcpy(dB, bias, 2 * (size_t)O, cudaMemcpyHostToDevice));
+            Q3_H2D_SYNC(dB, bias, 2 * (size_t)O);
         }
         GemmA a;
         a.ptr = dI; a.C = C; a.W = W; a.H = H; a.B = B;
@@ -641,11 +642,11 @@ int q3asr_debug_attention(q3asr_handle* hh, const uint16_t* q, const uint16_t* k
         Q3_CUDA(cudaMalloc(&dv, 2 * nk));
         Q3_CUDA(cudaMalloc(&dout, 2 * nq));
         Q3_CUDA(cudaMalloc(&dseg, sizeof(int) * 2 * n_segs));
-        Q3_CUDA(cudaMemcpy(dq, q, 2 * nq, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dk, k, 2 * nk, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dv, v, 2 * nk, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dseg, seg_row0, sizeof(int) * n_segs, cudaMemcpyHostToDevice));
-        Q3_CUDA(cudaMemcpy(dseg + n_segs, seg_len, sizeof(int) * n_segs, cudaMemcpyHostToDevice));
+        Q3_H2D_SYNC(dq, q, 2 * nq);
+        Q3_H2D_SYNC(dk, k, 2 * nk);
+        Q3_H2D_SYNC(dv, v, 2 * nk);
+        Q3_H2D_SYNC(dseg, seg_row0, sizeof(int) * n_segs);
+        Q3_H2D_SYNC(dseg + n_segs, seg_len, sizeof(int) * n_segs);
         Q3_CUDA(cudaMemset(dout, 0, 2 * nq));
         int max_len = 0;
         for (int i = 0; i < n_segs; i++) max_len = std::max(max_len, seg_len[i]);

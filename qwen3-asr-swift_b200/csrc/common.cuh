@@ -26,6 +26,17 @@ struct Error : public std::runtime_error {
                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");      \
     } while (0)
 
+// Synchronous host -> device copy that is really complete on return.  cudaMemcpy from PAGEABLE memory returns once the source has been
+// staged; the DMA to the device may still be in flight in the legacy default stream, and the handle's streams are non-blocking, so a
+// kernel launched on them right afterwards is not ordered behind it (seen as stale operands under stress in the debug hooks).
+// Synchronising the legacy stream closes the gap.  (The hot path does not come through here: it copies from pinned staging buffers
+// on its own streams.)
+#define Q3_H2D_SYNC(dst, src, bytes)                                                \
+    do {                                                                            \
+        Q3_CUDA(cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice));         \
+        Q3_CUDA(cudaStreamSynchronize(cudaStreamLegacy));                           \
+    } while (0)
+
 #define Q3_CHECK(cond, code, msg)                        \
     do {                                                 \
         if (!(cond)) throw ::q3::Error((code), (msg));   \

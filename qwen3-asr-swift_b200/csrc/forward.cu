@@ -1259,7 +1259,7 @@ void decode_forced(Handle* h, const float* pcm, size_t n, const q3asr_prompt* pr
     std::vector<int32_t> f(forced, forced + n_forced);
     f.push_back(0);
     bs->st_forced.reserve(f.size() * 4);
-    Q3_CUDA(cudaMemcpy(bs->st_forced.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    Q3_H2D_SYNC(bs->st_forced.p, f.data(), f.size() * 4);
     run_prefill(h, bs, 0, true);
     run_decode(h, bs, steps, 0, true);
     std::vector<int32_t> ids((size_t)bs->max_tokens);

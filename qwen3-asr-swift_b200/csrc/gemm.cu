@@ -416,9 +416,9 @@ int gemm_skinny_splits(int N, int K, int epi) {
 }
 
 void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, cudaStream_t st) {
-    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "gemm_skinny: 1..128 token rows per launch");
+    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "gemm_skinny: 1..256 token rows per launch");
     Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0, 1, "gemm_skinny: K and ldx must be multiples of 8");
-    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
+    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : Mtok <= 128 ? 128 : 256;
     SkinnyDev p;
     memset(&p, 0, sizeof(p));
     p.N = N;
@@ -453,7 +453,8 @@ void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, 
         case 16: launch_skinny_nb<16>(epi, deep, tw, tx, p, grid, st); break;
         case 32: launch_skinny_nb<32>(epi, deep, tw, tx, p, grid, st); break;
         case 64: launch_skinny_nb<64>(epi, deep, tw, tx, p, grid, st); break;
-        default: launch_skinny_nb<128>(epi, deep, tw, tx, p, grid, st); break;
+        case 128: launch_skinny_nb<128>(epi, deep, tw, tx, p, grid, st); break;
+        default: launch_skinny_nb<256>(epi, deep, tw, tx, p, grid, st); break;
     }
     Q3_CUDA(cudaGetLastError());
     g_launches++;
@@ -473,9 +474,9 @@ void launch_lmhead(const CUtensorMap& tw, const CUtensorMap& tx, const LmHeadDev
 int lmhead_tiles(int N) { return cdiv(N, SK_BM); }
 
 void lmhead_argmax(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, float* amax_val, int* amax_idx, cudaStream_t st) {
-    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "lmhead_argmax: 1..128 token rows per launch");
+    Q3_CHECK(Mtok > 0 && Mtok <= SKINNY_MAX_ROWS, 1, "lmhead_argmax: 1..256 token rows per launch");
     Q3_CHECK(K % 8 == 0 && ldx % 8 == 0 && N > 0 && amax_val && amax_idx, 1, "lmhead_argmax: bad argument");
-    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : 128;
+    const int nb = Mtok <= 16 ? 16 : Mtok <= 32 ? 32 : Mtok <= 64 ? 64 : Mtok <= 128 ? 128 : 256;
     LmHeadDev p;
     memset(&p, 0, sizeof(p));
     p.N = N;
@@ -504,7 +505,8 @@ void lmhead_argmax(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N
         case 16: launch_lmhead<16>(tw, tx, p, grid, st); break;
         case 32: launch_lmhead<32>(tw, tx, p, grid, st); break;
         case 64: launch_lmhead<64>(tw, tx, p, grid, st); break;
-        default: launch_lmhead<128>(tw, tx, p, grid, st); break;
+        case 128: launch_lmhead<128>(tw, tx, p, grid, st); break;
+        default: launch_lmhead<256>(tw, tx, p, grid, st); break;
     }
     Q3_CUDA(cudaGetLastError());
     g_launches++;

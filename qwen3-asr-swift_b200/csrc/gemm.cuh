@@ -636,7 +636,7 @@ void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const Gemm
 unsigned long long gemm_launch_count();
 
 // ---- decode-step weight-streaming GEMM (skinny.cuh): Y[Mtok, N] = X[Mtok, K](ldx) W[N, K]^T, Mtok <= 128 per launch ----
-constexpr int SKINNY_MAX_ROWS = 128;
+constexpr int SKINNY_MAX_ROWS = 256;  // token rows of the weight-streaming decode step: the UMMA N operand (<= 256)
 enum SkinnyEpi : int {
     SK_PARTIAL = 0,  // out(fp32)[split][m][n] = acc
     SK_STORE = 1,    // out(bf16)[m][n] = bf16(acc)                       (splits must be 1)

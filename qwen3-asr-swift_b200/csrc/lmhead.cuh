@@ -58,7 +58,7 @@ lmhead_argmax_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(SK_BM, NB);
     constexpr int CH = NB < 32 ? NB : 32;
-    static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "NB");
+    static_assert(NB % 16 == 0 && NB >= 16 && NB <= 256, "NB");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -175,8 +175,7 @@ lmhead_argmax_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-            const int m = threadIdx.x - 128;
-            if (m < NB && m < p.Mtok) {
+            for (int m = threadIdx.x - 128; m < NB && m < p.Mtok; m += 128) {  // 128 epilogue threads, up to 256 tokens
                 float bv = s_val[m];
                 int bi = s_idx[m];
 #pragma unroll

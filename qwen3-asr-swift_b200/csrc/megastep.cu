@@ -70,7 +70,7 @@ bool megastep_supported(const Handle* h, const BatchState* bs) {
     const char* env = getenv("Q3ASR_MEGA");
     if (!(env && atoi(env) != 0)) return false;
     const int gu = gu_bn_for(c, h->num_sms);
-    return bs->dec_rows >= 1 && bs->dec_rows <= SKINNY_MAX_ROWS && c.dec_head_dim == 128 && c.dec_heads == 2 * c.dec_kv_heads &&
+    return bs->dec_rows >= 1 && bs->dec_rows <= 128 /* the persistent kernel's sub-batch tiles */ && c.dec_head_dim == 128 && c.dec_heads == 2 * c.dec_kv_heads &&
            c.dec_hidden % 1024 == 0 && c.dec_hidden <= 2048 && c.dec_inter % 64 == 0 && (gu == 64 || gu == 128) &&
            (2 * c.dec_inter) % gu == 0 && h->num_sms >= 64;
 }

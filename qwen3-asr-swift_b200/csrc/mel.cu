@@ -626,11 +626,11 @@ void mel_tables_create(MelTables* t) {
     Q3_CUDA(cudaMalloc(&t->tw512, sizeof(float2) * 129));
     Q3_CUDA(cudaMalloc(&t->fbw, sizeof(float) * fbw.size()));
     Q3_CUDA(cudaMalloc(&t->fb_start, sizeof(int) * MEL_BINS));
-    Q3_CUDA(cudaMemcpy(t->hann, hann.data(), sizeof(float) * MEL_NFFT, cudaMemcpyHostToDevice));
-    Q3_CUDA(cudaMemcpy(t->tw256, tw256.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
-    Q3_CUDA(cudaMemcpy(t->tw512, tw512.data(), sizeof(float2) * 129, cudaMemcpyHostToDevice));
-    Q3_CUDA(cudaMemcpy(t->fbw, fbw.data(), sizeof(float) * fbw.size(), cudaMemcpyHostToDevice));
-    Q3_CUDA(cudaMemcpy(t->fb_start, start, sizeof(int) * MEL_BINS, cudaMemcpyHostToDevice));
+    Q3_H2D_SYNC(t->hann, hann.data(), sizeof(float) * MEL_NFFT);
+    Q3_H2D_SYNC(t->tw256, tw256.data(), sizeof(float2) * 256);
+    Q3_H2D_SYNC(t->tw512, tw512.data(), sizeof(float2) * 129);
+    Q3_H2D_SYNC(t->fbw, fbw.data(), sizeof(float) * fbw.size());
+    Q3_H2D_SYNC(t->fb_start, start, sizeof(int) * MEL_BINS);
     Q3_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mel_smem_bytes(t->fb_rows)));
 }
 

@@ -1,6 +1,6 @@
 // skinny.cuh — weight-streaming tcgen05 GEMM for the decode step (few token rows, big weight matrix).
 //
-//   Y[m, n] = sum_k X[m, k] W[n, k]        m < Mtok <= NB <= 128 token rows, n < N
+//   Y[m, n] = sum_k X[m, k] W[n, k]        m < Mtok <= NB <= 256 token rows (the widest UMMA N), n < N
 //
 // The decode-step products of FloatTextDecoder.swift:77-79, 107, 128-132 have M = batch (<= 64 per GPU in
 // the reference configs) and are pure weight streaming.  The general kernel (gemm.cuh) would waste half of
@@ -46,7 +46,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     constexpr int TMEM_COLS = sk_tmem_cols(NB);
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(SK_BM, NB);
     constexpr int CH = NB < 32 ? NB : 32;  // TMEM columns per epilogue chunk
-    static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "NB");
+    static_assert(NB % 16 == 0 && NB >= 16 && NB <= 256, "NB");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

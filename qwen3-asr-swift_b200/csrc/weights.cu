@@ -264,7 +264,7 @@ void model_set_tensor(Handle* h, const char* name, const void* data, int dtype, 
         if ((u & 0x7fffffffu) > 0x7f800000u) b[i] = (uint16_t)((u >> 16) | 0x40);
         else b[i] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1)) >> 16);
     }
-    Q3_CUDA(cudaMemcpy(t.d, b.data(), n * 2, cudaMemcpyHostToDevice));
+    Q3_H2D_SYNC(t.d, b.data(), n * 2);
     h->loaded = false;  // derived layouts are stale until q3asr_commit_weights
 }
 

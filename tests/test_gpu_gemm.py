@@ -125,7 +125,7 @@ def test_gemm_argmax(tiny_model):
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 4096, 128), (64, 151936, 1024), (1, 2048, 128), (17, 1280, 192), (33, 384, 64), (100, 2560, 256),
-                                   (128, 1024, 512), (5, 200, 136)])
+                                   (128, 1024, 512), (5, 200, 136), (129, 2048, 128), (200, 2560, 256), (256, 151936, 1024)])
 def test_lmhead_argmax_kernel(tiny_model, M, N, K):
     """The decode-step LM head (csrc/lmhead.cuh): first maximum of bf16(X E^T) per token row, ties to the lowest index."""
     rng = np.random.default_rng(M + N + K)
@@ -173,7 +173,7 @@ def test_conv_implicit_gemm(tiny_model, B, H, W, C, O, box, simt):
 
 # ---- decode-step weight-streaming kernel (csrc/skinny.cuh) ----
 @pytest.mark.parametrize("M,N,K", [(64, 4096, 1024), (64, 1024, 3072), (1, 1024, 2048), (8, 256, 192), (17, 384, 64), (33, 128, 1000),
-                                   (100, 640, 512), (128, 1024, 1024), (5, 200, 136)])
+                                   (100, 640, 512), (128, 1024, 1024), (5, 200, 136), (129, 1024, 512), (200, 640, 1024), (256, 4096, 1024)])
 def test_skinny_partial_and_store(tiny_model, M, N, K):
     rng = np.random.default_rng(M * 11 + N + K)
     A, W = _rand(rng, (M, K)), _rand(rng, (N, K), 0.05)

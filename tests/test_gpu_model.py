@@ -147,11 +147,11 @@ def test_batch_equals_single_and_order(tiny_model):
     assert [r.tolist() for r in rev[::-1]] == [b.tolist() for b in batch]
 
 
-@pytest.mark.parametrize("n_clips", [70, 128, 140, 300])
+@pytest.mark.parametrize("n_clips", [70, 128, 140, 256, 300])
 def test_wide_batches_equal_single(tiny_model, tiny_oracle, n_clips):
-    """Batches wider than 64 take the 128-column variants of the decode GEMMs and the LM head (<= 128 sequences); a request above
-    128 utterances is served as equal sub-batches of at most 128 (csrc/api.cu transcribe_chunked): the ids of every utterance equal
-    those of the utterance alone whatever the size of the request, and a sample equals the oracle."""
+    """Batches wider than 64 take the 128- and 256-column variants of the decode GEMMs and the LM head (<= 256 sequences: the UMMA N
+    operand); a request above 256 utterances is served as equal sub-batches (csrc/api.cu transcribe_chunked): the ids of every
+    utterance equal those of the utterance alone whatever the size of the request, and a sample equals the oracle."""
     rng = np.random.default_rng(n_clips)
     clips = [synth.clip(i, int(rng.integers(1600, 12000))) for i in range(n_clips)]
     batch = tiny_model.transcribe_ids(clips, max_tokens=10, stop_on_eos=False)
