@@ -257,7 +257,7 @@ int q3asr_pool_create(const q3asr_config* cfg, const int* devices, int n_devices
 void q3asr_pool_destroy(q3asr_pool* p);
 /* message of the last failed call on this pool; p == NULL: why the last q3asr_pool_create on the calling thread failed */
 const char* q3asr_pool_last_error(const q3asr_pool* p);
-/* max_batch_per_gpu <= 0 picks the default sub-batch (128 utterances).  The device list of q3asr_pool_create may name a GPU more than
+/* max_batch_per_gpu <= 0 picks the default sub-batch (256 utterances).  The device list of q3asr_pool_create may name a GPU more than
  * once: every entry is a worker with its own handle and stream, and two workers per GPU interleave the latency-bound decode steps of
  * their batches (+24 % aggregate throughput measured). */
 int q3asr_pool_transcribe_ids(q3asr_pool* p, const float* const* pcm, const size_t* n_samples, int batch,

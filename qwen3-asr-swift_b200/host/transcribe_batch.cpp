@@ -98,7 +98,7 @@ int main(int argc, char** argv) {
     std::string inputDir, outputDir, model = "0.6B", modelDir, extensions = "wav,flac,mp3", devicesArg = "0";
     std::optional<std::string> language;
     bool jsonl = false, listOnly = false;
-    int batch = 128, maxTokens = 448, workersPerGpu = 2;
+    int batch = 256, maxTokens = 448, workersPerGpu = 2;
     float windowSeconds = 30.f;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
