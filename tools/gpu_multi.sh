@@ -12,7 +12,7 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/r2d_bench_n$N.json"))
 print("n", d["n_gpus"], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "pipelined", d["e2e_pipelined"] and round(d["e2e_pipelined"]["value"]), "ms", d["ms_per_step"])
-for k in ("e2e_pool","strong_scaling","config2","config4","config5","error"):
+for k in ("e2e_pool","strong_scaling","config2","throughput_mode","config4","config5","error"):
     if k in d: print(k, {kk: vv for kk, vv in d[k].items() if kk != "how"} if isinstance(d[k], dict) else d[k])
 PY
 tail -n 3 gpurun_out/r2d_bench_n$N.err
