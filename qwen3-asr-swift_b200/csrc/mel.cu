@@ -45,19 +45,19 @@ namespace q3 {
 namespace {
 
 constexpr int TPF = 16;                                // lanes per frame pair
-constexpr int MEL_THREADS = 8 * MEL_TILE;               // 16 lanes per frame pair
+constexpr int MEL_THREADS = 8 * MEL_TILE;               // threads that transform one tile together (a group)
 // A CTA is GROUPS independent groups of MEL_THREADS threads: each walks its own tiles with its own sample buffer, scratch and named
 // barrier, and they share the constant tables.  One CTA per SM: 5 groups of 16-frame tiles (20 warps at <= 102 registers, 224 KB
 // of shared memory — both budgets nearly full) where four separate CTAs, each with its own copy of the tables, were the limit.
 constexpr int GROUPS = MEL_TILE == 16 ? 5 : 2;
-constexpr int PAIRS = MEL_THREADS / TPF;               // 16 frame pairs in flight per CTA = the 32 frames of a tile
-static_assert(MEL_TILE == 2 * PAIRS, "a CTA transforms a whole tile in one pass");
-constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 5360
+constexpr int PAIRS = MEL_THREADS / TPF;               // frame pairs in flight per group = the frames of a tile
+static_assert(MEL_TILE == 2 * PAIRS, "a group transforms a whole tile in one pass");
+constexpr int TILE_SAMPLES = (MEL_TILE - 1) * MEL_HOP + MEL_NFFT;  // 2800 (16-frame tiles)
 constexpr int SX_FLOATS = TILE_SAMPLES + 16;
 constexpr int SCR_F4 = 256;                            // float4s of scratch per frame pair: the 16x16 transpose (XOR-swizzled columns,
                                                        // no padding) and then the flat spectrum
 constexpr int PARK_F2 = 384;                          // float2 offset of the parked features inside a pair's scratch block (the spectrum ends at 257)
-constexpr int HANN_PAD = 416;                          // window taps as (h, h) pairs, zero beyond 400
+constexpr int HANN_PAD = 416;                          // window taps, zero beyond 400
 
 struct MelParams {
     const float* hann;
