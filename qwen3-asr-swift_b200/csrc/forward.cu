@@ -583,7 +583,8 @@ void decoder_layers_decode(Handle* h, BatchState* bs) {
         }
         {
             ProfScope ps(h, "dec_gateup", 4.0 * B * H * c.dec_inter, 4.0 * H * c.dec_inter);
-            // M = B <= 128 fits one M tile of the general kernel; 64-column tiles give N/64 CTAs, each streaming its weight rows once
+            // M = B <= 128 fits one M tile of the general kernel (two above, up to 256 rows); 64-column tiles give N/64 CTAs per M tile,
+            // each streaming its weight rows once
             GemmEpiArgs eg;
             eg.epi = EPI_SWIGLU; eg.out = act; eg.ldo = c.dec_inter;
             // narrowest 64-multiple tile that still gives one CTA per SM at most (0.6B: 96 tiles of 64, 1.7B: 96 tiles of 128)

@@ -635,7 +635,7 @@ void gemm(const bf16* A, int lda, int M, int K, const bf16* W, int N, const Gemm
           bool simt = false, int bn = 0);
 unsigned long long gemm_launch_count();
 
-// ---- decode-step weight-streaming GEMM (skinny.cuh): Y[Mtok, N] = X[Mtok, K](ldx) W[N, K]^T, Mtok <= 128 per launch ----
+// ---- decode-step weight-streaming GEMM (skinny.cuh): Y[Mtok, N] = X[Mtok, K](ldx) W[N, K]^T, Mtok <= SKINNY_MAX_ROWS (256) per launch ----
 constexpr int SKINNY_MAX_ROWS = 256;  // token rows of the weight-streaming decode step: the UMMA N operand (<= 256)
 enum SkinnyEpi : int {
     SK_PARTIAL = 0,  // out(fp32)[split][m][n] = acc
@@ -647,7 +647,7 @@ int gemm_skinny_splits(int N, int K, int epi);
 // SK_PARTIAL: out = fp32 [splits][Mtok][N] (split_stride = Mtok * N); SK_STORE: bf16 [Mtok, ldo]
 void gemm_skinny(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, int epi, void* out, int ldo, cudaStream_t st);
 // Decode-step LM head (lmhead.cuh): per 128-row vocabulary tile the (value, index) of the first maximum of bf16(X E^T) for every token
-// row, amax_val / amax_idx [Mtok, lmhead_tiles(N)], to be merged by argmax_reduce.  Mtok <= 128.
+// row, amax_val / amax_idx [Mtok, lmhead_tiles(N)], to be merged by argmax_reduce.  Mtok <= SKINNY_MAX_ROWS.
 int lmhead_tiles(int N);
 void lmhead_argmax(const bf16* X, int ldx, int Mtok, int K, const bf16* W, int N, float* amax_val, int* amax_idx, cudaStream_t st);
 // final reduce of EPI_ARGMAX partials: out[row] = index of the maximum (lowest index on ties)
