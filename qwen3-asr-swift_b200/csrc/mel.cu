@@ -285,13 +285,32 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
             if (prev_on) prev_o[(size_t)m * prev_T] = val;
         }
     };
-    if (tid == 0) {  // clips of the first two tiles; later ones are searched two tiles ahead
+    if (tid == 0) {
         ptx::mbar_init(s_bar, 1);
         ptx::fence_barrier_init();
-        s_next[0] = find_clip(p.clips, p.batch, min(tile_first, p.total_tiles - 1));
-        s_next[1] = find_clip(p.clips, p.batch, min(tile_first + tile_step, p.total_tiles - 1));
-        s_clip[0] = p.clips[s_next[0]];
-        s_clip[1] = p.clips[s_next[1]];
+    }
+    if (warp == 0) {  // clips of the first two tiles (later ones are looked up two tiles ahead): one round of loads for the whole warp
+                      // instead of two binary searches by one thread (13 dependent L2 round trips, ~9 us before the first tile moved)
+        const int ta = min(tile_first, p.total_tiles - 1), tb = min(tile_first + tile_step, p.total_tiles - 1);
+        int ca, cb;
+        if (p.batch <= 32 * 4) {
+            int na = 0, nb = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int first = lane + 32 * k < p.batch ? __ldg(&p.clips[lane + 32 * k].tile0) : 0x7fffffff;
+                na += first <= ta ? 1 : 0;
+                nb += first <= tb ? 1 : 0;
+            }
+            ca = __reduce_add_sync(0xffffffffu, na) - 1;
+            cb = __reduce_add_sync(0xffffffffu, nb) - 1;
+        } else {
+            ca = __shfl_sync(0xffffffffu, lane == 0 ? find_clip(p.clips, p.batch, ta) : 0, 0);
+            cb = __shfl_sync(0xffffffffu, lane == 1 ? find_clip(p.clips, p.batch, tb) : 0, 1);
+        }
+        if (lane == 0) { s_next[0] = ca; s_next[1] = cb; }
+        constexpr int CW = (int)(sizeof(MelClip) / 4);
+        if (lane < 2 * CW)
+            reinterpret_cast<int*>(&s_clip[lane / CW])[lane % CW] = __ldg(reinterpret_cast<const int*>(&p.clips[lane < CW ? ca : cb]) + lane % CW);
     }
     __syncthreads();
     if (tile_first < p.total_tiles) {
