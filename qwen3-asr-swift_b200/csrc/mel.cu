@@ -78,36 +78,49 @@ struct MelParams {
     int* tclip;  // clip of every tile (for the clamp pass)
 };
 
+// Filter weights in shared memory: one row of FBW_STRIDE floats per lane (its eight filters' taps, round after round), read with
+// 128-bit loads: 13 per frame pair instead of 40 scalar ones.  52 = 20 mod 32 puts the eight lanes of a quarter-warp in different
+// bank quads.
+constexpr int FBW_STRIDE = 52;
+constexpr int FBW_FLOATS = 16 * FBW_STRIDE;
 // hann | tw256 | tw512 | filterbank weights | filter starts | per group: samples | scratch | reductions.  The tables are NOT stored as
 // (w, w) pairs: the kernel is bound by shared-memory wavefronts (ncu: LSU data pipe 80 % busy), not by issue slots, so a pair is
 // formed with a register move after an 8-byte load
 __host__ __device__ constexpr int mel_smem_bytes(int fb_rows) {
-    return (HANN_PAD + 2 * 256 + 2 * 130 + fb_rows * 16 + 128 + GROUPS * (SX_FLOATS + 4 * PAIRS * SCR_F4 + 64)) * 4;  // the last 64 words: reductions [32], next clips' indices [2], clips [2]
+    return (HANN_PAD + 2 * 256 + 2 * 130 + FBW_FLOATS + 128 + GROUPS * (SX_FLOATS + 4 * PAIRS * SCR_F4 + 64)) * 4;  // the last 64 words: reductions [32], next clips' indices [2], clips [2]
 }
 
 // Widths (taps) of the eight filterbank rounds: a property of the slaney filterbank at 16 kHz / 512 points / 128 bins, checked
 // against the computed table in mel_tables_create.  Compile-time constants let the tap loops unroll completely (the loop control
 // was 15 % of the kernel's instructions).
-template <int J> struct FbRound;
-template <> struct FbRound<0> { static constexpr int W = 2, OFF = 0; };
-template <> struct FbRound<1> { static constexpr int W = 2, OFF = 2; };
-template <> struct FbRound<2> { static constexpr int W = 2, OFF = 4; };
-template <> struct FbRound<3> { static constexpr int W = 3, OFF = 6; };
-template <> struct FbRound<4> { static constexpr int W = 4, OFF = 9; };
-template <> struct FbRound<5> { static constexpr int W = 6, OFF = 13; };
-template <> struct FbRound<6> { static constexpr int W = 9, OFF = 19; };
-template <> struct FbRound<7> { static constexpr int W = 12, OFF = 28; };
+template <int J> struct FbRound;  // W taps; POFF: offset of the round in a lane's weight row (rounds padded to multiples of four taps)
+template <> struct FbRound<0> { static constexpr int W = 2, POFF = 0; };
+template <> struct FbRound<1> { static constexpr int W = 2, POFF = 4; };
+template <> struct FbRound<2> { static constexpr int W = 2, POFF = 8; };
+template <> struct FbRound<3> { static constexpr int W = 3, POFF = 12; };
+template <> struct FbRound<4> { static constexpr int W = 4, POFF = 16; };
+template <> struct FbRound<5> { static constexpr int W = 6, POFF = 20; };
+template <> struct FbRound<6> { static constexpr int W = 9, POFF = 28; };
+template <> struct FbRound<7> { static constexpr int W = 12, POFF = 40; };
+constexpr int FB_POFF[MEL_ROUNDS] = {0, 4, 8, 12, 16, 20, 28, 40};
 constexpr int FB_ROWS = 40;
 constexpr int FB_WIDTHS[MEL_ROUNDS] = {2, 2, 2, 3, 4, 6, 9, 12};
 
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c);
 template <int J>
 __device__ __forceinline__ float2 fb_round(const float2* __restrict__ scr, const float* __restrict__ s_fbw, const int* __restrict__ s_fbstart, int t) {
+    constexpr int W = FbRound<J>::W, Q = (W + 3) / 4;
     const float2* pp = scr + s_fbstart[t + 16 * J];
-    const float* wp = s_fbw + FbRound<J>::OFF * 16 + t;
+    const float4* wq = reinterpret_cast<const float4*>(s_fbw + t * FBW_STRIDE + FbRound<J>::POFF);
+    float wv[4 * Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const float4 v = wq[q];
+        wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+    }
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < FbRound<J>::W; w++) acc = fma2(pp[w], make_float2(wp[w * 16], wp[w * 16]), acc);
+    for (int w = 0; w < W; w++) acc = fma2(pp[w], make_float2(wv[w], wv[w]), acc);
     return acc;
 }
 
@@ -238,12 +251,13 @@ __device__ __forceinline__ void stage_tile(float* dst, const MelClip& c, const f
 static_assert((SX_FLOATS * 4) % 16 == 0 && (MEL_HOP * 4) % 16 == 0 && (MEL_NFFT / 2 * 4) % 16 == 0, "bulk copies need 16-byte aligned tiles");
 
 __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelParams p) {
+    ptx::grid_dep_launch();  // the clamp pass may be scheduled while this grid drains (it waits for the grid's completion itself)
     extern __shared__ float4 smem4[];
     float* s_hann = reinterpret_cast<float*>(smem4);                      // [416], zero beyond 400
     float2* s_tw256 = reinterpret_cast<float2*>(s_hann + HANN_PAD);       // [256] (wr, wi)
     float2* s_tw512 = s_tw256 + 256;                                      // [130]
-    float* s_fbw = reinterpret_cast<float*>(s_tw512 + 130);               // [fb_rows * 16]
-    int* s_fbstart = reinterpret_cast<int*>(s_fbw + p.fb_rows * 16);      // [128]
+    float* s_fbw = reinterpret_cast<float*>(s_tw512 + 130);               // [16 lanes][FBW_STRIDE]
+    int* s_fbstart = reinterpret_cast<int*>(s_fbw + FBW_FLOATS);          // [128]
     const int group = threadIdx.x / MEL_THREADS;                          // this thread's group and its private buffers
     float* s_x = reinterpret_cast<float*>(s_fbstart + 128) + (size_t)group * (SX_FLOATS + 4 * PAIRS * SCR_F4 + 64);
     float4* s_scr = reinterpret_cast<float4*>(s_x + SX_FLOATS);           // [PAIRS][SCR_F4]
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(GROUPS * MEL_THREADS, 1) mel_kernel(const MelP
     for (int i = threadIdx.x; i < HANN_PAD; i += blockDim.x) s_hann[i] = i < MEL_NFFT ? __ldg(&p.hann[i]) : 0.f;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tw256[i] = __ldg(&p.tw256[i]);
     for (int i = threadIdx.x; i < 129; i += blockDim.x) s_tw512[i] = __ldg(&p.tw512[i]);
-    for (int i = threadIdx.x; i < p.fb_rows * 16; i += blockDim.x) s_fbw[i] = __ldg(&p.fbw[i]);
+    for (int i = threadIdx.x; i < FBW_FLOATS; i += blockDim.x) s_fbw[i] = __ldg(&p.fbw[i]);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_fbstart[i] = __ldg(&p.fb_start[i]);
 
     float4* scr4 = s_scr + pr * SCR_F4;                    // complex pairs: (re_A, re_B, im_A, im_B)
@@ -509,6 +523,7 @@ __global__ void __launch_bounds__(256) mel_clamp_kernel(float* out, const MelCli
     __shared__ int s_tile[CLAMP_TILES], s_clip[CLAMP_TILES];
     __shared__ float s_lo[CLAMP_TILES];
     __shared__ int s_n;
+    ptx::grid_dep_wait();  // launched with programmatic stream serialization behind mel_kernel: its maxima, minima and features are complete
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const int tile = tile_lo + blockIdx.x * CLAMP_TILES + threadIdx.x;  // CLAMP_TILES deciders per CTA: about one tile to clamp per CTA
@@ -632,12 +647,12 @@ void mel_tables_create(MelTables* t) {
     for (int j = 0; j < MEL_ROUNDS; j++)  // the kernel's tap loops are unrolled for exactly these widths
         Q3_CHECK(t->fb_round_off[j + 1] - t->fb_round_off[j] == FB_WIDTHS[j] && t->fb_rows == FB_ROWS, 2,
                  "mel filterbank round widths differ from the kernel's compile-time table");
-    std::vector<float> fbw((size_t)t->fb_rows * 16, 0.0f);
+    std::vector<float> fbw((size_t)FBW_FLOATS, 0.0f);  // [lane i][round j: FB_POFF[j] + w]
     for (int j = 0; j < MEL_ROUNDS; j++) {
         const int mw = t->fb_round_off[j + 1] - t->fb_round_off[j];
         for (int i = 0; i < 16; i++) {
             const int m = 16 * j + i;
-            for (int w = 0; w < mw; w++) fbw[(size_t)(t->fb_round_off[j] + w) * 16 + i] = fb[m * MEL_NFREQ + start[m] + w];
+            for (int w = 0; w < mw; w++) fbw[(size_t)i * FBW_STRIDE + FB_POFF[j] + w] = fb[m * MEL_NFREQ + start[m] + w];
         }
     }
     Q3_CUDA(cudaMalloc(&t->hann, sizeof(float) * MEL_NFFT));
@@ -695,8 +710,19 @@ void mel_launch_range(const MelTables& t, const float* d_pcm, float* d_out, cons
     const int n_tiles = tile_hi - tile_lo;
     const int grid = std::min((n_tiles + GROUPS - 1) / GROUPS, num_sms);  // one CTA of GROUPS groups per SM
     mel_kernel<<<grid, GROUPS * MEL_THREADS, mel_smem_bytes(t.fb_rows), st>>>(p);
-    mel_clamp_kernel<<<(n_tiles + CLAMP_TILES - 1) / CLAMP_TILES, 256, 0, st>>>(d_out, d_clips, tile_lo, tile_hi, d_gmax, d_tmin, p.tclip);
     Q3_CUDA(cudaGetLastError());
+    {   // the clamp pass as a programmatic dependent: its launch latency hides behind the main kernel's tail
+        const bool was = pdl_enabled();
+        pdl_enabled() = true;
+        try {
+            launch_kernel(mel_clamp_kernel, dim3((n_tiles + CLAMP_TILES - 1) / CLAMP_TILES), dim3(256), 0, st, d_out, d_clips, tile_lo, tile_hi,
+                          (const int*)d_gmax, (const float*)d_tmin, (const int*)p.tclip);
+        } catch (...) {
+            pdl_enabled() = was;
+            throw;
+        }
+        pdl_enabled() = was;
+    }
 }
 
 }  // namespace q3
